@@ -1,0 +1,324 @@
+"""ctypes binding of the CPU ORACLE (oracle/_build/liblcto.so).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / `--impl reference` legs -- never from the product package `locityper_b200`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liblcto.so")
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in ("lcto_rng.c", "lcto_specfun.c", "lcto_model.c", "lcto_solve.c", "lcto.h")]
+    stale = force or not os.path.exists(_SO) or any(
+        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
+    return _SO
+
+
+class Rng(C.Structure):
+    _fields_ = [("s", C.c_uint64 * 4)]
+
+    @classmethod
+    def from_seed(cls, seed: int) -> "Rng":
+        r = cls()
+        lib().lcto_rng_seed_from_u64(C.byref(r), C.c_uint64(seed))
+        return r
+
+    @classmethod
+    def from_state(cls, s: Sequence[int]) -> "Rng":
+        r = cls()
+        for i in range(4):
+            r.s[i] = int(s[i])
+        return r
+
+    def state(self):
+        return [int(self.s[i]) for i in range(4)]
+
+
+class LocusC(C.Structure):
+    _fields_ = [
+        ("n_haps", C.c_uint32), ("n_reads", C.c_uint32), ("ploidy", C.c_uint32), ("is_paired", C.c_uint32),
+        ("n_genotypes", C.c_uint64),
+        ("gt_tuples", C.c_void_p), ("priors", C.c_void_p), ("unmapped_prob", C.c_void_p),
+        ("pa_off", C.c_void_p), ("pa_contig", C.c_void_p), ("pa_ln_prob", C.c_void_p),
+        ("pa_mid1", C.c_void_p), ("pa_mid2", C.c_void_p),
+        ("hap_len", C.c_void_p), ("hap_n_windows", C.c_void_p), ("hap_reg_start", C.c_void_p),
+        ("window", C.c_uint32), ("left_padding", C.c_uint32),
+        ("hap_pos_off", C.c_void_p), ("pos_weight", C.c_void_p), ("pos_gc", C.c_void_p),
+        ("depth_k", C.c_uint32), ("tweak", C.c_uint32),
+        ("depth_table", C.c_void_p),
+        ("prob_diff", C.c_double), ("lik_skew", C.c_double), ("min_weight", C.c_double),
+        ("filt_diff", C.c_double), ("prob_thresh", C.c_double),
+        ("dont_skip", C.c_uint32), ("out_bams", C.c_uint32),
+    ]
+
+
+class StageC(C.Structure):
+    _fields_ = [
+        ("kind", C.c_uint32), ("attempts", C.c_uint32), ("in_size", C.c_uint64),
+        ("best_start", C.c_uint32), ("_pad", C.c_uint32),
+        ("sample_size", C.c_uint64), ("plato_size", C.c_uint64), ("anneal_steps", C.c_uint64),
+        ("init_prob", C.c_double),
+    ]
+
+
+class ResultC(C.Structure):
+    _fields_ = [
+        ("n_out", C.c_uint64), ("gt_ix", C.c_uint64 * 50), ("lik_mean", C.c_double * 50),
+        ("lik_var", C.c_double * 50), ("attempts", C.c_uint16 * 50), ("ln_prob", C.c_double * 50),
+        ("quality", C.c_double), ("total_reads", C.c_uint32), ("unexpl_reads", C.c_uint32),
+        ("warn_no_probable", C.c_uint32), ("warn_few_reads", C.c_uint32),
+        ("n_filtered", C.c_uint64), ("n_stage_in", C.c_uint64 * 8),
+        ("t_prefilter_s", C.c_double), ("t_stages_s", C.c_double),
+    ]
+
+
+class AttemptOut(C.Structure):
+    _fields_ = [("lik", C.c_double), ("aln_lik", C.c_double), ("depth_lik", C.c_double),
+                ("iterations", C.c_uint64), ("moves", C.c_uint64)]
+
+
+class InstanceC(C.Structure):
+    _fields_ = [
+        ("n_reads", C.c_uint32), ("ploidy", C.c_uint32), ("total_windows", C.c_uint32),
+        ("n_alns", C.c_uint32), ("n_nontrivial", C.c_uint32),
+        ("haps", C.c_uint32 * 8), ("wshift", C.c_uint32 * 9),
+        ("read_ixs", C.POINTER(C.c_uint32)), ("nontrivial", C.POINTER(C.c_uint32)),
+        ("aln_ln_prob", C.POINTER(C.c_double)), ("aln_contig_ix", C.POINTER(C.c_uint8)),
+        ("aln_pa", C.POINTER(C.c_uint32)), ("aln_w", C.POINTER(C.c_uint32)),
+        ("win_weight", C.POINTER(C.c_double)), ("win_gc", C.POINTER(C.c_uint8)),
+        ("win_trivial", C.POINTER(C.c_uint8)),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.lcto_sizeof_locus.restype = C.c_size_t
+        L.lcto_sizeof_stage.restype = C.c_size_t
+        assert L.lcto_sizeof_locus() == C.sizeof(LocusC), (L.lcto_sizeof_locus(), C.sizeof(LocusC))
+        assert L.lcto_sizeof_stage() == C.sizeof(StageC)
+        L.lcto_rng_next_u64.restype = C.c_uint64
+        L.lcto_rng_next_u32.restype = C.c_uint32
+        L.lcto_rng_f64.restype = C.c_double
+        L.lcto_rng_range_u32_incl.restype = C.c_uint32
+        L.lcto_rng_range_u32_incl.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.lcto_rng_range_i32_incl.restype = C.c_int32
+        L.lcto_rng_range_i32_incl.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.lcto_rng_range_usize.restype = C.c_size_t
+        L.lcto_rng_range_usize.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t]
+        L.lcto_rng_range_u16.restype = C.c_uint16
+        L.lcto_rng_range_u16.argtypes = [C.c_void_p, C.c_uint16, C.c_uint16]
+        L.lcto_rng_sample_indices.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.lcto_rng_shuffle_usize.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        for f in ("lcto_ln_gamma",):
+            getattr(L, f).restype = C.c_double
+            getattr(L, f).argtypes = [C.c_double]
+        L.lcto_beta_reg.restype = C.c_double
+        L.lcto_beta_reg.argtypes = [C.c_double] * 3
+        L.lcto_students_t_cdf.restype = C.c_double
+        L.lcto_students_t_cdf.argtypes = [C.c_double] * 2
+        L.lcto_ln_add.restype = C.c_double
+        L.lcto_ln_add.argtypes = [C.c_double] * 2
+        L.lcto_build_depth_table.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
+                                             C.c_uint32, C.c_void_p]
+        L.lcto_genotype_tuple.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.lcto_best_aln_matrix.argtypes = [C.c_void_p, C.c_void_p]
+        L.lcto_prefilter_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.lcto_truncate_ixs.restype = C.c_size_t
+        L.lcto_truncate_ixs.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_double, C.c_size_t, C.c_size_t]
+        L.lcto_instance_new.restype = C.POINTER(InstanceC)
+        L.lcto_instance_new.argtypes = [C.c_void_p, C.c_uint64]
+        L.lcto_instance_free.argtypes = [C.c_void_p]
+        L.lcto_apply_tweak.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lcto_solve_attempt.argtypes = [C.c_void_p] * 7
+        L.lcto_solve_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                       C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.lcto_discard_improbable.restype = C.c_size_t
+        L.lcto_discard_improbable.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_double, C.c_size_t, C.c_size_t]
+        L.lcto_compare_two_likelihoods.restype = C.c_double
+        L.lcto_compare_two_likelihoods.argtypes = [C.c_double, C.c_double, C.c_uint16,
+                                                   C.c_double, C.c_double, C.c_uint16]
+        L.lcto_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lcto_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+def build_depth_table(nb_n, nb_p, is_paired, alt_cn, k_cols: int) -> np.ndarray:
+    nb_n = np.ascontiguousarray(nb_n, dtype=np.float64)
+    nb_p = np.ascontiguousarray(nb_p, dtype=np.float64)
+    alt = np.ascontiguousarray(alt_cn, dtype=np.float64)
+    out = np.empty((101, int(k_cols)), dtype=np.float64)
+    lib().lcto_build_depth_table(_ptr(nb_n), _ptr(nb_p), int(bool(is_paired)), _ptr(alt), len(alt),
+                                 int(k_cols), _ptr(out))
+    return out
+
+
+class OracleLocus:
+    """Keeps the numpy buffers alive behind an `lcto_locus` struct."""
+
+    def __init__(self, loc):
+        self.loc = loc
+        self._keep = []
+
+        def arr(a, dt):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=dt)
+            self._keep.append(a)
+            return a.ctypes.data
+
+        s = LocusC()
+        s.n_haps, s.n_reads, s.ploidy, s.is_paired = loc.n_haps, loc.n_reads, loc.ploidy, int(loc.is_paired)
+        s.n_genotypes = loc.n_genotypes
+        s.gt_tuples = arr(loc.gt_tuples, np.uint32)
+        s.priors = arr(loc.priors, np.float64)
+        s.unmapped_prob = arr(loc.unmapped_prob, np.float64)
+        s.pa_off = arr(loc.pa_off, np.uint64)
+        s.pa_contig = arr(loc.pa_contig, np.uint32)
+        s.pa_ln_prob = arr(loc.pa_ln_prob, np.float64)
+        s.pa_mid1 = arr(loc.pa_mid1, np.uint32)
+        s.pa_mid2 = arr(loc.pa_mid2, np.uint32)
+        s.hap_len = arr(loc.hap_len, np.uint32)
+        s.hap_n_windows = arr(loc.hap_n_windows, np.uint32)
+        s.hap_reg_start = arr(loc.hap_reg_start, np.uint32)
+        s.window, s.left_padding = loc.window, loc.left_padding
+        s.hap_pos_off = arr(loc.hap_pos_off, np.uint64)
+        s.pos_weight = arr(loc.pos_weight, np.float64)
+        s.pos_gc = arr(loc.pos_gc, np.uint8)
+        assert loc.depth_table is not None, "attach_depth_table first"
+        s.depth_k, s.tweak = loc.depth_k, loc.tweak
+        s.depth_table = arr(loc.depth_table, np.float64)
+        s.prob_diff, s.lik_skew, s.min_weight = loc.prob_diff, loc.lik_skew, loc.min_weight
+        s.filt_diff, s.prob_thresh = loc.filt_diff, loc.prob_thresh
+        s.dont_skip, s.out_bams = int(loc.dont_skip), loc.out_bams
+        self.c = s
+
+    @property
+    def ref(self):
+        return C.byref(self.c)
+
+
+@dataclass
+class Stage:
+    kind: str = "greedy"          # "greedy" | "anneal"
+    attempts: int = 20            # Stage::parse default (src/solvers/solve.rs:173-174)
+    in_size: int = 1000
+    best_start: bool = True       # Greedy defaults (src/solvers/stoch.rs:45-53)
+    sample_size: int = 10
+    plato_size: Optional[int] = None   # greedy 100, anneal 10000
+    anneal_steps: int = 20000     # SimAnneal defaults (src/solvers/stoch.rs:161-169)
+    init_prob: float = 0.5
+
+    def to_c(self) -> StageC:
+        s = StageC()
+        s.kind = 0 if self.kind == "greedy" else 1
+        s.attempts, s.in_size = self.attempts, self.in_size
+        s.best_start, s.sample_size = int(self.best_start), self.sample_size
+        s.plato_size = self.plato_size if self.plato_size is not None else (100 if s.kind == 0 else 10000)
+        s.anneal_steps, s.init_prob = self.anneal_steps, self.init_prob
+        return s
+
+
+DEFAULT_SCHEME = [Stage("greedy", attempts=1, in_size=5000), Stage("anneal", attempts=20, in_size=20)]
+
+
+def best_aln_matrix(ol: OracleLocus) -> np.ndarray:
+    M = np.empty((ol.loc.n_haps, ol.loc.n_reads), dtype=np.float64)
+    lib().lcto_best_aln_matrix(ol.ref, _ptr(M))
+    return M
+
+
+def prefilter_scores(ol: OracleLocus, ixs: Optional[np.ndarray] = None, M: Optional[np.ndarray] = None):
+    G = ol.loc.n_genotypes
+    if ixs is None:
+        ixs = np.arange(G, dtype=np.uint64)
+    ixs = np.ascontiguousarray(ixs, dtype=np.uint64)
+    if M is None:
+        M = best_aln_matrix(ol)
+    scores = np.empty(G, dtype=np.float64)
+    lib().lcto_prefilter_scores(ol.ref, _ptr(M), _ptr(ixs), len(ixs), _ptr(scores))
+    return scores
+
+
+def truncate_ixs(ixs: np.ndarray, scores: np.ndarray, filt_diff: float, min_size: int, threads: int):
+    ixs = np.array(ixs, dtype=np.uint64)
+    scores = np.ascontiguousarray(scores, dtype=np.float64)
+    m = lib().lcto_truncate_ixs(_ptr(ixs), len(ixs), _ptr(scores), filt_diff, min_size, threads)
+    return ixs[:m].copy()
+
+
+def solve_stage(ol: OracleLocus, stage: Stage, worker_ixs, worker_off, worker_rng: np.ndarray,
+                os_threads: int = 1, want_counts: bool = False, counts_cap: int = 0):
+    """worker_rng: u64[n_workers, 4] (updated in place)."""
+    worker_ixs = np.ascontiguousarray(worker_ixs, dtype=np.uint64)
+    worker_off = np.ascontiguousarray(worker_off, dtype=np.uint64)
+    assert worker_rng.dtype == np.uint64 and worker_rng.flags.c_contiguous
+    n_workers = len(worker_off) - 1
+    n = int(worker_off[-1])
+    st = stage.to_c()
+    lik_mean = np.empty(n); lik_var = np.empty(n)
+    liks = np.empty((n, stage.attempts))
+    n_alns = np.zeros(n, dtype=np.uint64); iters = np.zeros(n, dtype=np.uint64)
+    counts_off = counts = None
+    if want_counts:
+        counts_off = np.zeros(n + 1, dtype=np.uint64)
+        counts = np.zeros(max(1, counts_cap), dtype=np.uint16)
+    rc = lib().lcto_solve_stage(ol.ref, C.byref(st), _ptr(worker_ixs), _ptr(worker_off), n_workers,
+                                _ptr(worker_rng), os_threads, _ptr(lik_mean), _ptr(lik_var), _ptr(liks),
+                                _ptr(counts_off), _ptr(counts), int(counts_cap), _ptr(n_alns), _ptr(iters))
+    if rc != 0:
+        raise RuntimeError(f"lcto_solve_stage failed: {rc}")
+    return dict(lik_mean=lik_mean, lik_var=lik_var, liks=liks, n_alns=n_alns, iters=iters,
+                counts_off=counts_off, counts=counts)
+
+
+def solve(ol: OracleLocus, scheme: Sequence[Stage], threads: int, rng: Rng, os_threads: int = 1,
+          want_scores: bool = False):
+    G = ol.loc.n_genotypes
+    st = (StageC * len(scheme))(*[s.to_c() for s in scheme])
+    res = ResultC()
+    scores = np.empty(G) if want_scores else None
+    filt = np.zeros(G, dtype=np.uint64) if want_scores else None
+    rc = lib().lcto_solve(ol.ref, st, len(scheme), threads, C.byref(rng), os_threads, C.byref(res),
+                          _ptr(scores), _ptr(filt))
+    if rc != 0:
+        raise RuntimeError(f"lcto_solve failed: {rc}")
+    n = int(res.n_out)
+    out = dict(
+        gt_ix=np.array(res.gt_ix[:n], dtype=np.uint64), lik_mean=np.array(res.lik_mean[:n]),
+        lik_var=np.array(res.lik_var[:n]), attempts=np.array(res.attempts[:n]),
+        ln_prob=np.array(res.ln_prob[:n]), quality=res.quality, total_reads=res.total_reads,
+        unexpl_reads=res.unexpl_reads, warn_no_probable=bool(res.warn_no_probable),
+        warn_few_reads=bool(res.warn_few_reads), n_filtered=int(res.n_filtered),
+        n_stage_in=[int(x) for x in res.n_stage_in], t_prefilter_s=res.t_prefilter_s,
+        t_stages_s=res.t_stages_s,
+    )
+    if want_scores:
+        out["scores"] = scores
+        out["filtered_ixs"] = filt[:out["n_filtered"]].copy()
+    return out
