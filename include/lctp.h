@@ -1,0 +1,190 @@
+/*
+ * lctp.h -- C ABI of the B200-native genotype-evaluation hot path of locityper.
+ *
+ * This is the drop-in boundary.  The reference (tprodanov/locityper v1.7.2,
+ * Rust) has no C ABI for this path; the precedent for the shape is its WFA2 binding
+ * (/root/reference/build.rs:1-64, src/seq/wfa.rs:10-16).  A Rust maintainer binds these entry
+ * points with bindgen from `build.rs` and swaps two bodies in src/solvers/solve.rs:
+ *   (1) the `run_filter(...)` call at src/solvers/solve.rs:943-944        -> lctp_prefilter
+ *   (2) the per-stage dispatch + collect in MainWorker::run :1047-1081 /
+ *       solve_single_thread :814-843                                       -> lctp_solve_stage
+ * or the whole of `solve::solve` (:926-981) minus file output                 -> lctp_solve.
+ * See INTEGRATION.md for the Rust-side stubs.
+ *
+ * Conventions: plain pointers and sizes, caller owns every host buffer, the library owns device
+ * memory behind opaque handles, no host pointer is retained after a call returns.  Return value
+ * 0 = ok; LCTP_E_INVALID (-1) invalid argument; LCTP_E_CUDA (-2) CUDA failure (including "no
+ * device": there is NO CPU fallback on this path); LCTP_E_CAPACITY (-3) capacity / unsupported
+ * parameter (mirrors the asserts at src/model/assgn.rs:58, src/model/windows.rs:734).
+ * The message of the last error on this thread is returned by lctp_last_error().
+ */
+#ifndef LCTP_H
+#define LCTP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCTP_OK 0
+#define LCTP_E_INVALID (-1)
+#define LCTP_E_CUDA (-2)
+#define LCTP_E_CAPACITY (-3)
+
+#define LCTP_NONE_U32 0xFFFFFFFFu
+#define LCTP_GC_BINS 101     /* src/bg/depth.rs:42 */
+#define LCTP_MAX_PLOIDY 8
+#define LCTP_MAX_STAGES 8
+#define LCTP_MAX_OUT 50      /* MAX_GENOTYPES, src/solvers/solve.rs:486 */
+
+typedef struct lctp_ctx lctp_ctx;
+typedef struct lctp_locus_h lctp_locus_h;
+
+typedef struct lctp_device_cfg {
+    int32_t device;            /* CUDA device ordinal */
+    uint32_t flags;            /* reserved, 0 */
+    void *stream;              /* cudaStream_t to launch on; NULL = the library creates its own */
+    uint32_t max_resident_workers; /* 0 = auto (SM count x resident warps) -- scratch sizing only */
+    uint32_t _pad;
+} lctp_device_cfg;
+
+/* Flat per-locus input = solve::Data (src/solvers/solve.rs:254-273) with everything the device never
+ * touches removed; SURVEY.md Appendix C. */
+typedef struct lctp_locus {
+    uint32_t n_haps;               /* H: contigs of the locus */
+    uint32_t n_reads;              /* R: reads (read pairs for paired-end), all_alns.reads().len() */
+    uint32_t ploidy;               /* p */
+    uint32_t is_paired;
+    uint64_t n_genotypes;          /* G */
+    const uint32_t *gt_tuples;     /* [G*p] Genotype::ids(); NULL = generate_genotypes without priors
+                                      (src/command/genotype.rs:1123-1126, src/ext/vec.rs:298-339) */
+    const double   *priors;        /* [G]; NULL = 0.0 */
+    const double   *unmapped_prob; /* [R] GrouppedAlignments::unmapped_prob, src/model/locs.rs:600-602 */
+    /* GrouppedAlignments::aln_pairs of every read, concatenated (read-major): per read sorted by
+     * contig asc then ln_prob desc, <= 10 per (read, contig); src/model/locs.rs:669-735,793-798 */
+    const uint64_t *pa_off;        /* [R+1] */
+    const uint32_t *pa_contig;     /* [NPA] PairAlignment::contig_id */
+    const double   *pa_ln_prob;    /* [NPA] PairAlignment::ln_prob */
+    const uint32_t *pa_mid1;       /* [NPA] middle1(); LCTP_NONE_U32 = mate unmapped */
+    const uint32_t *pa_mid2;       /* [NPA] middle2() */
+    /* ContigInfo geometry, src/model/windows.rs:343-359,380-384 */
+    const uint32_t *hap_len;       /* [H] contig_len */
+    const uint32_t *hap_n_windows; /* [H] */
+    const uint32_t *hap_reg_start; /* [H] window_getter.start */
+    uint32_t window;               /* window size */
+    uint32_t left_padding;
+    const uint64_t *hap_pos_off;   /* [H+1] offsets into pos_weight / pos_gc (len_h = contig_len - neighb + 1) */
+    const double   *pos_weight;    /* ContigInfo::neighb_info(start).1 for every mov_info index (windows.rs:439-445) */
+    const uint8_t  *pos_gc;        /* NeighbInfo::gc_content */
+    uint32_t depth_k;              /* columns of depth_table; must be >= 2R+1 */
+    uint32_t tweak;                /* Params::tweak after set_tweak_size, src/model/mod.rs:179-197 */
+    const double   *depth_table;   /* [101][depth_k]: DistrCache ln_pmf per GC bin (src/model/distr_cache.rs:61-75) */
+    double prob_diff, lik_skew, min_weight, filt_diff, prob_thresh;   /* model::Params, src/model/mod.rs:64-106 */
+    uint32_t dont_skip;
+    uint32_t out_bams;
+} lctp_locus;
+
+/* One stage of the solving Scheme (src/solvers/solve.rs:138-202) with the solver's own parameters
+ * (Greedy: src/solvers/stoch.rs:36-53; SimAnneal: :151-169). */
+typedef struct lctp_stage {
+    uint32_t kind;         /* 0 = "greedy", 1 = "anneal" */
+    uint32_t attempts;     /* a */
+    uint64_t in_size;      /* i */
+    uint32_t best_start;   /* greedy x0: 1 = best, 0 = random */
+    uint32_t _pad;
+    uint64_t sample_size;  /* greedy s (device supports 1..=11: always Floyd sampling) */
+    uint64_t plato_size;   /* greedy p / anneal p */
+    uint64_t anneal_steps; /* anneal n */
+    double   init_prob;    /* anneal P */
+} lctp_stage;
+
+/* Genotyping (src/solvers/solve.rs:568-590) without strings. */
+typedef struct lctp_result {
+    uint64_t n_out;
+    uint64_t gt_ix[LCTP_MAX_OUT];
+    double   lik_mean[LCTP_MAX_OUT];
+    double   lik_var[LCTP_MAX_OUT];
+    uint16_t attempts[LCTP_MAX_OUT];
+    double   ln_prob[LCTP_MAX_OUT];
+    double   quality;
+    uint32_t total_reads;
+    uint32_t unexpl_reads;
+    uint32_t warn_no_probable;
+    uint32_t warn_few_reads;
+    uint64_t n_filtered;
+    uint64_t n_stage_in[LCTP_MAX_STAGES];
+    double   t_prefilter_s, t_stages_s;      /* host wall clock, diagnostics */
+} lctp_result;
+
+/* ---- library / context -------------------------------------------------------------------- */
+const char *lctp_version(void);
+const char *lctp_last_error(void);
+size_t lctp_sizeof_locus(void);
+size_t lctp_sizeof_stage(void);
+size_t lctp_sizeof_result(void);
+int  lctp_init(const lctp_device_cfg *cfg, lctp_ctx **out);
+void lctp_destroy(lctp_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py `gpu_launches`). */
+uint64_t lctp_launch_count(const lctp_ctx *ctx);
+int  lctp_sync(lctp_ctx *ctx);
+
+/* ---- locus upload (H2D once per locus; builds M = best_aln_matrix on the device, a1) ------- */
+int  lctp_locus_upload(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h **out);
+void lctp_locus_free(lctp_locus_h *h);
+/* a1: AllAlignments::best_aln_matrix (src/model/locs.rs:1203-1212), [H][R] row-major by haplotype. */
+int  lctp_best_aln_matrix(lctp_locus_h *h, double *m_out);
+
+/* ---- prefilter (a2 + a3) ------------------------------------------------------------------ */
+/* Scores of genotypes [g_begin, g_end) (src/solvers/solve.rs:105-119) computed on the device into the
+ * handle's score buffer; copied to scores_out[g_end - g_begin] when not NULL. */
+int  lctp_prefilter_scores(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, double *scores_out);
+/* run_filter (src/solvers/solve.rs:87-122): ixs holds n genotype ids in/out; *out_n survivors, sorted. */
+int  lctp_prefilter(lctp_locus_h *h, uint64_t *ixs, size_t n, size_t min_size, size_t threads,
+                    size_t *out_n, double *scores_out /* nullable, [G] */);
+/* truncate_ixs (src/solvers/solve.rs:52-84) on host arrays (used by the multi-GPU merge). */
+size_t lctp_truncate_ixs(uint64_t *ixs, size_t n, const double *scores, double filt_diff,
+                         size_t min_size, size_t threads);
+
+/* ---- one solver stage over explicit logical workers (a5-a14) ------------------------------- */
+/* worker w solves genotypes worker_ixs[worker_off[w] .. worker_off[w+1]) back to back on its own
+ * xoshiro256++ stream worker_rng[4*w .. 4*w+4) (in/out), exactly like Worker::run
+ * (src/solvers/solve.rs:1104-1145).  Outputs are indexed by position j in worker_ixs. */
+int  lctp_solve_stage(lctp_locus_h *h, const lctp_stage *st,
+                      const uint64_t *worker_ixs, const uint64_t *worker_off, size_t n_workers,
+                      uint64_t *worker_rng,
+                      double *lik_mean, double *lik_var,
+                      double *liks /* nullable [n*attempts] */,
+                      uint64_t *counts_off /* nullable [n+1] */, uint16_t *counts /* nullable */,
+                      uint64_t counts_cap,
+                      uint64_t *n_alns_out /* nullable [n] */, uint64_t *iters_out /* nullable [n] */);
+
+/* ---- host-side mirror of the scheduler (a14-a16) ------------------------------------------- */
+void lctp_rng_seed_from_u64(uint64_t state[4], uint64_t seed);   /* src/ext/rand.rs:12 */
+void lctp_rng_jump(uint64_t state[4]);                            /* src/solvers/solve.rs:1017 */
+void lctp_rng_long_jump(uint64_t state[4]);                       /* src/command/genotype.rs:1345 */
+/* MainWorker::run :1049-1063: shuffle ixs with the locus stream and cut into <= threads chunks.
+ * worker_off has threads+1 entries; returns the number of workers that received work. */
+size_t lctp_plan_stage(uint64_t rng[4], uint64_t *ixs, size_t n, size_t threads, uint64_t *worker_off);
+/* discard_improbable_genotypes :425-480; per-genotype arrays are indexed by genotype id. */
+size_t lctp_discard_improbable(uint64_t *ixs, size_t n, const double *lik_mean, const double *lik_var,
+                               const uint16_t *attempts, double prob_thresh, size_t out_size, size_t threads);
+double lctp_compare_two_likelihoods(double m1, double v1, uint16_t a1, double m2, double v2, uint16_t a2);
+/* DistrCache::new (src/model/distr_cache.rs:61-75): out[101][k_cols] from the preproc NB(n, p) per GC bin. */
+void lctp_build_depth_table(const double *nb_n, const double *nb_p, int is_paired,
+                            const double *alt_cn, size_t n_alt, uint32_t k_cols, double *out);
+
+/* solve::solve (src/solvers/solve.rs:926-981) without file output: prefilter -> stages -> result.
+ * `rng` is the locus stream (in/out); `threads` is the reference's -@ (number of logical workers). */
+int  lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_t threads,
+                uint64_t rng[4], lctp_result *res);
+/* Genotyping::to_json (src/solvers/solve.rs:732-773), pretty-printed with indent 4 like
+ * src/command/genotype.rs:1256.  hap_names[H]; returns bytes needed (excluding NUL). */
+size_t lctp_result_json(const lctp_result *res, const lctp_locus *loc, const char *const *hap_names,
+                        char *buf, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,146 @@
+// common.cuh -- shared definitions of the lctp library (sm_100a only; no CPU fallback).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+#include <vector>
+
+#include "../../include/lctp.h"
+
+namespace lctp {
+
+void set_error(const char *fmt, ...);
+
+#define LCTP_CUDA_CHECK(expr)                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            ::lctp::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,    \
+                              __LINE__, cudaGetErrorString(_e));                               \
+            return LCTP_E_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+// Monotone device buffer (freed with the owning handle).
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return LCTP_OK;
+        LCTP_CUDA_CHECK(cudaMalloc((void **)&p, count * sizeof(T)));
+        return LCTP_OK;
+    }
+    int ensure(size_t count) { return count <= n ? LCTP_OK : alloc(count); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+// Pinned host staging buffer.
+template <typename T>
+struct PinBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int ensure(size_t count) {
+        if (count <= n) return LCTP_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+        LCTP_CUDA_CHECK(cudaMallocHost((void **)&p, count * sizeof(T)));
+        n = count;
+        return LCTP_OK;
+    }
+    ~PinBuf() {
+        if (p) cudaFreeHost(p);
+    }
+    PinBuf() = default;
+    PinBuf(const PinBuf &) = delete;
+    PinBuf &operator=(const PinBuf &) = delete;
+};
+
+}  // namespace lctp
+
+struct lctp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    uint32_t max_resident_workers = 0;
+    uint64_t launches = 0;
+    // stage scratch, grown on demand and reused across loci / stages
+    lctp::DevBuf<unsigned char> scratch;
+    lctp::DevBuf<uint64_t> d_worker_ixs, d_worker_off, d_rng;
+    lctp::DevBuf<uint32_t> d_tuples;
+    lctp::DevBuf<double> d_lik_mean, d_lik_var, d_liks;
+    lctp::DevBuf<uint64_t> d_nalns, d_iters;
+    lctp::DevBuf<uint16_t> d_counts;
+    lctp::DevBuf<int> d_flags;
+    lctp::PinBuf<unsigned char> pin;
+};
+
+// Device-side view of one uploaded locus (all pointers are device pointers).
+struct LocusDev {
+    uint32_t H, R, p, Hpad;
+    uint64_t G;
+    uint32_t window, left_padding, tweak, depth_k;
+    double prob_diff, depth_contrib, aln_contrib, rel_contrib, min_weight;
+    const double *Mt;            // [R][Hpad] best-alignment matrix, read-major (a1)
+    const double *unmapped;      // [R]
+    const uint32_t *cm_off;      // [H*R+1] contig-major CSR of pair alignments
+    const double *cm_lnprob;     // [NPA]
+    const uint2 *cm_mid;         // [NPA] (middle1, middle2)
+    const uint32_t *hap_len, *hap_n_windows, *hap_reg_start;   // [H]
+    const uint64_t *hap_pos_off; // [H+1]
+    const double *pos_weight;
+    const uint8_t *pos_gc;
+    const double *depth_table;   // [101][depth_k]
+    const uint32_t *gt_tuples;   // [G*p] or nullptr
+    const double *priors;        // [G] or nullptr
+};
+
+struct lctp_locus_h {
+    lctp_ctx *ctx = nullptr;
+    lctp_locus host;             // scalar copy (pointers NOT retained: nulled after upload)
+    LocusDev dev;
+    uint64_t npa = 0;
+    uint32_t max_hap_alns = 0;   // max over haplotypes of #pair alignments on that haplotype
+    uint32_t max_n_windows = 0;
+    std::vector<uint32_t> hap_alns;      // [H] #pair alignments per haplotype
+    std::vector<uint32_t> gt_tuples_host; // explicit genotype list (host copy), empty = full enumeration
+    std::vector<double> priors_host;      // host copy of priors, empty = 0.0
+    std::vector<double> unmapped_host;    // [R] host copy (count_unexplained_reads)
+    std::vector<uint32_t> hap_n_windows; // [H] host copy
+    lctp::DevBuf<double> Mt, unmapped, cm_lnprob, pos_weight, depth_table, priors, scores;
+    lctp::DevBuf<uint32_t> cm_off, hap_len, hap_nw, hap_rs, gt_tuples;
+    lctp::DevBuf<uint2> cm_mid;
+    lctp::DevBuf<uint64_t> hap_pos_off;
+    lctp::DevBuf<uint8_t> pos_gc;
+    bool scores_valid = false;
+};
+
+namespace lctp {
+// upload.cu
+int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h);
+// prefilter.cu
+int launch_prefilter(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, double *d_scores);
+// solver.cu
+int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_ixs,
+                 const uint64_t *worker_off, size_t n_workers, uint64_t *worker_rng,
+                 double *lik_mean, double *lik_var, double *liks, uint64_t *counts_off,
+                 uint16_t *counts, uint64_t counts_cap, uint64_t *n_alns_out, uint64_t *iters_out);
+// host_solve.cpp
+void genotype_tuple(uint32_t H, uint32_t p, const uint32_t *gt_tuples, uint64_t g, uint32_t *out);
+}  // namespace lctp

@@ -1,0 +1,672 @@
+// host_solve.cu -- host side of the C ABI: context / locus handles, and the host-resident part of the
+// reference's scheduler, restated in C++ above the device kernels:
+//   src/solvers/solve.rs:52-84     truncate_ixs            :319-336 compare_two_likelihoods
+//   src/solvers/solve.rs:425-480   discard_improbable_genotypes   :482-535 produce_result
+//   src/solvers/solve.rs:926-981   solve                   :996-1093 MainWorker::{new,run}
+//   src/solvers/solve.rs:732-773   Genotyping::to_json
+//   src/model/distr_cache.rs:61-75 DistrCache::new  (+ src/math/distr/{bayes,nbinom}.rs, src/math/mod.rs)
+//   src/ext/vec.rs:298-339         genotype enumeration    src/ext/rand.rs RNG seeding
+// Third-party arithmetic restated from the published algorithms (not vendored by the reference):
+// rand 0.10 shuffle / uniform ints, rand_xoshiro 0.8 jump polynomials, statrs 0.19 ln_gamma /
+// beta_reg / StudentsT::cdf.  None of this touches oracle/: the oracle is an independent C restatement.
+#include "common.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+namespace lctp {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+// ---------------------------------------------------------------- xoshiro256++ on the host -----
+
+struct HostRng {
+    uint64_t s[4];
+    static inline uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    uint64_t next_u64() {
+        const uint64_t r = rotl(s[0] + s[3], 23) + s[0];
+        const uint64_t t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t;
+        s[3] = rotl(s[3], 45);
+        return r;
+    }
+    uint32_t next_u32() { return (uint32_t)(next_u64() >> 32); }
+    void jump_poly(const uint64_t poly[4]) {
+        uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int i = 0; i < 4; i++)
+            for (int b = 0; b < 64; b++) {
+                if (poly[i] & (1ull << b)) { a0 ^= s[0]; a1 ^= s[1]; a2 ^= s[2]; a3 ^= s[3]; }
+                next_u64();
+            }
+        s[0] = a0; s[1] = a1; s[2] = a2; s[3] = a3;
+    }
+    // rand UniformInt<u32>::sample_single_inclusive(0, range - 1)
+    uint32_t below(uint32_t range) {
+        if (range == 0) return next_u32();
+        const uint64_t m = (uint64_t)next_u32() * range;
+        uint32_t res = (uint32_t)(m >> 32);
+        const uint32_t lo = (uint32_t)m;
+        if (lo > 0u - range) {
+            const uint32_t nh = (uint32_t)(((uint64_t)next_u32() * range) >> 32);
+            res += (uint32_t)(lo + nh < lo);
+        }
+        return res;
+    }
+    uint64_t below64(uint64_t range) {
+        if (range == 0) return next_u64();
+        const unsigned __int128 m = (unsigned __int128)next_u64() * range;
+        uint64_t res = (uint64_t)(m >> 64);
+        const uint64_t lo = (uint64_t)m;
+        if (lo > 0ull - range) {
+            const uint64_t nh = (uint64_t)(((unsigned __int128)next_u64() * range) >> 64);
+            res += (uint64_t)(lo + nh < lo);
+        }
+        return res;
+    }
+};
+
+static const uint64_t kJump[4] = {0x180ec6d33cfd0abaull, 0xd5a61266f0c9392cull, 0xa9582618e03fc9aaull, 0x39abdc4529b1661cull};
+static const uint64_t kLongJump[4] = {0x76e15d3efefdcbbfull, 0xc5004e441c522fb3ull, 0x77710069854ee241ull, 0x39109bb02acbe635ull};
+
+// SliceRandom::shuffle (rand >= 0.9): forward Fisher-Yates whose indices come from IncreasingUniform,
+// i.e. one bounded u32 draw is split into several indices by div/mod.
+static void shuffle_u64(HostRng &rng, uint64_t *v, size_t len) {
+    if (len <= 1) return;
+    if (len >= 0xFFFFFFFFull) {
+        for (size_t i = 0; i < len; i++) std::swap(v[i], v[(size_t)rng.below64(i + 1)]);
+        return;
+    }
+    uint32_t n = 0, chunk = 0;
+    uint8_t remaining = 1;
+    for (size_t i = 0; i < len; i++) {
+        const uint32_t next_n = n + 1;
+        uint8_t next_remaining;
+        if (remaining >= 1) next_remaining = remaining - 1;
+        else {
+            uint32_t product = next_n, current = next_n + 1;
+            for (;;) {
+                const uint64_t pr = (uint64_t)product * current;
+                if (pr > 0xFFFFFFFFull) break;
+                product = (uint32_t)pr;
+                current++;
+            }
+            chunk = rng.below(product);
+            next_remaining = (uint8_t)(current - next_n - 1);
+        }
+        size_t index;
+        if (next_remaining == 0) index = chunk;
+        else { index = chunk % next_n; chunk /= next_n; }
+        remaining = next_remaining;
+        n = next_n;
+        std::swap(v[i], v[index]);
+    }
+}
+
+// ---------------------------------------------------------------- genotype enumeration ---------
+
+static uint64_t choose(uint64_t n, uint64_t k) {
+    if (k > n) return 0;
+    const uint64_t r = std::min(k, n - k);
+    uint64_t acc = 1;
+    for (uint64_t v = 1; v <= r; v++) acc = acc * (n - v + 1) / v;
+    return acc;
+}
+
+void genotype_tuple(uint32_t H, uint32_t p, const uint32_t *gt_tuples, uint64_t g, uint32_t *out) {
+    if (gt_tuples) { std::copy(gt_tuples + g * p, gt_tuples + (g + 1) * p, out); return; }
+    uint32_t lo = 0;
+    for (uint32_t d = 0; d < p; d++) {
+        const uint32_t rem = p - d - 1;
+        for (uint32_t v = lo; v < H; v++) {
+            const uint64_t cnt = rem == 0 ? 1 : choose((uint64_t)(H - v) + rem - 1, rem);
+            if (g < cnt) { out[d] = v; lo = v; break; }
+            g -= cnt;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- special functions ------------
+
+static const double kGammaR = 10.900511;
+static const double kGammaDk[11] = {
+    2.48574089138753565546e-5, 1.05142378581721974210, -3.45687097222016235469, 4.51227709466894823700,
+    -2.98285225323576655721, 1.05639711577126713077, -1.95428773191645869583e-1, 1.70970543404441224307e-2,
+    -5.71926117404305781283e-4, 4.63399473359905636708e-6, -2.71994908488607703910e-9};
+static const double kLnPi = 1.1447298858494001741434273513530587116472948129153;
+static const double kLn2SqrtEOverPi = 0.6207822376352452223455184457816472122518527279025978;
+
+// statrs::function::gamma::ln_gamma (Lanczos g = 10.900511, n = 11)
+static double ln_gamma(double x) {
+    double s = kGammaDk[0];
+    if (x < 0.5) {
+        for (int i = 1; i < 11; i++) s += kGammaDk[i] / ((double)i - x);
+        return kLnPi - std::log(std::sin(M_PI * x)) - std::log(s) - kLn2SqrtEOverPi -
+               (0.5 - x) * std::log((0.5 - x + kGammaR) / M_E);
+    }
+    for (int i = 1; i < 11; i++) s += kGammaDk[i] / (x + (double)i - 1.0);
+    return std::log(s) + kLn2SqrtEOverPi + (x - 0.5) * std::log((x - 0.5 + kGammaR) / M_E);
+}
+
+// statrs::function::beta::beta_reg (continued fraction)
+static double beta_reg(double a, double b, double x) {
+    if (!(a > 0.0) || !(b > 0.0) || !(x >= 0.0 && x <= 1.0)) return std::numeric_limits<double>::quiet_NaN();
+    double bt = 0.0;
+    if (!(std::fabs(x) < 1.1102230246251565e-15 || std::fabs(x - 1.0) <= 4.0 * std::numeric_limits<double>::epsilon()))
+        bt = std::exp(ln_gamma(a + b) - ln_gamma(a) - ln_gamma(b) + a * std::log(x) + b * std::log(1.0 - x));
+    const bool symm = x >= (a + 1.0) / (a + b + 2.0);
+    const double eps = 1.1102230246251565e-16;
+    const double fpmin = std::numeric_limits<double>::min() / eps;
+    if (symm) { std::swap(a, b); x = 1.0 - x; }
+    const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0, d = 1.0 - qab * x / qap;
+    if (std::fabs(d) < fpmin) d = fpmin;
+    d = 1.0 / d;
+    double hh = d;
+    for (int mi = 1; mi < 141; mi++) {
+        const double m = mi, m2 = m * 2.0;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d; if (std::fabs(d) < fpmin) d = fpmin;
+        c = 1.0 + aa / c; if (std::fabs(c) < fpmin) c = fpmin;
+        d = 1.0 / d;
+        hh = hh * d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d; if (std::fabs(d) < fpmin) d = fpmin;
+        c = 1.0 + aa / c; if (std::fabs(c) < fpmin) c = fpmin;
+        d = 1.0 / d;
+        const double del = d * c;
+        hh *= del;
+        if (std::fabs(del - 1.0) <= eps) break;
+    }
+    return symm ? 1.0 - bt * hh / a : bt * hh / a;
+}
+
+static double students_t_cdf(double x, double freedom) {
+    if (std::isinf(freedom)) return 0.5 * std::erfc(-x / M_SQRT2);
+    const double hh = freedom / (freedom + x * x);
+    const double ib = 0.5 * beta_reg(freedom / 2.0, 0.5, hh);
+    return x <= 0.0 ? ib : 1.0 - ib;
+}
+
+// Ln::add / Ln::sum / Ln::sum_init (src/math/mod.rs:28-94)
+static double ln_add(double a, double b) {
+    const double ninf = -std::numeric_limits<double>::infinity();
+    if (a >= b) return b == ninf ? a : b + std::log1p(std::exp(a - b));
+    return a == ninf ? b : a + std::log1p(std::exp(b - a));
+}
+static double ln_sum(const double *v, size_t n) {
+    if (n == 0) return -std::numeric_limits<double>::infinity();
+    if (n == 1) return v[0];
+    double m = -std::numeric_limits<double>::infinity();
+    for (size_t i = 0; i < n; i++) m = std::fmax(m, v[i]);
+    if (std::isinf(m)) return m;
+    double s = 0.0;
+    for (size_t i = 0; i < n; i++) s += std::exp(v[i] - m);
+    return m + std::log(s);
+}
+static double ln_sum_init(const double *v, size_t n, double init) {
+    if (n == 0) return init;
+    if (n == 1) return ln_add(init, v[0]);
+    double m = init;
+    for (size_t i = 0; i < n; i++) m = std::fmax(m, v[i]);
+    if (std::isinf(m)) return m;
+    double s = std::exp(init - m);
+    for (size_t i = 0; i < n; i++) s += std::exp(v[i] - m);
+    return m + std::log(s);
+}
+
+struct NBinom {   // src/math/distr/nbinom.rs:24-42,127-132
+    double n, p, lnq, lnpmf_const;
+    NBinom() = default;
+    NBinom(double n_, double p_) : n(n_), p(p_), lnq(std::log1p(-p_)), lnpmf_const(n_ * std::log(p_) - ln_gamma(n_)) {}
+    double ln_pmf(uint32_t k) const {
+        const double x = k;
+        return lnpmf_const + ln_gamma(n + x) - ln_gamma(x + 1.0) + x * lnq;
+    }
+};
+
+// ---------------------------------------------------------------- sorting helpers --------------
+
+static inline int64_t total_key(double v) {
+    int64_t b;
+    std::memcpy(&b, &v, 8);
+    return b ^ (int64_t)(((uint64_t)(b >> 63)) >> 1);
+}
+
+// Descending by key with f64::total_cmp; equal keys keep their current order (the reference uses
+// sort_unstable_by, whose tie order is unspecified -- see DESIGN.md "unpinned behaviour").
+static void sort_desc_stable(uint64_t *ixs, size_t n, const double *key) {
+    std::stable_sort(ixs, ixs + n, [key](uint64_t a, uint64_t b) { return total_key(key[a]) > total_key(key[b]); });
+}
+
+// compare_two_likelihoods (src/solvers/solve.rs:319-336) with the t-tests of src/math/mod.rs:180-220
+static double compare_two(double m1, double v1, uint16_t a1, double m2, double v2, uint16_t a2) {
+    const double simple_norm = m1 - ln_add(m1, m2);
+    if (std::isnormal(v1) && std::isnormal(v2)) {
+        double t_pval;
+        if (a1 == a2) {
+            const double n = a1, var_sum = v1 + v2;
+            const double t_stat = (m1 - m2) * std::sqrt(n / var_sum);
+            const double freedom = (n - 1.0) * var_sum * var_sum / (v1 * v1 + v2 * v2);
+            t_pval = students_t_cdf(t_stat, freedom);
+        } else {
+            const double n1 = a1, n2 = a2, nv1 = v1 / n1, nv2 = v2 / n2, sv = nv1 + nv2;
+            const double t_stat = (m1 - m2) / std::sqrt(sv);
+            const double freedom = sv * sv / (nv1 * nv1 / (n1 - 1.0) + nv2 * nv2 / (n2 - 1.0));
+            t_pval = students_t_cdf(t_stat, freedom);
+        }
+        return std::fmax(simple_norm, std::log(t_pval));
+    }
+    return simple_norm;
+}
+
+}  // namespace lctp
+
+using namespace lctp;
+
+// =============================================================================== C ABI =========
+
+extern "C" {
+
+const char *lctp_version(void) { return "lctp 0.1.0 (sm_100a; restates locityper v1.7.2 genotype evaluation)"; }
+const char *lctp_last_error(void) { return g_last_error.c_str(); }
+size_t lctp_sizeof_locus(void) { return sizeof(lctp_locus); }
+size_t lctp_sizeof_stage(void) { return sizeof(lctp_stage); }
+size_t lctp_sizeof_result(void) { return sizeof(lctp_result); }
+
+int lctp_init(const lctp_device_cfg *cfg, lctp_ctx **out) {
+    if (!out) { set_error("lctp_init: out is NULL"); return LCTP_E_INVALID; }
+    *out = nullptr;
+    int dev = cfg ? cfg->device : 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("lctp_init: no CUDA device available (%s); this path has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return LCTP_E_CUDA;
+    }
+    if (dev < 0 || dev >= count) { set_error("lctp_init: device %d out of range (0..%d)", dev, count - 1); return LCTP_E_INVALID; }
+    LCTP_CUDA_CHECK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    LCTP_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        set_error("lctp_init: device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+        return LCTP_E_CUDA;
+    }
+    lctp_ctx *ctx = new lctp_ctx();
+    ctx->device = dev;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->max_resident_workers = cfg ? cfg->max_resident_workers : 0;
+    if (cfg && cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
+    else {
+        cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (se != cudaSuccess) { set_error("lctp_init: cudaStreamCreate failed: %s", cudaGetErrorString(se)); delete ctx; return LCTP_E_CUDA; }
+        ctx->own_stream = true;
+    }
+    *out = ctx;
+    return LCTP_OK;
+}
+
+void lctp_destroy(lctp_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+uint64_t lctp_launch_count(const lctp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int lctp_sync(lctp_ctx *ctx) {
+    if (!ctx) { set_error("lctp_sync: NULL context"); return LCTP_E_INVALID; }
+    LCTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return LCTP_OK;
+}
+
+int lctp_locus_upload(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h **out) {
+    if (!ctx || !in || !out) { set_error("lctp_locus_upload: NULL argument"); return LCTP_E_INVALID; }
+    *out = nullptr;
+    LCTP_CUDA_CHECK(cudaSetDevice(ctx->device));
+    lctp_locus_h *h = new lctp_locus_h();
+    int rc = upload_locus(ctx, in, h);
+    if (rc != LCTP_OK) { delete h; return rc; }
+    *out = h;
+    return LCTP_OK;
+}
+
+void lctp_locus_free(lctp_locus_h *h) {
+    if (!h) return;
+    if (h->ctx) { cudaSetDevice(h->ctx->device); cudaStreamSynchronize(h->ctx->stream); }
+    delete h;
+}
+
+int lctp_best_aln_matrix(lctp_locus_h *h, double *m_out) {
+    if (!h || !m_out) { set_error("lctp_best_aln_matrix: NULL argument"); return LCTP_E_INVALID; }
+    const uint32_t H = h->dev.H, R = h->dev.R, Hpad = h->dev.Hpad;
+    std::vector<double> mt((size_t)R * Hpad);
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(mt.data(), h->Mt.p, mt.size() * 8, cudaMemcpyDeviceToHost, h->ctx->stream));
+    LCTP_CUDA_CHECK(cudaStreamSynchronize(h->ctx->stream));
+    for (uint32_t k = 0; k < H; k++)
+        for (uint32_t r = 0; r < R; r++) m_out[(size_t)k * R + r] = mt[(size_t)r * Hpad + k];
+    return LCTP_OK;
+}
+
+int lctp_prefilter_scores(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, double *scores_out) {
+    if (!h) { set_error("lctp_prefilter_scores: NULL handle"); return LCTP_E_INVALID; }
+    if (g_begin > g_end || g_end > h->dev.G) { set_error("lctp_prefilter_scores: bad range"); return LCTP_E_INVALID; }
+    LCTP_CUDA_CHECK(cudaSetDevice(h->ctx->device));
+    int rc = launch_prefilter(h, g_begin, g_end, h->scores.p);
+    if (rc) return rc;
+    if (scores_out && g_end > g_begin)
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(scores_out, h->scores.p + g_begin, (g_end - g_begin) * 8,
+                                        cudaMemcpyDeviceToHost, h->ctx->stream));
+    LCTP_CUDA_CHECK(cudaStreamSynchronize(h->ctx->stream));
+    return LCTP_OK;
+}
+
+size_t lctp_truncate_ixs(uint64_t *ixs, size_t n, const double *scores, double filt_diff, size_t min_size,
+                         size_t threads) {
+    if (n == 0) return 0;
+    sort_desc_stable(ixs, n, scores);
+    const double best = scores[ixs[0]], worst = scores[ixs[n - 1]];
+    double thresh = best - filt_diff;
+    if (min_size >= n || worst >= thresh) return n;
+    auto part = [&](double th) {
+        return (size_t)(std::partition_point(ixs, ixs + n, [&](uint64_t i) { return scores[i] >= th; }) - ixs);
+    };
+    size_t m = part(thresh);
+    if (m < min_size) { thresh = scores[ixs[min_size - 1]]; m = part(thresh); }
+    m = std::min(std::max(m, threads), n);
+    return m;
+}
+
+int lctp_prefilter(lctp_locus_h *h, uint64_t *ixs, size_t n, size_t min_size, size_t threads, size_t *out_n,
+                   double *scores_out) {
+    if (!h || !ixs || !out_n || n == 0) { set_error("lctp_prefilter: NULL/empty argument"); return LCTP_E_INVALID; }
+    const uint64_t G = h->dev.G;
+    std::vector<double> scores(G, -std::numeric_limits<double>::infinity());
+    // The reference always filters the complete list (predictions.ixs = 0..G, solve.rs:939-944); an
+    // arbitrary subset is scored over its covering range.
+    uint64_t lo = G, hi = 0;
+    for (size_t q = 0; q < n; q++) {
+        if (ixs[q] >= G) { set_error("lctp_prefilter: genotype id out of range"); return LCTP_E_INVALID; }
+        lo = std::min(lo, ixs[q]); hi = std::max(hi, ixs[q] + 1);
+    }
+    std::vector<double> part(hi - lo);
+    int rc = lctp_prefilter_scores(h, lo, hi, part.data());
+    if (rc) return rc;
+    for (size_t q = 0; q < n; q++) scores[ixs[q]] = part[ixs[q] - lo];
+    *out_n = lctp_truncate_ixs(ixs, n, scores.data(), h->host.filt_diff, min_size, threads);
+    if (scores_out) std::copy(scores.begin(), scores.end(), scores_out);
+    return LCTP_OK;
+}
+
+int lctp_solve_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_ixs, const uint64_t *worker_off,
+                     size_t n_workers, uint64_t *worker_rng, double *lik_mean, double *lik_var, double *liks,
+                     uint64_t *counts_off, uint16_t *counts, uint64_t counts_cap, uint64_t *n_alns_out,
+                     uint64_t *iters_out) {
+    if (!h) { set_error("lctp_solve_stage: NULL handle"); return LCTP_E_INVALID; }
+    LCTP_CUDA_CHECK(cudaSetDevice(h->ctx->device));
+    return launch_stage(h, st, worker_ixs, worker_off, n_workers, worker_rng, lik_mean, lik_var, liks, counts_off,
+                        counts, counts_cap, n_alns_out, iters_out);
+}
+
+void lctp_rng_seed_from_u64(uint64_t state[4], uint64_t seed) {
+    uint64_t x = seed;   // SplitMix64 fill (rand_xoshiro seed_from_u64)
+    for (int i = 0; i < 4; i++) {
+        uint64_t z = (x += 0x9e3779b97f4a7c15ull);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        state[i] = z ^ (z >> 31);
+    }
+}
+void lctp_rng_jump(uint64_t state[4]) {
+    HostRng r; std::memcpy(r.s, state, 32); r.jump_poly(kJump); std::memcpy(state, r.s, 32);
+}
+void lctp_rng_long_jump(uint64_t state[4]) {
+    HostRng r; std::memcpy(r.s, state, 32); r.jump_poly(kLongJump); std::memcpy(state, r.s, 32);
+}
+
+size_t lctp_plan_stage(uint64_t rng[4], uint64_t *ixs, size_t n, size_t threads, uint64_t *worker_off) {
+    HostRng r; std::memcpy(r.s, rng, 32);
+    shuffle_u64(r, ixs, n);                       // solve.rs:1051
+    std::memcpy(rng, r.s, 32);
+    size_t start = 0, nw = 0;
+    worker_off[0] = 0;
+    for (size_t i = 0; i < threads; i++) {        // solve.rs:1052-1062
+        if (start == n) break;
+        const size_t rem_workers = threads - i;
+        start += (n - start + rem_workers - 1) / rem_workers;   // fast_ceil_div
+        worker_off[++nw] = start;
+    }
+    return nw;
+}
+
+double lctp_compare_two_likelihoods(double m1, double v1, uint16_t a1, double m2, double v2, uint16_t a2) {
+    return compare_two(m1, v1, a1, m2, v2, a2);
+}
+
+size_t lctp_discard_improbable(uint64_t *ixs, size_t n, const double *lik_mean, const double *lik_var,
+                               const uint16_t *attempts, double prob_thresh, size_t out_size, size_t threads) {
+    out_size = std::max(out_size, threads);
+    if (prob_thresh == -std::numeric_limits<double>::infinity() || out_size >= n) return n;
+    sort_desc_stable(ixs, n, lik_mean);
+    const uint64_t best = ixs[0];
+    size_t m = out_size;
+    if (out_size <= 500) {                       // SOPHISTICATED_COUNT
+        uint32_t dropped = 0;
+        for (size_t q = out_size; q < n; q++) {
+            const uint64_t ix = ixs[q];
+            const double ln_pval = compare_two(lik_mean[ix], lik_var[ix], attempts[ix], lik_mean[best], lik_var[best], attempts[best]);
+            if (ln_pval >= prob_thresh) ixs[m++] = ix;
+            else if (++dropped >= 5) break;      // STOP_COUNT
+        }
+    }
+    return m;
+}
+
+void lctp_build_depth_table(const double *nb_n, const double *nb_p, int is_paired, const double *alt_cn,
+                            size_t n_alt, uint32_t k_cols, double *out) {
+    const double mul_coef = is_paired ? 2.0 : 1.0;           // distr_cache.rs:66
+    if (n_alt > 16) n_alt = 16;
+    for (int gc = 0; gc < LCTP_GC_BINS; gc++) {
+        const NBinom cn1(nb_n[gc] * mul_coef, nb_p[gc]);     // NBinom::mul, nbinom.rs:68-70
+        NBinom alts[16];
+        for (size_t a = 0; a < n_alt; a++) alts[a] = NBinom(cn1.n * alt_cn[a], cn1.p);
+        for (uint32_t k = 0; k < k_cols; k++) {
+            const double null_prob = cn1.ln_pmf(k);          // BayesCalc::ln_pmf, bayes.rs:26-35
+            double probs[16];
+            for (size_t a = 0; a < n_alt; a++) probs[a] = alts[a].ln_pmf(k);
+            out[(size_t)gc * k_cols + k] = null_prob - ln_sum_init(probs, n_alt, null_prob);
+        }
+    }
+}
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_t threads, uint64_t rng[4],
+               lctp_result *res) {
+    if (!h || !stages || !rng || !res || n_stages == 0 || n_stages > LCTP_MAX_STAGES) {
+        set_error("lctp_solve: invalid argument");
+        return LCTP_E_INVALID;
+    }
+    const uint64_t G = h->dev.G;
+    std::memset(res, 0, sizeof(*res));
+    threads = std::max<size_t>(1, std::min<size_t>(threads, G));     // genotype.rs:1247
+    std::vector<uint64_t> ixs(G);
+    std::iota(ixs.begin(), ixs.end(), 0);
+    size_t n = G;
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    std::vector<double> lik_mean(G, nan), lik_var(G, nan);
+    std::vector<uint16_t> attempts(G, 0);
+
+    const double t0 = now_s();
+    if (h->host.dont_skip || stages[0].in_size < G) {                // solve.rs:941-945
+        int rc = lctp_prefilter(h, ixs.data(), n, stages[0].in_size, threads, &n, nullptr);
+        if (rc) return rc;
+    }
+    res->n_filtered = n;
+    const double t1 = now_s();
+    res->t_prefilter_s = t1 - t0;
+
+    std::vector<uint64_t> wrng;
+    if (threads > 1) {                                               // MainWorker::new, solve.rs:1007-1018
+        wrng.resize(threads * 4);
+        HostRng r; std::memcpy(r.s, rng, 32);
+        for (size_t w = 0; w < threads; w++) { std::memcpy(&wrng[4 * w], r.s, 32); r.jump_poly(kJump); }
+        std::memcpy(rng, r.s, 32);
+    }
+    std::vector<uint64_t> off(threads + 1);
+    std::vector<double> lm, lv;
+    for (size_t s = 0; s < n_stages; s++) {
+        const lctp_stage &st = stages[s];
+        const bool has_next = s + 1 < n_stages;
+        const size_t out_size = has_next ? stages[s + 1].in_size : 0;
+        if (!(h->host.dont_skip || !has_next || out_size < n)) continue;   // solve.rs:1041-1045
+        res->n_stage_in[s] = n;
+        lm.resize(n); lv.resize(n);
+        int rc;
+        if (threads == 1) {                                          // solve_single_thread, solve.rs:814-843
+            off[0] = 0; off[1] = n;
+            rc = lctp_solve_stage(h, &st, ixs.data(), off.data(), 1, rng, lm.data(), lv.data(), nullptr, nullptr,
+                                  nullptr, 0, nullptr, nullptr);
+        } else {
+            const size_t nw = lctp_plan_stage(rng, ixs.data(), n, threads, off.data());
+            rc = lctp_solve_stage(h, &st, ixs.data(), off.data(), nw, wrng.data(), lm.data(), lv.data(), nullptr,
+                                  nullptr, nullptr, 0, nullptr, nullptr);
+        }
+        if (rc) return rc;
+        for (size_t q = 0; q < n; q++) { lik_mean[ixs[q]] = lm[q]; lik_var[ixs[q]] = lv[q]; attempts[ixs[q]] = (uint16_t)st.attempts; }
+        if (has_next)
+            n = lctp_discard_improbable(ixs.data(), n, lik_mean.data(), lik_var.data(), attempts.data(),
+                                        h->host.prob_thresh, out_size, threads);
+    }
+    res->t_stages_s = now_s() - t1;
+
+    // produce_result, solve.rs:482-535
+    const double THRESH = -11.512925464970229;
+    const size_t min_output = std::max<size_t>(4, h->host.out_bams);
+    const double thresh_prob = std::fmin(THRESH, h->host.prob_thresh);
+    sort_desc_stable(ixs.data(), n, lik_mean.data());
+    size_t m = std::min<size_t>(n, LCTP_MAX_OUT);
+    double ln_probs[LCTP_MAX_OUT];
+    std::fill(ln_probs, ln_probs + LCTP_MAX_OUT, 0.0);
+    for (size_t i = 0; i < m; i++) {
+        const uint64_t u = ixs[i];
+        const size_t m_loop = m;
+        for (size_t j = i + 1; j < m_loop; j++) {
+            const uint64_t v = ixs[j];
+            const double prob_j = compare_two(lik_mean[v], lik_var[v], attempts[v], lik_mean[u], lik_var[u], attempts[u]);
+            if (i == 0 && j >= min_output && prob_j < thresh_prob) { m = j; break; }
+            ln_probs[i] += std::log1p(-std::exp(prob_j));
+            ln_probs[j] += prob_j;
+        }
+        res->gt_ix[i] = u; res->lik_mean[i] = lik_mean[u]; res->lik_var[i] = lik_var[u]; res->attempts[i] = attempts[u];
+    }
+    const double norm = ln_sum(ln_probs, m);
+    for (size_t k = 0; k < m; k++) { ln_probs[k] -= norm; res->ln_prob[k] = ln_probs[k]; }
+    const double others = m >= 1 ? ln_sum(ln_probs + 1, m - 1) : -std::numeric_limits<double>::infinity();
+    res->quality = std::fmin(-10.0 * (others * 0.4342944819032518277), 1e9);   // Phred::from_ln_prob
+    res->n_out = m;
+    res->total_reads = h->dev.R;
+    // check_first_prob (solve.rs:637-645), check_num_of_reads (:649-678)
+    const double lp0 = res->ln_prob[0];
+    res->warn_no_probable = (std::isnan(lp0) || lp0 < -2.0 * 2.302585092994045684) ? 1 : 0;
+    const uint32_t p = h->dev.p, nr = h->dev.R;
+    if (nr < p) res->warn_few_reads = 1;
+    else if (p > 1 && nr < p * 10) {
+        const double k = p, nn = nr;
+        if (std::exp(std::log(k - 1.0) * nn - std::log(k) * (nn - 1.0)) > 0.1) res->warn_few_reads = 1;
+    }
+    // count_unexplained_reads (solve.rs:719-729): best_at_contig over the called genotype's contigs = the
+    // matrix column of those contigs, which lives on the device (Mt).
+    {
+        uint32_t ids[LCTP_MAX_PLOIDY];
+        genotype_tuple(h->dev.H, p, h->gt_tuples_host.empty() ? nullptr : h->gt_tuples_host.data(), res->gt_ix[0], ids);
+        std::vector<double> col((size_t)nr * p);
+        for (uint32_t k = 0; k < p; k++)
+            LCTP_CUDA_CHECK(cudaMemcpy2DAsync(col.data() + (size_t)k * nr, 8, h->Mt.p + ids[k], (size_t)h->dev.Hpad * 8, 8, nr,
+                                              cudaMemcpyDeviceToHost, h->ctx->stream));
+        LCTP_CUDA_CHECK(cudaStreamSynchronize(h->ctx->stream));
+        uint32_t unexpl = 0;
+        for (uint32_t r = 0; r < nr; r++) {
+            double best = -std::numeric_limits<double>::infinity();
+            for (uint32_t k = 0; k < p; k++) best = std::fmax(best, col[(size_t)k * nr + r]);
+            unexpl += best < h->unmapped_host[r] + 1e-8 ? 1u : 0u;
+        }
+        res->unexpl_reads = unexpl;
+    }
+    return LCTP_OK;
+}
+
+// Minimal writer compatible with `json::JsonValue::write_pretty(.., 4)`: keys in insertion order.
+static void json_num(std::string &o, double v) {
+    char b[64];
+    if (std::isnan(v) || std::isinf(v)) { o += "null"; return; }
+    if (v == std::floor(v) && std::fabs(v) < 1e15) snprintf(b, sizeof b, "%.0f", v);
+    else snprintf(b, sizeof b, "%.17g", v);
+    o += b;
+}
+
+size_t lctp_result_json(const lctp_result *res, const lctp_locus *loc, const char *const *hap_names, char *buf,
+                        size_t cap) {
+    std::string o;
+    const double inv_ln10 = 0.4342944819032518277;
+    auto gt_name = [&](uint64_t g) {
+        uint32_t ids[LCTP_MAX_PLOIDY];
+        genotype_tuple(loc->n_haps, loc->ploidy, loc->gt_tuples, g, ids);
+        std::string s;
+        for (uint32_t k = 0; k < loc->ploidy; k++) { if (k) s += ","; s += hap_names[ids[k]]; }   // Genotype name, contigs.rs:404-459
+        return s;
+    };
+    o += "{\n    \"total_reads\": "; json_num(o, res->total_reads);
+    o += ",\n    \"quality\": "; json_num(o, res->quality);
+    o += ",\n    \"unexpl_reads\": "; json_num(o, res->unexpl_reads);
+    if (res->n_out) {
+        o += ",\n    \"genotype\": \"" + gt_name(res->gt_ix[0]) + "\"";
+        o += ",\n    \"options\": [";
+        for (uint64_t i = 0; i < res->n_out; i++) {
+            o += i ? ",\n        {" : "\n        {";
+            o += "\n            \"genotype\": \"" + gt_name(res->gt_ix[i]) + "\"";
+            o += ",\n            \"lik_mean\": "; json_num(o, res->lik_mean[i] * inv_ln10);
+            o += ",\n            \"lik_sd\": "; json_num(o, res->lik_var[i] * inv_ln10);   // sic: log10 of the variance (solve.rs:755)
+            o += ",\n            \"prob\": "; json_num(o, std::exp(res->ln_prob[i]));
+            o += ",\n            \"log10_prob\": "; json_num(o, res->ln_prob[i] * inv_ln10);
+            o += "\n        }";
+        }
+        o += "\n    ]";
+    }
+    if (res->warn_no_probable || res->warn_few_reads) {
+        o += ",\n    \"warnings\": [";
+        bool first = true;
+        if (res->warn_no_probable) { o += "\n        \"NoProbableGenotype\""; first = false; }
+        if (res->warn_few_reads) {
+            char b[64]; snprintf(b, sizeof b, "%s\n        \"FewReads(%u)\"", first ? "" : ",", res->total_reads); o += b;
+        }
+        o += "\n    ]";
+    }
+    o += "\n}";
+    if (buf && cap) {
+        size_t ncopy = std::min(cap - 1, o.size());
+        std::memcpy(buf, o.data(), ncopy);
+        buf[ncopy] = 0;
+    }
+    return o.size();
+}
+
+}  // extern "C"

@@ -1,0 +1,779 @@
+// solver.cu -- a5..a13: one solver stage on the device.
+//
+// One WARP per logical worker (= one xoshiro256++ stream of the reference, src/solvers/solve.rs:1007-1018).
+// A worker solves its genotypes back to back on that stream exactly like Worker::run (:1104-1145):
+//   per genotype: GenotypeAlignments::new (src/model/assgn.rs:41-84, windows.rs:762-797)   -> build_instance
+//   per attempt : apply_tweak (assgn.rs:127-151, windows.rs:123-136,478-486)               -> apply_tweak
+//                 Solver::solve (solvers/mod.rs:61-72) = Greedy (stoch.rs:81-120) | SimAnneal (:197-242)
+//                 lik = prior + likelihood() (solve.rs:1126); update_counts (assgn.rs:374-378)
+//   mean / variance over attempts (ext/vec.rs:74-116)
+//
+// Exactness: all f64 arithmetic that feeds an accept/reject uses the non-contracting intrinsics
+// (__dadd_rn/__dmul_rn/__dsub_rn) in the reference's association order; the file is also compiled with
+// -fmad=false.  The RNG state is replicated in every lane (all lanes step it identically), so draws are
+// consumed in exactly the reference's order with warp-uniform control flow.
+//
+// Per-worker state: depth[], window distributions and the two likelihood accumulators live in shared
+// memory / registers; candidate arrays live in a per-warp global slab (L2-resident for typical loci).
+#include "common.cuh"
+
+#include <cmath>
+#include <algorithm>
+
+namespace lctp {
+
+static constexpr int WARPS_PER_CTA = 4;
+static constexpr uint32_t TRIVIAL_ROW = 0xFFFFFFFFu;
+static constexpr unsigned FULL = 0xFFFFFFFFu;
+
+struct StageParams {
+    uint32_t kind, attempts, best_start, sample_size;
+    uint64_t plato_size, anneal_steps, max_iter;
+    double ln_init_prob;
+    uint32_t n_workers, cap, Wmax, want_counts;
+    uint64_t slab_bytes;
+};
+
+struct Slab {
+    double *cand_lnprob;   // [cap]
+    uint32_t *cand_w;      // [cap]  (w1 | w2 << 16)
+    uint32_t *cand_src;    // [cap]  index into cm arrays, LCTP_NONE_U32 = "both mates unmapped" option
+    uint2 *nt_info;        // [R]    (start, n << 16 | assgn) for every non-trivial read, in read order
+    uint32_t *read_off;    // [R+1]
+    uint8_t *cand_cix;     // [cap]
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline size_t slab_layout(uint32_t cap, uint32_t R, unsigned char *base, Slab *s) {
+    size_t o = 0;
+    if (s) s->cand_lnprob = (double *)(base + o);
+    o += align_up((size_t)cap * 8, 128);
+    if (s) s->cand_w = (uint32_t *)(base + o);
+    o += align_up((size_t)cap * 4, 128);
+    if (s) s->cand_src = (uint32_t *)(base + o);
+    o += align_up((size_t)cap * 4, 128);
+    if (s) s->nt_info = (uint2 *)(base + o);
+    o += align_up((size_t)R * 8, 128);
+    if (s) s->read_off = (uint32_t *)(base + o);
+    o += align_up(((size_t)R + 1) * 4, 128);
+    if (s) s->cand_cix = (uint8_t *)(base + o);
+    o += align_up((size_t)cap, 128);
+    return o;
+}
+
+// ------------------------------------------------------------------ RNG (warp-uniform) -----------
+
+struct Xo { uint64_t s0, s1, s2, s3; };
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+
+// xoshiro256++ (rand_xoshiro::Xoshiro256PlusPlus, src/ext/rand.rs:3)
+__device__ __forceinline__ uint64_t xo_next(Xo &x) {
+    const uint64_t r = rotl64(x.s0 + x.s3, 23) + x.s0;
+    const uint64_t t = x.s1 << 17;
+    x.s2 ^= x.s0; x.s3 ^= x.s1; x.s1 ^= x.s2; x.s0 ^= x.s3; x.s2 ^= t;
+    x.s3 = rotl64(x.s3, 45);
+    return r;
+}
+__device__ __forceinline__ uint32_t xo_u32(Xo &x) { return (uint32_t)(xo_next(x) >> 32); }
+
+// rand UniformInt::sample_single_inclusive with a u32 sample type: value in [0, range), range != 0.
+__device__ __forceinline__ uint32_t xo_below(Xo &x, uint32_t range) {
+    const uint64_t m = (uint64_t)xo_u32(x) * (uint64_t)range;
+    uint32_t res = (uint32_t)(m >> 32);
+    const uint32_t lo = (uint32_t)m;
+    if (lo > 0u - range) {   // biased zone: one extra draw (warp-uniform branch)
+        const uint32_t nh = (uint32_t)(((uint64_t)xo_u32(x) * (uint64_t)range) >> 32);
+        res += (lo + nh < lo) ? 1u : 0u;
+    }
+    return res;
+}
+// rand StandardUniform f64 (src/solvers/stoch.rs:216)
+__device__ __forceinline__ double xo_f64(Xo &x) {
+    return (double)(xo_next(x) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// ------------------------------------------------------------------ small helpers ---------------
+
+__device__ __forceinline__ double shfl_d(double v, int src) {
+    return __shfl_sync(FULL, v, src);
+}
+__device__ __forceinline__ double shfl_xor_d(double v, int m) {
+    return __shfl_xor_sync(FULL, v, m);
+}
+// f64::total_cmp key (Rust std)
+__device__ __forceinline__ long long total_key(double v) {
+    long long b = __double_as_longlong(v);
+    return b ^ (long long)(((unsigned long long)(b >> 63)) >> 1);
+}
+
+struct WarpShared {
+    uint32_t *depth;     // [Wmax]
+    double *wd_weight;   // [Wmax]
+    uint32_t *wd_row;    // [Wmax]  gc * depth_k, or TRIVIAL_ROW
+};
+
+// WindowDistr::ln_prob (src/model/distr_cache.rs:34-39)
+__device__ __forceinline__ double win_ln_prob(const WarpShared &ws, const double *__restrict__ table,
+                                              uint32_t w, uint32_t k) {
+    const uint32_t row = ws.wd_row[w];
+    if (row == TRIVIAL_ROW) return 0.0;
+    return __dmul_rn(ws.wd_weight[w], __ldg(table + row + k));
+}
+
+// atomic_depth_lik_diff (src/model/assgn.rs:244-254)
+__device__ __forceinline__ double atomic_diff(const WarpShared &ws, const double *__restrict__ table,
+                                              uint32_t w, int change) {
+    if (change == 0) return 0.0;
+    const uint32_t row = ws.wd_row[w];
+    if (row == TRIVIAL_ROW) return 0.0;      // 0.0 - 0.0
+    const uint32_t od = ws.depth[w];
+    const uint32_t nd = (uint32_t)((int)od + change);
+    const double wt = ws.wd_weight[w];
+    return __dsub_rn(__dmul_rn(wt, __ldg(table + row + nd)), __dmul_rn(wt, __ldg(table + row + od)));
+}
+
+// depth_lik_diff (src/model/assgn.rs:259-284): ((a1 + a2) + a3) + a4
+__device__ __forceinline__ double depth_lik_diff(const WarpShared &ws, const double *__restrict__ table,
+                                                 uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4) {
+    int c1 = -1, c2, c3, c4;
+    if (w2 == w1) { c1 -= 1; c2 = 0; } else c2 = -1;
+    if (w3 == w1) { c1 += 1; c3 = 0; } else if (w3 == w2) { c2 += 1; c3 = 0; } else c3 = 1;
+    if (w4 == w1) { c1 += 1; c4 = 0; } else if (w4 == w2) { c2 += 1; c4 = 0; }
+    else if (w4 == w3) { c3 += 1; c4 = 0; } else c4 = 1;
+    double s = __dadd_rn(atomic_diff(ws, table, w1, c1), atomic_diff(ws, table, w2, c2));
+    s = __dadd_rn(s, atomic_diff(ws, table, w3, c3));
+    return __dadd_rn(s, atomic_diff(ws, table, w4, c4));
+}
+
+// ------------------------------------------------------------------ a5: instance build ----------
+
+struct Instance {
+    uint32_t haps[LCTP_MAX_PLOIDY];
+    uint32_t wshift[LCTP_MAX_PLOIDY + 1];
+    uint32_t W, A, n_nt;
+};
+
+// GenotypeAlignments::new: per read, gather candidates of every genotype contig above the running
+// threshold, append the unmapped option, stable-sort descending (here: a p-way merge of the already
+// sorted per-contig lists, ties resolved in insertion order = contig order, unmapped last), cut at the
+// final threshold.  Returns false on slab overflow.
+__device__ bool build_instance(const LocusDev &L, const Slab &S, uint32_t cap, Instance &I, int lane) {
+    const uint32_t R = L.R, p = L.p;
+    uint32_t base = 0, nt_base = 0;
+    bool ok = true;
+    for (uint32_t r0 = 0; r0 < R; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        const bool valid = r < R;
+        uint32_t lb[LCTP_MAX_PLOIDY], le[LCTP_MAX_PLOIDY];
+        double unm = 0.0, thresh = 0.0;
+        uint32_t nw = 0;
+        bool with_unm = false;
+        if (valid) {
+            unm = L.unmapped[r];
+            thresh = __dsub_rn(unm, L.prob_diff);
+            for (uint32_t k = 0; k < p; k++) {
+                const size_t key = (size_t)I.haps[k] * R + r;
+                lb[k] = L.cm_off[key];
+                le[k] = L.cm_off[key + 1];
+                if (le[k] > lb[k]) thresh = fmax(thresh, __dsub_rn(L.cm_lnprob[lb[k]], L.prob_diff));
+            }
+            for (uint32_t k = 0; k < p; k++) {
+                uint32_t e = lb[k];
+                while (e < le[k] && L.cm_lnprob[e] >= thresh) e++;
+                le[k] = e;
+                nw += e - lb[k];
+            }
+            with_unm = unm >= thresh;
+            nw += with_unm ? 1u : 0u;
+        }
+        uint32_t incl = nw;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        const uint32_t start = base + incl - nw;
+        const bool nt = valid && nw > 1;
+        const unsigned ntmask = __ballot_sync(FULL, nt);
+        if (valid) S.read_off[r] = start;
+        if (base + total > cap) ok = false;
+        if (ok && valid) {
+            if (nt) {
+                const uint32_t pos = nt_base + __popc(ntmask & ((1u << lane) - 1u));
+                S.nt_info[pos] = make_uint2(start, nw << 16);
+            }
+            bool unm_left = with_unm;
+            const long long unm_key = total_key(unm);
+            for (uint32_t t = 0; t < nw; t++) {
+                int bk = -1;
+                long long bkey = 0;
+                for (uint32_t k = 0; k < p; k++) {
+                    if (lb[k] < le[k]) {
+                        const long long key = total_key(L.cm_lnprob[lb[k]]);
+                        if (bk < 0 || key > bkey) { bk = (int)k; bkey = key; }
+                    }
+                }
+                const uint32_t o = start + t;
+                if (bk >= 0 && !(unm_left && unm_key > bkey)) {
+                    S.cand_lnprob[o] = L.cm_lnprob[lb[bk]];
+                    S.cand_src[o] = lb[bk];
+                    S.cand_cix[o] = (uint8_t)bk;
+                    lb[bk]++;
+                } else {
+                    S.cand_lnprob[o] = unm;
+                    S.cand_src[o] = LCTP_NONE_U32;
+                    S.cand_cix[o] = 255;
+                    unm_left = false;
+                }
+                S.cand_w[o] = 0;   // [UNMAPPED_WINDOW; 2] until apply_tweak
+            }
+        }
+        base += total;
+        nt_base += __popc(ntmask);
+    }
+    if (lane == 0) S.read_off[R] = base;
+    I.A = base;
+    I.n_nt = nt_base;
+    __syncwarp();
+    return ok;
+}
+
+// ------------------------------------------------------------------ a6: apply_tweak -------------
+
+// ContigInfo::get_shifted_window_ix (src/model/windows.rs:62-68,465-470)
+__device__ __forceinline__ uint32_t shifted_window(const LocusDev &L, uint32_t hap, uint32_t shift, uint32_t middle) {
+    const uint32_t start = L.hap_reg_start[hap];
+    const uint32_t end = start + L.hap_n_windows[hap] * L.window;
+    if (start <= middle && middle < end) return (middle - start) / L.window + shift;
+    return 1;   // BOUNDARY_WINDOW
+}
+
+__device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I, const WarpShared &ws,
+                            Xo &rng, int lane) {
+    const uint32_t tweak = L.tweak;
+    const uint32_t span = 2 * tweak + 1;
+    // (i) read middles: one next_u64 per candidate that has a parent, in candidate order
+    for (uint32_t c0 = 0; c0 < I.A; c0 += 32) {
+        const uint32_t c = c0 + lane;
+        const uint32_t src = c < I.A ? S.cand_src[c] : LCTP_NONE_U32;
+        const bool has_parent = src != LCTP_NONE_U32;
+        uint64_t mine = 0;
+        if (tweak != 0) {
+            const unsigned mask = __ballot_sync(FULL, has_parent);
+            const int my_rank = __popc(mask & ((1u << lane) - 1u));
+            const int n_draws = __popc(mask);
+            for (int q = 0; q < n_draws; q++) {
+                const uint64_t v = xo_next(rng);
+                if (q == my_rank) mine = v;
+            }
+        }
+        if (has_parent) {
+            const uint32_t k = S.cand_cix[c];
+            const uint32_t hap = I.haps[k], shift = I.wshift[k];
+            const uint2 mid = L.cm_mid[src];
+            const uint32_t t1 = tweak ? (uint32_t)(mine >> 32) % span : 0u;
+            const uint32_t t2 = tweak ? (uint32_t)mine % span : 0u;
+            const uint32_t w1 = mid.x == LCTP_NONE_U32 ? 0u : shifted_window(L, hap, shift, mid.x + t1);
+            const uint32_t w2 = mid.y == LCTP_NONE_U32 ? 0u : shifted_window(L, hap, shift, mid.y + t2);
+            S.cand_w[c] = w1 | (w2 << 16);
+        }
+    }
+    // (ii) window distributions: one bounded i32 draw per window, contigs in genotype order
+    if (lane < 2) { ws.wd_row[lane] = TRIVIAL_ROW; ws.wd_weight[lane] = 0.0; }
+    for (uint32_t k = 0; k < L.p; k++) {
+        const uint32_t hap = I.haps[k];
+        const uint32_t nwin = L.hap_n_windows[hap];
+        const uint32_t reg_start = L.hap_reg_start[hap], hlen = L.hap_len[hap];
+        const uint64_t pos_off = L.hap_pos_off[hap];
+        for (uint32_t i0 = 0; i0 < nwin; i0 += 32) {
+            const uint32_t cnt = min(32u, nwin - i0);
+            uint32_t my_wstart = 0;
+            for (uint32_t q = 0; q < cnt; q++) {
+                // generate_windows (windows.rs:478-486)
+                const uint32_t start = reg_start + (i0 + q) * L.window;
+                const uint32_t end = start + L.window;
+                const uint32_t left = min(tweak, start), right = min(tweak, hlen - end);
+                const uint32_t rr = xo_below(rng, left + right + 1u);   // random_range(-left..=right) + left
+                if ((uint32_t)lane == q) my_wstart = start + rr - left;
+            }
+            if ((uint32_t)lane < cnt) {
+                // neighb_info (windows.rs:439-445) + assgn.rs:144-148 + get_distribution (distr_cache.rs:83-92)
+                const uint32_t idx = my_wstart > L.left_padding ? my_wstart - L.left_padding : 0u;
+                const double weight = L.pos_weight[pos_off + idx];
+                const uint32_t gc = L.pos_gc[pos_off + idx];
+                const uint32_t w = I.wshift[k] + i0 + lane;
+                if (weight < L.min_weight || weight < 1e-7) { ws.wd_row[w] = TRIVIAL_ROW; ws.wd_weight[w] = 0.0; }
+                else { ws.wd_row[w] = gc * L.depth_k; ws.wd_weight[w] = weight; }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------ a8: ReadAssignment::new -----
+
+// Sequentially (in index order) add `count` per-lane terms to acc: reproduces iter().sum() order.
+__device__ __forceinline__ void seq_add(double &acc, double term, int count) {
+    for (int q = 0; q < count; q++) acc = __dadd_rn(acc, shfl_d(term, q));
+}
+
+// init_mode 0: every read at candidate 0; 1: random_range(0..m) per non-trivial read (read order).
+__device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance &I, const WarpShared &ws,
+                                Xo &rng, int init_mode, double &aln_lik, double &depth_lik, int lane) {
+    for (uint32_t w = lane; w < I.W; w += 32) ws.depth[w] = 0;
+    // assignments of non-trivial reads
+    for (uint32_t i0 = 0; i0 < I.n_nt; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        uint2 info = i < I.n_nt ? S.nt_info[i] : make_uint2(0, 0);
+        uint32_t a = 0;
+        if (init_mode == 1) {
+            const int cnt = (int)min(32u, I.n_nt - i0);
+            for (int q = 0; q < cnt; q++) {
+                const uint32_t m = __shfl_sync(FULL, info.y >> 16, q);
+                const uint32_t v = xo_below(rng, m);
+                if (lane == q) a = v;
+            }
+        }
+        if (i < I.n_nt) { info.y = (info.y & 0xFFFF0000u) | a; S.nt_info[i] = info; }
+    }
+    __syncwarp();
+    // depth counts + aln_lik in read order (src/model/assgn.rs:205-217,351-353)
+    double al = 0.0;
+    uint32_t nt_base = 0;
+    for (uint32_t r0 = 0; r0 < L.R; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        const bool valid = r < L.R;
+        uint32_t start = 0, nw = 0;
+        if (valid) { start = S.read_off[r]; nw = S.read_off[r + 1] - start; }
+        const bool nt = valid && nw > 1;
+        const unsigned ntmask = __ballot_sync(FULL, nt);
+        double term = 0.0;
+        if (valid) {
+            uint32_t a = 0;
+            if (nt) a = S.nt_info[nt_base + __popc(ntmask & ((1u << lane) - 1u))].y & 0xFFFFu;
+            const uint32_t ix = start + a;
+            term = S.cand_lnprob[ix];
+            const uint32_t w12 = S.cand_w[ix];
+            atomicAdd(&ws.depth[w12 & 0xFFFFu], 1u);
+            atomicAdd(&ws.depth[w12 >> 16], 1u);
+        }
+        nt_base += __popc(ntmask);
+        seq_add(al, term, (int)min(32u, L.R - r0));
+    }
+    __syncwarp();
+    // depth_lik in window order (assgn.rs:347-350)
+    double dl = 0.0;
+    for (uint32_t w0 = 0; w0 < I.W; w0 += 32) {
+        const uint32_t w = w0 + lane;
+        const double term = w < I.W ? win_ln_prob(ws, L.depth_table, w, ws.depth[w]) : 0.0;
+        seq_add(dl, term, (int)min(32u, I.W - w0));
+    }
+    aln_lik = al;
+    depth_lik = dl;
+}
+
+// ------------------------------------------------------------------ a9: targets -----------------
+
+struct Target { uint32_t idx, n, old_a, new_a, old_ix, new_ix; };
+
+// ReassignmentTarget::random (src/model/assgn.rs:451-471), warp-uniform
+__device__ __forceinline__ Target random_target(const Slab &S, const Instance &I, Xo &rng) {
+    Target t;
+    t.idx = xo_below(rng, I.n_nt);                     // random_range(0..n_nontrivial), usize via the u32 path
+    const uint2 info = S.nt_info[t.idx];
+    t.n = info.y >> 16;
+    t.old_a = info.y & 0xFFFFu;
+    if (t.n == 2) t.new_a = 1u - t.old_a;
+    else {
+        const uint32_t i = 1u + xo_below(rng, t.n - 1u);   // random_range(1..n as u16)
+        t.new_a = i <= t.old_a ? i - 1u : i;
+    }
+    t.old_ix = info.x + t.old_a;
+    t.new_ix = info.x + t.new_a;
+    return t;
+}
+
+struct Move { double dld, dlp; uint32_t w12, w34; };
+
+// calculate_improvement (src/model/assgn.rs:321-328)
+__device__ __forceinline__ double calc_improvement(const LocusDev &L, const Slab &S, const WarpShared &ws,
+                                                   const Target &t, Move &mv) {
+    mv.w12 = S.cand_w[t.old_ix];
+    mv.w34 = S.cand_w[t.new_ix];
+    mv.dld = depth_lik_diff(ws, L.depth_table, mv.w12 & 0xFFFFu, mv.w12 >> 16, mv.w34 & 0xFFFFu, mv.w34 >> 16);
+    mv.dlp = __dsub_rn(S.cand_lnprob[t.new_ix], S.cand_lnprob[t.old_ix]);
+    return __dadd_rn(__dmul_rn(L.depth_contrib, mv.dld), __dmul_rn(L.aln_contrib, mv.dlp));
+}
+
+// reassign (src/model/assgn.rs:331-343); warp-uniform inputs, lane 0 writes
+__device__ __forceinline__ void apply_move(const Slab &S, const WarpShared &ws, uint32_t idx, uint32_t n,
+                                           uint32_t new_a, const Move &mv, double &aln_lik, double &depth_lik,
+                                           int lane) {
+    depth_lik = __dadd_rn(depth_lik, mv.dld);
+    aln_lik = __dadd_rn(aln_lik, mv.dlp);
+    if (lane == 0) {
+        ws.depth[mv.w34 & 0xFFFFu] += 1;
+        ws.depth[mv.w34 >> 16] += 1;
+        ws.depth[mv.w12 & 0xFFFFu] -= 1;
+        ws.depth[mv.w12 >> 16] -= 1;
+        S.nt_info[idx].y = (n << 16) | new_a;
+    }
+    __syncwarp();
+}
+
+// max_abs_random (src/solvers/stoch.rs:19-22) with INIT_ITER = 100
+__device__ double max_abs_random(const LocusDev &L, const Slab &S, const Instance &I, const WarpShared &ws, Xo &rng) {
+    double acc = 0.0;
+    for (int q = 0; q < 100; q++) {
+        const Target t = random_target(S, I, rng);
+        Move mv;
+        acc = fmax(acc, fabs(calc_improvement(L, S, ws, t, mv)));
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------ a10: Greedy -----------------
+
+__device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab &S, const Instance &I,
+                             const WarpShared &ws, Xo &rng, double &aln_lik, double &depth_lik,
+                             uint64_t &iters_out, int lane) {
+    const uint32_t amount = min(P.sample_size, I.n_nt);
+    init_assignment(L, S, I, ws, rng, P.best_start ? 0 : 1, aln_lik, depth_lik, lane);
+    const double min_diff = fmax(__dmul_rn(1e-10, max_abs_random(L, S, I, ws, rng)), 1e-14);
+    const int slot = lane >> 1, sub = lane & 1;
+    const bool active = (uint32_t)slot < amount;
+    uint64_t curr_plato = 0, it = 0;
+    for (; it < P.max_iter; it++) {
+        // IndexedRandom::sample -> rand::seq::index::sample_floyd (amount <= 11)
+        uint32_t myv = 0;
+        for (uint32_t k = 0; k < amount; k++) {
+            const uint32_t j = I.n_nt - amount + k;
+            const uint32_t t = xo_below(rng, j + 1u);
+            if ((uint32_t)lane == k) myv = t;
+        }
+        for (uint32_t k = 1; k < amount; k++) {
+            const uint32_t t = __shfl_sync(FULL, myv, k);
+            if ((uint32_t)lane < k && myv == t) myv = I.n_nt - amount + k;
+        }
+        // best_read_improvement for every sampled read: 2 lanes per read
+        const uint32_t idx = __shfl_sync(FULL, myv, slot);
+        double best = -INFINITY, b_dld = 0.0, b_lp = 0.0, lp_old = 0.0;
+        uint32_t b_c = 0, b_w34 = 0, w12 = 0, n = 0;
+        if (active) {
+            const uint2 info = S.nt_info[idx];
+            n = info.y >> 16;
+            const uint32_t old_a = info.y & 0xFFFFu;
+            lp_old = S.cand_lnprob[info.x + old_a];
+            w12 = S.cand_w[info.x + old_a];
+            for (uint32_t c = sub; c < n; c += 2) {
+                if (c == old_a) continue;
+                const double lp = S.cand_lnprob[info.x + c];
+                const uint32_t w34 = S.cand_w[info.x + c];
+                const double dld = depth_lik_diff(ws, L.depth_table, w12 & 0xFFFFu, w12 >> 16, w34 & 0xFFFFu, w34 >> 16);
+                const double improv = __dadd_rn(lp, __dmul_rn(L.rel_contrib, dld));
+                if (improv > best) { best = improv; b_c = c; b_dld = dld; b_lp = lp; b_w34 = w34; }
+            }
+        }
+        {   // merge the two lanes of a read: strict '>' in candidate order = lowest index wins ties
+            const double o_best = shfl_xor_d(best, 1);
+            const uint32_t o_c = __shfl_xor_sync(FULL, b_c, 1);
+            if (o_best > best || (o_best == best && o_c < b_c)) { best = o_best; b_c = o_c; }
+        }
+        // assgn.rs:310
+        double s_improv = active ? __dmul_rn(L.aln_contrib, __dsub_rn(best, lp_old)) : -INFINITY;
+        uint32_t key = ((uint32_t)slot << 16) | b_c;
+#pragma unroll
+        for (int m = 2; m < 32; m <<= 1) {   // across reads: first (lowest slot) strictly-greater wins
+            const double o_s = shfl_xor_d(s_improv, m);
+            const uint32_t o_key = __shfl_xor_sync(FULL, key, m);
+            if (o_s > s_improv || (o_s == s_improv && (o_key >> 16) < (key >> 16))) { s_improv = o_s; key = o_key; }
+        }
+        if (s_improv > min_diff) {
+            const int wl = (int)((key >> 16) * 2 + (key & 1u));   // lane that evaluated the winning candidate
+            Move mv;
+            mv.dld = shfl_d(b_dld, wl);
+            mv.dlp = shfl_d(__dsub_rn(b_lp, lp_old), wl);
+            mv.w12 = __shfl_sync(FULL, w12, wl);
+            mv.w34 = __shfl_sync(FULL, b_w34, wl);
+            const uint32_t w_idx = __shfl_sync(FULL, idx, wl);
+            const uint32_t w_n = __shfl_sync(FULL, n, wl);
+            apply_move(S, ws, w_idx, w_n, key & 0xFFFFu, mv, aln_lik, depth_lik, lane);
+            curr_plato = 0;
+        } else {
+            curr_plato += 1;
+            if (curr_plato > P.plato_size) { it++; break; }
+        }
+    }
+    iters_out += it;
+}
+
+// ------------------------------------------------------------------ a11: SimAnneal --------------
+
+__device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab &S, const Instance &I,
+                             const WarpShared &ws, Xo &rng, double &aln_lik, double &depth_lik,
+                             uint64_t &iters_out, int lane) {
+    init_assignment(L, S, I, ws, rng, 1, aln_lik, depth_lik, lane);
+    const double max_abs = max_abs_random(L, S, I, ws, rng);
+    const double min_diff = fmax(__dmul_rn(1e-10, max_abs), 1e-14);
+    const double start_temp = fmax(__ddiv_rn(-max_abs, P.ln_init_prob), 1e-5);
+    const double temp_step = __ddiv_rn(start_temp, (double)P.anneal_steps);
+    uint64_t curr_plato = 0, steps = 0;
+    for (uint64_t i = P.anneal_steps; i >= 1; i--) {
+        const Target t = random_target(S, I, rng);
+        Move mv;
+        const double diff = __dsub_rn(calc_improvement(L, S, ws, t, mv), min_diff);
+        steps++;
+        bool accept = diff >= 0.0;
+        if (!accept) {
+            const double u = xo_f64(rng);
+            accept = u <= exp(__ddiv_rn(diff, __dmul_rn(temp_step, (double)i)));
+        }
+        if (accept) { apply_move(S, ws, t.idx, t.n, t.new_a, mv, aln_lik, depth_lik, lane); curr_plato = 0; }
+        else { curr_plato += 1; if (curr_plato >= P.plato_size) break; }
+    }
+    for (uint64_t k = 0; k < P.max_iter; k++) {
+        if (curr_plato >= P.plato_size) break;
+        const Target t = random_target(S, I, rng);
+        Move mv;
+        const double diff = calc_improvement(L, S, ws, t, mv);
+        steps++;
+        if (diff > min_diff) { apply_move(S, ws, t.idx, t.n, t.new_a, mv, aln_lik, depth_lik, lane); curr_plato = 0; }
+        else curr_plato += 1;
+    }
+    iters_out += steps;
+}
+
+// ------------------------------------------------------------------ stage kernel ----------------
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs,
+              const uint64_t *__restrict__ worker_off, const uint32_t *__restrict__ tuples,
+              uint64_t *__restrict__ rng_states, double *__restrict__ lik_mean, double *__restrict__ lik_var,
+              double *__restrict__ liks, uint64_t *__restrict__ n_alns, uint64_t *__restrict__ iters,
+              uint16_t *__restrict__ counts, unsigned char *__restrict__ scratch,
+              unsigned int *__restrict__ work_counter, int *__restrict__ err) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t per_warp = (size_t)P.Wmax * 16;
+    WarpShared ws;
+    ws.wd_weight = (double *)(smem + wib * per_warp);
+    ws.depth = (uint32_t *)(smem + wib * per_warp + (size_t)P.Wmax * 8);
+    ws.wd_row = ws.depth + P.Wmax;
+    const uint32_t slot = blockIdx.x * WARPS_PER_CTA + wib;
+    Slab S;
+    slab_layout(P.cap, L.R, scratch + (size_t)slot * P.slab_bytes, &S);
+
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(work_counter, 1u);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= P.n_workers) break;
+        Xo rng;
+        rng.s0 = rng_states[4 * (size_t)w + 0]; rng.s1 = rng_states[4 * (size_t)w + 1];
+        rng.s2 = rng_states[4 * (size_t)w + 2]; rng.s3 = rng_states[4 * (size_t)w + 3];
+        for (uint64_t j = worker_off[w]; j < worker_off[w + 1]; j++) {
+            const uint64_t g = worker_ixs[j];
+            const double prior = L.priors ? L.priors[g] : 0.0;
+            Instance I;
+            uint32_t wsft = 2;
+            I.wshift[0] = wsft;
+            for (uint32_t k = 0; k < L.p; k++) {
+                I.haps[k] = tuples[j * L.p + k];
+                wsft += L.hap_n_windows[I.haps[k]];
+                I.wshift[k + 1] = wsft;
+            }
+            I.W = wsft;
+            const bool ok = build_instance(L, S, P.cap, I, lane);
+            if (!ok) {
+                if (lane == 0) { atomicOr(err, 1); lik_mean[j] = NAN; lik_var[j] = NAN; n_alns[j] = I.A; }
+                continue;
+            }
+            uint16_t *cnt = P.want_counts ? counts + (size_t)j * P.cap : nullptr;
+            if (cnt) { for (uint32_t c = lane; c < I.A; c += 32) cnt[c] = 0; }
+            uint64_t it_total = 0;
+            for (uint32_t a = 0; a < P.attempts; a++) {
+                apply_tweak(L, S, I, ws, rng, lane);
+                double aln_lik = 0.0, depth_lik = 0.0;
+                if (I.n_nt == 0) init_assignment(L, S, I, ws, rng, 0, aln_lik, depth_lik, lane);
+                else if (P.kind == 0) greedy_solve(L, P, S, I, ws, rng, aln_lik, depth_lik, it_total, lane);
+                else anneal_solve(L, P, S, I, ws, rng, aln_lik, depth_lik, it_total, lane);
+                // likelihood (assgn.rs:235-237) + prior (solve.rs:1126)
+                const double lik = __dadd_rn(prior, __dadd_rn(__dmul_rn(L.depth_contrib, depth_lik),
+                                                              __dmul_rn(L.aln_contrib, aln_lik)));
+                if (lane == 0) liks[j * P.attempts + a] = lik;
+                if (cnt) {   // update_counts (assgn.rs:374-378)
+                    __syncwarp();
+                    uint32_t nt_base = 0;
+                    for (uint32_t r0 = 0; r0 < L.R; r0 += 32) {
+                        const uint32_t r = r0 + lane;
+                        const bool valid = r < L.R;
+                        uint32_t start = 0, nw = 0;
+                        if (valid) { start = S.read_off[r]; nw = S.read_off[r + 1] - start; }
+                        const bool nt = valid && nw > 1;
+                        const unsigned ntmask = __ballot_sync(FULL, nt);
+                        if (valid) {
+                            uint32_t as = 0;
+                            if (nt) as = S.nt_info[nt_base + __popc(ntmask & ((1u << lane) - 1u))].y & 0xFFFFu;
+                            cnt[start + as] += 1;
+                        }
+                        nt_base += __popc(ntmask);
+                    }
+                }
+                __syncwarp();
+            }
+            __syncwarp();
+            // mean_variance_or_nan (ext/vec.rs:74-78,86-93,109-116)
+            if (lane == 0) {
+                const double *x = liks + j * P.attempts;
+                double s = 0.0;
+                for (uint32_t a = 0; a < P.attempts; a++) s = __dadd_rn(s, x[a]);
+                const double mean = __ddiv_rn(s, (double)P.attempts);
+                double var = NAN;
+                if (P.attempts > 1) {
+                    double acc = 0.0;
+                    for (uint32_t a = 0; a < P.attempts; a++) {
+                        const double d = __dsub_rn(x[a], mean);
+                        acc = __dadd_rn(acc, __dmul_rn(d, d));
+                    }
+                    var = __ddiv_rn(acc, (double)(P.attempts - 1));
+                }
+                lik_mean[j] = mean;
+                lik_var[j] = var;
+                n_alns[j] = I.A;
+                iters[j] = it_total;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            rng_states[4 * (size_t)w + 0] = rng.s0; rng_states[4 * (size_t)w + 1] = rng.s1;
+            rng_states[4 * (size_t)w + 2] = rng.s2; rng_states[4 * (size_t)w + 3] = rng.s3;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host launch -----------------
+
+int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_ixs, const uint64_t *worker_off,
+                 size_t n_workers, uint64_t *worker_rng, double *lik_mean, double *lik_var, double *liks,
+                 uint64_t *counts_off, uint16_t *counts, uint64_t counts_cap, uint64_t *n_alns_out,
+                 uint64_t *iters_out) {
+    lctp_ctx *ctx = h->ctx;
+    cudaStream_t s = ctx->stream;
+    const LocusDev &L = h->dev;
+    if (!st || !worker_ixs || !worker_off || !worker_rng || !lik_mean || !lik_var || n_workers == 0) {
+        set_error("lctp_solve_stage: NULL argument");
+        return LCTP_E_INVALID;
+    }
+    if (st->kind > 1 || st->attempts == 0 || st->attempts > 65535) {
+        set_error("lctp_solve_stage: invalid stage (kind=%u attempts=%u)", st->kind, st->attempts);
+        return LCTP_E_INVALID;
+    }
+    if (st->kind == 0 && (st->sample_size == 0 || st->sample_size > 11)) {
+        // rand::seq::index::sample switches from Floyd's to the in-place algorithm for amount > 11 on
+        // short lists; only the Floyd branch is implemented on the device.
+        set_error("lctp_solve_stage: greedy sample size %llu unsupported on device (1..=11)",
+                  (unsigned long long)st->sample_size);
+        return LCTP_E_CAPACITY;
+    }
+    if (st->kind == 1 && (!(st->init_prob > 0.0 && st->init_prob <= 1.0) || st->anneal_steps == 0)) {
+        set_error("lctp_solve_stage: invalid annealing parameters");
+        return LCTP_E_INVALID;
+    }
+    const size_t n = (size_t)worker_off[n_workers];
+    if (n == 0 || n_workers > 0xFFFFFFF0ull) { set_error("lctp_solve_stage: empty stage"); return LCTP_E_INVALID; }
+    const uint32_t p = L.p;
+
+    // genotype tuples by position + candidate capacity bound: A(g) <= sum_k #alns(h_k) + R
+    std::vector<uint32_t> tuples(n * p);
+    uint64_t cap64 = 0;
+    for (size_t j = 0; j < n; j++) {
+        const uint64_t g = worker_ixs[j];
+        if (g >= L.G) { set_error("lctp_solve_stage: genotype id %llu out of range", (unsigned long long)g); return LCTP_E_INVALID; }
+        genotype_tuple(L.H, p, h->gt_tuples_host.empty() ? nullptr : h->gt_tuples_host.data(), g, &tuples[j * p]);
+        uint64_t a = L.R;
+        for (uint32_t k = 0; k < p; k++) a += h->hap_alns[tuples[j * p + k]];
+        cap64 = std::max(cap64, a);
+    }
+    if (cap64 > 0x7FFFFFF0ull) { set_error("lctp_solve_stage: candidate capacity overflow"); return LCTP_E_CAPACITY; }
+    const uint32_t cap = (uint32_t)cap64;
+    const uint32_t Wmax = 2 + p * h->max_n_windows;
+
+    StageParams P;
+    P.kind = st->kind; P.attempts = st->attempts; P.best_start = st->best_start; P.sample_size = (uint32_t)st->sample_size;
+    P.plato_size = st->plato_size; P.anneal_steps = st->anneal_steps;
+    P.max_iter = std::max<uint64_t>(100000, st->plato_size * 100);
+    P.ln_init_prob = st->kind == 1 ? std::log(st->init_prob) : 0.0;
+    P.n_workers = (uint32_t)n_workers; P.cap = cap; P.Wmax = Wmax;
+    const bool want_counts = counts != nullptr && counts_off != nullptr;
+    P.want_counts = want_counts ? 1 : 0;
+    P.slab_bytes = slab_layout(cap, L.R, nullptr, nullptr);
+
+    const size_t smem = (size_t)WARPS_PER_CTA * Wmax * 16;
+    if (smem > ctx->smem_optin) { set_error("lctp_solve_stage: %zu bytes of shared memory needed", smem); return LCTP_E_CAPACITY; }
+    LCTP_CUDA_CHECK(cudaFuncSetAttribute(k_solve_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    LCTP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_stage, WARPS_PER_CTA * 32, smem));
+    if (occ < 1) occ = 1;
+    uint32_t resident_warps = (uint32_t)ctx->sm_count * occ * WARPS_PER_CTA;
+    if (ctx->max_resident_workers && ctx->max_resident_workers < resident_warps) resident_warps = ctx->max_resident_workers;
+    uint32_t warps = (uint32_t)std::min<size_t>(n_workers, resident_warps);
+    const uint32_t grid = (warps + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+
+    int rc;
+    if ((rc = ctx->scratch.ensure((size_t)grid * WARPS_PER_CTA * P.slab_bytes))) return rc;
+    if ((rc = ctx->d_worker_ixs.ensure(n))) return rc;
+    if ((rc = ctx->d_worker_off.ensure(n_workers + 1))) return rc;
+    if ((rc = ctx->d_rng.ensure(n_workers * 4))) return rc;
+    if ((rc = ctx->d_tuples.ensure(n * p))) return rc;
+    if ((rc = ctx->d_lik_mean.ensure(n))) return rc;
+    if ((rc = ctx->d_lik_var.ensure(n))) return rc;
+    if ((rc = ctx->d_liks.ensure(n * st->attempts))) return rc;
+    if ((rc = ctx->d_nalns.ensure(n))) return rc;
+    if ((rc = ctx->d_iters.ensure(n))) return rc;
+    if ((rc = ctx->d_flags.ensure(2))) return rc;
+    if (want_counts) { if ((rc = ctx->d_counts.ensure(n * (size_t)cap))) return rc; }
+
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_worker_ixs.p, worker_ixs, n * 8, cudaMemcpyHostToDevice, s));
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_worker_off.p, worker_off, (n_workers + 1) * 8, cudaMemcpyHostToDevice, s));
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_rng.p, worker_rng, n_workers * 32, cudaMemcpyHostToDevice, s));
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tuples.p, tuples.data(), n * p * 4, cudaMemcpyHostToDevice, s));
+    LCTP_CUDA_CHECK(cudaMemsetAsync(ctx->d_flags.p, 0, 2 * sizeof(int), s));
+
+    k_solve_stage<<<grid, WARPS_PER_CTA * 32, smem, s>>>(
+        L, P, ctx->d_worker_ixs.p, ctx->d_worker_off.p, ctx->d_tuples.p, ctx->d_rng.p, ctx->d_lik_mean.p,
+        ctx->d_lik_var.p, ctx->d_liks.p, ctx->d_nalns.p, ctx->d_iters.p, want_counts ? ctx->d_counts.p : nullptr,
+        ctx->scratch.p, (unsigned int *)(ctx->d_flags.p + 1), ctx->d_flags.p);
+    ctx->launches++;
+    LCTP_CUDA_CHECK(cudaGetLastError());
+
+    int flags[2] = {0, 0};
+    std::vector<uint64_t> nal(n);
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(lik_mean, ctx->d_lik_mean.p, n * 8, cudaMemcpyDeviceToHost, s));
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(lik_var, ctx->d_lik_var.p, n * 8, cudaMemcpyDeviceToHost, s));
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(worker_rng, ctx->d_rng.p, n_workers * 32, cudaMemcpyDeviceToHost, s));
+    if (liks) LCTP_CUDA_CHECK(cudaMemcpyAsync(liks, ctx->d_liks.p, n * st->attempts * 8, cudaMemcpyDeviceToHost, s));
+    if (n_alns_out || want_counts) LCTP_CUDA_CHECK(cudaMemcpyAsync(nal.data(), ctx->d_nalns.p, n * 8, cudaMemcpyDeviceToHost, s));
+    if (iters_out) LCTP_CUDA_CHECK(cudaMemcpyAsync(iters_out, ctx->d_iters.p, n * 8, cudaMemcpyDeviceToHost, s));
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(flags, ctx->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (flags[0]) { set_error("lctp_solve_stage: candidate slab overflow (cap=%u)", cap); return LCTP_E_CAPACITY; }
+    if (n_alns_out) std::copy(nal.begin(), nal.end(), n_alns_out);
+    if (want_counts) {
+        uint64_t off = 0;
+        for (size_t j = 0; j < n; j++) {
+            counts_off[j] = off;
+            if (off + nal[j] > counts_cap) { set_error("lctp_solve_stage: counts buffer too small"); return LCTP_E_CAPACITY; }
+            LCTP_CUDA_CHECK(cudaMemcpyAsync(counts + off, ctx->d_counts.p + j * (size_t)cap, nal[j] * 2,
+                                            cudaMemcpyDeviceToHost, s));
+            off += nal[j];
+        }
+        counts_off[n] = off;
+        LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    return LCTP_OK;
+}
+
+}  // namespace lctp

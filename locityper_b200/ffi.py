@@ -1,0 +1,134 @@
+"""ctypes binding of the lctp C ABI (include/lctp.h, locityper_b200/_lib/liblctp.so).
+
+The library is hand-written CUDA for sm_100a; there is NO CPU fallback: every compute entry point fails
+with LCTP_E_CUDA when no B200 is present, and `load()` raises if the shared library has not been built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "liblctp.so")
+CSRC = os.path.join(_HERE, "csrc")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "lctp.h")
+
+OK, E_INVALID, E_CUDA, E_CAPACITY = 0, -1, -2, -3
+MAX_OUT, MAX_STAGES = 50, 8
+
+
+class LctpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"lctp error {code}: {msg}")
+        self.code = code
+
+
+class DeviceCfg(C.Structure):
+    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("stream", C.c_void_p),
+                ("max_resident_workers", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class LocusC(C.Structure):
+    _fields_ = [
+        ("n_haps", C.c_uint32), ("n_reads", C.c_uint32), ("ploidy", C.c_uint32), ("is_paired", C.c_uint32),
+        ("n_genotypes", C.c_uint64),
+        ("gt_tuples", C.c_void_p), ("priors", C.c_void_p), ("unmapped_prob", C.c_void_p),
+        ("pa_off", C.c_void_p), ("pa_contig", C.c_void_p), ("pa_ln_prob", C.c_void_p),
+        ("pa_mid1", C.c_void_p), ("pa_mid2", C.c_void_p),
+        ("hap_len", C.c_void_p), ("hap_n_windows", C.c_void_p), ("hap_reg_start", C.c_void_p),
+        ("window", C.c_uint32), ("left_padding", C.c_uint32),
+        ("hap_pos_off", C.c_void_p), ("pos_weight", C.c_void_p), ("pos_gc", C.c_void_p),
+        ("depth_k", C.c_uint32), ("tweak", C.c_uint32),
+        ("depth_table", C.c_void_p),
+        ("prob_diff", C.c_double), ("lik_skew", C.c_double), ("min_weight", C.c_double),
+        ("filt_diff", C.c_double), ("prob_thresh", C.c_double),
+        ("dont_skip", C.c_uint32), ("out_bams", C.c_uint32),
+    ]
+
+
+class StageC(C.Structure):
+    _fields_ = [
+        ("kind", C.c_uint32), ("attempts", C.c_uint32), ("in_size", C.c_uint64),
+        ("best_start", C.c_uint32), ("_pad", C.c_uint32),
+        ("sample_size", C.c_uint64), ("plato_size", C.c_uint64), ("anneal_steps", C.c_uint64),
+        ("init_prob", C.c_double),
+    ]
+
+
+class ResultC(C.Structure):
+    _fields_ = [
+        ("n_out", C.c_uint64), ("gt_ix", C.c_uint64 * MAX_OUT), ("lik_mean", C.c_double * MAX_OUT),
+        ("lik_var", C.c_double * MAX_OUT), ("attempts", C.c_uint16 * MAX_OUT), ("ln_prob", C.c_double * MAX_OUT),
+        ("quality", C.c_double), ("total_reads", C.c_uint32), ("unexpl_reads", C.c_uint32),
+        ("warn_no_probable", C.c_uint32), ("warn_few_reads", C.c_uint32),
+        ("n_filtered", C.c_uint64), ("n_stage_in", C.c_uint64 * MAX_STAGES),
+        ("t_prefilter_s", C.c_double), ("t_stages_s", C.c_double),
+    ]
+
+
+# Every symbol include/lctp.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "lctp_version": (C.c_char_p, []),
+    "lctp_last_error": (C.c_char_p, []),
+    "lctp_sizeof_locus": (C.c_size_t, []),
+    "lctp_sizeof_stage": (C.c_size_t, []),
+    "lctp_sizeof_result": (C.c_size_t, []),
+    "lctp_init": (C.c_int, [_P, _P]),
+    "lctp_destroy": (None, [_P]),
+    "lctp_launch_count": (C.c_uint64, [_P]),
+    "lctp_sync": (C.c_int, [_P]),
+    "lctp_locus_upload": (C.c_int, [_P, _P, _P]),
+    "lctp_locus_free": (None, [_P]),
+    "lctp_best_aln_matrix": (C.c_int, [_P, _P]),
+    "lctp_prefilter_scores": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P]),
+    "lctp_prefilter": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.c_size_t, _P, _P]),
+    "lctp_truncate_ixs": (C.c_size_t, [_P, C.c_size_t, _P, C.c_double, C.c_size_t, C.c_size_t]),
+    "lctp_solve_stage": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P, _P, _P, _P, _P, _P, C.c_uint64, _P, _P]),
+    "lctp_rng_seed_from_u64": (None, [_P, C.c_uint64]),
+    "lctp_rng_jump": (None, [_P]),
+    "lctp_rng_long_jump": (None, [_P]),
+    "lctp_plan_stage": (C.c_size_t, [_P, _P, C.c_size_t, C.c_size_t, _P]),
+    "lctp_discard_improbable": (C.c_size_t, [_P, C.c_size_t, _P, _P, _P, C.c_double, C.c_size_t, C.c_size_t]),
+    "lctp_compare_two_likelihoods": (C.c_double, [C.c_double, C.c_double, C.c_uint16, C.c_double, C.c_double, C.c_uint16]),
+    "lctp_build_depth_table": (None, [_P, _P, C.c_int, _P, C.c_size_t, C.c_uint32, _P]),
+    "lctp_solve": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, _P]),
+    "lctp_result_json": (C.c_size_t, [_P, _P, _P, _P, C.c_size_t]),
+}
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the CUDA extension in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [HEADER]
+    stale = force or not os.path.exists(LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if stale:
+        subprocess.run(["make", "-C", CSRC, "-j4"] + (["-B"] if force else []), check=True,
+                       stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LctpError(E_CUDA, f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; "
+                                    "g.build()'`); the genotype-evaluation path has no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        assert lib.lctp_sizeof_locus() == C.sizeof(LocusC)
+        assert lib.lctp_sizeof_stage() == C.sizeof(StageC)
+        assert lib.lctp_sizeof_result() == C.sizeof(ResultC)
+        _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != OK:
+        raise LctpError(rc, load().lctp_last_error().decode())

@@ -1,0 +1,398 @@
+"""Host-side mirror of the reference's interface for the genotype-evaluation path.
+
+Same names, argument meaning and error behaviour as the reference (tprodanov/locityper v1.7.2):
+  * `Stage.parse` / `Scheme.parse`   <- Stage::parse / Scheme::parse, src/solvers/solve.rs:150-251
+  * solver parameters                <- Greedy / SimAnneal set_param, src/solvers/stoch.rs:130-138,251-258
+  * `solve(data, rng, threads)`      <- solve::solve, src/solvers/solve.rs:926-981
+  * `Genotyping.to_json()`           <- Genotyping::to_json, src/solvers/solve.rs:732-773
+Everything that computes runs in the CUDA library behind include/lctp.h; this module only marshals.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import ffi
+from .synth import Locus
+
+
+class InvalidInput(ValueError):
+    """crate::Error::InvalidInput"""
+
+
+def parse_pretty_usize(s: str) -> int:
+    """PrettyUsize::from_str (src/ext/fmt.rs:113-157): 5k, 2M, 1G, 10_000, inf."""
+    if s in ("inf", "Inf", "INF"):
+        return (1 << 64) - 1
+    if not s:
+        raise InvalidInput("Cannot parse an empty string into int")
+    last = s[-1]
+    if last in "GgBb":
+        n, mult = 0, 10 ** 9
+    elif last in "Mm":
+        n, mult = 0, 10 ** 6
+    elif last in "Kk":
+        n, mult = 0, 1000
+    elif last.isdigit() and last.isascii():
+        n, mult = int(last), 10
+    else:
+        raise InvalidInput(f"Cannot convert string `{s}` to int, unexpected last symbol '{last}'")
+    was_digit = mult == 10
+    for c in reversed(s[:-1]):
+        if c.isdigit() and c.isascii():
+            was_digit = True
+            n += mult * int(c)
+            mult *= 10
+        elif c in ",_":
+            was_digit = False
+        else:
+            raise InvalidInput(f"Cannot convert string `{s}` to int, unexpected symbol '{c}'")
+    if not was_digit:
+        raise InvalidInput(f"Cannot convert string `{s}` to int, unexpected first letter")
+    return n
+
+
+@dataclass
+class Stage:
+    """One stage of the solving scheme: SOLVER[:PARAM=VALUE,...]."""
+
+    kind: str = "greedy"
+    attempts: int = 20                 # Stage::parse defaults, solve.rs:173-174
+    in_size: int = 1000
+    best_start: bool = True            # Greedy::default, stoch.rs:45-53
+    sample_size: int = 10
+    plato_size: Optional[int] = None   # Greedy 100 / SimAnneal 10000
+    anneal_steps: int = 20000          # SimAnneal::default, stoch.rs:161-169
+    init_prob: float = 0.5
+
+    @staticmethod
+    def parse(ix: int, s: str) -> "Stage":
+        name, _, params = s.partition(":")
+        if name == "greedy":
+            st = Stage("greedy")
+        elif name in ("anneal", "simanneal", "annealing", "simannealing"):
+            st = Stage("anneal")
+        elif name in ("highs", "gurobi"):
+            raise RuntimeError(f"{name} solver is disabled (ILP solvers are feature-gated off in the reference "
+                               "default build and are not part of the device path)")
+        else:
+            raise InvalidInput(f"Unknown solver {name!r}")
+        if params:
+            for kv in params.split(","):
+                if "=" not in kv:
+                    raise InvalidInput(f"Could not parse solver definition `{s}`")
+                key, val = kv.split("=", 1)
+                try:
+                    if key in ("i", "input", "in-size"):
+                        st.in_size = parse_pretty_usize(val)
+                    elif key in ("a", "attempts"):
+                        st.attempts = int(val)
+                        if not 0 <= st.attempts <= 65535:
+                            raise ValueError
+                    else:
+                        st._set_param(key, val, s)
+                except (ValueError, InvalidInput) as e:
+                    if isinstance(e, InvalidInput) and "Invalid value" in str(e):
+                        raise
+                    raise InvalidInput(f"Could not parse `{kv}` in solver definition `{s}`") from e
+        if st.attempts <= 0:
+            raise InvalidInput(f"At least one attempt is required for each stage (`{s}`)")
+        if st.in_size <= 0:
+            raise InvalidInput(f"At least one input genotype is required for each stage (`{s}`)")
+        return st
+
+    def _set_param(self, key: str, val: str, s: str) -> None:
+        k = key.lower()
+        if self.kind == "greedy":
+            if k in ("x0", "start"):
+                if val in ("b", "best"):
+                    self.best_start = True
+                elif val in ("r", "rand", "random"):
+                    self.best_start = False
+                else:
+                    raise InvalidInput(f"Invalid value of `{key}={val}` in `{s}`: Invalid start value {val}")
+            elif k in ("s", "sample"):
+                v = parse_pretty_usize(val)
+                if v == 0:
+                    raise InvalidInput(f"Invalid value of `{key}={val}` in `{s}`: Sample size must be positive")
+                self.sample_size = v
+            elif k in ("p", "plato"):
+                self.plato_size = parse_pretty_usize(val)
+            # unknown keys are logged and ignored by the reference (solve.rs:187-188)
+        else:
+            if k in ("n", "steps"):
+                v = parse_pretty_usize(val)
+                if v == 0:
+                    raise InvalidInput(f"Invalid value of `{key}={val}` in `{s}`: Number of annealing steps (0) must be positive")
+                self.anneal_steps = v
+            elif k in ("p", "plato"):
+                self.plato_size = parse_pretty_usize(val)
+            elif key in ("P", "prob", "init-prob") or k in ("prob", "init-prob"):
+                v = float(val)
+                if not (0.0 < v <= 1.0):
+                    raise InvalidInput(f"Invalid value of `{key}={val}` in `{s}`: Initial probability ({v}) must be within (0, 1]")
+                self.init_prob = v
+
+    def to_c(self) -> ffi.StageC:
+        c = ffi.StageC()
+        c.kind = 0 if self.kind == "greedy" else 1
+        c.attempts, c.in_size = self.attempts, self.in_size
+        c.best_start, c.sample_size = int(self.best_start), self.sample_size
+        c.plato_size = self.plato_size if self.plato_size is not None else (100 if c.kind == 0 else 10000)
+        c.anneal_steps, c.init_prob = self.anneal_steps, self.init_prob
+        return c
+
+
+@dataclass
+class Scheme:
+    stages: List[Stage] = field(default_factory=list)
+
+    @staticmethod
+    def default() -> "Scheme":
+        """DEFAULT_STAGES = "-S greedy:i=5k,a=1 -S anneal:i=20,a=20" (solve.rs:211-230)."""
+        return Scheme([Stage("greedy", attempts=1, in_size=5000), Stage("anneal", attempts=20, in_size=20)])
+
+    @staticmethod
+    def parse(solvers: Sequence[str]) -> "Scheme":
+        if not solvers:
+            return Scheme.default()
+        return Scheme([Stage.parse(i, s) for i, s in enumerate(solvers)])
+
+    def to_c(self):
+        return (ffi.StageC * len(self.stages))(*[s.to_c() for s in self.stages])
+
+
+def build_depth_table(nb_n, nb_p, is_paired, alt_cn, k_cols: int) -> np.ndarray:
+    """DistrCache::new (src/model/distr_cache.rs:61-75) through the C ABI (host code, no GPU needed)."""
+    nb_n = np.ascontiguousarray(nb_n, dtype=np.float64)
+    nb_p = np.ascontiguousarray(nb_p, dtype=np.float64)
+    alt = np.ascontiguousarray(alt_cn, dtype=np.float64)
+    out = np.empty((ffi_GC_BINS, int(k_cols)), dtype=np.float64)
+    ffi.load().lctp_build_depth_table(nb_n.ctypes.data, nb_p.ctypes.data, int(bool(is_paired)), alt.ctypes.data,
+                                      len(alt), int(k_cols), out.ctypes.data)
+    return out
+
+
+ffi_GC_BINS = 101
+
+
+def init_rng(seed: int) -> np.ndarray:
+    """ext::rand::init_rng (src/ext/rand.rs:6-22): xoshiro256++ seeded by SplitMix64."""
+    st = np.zeros(4, dtype=np.uint64)
+    ffi.load().lctp_rng_seed_from_u64(st.ctypes.data, C.c_uint64(seed))
+    return st
+
+
+def rng_long_jump(state: np.ndarray) -> None:
+    ffi.load().lctp_rng_long_jump(state.ctypes.data)
+
+
+def rng_jump(state: np.ndarray) -> None:
+    ffi.load().lctp_rng_jump(state.ctypes.data)
+
+
+class Context:
+    """lctp_ctx: one per GPU (Send, not Sync)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None, max_resident_workers: int = 0):
+        self.lib = ffi.load()
+        cfg = ffi.DeviceCfg(device=device, flags=0, stream=stream, max_resident_workers=max_resident_workers)
+        self._h = C.c_void_p()
+        ffi.check(self.lib.lctp_init(C.byref(cfg), C.byref(self._h)))
+
+    def launch_count(self) -> int:
+        return int(self.lib.lctp_launch_count(self._h))
+
+    def sync(self) -> None:
+        ffi.check(self.lib.lctp_sync(self._h))
+
+    def upload(self, loc: Locus) -> "DeviceLocus":
+        return DeviceLocus(self, loc)
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.lctp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def locus_to_c(loc: Locus, keep: list) -> ffi.LocusC:
+    def arr(a, dt):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    s = ffi.LocusC()
+    s.n_haps, s.n_reads, s.ploidy, s.is_paired = loc.n_haps, loc.n_reads, loc.ploidy, int(loc.is_paired)
+    s.n_genotypes = loc.n_genotypes
+    s.gt_tuples = arr(loc.gt_tuples, np.uint32)
+    s.priors = arr(loc.priors, np.float64)
+    s.unmapped_prob = arr(loc.unmapped_prob, np.float64)
+    s.pa_off = arr(loc.pa_off, np.uint64)
+    s.pa_contig = arr(loc.pa_contig, np.uint32)
+    s.pa_ln_prob = arr(loc.pa_ln_prob, np.float64)
+    s.pa_mid1 = arr(loc.pa_mid1, np.uint32)
+    s.pa_mid2 = arr(loc.pa_mid2, np.uint32)
+    s.hap_len = arr(loc.hap_len, np.uint32)
+    s.hap_n_windows = arr(loc.hap_n_windows, np.uint32)
+    s.hap_reg_start = arr(loc.hap_reg_start, np.uint32)
+    s.window, s.left_padding = loc.window, loc.left_padding
+    s.hap_pos_off = arr(loc.hap_pos_off, np.uint64)
+    s.pos_weight = arr(loc.pos_weight, np.float64)
+    s.pos_gc = arr(loc.pos_gc, np.uint8)
+    if loc.depth_table is None:
+        raise InvalidInput("depth table missing: call synth.attach_depth_table(loc, genotype.build_depth_table)")
+    s.depth_k, s.tweak = loc.depth_k, loc.tweak
+    s.depth_table = arr(loc.depth_table, np.float64)
+    s.prob_diff, s.lik_skew, s.min_weight = loc.prob_diff, loc.lik_skew, loc.min_weight
+    s.filt_diff, s.prob_thresh = loc.filt_diff, loc.prob_thresh
+    s.dont_skip, s.out_bams = int(loc.dont_skip), loc.out_bams
+    return s
+
+
+@dataclass
+class Genotyping:
+    """solve::Genotyping (src/solvers/solve.rs:568-590)."""
+
+    gt_ix: np.ndarray
+    lik_mean: np.ndarray
+    lik_var: np.ndarray
+    attempts: np.ndarray
+    ln_prob: np.ndarray
+    quality: float
+    total_reads: int
+    unexpl_reads: int
+    warnings: List[str]
+    n_filtered: int
+    n_stage_in: List[int]
+    t_prefilter_s: float
+    t_stages_s: float
+    json_text: str = ""
+
+    def to_json(self) -> dict:
+        return json.loads(self.json_text)
+
+
+class DeviceLocus:
+    """lctp_locus_h: a locus resident in HBM."""
+
+    def __init__(self, ctx: Context, loc: Locus):
+        self.ctx, self.loc, self.lib = ctx, loc, ctx.lib
+        self._keep: list = []
+        self.c = locus_to_c(loc, self._keep)
+        self._h = C.c_void_p()
+        ffi.check(self.lib.lctp_locus_upload(ctx._h, C.byref(self.c), C.byref(self._h)))
+
+    def free(self) -> None:
+        if self._h:
+            self.lib.lctp_locus_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def best_aln_matrix(self) -> np.ndarray:
+        M = np.empty((self.loc.n_haps, self.loc.n_reads), dtype=np.float64)
+        ffi.check(self.lib.lctp_best_aln_matrix(self._h, M.ctypes.data))
+        return M
+
+    def prefilter_scores(self, g_begin: int = 0, g_end: Optional[int] = None, fetch: bool = True):
+        g_end = self.loc.n_genotypes if g_end is None else g_end
+        out = np.empty(g_end - g_begin, dtype=np.float64) if fetch else None
+        ffi.check(self.lib.lctp_prefilter_scores(self._h, g_begin, g_end, None if out is None else out.ctypes.data))
+        return out
+
+    def prefilter(self, min_size: int, threads: int, ixs: Optional[np.ndarray] = None, want_scores: bool = False):
+        """run_filter: returns the sorted survivors (and all scores if requested)."""
+        G = self.loc.n_genotypes
+        ixs = np.arange(G, dtype=np.uint64) if ixs is None else np.array(ixs, dtype=np.uint64)
+        n_out = C.c_size_t(0)
+        scores = np.empty(G, dtype=np.float64) if want_scores else None
+        ffi.check(self.lib.lctp_prefilter(self._h, ixs.ctypes.data, len(ixs), min_size, threads, C.byref(n_out),
+                                          None if scores is None else scores.ctypes.data))
+        surv = ixs[:n_out.value].copy()
+        return (surv, scores) if want_scores else surv
+
+    def solve_stage(self, stage: Stage, worker_ixs, worker_off, worker_rng: np.ndarray, want_liks: bool = True,
+                    want_counts: bool = False, counts_cap: int = 0):
+        worker_ixs = np.ascontiguousarray(worker_ixs, dtype=np.uint64)
+        worker_off = np.ascontiguousarray(worker_off, dtype=np.uint64)
+        assert worker_rng.dtype == np.uint64 and worker_rng.flags.c_contiguous
+        n_workers, n = len(worker_off) - 1, int(worker_off[-1])
+        st = stage.to_c()
+        lik_mean, lik_var = np.empty(n), np.empty(n)
+        liks = np.empty((n, stage.attempts)) if want_liks else None
+        n_alns, iters = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+        counts_off = counts = None
+        if want_counts:
+            counts_off = np.zeros(n + 1, dtype=np.uint64)
+            counts = np.zeros(max(1, counts_cap), dtype=np.uint16)
+        p = lambda a: None if a is None else a.ctypes.data
+        ffi.check(self.lib.lctp_solve_stage(self._h, C.byref(st), p(worker_ixs), p(worker_off), n_workers,
+                                            p(worker_rng), p(lik_mean), p(lik_var), p(liks), p(counts_off), p(counts),
+                                            int(counts_cap), p(n_alns), p(iters)))
+        return dict(lik_mean=lik_mean, lik_var=lik_var, liks=liks, n_alns=n_alns, iters=iters,
+                    counts_off=counts_off, counts=counts)
+
+    def solve(self, scheme: Scheme, threads: int, rng: np.ndarray, hap_names: Optional[Sequence[str]] = None) -> Genotyping:
+        """solve::solve: prefilter -> stages -> result.  `rng` (u64[4], the locus stream) is updated in place."""
+        st = scheme.to_c()
+        res = ffi.ResultC()
+        ffi.check(self.lib.lctp_solve(self._h, st, len(scheme.stages), threads, rng.ctypes.data, C.byref(res)))
+        n = int(res.n_out)
+        names = list(hap_names) if hap_names is not None else [f"hap{i}" for i in range(self.loc.n_haps)]
+        cn = (C.c_char_p * len(names))(*[s.encode() for s in names])
+        need = self.lib.lctp_result_json(C.byref(res), C.byref(self.c), cn, None, 0)
+        buf = C.create_string_buffer(need + 1)
+        self.lib.lctp_result_json(C.byref(res), C.byref(self.c), cn, buf, need + 1)
+        warnings = []
+        if res.warn_no_probable:
+            warnings.append("NoProbableGenotype")
+        if res.warn_few_reads:
+            warnings.append(f"FewReads({res.total_reads})")
+        return Genotyping(
+            gt_ix=np.array(res.gt_ix[:n], dtype=np.uint64), lik_mean=np.array(res.lik_mean[:n]),
+            lik_var=np.array(res.lik_var[:n]), attempts=np.array(res.attempts[:n]),
+            ln_prob=np.array(res.ln_prob[:n]), quality=res.quality, total_reads=res.total_reads,
+            unexpl_reads=res.unexpl_reads, warnings=warnings, n_filtered=int(res.n_filtered),
+            n_stage_in=[int(x) for x in res.n_stage_in], t_prefilter_s=res.t_prefilter_s,
+            t_stages_s=res.t_stages_s, json_text=buf.value.decode())
+
+
+def truncate_ixs(ixs, scores, filt_diff: float, min_size: int, threads: int) -> np.ndarray:
+    ixs = np.array(ixs, dtype=np.uint64)
+    scores = np.ascontiguousarray(scores, dtype=np.float64)
+    m = ffi.load().lctp_truncate_ixs(ixs.ctypes.data, len(ixs), scores.ctypes.data, filt_diff, min_size, threads)
+    return ixs[:m].copy()
+
+
+def plan_stage(rng: np.ndarray, ixs: np.ndarray, threads: int):
+    """MainWorker::run :1049-1063: shuffle (in place) + contiguous partition. Returns worker_off."""
+    assert ixs.dtype == np.uint64 and ixs.flags.c_contiguous
+    off = np.zeros(threads + 1, dtype=np.uint64)
+    nw = ffi.load().lctp_plan_stage(rng.ctypes.data, ixs.ctypes.data, len(ixs), threads, off.ctypes.data)
+    return off[:nw + 1].copy()
+
+
+def discard_improbable(ixs, lik_mean, lik_var, attempts, prob_thresh: float, out_size: int, threads: int) -> np.ndarray:
+    ixs = np.array(ixs, dtype=np.uint64)
+    lm = np.ascontiguousarray(lik_mean, dtype=np.float64)
+    lv = np.ascontiguousarray(lik_var, dtype=np.float64)
+    at = np.ascontiguousarray(attempts, dtype=np.uint16)
+    m = ffi.load().lctp_discard_improbable(ixs.ctypes.data, len(ixs), lm.ctypes.data, lv.ctypes.data, at.ctypes.data,
+                                           prob_thresh, out_size, threads)
+    return ixs[:m].copy()
