@@ -1,0 +1,447 @@
+#!/usr/bin/env python
+"""bench.py -- genotypes scored/sec (prefilter + solver) on BASELINE.json's configs.
+
+  python bench.py --gpus N --steps K --warmup W            (ours: sm_100a CUDA through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the reference's algorithm on host cores)
+
+A *step* is one pass of the hot path (prefilter + greedy stage) over one batch of synthetic loci of the
+shape BASELINE.json quotes the metric on: configs[1] = "HLA class I panel (HLA-A/B/C) ~300 haplotypes each,
+45k diploid genotypes per locus, 30x short reads, prefilter + greedy on 1 B200"  ->  3 loci per step per GPU.
+N > 1 (torchrun, one rank per GPU): loci are independent (src/command/genotype.rs:1331-1351), so every rank
+processes its own 3 loci (weak scaling, no data-path collective); the calls are all-gathered over NCCL at the
+end.  `--mode shard` runs the KIR-scale configs[3] instead: one locus whose genotype list is partitioned
+across ranks with an NCCL all-gather of per-GPU top-k (score, id) candidates.
+
+The reference (Rust) cannot be built in this image, so the CPU arm is the oracle port (oracle/, plain C,
+pthreads) on all host cores: `cpu_baseline.kind = "port"`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "genotypes scored/sec (prefilter+solver)"
+UNIT = "genotypes/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="loci", choices=["loci", "shard"])
+    ap.add_argument("--config", default="C2", help="shape of the loci (C1..C5); C2 is the metric's config")
+    ap.add_argument("--loci", type=int, default=3, help="loci per step per GPU")
+    ap.add_argument("--threads", type=int, default=0,
+                    help="reference -@ T = number of logical workers / RNG streams (0 = auto: one per survivor "
+                         "slot that fits the GPU, same T for the CPU arm)")
+    ap.add_argument("--scheme", nargs="*", default=["greedy:i=5k,a=1"],
+                    help="reference -S stages; configs[1] is 'prefilter + greedy'")
+    ap.add_argument("--seed", type=int, default=2001)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-loci", type=int, default=0, help="loci in the bounded CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def auto_threads(args) -> int:
+    # One logical worker per resident warp slot: 148 SMs x 32 warps.  Also a legal reference `-@` (u16).
+    return args.threads if args.threads > 0 else 4736
+
+
+def make_loci(args, rank: int, table_builder, n: int):
+    from locityper_b200 import synth
+    shape = synth.config_shape(args.config)
+    loci = []
+    for i in range(n):
+        seed = args.seed + 1000 * rank + i
+        loci.append(synth.make_locus(**shape, seed=seed, table_builder=table_builder))
+    return loci
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def pinned_locus(loc):
+    """Move every input array of the locus into pinned host memory (e2e copies start from pinned memory)."""
+    import torch
+    keep = []
+    for name in ("unmapped_prob", "pa_off", "pa_contig", "pa_ln_prob", "pa_mid1", "pa_mid2", "hap_len",
+                 "hap_n_windows", "hap_reg_start", "hap_pos_off", "pos_weight", "pos_gc", "depth_table"):
+        a = np.ascontiguousarray(getattr(loc, name))
+        t = torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).pin_memory()
+        keep.append(t)
+        setattr(loc, name, t.numpy().view(a.dtype).reshape(a.shape))
+    loc.meta["_pinned"] = keep
+    return loc
+
+
+def input_bytes(loc) -> int:
+    return int(sum(np.asarray(getattr(loc, n)).nbytes for n in (
+        "unmapped_prob", "pa_off", "pa_contig", "pa_ln_prob", "pa_mid1", "pa_mid2", "hap_len", "hap_n_windows",
+        "hap_reg_start", "hap_pos_off", "pos_weight", "pos_gc", "depth_table")))
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+
+def cpu_run(args, loci, T, os_threads):
+    """One pass of the oracle port over `loci`; returns (genotypes, seconds)."""
+    from oracle import lcto_py as O
+    scheme = []
+    from locityper_b200.genotype import Scheme
+    for st in Scheme.parse(args.scheme).stages:
+        scheme.append(O.Stage(st.kind, attempts=st.attempts, in_size=st.in_size, best_start=st.best_start,
+                              sample_size=st.sample_size, plato_size=st.plato_size, anneal_steps=st.anneal_steps,
+                              init_prob=st.init_prob))
+    ols = [O.OracleLocus(l) for l in loci]
+    t0 = time.perf_counter()
+    g = 0
+    for i, ol in enumerate(ols):
+        rng = O.Rng.from_seed(args.seed + i)
+        O.solve(ol, scheme, T, rng, os_threads=os_threads)
+        g += ol.loc.n_genotypes
+    return g, time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle import lcto_py as O
+    O.lib()
+    cores = os.cpu_count() or 1
+    T = auto_threads(args)
+    # table builder: the oracle's own (the CPU arm must not need the CUDA library)
+    loci = make_loci(args, 0, O.build_depth_table, args.loci)
+    for _ in range(args.warmup):
+        cpu_run(args, loci[:1], T, cores)
+    times, g = [], 0
+    for _ in range(args.steps):
+        g, dt = cpu_run(args, loci, T, cores)
+        times.append(dt)
+    total = sum(times)
+    value = g * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, T, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.loci} loci x {args.steps} steps, T={T} logical workers on {cores} pthreads "
+                                   "(prefilter single-threaded like the reference)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is Rust and cannot be built here (no cargo); this is the plain-C oracle port of the same path",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, T, world):
+    from locityper_b200 import synth
+    sh = synth.config_shape(args.config)
+    G = sh["n_haps"] * (sh["n_haps"] + 1) // 2
+    return {"workload": f"BASELINE configs[1]: {args.loci} loci/step/GPU x H={sh['n_haps']} haplotypes "
+                        f"(G={G} diploid genotypes), R={sh['n_reads']} read pairs, {sh['locus_len']} bp, "
+                        f"{sh['tech']}; scheme {' '.join('-S ' + s for s in args.scheme)}",
+            "shape": args.config, "loci_per_step_per_gpu": args.loci, "threads_T": T, "mode": args.mode,
+            "parallelism": f"loci x{world}" if args.mode == "loci" else f"genotype-shard x{world}",
+            "l2": "per-step working set (per-warp candidate slabs, ~0.7 GB) exceeds the 126 MB L2; "
+                  "an L2 flush buffer is also written between timed steps"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from locityper_b200 import genotype
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the genotype-evaluation path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream(dev)
+    ctx = genotype.Context(device=local, stream=stream.cuda_stream)
+    T = auto_threads(args)
+    scheme = genotype.Scheme.parse(args.scheme)
+
+    if args.mode == "shard":
+        return run_shard(args, ctx, scheme, T, rank, world, dev)
+
+    loci = [pinned_locus(l) for l in make_loci(args, rank, genotype.build_depth_table, args.loci)]
+    G_step = sum(l.n_genotypes for l in loci)
+    h2d = sum(input_bytes(l) for l in loci)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_resident(dls):
+        calls = []
+        for i, dl in enumerate(dls):
+            rng = genotype.init_rng(args.seed + i)
+            calls.append(dl.solve(scheme, T, rng))
+        return calls
+
+    def step_e2e():
+        calls = []
+        for i, loc in enumerate(loci):
+            dl = ctx.upload(loc)              # H2D of the whole flat locus from pinned host memory
+            rng = genotype.init_rng(args.seed + i)
+            calls.append(dl.solve(scheme, T, rng))   # D2H of (lik_mean, lik_var, RNG states, calls)
+            dl.free()
+        return calls
+
+    # ---- value: inputs resident in HBM when the timed region starts
+    dls = [ctx.upload(l) for l in loci]
+    for _ in range(args.warmup):
+        step_resident(dls)
+    ctx.stats(reset=True)
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    calls = None
+    for k in range(args.steps):
+        flush.zero_()                         # L2 flush, outside the event pair
+        ev[k][0].record(stream)
+        calls = step_resident(dls)
+        ev[k][1].record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    st = ctx.stats(reset=True)
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    t_total = torch.tensor([sum(ms_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+    ms_total = float(t_total.item())
+    value = world * G_step * args.steps / (ms_total / 1e3)
+    for dl in dls:
+        dl.free()
+
+    # ---- e2e: host buffers in, host results out, through the public API, copies inside the timed region
+    for _ in range(max(1, args.warmup - 1)):
+        step_e2e()
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()
+        ev2[k][0].record(stream)
+        calls = step_e2e()
+        ev2[k][1].record(stream)
+    barrier()
+    t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * G_step * args.steps / (float(t2.item()) / 1e3)
+    n_surv = sum(c.n_filtered for c in calls)
+    d2h = int(n_surv * 16 + min(T, n_surv) * 32 + n_surv * 16 + len(loci) * 2000 * 8 * 2)
+
+    # all ranks exchange their calls (tiny) -- the only cross-GPU traffic of the loci mode
+    my = torch.tensor([int(c.gt_ix[0]) for c in calls], dtype=torch.int64, device=dev)
+    if world > 1:
+        allc = [torch.empty_like(my) for _ in range(world)]
+        dist.all_gather(allc, my)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, T, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+        }
+        line.update(rooflines(st, loci, args, peak, peak_src))
+        line["calls_vs_truth"] = [[list(l.genotype_tuple(int(c.gt_ix[0]))), list(l.truth)] for l, c in zip(loci, calls)]
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args, loci, T)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def rooflines(st, loci, args, peak, peak_src):
+    """roofline of the dominant kernel (the solver stage) + the prefilter kernel, from device-side timings."""
+    loc = loci[0]
+    R, p = loc.n_reads, loc.ploidy
+    out = {}
+    # solver stage kernel: algorithmic bytes = build + tweak + iterations (DESIGN.md section "Kernels")
+    if st["stage_launches"]:
+        g, A, it = st["stage_genotypes"], st["stage_alns"], st["stage_iters"]
+        cbar = A / max(1, g * R)
+        bytes_alg = g * R * p * 24 + A * 17 + st["stage_attempts"] * (A / max(1, g)) * 16 + it * 10 * max(cbar - 1, 0.5) * 80
+        sec = st["stage_ms"] / 1e3
+        ach = bytes_alg / sec / 1e9
+        out["roofline"] = {"kernel": "k_solve_stage", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                           "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                           "avg_launch_ms": st["stage_ms"] / st["stage_launches"],
+                           "note": "latency/issue-bound dependent chains (SURVEY 8d): HBM fraction is not the limiter; "
+                                   "see iters_per_s", "iters_per_s": it / sec, "genotypes_per_s": g / sec}
+    if st["prefilter_launches"]:
+        gp = st["prefilter_genotypes"]
+        sec = st["prefilter_ms"] / 1e3
+        bytes_alg = gp * (p * R * 8 + 8)
+        ops = gp * p * R
+        out["roofline_prefilter"] = {"kernel": "k_prefilter_pairs", "bound": "hbm", "achieved": bytes_alg / sec / 1e9,
+                                     "peak": peak, "unit": "GB/s", "frac": bytes_alg / sec / 1e9 / peak,
+                                     "traffic": None, "f64_ops_per_s": ops / sec,
+                                     "avg_launch_ms": st["prefilter_ms"] / st["prefilter_launches"]}
+    return out
+
+
+def cpu_baseline(args, loci, T):
+    cores = os.cpu_count() or 1
+    n = args.cpu_loci or len(loci)
+    cpu_run(args, loci[:1], T, cores)           # warm-up (page-in, thread pool)
+    g, dt, reps = 0, 0.0, 0
+    while dt < 10.0 and reps < 8:               # bounded sample: ~10-30 s of CPU work
+        gi, di = cpu_run(args, loci[:n], T, cores)
+        g += gi; dt += di; reps += 1
+    return {"value": g / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} loci x {reps} passes of the same workload, T={T} logical workers on {cores} pthreads"}
+
+
+def run_shard(args, ctx, scheme, T, rank, world, dev):
+    """configs[3]: one KIR-scale locus, genotype list partitioned across ranks."""
+    import torch
+    import torch.distributed as dist
+    from locityper_b200 import genotype
+    from locityper_b200 import dist as ldist
+    args.config = "C4" if args.config == "C2" else args.config
+    loc = pinned_locus(make_loci(args, 0, genotype.build_depth_table, 1)[0])   # same locus on every rank
+    stream = torch.cuda.current_stream(dev)
+    dl = ctx.upload(loc)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        ldist.solve_sharded(dl, scheme, T, genotype.init_rng(args.seed), rank, world, dev)
+    ctx.stats(reset=True)
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(dev.index or 0)
+    barrier()
+    sampler.start()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    res = None
+    for _ in range(args.steps):
+        res = ldist.solve_sharded(dl, scheme, T, genotype.init_rng(args.seed), rank, world, dev)
+    b.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    st = ctx.stats(reset=True)
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        ms = float(t.item())
+        line = {"metric": METRIC, "value": loc.n_genotypes * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, T, world), "clocks": clocks,
+                "gpu_launches": int(ctx.launch_count() - launches0),
+                "call": list(loc.genotype_tuple(int(res["gt_ix"][0]))), "truth": list(loc.truth)}
+        line.update(rooflines(st, [loc], args, peak, peak_src))
+        print(json.dumps(line), flush=True)
+    dl.free()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -118,6 +118,20 @@ typedef struct lctp_result {
     double   t_prefilter_s, t_stages_s;      /* host wall clock, diagnostics */
 } lctp_result;
 
+/* Device-side timing (CUDA events on the launch stream around each hot kernel) and work counters,
+ * accumulated since the last reset; bench.py derives the roofline numbers from these. */
+typedef struct lctp_stats {
+    double   prefilter_ms;         /* sum of prefilter kernel durations */
+    uint64_t prefilter_launches;
+    uint64_t prefilter_genotypes;  /* genotypes scored */
+    double   stage_ms;             /* sum of solver stage kernel durations */
+    uint64_t stage_launches;
+    uint64_t stage_genotypes;      /* genotypes solved */
+    uint64_t stage_attempts;       /* genotype-attempts solved */
+    uint64_t stage_iters;          /* greedy iterations + annealing steps executed */
+    uint64_t stage_alns;           /* candidate locations built (sum of A) */
+} lctp_stats;
+
 /* ---- library / context -------------------------------------------------------------------- */
 const char *lctp_version(void);
 const char *lctp_last_error(void);
@@ -129,6 +143,7 @@ void lctp_destroy(lctp_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py `gpu_launches`). */
 uint64_t lctp_launch_count(const lctp_ctx *ctx);
 int  lctp_sync(lctp_ctx *ctx);
+int  lctp_get_stats(lctp_ctx *ctx, lctp_stats *out, int reset);
 
 /* ---- locus upload (H2D once per locus; builds M = best_aln_matrix on the device, a1) ------- */
 int  lctp_locus_upload(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h **out);

@@ -80,6 +80,8 @@ struct lctp_ctx {
     size_t smem_optin = 0;
     uint32_t max_resident_workers = 0;
     uint64_t launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // prefilter start/stop, stage start/stop
+    lctp_stats stats = {};
     // stage scratch, grown on demand and reused across loci / stages
     lctp::DevBuf<unsigned char> scratch;
     lctp::DevBuf<uint64_t> d_worker_ixs, d_worker_off, d_rng;

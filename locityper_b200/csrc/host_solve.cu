@@ -316,6 +316,10 @@ int lctp_init(const lctp_device_cfg *cfg, lctp_ctx **out) {
         if (se != cudaSuccess) { set_error("lctp_init: cudaStreamCreate failed: %s", cudaGetErrorString(se)); delete ctx; return LCTP_E_CUDA; }
         ctx->own_stream = true;
     }
+    for (int i = 0; i < 4; i++) {
+        cudaError_t ee = cudaEventCreate(&ctx->ev[i]);
+        if (ee != cudaSuccess) { set_error("lctp_init: cudaEventCreate failed: %s", cudaGetErrorString(ee)); delete ctx; return LCTP_E_CUDA; }
+    }
     *out = ctx;
     return LCTP_OK;
 }
@@ -324,6 +328,7 @@ void lctp_destroy(lctp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -333,6 +338,13 @@ uint64_t lctp_launch_count(const lctp_ctx *ctx) { return ctx ? ctx->launches : 0
 int lctp_sync(lctp_ctx *ctx) {
     if (!ctx) { set_error("lctp_sync: NULL context"); return LCTP_E_INVALID; }
     LCTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return LCTP_OK;
+}
+
+int lctp_get_stats(lctp_ctx *ctx, lctp_stats *out, int reset) {
+    if (!ctx || !out) { set_error("lctp_get_stats: NULL argument"); return LCTP_E_INVALID; }
+    *out = ctx->stats;
+    if (reset) ctx->stats = lctp_stats{};
     return LCTP_OK;
 }
 
@@ -368,12 +380,19 @@ int lctp_prefilter_scores(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, dou
     if (!h) { set_error("lctp_prefilter_scores: NULL handle"); return LCTP_E_INVALID; }
     if (g_begin > g_end || g_end > h->dev.G) { set_error("lctp_prefilter_scores: bad range"); return LCTP_E_INVALID; }
     LCTP_CUDA_CHECK(cudaSetDevice(h->ctx->device));
+    LCTP_CUDA_CHECK(cudaEventRecord(h->ctx->ev[0], h->ctx->stream));
     int rc = launch_prefilter(h, g_begin, g_end, h->scores.p);
     if (rc) return rc;
+    LCTP_CUDA_CHECK(cudaEventRecord(h->ctx->ev[1], h->ctx->stream));
     if (scores_out && g_end > g_begin)
         LCTP_CUDA_CHECK(cudaMemcpyAsync(scores_out, h->scores.p + g_begin, (g_end - g_begin) * 8,
                                         cudaMemcpyDeviceToHost, h->ctx->stream));
     LCTP_CUDA_CHECK(cudaStreamSynchronize(h->ctx->stream));
+    float ms = 0.f;
+    LCTP_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ctx->ev[0], h->ctx->ev[1]));
+    h->ctx->stats.prefilter_ms += ms;
+    h->ctx->stats.prefilter_launches += 1;
+    h->ctx->stats.prefilter_genotypes += g_end - g_begin;
     return LCTP_OK;
 }
 

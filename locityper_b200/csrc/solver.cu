@@ -23,7 +23,6 @@
 namespace lctp {
 
 static constexpr int WARPS_PER_CTA = 4;
-static constexpr uint32_t TRIVIAL_ROW = 0xFFFFFFFFu;
 static constexpr unsigned FULL = 0xFFFFFFFFu;
 
 struct StageParams {
@@ -108,43 +107,61 @@ __device__ __forceinline__ long long total_key(double v) {
     return b ^ (long long)(((unsigned long long)(b >> 63)) >> 1);
 }
 
+// Per-window state in shared memory, one 16-byte record per window so a window costs one LDS.128:
+//   x,y = weight (f64 bits), z = row offset (gc * depth_k) into the depth table, w = current read depth.
+// TRIVIAL windows (WindowDistr::TRIVIAL, src/model/distr_cache.rs:27-30) are stored as weight 0 on the
+// all-zero extra row of the device table, so 0*0 - 0*0 = +0.0 reproduces the reference's literal 0.0 with
+// no branch; a zero depth change gives w*t - w*t = +0.0 the same way.
 struct WarpShared {
-    uint32_t *depth;     // [Wmax]
-    double *wd_weight;   // [Wmax]
-    uint32_t *wd_row;    // [Wmax]  gc * depth_k, or TRIVIAL_ROW
+    uint4 *win;          // [Wmax]
+    uint32_t zero_row;   // offset of the all-zero row
 };
 
-// WindowDistr::ln_prob (src/model/distr_cache.rs:34-39)
-__device__ __forceinline__ double win_ln_prob(const WarpShared &ws, const double *__restrict__ table,
-                                              uint32_t w, uint32_t k) {
-    const uint32_t row = ws.wd_row[w];
-    if (row == TRIVIAL_ROW) return 0.0;
-    return __dmul_rn(ws.wd_weight[w], __ldg(table + row + k));
+__device__ __forceinline__ double win_weight(const uint4 &r) { return __hiloint2double((int)r.y, (int)r.x); }
+__device__ __forceinline__ uint4 make_win(double weight, uint32_t row, uint32_t depth) {
+    return make_uint4((uint32_t)__double2loint(weight), (uint32_t)__double2hiint(weight), row, depth);
 }
 
-// atomic_depth_lik_diff (src/model/assgn.rs:244-254)
+// WindowDistr::ln_prob (src/model/distr_cache.rs:34-39)
+__device__ __forceinline__ double win_ln_prob(const WarpShared &ws, const double *__restrict__ table, uint32_t w) {
+    const uint4 r = ws.win[w];
+    return __dmul_rn(win_weight(r), __ldg(table + r.z + r.w));
+}
+
+// atomic_depth_lik_diff (src/model/assgn.rs:244-254), branch-free
 __device__ __forceinline__ double atomic_diff(const WarpShared &ws, const double *__restrict__ table,
                                               uint32_t w, int change) {
-    if (change == 0) return 0.0;
-    const uint32_t row = ws.wd_row[w];
-    if (row == TRIVIAL_ROW) return 0.0;      // 0.0 - 0.0
-    const uint32_t od = ws.depth[w];
-    const uint32_t nd = (uint32_t)((int)od + change);
-    const double wt = ws.wd_weight[w];
-    return __dsub_rn(__dmul_rn(wt, __ldg(table + row + nd)), __dmul_rn(wt, __ldg(table + row + od)));
+    const uint4 r = ws.win[w];
+    const double wt = win_weight(r);
+    const double *row = table + r.z + r.w;
+    return __dsub_rn(__dmul_rn(wt, __ldg(row + change)), __dmul_rn(wt, __ldg(row)));
 }
 
-// depth_lik_diff (src/model/assgn.rs:259-284): ((a1 + a2) + a3) + a4
+// depth_lik_diff (src/model/assgn.rs:259-284): ((a1 + a2) + a3) + a4, window merging done with selects
 __device__ __forceinline__ double depth_lik_diff(const WarpShared &ws, const double *__restrict__ table,
                                                  uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4) {
-    int c1 = -1, c2, c3, c4;
-    if (w2 == w1) { c1 -= 1; c2 = 0; } else c2 = -1;
-    if (w3 == w1) { c1 += 1; c3 = 0; } else if (w3 == w2) { c2 += 1; c3 = 0; } else c3 = 1;
-    if (w4 == w1) { c1 += 1; c4 = 0; } else if (w4 == w2) { c2 += 1; c4 = 0; }
-    else if (w4 == w3) { c3 += 1; c4 = 0; } else c4 = 1;
+    const int e21 = w2 == w1, e31 = w3 == w1, e32 = (w3 == w2) & !e31;
+    const int e41 = w4 == w1, e42 = (w4 == w2) & !e41, e43 = (w4 == w3) & !e41 & !e42;
+    const int c1 = -1 - e21 + e31 + e41;
+    const int c2 = e21 ? 0 : -1 + e32 + e42;
+    const int c3 = (e31 | e32) ? 0 : 1 + e43;
+    const int c4 = (e41 | e42 | e43) ? 0 : 1;
     double s = __dadd_rn(atomic_diff(ws, table, w1, c1), atomic_diff(ws, table, w2, c2));
     s = __dadd_rn(s, atomic_diff(ws, table, w3, c3));
     return __dadd_rn(s, atomic_diff(ws, table, w4, c4));
+}
+
+// Monotone u64 key of an f64 (no NaNs on this path) and a REDUX-based "first lane holding the maximum".
+__device__ __forceinline__ unsigned long long ord_key(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
+}
+__device__ __forceinline__ int warp_argmax_first(unsigned long long key) {
+    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+    const uint32_t mh = __reduce_max_sync(FULL, hi);
+    const bool c = hi == mh;
+    const uint32_t ml = __reduce_max_sync(FULL, c ? lo : 0u);
+    return __ffs(__ballot_sync(FULL, c && lo == ml)) - 1;
 }
 
 // ------------------------------------------------------------------ a5: instance build ----------
@@ -282,7 +299,7 @@ __device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I,
         }
     }
     // (ii) window distributions: one bounded i32 draw per window, contigs in genotype order
-    if (lane < 2) { ws.wd_row[lane] = TRIVIAL_ROW; ws.wd_weight[lane] = 0.0; }
+    if (lane < 2) ws.win[lane] = make_win(0.0, ws.zero_row, 0);
     for (uint32_t k = 0; k < L.p; k++) {
         const uint32_t hap = I.haps[k];
         const uint32_t nwin = L.hap_n_windows[hap];
@@ -305,8 +322,8 @@ __device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I,
                 const double weight = L.pos_weight[pos_off + idx];
                 const uint32_t gc = L.pos_gc[pos_off + idx];
                 const uint32_t w = I.wshift[k] + i0 + lane;
-                if (weight < L.min_weight || weight < 1e-7) { ws.wd_row[w] = TRIVIAL_ROW; ws.wd_weight[w] = 0.0; }
-                else { ws.wd_row[w] = gc * L.depth_k; ws.wd_weight[w] = weight; }
+                if (weight < L.min_weight || weight < 1e-7) ws.win[w] = make_win(0.0, ws.zero_row, 0);
+                else ws.win[w] = make_win(weight, gc * L.depth_k, 0);
             }
         }
     }
@@ -323,7 +340,7 @@ __device__ __forceinline__ void seq_add(double &acc, double term, int count) {
 // init_mode 0: every read at candidate 0; 1: random_range(0..m) per non-trivial read (read order).
 __device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance &I, const WarpShared &ws,
                                 Xo &rng, int init_mode, double &aln_lik, double &depth_lik, int lane) {
-    for (uint32_t w = lane; w < I.W; w += 32) ws.depth[w] = 0;
+    for (uint32_t w = lane; w < I.W; w += 32) ws.win[w].w = 0;
     // assignments of non-trivial reads
     for (uint32_t i0 = 0; i0 < I.n_nt; i0 += 32) {
         const uint32_t i = i0 + lane;
@@ -357,8 +374,8 @@ __device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance
             const uint32_t ix = start + a;
             term = S.cand_lnprob[ix];
             const uint32_t w12 = S.cand_w[ix];
-            atomicAdd(&ws.depth[w12 & 0xFFFFu], 1u);
-            atomicAdd(&ws.depth[w12 >> 16], 1u);
+            atomicAdd(&ws.win[w12 & 0xFFFFu].w, 1u);
+            atomicAdd(&ws.win[w12 >> 16].w, 1u);
         }
         nt_base += __popc(ntmask);
         seq_add(al, term, (int)min(32u, L.R - r0));
@@ -368,7 +385,7 @@ __device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance
     double dl = 0.0;
     for (uint32_t w0 = 0; w0 < I.W; w0 += 32) {
         const uint32_t w = w0 + lane;
-        const double term = w < I.W ? win_ln_prob(ws, L.depth_table, w, ws.depth[w]) : 0.0;
+        const double term = w < I.W ? win_ln_prob(ws, L.depth_table, w) : 0.0;
         seq_add(dl, term, (int)min(32u, I.W - w0));
     }
     aln_lik = al;
@@ -415,10 +432,10 @@ __device__ __forceinline__ void apply_move(const Slab &S, const WarpShared &ws, 
     depth_lik = __dadd_rn(depth_lik, mv.dld);
     aln_lik = __dadd_rn(aln_lik, mv.dlp);
     if (lane == 0) {
-        ws.depth[mv.w34 & 0xFFFFu] += 1;
-        ws.depth[mv.w34 >> 16] += 1;
-        ws.depth[mv.w12 & 0xFFFFu] -= 1;
-        ws.depth[mv.w12 >> 16] -= 1;
+        ws.win[mv.w34 & 0xFFFFu].w += 1;
+        ws.win[mv.w34 >> 16].w += 1;
+        ws.win[mv.w12 & 0xFFFFu].w -= 1;
+        ws.win[mv.w12 >> 16].w -= 1;
         S.nt_info[idx].y = (n << 16) | new_a;
     }
     __syncwarp();
@@ -482,16 +499,12 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
             const uint32_t o_c = __shfl_xor_sync(FULL, b_c, 1);
             if (o_best > best || (o_best == best && o_c < b_c)) { best = o_best; b_c = o_c; }
         }
-        // assgn.rs:310
-        double s_improv = active ? __dmul_rn(L.aln_contrib, __dsub_rn(best, lp_old)) : -INFINITY;
-        uint32_t key = ((uint32_t)slot << 16) | b_c;
-#pragma unroll
-        for (int m = 2; m < 32; m <<= 1) {   // across reads: first (lowest slot) strictly-greater wins
-            const double o_s = shfl_xor_d(s_improv, m);
-            const uint32_t o_key = __shfl_xor_sync(FULL, key, m);
-            if (o_s > s_improv || (o_s == s_improv && (o_key >> 16) < (key >> 16))) { s_improv = o_s; key = o_key; }
-        }
-        if (s_improv > min_diff) {
+        // assgn.rs:310; across reads the first (lowest slot) strictly-greater improvement wins
+        const double s_improv = active ? __dmul_rn(L.aln_contrib, __dsub_rn(best, lp_old)) : -INFINITY;
+        const int wl0 = warp_argmax_first(ord_key(s_improv));
+        const double s_best = shfl_d(s_improv, wl0);
+        const uint32_t key = ((uint32_t)(wl0 >> 1) << 16) | __shfl_sync(FULL, b_c, wl0);
+        if (s_best > min_diff) {
             const int wl = (int)((key >> 16) * 2 + (key & 1u));   // lane that evaluated the winning candidate
             Move mv;
             mv.dld = shfl_d(b_dld, wl);
@@ -557,11 +570,9 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
               unsigned int *__restrict__ work_counter, int *__restrict__ err) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const size_t per_warp = (size_t)P.Wmax * 16;
     WarpShared ws;
-    ws.wd_weight = (double *)(smem + wib * per_warp);
-    ws.depth = (uint32_t *)(smem + wib * per_warp + (size_t)P.Wmax * 8);
-    ws.wd_row = ws.depth + P.Wmax;
+    ws.win = (uint4 *)smem + (size_t)wib * P.Wmax;
+    ws.zero_row = LCTP_GC_BINS * L.depth_k;
     const uint32_t slot = blockIdx.x * WARPS_PER_CTA + wib;
     Slab S;
     slab_layout(P.cap, L.R, scratch + (size_t)slot * P.slab_bytes, &S);
@@ -742,25 +753,37 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     LCTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tuples.p, tuples.data(), n * p * 4, cudaMemcpyHostToDevice, s));
     LCTP_CUDA_CHECK(cudaMemsetAsync(ctx->d_flags.p, 0, 2 * sizeof(int), s));
 
+    LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[2], s));
     k_solve_stage<<<grid, WARPS_PER_CTA * 32, smem, s>>>(
         L, P, ctx->d_worker_ixs.p, ctx->d_worker_off.p, ctx->d_tuples.p, ctx->d_rng.p, ctx->d_lik_mean.p,
         ctx->d_lik_var.p, ctx->d_liks.p, ctx->d_nalns.p, ctx->d_iters.p, want_counts ? ctx->d_counts.p : nullptr,
         ctx->scratch.p, (unsigned int *)(ctx->d_flags.p + 1), ctx->d_flags.p);
     ctx->launches++;
     LCTP_CUDA_CHECK(cudaGetLastError());
+    LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[3], s));
 
     int flags[2] = {0, 0};
-    std::vector<uint64_t> nal(n);
+    std::vector<uint64_t> nal(n), its(n);
     LCTP_CUDA_CHECK(cudaMemcpyAsync(lik_mean, ctx->d_lik_mean.p, n * 8, cudaMemcpyDeviceToHost, s));
     LCTP_CUDA_CHECK(cudaMemcpyAsync(lik_var, ctx->d_lik_var.p, n * 8, cudaMemcpyDeviceToHost, s));
     LCTP_CUDA_CHECK(cudaMemcpyAsync(worker_rng, ctx->d_rng.p, n_workers * 32, cudaMemcpyDeviceToHost, s));
     if (liks) LCTP_CUDA_CHECK(cudaMemcpyAsync(liks, ctx->d_liks.p, n * st->attempts * 8, cudaMemcpyDeviceToHost, s));
-    if (n_alns_out || want_counts) LCTP_CUDA_CHECK(cudaMemcpyAsync(nal.data(), ctx->d_nalns.p, n * 8, cudaMemcpyDeviceToHost, s));
-    if (iters_out) LCTP_CUDA_CHECK(cudaMemcpyAsync(iters_out, ctx->d_iters.p, n * 8, cudaMemcpyDeviceToHost, s));
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(nal.data(), ctx->d_nalns.p, n * 8, cudaMemcpyDeviceToHost, s));
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(its.data(), ctx->d_iters.p, n * 8, cudaMemcpyDeviceToHost, s));
     LCTP_CUDA_CHECK(cudaMemcpyAsync(flags, ctx->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
     if (flags[0]) { set_error("lctp_solve_stage: candidate slab overflow (cap=%u)", cap); return LCTP_E_CAPACITY; }
+    {
+        float ms = 0.f;
+        LCTP_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+        ctx->stats.stage_ms += ms;
+        ctx->stats.stage_launches += 1;
+        ctx->stats.stage_genotypes += n;
+        ctx->stats.stage_attempts += n * st->attempts;
+        for (size_t j = 0; j < n; j++) { ctx->stats.stage_iters += its[j]; ctx->stats.stage_alns += nal[j]; }
+    }
     if (n_alns_out) std::copy(nal.begin(), nal.end(), n_alns_out);
+    if (iters_out) std::copy(its.begin(), its.end(), iters_out);
     if (want_counts) {
         uint64_t off = 0;
         for (size_t j = 0; j < n; j++) {

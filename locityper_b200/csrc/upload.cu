@@ -159,7 +159,12 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h) {
     const uint64_t npos = in->hap_pos_off[H];
     if ((rc = h2d(h->pos_weight, in->pos_weight, npos, s))) return rc;
     if ((rc = h2d(h->pos_gc, in->pos_gc, npos, s))) return rc;
-    if ((rc = h2d(h->depth_table, in->depth_table, (size_t)LCTP_GC_BINS * in->depth_k, s))) return rc;
+    {   // device table = [101][K] + one all-zero row used by TRIVIAL windows
+        const size_t nt = (size_t)LCTP_GC_BINS * in->depth_k;
+        if ((rc = h->depth_table.alloc(nt + in->depth_k))) return rc;
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(h->depth_table.p, in->depth_table, nt * 8, cudaMemcpyHostToDevice, s));
+        LCTP_CUDA_CHECK(cudaMemsetAsync(h->depth_table.p + nt, 0, (size_t)in->depth_k * 8, s));
+    }
     if (in->gt_tuples) {
         if ((rc = h2d(h->gt_tuples, in->gt_tuples, (size_t)in->n_genotypes * p, s))) return rc;
     }

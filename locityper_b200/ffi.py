@@ -67,6 +67,12 @@ class ResultC(C.Structure):
     ]
 
 
+class StatsC(C.Structure):
+    _fields_ = [("prefilter_ms", C.c_double), ("prefilter_launches", C.c_uint64), ("prefilter_genotypes", C.c_uint64),
+                ("stage_ms", C.c_double), ("stage_launches", C.c_uint64), ("stage_genotypes", C.c_uint64),
+                ("stage_attempts", C.c_uint64), ("stage_iters", C.c_uint64), ("stage_alns", C.c_uint64)]
+
+
 # Every symbol include/lctp.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -79,6 +85,7 @@ SYMBOLS = {
     "lctp_destroy": (None, [_P]),
     "lctp_launch_count": (C.c_uint64, [_P]),
     "lctp_sync": (C.c_int, [_P]),
+    "lctp_get_stats": (C.c_int, [_P, _P, C.c_int]),
     "lctp_locus_upload": (C.c_int, [_P, _P, _P]),
     "lctp_locus_free": (None, [_P]),
     "lctp_best_aln_matrix": (C.c_int, [_P, _P]),

@@ -210,6 +210,11 @@ class Context:
     def sync(self) -> None:
         ffi.check(self.lib.lctp_sync(self._h))
 
+    def stats(self, reset: bool = False) -> dict:
+        st = ffi.StatsC()
+        ffi.check(self.lib.lctp_get_stats(self._h, C.byref(st), int(reset)))
+        return {k: getattr(st, k) for k, _ in ffi.StatsC._fields_}
+
     def upload(self, loc: Locus) -> "DeviceLocus":
         return DeviceLocus(self, loc)
 
