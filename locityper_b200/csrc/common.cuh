@@ -87,7 +87,7 @@ struct lctp_ctx {
     lctp::DevBuf<uint64_t> d_worker_ixs, d_worker_off, d_rng;
     lctp::DevBuf<uint32_t> d_tuples;
     lctp::DevBuf<double> d_lik_mean, d_lik_var, d_liks;
-    lctp::DevBuf<uint64_t> d_nalns, d_iters;
+    lctp::DevBuf<uint64_t> d_nalns, d_iters, d_rng_mats;
     lctp::DevBuf<uint16_t> d_counts;
     lctp::DevBuf<int> d_flags;
     lctp::PinBuf<unsigned char> pin;

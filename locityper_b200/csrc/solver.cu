@@ -19,6 +19,7 @@
 
 #include <cmath>
 #include <algorithm>
+#include <cstring>
 
 namespace lctp {
 
@@ -40,6 +41,8 @@ struct Slab {
     uint2 *nt_info;        // [R]    (start, n << 16 | assgn) for every non-trivial read, in read order
     uint32_t *read_off;    // [R+1]
     uint8_t *cand_cix;     // [cap]
+    uint64_t *rng_buf;     // [RNG_FILL] pre-generated draws of the worker's stream
+    uint64_t *rng_blk;     // [32*4] block-start generator states of the current fill
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -58,24 +61,163 @@ __host__ __device__ inline size_t slab_layout(uint32_t cap, uint32_t R, unsigned
     o += align_up(((size_t)R + 1) * 4, 128);
     if (s) s->cand_cix = (uint8_t *)(base + o);
     o += align_up((size_t)cap, 128);
+    if (s) s->rng_buf = (uint64_t *)(base + o);
+    o += (size_t)2048 * 8;
+    if (s) s->rng_blk = (uint64_t *)(base + o);
+    o += 32 * 4 * 8;
     return o;
 }
 
-// ------------------------------------------------------------------ RNG (warp-uniform) -----------
+// ------------------------------------------------------------------ RNG stream -------------------
+//
+// The reference consumes ONE sequential xoshiro256++ stream per worker.  Stepping that generator
+// redundantly in all 32 lanes costs ~25 instructions per draw and was a third of the solver's issue
+// slots.  Instead the warp pre-generates the stream in bulk: xoshiro's state transition is linear over
+// GF(2), so lane l jumps its copy of the state ahead by l*RNG_C steps (256x256 bit-matrix products with
+// host-precomputed powers of the transition matrix) and then generates RNG_C consecutive outputs of the
+// SAME sequential stream into a per-warp buffer: 32 lanes produce 2048 exact draws per fill.  Consumers
+// read the buffer through a 32-entry register window with warp shuffles, in stream order, so the draw
+// sequence (including the data-dependent extra draw of biased bounded samples) is bit-identical to the
+// sequential generator.  At the end of a worker the exact state at the consumed position is rebuilt
+// from the owning lane's block-start state.
 
-struct Xo { uint64_t s0, s1, s2, s3; };
+static constexpr int RNG_C = 64;               // outputs per lane per fill
+static constexpr int RNG_FILL = 32 * RNG_C;    // 2048 draws per fill
+static constexpr int N_SETUP_MATS = 5;         // T^(C*2^k), k = 0..4
 
-__device__ __forceinline__ uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+__constant__ uint64_t c_refill_mat[256 * 4];   // T^(31*C): columns, 4 words each
+
+struct Gen { uint64_t s0, s1, s2, s3; };
+
+__device__ __host__ __forceinline__ uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
 
 // xoshiro256++ (rand_xoshiro::Xoshiro256PlusPlus, src/ext/rand.rs:3)
-__device__ __forceinline__ uint64_t xo_next(Xo &x) {
+__device__ __host__ __forceinline__ uint64_t gen_next(Gen &x) {
     const uint64_t r = rotl64(x.s0 + x.s3, 23) + x.s0;
     const uint64_t t = x.s1 << 17;
     x.s2 ^= x.s0; x.s3 ^= x.s1; x.s1 ^= x.s2; x.s0 ^= x.s3; x.s2 ^= t;
     x.s3 = rotl64(x.s3, 45);
     return r;
 }
-__device__ __forceinline__ uint32_t xo_u32(Xo &x) { return (uint32_t)(xo_next(x) >> 32); }
+
+// state <- M * state over GF(2); M given by its 256 columns (4 words each); `take` selects per lane
+// whether the product replaces the state (all lanes execute the same instruction stream).
+__device__ __forceinline__ void gen_mat_apply(Gen &g, const uint64_t *__restrict__ mat, bool take) {
+    uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 1
+    for (int w = 0; w < 4; w++) {
+        const uint64_t sw = w == 0 ? g.s0 : w == 1 ? g.s1 : w == 2 ? g.s2 : g.s3;
+#pragma unroll 8
+        for (int b = 0; b < 64; b++) {
+            const uint64_t m = 0ull - ((sw >> b) & 1ull);
+            const uint64_t *c = mat + (size_t)(w * 64 + b) * 4;
+            a0 ^= c[0] & m; a1 ^= c[1] & m; a2 ^= c[2] & m; a3 ^= c[3] & m;
+        }
+    }
+    if (take) { g.s0 = a0; g.s1 = a1; g.s2 = a2; g.s3 = a3; }
+}
+
+struct Xo {                // the worker's stream as seen by the solver code
+    Gen g;                 // this lane's generator (positioned at the end of its block after a fill)
+    uint32_t win_lo, win_hi;   // register window: buf[(pos & ~31) + lane]
+    uint32_t pos;          // draws consumed from the current fill
+    uint32_t wbase;        // stream position held by lane 0 of the register window
+    uint64_t *buf;         // [RNG_FILL] per-warp buffer (global, L2-resident)
+    uint64_t *blk;         // [32][4] block-start states of the current fill
+    int lane;
+};
+
+__device__ __forceinline__ void stream_fill(Xo &x) {
+    uint64_t *b = x.blk + x.lane * 4;
+    b[0] = x.g.s0; b[1] = x.g.s1; b[2] = x.g.s2; b[3] = x.g.s3;
+    uint64_t *o = x.buf + x.lane * RNG_C;
+#pragma unroll 4
+    for (int q = 0; q < RNG_C; q++) o[q] = gen_next(x.g);
+    x.pos = 0;
+    x.wbase = 0x80000000u;   // window invalid
+    __syncwarp();
+}
+
+// Start a stream from the scalar state st[4]: lane l jumps ahead by l*RNG_C (binary decomposition of l).
+__device__ void stream_begin(Xo &x, const uint64_t *__restrict__ st, const uint64_t *__restrict__ setup_mats) {
+    x.g.s0 = st[0]; x.g.s1 = st[1]; x.g.s2 = st[2]; x.g.s3 = st[3];
+    for (int k = 0; k < N_SETUP_MATS; k++) gen_mat_apply(x.g, setup_mats + (size_t)k * 1024, (x.lane >> k) & 1);
+    stream_fill(x);
+}
+
+__device__ __noinline__ void stream_refill(Xo &x) {
+    gen_mat_apply(x.g, c_refill_mat, true);    // end of own block -> start of own block in the next fill
+    stream_fill(x);
+}
+
+// Exact scalar state after the draws consumed so far (what the sequential generator would hold).
+__device__ void stream_end(Xo &x, uint64_t *__restrict__ out) {
+    __syncwarp();
+    Gen g;
+    int owner;
+    if (x.pos >= RNG_FILL) { owner = 31; g = x.g; }
+    else {
+        owner = x.pos / RNG_C;
+        const uint64_t *b = x.blk + owner * 4;
+        g.s0 = b[0]; g.s1 = b[1]; g.s2 = b[2]; g.s3 = b[3];
+        const int steps = x.pos - owner * RNG_C;
+        for (int q = 0; q < steps; q++) gen_next(g);
+    }
+    if (x.lane == 0) { out[0] = g.s0; out[1] = g.s1; out[2] = g.s2; out[3] = g.s3; }
+}
+
+// Make the register window cover stream positions [pos, pos + count); false = the fill ends first
+// (the caller then falls back to the one-draw-at-a-time path, which refills).
+__device__ __forceinline__ bool stream_cover(Xo &x, uint32_t count) {
+    if (x.pos + count > (uint32_t)RNG_FILL) return false;
+    if (x.pos - x.wbase + count > 32u) {          // also true when wbase is invalid (> pos)
+        x.wbase = x.pos;
+        const uint64_t v = x.buf[min(x.pos + (uint32_t)x.lane, (uint32_t)RNG_FILL - 1u)];
+        x.win_lo = (uint32_t)v; x.win_hi = (uint32_t)(v >> 32);
+    }
+    return true;
+}
+// After stream_cover(count): the (pos + rank)-th draw of the stream, for any per-lane rank < count.
+__device__ __forceinline__ uint32_t stream_peek_hi(const Xo &x, uint32_t rank) {
+    return __shfl_sync(0xFFFFFFFFu, x.win_hi, (x.pos - x.wbase + rank) & 31u);
+}
+__device__ __forceinline__ uint64_t stream_peek64(const Xo &x, uint32_t rank) {
+    const uint32_t src = (x.pos - x.wbase + rank) & 31u;
+    const uint32_t hi = __shfl_sync(0xFFFFFFFFu, x.win_hi, src);
+    const uint32_t lo = __shfl_sync(0xFFFFFFFFu, x.win_lo, src);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void stream_advance(Xo &x) {
+    if (x.pos == (uint32_t)RNG_FILL) stream_refill(x);
+    stream_cover(x, 1);
+}
+__device__ __forceinline__ uint32_t xo_u32(Xo &x) {   // next_u32 = upper half of next_u64
+    stream_advance(x);
+    const uint32_t r = stream_peek_hi(x, 0);
+    x.pos++;
+    return r;
+}
+__device__ __forceinline__ uint64_t xo_next(Xo &x) {
+    stream_advance(x);
+    const uint64_t r = stream_peek64(x, 0);
+    x.pos++;
+    return r;
+}
+
+// Lane-parallel bounded draws: lanes < count each want random_range(0..range) and lane k must receive
+// the k-th draw of the stream.  Succeeds (and consumes `count` draws) only when no lane lands in the
+// biased zone -- which would consume an extra draw and shift every later lane -- otherwise nothing is
+// consumed and the caller runs the sequential path.  P(fallback) ~ count * range / 2^32.
+__device__ __forceinline__ bool xo_below_parallel(Xo &x, uint32_t count, uint32_t range, uint32_t &res) {
+    if (!stream_cover(x, count)) return false;
+    const uint64_t m = (uint64_t)stream_peek_hi(x, (uint32_t)x.lane) * (uint64_t)range;
+    const bool biased = (uint32_t)x.lane < count && (uint32_t)m > 0u - range;
+    if (__any_sync(0xFFFFFFFFu, biased)) return false;
+    res = (uint32_t)(m >> 32);
+    x.pos += count;
+    return true;
+}
 
 // rand UniformInt::sample_single_inclusive with a u32 sample type: value in [0, range), range != 0.
 __device__ __forceinline__ uint32_t xo_below(Xo &x, uint32_t range) {
@@ -282,9 +424,14 @@ __device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I,
             const unsigned mask = __ballot_sync(FULL, has_parent);
             const int my_rank = __popc(mask & ((1u << lane) - 1u));
             const int n_draws = __popc(mask);
-            for (int q = 0; q < n_draws; q++) {
-                const uint64_t v = xo_next(rng);
-                if (q == my_rank) mine = v;
+            if (stream_cover(rng, (uint32_t)n_draws)) {
+                mine = stream_peek64(rng, (uint32_t)my_rank);
+                rng.pos += (uint32_t)n_draws;
+            } else {
+                for (int q = 0; q < n_draws; q++) {
+                    const uint64_t v = xo_next(rng);
+                    if (q == my_rank) mine = v;
+                }
             }
         }
         if (has_parent) {
@@ -308,13 +455,21 @@ __device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I,
         for (uint32_t i0 = 0; i0 < nwin; i0 += 32) {
             const uint32_t cnt = min(32u, nwin - i0);
             uint32_t my_wstart = 0;
-            for (uint32_t q = 0; q < cnt; q++) {
-                // generate_windows (windows.rs:478-486)
-                const uint32_t start = reg_start + (i0 + q) * L.window;
+            {
+                // generate_windows (windows.rs:478-486): random_range(-left..=right), one per window
+                const uint32_t start = reg_start + (i0 + min((uint32_t)lane, cnt - 1u)) * L.window;
                 const uint32_t end = start + L.window;
                 const uint32_t left = min(tweak, start), right = min(tweak, hlen - end);
-                const uint32_t rr = xo_below(rng, left + right + 1u);   // random_range(-left..=right) + left
-                if ((uint32_t)lane == q) my_wstart = start + rr - left;
+                uint32_t rr;
+                if (xo_below_parallel(rng, cnt, left + right + 1u, rr)) my_wstart = start + rr - left;
+                else {
+                    for (uint32_t q = 0; q < cnt; q++) {
+                        const uint32_t st_q = reg_start + (i0 + q) * L.window;
+                        const uint32_t l_q = min(tweak, st_q), r_q = min(tweak, hlen - (st_q + L.window));
+                        const uint32_t v = xo_below(rng, l_q + r_q + 1u);
+                        if ((uint32_t)lane == q) my_wstart = st_q + v - l_q;
+                    }
+                }
             }
             if ((uint32_t)lane < cnt) {
                 // neighb_info (windows.rs:439-445) + assgn.rs:144-148 + get_distribution (distr_cache.rs:83-92)
@@ -348,10 +503,13 @@ __device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance
         uint32_t a = 0;
         if (init_mode == 1) {
             const int cnt = (int)min(32u, I.n_nt - i0);
-            for (int q = 0; q < cnt; q++) {
-                const uint32_t m = __shfl_sync(FULL, info.y >> 16, q);
-                const uint32_t v = xo_below(rng, m);
-                if (lane == q) a = v;
+            const uint32_t my_m = max(info.y >> 16, 1u);
+            if (!xo_below_parallel(rng, (uint32_t)cnt, my_m, a)) {
+                for (int q = 0; q < cnt; q++) {
+                    const uint32_t m = __shfl_sync(FULL, info.y >> 16, q);
+                    const uint32_t v = xo_below(rng, m);
+                    if (lane == q) a = v;
+                }
             }
         }
         if (i < I.n_nt) { info.y = (info.y & 0xFFFF0000u) | a; S.nt_info[i] = info; }
@@ -464,16 +622,27 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
     const bool active = (uint32_t)slot < amount;
     uint64_t curr_plato = 0, it = 0;
     for (; it < P.max_iter; it++) {
-        // IndexedRandom::sample -> rand::seq::index::sample_floyd (amount <= 11)
+        // IndexedRandom::sample -> rand::seq::index::sample_floyd (amount <= 11): draw k is
+        // random_range(..=j_k), j_k = n_nt - amount + k; a draw equal to an earlier entry replaces
+        // that entry by j_k.  Fast path: all draws lane-parallel; collisions / biased draws are rare.
         uint32_t myv = 0;
-        for (uint32_t k = 0; k < amount; k++) {
-            const uint32_t j = I.n_nt - amount + k;
-            const uint32_t t = xo_below(rng, j + 1u);
-            if ((uint32_t)lane == k) myv = t;
+        const uint32_t my_j = I.n_nt - amount + min((uint32_t)lane, amount - 1u);
+        bool need_fixup = true;
+        if (xo_below_parallel(rng, amount, my_j + 1u, myv)) {
+            const unsigned amask = (1u << amount) - 1u;
+            const unsigned peers = __match_any_sync(FULL, (uint32_t)lane < amount ? myv : 0xFFFFFFFFu);
+            need_fixup = __any_sync(FULL, (uint32_t)lane < amount && (peers & amask) != (1u << lane));
+        } else {
+            for (uint32_t k = 0; k < amount; k++) {
+                const uint32_t t = xo_below(rng, I.n_nt - amount + k + 1u);
+                if ((uint32_t)lane == k) myv = t;
+            }
         }
-        for (uint32_t k = 1; k < amount; k++) {
-            const uint32_t t = __shfl_sync(FULL, myv, k);
-            if ((uint32_t)lane < k && myv == t) myv = I.n_nt - amount + k;
+        if (need_fixup) {
+            for (uint32_t k = 1; k < amount; k++) {
+                const uint32_t t = __shfl_sync(FULL, myv, k);
+                if ((uint32_t)lane < k && myv == t) myv = I.n_nt - amount + k;
+            }
         }
         // best_read_improvement for every sampled read: 2 lanes per read
         const uint32_t idx = __shfl_sync(FULL, myv, slot);
@@ -567,7 +736,8 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
               uint64_t *__restrict__ rng_states, double *__restrict__ lik_mean, double *__restrict__ lik_var,
               double *__restrict__ liks, uint64_t *__restrict__ n_alns, uint64_t *__restrict__ iters,
               uint16_t *__restrict__ counts, unsigned char *__restrict__ scratch,
-              unsigned int *__restrict__ work_counter, int *__restrict__ err) {
+              unsigned int *__restrict__ work_counter, int *__restrict__ err,
+              const uint64_t *__restrict__ setup_mats) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpShared ws;
@@ -583,8 +753,8 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
         w = __shfl_sync(FULL, w, 0);
         if (w >= P.n_workers) break;
         Xo rng;
-        rng.s0 = rng_states[4 * (size_t)w + 0]; rng.s1 = rng_states[4 * (size_t)w + 1];
-        rng.s2 = rng_states[4 * (size_t)w + 2]; rng.s3 = rng_states[4 * (size_t)w + 3];
+        rng.lane = lane; rng.buf = S.rng_buf; rng.blk = S.rng_blk;
+        stream_begin(rng, rng_states + 4 * (size_t)w, setup_mats);
         for (uint64_t j = worker_off[w]; j < worker_off[w + 1]; j++) {
             const uint64_t g = worker_ixs[j];
             const double prior = L.priors ? L.priors[g] : 0.0;
@@ -658,11 +828,59 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
             }
             __syncwarp();
         }
-        if (lane == 0) {
-            rng_states[4 * (size_t)w + 0] = rng.s0; rng_states[4 * (size_t)w + 1] = rng.s1;
-            rng_states[4 * (size_t)w + 2] = rng.s2; rng_states[4 * (size_t)w + 3] = rng.s3;
-        }
+        stream_end(rng, rng_states + 4 * (size_t)w);
+        __syncwarp();
     }
+}
+
+// ------------------------------------------------------------------ host: jump matrices ---------
+
+// 256x256 matrices over GF(2) stored by columns (4 words per column).
+struct BitMat { uint64_t c[256][4]; };
+
+static void bm_step(BitMat &T) {      // one xoshiro256++ state transition
+    for (int j = 0; j < 256; j++) {
+        Gen g = {0, 0, 0, 0};
+        (j < 64 ? g.s0 : j < 128 ? g.s1 : j < 192 ? g.s2 : g.s3) = 1ull << (j & 63);
+        gen_next(g);
+        T.c[j][0] = g.s0; T.c[j][1] = g.s1; T.c[j][2] = g.s2; T.c[j][3] = g.s3;
+    }
+}
+static void bm_mul(const BitMat &A, const BitMat &B, BitMat &out) {   // out = A * B
+    for (int j = 0; j < 256; j++) {
+        uint64_t a[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 256; i++)
+            if ((B.c[j][i >> 6] >> (i & 63)) & 1ull) { a[0] ^= A.c[i][0]; a[1] ^= A.c[i][1]; a[2] ^= A.c[i][2]; a[3] ^= A.c[i][3]; }
+        out.c[j][0] = a[0]; out.c[j][1] = a[1]; out.c[j][2] = a[2]; out.c[j][3] = a[3];
+    }
+}
+static void bm_pow(const BitMat &T, unsigned e, BitMat &out) {
+    BitMat base = T, acc, tmp;
+    for (int j = 0; j < 256; j++) for (int k = 0; k < 4; k++) acc.c[j][k] = (k == (j >> 6)) ? 1ull << (j & 63) : 0;
+    while (e) {
+        if (e & 1) { bm_mul(base, acc, tmp); acc = tmp; }
+        bm_mul(base, base, tmp); base = tmp;
+        e >>= 1;
+    }
+    out = acc;
+}
+
+static int ensure_rng_mats(lctp_ctx *ctx) {
+    if (ctx->d_rng_mats.p) return LCTP_OK;
+    static BitMat T, M;            // static: 16 KB of stack otherwise
+    bm_step(T);
+    std::vector<uint64_t> host((size_t)N_SETUP_MATS * 1024);
+    for (int k = 0; k < N_SETUP_MATS; k++) {
+        bm_pow(T, (unsigned)RNG_C << k, M);
+        std::memcpy(&host[(size_t)k * 1024], M.c, sizeof(M.c));
+    }
+    int rc = ctx->d_rng_mats.alloc(host.size());
+    if (rc) return rc;
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_rng_mats.p, host.data(), host.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    bm_pow(T, 31u * RNG_C, M);
+    LCTP_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_refill_mat, M.c, sizeof(M.c), 0, cudaMemcpyHostToDevice, ctx->stream));
+    LCTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return LCTP_OK;
 }
 
 // ------------------------------------------------------------------ host launch -----------------
@@ -734,6 +952,7 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     const uint32_t grid = (warps + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
 
     int rc;
+    if ((rc = ensure_rng_mats(ctx))) return rc;
     if ((rc = ctx->scratch.ensure((size_t)grid * WARPS_PER_CTA * P.slab_bytes))) return rc;
     if ((rc = ctx->d_worker_ixs.ensure(n))) return rc;
     if ((rc = ctx->d_worker_off.ensure(n_workers + 1))) return rc;
@@ -757,7 +976,7 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     k_solve_stage<<<grid, WARPS_PER_CTA * 32, smem, s>>>(
         L, P, ctx->d_worker_ixs.p, ctx->d_worker_off.p, ctx->d_tuples.p, ctx->d_rng.p, ctx->d_lik_mean.p,
         ctx->d_lik_var.p, ctx->d_liks.p, ctx->d_nalns.p, ctx->d_iters.p, want_counts ? ctx->d_counts.p : nullptr,
-        ctx->scratch.p, (unsigned int *)(ctx->d_flags.p + 1), ctx->d_flags.p);
+        ctx->scratch.p, (unsigned int *)(ctx->d_flags.p + 1), ctx->d_flags.p, ctx->d_rng_mats.p);
     ctx->launches++;
     LCTP_CUDA_CHECK(cudaGetLastError());
     LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[3], s));
