@@ -24,21 +24,27 @@ void set_error(const char *fmt, ...);
         }                                                                                      \
     } while (0)
 
-// Monotone device buffer (freed with the owning handle).
+// Device buffer from the stream-ordered pool (cudaMallocAsync): after warm-up, allocating and freeing
+// the per-locus buffers costs no driver round trip, which matters for the end-to-end (upload + solve) path.
+cudaStream_t current_alloc_stream();
+void set_alloc_stream(cudaStream_t s);
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    cudaStream_t s = nullptr;
     int alloc(size_t count) {
         release();
         n = count;
         if (count == 0) return LCTP_OK;
-        LCTP_CUDA_CHECK(cudaMalloc((void **)&p, count * sizeof(T)));
+        s = current_alloc_stream();
+        LCTP_CUDA_CHECK(cudaMallocAsync((void **)&p, count * sizeof(T), s));
         return LCTP_OK;
     }
     int ensure(size_t count) { return count <= n ? LCTP_OK : alloc(count); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, s);
         p = nullptr;
         n = 0;
     }

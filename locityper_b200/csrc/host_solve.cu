@@ -21,6 +21,9 @@
 namespace lctp {
 
 static thread_local std::string g_last_error;
+static thread_local cudaStream_t g_alloc_stream = nullptr;
+cudaStream_t current_alloc_stream() { return g_alloc_stream; }
+void set_alloc_stream(cudaStream_t s) { g_alloc_stream = s; }
 
 void set_error(const char *fmt, ...) {
     char buf[1024];
@@ -81,6 +84,39 @@ struct HostRng {
 static const uint64_t kJump[4] = {0x180ec6d33cfd0abaull, 0xd5a61266f0c9392cull, 0xa9582618e03fc9aaull, 0x39abdc4529b1661cull};
 static const uint64_t kLongJump[4] = {0x76e15d3efefdcbbfull, 0xc5004e441c522fb3ull, 0x77710069854ee241ull, 0x39109bb02acbe635ull};
 
+// The xoshiro jump (2^128 steps) is a linear map J over GF(2).  MainWorker::new needs J^w * state for
+// every worker w (solve.rs:1007-1018); with thousands of logical workers the polynomial method (256
+// generator steps per jump) costs milliseconds, so J is tabulated once by byte slices:
+// J*s = XOR_b tab[b][byte_b(s)].
+struct JumpTable {
+    std::vector<uint64_t> t;   // [32][256][4]
+    JumpTable() : t((size_t)32 * 256 * 4, 0) {
+        uint64_t col[256][4];
+        for (int j = 0; j < 256; j++) {
+            HostRng r; r.s[0] = r.s[1] = r.s[2] = r.s[3] = 0;
+            r.s[j >> 6] = 1ull << (j & 63);
+            r.jump_poly(kJump);
+            for (int k = 0; k < 4; k++) col[j][k] = r.s[k];
+        }
+        for (int b = 0; b < 32; b++)
+            for (int v = 0; v < 256; v++) {
+                uint64_t *o = &t[((size_t)b * 256 + v) * 4];
+                for (int bit = 0; bit < 8; bit++)
+                    if (v & (1 << bit)) for (int k = 0; k < 4; k++) o[k] ^= col[b * 8 + bit][k];
+            }
+    }
+    void apply(uint64_t s[4]) const {
+        uint64_t a[4] = {0, 0, 0, 0};
+        for (int b = 0; b < 32; b++) {
+            const unsigned v = (unsigned)((s[b >> 3] >> ((b & 7) * 8)) & 0xFF);
+            const uint64_t *o = &t[((size_t)b * 256 + v) * 4];
+            a[0] ^= o[0]; a[1] ^= o[1]; a[2] ^= o[2]; a[3] ^= o[3];
+        }
+        s[0] = a[0]; s[1] = a[1]; s[2] = a[2]; s[3] = a[3];
+    }
+};
+static const JumpTable &jump_table() { static const JumpTable jt; return jt; }
+
 // SliceRandom::shuffle (rand >= 0.9): forward Fisher-Yates whose indices come from IncreasingUniform,
 // i.e. one bounded u32 draw is split into several indices by div/mod.
 static void shuffle_u64(HostRng &rng, uint64_t *v, size_t len) {
@@ -127,6 +163,15 @@ static uint64_t choose(uint64_t n, uint64_t k) {
 
 void genotype_tuple(uint32_t H, uint32_t p, const uint32_t *gt_tuples, uint64_t g, uint32_t *out) {
     if (gt_tuples) { std::copy(gt_tuples + g * p, gt_tuples + (g + 1) * p, out); return; }
+    if (p == 2) {   // closed form: row i starts at i*H - i(i-1)/2
+        const double Hd = (double)H + 0.5;
+        uint64_t i = (uint64_t)std::floor(Hd - std::sqrt(std::max(0.0, Hd * Hd - 2.0 * (double)g)));
+        auto row = [&](uint64_t r) { return r * H - r * (r - 1) / 2; };
+        while (i > 0 && row(i) > g) i--;
+        while (i + 1 < H && row(i + 1) <= g) i++;
+        out[0] = (uint32_t)i; out[1] = (uint32_t)(i + (g - row(i)));
+        return;
+    }
     uint32_t lo = 0;
     for (uint32_t d = 0; d < p; d++) {
         const uint32_t rem = p - d - 1;
@@ -316,6 +361,14 @@ int lctp_init(const lctp_device_cfg *cfg, lctp_ctx **out) {
         if (se != cudaSuccess) { set_error("lctp_init: cudaStreamCreate failed: %s", cudaGetErrorString(se)); delete ctx; return LCTP_E_CUDA; }
         ctx->own_stream = true;
     }
+    {   // keep freed blocks in the pool instead of returning them to the driver at every sync
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
+    set_alloc_stream(ctx->stream);
     for (int i = 0; i < 4; i++) {
         cudaError_t ee = cudaEventCreate(&ctx->ev[i]);
         if (ee != cudaSuccess) { set_error("lctp_init: cudaEventCreate failed: %s", cudaGetErrorString(ee)); delete ctx; return LCTP_E_CUDA; }
@@ -327,10 +380,14 @@ int lctp_init(const lctp_device_cfg *cfg, lctp_ctx **out) {
 void lctp_destroy(lctp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    set_alloc_stream(ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    cudaStream_t st = ctx->stream;
+    const bool own = ctx->own_stream;
+    delete ctx;                       // frees the scratch buffers on the stream
+    cudaStreamSynchronize(st);
+    if (own) cudaStreamDestroy(st);
 }
 
 uint64_t lctp_launch_count(const lctp_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -352,6 +409,7 @@ int lctp_locus_upload(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h **out) {
     if (!ctx || !in || !out) { set_error("lctp_locus_upload: NULL argument"); return LCTP_E_INVALID; }
     *out = nullptr;
     LCTP_CUDA_CHECK(cudaSetDevice(ctx->device));
+    set_alloc_stream(ctx->stream);
     lctp_locus_h *h = new lctp_locus_h();
     int rc = upload_locus(ctx, in, h);
     if (rc != LCTP_OK) { delete h; return rc; }
@@ -361,7 +419,7 @@ int lctp_locus_upload(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h **out) {
 
 void lctp_locus_free(lctp_locus_h *h) {
     if (!h) return;
-    if (h->ctx) { cudaSetDevice(h->ctx->device); cudaStreamSynchronize(h->ctx->stream); }
+    if (h->ctx) { cudaSetDevice(h->ctx->device); set_alloc_stream(h->ctx->stream); }
     delete h;
 }
 
@@ -399,17 +457,56 @@ int lctp_prefilter_scores(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, dou
 size_t lctp_truncate_ixs(uint64_t *ixs, size_t n, const double *scores, double filt_diff, size_t min_size,
                          size_t threads) {
     if (n == 0) return 0;
-    sort_desc_stable(ixs, n, scores);
-    const double best = scores[ixs[0]], worst = scores[ixs[n - 1]];
+    // Reference: sort all, then cut (solve.rs:60-81).  Equivalent and much cheaper for large n: find the
+    // cut first, partition the survivors to the front (keeping their order), sort only those.
+    bool ascending = true;
+    for (size_t q = 1; q < n && ascending; q++) ascending = ixs[q - 1] < ixs[q];
+    double best = scores[ixs[0]], worst = best;
+    for (size_t q = 1; q < n; q++) {
+        const double v = scores[ixs[q]];
+        if (total_key(v) > total_key(best)) best = v;
+        if (total_key(v) < total_key(worst)) worst = v;
+    }
     double thresh = best - filt_diff;
-    if (min_size >= n || worst >= thresh) return n;
-    auto part = [&](double th) {
-        return (size_t)(std::partition_point(ixs, ixs + n, [&](uint64_t i) { return scores[i] >= th; }) - ixs);
-    };
-    size_t m = part(thresh);
-    if (m < min_size) { thresh = scores[ixs[min_size - 1]]; m = part(thresh); }
-    m = std::min(std::max(m, threads), n);
-    return m;
+    size_t m;
+    if (min_size >= n || worst >= thresh) m = n;
+    else {
+        auto count_ge = [&](double th) { size_t c = 0; for (size_t q = 0; q < n; q++) c += scores[ixs[q]] >= th; return c; };
+        m = count_ge(thresh);
+        if (m < min_size) {
+            std::vector<double> tmp(n);
+            for (size_t q = 0; q < n; q++) tmp[q] = scores[ixs[q]];
+            std::nth_element(tmp.begin(), tmp.begin() + (min_size - 1), tmp.end(),
+                             [](double a, double b) { return total_key(a) > total_key(b); });
+            thresh = tmp[min_size - 1];
+            m = count_ge(thresh);
+        }
+        m = std::min(std::max(m, threads), n);
+    }
+    if (m == n || !ascending) {   // nothing to gain, or arbitrary input order: literal restatement
+        sort_desc_stable(ixs, n, scores);
+        return m;
+    }
+    // the m best under (score desc, input order asc): everything >= the m-th best key, ties by position
+    std::vector<uint64_t> keep;
+    keep.reserve(m + 16);
+    const size_t n_ge = [&] { size_t c = 0; for (size_t q = 0; q < n; q++) c += scores[ixs[q]] >= thresh; return c; }();
+    if (n_ge >= m) {
+        // m was not raised by `threads`: survivors are exactly {score >= thresh} (m == n_ge)
+        for (size_t q = 0; q < n; q++) if (scores[ixs[q]] >= thresh) keep.push_back(ixs[q]);
+    } else {
+        // raised to `threads`: take the m best overall
+        std::vector<uint64_t> all(ixs, ixs + n);
+        std::nth_element(all.begin(), all.begin() + (m - 1), all.end(), [&](uint64_t a, uint64_t b) {
+            const int64_t ka = total_key(scores[a]), kb = total_key(scores[b]);
+            return ka != kb ? ka > kb : a < b;
+        });
+        keep.assign(all.begin(), all.begin() + m);
+        std::sort(keep.begin(), keep.end());
+    }
+    sort_desc_stable(keep.data(), keep.size(), scores);
+    std::copy(keep.begin(), keep.end(), ixs);
+    return keep.size();
 }
 
 int lctp_prefilter(lctp_locus_h *h, uint64_t *ixs, size_t n, size_t min_size, size_t threads, size_t *out_n,
@@ -439,6 +536,7 @@ int lctp_solve_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *work
                      uint64_t *iters_out) {
     if (!h) { set_error("lctp_solve_stage: NULL handle"); return LCTP_E_INVALID; }
     LCTP_CUDA_CHECK(cudaSetDevice(h->ctx->device));
+    set_alloc_stream(h->ctx->stream);
     return launch_stage(h, st, worker_ixs, worker_off, n_workers, worker_rng, lik_mean, lik_var, liks, counts_off,
                         counts, counts_cap, n_alns_out, iters_out);
 }
@@ -452,9 +550,7 @@ void lctp_rng_seed_from_u64(uint64_t state[4], uint64_t seed) {
         state[i] = z ^ (z >> 31);
     }
 }
-void lctp_rng_jump(uint64_t state[4]) {
-    HostRng r; std::memcpy(r.s, state, 32); r.jump_poly(kJump); std::memcpy(state, r.s, 32);
-}
+void lctp_rng_jump(uint64_t state[4]) { jump_table().apply(state); }
 void lctp_rng_long_jump(uint64_t state[4]) {
     HostRng r; std::memcpy(r.s, state, 32); r.jump_poly(kLongJump); std::memcpy(state, r.s, 32);
 }
@@ -546,9 +642,8 @@ int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_
     std::vector<uint64_t> wrng;
     if (threads > 1) {                                               // MainWorker::new, solve.rs:1007-1018
         wrng.resize(threads * 4);
-        HostRng r; std::memcpy(r.s, rng, 32);
-        for (size_t w = 0; w < threads; w++) { std::memcpy(&wrng[4 * w], r.s, 32); r.jump_poly(kJump); }
-        std::memcpy(rng, r.s, 32);
+        const JumpTable &jt = jump_table();
+        for (size_t w = 0; w < threads; w++) { std::memcpy(&wrng[4 * w], rng, 32); jt.apply(rng); }
     }
     std::vector<uint64_t> off(threads + 1);
     std::vector<double> lm, lv;

@@ -20,6 +20,7 @@
 #include <cmath>
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 namespace lctp {
 
@@ -38,7 +39,6 @@ struct Slab {
     double *cand_lnprob;   // [cap]
     uint32_t *cand_w;      // [cap]  (w1 | w2 << 16)
     uint32_t *cand_src;    // [cap]  index into cm arrays, LCTP_NONE_U32 = "both mates unmapped" option
-    uint2 *nt_info;        // [R]    (start, n << 16 | assgn) for every non-trivial read, in read order
     uint32_t *read_off;    // [R+1]
     uint8_t *cand_cix;     // [cap]
     uint64_t *rng_buf;     // [RNG_FILL] pre-generated draws of the worker's stream
@@ -55,8 +55,6 @@ __host__ __device__ inline size_t slab_layout(uint32_t cap, uint32_t R, unsigned
     o += align_up((size_t)cap * 4, 128);
     if (s) s->cand_src = (uint32_t *)(base + o);
     o += align_up((size_t)cap * 4, 128);
-    if (s) s->nt_info = (uint2 *)(base + o);
-    o += align_up((size_t)R * 8, 128);
     if (s) s->read_off = (uint32_t *)(base + o);
     o += align_up(((size_t)R + 1) * 4, 128);
     if (s) s->cand_cix = (uint8_t *)(base + o);
@@ -254,10 +252,23 @@ __device__ __forceinline__ long long total_key(double v) {
 // TRIVIAL windows (WindowDistr::TRIVIAL, src/model/distr_cache.rs:27-30) are stored as weight 0 on the
 // all-zero extra row of the device table, so 0*0 - 0*0 = +0.0 reproduces the reference's literal 0.0 with
 // no branch; a zero depth change gives w*t - w*t = +0.0 the same way.
+// Also in shared memory, per worker: for every NON-TRIVIAL read (in read order) its candidate range
+// `nt_loc` = start | n << 24 and its current assignment `nt_assgn`, plus a 2-stage staging area that
+// cp.async fills with the candidates (ln_prob, windows) of the reads sampled for the NEXT greedy iteration.
+static constexpr int MAX_SAMPLE = 11;          // Floyd branch of rand::seq::index::sample
+static constexpr int STAGE_CANDS = 8;          // candidates per sampled read staged in smem (rest: global)
 struct WarpShared {
     uint4 *win;          // [Wmax]
+    uint32_t *nt_loc;    // [R]
+    uint8_t *nt_assgn;   // [R]
+    double *st_lp;       // [2][MAX_SAMPLE][STAGE_CANDS]
+    uint32_t *st_w;      // [2][MAX_SAMPLE][STAGE_CANDS]
     uint32_t zero_row;   // offset of the all-zero row
 };
+__host__ __device__ inline size_t warp_smem_bytes(uint32_t Wmax, uint32_t R) {
+    return align_up((size_t)Wmax * 16, 16) + align_up((size_t)R * 4, 16) + align_up((size_t)R, 16) +
+           (size_t)2 * MAX_SAMPLE * STAGE_CANDS * 12;
+}
 
 __device__ __forceinline__ double win_weight(const uint4 &r) { return __hiloint2double((int)r.y, (int)r.x); }
 __device__ __forceinline__ uint4 make_win(double weight, uint32_t row, uint32_t depth) {
@@ -318,7 +329,7 @@ struct Instance {
 // threshold, append the unmapped option, stable-sort descending (here: a p-way merge of the already
 // sorted per-contig lists, ties resolved in insertion order = contig order, unmapped last), cut at the
 // final threshold.  Returns false on slab overflow.
-__device__ bool build_instance(const LocusDev &L, const Slab &S, uint32_t cap, Instance &I, int lane) {
+__device__ bool build_instance(const LocusDev &L, const Slab &S, const WarpShared &ws, uint32_t cap, Instance &I, int lane) {
     const uint32_t R = L.R, p = L.p;
     uint32_t base = 0, nt_base = 0;
     bool ok = true;
@@ -362,7 +373,8 @@ __device__ bool build_instance(const LocusDev &L, const Slab &S, uint32_t cap, I
         if (ok && valid) {
             if (nt) {
                 const uint32_t pos = nt_base + __popc(ntmask & ((1u << lane) - 1u));
-                S.nt_info[pos] = make_uint2(start, nw << 16);
+                ws.nt_loc[pos] = start | (nw << 24);
+                ws.nt_assgn[pos] = 0;
             }
             bool unm_left = with_unm;
             const long long unm_key = total_key(unm);
@@ -499,20 +511,19 @@ __device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance
     // assignments of non-trivial reads
     for (uint32_t i0 = 0; i0 < I.n_nt; i0 += 32) {
         const uint32_t i = i0 + lane;
-        uint2 info = i < I.n_nt ? S.nt_info[i] : make_uint2(0, 0);
+        const uint32_t my_n = i < I.n_nt ? ws.nt_loc[i] >> 24 : 1u;
         uint32_t a = 0;
         if (init_mode == 1) {
             const int cnt = (int)min(32u, I.n_nt - i0);
-            const uint32_t my_m = max(info.y >> 16, 1u);
-            if (!xo_below_parallel(rng, (uint32_t)cnt, my_m, a)) {
+            if (!xo_below_parallel(rng, (uint32_t)cnt, my_n, a)) {
                 for (int q = 0; q < cnt; q++) {
-                    const uint32_t m = __shfl_sync(FULL, info.y >> 16, q);
+                    const uint32_t m = __shfl_sync(FULL, my_n, q);
                     const uint32_t v = xo_below(rng, m);
                     if (lane == q) a = v;
                 }
             }
         }
-        if (i < I.n_nt) { info.y = (info.y & 0xFFFF0000u) | a; S.nt_info[i] = info; }
+        if (i < I.n_nt) ws.nt_assgn[i] = (uint8_t)a;
     }
     __syncwarp();
     // depth counts + aln_lik in read order (src/model/assgn.rs:205-217,351-353)
@@ -528,7 +539,7 @@ __device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance
         double term = 0.0;
         if (valid) {
             uint32_t a = 0;
-            if (nt) a = S.nt_info[nt_base + __popc(ntmask & ((1u << lane) - 1u))].y & 0xFFFFu;
+            if (nt) a = ws.nt_assgn[nt_base + __popc(ntmask & ((1u << lane) - 1u))];
             const uint32_t ix = start + a;
             term = S.cand_lnprob[ix];
             const uint32_t w12 = S.cand_w[ix];
@@ -555,19 +566,19 @@ __device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance
 struct Target { uint32_t idx, n, old_a, new_a, old_ix, new_ix; };
 
 // ReassignmentTarget::random (src/model/assgn.rs:451-471), warp-uniform
-__device__ __forceinline__ Target random_target(const Slab &S, const Instance &I, Xo &rng) {
+__device__ __forceinline__ Target random_target(const WarpShared &ws, const Instance &I, Xo &rng) {
     Target t;
     t.idx = xo_below(rng, I.n_nt);                     // random_range(0..n_nontrivial), usize via the u32 path
-    const uint2 info = S.nt_info[t.idx];
-    t.n = info.y >> 16;
-    t.old_a = info.y & 0xFFFFu;
+    const uint32_t loc = ws.nt_loc[t.idx];
+    t.n = loc >> 24;
+    t.old_a = ws.nt_assgn[t.idx];
     if (t.n == 2) t.new_a = 1u - t.old_a;
     else {
         const uint32_t i = 1u + xo_below(rng, t.n - 1u);   // random_range(1..n as u16)
         t.new_a = i <= t.old_a ? i - 1u : i;
     }
-    t.old_ix = info.x + t.old_a;
-    t.new_ix = info.x + t.new_a;
+    t.old_ix = (loc & 0xFFFFFFu) + t.old_a;
+    t.new_ix = (loc & 0xFFFFFFu) + t.new_a;
     return t;
 }
 
@@ -594,7 +605,7 @@ __device__ __forceinline__ void apply_move(const Slab &S, const WarpShared &ws, 
         ws.win[mv.w34 >> 16].w += 1;
         ws.win[mv.w12 & 0xFFFFu].w -= 1;
         ws.win[mv.w12 >> 16].w -= 1;
-        S.nt_info[idx].y = (n << 16) | new_a;
+        ws.nt_assgn[idx] = (uint8_t)new_a;
     }
     __syncwarp();
 }
@@ -603,7 +614,7 @@ __device__ __forceinline__ void apply_move(const Slab &S, const WarpShared &ws, 
 __device__ double max_abs_random(const LocusDev &L, const Slab &S, const Instance &I, const WarpShared &ws, Xo &rng) {
     double acc = 0.0;
     for (int q = 0; q < 100; q++) {
-        const Target t = random_target(S, I, rng);
+        const Target t = random_target(ws, I, rng);
         Move mv;
         acc = fmax(acc, fabs(calc_improvement(L, S, ws, t, mv)));
     }
@@ -612,6 +623,60 @@ __device__ double max_abs_random(const LocusDev &L, const Slab &S, const Instanc
 
 // ------------------------------------------------------------------ a10: Greedy -----------------
 
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit_g() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all_g() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// One sample of `amount` distinct non-trivial reads (IndexedRandom::sample -> index::sample_floyd):
+// draw k is random_range(..=j_k), j_k = n_nt - amount + k; a draw equal to an earlier entry replaces
+// that entry by j_k.  `fast_only`: succeed only through the lane-parallel path (no refill, no biased
+// draw), so the caller can un-consume the draws again with `rng.pos -= amount`.
+__device__ __forceinline__ bool sample_reads(Xo &rng, uint32_t n_nt, uint32_t amount, bool fast_only,
+                                             uint32_t &myv, int lane) {
+    const uint32_t my_j = n_nt - amount + min((uint32_t)lane, amount - 1u);
+    bool need_fixup = true;
+    if (xo_below_parallel(rng, amount, my_j + 1u, myv)) {
+        const unsigned amask = (1u << amount) - 1u;
+        const unsigned peers = __match_any_sync(FULL, (uint32_t)lane < amount ? myv : 0xFFFFFFFFu);
+        need_fixup = __any_sync(FULL, (uint32_t)lane < amount && (peers & amask) != (1u << lane));
+    } else {
+        if (fast_only) return false;
+        for (uint32_t k = 0; k < amount; k++) {
+            const uint32_t t = xo_below(rng, n_nt - amount + k + 1u);
+            if ((uint32_t)lane == k) myv = t;
+        }
+    }
+    if (need_fixup) {
+        for (uint32_t k = 1; k < amount; k++) {
+            const uint32_t t = __shfl_sync(FULL, myv, k);
+            if ((uint32_t)lane < k && myv == t) myv = n_nt - amount + k;
+        }
+    }
+    return true;
+}
+
+// Stage the static candidate data of a sampled read: this lane copies the candidates it will evaluate
+// (c = sub, sub+2, ... < min(n, STAGE_CANDS)) from the slab into shared memory with cp.async.
+__device__ __forceinline__ void stage_read(const Slab &S, const WarpShared &ws, int stage, int slot, int sub,
+                                           uint32_t loc) {
+    const uint32_t start = loc & 0xFFFFFFu, n = min(loc >> 24, (uint32_t)STAGE_CANDS);
+    double *lp = ws.st_lp + (stage * MAX_SAMPLE + slot) * STAGE_CANDS;
+    uint32_t *w = ws.st_w + (stage * MAX_SAMPLE + slot) * STAGE_CANDS;
+    for (uint32_t c = sub; c < n; c += 2) {
+        cp_async8(lp + c, S.cand_lnprob + start + c);
+        cp_async4(w + c, S.cand_w + start + c);
+    }
+}
+
+// Greedy::solve_nontrivial (src/solvers/stoch.rs:81-120).  Two lanes per sampled read evaluate its
+// candidates (best_read_improvement, src/model/assgn.rs:287-317).  Software pipeline: the sample of
+// iteration i+1 is drawn and its (static) candidate data is cp.async-staged while iteration i is
+// evaluated, so an iteration touches only shared memory and the L1-resident depth table.
 __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab &S, const Instance &I,
                              const WarpShared &ws, Xo &rng, double &aln_lik, double &depth_lik,
                              uint64_t &iters_out, int lane) {
@@ -621,43 +686,47 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
     const int slot = lane >> 1, sub = lane & 1;
     const bool active = (uint32_t)slot < amount;
     uint64_t curr_plato = 0, it = 0;
+    bool have_next = false;
+    uint32_t next_idx = 0, next_loc = 0;
+    int stage = 0;
     for (; it < P.max_iter; it++) {
-        // IndexedRandom::sample -> rand::seq::index::sample_floyd (amount <= 11): draw k is
-        // random_range(..=j_k), j_k = n_nt - amount + k; a draw equal to an earlier entry replaces
-        // that entry by j_k.  Fast path: all draws lane-parallel; collisions / biased draws are rare.
-        uint32_t myv = 0;
-        const uint32_t my_j = I.n_nt - amount + min((uint32_t)lane, amount - 1u);
-        bool need_fixup = true;
-        if (xo_below_parallel(rng, amount, my_j + 1u, myv)) {
-            const unsigned amask = (1u << amount) - 1u;
-            const unsigned peers = __match_any_sync(FULL, (uint32_t)lane < amount ? myv : 0xFFFFFFFFu);
-            need_fixup = __any_sync(FULL, (uint32_t)lane < amount && (peers & amask) != (1u << lane));
-        } else {
-            for (uint32_t k = 0; k < amount; k++) {
-                const uint32_t t = xo_below(rng, I.n_nt - amount + k + 1u);
-                if ((uint32_t)lane == k) myv = t;
+        uint32_t idx, loc;
+        if (have_next) { idx = next_idx; loc = next_loc; }
+        else {
+            uint32_t myv = 0;
+            sample_reads(rng, I.n_nt, amount, false, myv, lane);
+            idx = __shfl_sync(FULL, myv, slot);
+            loc = active ? ws.nt_loc[idx] : 0u;
+            if (active) stage_read(S, ws, stage, slot, sub, loc);
+            cp_async_commit_g();
+        }
+        cp_async_wait_all_g();
+        __syncwarp();
+        {   // pre-draw the next sample and start staging it
+            uint32_t myv = 0;
+            have_next = sample_reads(rng, I.n_nt, amount, true, myv, lane);
+            if (have_next) {
+                next_idx = __shfl_sync(FULL, myv, slot);
+                next_loc = active ? ws.nt_loc[next_idx] : 0u;
+                if (active) stage_read(S, ws, stage ^ 1, slot, sub, next_loc);
+                cp_async_commit_g();
             }
         }
-        if (need_fixup) {
-            for (uint32_t k = 1; k < amount; k++) {
-                const uint32_t t = __shfl_sync(FULL, myv, k);
-                if ((uint32_t)lane < k && myv == t) myv = I.n_nt - amount + k;
-            }
-        }
-        // best_read_improvement for every sampled read: 2 lanes per read
-        const uint32_t idx = __shfl_sync(FULL, myv, slot);
+        // best_read_improvement for every sampled read
         double best = -INFINITY, b_dld = 0.0, b_lp = 0.0, lp_old = 0.0;
-        uint32_t b_c = 0, b_w34 = 0, w12 = 0, n = 0;
+        uint32_t b_c = 0, b_w34 = 0, w12 = 0;
+        const uint32_t start = loc & 0xFFFFFFu, n = loc >> 24;
         if (active) {
-            const uint2 info = S.nt_info[idx];
-            n = info.y >> 16;
-            const uint32_t old_a = info.y & 0xFFFFu;
-            lp_old = S.cand_lnprob[info.x + old_a];
-            w12 = S.cand_w[info.x + old_a];
+            const double *slp = ws.st_lp + (stage * MAX_SAMPLE + slot) * STAGE_CANDS;
+            const uint32_t *sw = ws.st_w + (stage * MAX_SAMPLE + slot) * STAGE_CANDS;
+            const uint32_t old_a = ws.nt_assgn[idx];
+            if (old_a < (uint32_t)STAGE_CANDS) { lp_old = slp[old_a]; w12 = sw[old_a]; }
+            else { lp_old = S.cand_lnprob[start + old_a]; w12 = S.cand_w[start + old_a]; }
             for (uint32_t c = sub; c < n; c += 2) {
                 if (c == old_a) continue;
-                const double lp = S.cand_lnprob[info.x + c];
-                const uint32_t w34 = S.cand_w[info.x + c];
+                double lp; uint32_t w34;
+                if (c < (uint32_t)STAGE_CANDS) { lp = slp[c]; w34 = sw[c]; }
+                else { lp = S.cand_lnprob[start + c]; w34 = S.cand_w[start + c]; }
                 const double dld = depth_lik_diff(ws, L.depth_table, w12 & 0xFFFFu, w12 >> 16, w34 & 0xFFFFu, w34 >> 16);
                 const double improv = __dadd_rn(lp, __dmul_rn(L.rel_contrib, dld));
                 if (improv > best) { best = improv; b_c = c; b_dld = dld; b_lp = lp; b_w34 = w34; }
@@ -672,23 +741,26 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
         const double s_improv = active ? __dmul_rn(L.aln_contrib, __dsub_rn(best, lp_old)) : -INFINITY;
         const int wl0 = warp_argmax_first(ord_key(s_improv));
         const double s_best = shfl_d(s_improv, wl0);
-        const uint32_t key = ((uint32_t)(wl0 >> 1) << 16) | __shfl_sync(FULL, b_c, wl0);
+        const uint32_t win_c = __shfl_sync(FULL, b_c, wl0);
         if (s_best > min_diff) {
-            const int wl = (int)((key >> 16) * 2 + (key & 1u));   // lane that evaluated the winning candidate
+            const int wl = (wl0 & ~1) | (int)(win_c & 1u);   // lane that evaluated the winning candidate
             Move mv;
             mv.dld = shfl_d(b_dld, wl);
             mv.dlp = shfl_d(__dsub_rn(b_lp, lp_old), wl);
             mv.w12 = __shfl_sync(FULL, w12, wl);
             mv.w34 = __shfl_sync(FULL, b_w34, wl);
             const uint32_t w_idx = __shfl_sync(FULL, idx, wl);
-            const uint32_t w_n = __shfl_sync(FULL, n, wl);
-            apply_move(S, ws, w_idx, w_n, key & 0xFFFFu, mv, aln_lik, depth_lik, lane);
+            apply_move(S, ws, w_idx, 0, win_c, mv, aln_lik, depth_lik, lane);
             curr_plato = 0;
         } else {
             curr_plato += 1;
             if (curr_plato > P.plato_size) { it++; break; }
         }
+        stage ^= 1;
     }
+    if (have_next) rng.pos -= amount;     // the pre-drawn sample of the iteration that never ran
+    cp_async_wait_all_g();
+    __syncwarp();
     iters_out += it;
 }
 
@@ -704,7 +776,7 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
     const double temp_step = __ddiv_rn(start_temp, (double)P.anneal_steps);
     uint64_t curr_plato = 0, steps = 0;
     for (uint64_t i = P.anneal_steps; i >= 1; i--) {
-        const Target t = random_target(S, I, rng);
+        const Target t = random_target(ws, I, rng);
         Move mv;
         const double diff = __dsub_rn(calc_improvement(L, S, ws, t, mv), min_diff);
         steps++;
@@ -718,7 +790,7 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
     }
     for (uint64_t k = 0; k < P.max_iter; k++) {
         if (curr_plato >= P.plato_size) break;
-        const Target t = random_target(S, I, rng);
+        const Target t = random_target(ws, I, rng);
         Move mv;
         const double diff = calc_improvement(L, S, ws, t, mv);
         steps++;
@@ -741,8 +813,15 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpShared ws;
-    ws.win = (uint4 *)smem + (size_t)wib * P.Wmax;
-    ws.zero_row = LCTP_GC_BINS * L.depth_k;
+    {
+        unsigned char *base = smem + (size_t)wib * warp_smem_bytes(P.Wmax, L.R);
+        ws.win = (uint4 *)base;                base += align_up((size_t)P.Wmax * 16, 16);
+        ws.nt_loc = (uint32_t *)base;          base += align_up((size_t)L.R * 4, 16);
+        ws.nt_assgn = (uint8_t *)base;         base += align_up((size_t)L.R, 16);
+        ws.st_lp = (double *)base;             base += (size_t)2 * MAX_SAMPLE * STAGE_CANDS * 8;
+        ws.st_w = (uint32_t *)base;
+        ws.zero_row = LCTP_GC_BINS * L.depth_k;
+    }
     const uint32_t slot = blockIdx.x * WARPS_PER_CTA + wib;
     Slab S;
     slab_layout(P.cap, L.R, scratch + (size_t)slot * P.slab_bytes, &S);
@@ -767,7 +846,7 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
                 I.wshift[k + 1] = wsft;
             }
             I.W = wsft;
-            const bool ok = build_instance(L, S, P.cap, I, lane);
+            const bool ok = build_instance(L, S, ws, P.cap, I, lane);
             if (!ok) {
                 if (lane == 0) { atomicOr(err, 1); lik_mean[j] = NAN; lik_var[j] = NAN; n_alns[j] = I.A; }
                 continue;
@@ -797,7 +876,7 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
                         const unsigned ntmask = __ballot_sync(FULL, nt);
                         if (valid) {
                             uint32_t as = 0;
-                            if (nt) as = S.nt_info[nt_base + __popc(ntmask & ((1u << lane) - 1u))].y & 0xFFFFu;
+                            if (nt) as = ws.nt_assgn[nt_base + __popc(ntmask & ((1u << lane) - 1u))];
                             cnt[start + as] += 1;
                         }
                         nt_base += __popc(ntmask);
@@ -940,11 +1019,15 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     P.want_counts = want_counts ? 1 : 0;
     P.slab_bytes = slab_layout(cap, L.R, nullptr, nullptr);
 
-    const size_t smem = (size_t)WARPS_PER_CTA * Wmax * 16;
+    const size_t smem = (size_t)WARPS_PER_CTA * warp_smem_bytes(Wmax, L.R);
+    if (cap >= (1u << 24)) { set_error("lctp_solve_stage: %u candidate locations per genotype exceed 2^24", cap); return LCTP_E_CAPACITY; }
     if (smem > ctx->smem_optin) { set_error("lctp_solve_stage: %zu bytes of shared memory needed", smem); return LCTP_E_CAPACITY; }
     LCTP_CUDA_CHECK(cudaFuncSetAttribute(k_solve_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (const char *e = getenv("LCTP_CARVEOUT"))   // tuning knob: shared-memory carveout percentage
+        LCTP_CUDA_CHECK(cudaFuncSetAttribute(k_solve_stage, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
     int occ = 0;
     LCTP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_stage, WARPS_PER_CTA * 32, smem));
+    if (const char *e = getenv("LCTP_MAX_CTAS_PER_SM")) occ = std::min(occ, std::max(1, atoi(e)));
     if (occ < 1) occ = 1;
     uint32_t resident_warps = (uint32_t)ctx->sm_count * occ * WARPS_PER_CTA;
     if (ctx->max_resident_workers && ctx->max_resident_workers < resident_warps) resident_warps = ctx->max_resident_workers;

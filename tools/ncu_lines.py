@@ -1,0 +1,49 @@
+"""Attribute an ncu report's per-SASS counters to CUDA source lines (needs -lineinfo).
+usage: python tools/ncu_lines.py REPORT.ncu-rep [kernel_substr] [iterations]"""
+import collections, csv, io, os, re, subprocess, sys, tempfile
+rep = sys.argv[1]
+kern = sys.argv[2] if len(sys.argv) > 2 else "k_solve_stage"
+iters = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "locityper_b200/_lib/liblctp.so")], cwd=tmp, capture_output=True)
+sass = ""
+for f in os.listdir(tmp):
+    out = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+    if kern in out:
+        sass = out
+cur, off2line, infunc = None, {}, False
+for ln in sass.split("\n"):
+    if ".text." in ln and kern in ln:
+        infunc = True
+    m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
+    if m:
+        cur = (os.path.basename(m.group(1)), int(m.group(2)))
+    m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
+    if m and infunc:
+        off2line[int(m.group(1), 16)] = cur
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+h = rows[1]
+ci, smp = h.index("Instructions Executed"), h.index("# Samples")
+base, byi, bys, ti, ts = None, collections.Counter(), collections.Counter(), 0, 0
+for r in rows[2:]:
+    try:
+        a, n, sm = int(r[0], 16), int(r[ci]), int(r[smp])
+    except Exception:
+        continue
+    if base is None:
+        base = a
+    l = off2line.get(a - base)
+    byi[l] += n; bys[l] += sm; ti += n; ts += sm
+src = {}
+def text(l):
+    if not l: return "?"
+    path = os.path.join(root, "locityper_b200/csrc", l[0])
+    if l[0] not in src:
+        src[l[0]] = open(path).read().split("\n") if os.path.exists(path) else None
+    return (src[l[0]][l[1] - 1].strip()[:100] if src[l[0]] else l[0])
+print(f"total warp-instructions {ti} ({ti/iters:.1f} per iteration), samples {ts}")
+print("--- by samples (time)")
+for l, n in bys.most_common(28):
+    print(f"{n/ts*100:5.1f}% smp {byi[l]/iters:7.1f} inst/iter  {l[1] if l else 0:>4} {text(l)}")
