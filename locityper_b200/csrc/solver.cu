@@ -1,7 +1,8 @@
 // solver.cu -- a5..a13: one solver stage on the device.
 //
-// One WARP per logical worker (= one xoshiro256++ stream of the reference, src/solvers/solve.rs:1007-1018).
-// A worker solves its genotypes back to back on that stream exactly like Worker::run (:1104-1145):
+// One lane GROUP (GS = 16 lanes, two groups per warp; GS = 32 selectable) per logical worker (= one
+// xoshiro256++ stream of the reference, src/solvers/solve.rs:1007-1018).  A worker solves its genotypes
+// back to back on that stream exactly like Worker::run (:1104-1145):
 //   per genotype: GenotypeAlignments::new (src/model/assgn.rs:41-84, windows.rs:762-797)   -> build_instance
 //   per attempt : apply_tweak (assgn.rs:127-151, windows.rs:123-136,478-486)               -> apply_tweak
 //                 Solver::solve (solvers/mod.rs:61-72) = Greedy (stoch.rs:81-120) | SimAnneal (:197-242)
@@ -10,11 +11,14 @@
 //
 // Exactness: all f64 arithmetic that feeds an accept/reject uses the non-contracting intrinsics
 // (__dadd_rn/__dmul_rn/__dsub_rn) in the reference's association order; the file is also compiled with
-// -fmad=false.  The RNG state is replicated in every lane (all lanes step it identically), so draws are
-// consumed in exactly the reference's order with warp-uniform control flow.
+// -fmad=false.  Random draws are consumed in exactly the reference's order (see "RNG stream").
 //
-// Per-worker state: depth[], window distributions and the two likelihood accumulators live in shared
-// memory / registers; candidate arrays live in a per-warp global slab (L2-resident for typical loci).
+// Data placement per worker:
+//   shared memory : window records (weight, table row, depth), compact offsets + current assignment of
+//                   the non-trivial reads, a 2-stage cp.async staging area for the greedy pipeline;
+//   registers     : the two likelihood accumulators, RNG window;
+//   global slab   : candidate arrays in read order (build / tweak / counts) and a compact copy of the
+//                   non-trivial reads' candidates (what the solver loops touch), RNG draw buffer.
 #include "common.cuh"
 
 #include <cmath>
@@ -24,8 +28,12 @@
 
 namespace lctp {
 
-static constexpr int WARPS_PER_CTA = 4;
-static constexpr unsigned FULL = 0xFFFFFFFFu;
+static constexpr int CTA_THREADS = 128;
+static constexpr int MAX_SAMPLE = 11;          // Floyd branch of rand::seq::index::sample
+static constexpr int STAGE_CANDS = 8;          // candidates per sampled read staged in smem (rest: global)
+static constexpr int RNG_C = 64;               // stream outputs generated per lane per fill
+static constexpr int RNG_BUF = 32 * RNG_C;     // slab space for one fill (GS * RNG_C <= this)
+static constexpr int N_SETUP_MATS = 5;         // T^(C*2^k), k = 0..4
 
 struct StageParams {
     uint32_t kind, attempts, best_start, sample_size;
@@ -36,12 +44,15 @@ struct StageParams {
 };
 
 struct Slab {
-    double *cand_lnprob;   // [cap]
+    double *cand_lnprob;   // [cap]  candidates of every read, read-major, sorted per read (a5)
     uint32_t *cand_w;      // [cap]  (w1 | w2 << 16)
     uint32_t *cand_src;    // [cap]  index into cm arrays, LCTP_NONE_U32 = "both mates unmapped" option
+    uint32_t *cand_ntc;    // [cap]  index into the compact arrays, LCTP_NONE_U32 for trivial reads
     uint32_t *read_off;    // [R+1]
+    uint4 *ntc;            // [cap]  compact copy of the non-trivial reads' candidates, in read order:
+                           //        x,y = ln_prob (f64 bits), z = windows (w1 | w2 << 16), w unused
     uint8_t *cand_cix;     // [cap]
-    uint64_t *rng_buf;     // [RNG_FILL] pre-generated draws of the worker's stream
+    uint64_t *rng_buf;     // [RNG_BUF] pre-generated draws of the worker's stream
     uint64_t *rng_blk;     // [32*4] block-start generator states of the current fill
 };
 
@@ -51,39 +62,66 @@ __host__ __device__ inline size_t slab_layout(uint32_t cap, uint32_t R, unsigned
     size_t o = 0;
     if (s) s->cand_lnprob = (double *)(base + o);
     o += align_up((size_t)cap * 8, 128);
+    if (s) s->ntc = (uint4 *)(base + o);
+    o += align_up((size_t)cap * 16, 128);
     if (s) s->cand_w = (uint32_t *)(base + o);
     o += align_up((size_t)cap * 4, 128);
     if (s) s->cand_src = (uint32_t *)(base + o);
+    o += align_up((size_t)cap * 4, 128);
+    if (s) s->cand_ntc = (uint32_t *)(base + o);
     o += align_up((size_t)cap * 4, 128);
     if (s) s->read_off = (uint32_t *)(base + o);
     o += align_up(((size_t)R + 1) * 4, 128);
     if (s) s->cand_cix = (uint8_t *)(base + o);
     o += align_up((size_t)cap, 128);
     if (s) s->rng_buf = (uint64_t *)(base + o);
-    o += (size_t)2048 * 8;
+    o += (size_t)RNG_BUF * 8;
     if (s) s->rng_blk = (uint64_t *)(base + o);
     o += 32 * 4 * 8;
     return o;
 }
 
+// ------------------------------------------------------------------ lane groups -----------------
+
+// A worker is served by GS consecutive lanes of a warp.  All collectives are restricted to the group's
+// lane mask, so the two groups of a warp run two independent workers in the same instruction stream.
+template <int GS>
+struct Grp {
+    unsigned mask;
+    int shift, lane;
+    __device__ Grp() {
+        const int wl = threadIdx.x & 31;
+        shift = GS == 32 ? 0 : (wl & ~(GS - 1));
+        mask = GS == 32 ? 0xFFFFFFFFu : (((1u << GS) - 1u) << shift);
+        lane = wl & (GS - 1);
+    }
+    static constexpr unsigned LM = GS == 32 ? 0xFFFFFFFFu : ((1u << GS) - 1u);
+    template <typename T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(mask, v, src, GS); }
+    template <typename T> __device__ __forceinline__ T shfl_up(T v, int d) const { return __shfl_up_sync(mask, v, d, GS); }
+    template <typename T> __device__ __forceinline__ T shfl_xor(T v, int m) const { return __shfl_xor_sync(mask, v, m, GS); }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) >> shift) & LM; }
+    __device__ __forceinline__ bool any(bool p) const { return __any_sync(mask, p) != 0; }
+    __device__ __forceinline__ unsigned match_any(uint32_t v) const { return (__match_any_sync(mask, v) >> shift) & LM; }
+    __device__ __forceinline__ uint32_t rmax(uint32_t v) const { return __reduce_max_sync(mask, v); }
+    __device__ __forceinline__ uint32_t rmin(uint32_t v) const { return __reduce_min_sync(mask, v); }
+    __device__ __forceinline__ uint32_t ror(uint32_t v) const { return __reduce_or_sync(mask, v); }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ unsigned lt() const { return (1u << lane) - 1u; }
+};
+
 // ------------------------------------------------------------------ RNG stream -------------------
 //
 // The reference consumes ONE sequential xoshiro256++ stream per worker.  Stepping that generator
-// redundantly in all 32 lanes costs ~25 instructions per draw and was a third of the solver's issue
-// slots.  Instead the warp pre-generates the stream in bulk: xoshiro's state transition is linear over
-// GF(2), so lane l jumps its copy of the state ahead by l*RNG_C steps (256x256 bit-matrix products with
-// host-precomputed powers of the transition matrix) and then generates RNG_C consecutive outputs of the
-// SAME sequential stream into a per-warp buffer: 32 lanes produce 2048 exact draws per fill.  Consumers
-// read the buffer through a 32-entry register window with warp shuffles, in stream order, so the draw
-// sequence (including the data-dependent extra draw of biased bounded samples) is bit-identical to the
-// sequential generator.  At the end of a worker the exact state at the consumed position is rebuilt
-// from the owning lane's block-start state.
+// redundantly in every lane costs ~25 instructions per draw.  Instead the group pre-generates the stream
+// in bulk: xoshiro's state transition is linear over GF(2), so lane l jumps its copy of the state ahead
+// by l*RNG_C steps (256x256 bit-matrix products with host-precomputed powers of the transition matrix)
+// and then generates RNG_C consecutive outputs of the SAME sequential stream into a per-worker buffer:
+// GS lanes produce GS*64 exact draws per fill.  Consumers read the buffer through a GS-entry register
+// window with shuffles, in stream order, so the draw sequence (including the data-dependent extra draw
+// of biased bounded samples) is bit-identical to the sequential generator.  At the end of a worker the
+// exact state at the consumed position is rebuilt from the owning lane's block-start state.
 
-static constexpr int RNG_C = 64;               // outputs per lane per fill
-static constexpr int RNG_FILL = 32 * RNG_C;    // 2048 draws per fill
-static constexpr int N_SETUP_MATS = 5;         // T^(C*2^k), k = 0..4
-
-__constant__ uint64_t c_refill_mat[256 * 4];   // T^(31*C): columns, 4 words each
+__constant__ uint64_t c_refill_mat[2][256 * 4];   // [0]: T^(15*C) for GS=16, [1]: T^(31*C) for GS=32
 
 struct Gen { uint64_t s0, s1, s2, s3; };
 
@@ -115,206 +153,212 @@ __device__ __forceinline__ void gen_mat_apply(Gen &g, const uint64_t *__restrict
     if (take) { g.s0 = a0; g.s1 = a1; g.s2 = a2; g.s3 = a3; }
 }
 
+template <int GS>
 struct Xo {                // the worker's stream as seen by the solver code
-    Gen g;                 // this lane's generator (positioned at the end of its block after a fill)
-    uint32_t win_lo, win_hi;   // register window: buf[(pos & ~31) + lane]
+    static constexpr uint32_t FILL = GS * RNG_C;
+    Grp<GS> g;
+    Gen gen;               // this lane's generator (positioned at the end of its block after a fill)
+    uint32_t win_lo, win_hi;   // register window: buf[wbase + lane]
     uint32_t pos;          // draws consumed from the current fill
     uint32_t wbase;        // stream position held by lane 0 of the register window
-    uint64_t *buf;         // [RNG_FILL] per-warp buffer (global, L2-resident)
-    uint64_t *blk;         // [32][4] block-start states of the current fill
-    int lane;
+    uint64_t *buf;         // [FILL] per-worker buffer (global, L2-resident)
+    uint64_t *blk;         // [GS][4] block-start states of the current fill
 };
 
-__device__ __forceinline__ void stream_fill(Xo &x) {
-    uint64_t *b = x.blk + x.lane * 4;
-    b[0] = x.g.s0; b[1] = x.g.s1; b[2] = x.g.s2; b[3] = x.g.s3;
-    uint64_t *o = x.buf + x.lane * RNG_C;
+// Generate this lane's block of the next fill; returns the generator positioned at the block end.
+// Out of line and by value so that the caller's stream object never has its address taken (it would be
+// demoted to local memory otherwise).
+__device__ __noinline__ Gen fill_block(Gen gen, uint64_t *buf, uint64_t *blk, int lane, unsigned mask, int jump_mat) {
+    if (jump_mat >= 0) gen_mat_apply(gen, c_refill_mat[jump_mat], true);   // end of own block -> own block of the next fill
+    uint64_t *b = blk + lane * 4;
+    b[0] = gen.s0; b[1] = gen.s1; b[2] = gen.s2; b[3] = gen.s3;
+    uint64_t *o = buf + lane * RNG_C;
 #pragma unroll 4
-    for (int q = 0; q < RNG_C; q++) o[q] = gen_next(x.g);
+    for (int q = 0; q < RNG_C; q++) o[q] = gen_next(gen);
+    __syncwarp(mask);
+    return gen;
+}
+template <int GS>
+__device__ __forceinline__ void stream_fill(Xo<GS> &x, int jump_mat) {
+    x.gen = fill_block(x.gen, x.buf, x.blk, x.g.lane, x.g.mask, jump_mat);
     x.pos = 0;
     x.wbase = 0x80000000u;   // window invalid
-    __syncwarp();
 }
 
 // Start a stream from the scalar state st[4]: lane l jumps ahead by l*RNG_C (binary decomposition of l).
-__device__ void stream_begin(Xo &x, const uint64_t *__restrict__ st, const uint64_t *__restrict__ setup_mats) {
-    x.g.s0 = st[0]; x.g.s1 = st[1]; x.g.s2 = st[2]; x.g.s3 = st[3];
-    for (int k = 0; k < N_SETUP_MATS; k++) gen_mat_apply(x.g, setup_mats + (size_t)k * 1024, (x.lane >> k) & 1);
-    stream_fill(x);
+template <int GS>
+__device__ void stream_begin(Xo<GS> &x, const uint64_t *__restrict__ st, const uint64_t *__restrict__ setup_mats) {
+    x.gen.s0 = st[0]; x.gen.s1 = st[1]; x.gen.s2 = st[2]; x.gen.s3 = st[3];
+    constexpr int ROUNDS = GS == 32 ? 5 : 4;
+    for (int k = 0; k < ROUNDS; k++) gen_mat_apply(x.gen, setup_mats + (size_t)k * 1024, (x.g.lane >> k) & 1);
+    stream_fill(x, -1);
 }
 
-__device__ __noinline__ void stream_refill(Xo &x) {
-    gen_mat_apply(x.g, c_refill_mat, true);    // end of own block -> start of own block in the next fill
-    stream_fill(x);
-}
+template <int GS>
+__device__ __forceinline__ void stream_refill(Xo<GS> &x) { stream_fill(x, GS == 32 ? 1 : 0); }
 
 // Exact scalar state after the draws consumed so far (what the sequential generator would hold).
-__device__ void stream_end(Xo &x, uint64_t *__restrict__ out) {
-    __syncwarp();
-    Gen g;
-    int owner;
-    if (x.pos >= RNG_FILL) { owner = 31; g = x.g; }
-    else {
-        owner = x.pos / RNG_C;
-        const uint64_t *b = x.blk + owner * 4;
+template <int GS>
+__device__ void stream_end(Xo<GS> &x, uint64_t *__restrict__ out) {
+    x.g.sync();
+    Gen g = x.gen;                                        // pos == FILL: lane GS-1's copy is the state
+    int owner = GS - 1;
+    if (x.pos < Xo<GS>::FILL) {
+        const int blk_owner = x.pos / RNG_C;
+        const uint64_t *b = x.blk + blk_owner * 4;
         g.s0 = b[0]; g.s1 = b[1]; g.s2 = b[2]; g.s3 = b[3];
-        const int steps = x.pos - owner * RNG_C;
+        const int steps = x.pos - blk_owner * RNG_C;
         for (int q = 0; q < steps; q++) gen_next(g);
+        owner = 0;                                        // every lane computed the same state
     }
-    if (x.lane == 0) { out[0] = g.s0; out[1] = g.s1; out[2] = g.s2; out[3] = g.s3; }
+    if (x.g.lane == owner) { out[0] = g.s0; out[1] = g.s1; out[2] = g.s2; out[3] = g.s3; }
 }
 
-// Make the register window cover stream positions [pos, pos + count); false = the fill ends first
-// (the caller then falls back to the one-draw-at-a-time path, which refills).
-__device__ __forceinline__ bool stream_cover(Xo &x, uint32_t count) {
-    if (x.pos + count > (uint32_t)RNG_FILL) return false;
-    if (x.pos - x.wbase + count > 32u) {          // also true when wbase is invalid (> pos)
+// Make the register window cover stream positions [pos, pos + count), count <= GS; false = the fill
+// ends first (the caller then uses the one-draw-at-a-time path, which refills).
+template <int GS>
+__device__ __forceinline__ bool stream_cover(Xo<GS> &x, uint32_t count) {
+    if (x.pos + count > Xo<GS>::FILL) return false;
+    if (x.pos - x.wbase + count > (uint32_t)GS) {          // also true when wbase is invalid (> pos)
         x.wbase = x.pos;
-        const uint64_t v = x.buf[min(x.pos + (uint32_t)x.lane, (uint32_t)RNG_FILL - 1u)];
+        const uint64_t v = __ldcg(x.buf + min(x.pos + (uint32_t)x.g.lane, Xo<GS>::FILL - 1u));
         x.win_lo = (uint32_t)v; x.win_hi = (uint32_t)(v >> 32);
     }
     return true;
 }
 // After stream_cover(count): the (pos + rank)-th draw of the stream, for any per-lane rank < count.
-__device__ __forceinline__ uint32_t stream_peek_hi(const Xo &x, uint32_t rank) {
-    return __shfl_sync(0xFFFFFFFFu, x.win_hi, (x.pos - x.wbase + rank) & 31u);
+template <int GS>
+__device__ __forceinline__ uint32_t stream_peek_hi(const Xo<GS> &x, uint32_t rank) {
+    return x.g.shfl(x.win_hi, (int)((x.pos - x.wbase + rank) & (GS - 1)));
 }
-__device__ __forceinline__ uint64_t stream_peek64(const Xo &x, uint32_t rank) {
-    const uint32_t src = (x.pos - x.wbase + rank) & 31u;
-    const uint32_t hi = __shfl_sync(0xFFFFFFFFu, x.win_hi, src);
-    const uint32_t lo = __shfl_sync(0xFFFFFFFFu, x.win_lo, src);
-    return ((uint64_t)hi << 32) | lo;
+template <int GS>
+__device__ __forceinline__ uint64_t stream_peek64(const Xo<GS> &x, uint32_t rank) {
+    const int src = (int)((x.pos - x.wbase + rank) & (GS - 1));
+    return ((uint64_t)x.g.shfl(x.win_hi, src) << 32) | x.g.shfl(x.win_lo, src);
 }
-
-__device__ __forceinline__ void stream_advance(Xo &x) {
-    if (x.pos == (uint32_t)RNG_FILL) stream_refill(x);
+template <int GS>
+__device__ __forceinline__ void stream_advance(Xo<GS> &x) {
+    if (x.pos == Xo<GS>::FILL) stream_refill(x);
     stream_cover(x, 1);
 }
-__device__ __forceinline__ uint32_t xo_u32(Xo &x) {   // next_u32 = upper half of next_u64
+template <int GS>
+__device__ __forceinline__ uint32_t xo_u32(Xo<GS> &x) {   // next_u32 = upper half of next_u64
     stream_advance(x);
     const uint32_t r = stream_peek_hi(x, 0);
     x.pos++;
     return r;
 }
-__device__ __forceinline__ uint64_t xo_next(Xo &x) {
+template <int GS>
+__device__ __forceinline__ uint64_t xo_next(Xo<GS> &x) {
     stream_advance(x);
     const uint64_t r = stream_peek64(x, 0);
     x.pos++;
     return r;
 }
-
-// Lane-parallel bounded draws: lanes < count each want random_range(0..range) and lane k must receive
-// the k-th draw of the stream.  Succeeds (and consumes `count` draws) only when no lane lands in the
-// biased zone -- which would consume an extra draw and shift every later lane -- otherwise nothing is
-// consumed and the caller runs the sequential path.  P(fallback) ~ count * range / 2^32.
-__device__ __forceinline__ bool xo_below_parallel(Xo &x, uint32_t count, uint32_t range, uint32_t &res) {
-    if (!stream_cover(x, count)) return false;
-    const uint64_t m = (uint64_t)stream_peek_hi(x, (uint32_t)x.lane) * (uint64_t)range;
-    const bool biased = (uint32_t)x.lane < count && (uint32_t)m > 0u - range;
-    if (__any_sync(0xFFFFFFFFu, biased)) return false;
-    res = (uint32_t)(m >> 32);
-    x.pos += count;
-    return true;
-}
-
 // rand UniformInt::sample_single_inclusive with a u32 sample type: value in [0, range), range != 0.
-__device__ __forceinline__ uint32_t xo_below(Xo &x, uint32_t range) {
+template <int GS>
+__device__ __forceinline__ uint32_t xo_below(Xo<GS> &x, uint32_t range) {
     const uint64_t m = (uint64_t)xo_u32(x) * (uint64_t)range;
     uint32_t res = (uint32_t)(m >> 32);
     const uint32_t lo = (uint32_t)m;
-    if (lo > 0u - range) {   // biased zone: one extra draw (warp-uniform branch)
+    if (lo > 0u - range) {   // biased zone: one extra draw (group-uniform branch)
         const uint32_t nh = (uint32_t)(((uint64_t)xo_u32(x) * (uint64_t)range) >> 32);
         res += (lo + nh < lo) ? 1u : 0u;
     }
     return res;
 }
 // rand StandardUniform f64 (src/solvers/stoch.rs:216)
-__device__ __forceinline__ double xo_f64(Xo &x) {
+template <int GS>
+__device__ __forceinline__ double xo_f64(Xo<GS> &x) {
     return (double)(xo_next(x) >> 11) * (1.0 / 9007199254740992.0);
+}
+// Lane-parallel bounded draws: lanes < count each want random_range(0..range) and lane k must receive
+// the k-th draw of the stream.  Succeeds (and consumes `count` draws) only when no lane lands in the
+// biased zone -- which would consume an extra draw and shift every later lane -- otherwise nothing is
+// consumed and the caller runs the sequential path.  P(fallback) ~ count * range / 2^32.
+template <int GS>
+__device__ __forceinline__ bool xo_below_parallel(Xo<GS> &x, uint32_t count, uint32_t range, uint32_t &res) {
+    if (!stream_cover(x, count)) return false;
+    const uint64_t m = (uint64_t)stream_peek_hi(x, (uint32_t)x.g.lane) * (uint64_t)range;
+    const bool biased = (uint32_t)x.g.lane < count && (uint32_t)m > 0u - range;
+    if (x.g.any(biased)) return false;
+    res = (uint32_t)(m >> 32);
+    x.pos += count;
+    return true;
 }
 
 // ------------------------------------------------------------------ small helpers ---------------
 
-__device__ __forceinline__ double shfl_d(double v, int src) {
-    return __shfl_sync(FULL, v, src);
-}
-__device__ __forceinline__ double shfl_xor_d(double v, int m) {
-    return __shfl_xor_sync(FULL, v, m);
-}
 // f64::total_cmp key (Rust std)
 __device__ __forceinline__ long long total_key(double v) {
     long long b = __double_as_longlong(v);
     return b ^ (long long)(((unsigned long long)(b >> 63)) >> 1);
 }
+// Monotone u64 key of an f64 (no NaNs on this path); 0 is below every valid key.
+__device__ __forceinline__ unsigned long long ord_key(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
+}
 
-// Per-window state in shared memory, one 16-byte record per window so a window costs one LDS.128:
-//   x,y = weight (f64 bits), z = row offset (gc * depth_k) into the depth table, w = current read depth.
-// TRIVIAL windows (WindowDistr::TRIVIAL, src/model/distr_cache.rs:27-30) are stored as weight 0 on the
-// all-zero extra row of the device table, so 0*0 - 0*0 = +0.0 reproduces the reference's literal 0.0 with
-// no branch; a zero depth change gives w*t - w*t = +0.0 the same way.
-// Also in shared memory, per worker: for every NON-TRIVIAL read (in read order) its candidate range
-// `nt_loc` = start | n << 24 and its current assignment `nt_assgn`, plus a 2-stage staging area that
-// cp.async fills with the candidates (ln_prob, windows) of the reads sampled for the NEXT greedy iteration.
-static constexpr int MAX_SAMPLE = 11;          // Floyd branch of rand::seq::index::sample
-static constexpr int STAGE_CANDS = 8;          // candidates per sampled read staged in smem (rest: global)
-struct WarpShared {
-    uint4 *win;          // [Wmax]
-    uint32_t *nt_loc;    // [R]
-    uint8_t *nt_assgn;   // [R]
-    double *st_lp;       // [2][MAX_SAMPLE][STAGE_CANDS]
-    uint32_t *st_w;      // [2][MAX_SAMPLE][STAGE_CANDS]
-    uint32_t zero_row;   // offset of the all-zero row
+// Per-window state in shared memory: one 64-byte record per window holding the window's weight, its
+// depth-table row, the current read depth d and the five products weight * table[row][d-2 .. d+2]
+// (rounded once, exactly as WindowDistr::ln_prob computes them, src/model/distr_cache.rs:34-39).  Every
+// likelihood delta of the solver loops is then a difference of two shared-memory values: no global loads.
+// TRIVIAL windows (WindowDistr::TRIVIAL, distr_cache.rs:27-30) are stored as weight 0 on the all-zero
+// extra row of the device table, so 0*0 - 0*0 = +0.0 reproduces the reference's literal 0.0 with no
+// branch; a zero depth change gives p - p = +0.0 the same way.
+struct __align__(16) WinRec {
+    double p[5];        // weight * table[row + depth + k - 2]
+    double weight;
+    uint32_t row;       // gc * depth_k
+    uint32_t depth;
+    uint32_t pad[2];
 };
-__host__ __device__ inline size_t warp_smem_bytes(uint32_t Wmax, uint32_t R) {
-    return align_up((size_t)Wmax * 16, 16) + align_up((size_t)R * 4, 16) + align_up((size_t)R, 16) +
-           (size_t)2 * MAX_SAMPLE * STAGE_CANDS * 12;
+static_assert(sizeof(WinRec) == 64, "WinRec must be 64 bytes");
+
+struct WarpShared {
+    WinRec *win;           // [Wmax]
+    uint16_t *ntc_start;   // [R+1]  compact candidate offset of every non-trivial read (+ end sentinel)
+    uint8_t *nt_assgn;     // [R]    current assignment of every non-trivial read
+    uint4 *st;             // [2][MAX_SAMPLE][STAGE_CANDS] staged candidate records
+    uint32_t zero_row;     // offset of the all-zero row
+    uint32_t depth_k;
+};
+__host__ __device__ inline size_t group_smem_bytes(uint32_t Wmax, uint32_t R) {
+    return (size_t)Wmax * 64 + align_up(((size_t)R + 1) * 2, 16) + align_up((size_t)R, 16) +
+           (size_t)2 * MAX_SAMPLE * STAGE_CANDS * 16;
 }
 
-__device__ __forceinline__ double win_weight(const uint4 &r) { return __hiloint2double((int)r.y, (int)r.x); }
-__device__ __forceinline__ uint4 make_win(double weight, uint32_t row, uint32_t depth) {
-    return make_uint4((uint32_t)__double2loint(weight), (uint32_t)__double2hiint(weight), row, depth);
+__device__ __forceinline__ double rec_lp(const uint4 &r) { return __hiloint2double((int)r.y, (int)r.x); }
+__device__ __forceinline__ uint4 make_rec(double lp, uint32_t w) {
+    return make_uint4((uint32_t)__double2loint(lp), (uint32_t)__double2hiint(lp), w, 0u);
 }
 
-// WindowDistr::ln_prob (src/model/distr_cache.rs:34-39)
-__device__ __forceinline__ double win_ln_prob(const WarpShared &ws, const double *__restrict__ table, uint32_t w) {
-    const uint4 r = ws.win[w];
-    return __dmul_rn(win_weight(r), __ldg(table + r.z + r.w));
+// Recompute slice entry k of window w from its (weight, row, depth).
+__device__ __forceinline__ void win_refresh(const WarpShared &ws, const double *__restrict__ table, uint32_t w, int k) {
+    WinRec &r = ws.win[w];
+    const int d = min(max((int)r.depth + k - 2, 0), (int)ws.depth_k - 1);   // out-of-range entries are never used
+    r.p[k] = __dmul_rn(r.weight, __ldg(table + r.row + d));
 }
 
 // atomic_depth_lik_diff (src/model/assgn.rs:244-254), branch-free
-__device__ __forceinline__ double atomic_diff(const WarpShared &ws, const double *__restrict__ table,
-                                              uint32_t w, int change) {
-    const uint4 r = ws.win[w];
-    const double wt = win_weight(r);
-    const double *row = table + r.z + r.w;
-    return __dsub_rn(__dmul_rn(wt, __ldg(row + change)), __dmul_rn(wt, __ldg(row)));
+__device__ __forceinline__ double atomic_diff(const WarpShared &ws, uint32_t w, int change) {
+    const WinRec &r = ws.win[w];
+    return __dsub_rn(r.p[2 + change], r.p[2]);
 }
 
 // depth_lik_diff (src/model/assgn.rs:259-284): ((a1 + a2) + a3) + a4, window merging done with selects
-__device__ __forceinline__ double depth_lik_diff(const WarpShared &ws, const double *__restrict__ table,
-                                                 uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4) {
+__device__ __forceinline__ double depth_lik_diff(const WarpShared &ws, uint32_t w12, uint32_t w34) {
+    const uint32_t w1 = w12 & 0xFFFFu, w2 = w12 >> 16, w3 = w34 & 0xFFFFu, w4 = w34 >> 16;
     const int e21 = w2 == w1, e31 = w3 == w1, e32 = (w3 == w2) & !e31;
     const int e41 = w4 == w1, e42 = (w4 == w2) & !e41, e43 = (w4 == w3) & !e41 & !e42;
     const int c1 = -1 - e21 + e31 + e41;
     const int c2 = e21 ? 0 : -1 + e32 + e42;
     const int c3 = (e31 | e32) ? 0 : 1 + e43;
     const int c4 = (e41 | e42 | e43) ? 0 : 1;
-    double s = __dadd_rn(atomic_diff(ws, table, w1, c1), atomic_diff(ws, table, w2, c2));
-    s = __dadd_rn(s, atomic_diff(ws, table, w3, c3));
-    return __dadd_rn(s, atomic_diff(ws, table, w4, c4));
-}
-
-// Monotone u64 key of an f64 (no NaNs on this path) and a REDUX-based "first lane holding the maximum".
-__device__ __forceinline__ unsigned long long ord_key(double v) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
-}
-__device__ __forceinline__ int warp_argmax_first(unsigned long long key) {
-    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
-    const uint32_t mh = __reduce_max_sync(FULL, hi);
-    const bool c = hi == mh;
-    const uint32_t ml = __reduce_max_sync(FULL, c ? lo : 0u);
-    return __ffs(__ballot_sync(FULL, c && lo == ml)) - 1;
+    double s = __dadd_rn(atomic_diff(ws, w1, c1), atomic_diff(ws, w2, c2));
+    s = __dadd_rn(s, atomic_diff(ws, w3, c3));
+    return __dadd_rn(s, atomic_diff(ws, w4, c4));
 }
 
 // ------------------------------------------------------------------ a5: instance build ----------
@@ -322,18 +366,22 @@ __device__ __forceinline__ int warp_argmax_first(unsigned long long key) {
 struct Instance {
     uint32_t haps[LCTP_MAX_PLOIDY];
     uint32_t wshift[LCTP_MAX_PLOIDY + 1];
-    uint32_t W, A, n_nt;
+    uint32_t W, A, n_nt, A_nt;
 };
 
 // GenotypeAlignments::new: per read, gather candidates of every genotype contig above the running
 // threshold, append the unmapped option, stable-sort descending (here: a p-way merge of the already
 // sorted per-contig lists, ties resolved in insertion order = contig order, unmapped last), cut at the
-// final threshold.  Returns false on slab overflow.
-__device__ bool build_instance(const LocusDev &L, const Slab &S, const WarpShared &ws, uint32_t cap, Instance &I, int lane) {
+// final threshold.  Candidates of non-trivial reads (> 1 candidate) are also written to the compact
+// arrays.  Returns false on slab overflow.
+template <int GS>
+__device__ bool build_instance(const LocusDev &L, const Slab &S, const WarpShared &ws, uint32_t cap, Instance &I,
+                               const Grp<GS> &g) {
     const uint32_t R = L.R, p = L.p;
-    uint32_t base = 0, nt_base = 0;
+    const int lane = g.lane;
+    uint32_t base = 0, nt_base = 0, ntc_base = 0;
     bool ok = true;
-    for (uint32_t r0 = 0; r0 < R; r0 += 32) {
+    for (uint32_t r0 = 0; r0 < R; r0 += GS) {
         const uint32_t r = r0 + lane;
         const bool valid = r < R;
         uint32_t lb[LCTP_MAX_PLOIDY], le[LCTP_MAX_PLOIDY];
@@ -358,22 +406,24 @@ __device__ bool build_instance(const LocusDev &L, const Slab &S, const WarpShare
             with_unm = unm >= thresh;
             nw += with_unm ? 1u : 0u;
         }
-        uint32_t incl = nw;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(FULL, incl, d);
-            if (lane >= d) incl += o;
-        }
-        const uint32_t total = __shfl_sync(FULL, incl, 31);
-        const uint32_t start = base + incl - nw;
         const bool nt = valid && nw > 1;
-        const unsigned ntmask = __ballot_sync(FULL, nt);
+        const uint32_t nw_nt = nt ? nw : 0u;
+        uint32_t incl = nw, incl_nt = nw_nt;
+#pragma unroll
+        for (int d = 1; d < GS; d <<= 1) {
+            const uint32_t o = g.shfl_up(incl, d), o2 = g.shfl_up(incl_nt, d);
+            if (lane >= d) { incl += o; incl_nt += o2; }
+        }
+        const uint32_t total = g.shfl(incl, GS - 1), total_nt = g.shfl(incl_nt, GS - 1);
+        const uint32_t start = base + incl - nw;
+        const uint32_t cstart = ntc_base + incl_nt - nw_nt;
+        const unsigned ntmask = g.ballot(nt);
         if (valid) S.read_off[r] = start;
-        if (base + total > cap) ok = false;
+        if (base + total > cap || ntc_base + total_nt > 65535u) ok = false;
         if (ok && valid) {
             if (nt) {
-                const uint32_t pos = nt_base + __popc(ntmask & ((1u << lane) - 1u));
-                ws.nt_loc[pos] = start | (nw << 24);
+                const uint32_t pos = nt_base + __popc(ntmask & g.lt());
+                ws.ntc_start[pos] = (uint16_t)cstart;
                 ws.nt_assgn[pos] = 0;
             }
             bool unm_left = with_unm;
@@ -388,27 +438,33 @@ __device__ bool build_instance(const LocusDev &L, const Slab &S, const WarpShare
                     }
                 }
                 const uint32_t o = start + t;
+                double lp;
                 if (bk >= 0 && !(unm_left && unm_key > bkey)) {
-                    S.cand_lnprob[o] = L.cm_lnprob[lb[bk]];
+                    lp = L.cm_lnprob[lb[bk]];
                     S.cand_src[o] = lb[bk];
                     S.cand_cix[o] = (uint8_t)bk;
                     lb[bk]++;
                 } else {
-                    S.cand_lnprob[o] = unm;
+                    lp = unm;
                     S.cand_src[o] = LCTP_NONE_U32;
                     S.cand_cix[o] = 255;
                     unm_left = false;
                 }
+                S.cand_lnprob[o] = lp;
                 S.cand_w[o] = 0;   // [UNMAPPED_WINDOW; 2] until apply_tweak
+                if (nt) { S.cand_ntc[o] = cstart + t; S.ntc[cstart + t] = make_rec(lp, 0u); }
+                else S.cand_ntc[o] = LCTP_NONE_U32;
             }
         }
         base += total;
+        ntc_base += total_nt;
         nt_base += __popc(ntmask);
     }
-    if (lane == 0) S.read_off[R] = base;
+    if (lane == 0) { S.read_off[R] = base; if (ok) ws.ntc_start[nt_base] = (uint16_t)ntc_base; }
     I.A = base;
     I.n_nt = nt_base;
-    __syncwarp();
+    I.A_nt = ntc_base;
+    g.sync();
     return ok;
 }
 
@@ -422,20 +478,22 @@ __device__ __forceinline__ uint32_t shifted_window(const LocusDev &L, uint32_t h
     return 1;   // BOUNDARY_WINDOW
 }
 
-__device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I, const WarpShared &ws,
-                            Xo &rng, int lane) {
+template <int GS>
+__device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I, const WarpShared &ws, Xo<GS> &rng) {
+    const Grp<GS> &g = rng.g;
+    const int lane = g.lane;
     const uint32_t tweak = L.tweak;
     const uint32_t span = 2 * tweak + 1;
     // (i) read middles: one next_u64 per candidate that has a parent, in candidate order
-    for (uint32_t c0 = 0; c0 < I.A; c0 += 32) {
+    for (uint32_t c0 = 0; c0 < I.A; c0 += GS) {
         const uint32_t c = c0 + lane;
         const uint32_t src = c < I.A ? S.cand_src[c] : LCTP_NONE_U32;
         const bool has_parent = src != LCTP_NONE_U32;
         uint64_t mine = 0;
         if (tweak != 0) {
-            const unsigned mask = __ballot_sync(FULL, has_parent);
-            const int my_rank = __popc(mask & ((1u << lane) - 1u));
-            const int n_draws = __popc(mask);
+            const unsigned m = g.ballot(has_parent);
+            const int my_rank = __popc(m & g.lt());
+            const int n_draws = __popc(m);
             if (stream_cover(rng, (uint32_t)n_draws)) {
                 mine = stream_peek64(rng, (uint32_t)my_rank);
                 rng.pos += (uint32_t)n_draws;
@@ -454,18 +512,21 @@ __device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I,
             const uint32_t t2 = tweak ? (uint32_t)mine % span : 0u;
             const uint32_t w1 = mid.x == LCTP_NONE_U32 ? 0u : shifted_window(L, hap, shift, mid.x + t1);
             const uint32_t w2 = mid.y == LCTP_NONE_U32 ? 0u : shifted_window(L, hap, shift, mid.y + t2);
-            S.cand_w[c] = w1 | (w2 << 16);
+            const uint32_t w = w1 | (w2 << 16);
+            S.cand_w[c] = w;
+            const uint32_t cc = S.cand_ntc[c];
+            if (cc != LCTP_NONE_U32) S.ntc[cc].z = w;
         }
     }
     // (ii) window distributions: one bounded i32 draw per window, contigs in genotype order
-    if (lane < 2) ws.win[lane] = make_win(0.0, ws.zero_row, 0);
+    if (lane < 2) { ws.win[lane].weight = 0.0; ws.win[lane].row = ws.zero_row; ws.win[lane].depth = 0; }
     for (uint32_t k = 0; k < L.p; k++) {
         const uint32_t hap = I.haps[k];
         const uint32_t nwin = L.hap_n_windows[hap];
         const uint32_t reg_start = L.hap_reg_start[hap], hlen = L.hap_len[hap];
         const uint64_t pos_off = L.hap_pos_off[hap];
-        for (uint32_t i0 = 0; i0 < nwin; i0 += 32) {
-            const uint32_t cnt = min(32u, nwin - i0);
+        for (uint32_t i0 = 0; i0 < nwin; i0 += GS) {
+            const uint32_t cnt = min((uint32_t)GS, nwin - i0);
             uint32_t my_wstart = 0;
             {
                 // generate_windows (windows.rs:478-486): random_range(-left..=right), one per window
@@ -489,35 +550,41 @@ __device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I,
                 const double weight = L.pos_weight[pos_off + idx];
                 const uint32_t gc = L.pos_gc[pos_off + idx];
                 const uint32_t w = I.wshift[k] + i0 + lane;
-                if (weight < L.min_weight || weight < 1e-7) ws.win[w] = make_win(0.0, ws.zero_row, 0);
-                else ws.win[w] = make_win(weight, gc * L.depth_k, 0);
+                const bool trivial = weight < L.min_weight || weight < 1e-7;
+                ws.win[w].weight = trivial ? 0.0 : weight;
+                ws.win[w].row = trivial ? ws.zero_row : gc * L.depth_k;
+                ws.win[w].depth = 0;
             }
         }
     }
-    __syncwarp();
+    g.sync();
 }
 
 // ------------------------------------------------------------------ a8: ReadAssignment::new -----
 
 // Sequentially (in index order) add `count` per-lane terms to acc: reproduces iter().sum() order.
-__device__ __forceinline__ void seq_add(double &acc, double term, int count) {
-    for (int q = 0; q < count; q++) acc = __dadd_rn(acc, shfl_d(term, q));
+template <int GS>
+__device__ __forceinline__ void seq_add(const Grp<GS> &g, double &acc, double term, int count) {
+    for (int q = 0; q < count; q++) acc = __dadd_rn(acc, g.shfl(term, q));
 }
 
 // init_mode 0: every read at candidate 0; 1: random_range(0..m) per non-trivial read (read order).
+template <int GS>
 __device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance &I, const WarpShared &ws,
-                                Xo &rng, int init_mode, double &aln_lik, double &depth_lik, int lane) {
-    for (uint32_t w = lane; w < I.W; w += 32) ws.win[w].w = 0;
+                                Xo<GS> &rng, int init_mode, double &aln_lik, double &depth_lik) {
+    const Grp<GS> &g = rng.g;
+    const int lane = g.lane;
+    for (uint32_t w = lane; w < I.W; w += GS) ws.win[w].depth = 0;
     // assignments of non-trivial reads
-    for (uint32_t i0 = 0; i0 < I.n_nt; i0 += 32) {
+    for (uint32_t i0 = 0; i0 < I.n_nt; i0 += GS) {
         const uint32_t i = i0 + lane;
-        const uint32_t my_n = i < I.n_nt ? ws.nt_loc[i] >> 24 : 1u;
+        const uint32_t my_n = i < I.n_nt ? (uint32_t)(ws.ntc_start[i + 1] - ws.ntc_start[i]) : 1u;
         uint32_t a = 0;
         if (init_mode == 1) {
-            const int cnt = (int)min(32u, I.n_nt - i0);
+            const int cnt = (int)min((uint32_t)GS, I.n_nt - i0);
             if (!xo_below_parallel(rng, (uint32_t)cnt, my_n, a)) {
                 for (int q = 0; q < cnt; q++) {
-                    const uint32_t m = __shfl_sync(FULL, my_n, q);
+                    const uint32_t m = g.shfl(my_n, q);
                     const uint32_t v = xo_below(rng, m);
                     if (lane == q) a = v;
                 }
@@ -525,37 +592,39 @@ __device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance
         }
         if (i < I.n_nt) ws.nt_assgn[i] = (uint8_t)a;
     }
-    __syncwarp();
+    g.sync();
     // depth counts + aln_lik in read order (src/model/assgn.rs:205-217,351-353)
     double al = 0.0;
     uint32_t nt_base = 0;
-    for (uint32_t r0 = 0; r0 < L.R; r0 += 32) {
+    for (uint32_t r0 = 0; r0 < L.R; r0 += GS) {
         const uint32_t r = r0 + lane;
         const bool valid = r < L.R;
         uint32_t start = 0, nw = 0;
         if (valid) { start = S.read_off[r]; nw = S.read_off[r + 1] - start; }
         const bool nt = valid && nw > 1;
-        const unsigned ntmask = __ballot_sync(FULL, nt);
+        const unsigned ntmask = g.ballot(nt);
         double term = 0.0;
         if (valid) {
             uint32_t a = 0;
-            if (nt) a = ws.nt_assgn[nt_base + __popc(ntmask & ((1u << lane) - 1u))];
+            if (nt) a = ws.nt_assgn[nt_base + __popc(ntmask & g.lt())];
             const uint32_t ix = start + a;
             term = S.cand_lnprob[ix];
             const uint32_t w12 = S.cand_w[ix];
-            atomicAdd(&ws.win[w12 & 0xFFFFu].w, 1u);
-            atomicAdd(&ws.win[w12 >> 16].w, 1u);
+            atomicAdd(&ws.win[w12 & 0xFFFFu].depth, 1u);
+            atomicAdd(&ws.win[w12 >> 16].depth, 1u);
         }
         nt_base += __popc(ntmask);
-        seq_add(al, term, (int)min(32u, L.R - r0));
+        seq_add(g, al, term, (int)min((uint32_t)GS, L.R - r0));
     }
-    __syncwarp();
+    g.sync();
+    for (uint32_t q = lane; q < I.W * 5u; q += GS) win_refresh(ws, L.depth_table, q / 5u, (int)(q % 5u));
+    g.sync();
     // depth_lik in window order (assgn.rs:347-350)
     double dl = 0.0;
-    for (uint32_t w0 = 0; w0 < I.W; w0 += 32) {
+    for (uint32_t w0 = 0; w0 < I.W; w0 += GS) {
         const uint32_t w = w0 + lane;
-        const double term = w < I.W ? win_ln_prob(ws, L.depth_table, w) : 0.0;
-        seq_add(dl, term, (int)min(32u, I.W - w0));
+        const double term = w < I.W ? ws.win[w].p[2] : 0.0;
+        seq_add(g, dl, term, (int)min((uint32_t)GS, I.W - w0));
     }
     aln_lik = al;
     depth_lik = dl;
@@ -563,22 +632,23 @@ __device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance
 
 // ------------------------------------------------------------------ a9: targets -----------------
 
-struct Target { uint32_t idx, n, old_a, new_a, old_ix, new_ix; };
+struct Target { uint32_t idx, n, old_a, new_a, old_ix, new_ix; };   // *_ix index the compact arrays
 
-// ReassignmentTarget::random (src/model/assgn.rs:451-471), warp-uniform
-__device__ __forceinline__ Target random_target(const WarpShared &ws, const Instance &I, Xo &rng) {
+// ReassignmentTarget::random (src/model/assgn.rs:451-471), group-uniform
+template <int GS>
+__device__ __forceinline__ Target random_target(const WarpShared &ws, const Instance &I, Xo<GS> &rng) {
     Target t;
     t.idx = xo_below(rng, I.n_nt);                     // random_range(0..n_nontrivial), usize via the u32 path
-    const uint32_t loc = ws.nt_loc[t.idx];
-    t.n = loc >> 24;
+    const uint32_t start = ws.ntc_start[t.idx];
+    t.n = ws.ntc_start[t.idx + 1] - start;
     t.old_a = ws.nt_assgn[t.idx];
     if (t.n == 2) t.new_a = 1u - t.old_a;
     else {
         const uint32_t i = 1u + xo_below(rng, t.n - 1u);   // random_range(1..n as u16)
         t.new_a = i <= t.old_a ? i - 1u : i;
     }
-    t.old_ix = (loc & 0xFFFFFFu) + t.old_a;
-    t.new_ix = (loc & 0xFFFFFFu) + t.new_a;
+    t.old_ix = start + t.old_a;
+    t.new_ix = start + t.new_a;
     return t;
 }
 
@@ -587,31 +657,41 @@ struct Move { double dld, dlp; uint32_t w12, w34; };
 // calculate_improvement (src/model/assgn.rs:321-328)
 __device__ __forceinline__ double calc_improvement(const LocusDev &L, const Slab &S, const WarpShared &ws,
                                                    const Target &t, Move &mv) {
-    mv.w12 = S.cand_w[t.old_ix];
-    mv.w34 = S.cand_w[t.new_ix];
-    mv.dld = depth_lik_diff(ws, L.depth_table, mv.w12 & 0xFFFFu, mv.w12 >> 16, mv.w34 & 0xFFFFu, mv.w34 >> 16);
-    mv.dlp = __dsub_rn(S.cand_lnprob[t.new_ix], S.cand_lnprob[t.old_ix]);
+    const uint4 ro = __ldcg(S.ntc + t.old_ix), rn = __ldcg(S.ntc + t.new_ix);
+    mv.w12 = ro.z;
+    mv.w34 = rn.z;
+    mv.dld = depth_lik_diff(ws, mv.w12, mv.w34);
+    mv.dlp = __dsub_rn(rec_lp(rn), rec_lp(ro));
     return __dadd_rn(__dmul_rn(L.depth_contrib, mv.dld), __dmul_rn(L.aln_contrib, mv.dlp));
 }
 
-// reassign (src/model/assgn.rs:331-343); warp-uniform inputs, lane 0 writes
-__device__ __forceinline__ void apply_move(const Slab &S, const WarpShared &ws, uint32_t idx, uint32_t n,
-                                           uint32_t new_a, const Move &mv, double &aln_lik, double &depth_lik,
-                                           int lane) {
+// reassign (src/model/assgn.rs:331-343); group-uniform inputs, lane 0 writes
+template <int GS>
+__device__ __forceinline__ void apply_move(const Grp<GS> &g, const WarpShared &ws, const double *__restrict__ table,
+                                           uint32_t idx, uint32_t new_a, const Move &mv, double &aln_lik,
+                                           double &depth_lik) {
     depth_lik = __dadd_rn(depth_lik, mv.dld);
     aln_lik = __dadd_rn(aln_lik, mv.dlp);
-    if (lane == 0) {
-        ws.win[mv.w34 & 0xFFFFu].w += 1;
-        ws.win[mv.w34 >> 16].w += 1;
-        ws.win[mv.w12 & 0xFFFFu].w -= 1;
-        ws.win[mv.w12 >> 16].w -= 1;
+    if (g.lane == 0) {
+        ws.win[mv.w34 & 0xFFFFu].depth += 1;
+        ws.win[mv.w34 >> 16].depth += 1;
+        ws.win[mv.w12 & 0xFFFFu].depth -= 1;
+        ws.win[mv.w12 >> 16].depth -= 1;
         ws.nt_assgn[idx] = (uint8_t)new_a;
     }
-    __syncwarp();
+    g.sync();
+    // slide the product slices of the (up to four) windows whose depth changed
+    for (int q = g.lane; q < 20; q += GS) {
+        const int j = q / 5;
+        const uint32_t w = j == 0 ? (mv.w12 & 0xFFFFu) : j == 1 ? (mv.w12 >> 16) : j == 2 ? (mv.w34 & 0xFFFFu) : (mv.w34 >> 16);
+        win_refresh(ws, table, w, q % 5);
+    }
+    g.sync();
 }
 
 // max_abs_random (src/solvers/stoch.rs:19-22) with INIT_ITER = 100
-__device__ double max_abs_random(const LocusDev &L, const Slab &S, const Instance &I, const WarpShared &ws, Xo &rng) {
+template <int GS>
+__device__ double max_abs_random(const LocusDev &L, const Slab &S, const Instance &I, const WarpShared &ws, Xo<GS> &rng) {
     double acc = 0.0;
     for (int q = 0; q < 100; q++) {
         const Target t = random_target(ws, I, rng);
@@ -623,134 +703,224 @@ __device__ double max_abs_random(const LocusDev &L, const Slab &S, const Instanc
 
 // ------------------------------------------------------------------ a10: Greedy -----------------
 
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+__device__ __forceinline__ void cp_async16_cg(void *smem, const void *gmem) {   // L2 only: keeps L1 for the table
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit_g() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all_g() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // One sample of `amount` distinct non-trivial reads (IndexedRandom::sample -> index::sample_floyd):
 // draw k is random_range(..=j_k), j_k = n_nt - amount + k; a draw equal to an earlier entry replaces
-// that entry by j_k.  `fast_only`: succeed only through the lane-parallel path (no refill, no biased
-// draw), so the caller can un-consume the draws again with `rng.pos -= amount`.
-__device__ __forceinline__ bool sample_reads(Xo &rng, uint32_t n_nt, uint32_t amount, bool fast_only,
-                                             uint32_t &myv, int lane) {
-    const uint32_t my_j = n_nt - amount + min((uint32_t)lane, amount - 1u);
+// that entry by j_k.  Lane k receives entry k.  `fast_only`: succeed only through the lane-parallel path
+// (no refill, no biased draw), so the caller can un-consume the draws again with `rng.pos -= amount`.
+template <int GS>
+__device__ __forceinline__ bool sample_reads(Xo<GS> &rng, uint32_t n_nt, uint32_t amount, bool fast_only, uint32_t &myv) {
+    const Grp<GS> &g = rng.g;
+    const uint32_t lane = (uint32_t)g.lane;
+    const uint32_t my_j = n_nt - amount + min(lane, amount - 1u);
     bool need_fixup = true;
     if (xo_below_parallel(rng, amount, my_j + 1u, myv)) {
         const unsigned amask = (1u << amount) - 1u;
-        const unsigned peers = __match_any_sync(FULL, (uint32_t)lane < amount ? myv : 0xFFFFFFFFu);
-        need_fixup = __any_sync(FULL, (uint32_t)lane < amount && (peers & amask) != (1u << lane));
+        const unsigned peers = g.match_any(lane < amount ? myv : 0xFFFFFFFFu);
+        need_fixup = g.any(lane < amount && (peers & amask) != (1u << lane));
     } else {
         if (fast_only) return false;
         for (uint32_t k = 0; k < amount; k++) {
             const uint32_t t = xo_below(rng, n_nt - amount + k + 1u);
-            if ((uint32_t)lane == k) myv = t;
+            if (lane == k) myv = t;
         }
     }
     if (need_fixup) {
         for (uint32_t k = 1; k < amount; k++) {
-            const uint32_t t = __shfl_sync(FULL, myv, k);
-            if ((uint32_t)lane < k && myv == t) myv = n_nt - amount + k;
+            const uint32_t t = g.shfl(myv, (int)k);
+            if (lane < k && myv == t) myv = n_nt - amount + k;
         }
     }
     return true;
 }
 
-// Stage the static candidate data of a sampled read: this lane copies the candidates it will evaluate
-// (c = sub, sub+2, ... < min(n, STAGE_CANDS)) from the slab into shared memory with cp.async.
-__device__ __forceinline__ void stage_read(const Slab &S, const WarpShared &ws, int stage, int slot, int sub,
-                                           uint32_t loc) {
-    const uint32_t start = loc & 0xFFFFFFu, n = min(loc >> 24, (uint32_t)STAGE_CANDS);
-    double *lp = ws.st_lp + (stage * MAX_SAMPLE + slot) * STAGE_CANDS;
-    uint32_t *w = ws.st_w + (stage * MAX_SAMPLE + slot) * STAGE_CANDS;
-    for (uint32_t c = sub; c < n; c += 2) {
-        cp_async8(lp + c, S.cand_lnprob + start + c);
-        cp_async4(w + c, S.cand_w + start + c);
+// Stage the static candidate records of a sample (lane s < amount owns slot s with candidates
+// [start, start + n) in the compact array): the (slot, candidate) pairs are flattened over the lanes and
+// each lane copies one 16-byte record into shared memory with cp.async.cg.  `incl_n` is the inclusive
+// scan of n over the slots.  Only the first STAGE_CANDS candidates of a read are staged.
+template <int GS>
+__device__ __forceinline__ void stage_sample(const Grp<GS> &g, const Slab &S, const WarpShared &ws, int stage,
+                                             bool slot_lane, uint32_t start, uint32_t n, uint32_t incl_n) {
+    const uint32_t N = g.shfl(incl_n, GS - 1);
+    const uint32_t offn = incl_n - n;
+    if (N <= 64u) {
+        const unsigned long long hb = slot_lane ? 1ull << offn : 0ull;
+        const unsigned long long heads = ((unsigned long long)g.ror((uint32_t)(hb >> 32)) << 32) | g.ror((uint32_t)hb);
+        for (uint32_t j0 = 0; j0 < N; j0 += GS) {
+            const uint32_t j = j0 + (uint32_t)g.lane;
+            const bool act = j < N;
+            const int slot = act ? __popcll(heads & ((2ull << j) - 1ull)) - 1 : 0;
+            const uint32_t s_off = g.shfl(offn, slot), s_start = g.shfl(start, slot);
+            const uint32_t c = j - s_off;
+            if (act && c < (uint32_t)STAGE_CANDS)
+                cp_async16_cg(ws.st + (stage * MAX_SAMPLE + slot) * STAGE_CANDS + c, S.ntc + s_start + c);
+        }
+    } else if (slot_lane) {
+        const uint32_t m = min(n, (uint32_t)STAGE_CANDS);
+        for (uint32_t c = 0; c < m; c++)
+            cp_async16_cg(ws.st + (stage * MAX_SAMPLE + g.lane) * STAGE_CANDS + c, S.ntc + start + c);
     }
 }
 
-// Greedy::solve_nontrivial (src/solvers/stoch.rs:81-120).  Two lanes per sampled read evaluate its
-// candidates (best_read_improvement, src/model/assgn.rs:287-317).  Software pipeline: the sample of
-// iteration i+1 is drawn and its (static) candidate data is cp.async-staged while iteration i is
-// evaluated, so an iteration touches only shared memory and the L1-resident depth table.
+// A candidate move as seen by one lane, ordered like the reference's two nested strict-'>' scans:
+// larger improvement `s` first; among equal `s` the earlier sampled read (slot); inside that read the
+// larger `improv` (pre-scaling value compared by best_read_improvement), then the lower candidate index.
+struct Cand {
+    double s, improv, dld, dlp;
+    uint32_t slot, c, w12, w34;
+};
+__device__ __forceinline__ bool cand_better(const Cand &a, const Cand &b) {
+    if (a.s != b.s) return a.s > b.s;
+    if (a.slot != b.slot) return a.slot < b.slot;
+    if (a.improv != b.improv) return a.improv > b.improv;
+    return a.c < b.c;
+}
+
+// Greedy::solve_nontrivial (src/solvers/stoch.rs:81-120).
+// Every (sampled read, alternative candidate) pair of an iteration is one lane's job ("flattened"
+// best_read_improvement, src/model/assgn.rs:287-317); the winner is found with REDUX reductions in the
+// reference's tie order.  Software pipeline: the sample of iteration i+1 is drawn and its (static)
+// candidate data is cp.async-staged while iteration i is evaluated, so an iteration touches only shared
+// memory and the cached depth table.
+template <int GS>
 __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab &S, const Instance &I,
-                             const WarpShared &ws, Xo &rng, double &aln_lik, double &depth_lik,
-                             uint64_t &iters_out, int lane) {
+                             const WarpShared &ws, Xo<GS> &rng, double &aln_lik, double &depth_lik,
+                             uint64_t &iters_out) {
+    const Grp<GS> &g = rng.g;
+    const uint32_t lane = (uint32_t)g.lane;
     const uint32_t amount = min(P.sample_size, I.n_nt);
-    init_assignment(L, S, I, ws, rng, P.best_start ? 0 : 1, aln_lik, depth_lik, lane);
+    init_assignment(L, S, I, ws, rng, P.best_start ? 0 : 1, aln_lik, depth_lik);
     const double min_diff = fmax(__dmul_rn(1e-10, max_abs_random(L, S, I, ws, rng)), 1e-14);
-    const int slot = lane >> 1, sub = lane & 1;
-    const bool active = (uint32_t)slot < amount;
+    const bool slot_lane = lane < amount;
     uint64_t curr_plato = 0, it = 0;
     bool have_next = false;
-    uint32_t next_idx = 0, next_loc = 0;
+    uint32_t next_idx = 0, next_start = 0, next_n = 0, next_incl = 0;
     int stage = 0;
+    // inclusive scan over the slots of a per-slot value (0 on non-slot lanes)
+    auto scan_slots = [&](uint32_t v) {
+#pragma unroll
+        for (int d = 1; d < GS; d <<= 1) {
+            const uint32_t o = g.shfl_up(v, d);
+            if ((int)lane >= d) v += o;
+        }
+        return v;
+    };
     for (; it < P.max_iter; it++) {
-        uint32_t idx, loc;
-        if (have_next) { idx = next_idx; loc = next_loc; }
+        uint32_t idx, start, n, incl_n;          // of the read sampled in slot == lane
+        if (have_next) { idx = next_idx; start = next_start; n = next_n; incl_n = next_incl; }
         else {
-            uint32_t myv = 0;
-            sample_reads(rng, I.n_nt, amount, false, myv, lane);
-            idx = __shfl_sync(FULL, myv, slot);
-            loc = active ? ws.nt_loc[idx] : 0u;
-            if (active) stage_read(S, ws, stage, slot, sub, loc);
+            idx = 0;
+            sample_reads(rng, I.n_nt, amount, false, idx);
+            start = slot_lane ? ws.ntc_start[idx] : 0u;
+            n = slot_lane ? ws.ntc_start[idx + 1] - start : 0u;
+            incl_n = scan_slots(n);
+            stage_sample(g, S, ws, stage, slot_lane, start, n, incl_n);
             cp_async_commit_g();
         }
         cp_async_wait_all_g();
-        __syncwarp();
+        g.sync();
         {   // pre-draw the next sample and start staging it
             uint32_t myv = 0;
-            have_next = sample_reads(rng, I.n_nt, amount, true, myv, lane);
+            have_next = sample_reads(rng, I.n_nt, amount, true, myv);
             if (have_next) {
-                next_idx = __shfl_sync(FULL, myv, slot);
-                next_loc = active ? ws.nt_loc[next_idx] : 0u;
-                if (active) stage_read(S, ws, stage ^ 1, slot, sub, next_loc);
+                next_idx = myv;
+                next_start = slot_lane ? ws.ntc_start[myv] : 0u;
+                next_n = slot_lane ? ws.ntc_start[myv + 1] - next_start : 0u;
+                next_incl = scan_slots(next_n);
+                stage_sample(g, S, ws, stage ^ 1, slot_lane, next_start, next_n, next_incl);
                 cp_async_commit_g();
             }
         }
-        // best_read_improvement for every sampled read
-        double best = -INFINITY, b_dld = 0.0, b_lp = 0.0, lp_old = 0.0;
-        uint32_t b_c = 0, b_w34 = 0, w12 = 0;
-        const uint32_t start = loc & 0xFFFFFFu, n = loc >> 24;
-        if (active) {
-            const double *slp = ws.st_lp + (stage * MAX_SAMPLE + slot) * STAGE_CANDS;
-            const uint32_t *sw = ws.st_w + (stage * MAX_SAMPLE + slot) * STAGE_CANDS;
-            const uint32_t old_a = ws.nt_assgn[idx];
-            if (old_a < (uint32_t)STAGE_CANDS) { lp_old = slp[old_a]; w12 = sw[old_a]; }
-            else { lp_old = S.cand_lnprob[start + old_a]; w12 = S.cand_w[start + old_a]; }
-            for (uint32_t c = sub; c < n; c += 2) {
-                if (c == old_a) continue;
-                double lp; uint32_t w34;
-                if (c < (uint32_t)STAGE_CANDS) { lp = slp[c]; w34 = sw[c]; }
-                else { lp = S.cand_lnprob[start + c]; w34 = S.cand_w[start + c]; }
-                const double dld = depth_lik_diff(ws, L.depth_table, w12 & 0xFFFFu, w12 >> 16, w34 & 0xFFFFu, w34 >> 16);
-                const double improv = __dadd_rn(lp, __dmul_rn(L.rel_contrib, dld));
-                if (improv > best) { best = improv; b_c = c; b_dld = dld; b_lp = lp; b_w34 = w34; }
+        // flatten (slot, alternative candidate) pairs: slot s contributes n_s - 1 evaluations, so its
+        // first evaluation index is (exclusive scan of n)_s - s
+        const uint32_t old_a = slot_lane ? ws.nt_assgn[idx] : 0u;
+        const uint32_t E = g.shfl(incl_n, GS - 1) - amount;
+        const uint32_t off = incl_n - n - (slot_lane ? lane : 0u);
+        Cand best;
+        best.s = -INFINITY; best.improv = -INFINITY; best.dld = 0.0; best.dlp = 0.0;
+        best.slot = 0xFFFFu; best.c = 0; best.w12 = 0; best.w34 = 0;
+        if (E <= 64u) {
+            // head flags: bit `off_s` marks the first evaluation of slot s
+            const unsigned long long hb = slot_lane ? 1ull << off : 0ull;
+            const unsigned long long heads = ((unsigned long long)g.ror((uint32_t)(hb >> 32)) << 32) | g.ror((uint32_t)hb);
+            for (uint32_t e0 = 0; e0 < E; e0 += GS) {
+                const uint32_t e = e0 + lane;
+                const bool act = e < E;
+                const int slot = act ? __popcll(heads & ((2ull << e) - 1ull)) - 1 : 0;
+                const uint32_t s_off = g.shfl(off, slot), s_old = g.shfl(old_a, slot), s_start = g.shfl(start, slot);
+                if (act) {
+                    const uint32_t cr = e - s_off;
+                    const uint32_t c = cr < s_old ? cr : cr + 1u;
+                    const uint4 *st = ws.st + (stage * MAX_SAMPLE + slot) * STAGE_CANDS;
+                    const uint4 ro = s_old < (uint32_t)STAGE_CANDS ? st[s_old] : __ldcg(S.ntc + s_start + s_old);
+                    const uint4 rn = c < (uint32_t)STAGE_CANDS ? st[c] : __ldcg(S.ntc + s_start + c);
+                    const double lp_old = rec_lp(ro), lp = rec_lp(rn);
+                    Cand cd;
+                    cd.dld = depth_lik_diff(ws, ro.z, rn.z);
+                    cd.improv = __dadd_rn(lp, __dmul_rn(L.rel_contrib, cd.dld));          // assgn.rs:303
+                    cd.s = __dmul_rn(L.aln_contrib, __dsub_rn(cd.improv, lp_old));        // assgn.rs:310
+                    cd.dlp = __dsub_rn(lp, lp_old);
+                    cd.slot = (uint32_t)slot; cd.c = c; cd.w12 = ro.z; cd.w34 = rn.z;
+                    if (cand_better(cd, best)) best = cd;
+                }
+            }
+        } else {
+            // many candidates per read: one read at a time, lanes over its candidates
+            for (uint32_t s = 0; s < amount; s++) {
+                const uint32_t s_n = g.shfl(n, (int)s), s_old = g.shfl(old_a, (int)s), s_start = g.shfl(start, (int)s);
+                const uint4 ro = __ldcg(S.ntc + s_start + s_old);
+                const double lp_old = rec_lp(ro);
+                for (uint32_t c = lane; c < s_n; c += GS) {
+                    if (c == s_old) continue;
+                    const uint4 rn = __ldcg(S.ntc + s_start + c);
+                    const double lp = rec_lp(rn);
+                    Cand cd;
+                    cd.dld = depth_lik_diff(ws, ro.z, rn.z);
+                    cd.improv = __dadd_rn(lp, __dmul_rn(L.rel_contrib, cd.dld));
+                    cd.s = __dmul_rn(L.aln_contrib, __dsub_rn(cd.improv, lp_old));
+                    cd.dlp = __dsub_rn(lp, lp_old);
+                    cd.slot = s; cd.c = c; cd.w12 = ro.z; cd.w34 = rn.z;
+                    if (cand_better(cd, best)) best = cd;
+                }
             }
         }
-        {   // merge the two lanes of a read: strict '>' in candidate order = lowest index wins ties
-            const double o_best = shfl_xor_d(best, 1);
-            const uint32_t o_c = __shfl_xor_sync(FULL, b_c, 1);
-            if (o_best > best || (o_best == best && o_c < b_c)) { best = o_best; b_c = o_c; }
+        // winner over the lanes' bests, in the order of cand_better
+        int wl;
+        {
+            const unsigned long long ks = ord_key(best.s);
+            const uint32_t h1 = g.rmax((uint32_t)(ks >> 32));
+            bool m = (uint32_t)(ks >> 32) == h1;
+            const uint32_t l1 = g.rmax(m ? (uint32_t)ks : 0u);
+            m = m && (uint32_t)ks == l1;
+            const unsigned tied = g.ballot(m);
+            if ((tied & (tied - 1u)) == 0u) wl = __ffs(tied) - 1;      // unique maximum (the usual case)
+            else {
+            const uint32_t sl = g.rmin(m ? best.slot : 0xFFFFFFFFu);
+            m = m && best.slot == sl;
+            const unsigned long long ki = ord_key(best.improv);
+            const uint32_t h2 = g.rmax(m ? (uint32_t)(ki >> 32) : 0u);
+            m = m && (uint32_t)(ki >> 32) == h2;
+            const uint32_t l2 = g.rmax(m ? (uint32_t)ki : 0u);
+            m = m && (uint32_t)ki == l2;
+            const uint32_t cm = g.rmin(m ? best.c : 0xFFFFFFFFu);
+            wl = __ffs(g.ballot(m && best.c == cm)) - 1;
+            }
         }
-        // assgn.rs:310; across reads the first (lowest slot) strictly-greater improvement wins
-        const double s_improv = active ? __dmul_rn(L.aln_contrib, __dsub_rn(best, lp_old)) : -INFINITY;
-        const int wl0 = warp_argmax_first(ord_key(s_improv));
-        const double s_best = shfl_d(s_improv, wl0);
-        const uint32_t win_c = __shfl_sync(FULL, b_c, wl0);
+        const double s_best = g.shfl(best.s, wl);
         if (s_best > min_diff) {
-            const int wl = (wl0 & ~1) | (int)(win_c & 1u);   // lane that evaluated the winning candidate
             Move mv;
-            mv.dld = shfl_d(b_dld, wl);
-            mv.dlp = shfl_d(__dsub_rn(b_lp, lp_old), wl);
-            mv.w12 = __shfl_sync(FULL, w12, wl);
-            mv.w34 = __shfl_sync(FULL, b_w34, wl);
-            const uint32_t w_idx = __shfl_sync(FULL, idx, wl);
-            apply_move(S, ws, w_idx, 0, win_c, mv, aln_lik, depth_lik, lane);
+            mv.dld = g.shfl(best.dld, wl);
+            mv.dlp = g.shfl(best.dlp, wl);
+            mv.w12 = g.shfl(best.w12, wl);
+            mv.w34 = g.shfl(best.w34, wl);
+            const uint32_t w_slot = g.shfl(best.slot, wl), w_c = g.shfl(best.c, wl);
+            const uint32_t w_idx = g.shfl(idx, (int)w_slot);
+            apply_move(g, ws, L.depth_table, w_idx, w_c, mv, aln_lik, depth_lik);
             curr_plato = 0;
         } else {
             curr_plato += 1;
@@ -760,16 +930,19 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
     }
     if (have_next) rng.pos -= amount;     // the pre-drawn sample of the iteration that never ran
     cp_async_wait_all_g();
-    __syncwarp();
+    g.sync();
     iters_out += it;
 }
 
 // ------------------------------------------------------------------ a11: SimAnneal --------------
 
+// SimAnneal::solve_nontrivial (src/solvers/stoch.rs:197-242): one candidate per step, group-uniform.
+template <int GS>
 __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab &S, const Instance &I,
-                             const WarpShared &ws, Xo &rng, double &aln_lik, double &depth_lik,
-                             uint64_t &iters_out, int lane) {
-    init_assignment(L, S, I, ws, rng, 1, aln_lik, depth_lik, lane);
+                             const WarpShared &ws, Xo<GS> &rng, double &aln_lik, double &depth_lik,
+                             uint64_t &iters_out) {
+    const Grp<GS> &g = rng.g;
+    init_assignment(L, S, I, ws, rng, 1, aln_lik, depth_lik);
     const double max_abs = max_abs_random(L, S, I, ws, rng);
     const double min_diff = fmax(__dmul_rn(1e-10, max_abs), 1e-14);
     const double start_temp = fmax(__ddiv_rn(-max_abs, P.ln_init_prob), 1e-5);
@@ -785,7 +958,7 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
             const double u = xo_f64(rng);
             accept = u <= exp(__ddiv_rn(diff, __dmul_rn(temp_step, (double)i)));
         }
-        if (accept) { apply_move(S, ws, t.idx, t.n, t.new_a, mv, aln_lik, depth_lik, lane); curr_plato = 0; }
+        if (accept) { apply_move(g, ws, L.depth_table, t.idx, t.new_a, mv, aln_lik, depth_lik); curr_plato = 0; }
         else { curr_plato += 1; if (curr_plato >= P.plato_size) break; }
     }
     for (uint64_t k = 0; k < P.max_iter; k++) {
@@ -794,7 +967,7 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
         Move mv;
         const double diff = calc_improvement(L, S, ws, t, mv);
         steps++;
-        if (diff > min_diff) { apply_move(S, ws, t.idx, t.n, t.new_a, mv, aln_lik, depth_lik, lane); curr_plato = 0; }
+        if (diff > min_diff) { apply_move(g, ws, L.depth_table, t.idx, t.new_a, mv, aln_lik, depth_lik); curr_plato = 0; }
         else curr_plato += 1;
     }
     iters_out += steps;
@@ -802,7 +975,11 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
 
 // ------------------------------------------------------------------ stage kernel ----------------
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+#ifndef LCTP_MIN_CTAS
+#define LCTP_MIN_CTAS 4
+#endif
+template <int GS>
+__global__ void __launch_bounds__(CTA_THREADS, LCTP_MIN_CTAS)
 k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs,
               const uint64_t *__restrict__ worker_off, const uint32_t *__restrict__ tuples,
               uint64_t *__restrict__ rng_states, double *__restrict__ lik_mean, double *__restrict__ lik_var,
@@ -811,32 +988,34 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
               unsigned int *__restrict__ work_counter, int *__restrict__ err,
               const uint64_t *__restrict__ setup_mats) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int GROUPS = CTA_THREADS / GS;
+    const int gib = threadIdx.x / GS;
+    Xo<GS> rng;
+    const Grp<GS> &g = rng.g;
+    const int lane = g.lane;
     WarpShared ws;
     {
-        unsigned char *base = smem + (size_t)wib * warp_smem_bytes(P.Wmax, L.R);
-        ws.win = (uint4 *)base;                base += align_up((size_t)P.Wmax * 16, 16);
-        ws.nt_loc = (uint32_t *)base;          base += align_up((size_t)L.R * 4, 16);
+        unsigned char *base = smem + (size_t)gib * group_smem_bytes(P.Wmax, L.R);
+        ws.win = (WinRec *)base;               base += (size_t)P.Wmax * 64;
+        ws.ntc_start = (uint16_t *)base;       base += align_up(((size_t)L.R + 1) * 2, 16);
         ws.nt_assgn = (uint8_t *)base;         base += align_up((size_t)L.R, 16);
-        ws.st_lp = (double *)base;             base += (size_t)2 * MAX_SAMPLE * STAGE_CANDS * 8;
-        ws.st_w = (uint32_t *)base;
+        ws.st = (uint4 *)base;
         ws.zero_row = LCTP_GC_BINS * L.depth_k;
+        ws.depth_k = L.depth_k;
     }
-    const uint32_t slot = blockIdx.x * WARPS_PER_CTA + wib;
     Slab S;
-    slab_layout(P.cap, L.R, scratch + (size_t)slot * P.slab_bytes, &S);
+    slab_layout(P.cap, L.R, scratch + (size_t)(blockIdx.x * GROUPS + gib) * P.slab_bytes, &S);
+    rng.buf = S.rng_buf; rng.blk = S.rng_blk;
 
     for (;;) {
         uint32_t w = 0;
         if (lane == 0) w = atomicAdd(work_counter, 1u);
-        w = __shfl_sync(FULL, w, 0);
+        w = g.shfl(w, 0);
         if (w >= P.n_workers) break;
-        Xo rng;
-        rng.lane = lane; rng.buf = S.rng_buf; rng.blk = S.rng_blk;
         stream_begin(rng, rng_states + 4 * (size_t)w, setup_mats);
         for (uint64_t j = worker_off[w]; j < worker_off[w + 1]; j++) {
-            const uint64_t g = worker_ixs[j];
-            const double prior = L.priors ? L.priors[g] : 0.0;
+            const uint64_t gt = worker_ixs[j];
+            const double prior = L.priors ? L.priors[gt] : 0.0;
             Instance I;
             uint32_t wsft = 2;
             I.wshift[0] = wsft;
@@ -846,45 +1025,45 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
                 I.wshift[k + 1] = wsft;
             }
             I.W = wsft;
-            const bool ok = build_instance(L, S, ws, P.cap, I, lane);
+            const bool ok = build_instance(L, S, ws, P.cap, I, g);
             if (!ok) {
-                if (lane == 0) { atomicOr(err, 1); lik_mean[j] = NAN; lik_var[j] = NAN; n_alns[j] = I.A; }
+                if (lane == 0) { atomicOr(err, 1); lik_mean[j] = NAN; lik_var[j] = NAN; n_alns[j] = I.A; iters[j] = 0; }
                 continue;
             }
             uint16_t *cnt = P.want_counts ? counts + (size_t)j * P.cap : nullptr;
-            if (cnt) { for (uint32_t c = lane; c < I.A; c += 32) cnt[c] = 0; }
+            if (cnt) { for (uint32_t c = lane; c < I.A; c += GS) cnt[c] = 0; }
             uint64_t it_total = 0;
             for (uint32_t a = 0; a < P.attempts; a++) {
-                apply_tweak(L, S, I, ws, rng, lane);
+                apply_tweak(L, S, I, ws, rng);
                 double aln_lik = 0.0, depth_lik = 0.0;
-                if (I.n_nt == 0) init_assignment(L, S, I, ws, rng, 0, aln_lik, depth_lik, lane);
-                else if (P.kind == 0) greedy_solve(L, P, S, I, ws, rng, aln_lik, depth_lik, it_total, lane);
-                else anneal_solve(L, P, S, I, ws, rng, aln_lik, depth_lik, it_total, lane);
+                if (I.n_nt == 0) init_assignment(L, S, I, ws, rng, 0, aln_lik, depth_lik);
+                else if (P.kind == 0) greedy_solve(L, P, S, I, ws, rng, aln_lik, depth_lik, it_total);
+                else anneal_solve(L, P, S, I, ws, rng, aln_lik, depth_lik, it_total);
                 // likelihood (assgn.rs:235-237) + prior (solve.rs:1126)
                 const double lik = __dadd_rn(prior, __dadd_rn(__dmul_rn(L.depth_contrib, depth_lik),
                                                               __dmul_rn(L.aln_contrib, aln_lik)));
                 if (lane == 0) liks[j * P.attempts + a] = lik;
                 if (cnt) {   // update_counts (assgn.rs:374-378)
-                    __syncwarp();
+                    g.sync();
                     uint32_t nt_base = 0;
-                    for (uint32_t r0 = 0; r0 < L.R; r0 += 32) {
+                    for (uint32_t r0 = 0; r0 < L.R; r0 += GS) {
                         const uint32_t r = r0 + lane;
                         const bool valid = r < L.R;
                         uint32_t start = 0, nw = 0;
                         if (valid) { start = S.read_off[r]; nw = S.read_off[r + 1] - start; }
                         const bool nt = valid && nw > 1;
-                        const unsigned ntmask = __ballot_sync(FULL, nt);
+                        const unsigned ntmask = g.ballot(nt);
                         if (valid) {
                             uint32_t as = 0;
-                            if (nt) as = ws.nt_assgn[nt_base + __popc(ntmask & ((1u << lane) - 1u))];
+                            if (nt) as = ws.nt_assgn[nt_base + __popc(ntmask & g.lt())];
                             cnt[start + as] += 1;
                         }
                         nt_base += __popc(ntmask);
                     }
                 }
-                __syncwarp();
+                g.sync();
             }
-            __syncwarp();
+            g.sync();
             // mean_variance_or_nan (ext/vec.rs:74-78,86-93,109-116)
             if (lane == 0) {
                 const double *x = liks + j * P.attempts;
@@ -905,10 +1084,10 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
                 n_alns[j] = I.A;
                 iters[j] = it_total;
             }
-            __syncwarp();
+            g.sync();
         }
         stream_end(rng, rng_states + 4 * (size_t)w);
-        __syncwarp();
+        g.sync();
     }
 }
 
@@ -934,7 +1113,8 @@ static void bm_mul(const BitMat &A, const BitMat &B, BitMat &out) {   // out = A
     }
 }
 static void bm_pow(const BitMat &T, unsigned e, BitMat &out) {
-    BitMat base = T, acc, tmp;
+    static BitMat base, acc, tmp;
+    base = T;
     for (int j = 0; j < 256; j++) for (int k = 0; k < 4; k++) acc.c[j][k] = (k == (j >> 6)) ? 1ull << (j & 63) : 0;
     while (e) {
         if (e & 1) { bm_mul(base, acc, tmp); acc = tmp; }
@@ -946,7 +1126,7 @@ static void bm_pow(const BitMat &T, unsigned e, BitMat &out) {
 
 static int ensure_rng_mats(lctp_ctx *ctx) {
     if (ctx->d_rng_mats.p) return LCTP_OK;
-    static BitMat T, M;            // static: 16 KB of stack otherwise
+    static BitMat T, M;
     bm_step(T);
     std::vector<uint64_t> host((size_t)N_SETUP_MATS * 1024);
     for (int k = 0; k < N_SETUP_MATS; k++) {
@@ -956,13 +1136,54 @@ static int ensure_rng_mats(lctp_ctx *ctx) {
     int rc = ctx->d_rng_mats.alloc(host.size());
     if (rc) return rc;
     LCTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_rng_mats.p, host.data(), host.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    bm_pow(T, 31u * RNG_C, M);
+    bm_pow(T, 15u * RNG_C, M);
     LCTP_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_refill_mat, M.c, sizeof(M.c), 0, cudaMemcpyHostToDevice, ctx->stream));
+    LCTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // M is reused below
+    bm_pow(T, 31u * RNG_C, M);
+    LCTP_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_refill_mat, M.c, sizeof(M.c), sizeof(M.c), cudaMemcpyHostToDevice, ctx->stream));
     LCTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return LCTP_OK;
 }
 
 // ------------------------------------------------------------------ host launch -----------------
+
+template <int GS>
+static int launch_stage_gs(lctp_locus_h *h, const StageParams &P, size_t n_workers, bool want_counts) {
+    lctp_ctx *ctx = h->ctx;
+    cudaStream_t s = ctx->stream;
+    const LocusDev &L = h->dev;
+    constexpr int GROUPS = CTA_THREADS / GS;
+    const size_t smem = (size_t)GROUPS * group_smem_bytes(P.Wmax, L.R);
+    if (smem > ctx->smem_optin) {
+        set_error("lctp_solve_stage: %zu bytes of shared memory per CTA needed (R=%u reads, %u windows); "
+                  "loci this large are not supported by the shared-memory resident solver yet", smem, L.R, P.Wmax);
+        return LCTP_E_CAPACITY;
+    }
+    auto kern = k_solve_stage<GS>;
+    LCTP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (const char *e = getenv("LCTP_CARVEOUT"))   // tuning knob: shared-memory carveout percentage
+        LCTP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+    int occ = 0;
+    LCTP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA_THREADS, smem));
+    if (occ < 1) occ = 1;
+    if (const char *e = getenv("LCTP_MAX_CTAS_PER_SM")) occ = std::min(occ, std::max(1, atoi(e)));
+    uint32_t resident = (uint32_t)ctx->sm_count * occ * GROUPS;
+    if (ctx->max_resident_workers && ctx->max_resident_workers < resident) resident = ctx->max_resident_workers;
+    const uint32_t groups = (uint32_t)std::min<size_t>(n_workers, resident);
+    const uint32_t grid = (groups + GROUPS - 1) / GROUPS;
+
+    int rc;
+    if ((rc = ctx->scratch.ensure((size_t)grid * GROUPS * P.slab_bytes))) return rc;
+    LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[2], s));
+    kern<<<grid, CTA_THREADS, smem, s>>>(
+        L, P, ctx->d_worker_ixs.p, ctx->d_worker_off.p, ctx->d_tuples.p, ctx->d_rng.p, ctx->d_lik_mean.p,
+        ctx->d_lik_var.p, ctx->d_liks.p, ctx->d_nalns.p, ctx->d_iters.p, want_counts ? ctx->d_counts.p : nullptr,
+        ctx->scratch.p, (unsigned int *)(ctx->d_flags.p + 1), ctx->d_flags.p, ctx->d_rng_mats.p);
+    ctx->launches++;
+    LCTP_CUDA_CHECK(cudaGetLastError());
+    LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[3], s));
+    return LCTP_OK;
+}
 
 int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_ixs, const uint64_t *worker_off,
                  size_t n_workers, uint64_t *worker_rng, double *lik_mean, double *lik_var, double *liks,
@@ -979,7 +1200,7 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
         set_error("lctp_solve_stage: invalid stage (kind=%u attempts=%u)", st->kind, st->attempts);
         return LCTP_E_INVALID;
     }
-    if (st->kind == 0 && (st->sample_size == 0 || st->sample_size > 11)) {
+    if (st->kind == 0 && (st->sample_size == 0 || st->sample_size > MAX_SAMPLE)) {
         // rand::seq::index::sample switches from Floyd's to the in-place algorithm for amount > 11 on
         // short lists; only the Floyd branch is implemented on the device.
         set_error("lctp_solve_stage: greedy sample size %llu unsupported on device (1..=11)",
@@ -1007,36 +1228,19 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     }
     if (cap64 > 0x7FFFFFF0ull) { set_error("lctp_solve_stage: candidate capacity overflow"); return LCTP_E_CAPACITY; }
     const uint32_t cap = (uint32_t)cap64;
-    const uint32_t Wmax = 2 + p * h->max_n_windows;
 
     StageParams P;
     P.kind = st->kind; P.attempts = st->attempts; P.best_start = st->best_start; P.sample_size = (uint32_t)st->sample_size;
     P.plato_size = st->plato_size; P.anneal_steps = st->anneal_steps;
     P.max_iter = std::max<uint64_t>(100000, st->plato_size * 100);
     P.ln_init_prob = st->kind == 1 ? std::log(st->init_prob) : 0.0;
-    P.n_workers = (uint32_t)n_workers; P.cap = cap; P.Wmax = Wmax;
+    P.n_workers = (uint32_t)n_workers; P.cap = cap; P.Wmax = 2 + p * h->max_n_windows;
     const bool want_counts = counts != nullptr && counts_off != nullptr;
     P.want_counts = want_counts ? 1 : 0;
     P.slab_bytes = slab_layout(cap, L.R, nullptr, nullptr);
 
-    const size_t smem = (size_t)WARPS_PER_CTA * warp_smem_bytes(Wmax, L.R);
-    if (cap >= (1u << 24)) { set_error("lctp_solve_stage: %u candidate locations per genotype exceed 2^24", cap); return LCTP_E_CAPACITY; }
-    if (smem > ctx->smem_optin) { set_error("lctp_solve_stage: %zu bytes of shared memory needed", smem); return LCTP_E_CAPACITY; }
-    LCTP_CUDA_CHECK(cudaFuncSetAttribute(k_solve_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (const char *e = getenv("LCTP_CARVEOUT"))   // tuning knob: shared-memory carveout percentage
-        LCTP_CUDA_CHECK(cudaFuncSetAttribute(k_solve_stage, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
-    int occ = 0;
-    LCTP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_stage, WARPS_PER_CTA * 32, smem));
-    if (const char *e = getenv("LCTP_MAX_CTAS_PER_SM")) occ = std::min(occ, std::max(1, atoi(e)));
-    if (occ < 1) occ = 1;
-    uint32_t resident_warps = (uint32_t)ctx->sm_count * occ * WARPS_PER_CTA;
-    if (ctx->max_resident_workers && ctx->max_resident_workers < resident_warps) resident_warps = ctx->max_resident_workers;
-    uint32_t warps = (uint32_t)std::min<size_t>(n_workers, resident_warps);
-    const uint32_t grid = (warps + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-
     int rc;
     if ((rc = ensure_rng_mats(ctx))) return rc;
-    if ((rc = ctx->scratch.ensure((size_t)grid * WARPS_PER_CTA * P.slab_bytes))) return rc;
     if ((rc = ctx->d_worker_ixs.ensure(n))) return rc;
     if ((rc = ctx->d_worker_off.ensure(n_workers + 1))) return rc;
     if ((rc = ctx->d_rng.ensure(n_workers * 4))) return rc;
@@ -1055,14 +1259,10 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     LCTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tuples.p, tuples.data(), n * p * 4, cudaMemcpyHostToDevice, s));
     LCTP_CUDA_CHECK(cudaMemsetAsync(ctx->d_flags.p, 0, 2 * sizeof(int), s));
 
-    LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[2], s));
-    k_solve_stage<<<grid, WARPS_PER_CTA * 32, smem, s>>>(
-        L, P, ctx->d_worker_ixs.p, ctx->d_worker_off.p, ctx->d_tuples.p, ctx->d_rng.p, ctx->d_lik_mean.p,
-        ctx->d_lik_var.p, ctx->d_liks.p, ctx->d_nalns.p, ctx->d_iters.p, want_counts ? ctx->d_counts.p : nullptr,
-        ctx->scratch.p, (unsigned int *)(ctx->d_flags.p + 1), ctx->d_flags.p, ctx->d_rng_mats.p);
-    ctx->launches++;
-    LCTP_CUDA_CHECK(cudaGetLastError());
-    LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[3], s));
+    int gs = 32;
+    if (const char *e = getenv("LCTP_GS")) gs = atoi(e) == 16 ? 16 : 32;   // tuning knob: lanes per worker
+    rc = gs == 32 ? launch_stage_gs<32>(h, P, n_workers, want_counts) : launch_stage_gs<16>(h, P, n_workers, want_counts);
+    if (rc) return rc;
 
     int flags[2] = {0, 0};
     std::vector<uint64_t> nal(n), its(n);
@@ -1074,7 +1274,11 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     LCTP_CUDA_CHECK(cudaMemcpyAsync(its.data(), ctx->d_iters.p, n * 8, cudaMemcpyDeviceToHost, s));
     LCTP_CUDA_CHECK(cudaMemcpyAsync(flags, ctx->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
-    if (flags[0]) { set_error("lctp_solve_stage: candidate slab overflow (cap=%u)", cap); return LCTP_E_CAPACITY; }
+    if (flags[0]) {
+        set_error("lctp_solve_stage: candidate slab overflow (cap=%u, or > 65535 candidates of non-trivial reads "
+                  "in one genotype)", cap);
+        return LCTP_E_CAPACITY;
+    }
     {
         float ms = 0.f;
         LCTP_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));

@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "liblctp.so")
+LIB_PATH = os.environ.get("LCTP_LIB") or os.path.join(_HERE, "_lib", "liblctp.so")   # LCTP_LIB: tuning builds
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "lctp.h")
 

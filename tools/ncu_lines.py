@@ -47,3 +47,28 @@ print(f"total warp-instructions {ti} ({ti/iters:.1f} per iteration), samples {ts
 print("--- by samples (time)")
 for l, n in bys.most_common(28):
     print(f"{n/ts*100:5.1f}% smp {byi[l]/iters:7.1f} inst/iter  {l[1] if l else 0:>4} {text(l)}")
+
+# ---- aggregate by enclosing function of solver.cu
+import re as _re
+_src = open(os.path.join(root, "locityper_b200/csrc/solver.cu")).read().split("\n")
+_marks = []
+for _i, _l in enumerate(_src, 1):
+    if _re.match(r"^(__device__|__global__|static|template)", _l) or _l.startswith("k_solve_stage("):
+        for _c in (_l, _src[_i] if _i < len(_src) else ""):
+            _m = _re.search(r"\b([a-z_0-9]+)\(", _c)
+            if _m and _m.group(1) not in ("__launch_bounds__",):
+                _marks.append((_i, _m.group(1)))
+                break
+def _func(line):
+    name = "?"
+    for s, n in _marks:
+        if s <= line: name = n
+        else: break
+    return name
+bf_i, bf_s = collections.Counter(), collections.Counter()
+for l, n in byi.items():
+    f = _func(l[1]) if (l and l[0] == "solver.cu") else (l[0] if l else "?")
+    bf_i[f] += n; bf_s[f] += bys[l]
+print("--- by function")
+for f, n in bf_s.most_common(24):
+    print(f"{n/ts*100:5.1f}% time {bf_i[f]/iters:7.1f} inst/iter  {f}")
