@@ -190,6 +190,13 @@ double lctp_compare_two_likelihoods(double m1, double v1, uint16_t a1, double m2
 void lctp_build_depth_table(const double *nb_n, const double *nb_p, int is_paired,
                             const double *alt_cn, size_t n_alt, uint32_t k_cols, double *out);
 
+/* Predictions::produce_result (src/solvers/solve.rs:482-535) followed by check_first_prob (:637-645),
+ * check_num_of_reads (:649-678) and count_unexplained_reads (:719-729).  ixs holds the n genotype ids that
+ * survived the last stage (reordered in place); the per-genotype arrays are indexed by genotype id.
+ * Fills every field of `res` except n_filtered / n_stage_in / t_*. */
+int  lctp_produce_result(lctp_locus_h *h, uint64_t *ixs, size_t n, const double *lik_mean,
+                         const double *lik_var, const uint16_t *attempts, lctp_result *res);
+
 /* solve::solve (src/solvers/solve.rs:926-981) without file output: prefilter -> stages -> result.
  * `rng` is the locus stream (in/out); `threads` is the reference's -@ (number of logical workers). */
 int  lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_t threads,

@@ -614,6 +614,71 @@ static double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+int lctp_produce_result(lctp_locus_h *h, uint64_t *ixs, size_t n, const double *lik_mean, const double *lik_var,
+                        const uint16_t *attempts, lctp_result *res) {
+    if (!h || !ixs || !lik_mean || !lik_var || !attempts || !res || n == 0) {
+        set_error("lctp_produce_result: invalid argument");
+        return LCTP_E_INVALID;
+    }
+    for (size_t q = 0; q < n; q++)
+        if (ixs[q] >= h->dev.G) { set_error("lctp_produce_result: genotype id out of range"); return LCTP_E_INVALID; }
+    std::memset(res, 0, sizeof(*res));
+    // produce_result, solve.rs:482-535
+    const double THRESH = -11.512925464970229;
+    const size_t min_output = std::max<size_t>(4, h->host.out_bams);
+    const double thresh_prob = std::fmin(THRESH, h->host.prob_thresh);
+    sort_desc_stable(ixs, n, lik_mean);
+    size_t m = std::min<size_t>(n, LCTP_MAX_OUT);
+    double ln_probs[LCTP_MAX_OUT];
+    std::fill(ln_probs, ln_probs + LCTP_MAX_OUT, 0.0);
+    for (size_t i = 0; i < m; i++) {
+        const uint64_t u = ixs[i];
+        const size_t m_loop = m;
+        for (size_t j = i + 1; j < m_loop; j++) {
+            const uint64_t v = ixs[j];
+            const double prob_j = compare_two(lik_mean[v], lik_var[v], attempts[v], lik_mean[u], lik_var[u], attempts[u]);
+            if (i == 0 && j >= min_output && prob_j < thresh_prob) { m = j; break; }
+            ln_probs[i] += std::log1p(-std::exp(prob_j));
+            ln_probs[j] += prob_j;
+        }
+        res->gt_ix[i] = u; res->lik_mean[i] = lik_mean[u]; res->lik_var[i] = lik_var[u]; res->attempts[i] = attempts[u];
+    }
+    const double norm = ln_sum(ln_probs, m);
+    for (size_t k = 0; k < m; k++) { ln_probs[k] -= norm; res->ln_prob[k] = ln_probs[k]; }
+    const double others = m >= 1 ? ln_sum(ln_probs + 1, m - 1) : -std::numeric_limits<double>::infinity();
+    res->quality = std::fmin(-10.0 * (others * 0.4342944819032518277), 1e9);   // Phred::from_ln_prob
+    res->n_out = m;
+    res->total_reads = h->dev.R;
+    // check_first_prob (solve.rs:637-645), check_num_of_reads (:649-678)
+    const double lp0 = res->ln_prob[0];
+    res->warn_no_probable = (std::isnan(lp0) || lp0 < -2.0 * 2.302585092994045684) ? 1 : 0;
+    const uint32_t p = h->dev.p, nr = h->dev.R;
+    if (nr < p) res->warn_few_reads = 1;
+    else if (p > 1 && nr < p * 10) {
+        const double k = p, nn = nr;
+        if (std::exp(std::log(k - 1.0) * nn - std::log(k) * (nn - 1.0)) > 0.1) res->warn_few_reads = 1;
+    }
+    // count_unexplained_reads (solve.rs:719-729): best_at_contig over the called genotype's contigs = the
+    // matrix column of those contigs, which lives on the device (Mt).
+    {
+        uint32_t ids[LCTP_MAX_PLOIDY];
+        genotype_tuple(h->dev.H, p, h->gt_tuples_host.empty() ? nullptr : h->gt_tuples_host.data(), res->gt_ix[0], ids);
+        std::vector<double> col((size_t)nr * p);
+        for (uint32_t k = 0; k < p; k++)
+            LCTP_CUDA_CHECK(cudaMemcpy2DAsync(col.data() + (size_t)k * nr, 8, h->Mt.p + ids[k], (size_t)h->dev.Hpad * 8, 8, nr,
+                                              cudaMemcpyDeviceToHost, h->ctx->stream));
+        LCTP_CUDA_CHECK(cudaStreamSynchronize(h->ctx->stream));
+        uint32_t unexpl = 0;
+        for (uint32_t r = 0; r < nr; r++) {
+            double best = -std::numeric_limits<double>::infinity();
+            for (uint32_t k = 0; k < p; k++) best = std::fmax(best, col[(size_t)k * nr + r]);
+            unexpl += best < h->unmapped_host[r] + 1e-8 ? 1u : 0u;
+        }
+        res->unexpl_reads = unexpl;
+    }
+    return LCTP_OK;
+}
+
 int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_t threads, uint64_t rng[4],
                lctp_result *res) {
     if (!h || !stages || !rng || !res || n_stages == 0 || n_stages > LCTP_MAX_STAGES) {
@@ -671,60 +736,15 @@ int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_
                                         h->host.prob_thresh, out_size, threads);
     }
     res->t_stages_s = now_s() - t1;
-
-    // produce_result, solve.rs:482-535
-    const double THRESH = -11.512925464970229;
-    const size_t min_output = std::max<size_t>(4, h->host.out_bams);
-    const double thresh_prob = std::fmin(THRESH, h->host.prob_thresh);
-    sort_desc_stable(ixs.data(), n, lik_mean.data());
-    size_t m = std::min<size_t>(n, LCTP_MAX_OUT);
-    double ln_probs[LCTP_MAX_OUT];
-    std::fill(ln_probs, ln_probs + LCTP_MAX_OUT, 0.0);
-    for (size_t i = 0; i < m; i++) {
-        const uint64_t u = ixs[i];
-        const size_t m_loop = m;
-        for (size_t j = i + 1; j < m_loop; j++) {
-            const uint64_t v = ixs[j];
-            const double prob_j = compare_two(lik_mean[v], lik_var[v], attempts[v], lik_mean[u], lik_var[u], attempts[u]);
-            if (i == 0 && j >= min_output && prob_j < thresh_prob) { m = j; break; }
-            ln_probs[i] += std::log1p(-std::exp(prob_j));
-            ln_probs[j] += prob_j;
-        }
-        res->gt_ix[i] = u; res->lik_mean[i] = lik_mean[u]; res->lik_var[i] = lik_var[u]; res->attempts[i] = attempts[u];
-    }
-    const double norm = ln_sum(ln_probs, m);
-    for (size_t k = 0; k < m; k++) { ln_probs[k] -= norm; res->ln_prob[k] = ln_probs[k]; }
-    const double others = m >= 1 ? ln_sum(ln_probs + 1, m - 1) : -std::numeric_limits<double>::infinity();
-    res->quality = std::fmin(-10.0 * (others * 0.4342944819032518277), 1e9);   // Phred::from_ln_prob
-    res->n_out = m;
-    res->total_reads = h->dev.R;
-    // check_first_prob (solve.rs:637-645), check_num_of_reads (:649-678)
-    const double lp0 = res->ln_prob[0];
-    res->warn_no_probable = (std::isnan(lp0) || lp0 < -2.0 * 2.302585092994045684) ? 1 : 0;
-    const uint32_t p = h->dev.p, nr = h->dev.R;
-    if (nr < p) res->warn_few_reads = 1;
-    else if (p > 1 && nr < p * 10) {
-        const double k = p, nn = nr;
-        if (std::exp(std::log(k - 1.0) * nn - std::log(k) * (nn - 1.0)) > 0.1) res->warn_few_reads = 1;
-    }
-    // count_unexplained_reads (solve.rs:719-729): best_at_contig over the called genotype's contigs = the
-    // matrix column of those contigs, which lives on the device (Mt).
-    {
-        uint32_t ids[LCTP_MAX_PLOIDY];
-        genotype_tuple(h->dev.H, p, h->gt_tuples_host.empty() ? nullptr : h->gt_tuples_host.data(), res->gt_ix[0], ids);
-        std::vector<double> col((size_t)nr * p);
-        for (uint32_t k = 0; k < p; k++)
-            LCTP_CUDA_CHECK(cudaMemcpy2DAsync(col.data() + (size_t)k * nr, 8, h->Mt.p + ids[k], (size_t)h->dev.Hpad * 8, 8, nr,
-                                              cudaMemcpyDeviceToHost, h->ctx->stream));
-        LCTP_CUDA_CHECK(cudaStreamSynchronize(h->ctx->stream));
-        uint32_t unexpl = 0;
-        for (uint32_t r = 0; r < nr; r++) {
-            double best = -std::numeric_limits<double>::infinity();
-            for (uint32_t k = 0; k < p; k++) best = std::fmax(best, col[(size_t)k * nr + r]);
-            unexpl += best < h->unmapped_host[r] + 1e-8 ? 1u : 0u;
-        }
-        res->unexpl_reads = unexpl;
-    }
+    const uint64_t n_filtered = res->n_filtered;
+    uint64_t n_stage_in[LCTP_MAX_STAGES];
+    std::memcpy(n_stage_in, res->n_stage_in, sizeof(n_stage_in));
+    const double tp = res->t_prefilter_s, ts = res->t_stages_s;
+    int rc = lctp_produce_result(h, ixs.data(), n, lik_mean.data(), lik_var.data(), attempts.data(), res);
+    if (rc) return rc;
+    res->n_filtered = n_filtered;
+    std::memcpy(res->n_stage_in, n_stage_in, sizeof(n_stage_in));
+    res->t_prefilter_s = tp; res->t_stages_s = ts;
     return LCTP_OK;
 }
 

@@ -100,6 +100,7 @@ SYMBOLS = {
     "lctp_discard_improbable": (C.c_size_t, [_P, C.c_size_t, _P, _P, _P, C.c_double, C.c_size_t, C.c_size_t]),
     "lctp_compare_two_likelihoods": (C.c_double, [C.c_double, C.c_double, C.c_uint16, C.c_double, C.c_double, C.c_uint16]),
     "lctp_build_depth_table": (None, [_P, _P, C.c_int, _P, C.c_size_t, C.c_uint32, _P]),
+    "lctp_produce_result": (C.c_int, [_P, _P, C.c_size_t, _P, _P, _P, _P]),
     "lctp_solve": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, _P]),
     "lctp_result_json": (C.c_size_t, [_P, _P, _P, _P, C.c_size_t]),
 }

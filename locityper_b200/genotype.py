@@ -353,6 +353,23 @@ class DeviceLocus:
         return dict(lik_mean=lik_mean, lik_var=lik_var, liks=liks, n_alns=n_alns, iters=iters,
                     counts_off=counts_off, counts=counts)
 
+    def produce_result(self, ixs, lik_mean, lik_var, attempts) -> dict:
+        """Predictions::produce_result + the Genotyping checks (solve.rs:482-535,637-678,719-729).
+        Per-genotype arrays are indexed by genotype id; `ixs` are the surviving ids."""
+        ixs = np.array(ixs, dtype=np.uint64)
+        lm = np.ascontiguousarray(lik_mean, dtype=np.float64)
+        lv = np.ascontiguousarray(lik_var, dtype=np.float64)
+        at = np.ascontiguousarray(attempts, dtype=np.uint16)
+        res = ffi.ResultC()
+        ffi.check(self.lib.lctp_produce_result(self._h, ixs.ctypes.data, len(ixs), lm.ctypes.data, lv.ctypes.data,
+                                               at.ctypes.data, C.byref(res)))
+        n = int(res.n_out)
+        return dict(gt_ix=np.array(res.gt_ix[:n], dtype=np.uint64), lik_mean=np.array(res.lik_mean[:n]),
+                    lik_var=np.array(res.lik_var[:n]), attempts=np.array(res.attempts[:n]),
+                    ln_prob=np.array(res.ln_prob[:n]), quality=res.quality, total_reads=res.total_reads,
+                    unexpl_reads=res.unexpl_reads, warn_no_probable=bool(res.warn_no_probable),
+                    warn_few_reads=bool(res.warn_few_reads))
+
     def solve(self, scheme: Scheme, threads: int, rng: np.ndarray, hap_names: Optional[Sequence[str]] = None) -> Genotyping:
         """solve::solve: prefilter -> stages -> result.  `rng` (u64[4], the locus stream) is updated in place."""
         st = scheme.to_c()

@@ -355,3 +355,31 @@ def config_shape(name: str) -> dict:
         "C5": dict(n_haps=500, n_reads=4000, locus_len=8000, tech="illumina"),
     }
     return dict(shapes[name])
+
+
+_ARRAY_FIELDS = ("unmapped_prob", "pa_off", "pa_contig", "pa_ln_prob", "pa_mid1", "pa_mid2", "hap_len",
+                 "hap_n_windows", "hap_reg_start", "hap_pos_off", "pos_weight", "pos_gc", "nb_n", "nb_p", "alt_cn",
+                 "depth_table", "gt_tuples", "priors")
+_SCALAR_FIELDS = ("n_haps", "n_reads", "ploidy", "is_paired", "window", "left_padding", "depth_k", "tweak",
+                  "prob_diff", "lik_skew", "min_weight", "filt_diff", "prob_thresh", "dont_skip", "out_bams")
+
+
+def save_locus(loc: Locus, path: str) -> None:
+    """Dump the flat locus (SURVEY.md Appendix C layout) as a compressed .npz -- fixtures, debugging."""
+    d = {k: getattr(loc, k) for k in _ARRAY_FIELDS if getattr(loc, k) is not None}
+    d["_scalars"] = np.array([float(getattr(loc, k)) for k in _SCALAR_FIELDS], dtype=np.float64)
+    d["_truth"] = np.array(loc.truth, dtype=np.int64)
+    np.savez_compressed(path, **d)
+
+
+def load_locus(path: str) -> Locus:
+    z = np.load(path)
+    sc = dict(zip(_SCALAR_FIELDS, z["_scalars"].tolist()))
+    kw = {k: (z[k] if k in z.files else None) for k in _ARRAY_FIELDS}
+    for k in ("n_haps", "n_reads", "ploidy", "window", "left_padding", "depth_k", "tweak", "out_bams"):
+        kw[k] = int(sc[k])
+    for k in ("is_paired", "dont_skip"):
+        kw[k] = bool(sc[k])
+    for k in ("prob_diff", "lik_skew", "min_weight", "filt_diff", "prob_thresh"):
+        kw[k] = float(sc[k])
+    return Locus(truth=tuple(int(x) for x in z["_truth"]), **kw)

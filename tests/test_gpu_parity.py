@@ -153,3 +153,45 @@ def test_full_solve_identical_calls(oracle, gpu_ctx, small_locus, threads):
     assert abs(got.quality - ref["quality"]) <= 1e-6 * max(1.0, abs(ref["quality"]))
     js = got.to_json()
     assert js["total_reads"] == loc.n_reads and len(js["options"]) == len(ref["gt_ix"])
+
+
+def test_sharded_solve_single_rank_equals_lctp_solve(oracle, gpu_ctx, small_locus):
+    """dist.solve_sharded composes the same C-ABI pieces as lctp_solve: identical calls and RNG stream."""
+    from locityper_b200 import dist as ldist
+    loc = small_locus
+    scheme = genotype.Scheme([genotype.Stage("greedy", attempts=1, in_size=100),
+                              genotype.Stage("anneal", attempts=4, in_size=10, anneal_steps=1500, plato_size=700)])
+    dl = gpu_ctx.upload(loc)
+    rng_a, rng_b = genotype.init_rng(123), genotype.init_rng(123)
+    mono = dl.solve(scheme, 16, rng_a)
+    shard = ldist.solve_sharded(dl, scheme, 16, rng_b, rank=0, world=1)
+    dl.free()
+    assert np.array_equal(mono.gt_ix, shard["gt_ix"])
+    assert np.array_equal(mono.lik_mean, shard["lik_mean"])
+    assert np.array_equal(mono.ln_prob, shard["ln_prob"])
+    assert mono.n_filtered == shard["n_filtered"] and mono.n_stage_in == shard["n_stage_in"]
+    assert np.array_equal(rng_a, rng_b)
+
+
+def test_sharded_prefilter_two_virtual_ranks_on_device(oracle, gpu_ctx):
+    """Rank-local candidate sets computed on the device for 2 and 3 shards merge to the exact survivor list."""
+    from locityper_b200 import dist as ldist
+    loc = _mk(oracle, 60, 250, 2500, 808)
+    ol = oracle.OracleLocus(loc)
+    s_ref = oracle.prefilter_scores(ol)
+    dl = gpu_ctx.upload(loc)
+    G = loc.n_genotypes
+    for world in (2, 3):
+        for min_size, threads in [(100, 8), (30, 64)]:
+            ids, sc = [], []
+            for r in range(world):
+                a, b = ldist.shard_range(G, r, world)
+                i, s = ldist.local_candidates(dl.prefilter_scores(a, b), a, loc.filt_diff, min_size, threads)
+                ids.append(i); sc.append(s)
+            ids, sc = np.concatenate(ids), np.concatenate(sc)
+            dense = np.full(G, -np.inf)
+            dense[ids.astype(np.int64)] = sc
+            merged = genotype.truncate_ixs(np.sort(ids), dense, loc.filt_diff, min_size, threads)
+            ref = oracle.truncate_ixs(np.arange(G), s_ref, loc.filt_diff, min_size, threads)
+            assert np.array_equal(merged, ref)
+    dl.free()
