@@ -144,6 +144,10 @@ void lctp_destroy(lctp_ctx *ctx);
 uint64_t lctp_launch_count(const lctp_ctx *ctx);
 int  lctp_sync(lctp_ctx *ctx);
 int  lctp_get_stats(lctp_ctx *ctx, lctp_stats *out, int reset);
+/* Measurement aid (no reference counterpart): FP64-pipe instruction rate of the device in lane-instructions
+ * per second, from a DADD microbenchmark run on the context's stream.  The prefilter (a2) issues two FP64-pipe
+ * instructions per genotype-read, so rate / 2 is the denominator of its roofline. */
+int  lctp_measure_fp64_rate(lctp_ctx *ctx, double *lane_inst_per_s);
 
 /* ---- locus upload (H2D once per locus; builds M = best_aln_matrix on the device, a1) ------- */
 int  lctp_locus_upload(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h **out);

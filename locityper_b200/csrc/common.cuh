@@ -137,6 +137,7 @@ struct lctp_locus_h {
     lctp::DevBuf<uint64_t> hap_pos_off;
     lctp::DevBuf<uint8_t> pos_gc;
     bool scores_valid = false;
+    bool mt_nonpositive = false;         // every matrix entry <= +0.0 (integer-pipe max is valid)
 };
 
 namespace lctp {
@@ -144,6 +145,7 @@ namespace lctp {
 int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h);
 // prefilter.cu
 int launch_prefilter(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, double *d_scores);
+int measure_fp64_rate(lctp_ctx *ctx, double *lane_inst_per_s);
 // solver.cu
 int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_ixs,
                  const uint64_t *worker_off, size_t n_workers, uint64_t *worker_rng,

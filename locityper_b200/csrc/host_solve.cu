@@ -405,6 +405,13 @@ int lctp_get_stats(lctp_ctx *ctx, lctp_stats *out, int reset) {
     return LCTP_OK;
 }
 
+int lctp_measure_fp64_rate(lctp_ctx *ctx, double *lane_inst_per_s) {
+    if (!ctx || !lane_inst_per_s) { set_error("lctp_measure_fp64_rate: NULL argument"); return LCTP_E_INVALID; }
+    LCTP_CUDA_CHECK(cudaSetDevice(ctx->device));
+    set_alloc_stream(ctx->stream);
+    return measure_fp64_rate(ctx, lane_inst_per_s);
+}
+
 int lctp_locus_upload(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h **out) {
     if (!ctx || !in || !out) { set_error("lctp_locus_upload: NULL argument"); return LCTP_E_INVALID; }
     *out = nullptr;

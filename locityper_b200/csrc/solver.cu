@@ -28,9 +28,11 @@
 
 namespace lctp {
 
-static constexpr int CTA_THREADS = 128;
+#ifndef LCTP_CTA_THREADS
+#define LCTP_CTA_THREADS 128
+#endif
+static constexpr int CTA_THREADS = LCTP_CTA_THREADS;
 static constexpr int MAX_SAMPLE = 11;          // Floyd branch of rand::seq::index::sample
-static constexpr int STAGE_CANDS = 8;          // candidates per sampled read staged in smem (rest: global)
 static constexpr int RNG_C = 64;               // stream outputs generated per lane per fill
 static constexpr int RNG_BUF = 32 * RNG_C;     // slab space for one fill (GS * RNG_C <= this)
 static constexpr int N_SETUP_MATS = 5;         // T^(C*2^k), k = 0..4
@@ -320,13 +322,11 @@ struct WarpShared {
     WinRec *win;           // [Wmax]
     uint16_t *ntc_start;   // [R+1]  compact candidate offset of every non-trivial read (+ end sentinel)
     uint8_t *nt_assgn;     // [R]    current assignment of every non-trivial read
-    uint4 *st;             // [2][MAX_SAMPLE][STAGE_CANDS] staged candidate records
     uint32_t zero_row;     // offset of the all-zero row
     uint32_t depth_k;
 };
 __host__ __device__ inline size_t group_smem_bytes(uint32_t Wmax, uint32_t R) {
-    return (size_t)Wmax * 64 + align_up(((size_t)R + 1) * 2, 16) + align_up((size_t)R, 16) +
-           (size_t)2 * MAX_SAMPLE * STAGE_CANDS * 16;
+    return (size_t)Wmax * 64 + align_up(((size_t)R + 1) * 2, 16) + align_up((size_t)R, 16);
 }
 
 __device__ __forceinline__ double rec_lp(const uint4 &r) { return __hiloint2double((int)r.y, (int)r.x); }
@@ -703,68 +703,50 @@ __device__ double max_abs_random(const LocusDev &L, const Slab &S, const Instanc
 
 // ------------------------------------------------------------------ a10: Greedy -----------------
 
-__device__ __forceinline__ void cp_async16_cg(void *smem, const void *gmem) {   // L2 only: keeps L1 for the table
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit_g() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all_g() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// Lane layout of the greedy loop: the `amount` sampled reads ("slots") each own LPS = GS / amount
+// consecutive lanes; lane (slot, rank) evaluates the rank-th alternative candidate of its slot's read
+// (further alternatives, when a read has more than LPS of them, in extra passes).  The mapping is fixed
+// for the whole solve, so an iteration needs no scan / flattening, and the candidate records of the NEXT
+// sample are prefetched into registers while the current sample is evaluated.
+struct SlotMap {
+    uint32_t lps, slot, rank, range;     // range = j_slot + 1 of Floyd's draw for this slot
+    bool valid;
+    unsigned lead_mask;                  // group-relative mask of the rank-0 lanes of the valid slots
+};
 
 // One sample of `amount` distinct non-trivial reads (IndexedRandom::sample -> index::sample_floyd):
 // draw k is random_range(..=j_k), j_k = n_nt - amount + k; a draw equal to an earlier entry replaces
-// that entry by j_k.  Lane k receives entry k.  `fast_only`: succeed only through the lane-parallel path
-// (no refill, no biased draw), so the caller can un-consume the draws again with `rng.pos -= amount`.
+// that entry by j_k.  Every lane of slot k receives entry k.  `fast_only`: succeed only through the
+// lane-parallel path (no refill, no biased draw), so the caller can un-consume the draws again with
+// `rng.pos -= amount`.
 template <int GS>
-__device__ __forceinline__ bool sample_reads(Xo<GS> &rng, uint32_t n_nt, uint32_t amount, bool fast_only, uint32_t &myv) {
+__device__ __forceinline__ bool sample_reads(Xo<GS> &rng, const SlotMap &sm, uint32_t n_nt, uint32_t amount,
+                                             bool fast_only, uint32_t &myv) {
     const Grp<GS> &g = rng.g;
-    const uint32_t lane = (uint32_t)g.lane;
-    const uint32_t my_j = n_nt - amount + min(lane, amount - 1u);
-    bool need_fixup = true;
-    if (xo_below_parallel(rng, amount, my_j + 1u, myv)) {
-        const unsigned amask = (1u << amount) - 1u;
-        const unsigned peers = g.match_any(lane < amount ? myv : 0xFFFFFFFFu);
-        need_fixup = g.any(lane < amount && (peers & amask) != (1u << lane));
-    } else {
+    bool fast = false;
+    if (stream_cover(rng, amount)) {
+        const uint64_t m = (uint64_t)stream_peek_hi(rng, sm.slot) * (uint64_t)sm.range;
+        if (!g.any(sm.valid && (uint32_t)m > 0u - sm.range)) {
+            myv = (uint32_t)(m >> 32);
+            rng.pos += amount;
+            fast = true;
+        }
+    }
+    if (!fast) {
         if (fast_only) return false;
         for (uint32_t k = 0; k < amount; k++) {
             const uint32_t t = xo_below(rng, n_nt - amount + k + 1u);
-            if (lane == k) myv = t;
+            if (sm.slot == k) myv = t;
         }
     }
-    if (need_fixup) {
+    const unsigned peers = g.match_any(sm.valid ? myv : 0xFFFFFFFFu);
+    if (g.any(sm.valid && (peers & sm.lead_mask) != (1u << (sm.slot * sm.lps)))) {
         for (uint32_t k = 1; k < amount; k++) {
-            const uint32_t t = g.shfl(myv, (int)k);
-            if (lane < k && myv == t) myv = n_nt - amount + k;
+            const uint32_t t = g.shfl(myv, (int)(k * sm.lps));
+            if (sm.slot < k && myv == t) myv = n_nt - amount + k;
         }
     }
     return true;
-}
-
-// Stage the static candidate records of a sample (lane s < amount owns slot s with candidates
-// [start, start + n) in the compact array): the (slot, candidate) pairs are flattened over the lanes and
-// each lane copies one 16-byte record into shared memory with cp.async.cg.  `incl_n` is the inclusive
-// scan of n over the slots.  Only the first STAGE_CANDS candidates of a read are staged.
-template <int GS>
-__device__ __forceinline__ void stage_sample(const Grp<GS> &g, const Slab &S, const WarpShared &ws, int stage,
-                                             bool slot_lane, uint32_t start, uint32_t n, uint32_t incl_n) {
-    const uint32_t N = g.shfl(incl_n, GS - 1);
-    const uint32_t offn = incl_n - n;
-    if (N <= 64u) {
-        const unsigned long long hb = slot_lane ? 1ull << offn : 0ull;
-        const unsigned long long heads = ((unsigned long long)g.ror((uint32_t)(hb >> 32)) << 32) | g.ror((uint32_t)hb);
-        for (uint32_t j0 = 0; j0 < N; j0 += GS) {
-            const uint32_t j = j0 + (uint32_t)g.lane;
-            const bool act = j < N;
-            const int slot = act ? __popcll(heads & ((2ull << j) - 1ull)) - 1 : 0;
-            const uint32_t s_off = g.shfl(offn, slot), s_start = g.shfl(start, slot);
-            const uint32_t c = j - s_off;
-            if (act && c < (uint32_t)STAGE_CANDS)
-                cp_async16_cg(ws.st + (stage * MAX_SAMPLE + slot) * STAGE_CANDS + c, S.ntc + s_start + c);
-        }
-    } else if (slot_lane) {
-        const uint32_t m = min(n, (uint32_t)STAGE_CANDS);
-        for (uint32_t c = 0; c < m; c++)
-            cp_async16_cg(ws.st + (stage * MAX_SAMPLE + g.lane) * STAGE_CANDS + c, S.ntc + start + c);
-    }
 }
 
 // A candidate move as seen by one lane, ordered like the reference's two nested strict-'>' scans:
@@ -781,12 +763,39 @@ __device__ __forceinline__ bool cand_better(const Cand &a, const Cand &b) {
     return a.c < b.c;
 }
 
+// The sampled read of this lane's slot and the two candidate records the lane works on.
+struct SlotRead {
+    uint32_t idx, start, n, old_a;
+    uint4 ro, rn;       // current candidate, and alternative #rank (valid when rank < n - 1)
+};
+template <int GS>
+__device__ __forceinline__ void load_slot(const Slab &S, const WarpShared &ws, const SlotMap &sm, uint32_t idx,
+                                          SlotRead &r) {
+    r.idx = idx;
+    r.start = ws.ntc_start[idx];
+    r.n = ws.ntc_start[idx + 1] - r.start;
+    r.old_a = ws.nt_assgn[idx];
+    const uint32_t c = sm.rank < r.old_a ? sm.rank : sm.rank + 1u;
+    r.ro = __ldcg(S.ntc + r.start + r.old_a);
+    r.rn = __ldcg(S.ntc + r.start + min(c, r.n - 1u));
+}
+
+__device__ __forceinline__ void eval_cand(const LocusDev &L, const WarpShared &ws, const uint4 &ro, const uint4 &rn,
+                                          uint32_t slot, uint32_t c, Cand &cd) {
+    const double lp_old = rec_lp(ro), lp = rec_lp(rn);
+    cd.dld = depth_lik_diff(ws, ro.z, rn.z);
+    cd.improv = __dadd_rn(lp, __dmul_rn(L.rel_contrib, cd.dld));          // assgn.rs:303
+    cd.s = __dmul_rn(L.aln_contrib, __dsub_rn(cd.improv, lp_old));        // assgn.rs:310
+    cd.dlp = __dsub_rn(lp, lp_old);
+    cd.slot = slot; cd.c = c; cd.w12 = ro.z; cd.w34 = rn.z;
+}
+
 // Greedy::solve_nontrivial (src/solvers/stoch.rs:81-120).
 // Every (sampled read, alternative candidate) pair of an iteration is one lane's job ("flattened"
 // best_read_improvement, src/model/assgn.rs:287-317); the winner is found with REDUX reductions in the
 // reference's tie order.  Software pipeline: the sample of iteration i+1 is drawn and its (static)
-// candidate data is cp.async-staged while iteration i is evaluated, so an iteration touches only shared
-// memory and the cached depth table.
+// candidate records are loaded into registers while iteration i is evaluated, so the evaluation itself
+// touches only registers and shared memory.
 template <int GS>
 __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab &S, const Instance &I,
                              const WarpShared &ws, Xo<GS> &rng, double &aln_lik, double &depth_lik,
@@ -796,95 +805,47 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
     const uint32_t amount = min(P.sample_size, I.n_nt);
     init_assignment(L, S, I, ws, rng, P.best_start ? 0 : 1, aln_lik, depth_lik);
     const double min_diff = fmax(__dmul_rn(1e-10, max_abs_random(L, S, I, ws, rng)), 1e-14);
-    const bool slot_lane = lane < amount;
+    SlotMap sm;
+    sm.lps = (uint32_t)GS / amount;
+    {
+        const uint32_t s = lane / sm.lps;
+        sm.valid = s < amount;
+        sm.slot = sm.valid ? s : amount - 1u;
+        sm.rank = lane - s * sm.lps;
+        sm.range = I.n_nt - amount + sm.slot + 1u;
+        sm.lead_mask = g.ballot(sm.valid && sm.rank == 0u);
+    }
     uint64_t curr_plato = 0, it = 0;
     bool have_next = false;
-    uint32_t next_idx = 0, next_start = 0, next_n = 0, next_incl = 0;
-    int stage = 0;
-    // inclusive scan over the slots of a per-slot value (0 on non-slot lanes)
-    auto scan_slots = [&](uint32_t v) {
-#pragma unroll
-        for (int d = 1; d < GS; d <<= 1) {
-            const uint32_t o = g.shfl_up(v, d);
-            if ((int)lane >= d) v += o;
-        }
-        return v;
-    };
+    SlotRead nx;
+    nx.idx = nx.start = nx.old_a = 0; nx.n = 1; nx.ro = nx.rn = make_uint4(0, 0, 0, 0);
     for (; it < P.max_iter; it++) {
-        uint32_t idx, start, n, incl_n;          // of the read sampled in slot == lane
-        if (have_next) { idx = next_idx; start = next_start; n = next_n; incl_n = next_incl; }
+        SlotRead cur;
+        if (have_next) cur = nx;
         else {
-            idx = 0;
-            sample_reads(rng, I.n_nt, amount, false, idx);
-            start = slot_lane ? ws.ntc_start[idx] : 0u;
-            n = slot_lane ? ws.ntc_start[idx + 1] - start : 0u;
-            incl_n = scan_slots(n);
-            stage_sample(g, S, ws, stage, slot_lane, start, n, incl_n);
-            cp_async_commit_g();
+            uint32_t v = 0;
+            sample_reads(rng, sm, I.n_nt, amount, false, v);
+            load_slot<GS>(S, ws, sm, v, cur);
         }
-        cp_async_wait_all_g();
-        g.sync();
-        {   // pre-draw the next sample and start staging it
-            uint32_t myv = 0;
-            have_next = sample_reads(rng, I.n_nt, amount, true, myv);
-            if (have_next) {
-                next_idx = myv;
-                next_start = slot_lane ? ws.ntc_start[myv] : 0u;
-                next_n = slot_lane ? ws.ntc_start[myv + 1] - next_start : 0u;
-                next_incl = scan_slots(next_n);
-                stage_sample(g, S, ws, stage ^ 1, slot_lane, next_start, next_n, next_incl);
-                cp_async_commit_g();
-            }
+        {   // pre-draw the next sample and start loading its records
+            uint32_t v = 0;
+            have_next = sample_reads(rng, sm, I.n_nt, amount, true, v);
+            if (have_next) load_slot<GS>(S, ws, sm, v, nx);
         }
-        // flatten (slot, alternative candidate) pairs: slot s contributes n_s - 1 evaluations, so its
-        // first evaluation index is (exclusive scan of n)_s - s
-        const uint32_t old_a = slot_lane ? ws.nt_assgn[idx] : 0u;
-        const uint32_t E = g.shfl(incl_n, GS - 1) - amount;
-        const uint32_t off = incl_n - n - (slot_lane ? lane : 0u);
         Cand best;
         best.s = -INFINITY; best.improv = -INFINITY; best.dld = 0.0; best.dlp = 0.0;
         best.slot = 0xFFFFu; best.c = 0; best.w12 = 0; best.w34 = 0;
-        if (E <= 64u) {
-            // head flags: bit `off_s` marks the first evaluation of slot s
-            const unsigned long long hb = slot_lane ? 1ull << off : 0ull;
-            const unsigned long long heads = ((unsigned long long)g.ror((uint32_t)(hb >> 32)) << 32) | g.ror((uint32_t)hb);
-            for (uint32_t e0 = 0; e0 < E; e0 += GS) {
-                const uint32_t e = e0 + lane;
-                const bool act = e < E;
-                const int slot = act ? __popcll(heads & ((2ull << e) - 1ull)) - 1 : 0;
-                const uint32_t s_off = g.shfl(off, slot), s_old = g.shfl(old_a, slot), s_start = g.shfl(start, slot);
-                if (act) {
-                    const uint32_t cr = e - s_off;
-                    const uint32_t c = cr < s_old ? cr : cr + 1u;
-                    const uint4 *st = ws.st + (stage * MAX_SAMPLE + slot) * STAGE_CANDS;
-                    const uint4 ro = s_old < (uint32_t)STAGE_CANDS ? st[s_old] : __ldcg(S.ntc + s_start + s_old);
-                    const uint4 rn = c < (uint32_t)STAGE_CANDS ? st[c] : __ldcg(S.ntc + s_start + c);
-                    const double lp_old = rec_lp(ro), lp = rec_lp(rn);
+        const uint32_t n_alt = cur.n - 1u;
+        if (sm.valid && sm.rank < n_alt)
+            eval_cand(L, ws, cur.ro, cur.rn, sm.slot, sm.rank < cur.old_a ? sm.rank : sm.rank + 1u, best);
+        if (g.any(sm.valid && n_alt > sm.lps)) {
+            // reads with more alternatives than lanes per slot: extra passes straight from the slab
+            for (uint32_t j = sm.rank + sm.lps; g.any(sm.valid && j < n_alt); j += sm.lps) {
+                if (sm.valid && j < n_alt) {
+                    const uint32_t c = j < cur.old_a ? j : j + 1u;
+                    const uint4 rn = __ldcg(S.ntc + cur.start + c);
                     Cand cd;
-                    cd.dld = depth_lik_diff(ws, ro.z, rn.z);
-                    cd.improv = __dadd_rn(lp, __dmul_rn(L.rel_contrib, cd.dld));          // assgn.rs:303
-                    cd.s = __dmul_rn(L.aln_contrib, __dsub_rn(cd.improv, lp_old));        // assgn.rs:310
-                    cd.dlp = __dsub_rn(lp, lp_old);
-                    cd.slot = (uint32_t)slot; cd.c = c; cd.w12 = ro.z; cd.w34 = rn.z;
-                    if (cand_better(cd, best)) best = cd;
-                }
-            }
-        } else {
-            // many candidates per read: one read at a time, lanes over its candidates
-            for (uint32_t s = 0; s < amount; s++) {
-                const uint32_t s_n = g.shfl(n, (int)s), s_old = g.shfl(old_a, (int)s), s_start = g.shfl(start, (int)s);
-                const uint4 ro = __ldcg(S.ntc + s_start + s_old);
-                const double lp_old = rec_lp(ro);
-                for (uint32_t c = lane; c < s_n; c += GS) {
-                    if (c == s_old) continue;
-                    const uint4 rn = __ldcg(S.ntc + s_start + c);
-                    const double lp = rec_lp(rn);
-                    Cand cd;
-                    cd.dld = depth_lik_diff(ws, ro.z, rn.z);
-                    cd.improv = __dadd_rn(lp, __dmul_rn(L.rel_contrib, cd.dld));
-                    cd.s = __dmul_rn(L.aln_contrib, __dsub_rn(cd.improv, lp_old));
-                    cd.dlp = __dsub_rn(lp, lp_old);
-                    cd.slot = s; cd.c = c; cd.w12 = ro.z; cd.w34 = rn.z;
+                    eval_cand(L, ws, cur.ro, rn, sm.slot, c, cd);
                     if (cand_better(cd, best)) best = cd;
                 }
             }
@@ -900,15 +861,15 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
             const unsigned tied = g.ballot(m);
             if ((tied & (tied - 1u)) == 0u) wl = __ffs(tied) - 1;      // unique maximum (the usual case)
             else {
-            const uint32_t sl = g.rmin(m ? best.slot : 0xFFFFFFFFu);
-            m = m && best.slot == sl;
-            const unsigned long long ki = ord_key(best.improv);
-            const uint32_t h2 = g.rmax(m ? (uint32_t)(ki >> 32) : 0u);
-            m = m && (uint32_t)(ki >> 32) == h2;
-            const uint32_t l2 = g.rmax(m ? (uint32_t)ki : 0u);
-            m = m && (uint32_t)ki == l2;
-            const uint32_t cm = g.rmin(m ? best.c : 0xFFFFFFFFu);
-            wl = __ffs(g.ballot(m && best.c == cm)) - 1;
+                const uint32_t sl = g.rmin(m ? best.slot : 0xFFFFFFFFu);
+                m = m && best.slot == sl;
+                const unsigned long long ki = ord_key(best.improv);
+                const uint32_t h2 = g.rmax(m ? (uint32_t)(ki >> 32) : 0u);
+                m = m && (uint32_t)(ki >> 32) == h2;
+                const uint32_t l2 = g.rmax(m ? (uint32_t)ki : 0u);
+                m = m && (uint32_t)ki == l2;
+                const uint32_t cm = g.rmin(m ? best.c : 0xFFFFFFFFu);
+                wl = __ffs(g.ballot(m && best.c == cm)) - 1;
             }
         }
         const double s_best = g.shfl(best.s, wl);
@@ -918,19 +879,18 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
             mv.dlp = g.shfl(best.dlp, wl);
             mv.w12 = g.shfl(best.w12, wl);
             mv.w34 = g.shfl(best.w34, wl);
-            const uint32_t w_slot = g.shfl(best.slot, wl), w_c = g.shfl(best.c, wl);
-            const uint32_t w_idx = g.shfl(idx, (int)w_slot);
+            const uint32_t w_c = g.shfl(best.c, wl);
+            const uint32_t w_idx = g.shfl(cur.idx, wl);
             apply_move(g, ws, L.depth_table, w_idx, w_c, mv, aln_lik, depth_lik);
             curr_plato = 0;
+            // the prefetched sample saw the old assignment of the moved read
+            if (have_next && g.any(sm.valid && nx.idx == w_idx)) load_slot<GS>(S, ws, sm, nx.idx, nx);
         } else {
             curr_plato += 1;
             if (curr_plato > P.plato_size) { it++; break; }
         }
-        stage ^= 1;
     }
     if (have_next) rng.pos -= amount;     // the pre-drawn sample of the iteration that never ran
-    cp_async_wait_all_g();
-    g.sync();
     iters_out += it;
 }
 
@@ -998,8 +958,7 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
         unsigned char *base = smem + (size_t)gib * group_smem_bytes(P.Wmax, L.R);
         ws.win = (WinRec *)base;               base += (size_t)P.Wmax * 64;
         ws.ntc_start = (uint16_t *)base;       base += align_up(((size_t)L.R + 1) * 2, 16);
-        ws.nt_assgn = (uint8_t *)base;         base += align_up((size_t)L.R, 16);
-        ws.st = (uint4 *)base;
+        ws.nt_assgn = (uint8_t *)base;
         ws.zero_row = LCTP_GC_BINS * L.depth_k;
         ws.depth_k = L.depth_k;
     }

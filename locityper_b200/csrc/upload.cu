@@ -13,12 +13,13 @@
 namespace lctp {
 
 __global__ void k_fill_mt(double *__restrict__ Mt, const double *__restrict__ unmapped, uint32_t R,
-                          uint32_t H, uint32_t Hpad) {
+                          uint32_t H, uint32_t Hpad, int *__restrict__ err) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t n = (size_t)R * Hpad;
     if (i >= n) return;
     uint32_t r = (uint32_t)(i / Hpad), h = (uint32_t)(i % Hpad);
     Mt[i] = h < H ? unmapped[r] : 0.0;
+    if (h == 0 && !(unmapped[r] <= 0.0)) atomicOr(err, 8);     // positive / NaN entry: see prefilter.cu dmax_nonpos
 }
 
 // One warp per read: walk its pair alignments (sorted by contig asc, ln_prob desc); the first entry
@@ -47,6 +48,7 @@ __global__ void k_group_runs(const uint64_t *__restrict__ pa_off, const uint32_t
         if (!SCATTER) {
             cnt_or_off[key] = len;
             Mt[(size_t)r * Hpad + h] = pa_lnprob[i];
+            if (!(pa_lnprob[i] <= 0.0)) atomicOr(err, 8);
         } else {
             uint32_t o = cnt_or_off[key];
             for (uint32_t t = 0; t < len; t++) {
@@ -186,7 +188,7 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h) {
 
     {
         size_t n = (size_t)R * Hpad;
-        k_fill_mt<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->Mt.p, h->unmapped.p, R, H, Hpad);
+        k_fill_mt<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->Mt.p, h->unmapped.p, R, H, Hpad, d_err.p);
         ctx->launches++;
     }
     const unsigned warps_per_block = 8;
@@ -214,6 +216,8 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h) {
     int err = 0;
     LCTP_CUDA_CHECK(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
+    h->mt_nonpositive = !(err & 8);
+    err &= 7;
     if (err) {
         set_error("lctp_locus_upload: malformed pair alignments (flags=%d: 1=contig id >= H, 2=contigs not "
                   "ascending within a read, 4=ln_prob not descending within a (read, contig) run)", err);

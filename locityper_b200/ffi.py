@@ -86,6 +86,7 @@ SYMBOLS = {
     "lctp_launch_count": (C.c_uint64, [_P]),
     "lctp_sync": (C.c_int, [_P]),
     "lctp_get_stats": (C.c_int, [_P, _P, C.c_int]),
+    "lctp_measure_fp64_rate": (C.c_int, [_P, _P]),
     "lctp_locus_upload": (C.c_int, [_P, _P, _P]),
     "lctp_locus_free": (None, [_P]),
     "lctp_best_aln_matrix": (C.c_int, [_P, _P]),

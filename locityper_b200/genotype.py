@@ -215,6 +215,12 @@ class Context:
         ffi.check(self.lib.lctp_get_stats(self._h, C.byref(st), int(reset)))
         return {k: getattr(st, k) for k, _ in ffi.StatsC._fields_}
 
+    def fp64_rate(self) -> float:
+        """FP64-pipe lane-instructions per second (DADD microbenchmark; roofline denominator of the prefilter)."""
+        v = C.c_double(0.0)
+        ffi.check(self.lib.lctp_measure_fp64_rate(self._h, C.byref(v)))
+        return float(v.value)
+
     def upload(self, loc: Locus) -> "DeviceLocus":
         return DeviceLocus(self, loc)
 

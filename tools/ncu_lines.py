@@ -72,3 +72,7 @@ for l, n in byi.items():
 print("--- by function")
 for f, n in bf_s.most_common(24):
     print(f"{n/ts*100:5.1f}% time {bf_i[f]/iters:7.1f} inst/iter  {f}")
+if os.environ.get("BY_INST"):
+    print("--- by instructions")
+    for l, n in byi.most_common(60):
+        print(f"{n/ti*100:5.1f}% inst {n/iters:9.1f} inst/iter {bys[l]/ts*100:5.1f}% smp  {l[1] if l else 0:>4} {text(l)}")

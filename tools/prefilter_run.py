@@ -1,0 +1,27 @@
+"""Driver for timing / profiling the prefilter kernel alone (a2) at a BASELINE shape (default C4: H=1000, R=10k)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import argparse
+from locityper_b200 import genotype, synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="C4")
+ap.add_argument("--passes", type=int, default=5)
+a = ap.parse_args()
+t0 = time.time()
+loc = synth.make_locus(**synth.config_shape(a.config), seed=4001, table_builder=genotype.build_depth_table)
+print(f"locus {a.config}: H={loc.n_haps} R={loc.n_reads} G={loc.n_genotypes} generated in {time.time()-t0:.1f}s", flush=True)
+ctx = genotype.Context(0)
+rate = ctx.fp64_rate()
+print(f"FP64 pipe: {rate/1e12:.2f} T lane-instructions/s (DADD microbenchmark)")
+dl = ctx.upload(loc)
+for i in range(a.passes):
+    if i == 1:
+        ctx.stats(reset=True)
+    s = dl.prefilter_scores()
+st = ctx.stats()
+n = st["prefilter_launches"]
+ms = st["prefilter_ms"] / max(1, n)
+el = loc.n_genotypes * loc.n_reads
+print(f"prefilter: {ms:.4f} ms/launch, {el/ms/1e9:.3f} T elements/s (1 max + 1 add each), "
+      f"{loc.n_genotypes*(2*loc.n_reads*8+8)/ms/1e6:.1f} GB/s algorithmic, checksum {float(s.sum()):.6e}; {2*el/ms/1e9*1e12/rate*100:.1f}% of the FP64-pipe roofline")

@@ -6,11 +6,16 @@ from locityper_b200 import genotype, synth
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="C2")
+ap.add_argument("--shape", default="", help="H,R,L override")
 ap.add_argument("--passes", type=int, default=2)
 ap.add_argument("--threads", type=int, default=4736)
 ap.add_argument("--scheme", nargs="*", default=["greedy:i=5k,a=1"])
 a = ap.parse_args()
-loc = synth.make_locus(**synth.config_shape(a.config), seed=2001, table_builder=genotype.build_depth_table)
+sh = synth.config_shape(a.config)
+if a.shape:
+    h, r, l = (int(x) for x in a.shape.split(","))
+    sh.update(n_haps=h, n_reads=r, locus_len=l)
+loc = synth.make_locus(**sh, seed=2001, table_builder=genotype.build_depth_table)
 ctx = genotype.Context(0)
 dl = ctx.upload(loc)
 scheme = genotype.Scheme.parse(a.scheme)

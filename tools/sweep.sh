@@ -1,6 +1,5 @@
 #!/bin/bash
-# tuning sweep: launch-bounds variants of the solver kernel (one C2 locus, 3 passes each)
-for lib in liblctp.so liblctp_mb5.so liblctp_mb6.so liblctp_mb7.so; do
-  export LCTP_LIB=$PWD/locityper_b200/_lib/$lib
-  echo "$lib: $(python tools/profile_run.py --passes 3 | sed -e 's/.*stage_ms.: \([0-9.]*\).*/stage_ms(3 passes)=\1/')"
-done
+# prefilter tile variants (LCTP_PREFILTER_VARIANT) at the BASELINE shapes
+for cfg in C4 C5 C2; do for v in 1 11 12 13 14 15; do
+  echo "$cfg variant=$v: $(LCTP_PREFILTER_VARIANT=$v timeout 120 python tools/prefilter_run.py --config $cfg | tail -1)"
+done; done
