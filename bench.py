@@ -48,6 +48,8 @@ def parse_args():
                          "slot that fits the GPU, same T for the CPU arm)")
     ap.add_argument("--scheme", nargs="*", default=["greedy:i=5k,a=1"],
                     help="reference -S stages; configs[1] is 'prefilter + greedy'")
+    ap.add_argument("--streams", type=int, default=0,
+                    help="loci in flight per GPU (one context + CUDA stream + host thread each); 0 = loci per step")
     ap.add_argument("--seed", type=int, default=2001)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-loci", type=int, default=0, help="loci in the bounded CPU sample (0 = auto)")
@@ -218,6 +220,7 @@ def workload_config(args, T, world):
                         f"{sh['tech']}; scheme {' '.join('-S ' + s for s in args.scheme)}",
             "shape": args.config, "loci_per_step_per_gpu": args.loci, "threads_T": T, "mode": args.mode,
             "parallelism": f"loci x{world}" if args.mode == "loci" else f"genotype-shard x{world}",
+            "loci_in_flight_per_gpu": (args.streams if args.streams > 0 else args.loci) if args.mode == "loci" else 1,
             "l2": "per-step working set (per-warp candidate slabs, ~0.7 GB) exceeds the 126 MB L2; "
                   "an L2 flush buffer is also written between timed steps"}
 
@@ -248,48 +251,53 @@ def run_ours(args):
     G_step = sum(l.n_genotypes for l in loci)
     h2d = sum(input_bytes(l) for l in loci)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # The loci of a step are independent (genotype.rs:1331-1351): each is solved by its own context (own
+    # CUDA stream, own host thread), so kernels, copies and host-side pruning of different loci overlap.
+    n_streams = args.streams if args.streams > 0 else len(loci)
+    pool = genotype.ContextPool(device=local, k=n_streams)
+    fp64_rate = ctx.fp64_rate()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def l2_flush():
+        flush.zero_()                         # L2 flush (256 MB > 126 MB), outside the event pair
+        torch.cuda.synchronize(dev)           # the loci run on other streams: do not let them overlap the flush
+
     def step_resident(dls):
-        calls = []
-        for i, dl in enumerate(dls):
-            rng = genotype.init_rng(args.seed + i)
-            calls.append(dl.solve(scheme, T, rng))
-        return calls
+        return pool.map(lambda c, i, dl: dl.solve(scheme, T, genotype.init_rng(args.seed + i)), dls)
+
+    def one_e2e(c, i, loc):
+        dl = c.upload(loc)                    # H2D of the whole flat locus from pinned host memory
+        res = dl.solve(scheme, T, genotype.init_rng(args.seed + i))   # D2H of (lik_mean, lik_var, RNG states, calls)
+        dl.free()
+        return res
 
     def step_e2e():
-        calls = []
-        for i, loc in enumerate(loci):
-            dl = ctx.upload(loc)              # H2D of the whole flat locus from pinned host memory
-            rng = genotype.init_rng(args.seed + i)
-            calls.append(dl.solve(scheme, T, rng))   # D2H of (lik_mean, lik_var, RNG states, calls)
-            dl.free()
-        return calls
+        return pool.map(one_e2e, loci)
 
     # ---- value: inputs resident in HBM when the timed region starts
-    dls = [ctx.upload(l) for l in loci]
+    dls = pool.map(lambda c, i, l: c.upload(l), loci)
     for _ in range(args.warmup):
         step_resident(dls)
-    ctx.stats(reset=True)
-    launches0 = ctx.launch_count()
+    pool.stats(reset=True)
+    launches0 = pool.launch_count()
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     calls = None
     for k in range(args.steps):
-        flush.zero_()                         # L2 flush, outside the event pair
+        l2_flush()
         ev[k][0].record(stream)
-        calls = step_resident(dls)
+        calls = step_resident(dls)            # returns when every locus' results are on the host
         ev[k][1].record(stream)
     barrier()
     clocks = sampler.stop()
-    launches = ctx.launch_count() - launches0
-    st = ctx.stats(reset=True)
+    launches = pool.launch_count() - launches0
+    st = pool.stats(reset=True)
     ms_steps = [a.elapsed_time(b) for a, b in ev]
     t_total = torch.tensor([sum(ms_steps)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -299,13 +307,27 @@ def run_ours(args):
     for dl in dls:
         dl.free()
 
+    # ---- kernel-level numbers: the same loci once more, one at a time on one stream, so that every launch's
+    # CUDA-event duration is the kernel alone (launches of concurrent loci share the SMs and their event
+    # durations overlap); the roofline objects are computed from this pass.
+    iso = [ctx.upload(l) for l in loci]
+    for i, dl in enumerate(iso):
+        dl.solve(scheme, T, genotype.init_rng(args.seed + i))
+    ctx.stats(reset=True)
+    l2_flush()
+    for i, dl in enumerate(iso):
+        dl.solve(scheme, T, genotype.init_rng(args.seed + i))
+    st_iso = ctx.stats(reset=True)
+    for dl in iso:
+        dl.free()
+
     # ---- e2e: host buffers in, host results out, through the public API, copies inside the timed region
     for _ in range(max(1, args.warmup - 1)):
         step_e2e()
     barrier()
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for k in range(args.steps):
-        flush.zero_()
+        l2_flush()
         ev2[k][0].record(stream)
         calls = step_e2e()
         ev2[k][1].record(stream)
@@ -334,7 +356,11 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
         }
-        line.update(rooflines(st, loci, args, peak, peak_src))
+        line.update(rooflines(st_iso, loci, args, peak, peak_src, fp64_rate))
+        line["roofline"]["in_step"] = {
+            "note": "all launches of the timed region (concurrent loci share the SMs): algorithmic bytes / step time",
+            "achieved": line["roofline"]["bytes_alg_per_launch"] * st["stage_launches"] / (ms_total / 1e3) / 1e9,
+            "launches": int(st["stage_launches"]), "sum_launch_ms": st["stage_ms"]}
         line["calls_vs_truth"] = [[list(l.genotype_tuple(int(c.gt_ix[0]))), list(l.truth)] for l, c in zip(loci, calls)]
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args, loci, T)
@@ -343,7 +369,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def rooflines(st, loci, args, peak, peak_src):
+def rooflines(st, loci, args, peak, peak_src, fp64_rate=None):
     """roofline of the dominant kernel (the solver stage) + the prefilter kernel, from device-side timings."""
     loc = loci[0]
     R, p = loc.n_reads, loc.ploidy
@@ -357,6 +383,7 @@ def rooflines(st, loci, args, peak, peak_src):
         ach = bytes_alg / sec / 1e9
         out["roofline"] = {"kernel": "k_solve_stage", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                            "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                           "bytes_alg_per_launch": bytes_alg / st["stage_launches"],
                            "avg_launch_ms": st["stage_ms"] / st["stage_launches"],
                            "note": "latency/issue-bound dependent chains (SURVEY 8d): HBM fraction is not the limiter; "
                                    "see iters_per_s", "iters_per_s": it / sec, "genotypes_per_s": g / sec}
@@ -368,7 +395,14 @@ def rooflines(st, loci, args, peak, peak_src):
         out["roofline_prefilter"] = {"kernel": "k_prefilter_pairs", "bound": "hbm", "achieved": bytes_alg / sec / 1e9,
                                      "peak": peak, "unit": "GB/s", "frac": bytes_alg / sec / 1e9 / peak,
                                      "traffic": None, "f64_ops_per_s": ops / sec,
-                                     "avg_launch_ms": st["prefilter_ms"] / st["prefilter_launches"]}
+                                     "avg_launch_ms": st["prefilter_ms"] / st["prefilter_launches"],
+                                     "note": "tiled (max,+) contraction: the matrix is read once per tile row, so the "
+                                             "reference-pattern bytes exceed HBM peak by design; the binding unit is the "
+                                             "FP64 pipe (DSETP + DADD per genotype-read), see fp64"}
+        if fp64_rate:
+            out["roofline_prefilter"]["fp64"] = {
+                "achieved": ops / sec / 1e12, "peak": fp64_rate / 1e12, "unit": "T FP64-pipe lane-instructions/s",
+                "frac": ops / sec / fp64_rate, "peak_source": "DADD microbenchmark run live (lctp_measure_fp64_rate)"}
     return out
 
 

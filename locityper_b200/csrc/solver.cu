@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
+#include <mutex>
 
 namespace lctp {
 
@@ -1083,23 +1084,39 @@ static void bm_pow(const BitMat &T, unsigned e, BitMat &out) {
     out = acc;
 }
 
+// The jump matrices depend only on the generator: computed once per process (contexts on several host
+// threads share them), uploaded once per context.
+struct RngMats {
+    std::vector<uint64_t> setup;     // N_SETUP_MATS matrices T^(C*2^k)
+    BitMat refill[2];                // T^(15*C), T^(31*C)
+};
+static const RngMats &rng_mats() {
+    static std::once_flag once;
+    static RngMats m;
+    std::call_once(once, [] {
+        static BitMat T, M;
+        bm_step(T);
+        m.setup.resize((size_t)N_SETUP_MATS * 1024);
+        for (int k = 0; k < N_SETUP_MATS; k++) {
+            bm_pow(T, (unsigned)RNG_C << k, M);
+            std::memcpy(&m.setup[(size_t)k * 1024], M.c, sizeof(M.c));
+        }
+        bm_pow(T, 15u * RNG_C, m.refill[0]);
+        bm_pow(T, 31u * RNG_C, m.refill[1]);
+    });
+    return m;
+}
+
 static int ensure_rng_mats(lctp_ctx *ctx) {
     if (ctx->d_rng_mats.p) return LCTP_OK;
-    static BitMat T, M;
-    bm_step(T);
-    std::vector<uint64_t> host((size_t)N_SETUP_MATS * 1024);
-    for (int k = 0; k < N_SETUP_MATS; k++) {
-        bm_pow(T, (unsigned)RNG_C << k, M);
-        std::memcpy(&host[(size_t)k * 1024], M.c, sizeof(M.c));
-    }
-    int rc = ctx->d_rng_mats.alloc(host.size());
+    const RngMats &m = rng_mats();
+    static std::mutex symbol_mutex;      // c_refill_mat is one symbol per device
+    std::lock_guard<std::mutex> lock(symbol_mutex);
+    int rc = ctx->d_rng_mats.alloc(m.setup.size());
     if (rc) return rc;
-    LCTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_rng_mats.p, host.data(), host.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    bm_pow(T, 15u * RNG_C, M);
-    LCTP_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_refill_mat, M.c, sizeof(M.c), 0, cudaMemcpyHostToDevice, ctx->stream));
-    LCTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // M is reused below
-    bm_pow(T, 31u * RNG_C, M);
-    LCTP_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_refill_mat, M.c, sizeof(M.c), sizeof(M.c), cudaMemcpyHostToDevice, ctx->stream));
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_rng_mats.p, m.setup.data(), m.setup.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    LCTP_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_refill_mat, m.refill[0].c, sizeof(m.refill[0].c), 0, cudaMemcpyHostToDevice, ctx->stream));
+    LCTP_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_refill_mat, m.refill[1].c, sizeof(m.refill[1].c), sizeof(m.refill[0].c), cudaMemcpyHostToDevice, ctx->stream));
     LCTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return LCTP_OK;
 }
@@ -1119,6 +1136,9 @@ static int launch_stage_gs(lctp_locus_h *h, const StageParams &P, size_t n_worke
         return LCTP_E_CAPACITY;
     }
     auto kern = k_solve_stage<GS>;
+    // function attributes are per-device state shared by every context: configure + launch under one lock
+    static std::mutex launch_mutex;
+    std::lock_guard<std::mutex> lock(launch_mutex);
     LCTP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (const char *e = getenv("LCTP_CARVEOUT"))   // tuning knob: shared-memory carveout percentage
         LCTP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));

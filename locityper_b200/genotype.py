@@ -236,6 +236,47 @@ class Context:
             pass
 
 
+class ContextPool:
+    """K contexts (one CUDA stream each) on one GPU, one host thread per context.  Loci are independent
+    units of work (src/command/genotype.rs:1331-1351: one `analyze_locus` per locus, separate long_jump
+    RNG streams), so their uploads, kernels and host-side pruning overlap; a context still has a single
+    locus in flight (lctp_ctx is Send, not Sync)."""
+
+    def __init__(self, device: int = 0, k: int = 3, max_resident_workers: int = 0):
+        from concurrent.futures import ThreadPoolExecutor
+        self.ctxs = [Context(device=device, max_resident_workers=max_resident_workers) for _ in range(k)]
+        self._pool = ThreadPoolExecutor(max_workers=k)
+
+    def map(self, fn, items):
+        """fn(ctx, index, item) for every item; items i, i+K, i+2K, ... run in order on context i."""
+        k = len(self.ctxs)
+        items = list(items)
+
+        def lane(c):
+            return [(i, fn(self.ctxs[c], i, items[i])) for i in range(c, len(items), k)]
+
+        out = [None] * len(items)
+        for fut in [self._pool.submit(lane, c) for c in range(min(k, len(items)))]:
+            for i, r in fut.result():
+                out[i] = r
+        return out
+
+    def launch_count(self) -> int:
+        return sum(c.launch_count() for c in self.ctxs)
+
+    def stats(self, reset: bool = False) -> dict:
+        tot: dict = {}
+        for c in self.ctxs:
+            for k_, v in c.stats(reset).items():
+                tot[k_] = tot.get(k_, 0) + v
+        return tot
+
+    def close(self) -> None:
+        self._pool.shutdown(wait=True)
+        for c in self.ctxs:
+            c.close()
+
+
 def locus_to_c(loc: Locus, keep: list) -> ffi.LocusC:
     def arr(a, dt):
         if a is None:
