@@ -30,7 +30,7 @@
 namespace lctp {
 
 #ifndef LCTP_CTA_THREADS
-#define LCTP_CTA_THREADS 128
+#define LCTP_CTA_THREADS 32
 #endif
 static constexpr int CTA_THREADS = LCTP_CTA_THREADS;
 static constexpr int MAX_SAMPLE = 11;          // Floyd branch of rand::seq::index::sample
@@ -161,9 +161,10 @@ struct Xo {                // the worker's stream as seen by the solver code
     static constexpr uint32_t FILL = GS * RNG_C;
     Grp<GS> g;
     Gen gen;               // this lane's generator (positioned at the end of its block after a fill)
-    uint32_t win_lo, win_hi;   // register window: buf[wbase + lane]
+    uint32_t a_lo, a_hi;   // register blocks: A = buf[base + lane], B = buf[base + GS + lane] (B is the
+    uint32_t b_lo, b_hi;   // prefetched successor, so moving the window never waits for memory)
     uint32_t pos;          // draws consumed from the current fill
-    uint32_t wbase;        // stream position held by lane 0 of the register window
+    uint32_t base;         // stream position of lane 0 of block A (multiple of GS)
     uint64_t *buf;         // [FILL] per-worker buffer (global, L2-resident)
     uint64_t *blk;         // [GS][4] block-start states of the current fill
 };
@@ -185,7 +186,10 @@ template <int GS>
 __device__ __forceinline__ void stream_fill(Xo<GS> &x, int jump_mat) {
     x.gen = fill_block(x.gen, x.buf, x.blk, x.g.lane, x.g.mask, jump_mat);
     x.pos = 0;
-    x.wbase = 0x80000000u;   // window invalid
+    x.base = 0;
+    const uint64_t a = __ldcg(x.buf + x.g.lane), b = __ldcg(x.buf + GS + x.g.lane);
+    x.a_lo = (uint32_t)a; x.a_hi = (uint32_t)(a >> 32);
+    x.b_lo = (uint32_t)b; x.b_hi = (uint32_t)(b >> 32);
 }
 
 // Start a stream from the scalar state st[4]: lane l jumps ahead by l*RNG_C (binary decomposition of l).
@@ -217,27 +221,43 @@ __device__ void stream_end(Xo<GS> &x, uint64_t *__restrict__ out) {
     if (x.g.lane == owner) { out[0] = g.s0; out[1] = g.s1; out[2] = g.s2; out[3] = g.s3; }
 }
 
-// Make the register window cover stream positions [pos, pos + count), count <= GS; false = the fill
-// ends first (the caller then uses the one-draw-at-a-time path, which refills).
+// Make the register blocks cover stream positions [pos, pos + count), count <= GS; false = the fill
+// ends first (the caller then uses the one-draw-at-a-time path, which refills).  Position q of the
+// stream lives in lane q % GS: in block A for q < base + GS, else in block B.
 template <int GS>
 __device__ __forceinline__ bool stream_cover(Xo<GS> &x, uint32_t count) {
     if (x.pos + count > Xo<GS>::FILL) return false;
-    if (x.pos - x.wbase + count > (uint32_t)GS) {          // also true when wbase is invalid (> pos)
-        x.wbase = x.pos;
-        const uint64_t v = __ldcg(x.buf + min(x.pos + (uint32_t)x.g.lane, Xo<GS>::FILL - 1u));
-        x.win_lo = (uint32_t)v; x.win_hi = (uint32_t)(v >> 32);
+    if (x.pos - x.base >= (uint32_t)GS) {                  // A is used up: B becomes A, prefetch the next B
+        x.a_lo = x.b_lo; x.a_hi = x.b_hi;
+        x.base += GS;
+        const uint64_t v = __ldcg(x.buf + min(x.base + GS + (uint32_t)x.g.lane, Xo<GS>::FILL - 1u));
+        x.b_lo = (uint32_t)v; x.b_hi = (uint32_t)(v >> 32);
     }
     return true;
 }
 // After stream_cover(count): the (pos + rank)-th draw of the stream, for any per-lane rank < count.
 template <int GS>
 __device__ __forceinline__ uint32_t stream_peek_hi(const Xo<GS> &x, uint32_t rank) {
-    return x.g.shfl(x.win_hi, (int)((x.pos - x.wbase + rank) & (GS - 1)));
+    const uint32_t off = x.pos - x.base;
+    return x.g.shfl((uint32_t)x.g.lane >= off ? x.a_hi : x.b_hi, (int)((off + rank) & (GS - 1)));
 }
 template <int GS>
 __device__ __forceinline__ uint64_t stream_peek64(const Xo<GS> &x, uint32_t rank) {
-    const int src = (int)((x.pos - x.wbase + rank) & (GS - 1));
-    return ((uint64_t)x.g.shfl(x.win_hi, src) << 32) | x.g.shfl(x.win_lo, src);
+    const uint32_t off = x.pos - x.base;
+    const bool in_a = (uint32_t)x.g.lane >= off;
+    const int src = (int)((off + rank) & (GS - 1));
+    return ((uint64_t)x.g.shfl(in_a ? x.a_hi : x.b_hi, src) << 32) | x.g.shfl(in_a ? x.a_lo : x.b_lo, src);
+}
+// Give back the last n draws (n <= GS, all taken from the current fill without a refill in between).
+template <int GS>
+__device__ __forceinline__ void stream_unconsume(Xo<GS> &x, uint32_t n) {
+    x.pos -= n;
+    while (x.pos < x.base) {
+        x.b_lo = x.a_lo; x.b_hi = x.a_hi;
+        x.base -= GS;
+        const uint64_t v = __ldcg(x.buf + x.base + x.g.lane);
+        x.a_lo = (uint32_t)v; x.a_hi = (uint32_t)(v >> 32);
+    }
 }
 template <int GS>
 __device__ __forceinline__ void stream_advance(Xo<GS> &x) {
@@ -817,26 +837,41 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
         sm.lead_mask = g.ballot(sm.valid && sm.rank == 0u);
     }
     uint64_t curr_plato = 0, it = 0;
-    bool have_next = false;
+    // Sample pipeline: `nx` = sample of iteration i+1 with its records in registers, `idx2` = sample of
+    // iteration i+2 (drawn, its slab lines prefetched into L2).
+    bool have1 = false, have2 = false;
+    uint32_t idx2 = 0;
     SlotRead nx;
     nx.idx = nx.start = nx.old_a = 0; nx.n = 1; nx.ro = nx.rn = make_uint4(0, 0, 0, 0);
     for (; it < P.max_iter; it++) {
         SlotRead cur;
-        if (have_next) cur = nx;
+        if (have1) cur = nx;
         else {
             uint32_t v = 0;
             sample_reads(rng, sm, I.n_nt, amount, false, v);
             load_slot<GS>(S, ws, sm, v, cur);
         }
-        {   // pre-draw the next sample and start loading its records
+        if (have2) { load_slot<GS>(S, ws, sm, idx2, nx); have1 = true; have2 = false; }
+        else {
             uint32_t v = 0;
-            have_next = sample_reads(rng, sm, I.n_nt, amount, true, v);
-            if (have_next) load_slot<GS>(S, ws, sm, v, nx);
+            have1 = sample_reads(rng, sm, I.n_nt, amount, true, v);
+            if (have1) load_slot<GS>(S, ws, sm, v, nx);
+        }
+        if (have1) {
+            have2 = sample_reads(rng, sm, I.n_nt, amount, true, idx2);
+            if (have2 && sm.rank < 2u) {
+                const uint32_t st2 = ws.ntc_start[idx2];
+                const uint32_t off2 = sm.rank == 0u ? 0u : (uint32_t)ws.ntc_start[idx2 + 1] - st2 - 1u;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(S.ntc + st2 + off2));
+            }
         }
         Cand best;
         best.s = -INFINITY; best.improv = -INFINITY; best.dld = 0.0; best.dlp = 0.0;
         best.slot = 0xFFFFu; best.c = 0; best.w12 = 0; best.w34 = 0;
         const uint32_t n_alt = cur.n - 1u;
+        // Keep the (unused) padding word of the prefetched records live until here: otherwise its register
+        // is recycled right after the load is issued and that write has to wait for the load (WAW).
+        asm volatile("" ::"r"(cur.ro.w), "r"(cur.rn.w));
         if (sm.valid && sm.rank < n_alt)
             eval_cand(L, ws, cur.ro, cur.rn, sm.slot, sm.rank < cur.old_a ? sm.rank : sm.rank + 1u, best);
         if (g.any(sm.valid && n_alt > sm.lps)) {
@@ -885,13 +920,14 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
             apply_move(g, ws, L.depth_table, w_idx, w_c, mv, aln_lik, depth_lik);
             curr_plato = 0;
             // the prefetched sample saw the old assignment of the moved read
-            if (have_next && g.any(sm.valid && nx.idx == w_idx)) load_slot<GS>(S, ws, sm, nx.idx, nx);
+            if (have1 && g.any(sm.valid && nx.idx == w_idx)) load_slot<GS>(S, ws, sm, nx.idx, nx);
         } else {
             curr_plato += 1;
             if (curr_plato > P.plato_size) { it++; break; }
         }
     }
-    if (have_next) rng.pos -= amount;     // the pre-drawn sample of the iteration that never ran
+    if (have2) stream_unconsume(rng, amount);   // the pre-drawn samples of iterations that never ran
+    if (have1) stream_unconsume(rng, amount);
     iters_out += it;
 }
 
@@ -937,7 +973,7 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
 // ------------------------------------------------------------------ stage kernel ----------------
 
 #ifndef LCTP_MIN_CTAS
-#define LCTP_MIN_CTAS 4
+#define LCTP_MIN_CTAS 17
 #endif
 template <int GS>
 __global__ void __launch_bounds__(CTA_THREADS, LCTP_MIN_CTAS)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# prefilter tile variants (LCTP_PREFILTER_VARIANT) at the BASELINE shapes
-for cfg in C4 C5 C2; do for v in 1 11 12 13 14 15; do
-  echo "$cfg variant=$v: $(LCTP_PREFILTER_VARIANT=$v timeout 120 python tools/prefilter_run.py --config $cfg | tail -1)"
-done; done
+# stage time of the default build on one C2 locus (3 passes), default and 20k-survivor stages
+echo "C2 i=5k T=4736 : $(python tools/profile_run.py --passes 3 | sed -e 's/.*stage_ms.: \([0-9.]*\).*/stage_ms(3 passes)=\1/')"
+echo "C2 i=5k T=5000 : $(python tools/profile_run.py --passes 3 --threads 5000 | sed -e 's/.*stage_ms.: \([0-9.]*\).*/stage_ms(3 passes)=\1/')"
+echo "C2 i=20k T=2960: $(python tools/profile_run.py --passes 3 --threads 2960 --scheme greedy:i=20k,a=1 | sed -e 's/.*stage_ms.: \([0-9.]*\).*/stage_ms(3 passes)=\1/')"
