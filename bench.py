@@ -52,6 +52,8 @@ def parse_args():
                     help="loci in flight per GPU (one context + CUDA stream + host thread each); 0 = loci per step")
     ap.add_argument("--seed", type=int, default=2001)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kir-prefilter", action="store_true",
+                    help="skip the extra prefilter-only measurement at the KIR-scale shape (configs[3])")
     ap.add_argument("--cpu-loci", type=int, default=0, help="loci in the bounded CPU sample (0 = auto)")
     return ap.parse_args()
 
@@ -221,8 +223,8 @@ def workload_config(args, T, world):
             "shape": args.config, "loci_per_step_per_gpu": args.loci, "threads_T": T, "mode": args.mode,
             "parallelism": f"loci x{world}" if args.mode == "loci" else f"genotype-shard x{world}",
             "loci_in_flight_per_gpu": (args.streams if args.streams > 0 else args.loci) if args.mode == "loci" else 1,
-            "l2": "per-step working set (per-warp candidate slabs, ~0.7 GB) exceeds the 126 MB L2; "
-                  "an L2 flush buffer is also written between timed steps"}
+            "l2": "per-step working set (per-worker candidate slabs, ~0.7 GB) exceeds the 126 MB L2; "
+                  "an L2 flush buffer (256 MB) is also written between timed steps"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -362,6 +364,8 @@ def run_ours(args):
             "achieved": line["roofline"]["bytes_alg_per_launch"] * st["stage_launches"] / (ms_total / 1e3) / 1e9,
             "launches": int(st["stage_launches"]), "sum_launch_ms": st["stage_ms"]}
         line["calls_vs_truth"] = [[list(l.genotype_tuple(int(c.gt_ix[0]))), list(l.truth)] for l, c in zip(loci, calls)]
+        if not args.no_kir_prefilter and world == 1:
+            line["roofline_prefilter_kir"] = kir_prefilter(ctx, genotype, peak, fp64_rate)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args, loci, T)
         print(json.dumps(line), flush=True)
@@ -404,6 +408,31 @@ def rooflines(st, loci, args, peak, peak_src, fp64_rate=None):
                 "achieved": ops / sec / 1e12, "peak": fp64_rate / 1e12, "unit": "T FP64-pipe lane-instructions/s",
                 "frac": ops / sec / fp64_rate, "peak_source": "DADD microbenchmark run live (lctp_measure_fp64_rate)"}
     return out
+
+
+def kir_prefilter(ctx, genotype, peak, fp64_rate):
+    """The prefilter kernel alone at the KIR-scale shape of BASELINE configs[3] (H=1000, G=500,500, R=10,000),
+    the size north_star's >= 60 % target is stated for; 5 launches after one warm-up, CUDA events."""
+    from locityper_b200 import synth
+    loc = synth.make_locus(**synth.config_shape("C4"), seed=4001, table_builder=genotype.build_depth_table)
+    dl = ctx.upload(loc)
+    dl.prefilter_scores(fetch=False)
+    ctx.stats(reset=True)
+    for _ in range(5):
+        dl.prefilter_scores(fetch=False)
+    ctx.sync()
+    st = ctx.stats(reset=True)
+    dl.free()
+    sec = st["prefilter_ms"] / 1e3
+    gp, R, p = st["prefilter_genotypes"], loc.n_reads, loc.ploidy
+    ops = gp * p * R
+    return {"kernel": "k_prefilter_pairs", "workload": "configs[3] shape: H=1000, G=500500, R=10000 (one locus, one GPU)",
+            "bound": "fp64-pipe", "achieved": ops / sec / 1e12, "peak": fp64_rate / 1e12,
+            "unit": "T FP64-pipe lane-instructions/s", "frac": ops / sec / fp64_rate,
+            "peak_source": "DADD microbenchmark run live (lctp_measure_fp64_rate)",
+            "avg_launch_ms": st["prefilter_ms"] / st["prefilter_launches"],
+            "hbm_reference_pattern": {"achieved": gp * (p * R * 8 + 8) / sec / 1e9, "peak": peak, "unit": "GB/s",
+                                      "frac": gp * (p * R * 8 + 8) / sec / 1e9 / peak}}
 
 
 def cpu_baseline(args, loci, T):

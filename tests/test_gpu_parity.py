@@ -195,3 +195,127 @@ def test_sharded_prefilter_two_virtual_ranks_on_device(oracle, gpu_ctx):
             ref = oracle.truncate_ixs(np.arange(G), s_ref, loc.filt_diff, min_size, threads)
             assert np.array_equal(merged, ref)
     dl.free()
+
+
+@pytest.mark.parametrize("H,R", [(150, 97), (70, 33)])
+def test_every_prefilter_kernel_variant_is_bit_exact(oracle, gpu_ctx, H, R, monkeypatch):
+    """All tile shapes of k_prefilter_pairs (register tiles 1x1..4x4, cp.async and TMA bulk-copy staging,
+    FP64 and integer-pipe max) give the oracle's scores bit for bit; ragged tiles, R not a multiple of the
+    chunk, shard sub-ranges."""
+    loc = _mk(oracle, H, R, 2500, 500 + H)
+    ref = oracle.prefilter_scores(oracle.OracleLocus(loc))
+    dl = gpu_ctx.upload(loc)
+    G = loc.n_genotypes
+    for variant in range(16):
+        monkeypatch.setenv("LCTP_PREFILTER_VARIANT", str(variant))
+        assert np.array_equal(dl.prefilter_scores(), ref), f"variant {variant}"
+        a, b = G // 4, G // 4 + G // 2
+        assert np.array_equal(dl.prefilter_scores(a, b), ref[a:b]), f"variant {variant} sub-range"
+    dl.free()
+
+
+def test_positive_matrix_entries_disable_the_integer_max(oracle, gpu_ctx, monkeypatch):
+    """dmax_nonpos is only valid for entries <= +0.0: a locus with a positive ln-prob must still be exact."""
+    loc = _mk(oracle, 40, 60, 2500, 77)
+    loc.pa_ln_prob = loc.pa_ln_prob.copy()
+    # per (read, contig) run the first entry is the best one: shifting every entry keeps runs sorted
+    loc.pa_ln_prob += 15.0
+    loc.unmapped_prob = loc.unmapped_prob + 15.0
+    ref = oracle.prefilter_scores(oracle.OracleLocus(loc))
+    dl = gpu_ctx.upload(loc)
+    assert (dl.best_aln_matrix() > 0).any()
+    for variant in (7, 8, 9, 10, 1):
+        monkeypatch.setenv("LCTP_PREFILTER_VARIANT", str(variant))
+        assert np.array_equal(dl.prefilter_scores(), ref), f"variant {variant}"
+    dl.free()
+
+
+@pytest.mark.parametrize("sample_size", [1, 2, 7, 10, 11])
+def test_greedy_sample_sizes_and_many_candidates(oracle, gpu_ctx, sample_size):
+    """Lanes-per-slot layouts 32/16/4/3/2 of the greedy loop; 90 % of the reads have secondary locations,
+    so most sampled reads have more alternatives than lanes per slot (extra evaluation passes)."""
+    loc = _mk(oracle, 14, 180, 2500, 900 + sample_size, multi_frac=0.9)
+    gts = list(range(0, loc.n_genotypes, 4))
+    _stage_parity(oracle, gpu_ctx, loc, dict(kind="greedy", attempts=2, sample_size=sample_size, plato_size=40), 3, gts)
+    _stage_parity(oracle, gpu_ctx, loc, dict(kind="greedy", attempts=1, sample_size=sample_size, best_start=False,
+                                             plato_size=25), 2, gts[:10])
+
+
+def test_fewer_nontrivial_reads_than_the_sample(oracle, gpu_ctx):
+    """n_nontrivial < sample_size (amount = n_nontrivial) and genotypes with no non-trivial read at all."""
+    loc = _mk(oracle, 6, 12, 2500, 4321, multi_frac=0.0, off_target=0.5)
+    gts = list(range(loc.n_genotypes))
+    _stage_parity(oracle, gpu_ctx, loc, dict(kind="greedy", attempts=2, plato_size=10), 2, gts)
+    _stage_parity(oracle, gpu_ctx, loc, dict(kind="anneal", attempts=2, anneal_steps=200, plato_size=100), 3, gts)
+
+
+def test_more_workers_than_genotypes(oracle, gpu_ctx, small_locus):
+    """T > n: trailing workers get no genotype; their RNG states must come back untouched."""
+    gts = [5, 17, 40]
+    ixs = np.array(gts, dtype=np.uint64)
+    off = np.array([0, 1, 2, 3, 3, 3], dtype=np.uint64)
+    rng_ref = _workers(oracle, 5, 8)
+    rng_gpu = rng_ref.copy()
+    ol = oracle.OracleLocus(small_locus)
+    dl = gpu_ctx.upload(small_locus)
+    ref = oracle.solve_stage(ol, oracle.Stage(kind="greedy", attempts=1), ixs, off, rng_ref, os_threads=2)
+    got = dl.solve_stage(genotype.Stage(kind="greedy", attempts=1), ixs, off, rng_gpu)
+    dl.free()
+    assert np.array_equal(rng_gpu, rng_ref)
+    assert np.array_equal(rng_gpu[3:], _workers(oracle, 5, 8)[3:])
+    assert np.array_equal(got["lik_mean"], ref["lik_mean"])
+
+
+def test_context_pool_concurrent_loci_equal_sequential(oracle, gpu_ctx):
+    """Three loci in flight on three contexts (streams + host threads) return exactly what one context
+    returns for them one after another -- the bench's execution mode."""
+    loci = [_mk(oracle, 20 + 3 * i, 200, 2500, 60 + i) for i in range(3)]
+    scheme = genotype.Scheme([genotype.Stage("greedy", attempts=1, in_size=80),
+                              genotype.Stage("anneal", attempts=3, in_size=6, anneal_steps=800, plato_size=400)])
+
+    def one(ctx, i, loc):
+        dl = ctx.upload(loc)
+        rng = genotype.init_rng(1000 + i)
+        res = dl.solve(scheme, 48, rng)
+        dl.free()
+        return res, rng
+
+    seq = [one(gpu_ctx, i, l) for i, l in enumerate(loci)]
+    pool = genotype.ContextPool(device=0, k=3)
+    for _ in range(2):
+        par = pool.map(one, loci)
+        for (a, ra), (b, rb) in zip(seq, par):
+            assert np.array_equal(a.gt_ix, b.gt_ix) and np.array_equal(a.lik_mean, b.lik_mean)
+            assert np.array_equal(a.ln_prob, b.ln_prob) and np.array_equal(ra, rb)
+    assert pool.launch_count() > 0
+    pool.close()
+
+
+def test_full_size_properties_c2(oracle, gpu_ctx):
+    """BASELINE configs[1] at full size (H=300, G=45,150, R=2,000): size-independent properties.
+    (1) scores of sampled genotypes equal a sequential numpy restatement from the device-built matrix;
+    (2) the two-shard prefilter equals the full one; (3) the survivor list is sorted by (score desc, id asc);
+    (4) the whole solve is deterministic and its stage-1 input has the requested size."""
+    loc = synth.make_locus(**synth.config_shape("C2"), seed=2001, table_builder=genotype.build_depth_table)
+    dl = gpu_ctx.upload(loc)
+    M = dl.best_aln_matrix()
+    s = dl.prefilter_scores()
+    rs = np.random.default_rng(5)
+    for g in rs.integers(0, loc.n_genotypes, 64):
+        i, j = loc.genotype_tuple(int(g))
+        acc = 0.0
+        for v in np.maximum(M[i], M[j]):
+            acc += v
+        assert s[g] == acc + 0.0
+    G = loc.n_genotypes
+    assert np.array_equal(np.concatenate([dl.prefilter_scores(0, G // 2), dl.prefilter_scores(G // 2, G)]), s)
+    surv = dl.prefilter(5000, 64)
+    key = list(zip(-s[surv.astype(np.int64)], surv))
+    assert key == sorted(key) and len(surv) >= 5000
+    scheme = genotype.Scheme.parse(["greedy:i=5k,a=1"])
+    a = dl.solve(scheme, 4736, genotype.init_rng(2001))
+    b = dl.solve(scheme, 4736, genotype.init_rng(2001))
+    dl.free()
+    assert a.n_stage_in[0] == 5000 or a.n_filtered <= 5000
+    assert np.array_equal(a.gt_ix, b.gt_ix) and np.array_equal(a.lik_mean, b.lik_mean)
+    assert loc.genotype_tuple(int(a.gt_ix[0])) == tuple(loc.truth)
