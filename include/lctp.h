@@ -130,7 +130,32 @@ typedef struct lctp_stats {
     uint64_t stage_attempts;       /* genotype-attempts solved */
     uint64_t stage_iters;          /* greedy iterations + annealing steps executed */
     uint64_t stage_alns;           /* candidate locations built (sum of A) */
+    double   pairing_ms;           /* sum of the two pairing kernel passes + scan (lctp_pair_alignments) */
+    uint64_t pairing_launches;
+    uint64_t pairing_mates;        /* mate alignment records read */
+    uint64_t pairing_pairs;        /* pair alignments written */
 } lctp_stats;
+
+/* Mate alignments of R read pairs = the input of identify_paired_end_alignments (src/model/locs.rs:805-868):
+ * per read sorted by contig ascending, first read end before second, ln_prob descending within an end (the
+ * order in which the reference consumes them after its sort at :819-820). */
+typedef struct lctp_mates {
+    uint32_t n_reads;              /* R */
+    uint32_t n_haps;               /* H (contig ids are < H) */
+    uint32_t max_alns;             /* MAX_USED_ALNS = 10 (locs.rs:741); <= 16 */
+    uint32_t ins_len;              /* entries of ins_ln_pmf; must exceed every possible insert size */
+    const uint64_t *ma_off;        /* [R+1] */
+    const uint32_t *ma_contig;     /* [N] */
+    const uint8_t  *ma_flags;      /* [N] bit0 = read end (0 first, 1 second), bit1 = strand */
+    const uint32_t *ma_start;      /* [N] Interval::start */
+    const uint32_t *ma_end;        /* [N] Interval::end (exclusive) */
+    const double   *ma_ln_prob;    /* [N] Alignment::ln_prob */
+    const double   *read_weight;   /* [R] ReadData::weight; NULL = 1.0 */
+    const double   *ins_ln_pmf;    /* [ins_len] InsertDistr::ln_prob(size) (src/bg/insertsz.rs:153-155) */
+    double unmapped_penalty;       /* Params::unmapped_penalty (src/model/mod.rs:55-60) */
+    double insert_penalty;         /* InsertDistr::insert_penalty (insertsz.rs:171-173) */
+    double prob_diff;              /* Params::prob_diff */
+} lctp_mates;
 
 /* ---- library / context -------------------------------------------------------------------- */
 const char *lctp_version(void);
@@ -154,6 +179,16 @@ int  lctp_locus_upload(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h **out);
 void lctp_locus_free(lctp_locus_h *h);
 /* a1: AllAlignments::best_aln_matrix (src/model/locs.rs:1203-1212), [H][R] row-major by haplotype. */
 int  lctp_best_aln_matrix(lctp_locus_h *h, double *m_out);
+
+/* ---- 8(f) rank 1: mate alignments -> pair alignments -------------------------------------------- */
+/* identify_paired_end_alignments + identify_contig_pair_alns (src/model/locs.rs:744-868) for every read on
+ * the device.  Outputs are exactly the pa_* / unmapped_prob arrays of lctp_locus (caller-allocated; `cap`
+ * entries in the four per-pair arrays, R+1 in pa_off, R in unmapped_prob); *n_out = pair alignments written.
+ * LCTP_E_CAPACITY when cap is too small, LCTP_E_INVALID for records out of the documented order. */
+int  lctp_pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t *pa_off,
+                          uint32_t *pa_contig, double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2,
+                          double *unmapped_prob, uint64_t *n_out);
+size_t lctp_sizeof_mates(void);
 
 /* ---- prefilter (a2 + a3) ------------------------------------------------------------------ */
 /* Scores of genotypes [g_begin, g_end) (src/solvers/solve.rs:105-119) computed on the device into the

@@ -146,6 +146,10 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h);
 // prefilter.cu
 int launch_prefilter(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, double *d_scores);
 int measure_fp64_rate(lctp_ctx *ctx, double *lane_inst_per_s);
+// pairs.cu
+int pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig,
+                    double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob,
+                    uint64_t *n_out);
 // solver.cu
 int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_ixs,
                  const uint64_t *worker_off, size_t n_workers, uint64_t *worker_rng,

@@ -405,6 +405,26 @@ int lctp_get_stats(lctp_ctx *ctx, lctp_stats *out, int reset) {
     return LCTP_OK;
 }
 
+size_t lctp_sizeof_mates(void) { return sizeof(lctp_mates); }
+
+int lctp_pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig,
+                         double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob,
+                         uint64_t *n_out) {
+    if (!ctx || !in || !pa_off || !unmapped_prob || (cap && (!pa_contig || !pa_ln_prob || !pa_mid1 || !pa_mid2)) ||
+        !in->ins_ln_pmf || in->ins_len == 0) {
+        set_error("lctp_pair_alignments: NULL argument");
+        return LCTP_E_INVALID;
+    }
+    if (in->n_reads && in->ma_off && in->ma_off[in->n_reads] &&
+        (!in->ma_contig || !in->ma_flags || !in->ma_start || !in->ma_end || !in->ma_ln_prob)) {
+        set_error("lctp_pair_alignments: NULL mate array");
+        return LCTP_E_INVALID;
+    }
+    LCTP_CUDA_CHECK(cudaSetDevice(ctx->device));
+    set_alloc_stream(ctx->stream);
+    return pair_alignments(ctx, in, cap, pa_off, pa_contig, pa_ln_prob, pa_mid1, pa_mid2, unmapped_prob, n_out);
+}
+
 int lctp_measure_fp64_rate(lctp_ctx *ctx, double *lane_inst_per_s) {
     if (!ctx || !lane_inst_per_s) { set_error("lctp_measure_fp64_rate: NULL argument"); return LCTP_E_INVALID; }
     LCTP_CUDA_CHECK(cudaSetDevice(ctx->device));

@@ -1,0 +1,256 @@
+// pairs.cu -- SURVEY.md section 8(f) rank 1: mate alignments -> per-contig pair alignments, the producer
+// of the flat locus' pa_* arrays (identify_paired_end_alignments + identify_contig_pair_alns,
+// src/model/locs.rs:744-868).
+//
+// Work unit = one (read pair, contig) group: all first-end x second-end combinations of opposite strand
+// ((ln1 + ln2) + insert-size ln-pmf, src/seq/aln.rs:236-238), the single-mate options that beat every
+// pairing of that mate (locs.rs:777-790), a stable descending selection of the best `max_alns` within
+// `prob_diff` of the best (locs.rs:793-798), scaled by the read weight (locs.rs:861-863).
+//
+// Device layout: one thread per mate record; the thread of the FIRST mate of a group owns the group (the
+// others exit), so groups are discovered without a host-side index and the output order (read, contig) is
+// the order of the owning records.  Two passes over the same code: pass 0 counts the kept pairs of every
+// group, an exclusive scan of the counts gives each group's output offset (and, read at ma_off[r], the
+// pa_off array), pass 1 recomputes and writes.  The byte traffic is one streaming read of the mate
+// records per pass plus the output: an HBM-bound kernel, no shared-memory staging needed because a
+// group's records are contiguous and read once.
+#include "common.cuh"
+
+#include <cub/device/device_scan.cuh>
+
+namespace lctp {
+
+static constexpr int PAIR_MAX_ALNS = 16;     // per read end and contig; the reference uses 10 (locs.rs:741)
+
+struct MatesDev {
+    uint32_t R, max_alns, ins_len;
+    uint64_t N;
+    const uint64_t *ma_off;
+    const uint32_t *ma_contig, *ma_start, *ma_end;
+    const uint8_t *ma_flags;
+    const double *ma_ln_prob, *read_weight, *ins_ln_pmf;
+    double unmapped_penalty, insert_penalty, prob_diff;
+};
+
+__device__ __forceinline__ long long pair_total_key(double v) {     // f64::total_cmp key
+    long long b = __double_as_longlong(v);
+    return b ^ (long long)(((unsigned long long)(b >> 63)) >> 1);
+}
+
+struct TopK {                       // stable descending top-`cap` list (cap <= PAIR_MAX_ALNS)
+    double lp[PAIR_MAX_ALNS];
+    uint32_t m1[PAIR_MAX_ALNS], m2[PAIR_MAX_ALNS];
+    uint32_t n, total;
+    __device__ void push(double p, uint32_t a, uint32_t b, uint32_t cap) {
+        total++;
+        const long long key = pair_total_key(p);
+        uint32_t pos = n;
+        while (pos > 0 && pair_total_key(lp[pos - 1]) < key) pos--;      // after every entry >= p: stable
+        if (pos >= cap) return;
+        const uint32_t last = n < cap ? n : cap - 1;
+        for (uint32_t q = last; q > pos; q--) { lp[q] = lp[q - 1]; m1[q] = m1[q - 1]; m2[q] = m2[q - 1]; }
+        lp[pos] = p; m1[pos] = a; m2[pos] = b;
+        if (n < cap) n++;
+    }
+};
+
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+k_pair_groups(MatesDev D, uint32_t *__restrict__ counts, const uint64_t *__restrict__ offs,
+              uint32_t *__restrict__ pa_contig, double *__restrict__ pa_ln_prob, uint32_t *__restrict__ pa_mid1,
+              uint32_t *__restrict__ pa_mid2, int *__restrict__ err) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D.N) return;
+    // read of this record: last r with ma_off[r] <= i
+    uint32_t lo = 0, hi = D.R;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (D.ma_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    const uint32_t r = lo;
+    const uint64_t rb = D.ma_off[r], re = D.ma_off[r + 1];
+    const uint32_t contig = D.ma_contig[i];
+    if (i > rb) {
+        const uint32_t prev = D.ma_contig[i - 1];
+        if (prev == contig) { if (!WRITE) counts[i] = 0; return; }        // not the owner of its group
+        if (prev > contig) atomicOr(err, 1);                               // contigs must ascend within a read
+    }
+    uint64_t e = i + 1;
+    while (e < re && D.ma_contig[e] == contig) e++;
+    uint64_t f = i;
+    while (f < e && (D.ma_flags[f] & 1u) == 0) f++;
+    for (uint64_t q = f; q < e; q++) if ((D.ma_flags[q] & 1u) == 0) atomicOr(err, 2);   // first end before second
+    const uint32_t M = D.max_alns;
+    const uint32_t n1 = (uint32_t)min((uint64_t)M, f - i), n2 = (uint32_t)min((uint64_t)M, e - f);
+    const double unm_ins = D.unmapped_penalty + D.insert_penalty;          // locs.rs:815-816
+
+    TopK top;
+    top.n = 0; top.total = 0;
+    double best2[PAIR_MAX_ALNS];
+    for (uint32_t b = 0; b < n2; b++) best2[b] = -INFINITY;
+    for (uint32_t a = 0; a < n1; a++) {
+        const uint64_t ia = i + a;
+        const uint32_t s1 = D.ma_start[ia], e1 = D.ma_end[ia];
+        const double l1 = D.ma_ln_prob[ia];
+        const uint32_t st1 = D.ma_flags[ia] & 2u;
+        if (a > 0 && l1 > D.ma_ln_prob[ia - 1]) atomicOr(err, 4);          // ln_prob must descend within an end
+        double max1 = -INFINITY;
+        for (uint32_t b = 0; b < n2; b++) {
+            const uint64_t ib = f + b;
+            if ((D.ma_flags[ib] & 2u) == st1) continue;                    // aln.rs: strands must differ
+            const uint32_t s2 = D.ma_start[ib], e2 = D.ma_end[ib];
+            const uint32_t insert = max(e1, e2) - min(s1, s2);             // interv.rs:179-185
+            if (insert >= D.ins_len) { atomicOr(err, 8); continue; }
+            const double prob = __dadd_rn(__dadd_rn(l1, D.ma_ln_prob[ib]), D.ins_ln_pmf[insert]);
+            if (isfinite(prob)) {
+                max1 = fmax(max1, prob);
+                best2[b] = fmax(best2[b], prob);
+                top.push(prob, (s1 + e1) / 2, (s2 + e2) / 2, M);
+            }
+        }
+        const double alone1 = __dadd_rn(l1, unm_ins);
+        if (alone1 >= max1) top.push(alone1, (s1 + e1) / 2, LCTP_NONE_U32, M);
+    }
+    for (uint32_t b = 0; b < n2; b++) {
+        const uint64_t ib = f + b;
+        const double l2 = D.ma_ln_prob[ib];
+        if (b > 0 && l2 > D.ma_ln_prob[ib - 1]) atomicOr(err, 4);
+        const double alone2 = __dadd_rn(l2, unm_ins);
+        if (alone2 >= best2[b]) top.push(alone2, LCTP_NONE_U32, (D.ma_start[ib] + D.ma_end[ib]) / 2, M);
+    }
+    // partition_point over the first min(len, max_alns) sorted entries (locs.rs:796-797)
+    const double thresh = __dsub_rn(top.lp[0], D.prob_diff);
+    uint32_t keep = 0;
+    while (keep < top.n && top.lp[keep] >= thresh) keep++;
+    if (!WRITE) { counts[i] = keep; return; }
+    const double weight = D.read_weight ? D.read_weight[r] : 1.0;
+    const uint64_t o = offs[i];
+    for (uint32_t q = 0; q < keep; q++) {
+        pa_contig[o + q] = contig;
+        pa_ln_prob[o + q] = __dmul_rn(top.lp[q], weight);                  // locs.rs:861-863
+        pa_mid1[o + q] = top.m1[q];
+        pa_mid2[o + q] = top.m2[q];
+    }
+}
+
+// pa_off[r] = offs[ma_off[r]]; unmapped_prob[r] = weight * (2 * unmapped_penalty + insert_penalty) (locs.rs:866)
+__global__ void k_pair_read_outputs(MatesDev D, const uint64_t *__restrict__ offs, uint64_t total,
+                                    uint64_t *__restrict__ pa_off, double *__restrict__ unmapped_prob) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > D.R) return;
+    const uint64_t m = D.ma_off[r];
+    pa_off[r] = m < D.N ? offs[m] : total;
+    if (r < D.R) {
+        const double weight = D.read_weight ? D.read_weight[r] : 1.0;
+        unmapped_prob[r] = __dmul_rn(weight, __dadd_rn(__dmul_rn(2.0, D.unmapped_penalty), D.insert_penalty));
+    }
+}
+
+template <typename T>
+static int to_dev(DevBuf<T> &dst, const T *src, size_t n, cudaStream_t s) {
+    int rc = dst.alloc(n);
+    if (rc) return rc;
+    if (n) LCTP_CUDA_CHECK(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    return LCTP_OK;
+}
+
+int pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig,
+                    double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob,
+                    uint64_t *n_out) {
+    cudaStream_t s = ctx->stream;
+    const uint32_t R = in->n_reads;
+    if (R == 0 || !in->ma_off) { set_error("lctp_pair_alignments: no reads"); return LCTP_E_INVALID; }
+    if (in->max_alns == 0 || in->max_alns > (uint32_t)PAIR_MAX_ALNS) {
+        set_error("lctp_pair_alignments: max_alns %u unsupported (1..=%d)", in->max_alns, PAIR_MAX_ALNS);
+        return LCTP_E_CAPACITY;
+    }
+    const uint64_t N = in->ma_off[R];
+    DevBuf<uint64_t> d_off, d_offs, d_pa_off;
+    DevBuf<uint32_t> d_contig, d_start, d_end, d_counts, d_oc, d_m1, d_m2;
+    DevBuf<uint8_t> d_flags;
+    DevBuf<double> d_lp, d_w, d_ins, d_olp, d_unm;
+    DevBuf<int> d_err;
+    DevBuf<unsigned char> d_tmp;
+    int rc;
+    if ((rc = to_dev(d_off, in->ma_off, (size_t)R + 1, s))) return rc;
+    if ((rc = to_dev(d_contig, in->ma_contig, N, s))) return rc;
+    if ((rc = to_dev(d_start, in->ma_start, N, s))) return rc;
+    if ((rc = to_dev(d_end, in->ma_end, N, s))) return rc;
+    if ((rc = to_dev(d_flags, in->ma_flags, N, s))) return rc;
+    if ((rc = to_dev(d_lp, in->ma_ln_prob, N, s))) return rc;
+    if (in->read_weight && (rc = to_dev(d_w, in->read_weight, R, s))) return rc;
+    if ((rc = to_dev(d_ins, in->ins_ln_pmf, in->ins_len, s))) return rc;
+    if ((rc = d_counts.alloc(N + 1))) return rc;
+    if ((rc = d_offs.alloc(N + 1))) return rc;
+    if ((rc = d_err.alloc(1))) return rc;
+    if ((rc = d_pa_off.alloc((size_t)R + 1))) return rc;
+    if ((rc = d_unm.alloc(R))) return rc;
+    LCTP_CUDA_CHECK(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
+    LCTP_CUDA_CHECK(cudaMemsetAsync(d_counts.p, 0, (N + 1) * sizeof(uint32_t), s));
+
+    MatesDev D;
+    D.R = R; D.max_alns = in->max_alns; D.ins_len = in->ins_len; D.N = N;
+    D.ma_off = d_off.p; D.ma_contig = d_contig.p; D.ma_start = d_start.p; D.ma_end = d_end.p;
+    D.ma_flags = d_flags.p; D.ma_ln_prob = d_lp.p; D.read_weight = in->read_weight ? d_w.p : nullptr;
+    D.ins_ln_pmf = d_ins.p;
+    D.unmapped_penalty = in->unmapped_penalty; D.insert_penalty = in->insert_penalty; D.prob_diff = in->prob_diff;
+
+    uint64_t total = 0;
+    if (N) {
+        const unsigned grid = (unsigned)((N + 127) / 128);
+        LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[0], s));
+        k_pair_groups<false><<<grid, 128, 0, s>>>(D, d_counts.p, nullptr, nullptr, nullptr, nullptr, nullptr, d_err.p);
+        ctx->launches++;
+        size_t tmp_bytes = 0;
+        LCTP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts.p, d_offs.p, (int)(N + 1), s));
+        if ((rc = d_tmp.alloc(tmp_bytes))) return rc;
+        LCTP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_counts.p, d_offs.p, (int)(N + 1), s));
+        ctx->launches++;
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(&total, d_offs.p + N, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        int err = 0;
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (err) {
+            set_error("lctp_pair_alignments: malformed mate alignments (flags=%d: 1=contigs not ascending within a "
+                      "read, 2=second-end record before a first-end record of the same contig, 4=ln_prob not "
+                      "descending within a (read, contig, end) run, 8=insert size outside the ln-pmf table)", err);
+            return LCTP_E_INVALID;
+        }
+        if (total > cap) {
+            set_error("lctp_pair_alignments: output capacity %llu too small (%llu pair alignments)",
+                      (unsigned long long)cap, (unsigned long long)total);
+            return LCTP_E_CAPACITY;
+        }
+        if ((rc = d_oc.alloc(total))) return rc;
+        if ((rc = d_olp.alloc(total))) return rc;
+        if ((rc = d_m1.alloc(total))) return rc;
+        if ((rc = d_m2.alloc(total))) return rc;
+        k_pair_groups<true><<<grid, 128, 0, s>>>(D, nullptr, d_offs.p, d_oc.p, d_olp.p, d_m1.p, d_m2.p, d_err.p);
+        ctx->launches++;
+        LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[1], s));
+    }
+    k_pair_read_outputs<<<(R + 1 + 255) / 256, 256, 0, s>>>(D, d_offs.p, total, d_pa_off.p, d_unm.p);
+    ctx->launches++;
+    LCTP_CUDA_CHECK(cudaGetLastError());
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_off, d_pa_off.p, ((size_t)R + 1) * 8, cudaMemcpyDeviceToHost, s));
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(unmapped_prob, d_unm.p, (size_t)R * 8, cudaMemcpyDeviceToHost, s));
+    if (total) {
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_contig, d_oc.p, total * 4, cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_ln_prob, d_olp.p, total * 8, cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_mid1, d_m1.p, total * 4, cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_mid2, d_m2.p, total * 4, cudaMemcpyDeviceToHost, s));
+    }
+    LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (N) {
+        float ms = 0.f;
+        LCTP_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        ctx->stats.pairing_ms += ms;
+        ctx->stats.pairing_launches += 1;
+        ctx->stats.pairing_mates += N;
+        ctx->stats.pairing_pairs += total;
+    }
+    if (n_out) *n_out = total;
+    return LCTP_OK;
+}
+
+}  // namespace lctp

@@ -70,7 +70,17 @@ class ResultC(C.Structure):
 class StatsC(C.Structure):
     _fields_ = [("prefilter_ms", C.c_double), ("prefilter_launches", C.c_uint64), ("prefilter_genotypes", C.c_uint64),
                 ("stage_ms", C.c_double), ("stage_launches", C.c_uint64), ("stage_genotypes", C.c_uint64),
-                ("stage_attempts", C.c_uint64), ("stage_iters", C.c_uint64), ("stage_alns", C.c_uint64)]
+                ("stage_attempts", C.c_uint64), ("stage_iters", C.c_uint64), ("stage_alns", C.c_uint64),
+                ("pairing_ms", C.c_double), ("pairing_launches", C.c_uint64), ("pairing_mates", C.c_uint64),
+                ("pairing_pairs", C.c_uint64)]
+
+
+class MatesC(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_haps", C.c_uint32), ("max_alns", C.c_uint32), ("ins_len", C.c_uint32),
+                ("ma_off", C.c_void_p), ("ma_contig", C.c_void_p), ("ma_flags", C.c_void_p), ("ma_start", C.c_void_p),
+                ("ma_end", C.c_void_p), ("ma_ln_prob", C.c_void_p), ("read_weight", C.c_void_p),
+                ("ins_ln_pmf", C.c_void_p),
+                ("unmapped_penalty", C.c_double), ("insert_penalty", C.c_double), ("prob_diff", C.c_double)]
 
 
 # Every symbol include/lctp.h declares: name -> (restype, argtypes)
@@ -87,6 +97,8 @@ SYMBOLS = {
     "lctp_sync": (C.c_int, [_P]),
     "lctp_get_stats": (C.c_int, [_P, _P, C.c_int]),
     "lctp_measure_fp64_rate": (C.c_int, [_P, _P]),
+    "lctp_pair_alignments": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P]),
+    "lctp_sizeof_mates": (C.c_size_t, []),
     "lctp_locus_upload": (C.c_int, [_P, _P, _P]),
     "lctp_locus_free": (None, [_P]),
     "lctp_best_aln_matrix": (C.c_int, [_P, _P]),
@@ -134,6 +146,7 @@ def load():
         assert lib.lctp_sizeof_locus() == C.sizeof(LocusC)
         assert lib.lctp_sizeof_stage() == C.sizeof(StageC)
         assert lib.lctp_sizeof_result() == C.sizeof(ResultC)
+        assert lib.lctp_sizeof_mates() == C.sizeof(MatesC)
         _lib = lib
     return _lib
 

@@ -236,6 +236,69 @@ class Context:
             pass
 
 
+@dataclass
+class Mates:
+    """Mate alignments of R read pairs: the input of identify_paired_end_alignments (src/model/locs.rs:805-868),
+    per read sorted by (contig asc, read end asc, ln_prob desc).  flags: bit0 = read end, bit1 = strand."""
+
+    n_reads: int
+    n_haps: int
+    ma_off: np.ndarray
+    ma_contig: np.ndarray
+    ma_flags: np.ndarray
+    ma_start: np.ndarray
+    ma_end: np.ndarray
+    ma_ln_prob: np.ndarray
+    ins_ln_pmf: np.ndarray
+    unmapped_penalty: float
+    insert_penalty: float
+    prob_diff: float
+    read_weight: Optional[np.ndarray] = None
+    max_alns: int = 10
+
+    def to_c(self, keep: list, struct=None):
+        def arr(a, dt):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data
+        m = (struct or ffi.MatesC)()
+        m.n_reads, m.n_haps, m.max_alns, m.ins_len = self.n_reads, self.n_haps, self.max_alns, len(self.ins_ln_pmf)
+        m.ma_off = arr(self.ma_off, np.uint64)
+        m.ma_contig = arr(self.ma_contig, np.uint32)
+        m.ma_flags = arr(self.ma_flags, np.uint8)
+        m.ma_start = arr(self.ma_start, np.uint32)
+        m.ma_end = arr(self.ma_end, np.uint32)
+        m.ma_ln_prob = arr(self.ma_ln_prob, np.float64)
+        m.read_weight = arr(self.read_weight, np.float64)
+        m.ins_ln_pmf = arr(self.ins_ln_pmf, np.float64)
+        m.unmapped_penalty, m.insert_penalty, m.prob_diff = self.unmapped_penalty, self.insert_penalty, self.prob_diff
+        return m
+
+
+def pair_alignments(ctx: "Context", mates: Mates, cap: Optional[int] = None) -> dict:
+    """lctp_pair_alignments: the pa_* / unmapped_prob arrays of the flat locus, computed on the device."""
+    keep: list = []
+    m = mates.to_c(keep)
+    R = mates.n_reads
+    n_groups_bound = len(mates.ma_contig)            # every group keeps <= max_alns and has >= 1 mate
+    cap = int(cap if cap is not None else min(n_groups_bound * mates.max_alns, max(1, n_groups_bound) * mates.max_alns))
+    pa_off = np.zeros(R + 1, dtype=np.uint64)
+    pa_contig = np.zeros(max(1, cap), dtype=np.uint32)
+    pa_ln_prob = np.zeros(max(1, cap), dtype=np.float64)
+    pa_mid1 = np.zeros(max(1, cap), dtype=np.uint32)
+    pa_mid2 = np.zeros(max(1, cap), dtype=np.uint32)
+    unm = np.zeros(R, dtype=np.float64)
+    n_out = C.c_uint64(0)
+    ffi.check(ctx.lib.lctp_pair_alignments(ctx._h, C.byref(m), cap, pa_off.ctypes.data, pa_contig.ctypes.data,
+                                           pa_ln_prob.ctypes.data, pa_mid1.ctypes.data, pa_mid2.ctypes.data,
+                                           unm.ctypes.data, C.byref(n_out)))
+    n = int(n_out.value)
+    return dict(pa_off=pa_off, pa_contig=pa_contig[:n].copy(), pa_ln_prob=pa_ln_prob[:n].copy(),
+                pa_mid1=pa_mid1[:n].copy(), pa_mid2=pa_mid2[:n].copy(), unmapped_prob=unm)
+
+
 class ContextPool:
     """K contexts (one CUDA stream each) on one GPU, one host thread per context.  Loci are independent
     units of work (src/command/genotype.rs:1331-1351: one `analyze_locus` per locus, separate long_jump

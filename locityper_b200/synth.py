@@ -383,3 +383,55 @@ def load_locus(path: str) -> Locus:
     for k in ("prob_diff", "lik_skew", "min_weight", "filt_diff", "prob_thresh"):
         kw[k] = float(sc[k])
     return Locus(truth=tuple(int(x) for x in z["_truth"]), **kw)
+
+
+def make_mates(n_haps: int, n_reads: int, locus_len: int, seed: int, *, multi_frac: float = 0.15,
+               over_cap_frac: float = 0.01, max_alns: int = 10) -> dict:
+    """Synthetic mate alignments (the input of identify_paired_end_alignments, src/model/locs.rs:805-868) for R
+    read pairs on H haplotypes: keyword arguments of `genotype.Mates`.  Per (read, haplotype) either both mates,
+    one of them or none align; `multi_frac` of the ends have 1-3 secondary alignments (random place and strand,
+    so same-strand combinations and far-apart pairs occur) and `over_cap_frac` have more than `max_alns`
+    alignments; records are sorted the way the reference consumes them (contig asc, end asc, ln_prob desc)."""
+    rng = np.random.default_rng(seed)
+    H, R, L = n_haps, n_reads, locus_len
+    read_len = 150
+    kind = rng.random((R, H))
+    has1 = kind < 0.88
+    has2 = (kind < 0.80) | ((kind >= 0.88) & (kind < 0.96))
+    cnt = np.zeros((R, H, 2), dtype=np.int64)
+    for e, has in enumerate((has1, has2)):
+        extra = np.where(rng.random((R, H)) < multi_frac, rng.integers(1, 4, (R, H)), 0)
+        extra = np.where(rng.random((R, H)) < over_cap_frac, max_alns + rng.integers(1, 4, (R, H)), extra)
+        cnt[:, :, e] = np.where(has, 1 + extra, 0)
+    flat = cnt.reshape(-1)
+    N = int(flat.sum())
+    key = np.repeat(np.arange(flat.size), flat)              # (r, h, e) of every record
+    r_ix, h_ix, e_ix = key // (2 * H), (key // 2) % H, key % 2
+    first_of_key = np.r_[True, key[1:] != key[:-1]] if N else np.zeros(0, dtype=bool)
+    base = rng.integers(0, max(1, L - 1200), R)
+    ins = np.clip(rng.normal(450.0, 60.0, R), 160, 1000).astype(np.int64)
+    jitter = rng.integers(-3, 4, N)
+    prim_start = np.where(e_ix == 0, base[r_ix], base[r_ix] + ins[r_ix] - read_len) + jitter
+    sec_start = rng.integers(0, max(1, L - read_len), N)
+    start = np.clip(np.where(first_of_key, prim_start, sec_start), 0, L - read_len)
+    length = read_len + rng.integers(-5, 6, N)
+    end = np.minimum(start + length, L)
+    strand = np.where(first_of_key, e_ix, rng.integers(0, 2, N))
+    ln_prob = np.where(first_of_key, -np.abs(rng.normal(0.0, 8.0, N)), -np.abs(rng.normal(20.0, 10.0, N)))
+    # a few exact ties inside a contig to exercise the stable order
+    tie = rng.random(N) < 0.02
+    ln_prob = np.where(tie, np.round(ln_prob), ln_prob)
+    order = np.lexsort((-ln_prob, e_ix, h_ix, r_ix))
+    r_ix, h_ix, e_ix = r_ix[order], h_ix[order], e_ix[order]
+    ma_off = np.zeros(R + 1, dtype=np.uint64)
+    np.cumsum(np.bincount(r_ix, minlength=R), out=ma_off[1:])
+    sizes = np.arange(L + 1, dtype=np.float64)
+    sd = 60.0
+    ins_ln_pmf = -0.5 * ((sizes - 450.0) / sd) ** 2 - math.log(sd * math.sqrt(2.0 * math.pi))
+    weight = rng.choice([1.0, 1.0, 1.0, 0.5, 0.25], R)
+    U = -10.0 * LN10
+    return dict(n_reads=R, n_haps=H, ma_off=ma_off, ma_contig=h_ix.astype(np.uint32),
+                ma_flags=(e_ix | (strand[order] << 1)).astype(np.uint8), ma_start=start[order].astype(np.uint32),
+                ma_end=end[order].astype(np.uint32), ma_ln_prob=ln_prob[order].astype(np.float64),
+                ins_ln_pmf=ins_ln_pmf, unmapped_penalty=U, insert_penalty=float(ins_ln_pmf.max()),
+                prob_diff=abs(U) + LN10, read_weight=weight.astype(np.float64), max_alns=max_alns)

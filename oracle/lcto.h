@@ -215,6 +215,27 @@ int lcto_solve(const lcto_locus *L, const lcto_stage *stages, size_t n_stages, s
 
 const char *lcto_version(void);
 
+/* ------------------------------------------------ pair alignments (lcto_pairs.c) */
+
+/* Mate alignments of R read pairs, per read sorted by (contig asc, read end asc, ln_prob desc). */
+typedef struct lcto_mates {
+    uint32_t n_reads, n_haps, max_alns, ins_len;
+    const uint64_t *ma_off;      /* [R+1] */
+    const uint32_t *ma_contig;   /* [N] */
+    const uint8_t  *ma_flags;    /* [N] bit0: read end (0 first / 1 second), bit1: strand */
+    const uint32_t *ma_start;    /* [N] interval start */
+    const uint32_t *ma_end;      /* [N] interval end (exclusive) */
+    const double   *ma_ln_prob;  /* [N] */
+    const double   *read_weight; /* [R] or NULL (= 1.0) */
+    const double   *ins_ln_pmf;  /* [ins_len] InsertDistr::ln_prob(size) */
+    double unmapped_penalty, insert_penalty, prob_diff;
+} lcto_mates;
+
+/* identify_paired_end_alignments for every read (src/model/locs.rs:805-868). Outputs are the `pa_*` /
+ * `unmapped_prob` arrays of the flat locus.  0 = ok, -2 = insert size outside the table, -3 = cap too small. */
+int lcto_pair_alignments(const lcto_mates *in, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig,
+                         double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob);
+
 #ifdef __cplusplus
 }
 #endif

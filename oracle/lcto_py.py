@@ -159,6 +159,8 @@ def lib():
                                                    C.c_double, C.c_double, C.c_uint16]
         L.lcto_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lcto_pair_alignments.restype = C.c_int
+        L.lcto_pair_alignments.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 6
         L.lcto_version.restype = C.c_char_p
         _lib = L
     return _lib
@@ -322,3 +324,33 @@ def solve(ol: OracleLocus, scheme: Sequence[Stage], threads: int, rng: Rng, os_t
         out["scores"] = scores
         out["filtered_ixs"] = filt[:out["n_filtered"]].copy()
     return out
+
+
+class MatesC(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_haps", C.c_uint32), ("max_alns", C.c_uint32), ("ins_len", C.c_uint32),
+                ("ma_off", C.c_void_p), ("ma_contig", C.c_void_p), ("ma_flags", C.c_void_p), ("ma_start", C.c_void_p),
+                ("ma_end", C.c_void_p), ("ma_ln_prob", C.c_void_p), ("read_weight", C.c_void_p),
+                ("ins_ln_pmf", C.c_void_p),
+                ("unmapped_penalty", C.c_double), ("insert_penalty", C.c_double), ("prob_diff", C.c_double)]
+
+
+def pair_alignments(mates) -> dict:
+    """lcto_pair_alignments on a locityper_b200.genotype.Mates-shaped object (plain data; the oracle does not
+    import the product's code paths, only reads the arrays)."""
+    keep: list = []
+    m = mates.to_c(keep, struct=MatesC)
+    R = mates.n_reads
+    cap = max(1, len(mates.ma_contig) * mates.max_alns)
+    pa_off = np.zeros(R + 1, dtype=np.uint64)
+    pa_contig = np.zeros(cap, dtype=np.uint32)
+    pa_ln_prob = np.zeros(cap, dtype=np.float64)
+    pa_mid1 = np.zeros(cap, dtype=np.uint32)
+    pa_mid2 = np.zeros(cap, dtype=np.uint32)
+    unm = np.zeros(R, dtype=np.float64)
+    rc = lib().lcto_pair_alignments(C.byref(m), cap, pa_off.ctypes.data, pa_contig.ctypes.data, pa_ln_prob.ctypes.data,
+                                    pa_mid1.ctypes.data, pa_mid2.ctypes.data, unm.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"lcto_pair_alignments failed: {rc}")
+    n = int(pa_off[R])
+    return dict(pa_off=pa_off, pa_contig=pa_contig[:n].copy(), pa_ln_prob=pa_ln_prob[:n].copy(),
+                pa_mid1=pa_mid1[:n].copy(), pa_mid2=pa_mid2[:n].copy(), unmapped_prob=unm)
