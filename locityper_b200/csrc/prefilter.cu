@@ -91,6 +91,8 @@ k_prefilter_pairs(const double *__restrict__ Mt, uint32_t R, uint32_t H, uint32_
     }
     const int tid = threadIdx.x;
     const int tx = tid % NTX, ty = tid / NTX;
+    // tile column of register column b of thread tx
+    auto col_of = [](int tx_, int b) { return TJ % 2 == 0 ? (b / 2) * (2 * NTX) + tx_ * 2 + (b & 1) : tx_ * TJ + b; };
 
     double acc[TI][TJ];
 #pragma unroll
@@ -158,9 +160,11 @@ k_prefilter_pairs(const double *__restrict__ Mt, uint32_t R, uint32_t H, uint32_
                 }
             } else ai[0] = sA[stage][rc][ty];
             if constexpr (TJ % 2 == 0) {
+                // column pairs are interleaved across the threads (thread tx owns pairs tx, tx + NTX, ...):
+                // a quarter-warp reads 8 consecutive 16-byte chunks, so the loads are bank-conflict free
 #pragma unroll
                 for (int b = 0; b < TJ; b += 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(&sB[stage][rc][tx * TJ + b]);
+                    const double2 v = *reinterpret_cast<const double2 *>(&sB[stage][rc][col_of(tx, b)]);
                     bj_[b] = v.x; bj_[b + 1] = v.y;
                 }
             } else bj_[0] = sB[stage][rc][tx];
@@ -177,7 +181,7 @@ k_prefilter_pairs(const double *__restrict__ Mt, uint32_t R, uint32_t H, uint32_
         const uint32_t i = i0 + ty * TI + a;
 #pragma unroll
         for (int b = 0; b < TJ; b++) {
-            const uint32_t j = j0 + tx * TJ + b;
+            const uint32_t j = j0 + col_of(tx, b);
             if (i <= j && j < H) {
                 const uint64_t g = pair_gid(i, j, H);
                 if (g >= g_begin && g < g_end) {

@@ -323,31 +323,35 @@ __device__ __forceinline__ unsigned long long ord_key(double v) {
     return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
 }
 
-// Per-window state in shared memory: one 64-byte record per window holding the window's weight, its
-// depth-table row, the current read depth d and the five products weight * table[row][d-2 .. d+2]
-// (rounded once, exactly as WindowDistr::ln_prob computes them, src/model/distr_cache.rs:34-39).  Every
-// likelihood delta of the solver loops is then a difference of two shared-memory values: no global loads.
+// Per-window state in shared memory, 64 bytes per window: the window's weight, its depth-table row, the
+// current read depth d and the five products weight * table[row][d-2 .. d+2] (rounded once, exactly as
+// WindowDistr::ln_prob computes them, src/model/distr_cache.rs:34-39).  Every likelihood delta of the
+// solver loops is then a difference of two shared-memory values: no global loads.
 // TRIVIAL windows (WindowDistr::TRIVIAL, distr_cache.rs:27-30) are stored as weight 0 on the all-zero
 // extra row of the device table, so 0*0 - 0*0 = +0.0 reproduces the reference's literal 0.0 with no
 // branch; a zero depth change gives p - p = +0.0 the same way.
-struct __align__(16) WinRec {
-    double p[5];        // weight * table[row + depth + k - 2]
-    double weight;
-    uint32_t row;       // gc * depth_k
-    uint32_t depth;
-    uint32_t pad[2];
+// Layout: structure of arrays (five product planes, then weight, row, depth), so that lanes looking up
+// DIFFERENT windows hit different banks -- with one 64-byte record per window every lane of an evaluation
+// pass landed in the same two bank groups (16-way conflicts on the hottest loads of the kernel).
+struct WinState {
+    double *base;       // p[5][wp] | weight[wp] | row[wp] (u32) | depth[wp] (u32)
+    uint32_t wp;        // plane stride (windows, even)
+    __device__ __forceinline__ double &p(uint32_t w, int k) const { return base[(uint32_t)k * wp + w]; }
+    __device__ __forceinline__ double &weight(uint32_t w) const { return base[5u * wp + w]; }
+    __device__ __forceinline__ uint32_t &row(uint32_t w) const { return ((uint32_t *)(base + 6u * wp))[w]; }
+    __device__ __forceinline__ uint32_t &depth(uint32_t w) const { return ((uint32_t *)(base + 6u * wp))[wp + w]; }
 };
-static_assert(sizeof(WinRec) == 64, "WinRec must be 64 bytes");
+__host__ __device__ inline uint32_t win_stride(uint32_t Wmax) { return (Wmax + 1u) & ~1u; }
 
 struct WarpShared {
-    WinRec *win;           // [Wmax]
+    WinState win;
     uint16_t *ntc_start;   // [R+1]  compact candidate offset of every non-trivial read (+ end sentinel)
     uint8_t *nt_assgn;     // [R]    current assignment of every non-trivial read
     uint32_t zero_row;     // offset of the all-zero row
     uint32_t depth_k;
 };
 __host__ __device__ inline size_t group_smem_bytes(uint32_t Wmax, uint32_t R) {
-    return (size_t)Wmax * 64 + align_up(((size_t)R + 1) * 2, 16) + align_up((size_t)R, 16);
+    return (size_t)win_stride(Wmax) * 64 + align_up(((size_t)R + 1) * 2, 16) + align_up((size_t)R, 16);
 }
 
 __device__ __forceinline__ double rec_lp(const uint4 &r) { return __hiloint2double((int)r.y, (int)r.x); }
@@ -357,15 +361,13 @@ __device__ __forceinline__ uint4 make_rec(double lp, uint32_t w) {
 
 // Recompute slice entry k of window w from its (weight, row, depth).
 __device__ __forceinline__ void win_refresh(const WarpShared &ws, const double *__restrict__ table, uint32_t w, int k) {
-    WinRec &r = ws.win[w];
-    const int d = min(max((int)r.depth + k - 2, 0), (int)ws.depth_k - 1);   // out-of-range entries are never used
-    r.p[k] = __dmul_rn(r.weight, __ldg(table + r.row + d));
+    const int d = min(max((int)ws.win.depth(w) + k - 2, 0), (int)ws.depth_k - 1);   // out-of-range entries are never used
+    ws.win.p(w, k) = __dmul_rn(ws.win.weight(w), __ldg(table + ws.win.row(w) + d));
 }
 
 // atomic_depth_lik_diff (src/model/assgn.rs:244-254), branch-free
 __device__ __forceinline__ double atomic_diff(const WarpShared &ws, uint32_t w, int change) {
-    const WinRec &r = ws.win[w];
-    return __dsub_rn(r.p[2 + change], r.p[2]);
+    return __dsub_rn(ws.win.p(w, 2 + change), ws.win.p(w, 2));
 }
 
 // depth_lik_diff (src/model/assgn.rs:259-284): ((a1 + a2) + a3) + a4, window merging done with selects
@@ -540,7 +542,7 @@ __device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I,
         }
     }
     // (ii) window distributions: one bounded i32 draw per window, contigs in genotype order
-    if (lane < 2) { ws.win[lane].weight = 0.0; ws.win[lane].row = ws.zero_row; ws.win[lane].depth = 0; }
+    if (lane < 2) { ws.win.weight(lane) = 0.0; ws.win.row(lane) = ws.zero_row; ws.win.depth(lane) = 0; }
     for (uint32_t k = 0; k < L.p; k++) {
         const uint32_t hap = I.haps[k];
         const uint32_t nwin = L.hap_n_windows[hap];
@@ -572,9 +574,9 @@ __device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I,
                 const uint32_t gc = L.pos_gc[pos_off + idx];
                 const uint32_t w = I.wshift[k] + i0 + lane;
                 const bool trivial = weight < L.min_weight || weight < 1e-7;
-                ws.win[w].weight = trivial ? 0.0 : weight;
-                ws.win[w].row = trivial ? ws.zero_row : gc * L.depth_k;
-                ws.win[w].depth = 0;
+                ws.win.weight(w) = trivial ? 0.0 : weight;
+                ws.win.row(w) = trivial ? ws.zero_row : gc * L.depth_k;
+                ws.win.depth(w) = 0;
             }
         }
     }
@@ -595,7 +597,7 @@ __device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance
                                 Xo<GS> &rng, int init_mode, double &aln_lik, double &depth_lik) {
     const Grp<GS> &g = rng.g;
     const int lane = g.lane;
-    for (uint32_t w = lane; w < I.W; w += GS) ws.win[w].depth = 0;
+    for (uint32_t w = lane; w < I.W; w += GS) ws.win.depth(w) = 0;
     // assignments of non-trivial reads
     for (uint32_t i0 = 0; i0 < I.n_nt; i0 += GS) {
         const uint32_t i = i0 + lane;
@@ -631,8 +633,8 @@ __device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance
             const uint32_t ix = start + a;
             term = S.cand_lnprob[ix];
             const uint32_t w12 = S.cand_w[ix];
-            atomicAdd(&ws.win[w12 & 0xFFFFu].depth, 1u);
-            atomicAdd(&ws.win[w12 >> 16].depth, 1u);
+            atomicAdd(&ws.win.depth(w12 & 0xFFFFu), 1u);
+            atomicAdd(&ws.win.depth(w12 >> 16), 1u);
         }
         nt_base += __popc(ntmask);
         seq_add(g, al, term, (int)min((uint32_t)GS, L.R - r0));
@@ -644,7 +646,7 @@ __device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance
     double dl = 0.0;
     for (uint32_t w0 = 0; w0 < I.W; w0 += GS) {
         const uint32_t w = w0 + lane;
-        const double term = w < I.W ? ws.win[w].p[2] : 0.0;
+        const double term = w < I.W ? ws.win.p(w, 2) : 0.0;
         seq_add(g, dl, term, (int)min((uint32_t)GS, I.W - w0));
     }
     aln_lik = al;
@@ -694,10 +696,10 @@ __device__ __forceinline__ void apply_move(const Grp<GS> &g, const WarpShared &w
     depth_lik = __dadd_rn(depth_lik, mv.dld);
     aln_lik = __dadd_rn(aln_lik, mv.dlp);
     if (g.lane == 0) {
-        ws.win[mv.w34 & 0xFFFFu].depth += 1;
-        ws.win[mv.w34 >> 16].depth += 1;
-        ws.win[mv.w12 & 0xFFFFu].depth -= 1;
-        ws.win[mv.w12 >> 16].depth -= 1;
+        ws.win.depth(mv.w34 & 0xFFFFu) += 1;
+        ws.win.depth(mv.w34 >> 16) += 1;
+        ws.win.depth(mv.w12 & 0xFFFFu) -= 1;
+        ws.win.depth(mv.w12 >> 16) -= 1;
         ws.nt_assgn[idx] = (uint8_t)new_a;
     }
     g.sync();
@@ -993,7 +995,8 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
     WarpShared ws;
     {
         unsigned char *base = smem + (size_t)gib * group_smem_bytes(P.Wmax, L.R);
-        ws.win = (WinRec *)base;               base += (size_t)P.Wmax * 64;
+        ws.win.base = (double *)base;          ws.win.wp = win_stride(P.Wmax);
+        base += (size_t)ws.win.wp * 64;
         ws.ntc_start = (uint16_t *)base;       base += align_up(((size_t)L.R + 1) * 2, 16);
         ws.nt_assgn = (uint8_t *)base;
         ws.zero_row = LCTP_GC_BINS * L.depth_k;
