@@ -373,6 +373,16 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r01_ncu_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            e = json.load(f)[kernel]
+        return {"dram_bytes_per_launch": e["dram_bytes_per_launch"], "capture": e["capture"]}
+    except Exception:
+        return None
+
+
 def rooflines(st, loci, args, peak, peak_src, fp64_rate=None):
     """roofline of the dominant kernel (the solver stage) + the prefilter kernel, from device-side timings."""
     loc = loci[0]
@@ -386,7 +396,8 @@ def rooflines(st, loci, args, peak, peak_src, fp64_rate=None):
         sec = st["stage_ms"] / 1e3
         ach = bytes_alg / sec / 1e9
         out["roofline"] = {"kernel": "k_solve_stage", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                           "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                           "frac": ach / peak, "traffic": ncu_traffic("k_solve_stage") if args.config == "C2" else None,
+                           "peak_source": peak_src,
                            "bytes_alg_per_launch": bytes_alg / st["stage_launches"],
                            "avg_launch_ms": st["stage_ms"] / st["stage_launches"],
                            "note": "latency/issue-bound dependent chains (SURVEY 8d): HBM fraction is not the limiter; "
@@ -431,6 +442,7 @@ def kir_prefilter(ctx, genotype, peak, fp64_rate):
             "unit": "T FP64-pipe lane-instructions/s", "frac": ops / sec / fp64_rate,
             "peak_source": "DADD microbenchmark run live (lctp_measure_fp64_rate)",
             "avg_launch_ms": st["prefilter_ms"] / st["prefilter_launches"],
+            "traffic": ncu_traffic("k_prefilter_pairs_kir"),
             "hbm_reference_pattern": {"achieved": gp * (p * R * 8 + 8) / sec / 1e9, "peak": peak, "unit": "GB/s",
                                       "frac": gp * (p * R * 8 + 8) / sec / 1e9 / peak}}
 
