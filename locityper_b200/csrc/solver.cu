@@ -34,7 +34,10 @@ namespace lctp {
 #endif
 static constexpr int CTA_THREADS = LCTP_CTA_THREADS;
 static constexpr int MAX_SAMPLE = 11;          // Floyd branch of rand::seq::index::sample
-static constexpr int RNG_C = 64;               // stream outputs generated per lane per fill
+#ifndef LCTP_RNG_C
+#define LCTP_RNG_C 256
+#endif
+static constexpr int RNG_C = LCTP_RNG_C;               // stream outputs generated per lane per fill
 static constexpr int RNG_BUF = 32 * RNG_C;     // slab space for one fill (GS * RNG_C <= this)
 static constexpr int N_SETUP_MATS = 5;         // T^(C*2^k), k = 0..4
 
