@@ -34,6 +34,9 @@ namespace lctp {
 #endif
 static constexpr int CTA_THREADS = LCTP_CTA_THREADS;
 static constexpr int MAX_SAMPLE = 11;          // Floyd branch of rand::seq::index::sample
+#ifndef LCTP_HEADS
+#define LCTP_HEADS 2
+#endif
 #ifndef LCTP_RNG_C
 #define LCTP_RNG_C 256
 #endif
@@ -50,36 +53,36 @@ struct StageParams {
 };
 
 struct Slab {
-    double *cand_lnprob;   // [cap]  candidates of every read, read-major, sorted per read (a5)
-    uint32_t *cand_w;      // [cap]  (w1 | w2 << 16)
-    uint32_t *cand_src;    // [cap]  index into cm arrays, LCTP_NONE_U32 = "both mates unmapped" option
-    uint32_t *cand_ntc;    // [cap]  index into the compact arrays, LCTP_NONE_U32 for trivial reads
+    // Candidates of every read in read order (the reference's `alns`, a5): only what apply_tweak and the
+    // count output need per candidate -- where it came from and where its solver record lives.
+    uint2 *cmap;           // [cap]  x = index into the cm arrays | contig index << 28 (LCTP_NONE_U32 = the
+                           //        "both mates unmapped" option); y = index of its record in `ntc`, or
+                           //        TRIV_TAG | read id for the single candidate of a trivial read
     uint32_t *read_off;    // [R+1]
-    uint4 *ntc;            // [cap]  compact copy of the non-trivial reads' candidates, in read order:
+    uint4 *ntc;            // [cap]  records of the non-trivial reads' candidates, compact, in read order:
                            //        x,y = ln_prob (f64 bits), z = windows (w1 | w2 << 16), w unused
-    uint8_t *cand_cix;     // [cap]
+    double *triv_lp;       // [R]    ln_prob of the only candidate of a trivial read
+    uint32_t *triv_w;      // [R]    its windows
     uint64_t *rng_buf;     // [RNG_BUF] pre-generated draws of the worker's stream
     uint64_t *rng_blk;     // [32*4] block-start generator states of the current fill
 };
+static constexpr uint32_t TRIV_TAG = 0x80000000u;
+static constexpr uint32_t SRC_MASK = 0x0FFFFFFFu;     // cm index bits of cmap.x (the contig index sits above)
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 __host__ __device__ inline size_t slab_layout(uint32_t cap, uint32_t R, unsigned char *base, Slab *s) {
     size_t o = 0;
-    if (s) s->cand_lnprob = (double *)(base + o);
-    o += align_up((size_t)cap * 8, 128);
     if (s) s->ntc = (uint4 *)(base + o);
     o += align_up((size_t)cap * 16, 128);
-    if (s) s->cand_w = (uint32_t *)(base + o);
-    o += align_up((size_t)cap * 4, 128);
-    if (s) s->cand_src = (uint32_t *)(base + o);
-    o += align_up((size_t)cap * 4, 128);
-    if (s) s->cand_ntc = (uint32_t *)(base + o);
-    o += align_up((size_t)cap * 4, 128);
+    if (s) s->cmap = (uint2 *)(base + o);
+    o += align_up((size_t)cap * 8, 128);
+    if (s) s->triv_lp = (double *)(base + o);
+    o += align_up((size_t)R * 8, 128);
+    if (s) s->triv_w = (uint32_t *)(base + o);
+    o += align_up((size_t)R * 4, 128);
     if (s) s->read_off = (uint32_t *)(base + o);
     o += align_up(((size_t)R + 1) * 4, 128);
-    if (s) s->cand_cix = (uint8_t *)(base + o);
-    o += align_up((size_t)cap, 128);
     if (s) s->rng_buf = (uint64_t *)(base + o);
     o += (size_t)RNG_BUF * 8;
     if (s) s->rng_blk = (uint64_t *)(base + o);
@@ -398,11 +401,15 @@ struct Instance {
 // GenotypeAlignments::new: per read, gather candidates of every genotype contig above the running
 // threshold, append the unmapped option, stable-sort descending (here: a p-way merge of the already
 // sorted per-contig lists, ties resolved in insertion order = contig order, unmapped last), cut at the
-// final threshold.  Candidates of non-trivial reads (> 1 candidate) are also written to the compact
-// arrays.  Returns false on slab overflow.
-template <int GS>
+// final threshold.  Returns false on slab overflow.
+// HEADS > 0 (ploidy <= 2): the first HEADS ln-probs of each contig's run are fetched up front with
+// independent loads and the threshold / cut / merge run on registers; runs longer than HEADS fall back to
+// memory for the tail.  HEADS == 0: everything from memory (any ploidy).
+template <int GS, int HEADS>
 __device__ bool build_instance(const LocusDev &L, const Slab &S, const WarpShared &ws, uint32_t cap, Instance &I,
                                const Grp<GS> &g) {
+    constexpr int PK = HEADS > 0 ? 2 : LCTP_MAX_PLOIDY;
+    constexpr int HN = HEADS > 0 ? HEADS : 1;
     const uint32_t R = L.R, p = L.p;
     const int lane = g.lane;
     uint32_t base = 0, nt_base = 0, ntc_base = 0;
@@ -410,24 +417,48 @@ __device__ bool build_instance(const LocusDev &L, const Slab &S, const WarpShare
     for (uint32_t r0 = 0; r0 < R; r0 += GS) {
         const uint32_t r = r0 + lane;
         const bool valid = r < R;
-        uint32_t lb[LCTP_MAX_PLOIDY], le[LCTP_MAX_PLOIDY];
+        uint32_t lb[PK], le[PK], l0[PK];
+        double hv[PK][HN];
         double unm = 0.0, thresh = 0.0;
         uint32_t nw = 0;
         bool with_unm = false;
+        // value j of contig k's run (j counted from the run start l0[k])
+        auto val = [&](int k, uint32_t ix) -> double {
+            if (HEADS > 0) {
+                const uint32_t j = ix - l0[k];
+#pragma unroll
+                for (int q = 0; q < HN; q++) if (j == (uint32_t)q) return hv[k][q];
+            }
+            return L.cm_lnprob[ix];
+        };
         if (valid) {
             unm = L.unmapped[r];
             thresh = __dsub_rn(unm, L.prob_diff);
-            for (uint32_t k = 0; k < p; k++) {
-                const size_t key = (size_t)I.haps[k] * R + r;
-                lb[k] = L.cm_off[key];
-                le[k] = L.cm_off[key + 1];
-                if (le[k] > lb[k]) thresh = fmax(thresh, __dsub_rn(L.cm_lnprob[lb[k]], L.prob_diff));
+#pragma unroll
+            for (int k = 0; k < PK; k++) {
+                if ((uint32_t)k < p) {
+                    const size_t key = (size_t)I.haps[k] * R + r;
+                    lb[k] = l0[k] = L.cm_off[key];
+                    le[k] = L.cm_off[key + 1];
+                } else lb[k] = le[k] = l0[k] = 0;
             }
-            for (uint32_t k = 0; k < p; k++) {
-                uint32_t e = lb[k];
-                while (e < le[k] && L.cm_lnprob[e] >= thresh) e++;
-                le[k] = e;
-                nw += e - lb[k];
+            if (HEADS > 0) {
+#pragma unroll
+                for (int k = 0; k < PK; k++)
+#pragma unroll
+                    for (int q = 0; q < HN; q++) hv[k][q] = lb[k] + q < le[k] ? L.cm_lnprob[lb[k] + q] : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < PK; k++)
+                if ((uint32_t)k < p && le[k] > lb[k]) thresh = fmax(thresh, __dsub_rn(val(k, lb[k]), L.prob_diff));
+#pragma unroll
+            for (int k = 0; k < PK; k++) {
+                if ((uint32_t)k < p) {
+                    uint32_t e = lb[k];
+                    while (e < le[k] && val(k, e) >= thresh) e++;
+                    le[k] = e;
+                    nw += e - lb[k];
+                }
             }
             with_unm = unm >= thresh;
             nw += with_unm ? 1u : 0u;
@@ -457,29 +488,31 @@ __device__ bool build_instance(const LocusDev &L, const Slab &S, const WarpShare
             for (uint32_t t = 0; t < nw; t++) {
                 int bk = -1;
                 long long bkey = 0;
-                for (uint32_t k = 0; k < p; k++) {
-                    if (lb[k] < le[k]) {
-                        const long long key = total_key(L.cm_lnprob[lb[k]]);
-                        if (bk < 0 || key > bkey) { bk = (int)k; bkey = key; }
+                double bval = 0.0;
+#pragma unroll
+                for (int k = 0; k < PK; k++) {
+                    if ((uint32_t)k < p && lb[k] < le[k]) {
+                        const double v = val(k, lb[k]);
+                        const long long key = total_key(v);
+                        if (bk < 0 || key > bkey) { bk = k; bkey = key; bval = v; }
                     }
                 }
-                const uint32_t o = start + t;
                 double lp;
+                uint32_t src;
                 if (bk >= 0 && !(unm_left && unm_key > bkey)) {
-                    lp = L.cm_lnprob[lb[bk]];
-                    S.cand_src[o] = lb[bk];
-                    S.cand_cix[o] = (uint8_t)bk;
-                    lb[bk]++;
+                    lp = bval;
+                    uint32_t ix = 0;
+#pragma unroll
+                    for (int k = 0; k < PK; k++) if (k == bk) { ix = lb[k]; lb[k]++; }
+                    src = ix | ((uint32_t)bk << 28);
                 } else {
                     lp = unm;
-                    S.cand_src[o] = LCTP_NONE_U32;
-                    S.cand_cix[o] = 255;
+                    src = LCTP_NONE_U32;
                     unm_left = false;
                 }
-                S.cand_lnprob[o] = lp;
-                S.cand_w[o] = 0;   // [UNMAPPED_WINDOW; 2] until apply_tweak
-                if (nt) { S.cand_ntc[o] = cstart + t; S.ntc[cstart + t] = make_rec(lp, 0u); }
-                else S.cand_ntc[o] = LCTP_NONE_U32;
+                // windows stay [UNMAPPED_WINDOW; 2] = 0 until apply_tweak
+                if (nt) { S.cmap[start + t] = make_uint2(src, cstart + t); S.ntc[cstart + t] = make_rec(lp, 0u); }
+                else { S.cmap[start + t] = make_uint2(src, TRIV_TAG | r); S.triv_lp[r] = lp; S.triv_w[r] = 0u; }
             }
         }
         base += total;
@@ -513,8 +546,8 @@ __device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I,
     // (i) read middles: one next_u64 per candidate that has a parent, in candidate order
     for (uint32_t c0 = 0; c0 < I.A; c0 += GS) {
         const uint32_t c = c0 + lane;
-        const uint32_t src = c < I.A ? S.cand_src[c] : LCTP_NONE_U32;
-        const bool has_parent = src != LCTP_NONE_U32;
+        const uint2 cm = c < I.A ? S.cmap[c] : make_uint2(LCTP_NONE_U32, 0u);
+        const bool has_parent = cm.x != LCTP_NONE_U32;
         uint64_t mine = 0;
         if (tweak != 0) {
             const unsigned m = g.ballot(has_parent);
@@ -531,17 +564,16 @@ __device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I,
             }
         }
         if (has_parent) {
-            const uint32_t k = S.cand_cix[c];
+            const uint32_t k = cm.x >> 28;
             const uint32_t hap = I.haps[k], shift = I.wshift[k];
-            const uint2 mid = L.cm_mid[src];
+            const uint2 mid = L.cm_mid[cm.x & SRC_MASK];
             const uint32_t t1 = tweak ? (uint32_t)(mine >> 32) % span : 0u;
             const uint32_t t2 = tweak ? (uint32_t)mine % span : 0u;
             const uint32_t w1 = mid.x == LCTP_NONE_U32 ? 0u : shifted_window(L, hap, shift, mid.x + t1);
             const uint32_t w2 = mid.y == LCTP_NONE_U32 ? 0u : shifted_window(L, hap, shift, mid.y + t2);
             const uint32_t w = w1 | (w2 << 16);
-            S.cand_w[c] = w;
-            const uint32_t cc = S.cand_ntc[c];
-            if (cc != LCTP_NONE_U32) S.ntc[cc].z = w;
+            if (cm.y & TRIV_TAG) S.triv_w[cm.y & ~TRIV_TAG] = w;
+            else S.ntc[cm.y].z = w;
         }
     }
     // (ii) window distributions: one bounded i32 draw per window, contigs in genotype order
@@ -631,11 +663,16 @@ __device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance
         const unsigned ntmask = g.ballot(nt);
         double term = 0.0;
         if (valid) {
-            uint32_t a = 0;
-            if (nt) a = ws.nt_assgn[nt_base + __popc(ntmask & g.lt())];
-            const uint32_t ix = start + a;
-            term = S.cand_lnprob[ix];
-            const uint32_t w12 = S.cand_w[ix];
+            uint32_t w12;
+            if (nt) {
+                const uint32_t pos = nt_base + __popc(ntmask & g.lt());
+                const uint4 rec = S.ntc[(uint32_t)ws.ntc_start[pos] + ws.nt_assgn[pos]];
+                term = rec_lp(rec);
+                w12 = rec.z;
+            } else {
+                term = S.triv_lp[r];
+                w12 = S.triv_w[r];
+            }
             atomicAdd(&ws.win.depth(w12 & 0xFFFFu), 1u);
             atomicAdd(&ws.win.depth(w12 >> 16), 1u);
         }
@@ -1027,7 +1064,8 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
                 I.wshift[k + 1] = wsft;
             }
             I.W = wsft;
-            const bool ok = build_instance(L, S, ws, P.cap, I, g);
+            const bool ok = L.p <= 2 ? build_instance<GS, LCTP_HEADS>(L, S, ws, P.cap, I, g)
+                                     : build_instance<GS, 0>(L, S, ws, P.cap, I, g);
             if (!ok) {
                 if (lane == 0) { atomicOr(err, 1); lik_mean[j] = NAN; lik_var[j] = NAN; n_alns[j] = I.A; iters[j] = 0; }
                 continue;
@@ -1231,6 +1269,11 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     if (st->kind == 1 && (!(st->init_prob > 0.0 && st->init_prob <= 1.0) || st->anneal_steps == 0)) {
         set_error("lctp_solve_stage: invalid annealing parameters");
         return LCTP_E_INVALID;
+    }
+    if (h->npa > (uint64_t)SRC_MASK) {
+        set_error("lctp_solve_stage: %llu pair alignments exceed the 2^28 the candidate map can address",
+                  (unsigned long long)h->npa);
+        return LCTP_E_CAPACITY;
     }
     const size_t n = (size_t)worker_off[n_workers];
     if (n == 0 || n_workers > 0xFFFFFFF0ull) { set_error("lctp_solve_stage: empty stage"); return LCTP_E_INVALID; }
