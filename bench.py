@@ -217,7 +217,8 @@ def workload_config(args, T, world):
     from locityper_b200 import synth
     sh = synth.config_shape(args.config)
     G = sh["n_haps"] * (sh["n_haps"] + 1) // 2
-    return {"workload": f"BASELINE configs[1]: {args.loci} loci/step/GPU x H={sh['n_haps']} haplotypes "
+    cfg_ix = {"C1": 0, "C2": 1, "C3": 2, "C4": 3, "C5": 4}.get(args.config, 1)
+    return {"workload": f"BASELINE configs[{cfg_ix}]: {args.loci if args.mode == 'loci' else 1} loci/step/GPU x H={sh['n_haps']} haplotypes "
                         f"(G={G} diploid genotypes), R={sh['n_reads']} read pairs, {sh['locus_len']} bp, "
                         f"{sh['tech']}; scheme {' '.join('-S ' + s for s in args.scheme)}",
             "shape": args.config, "loci_per_step_per_gpu": args.loci, "threads_T": T, "mode": args.mode,
