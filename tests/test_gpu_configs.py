@@ -1,0 +1,48 @@
+"""GPU parity at the FULL sizes of every BASELINE.json config (C1..C5), not only through properties.
+
+Each case runs the whole hot path (prefilter -> truncate -> greedy stage -> pruning -> annealing stage -> result) with
+the reference's default scheme `greedy:i=5k,a=1` + `anneal:i=20,a=20` (src/solvers/solve.rs:211) through the C ABI and
+compares it with the CPU oracle on the same seeded synthetic locus: identical survivor counts, identical genotype
+ranking and final call, identical locus RNG stream position, ln-likelihoods / probabilities within 1e-6 relative.
+T (`-@`) is kept small so the oracle's annealing stage (max(20, T) genotypes x 20 attempts) finishes in seconds;
+C4 (KIR scale: 500,500 genotypes x 10,000 reads) is the slow one (~1 min of oracle time on 8 cores).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from locityper_b200 import genotype, synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6
+
+CASES = [
+    # config, seed, T
+    ("C1", 1001, 8),      # the reference's own default -@ 8
+    ("C2", 2001, 64),
+    ("C3", 3001, 64),
+    ("C4", 4001, 64),
+    ("C5", 5000, 64),
+]
+
+
+@pytest.mark.parametrize("cfg,seed,threads", CASES, ids=[c[0] for c in CASES])
+def test_full_config_parity(oracle, gpu_ctx, cfg, seed, threads):
+    loc = synth.make_locus(**synth.config_shape(cfg), seed=seed, table_builder=oracle.build_depth_table)
+    scheme_o = [oracle.Stage("greedy", attempts=1, in_size=5000), oracle.Stage("anneal", attempts=20, in_size=20)]
+    scheme_g = genotype.Scheme.parse(["greedy:i=5k,a=1", "anneal:i=20,a=20"])
+    rng_o = oracle.Rng.from_seed(seed)
+    ref = oracle.solve(oracle.OracleLocus(loc), scheme_o, threads, rng_o, os_threads=os.cpu_count() or 4)
+    dl = gpu_ctx.upload(loc)
+    rng_g = genotype.init_rng(seed)
+    got = dl.solve(scheme_g, threads, rng_g)
+    dl.free()
+    assert got.n_filtered == ref["n_filtered"] and list(got.n_stage_in) == list(ref["n_stage_in"])
+    assert np.array_equal(got.gt_ix, ref["gt_ix"]), "ranking / final call differs from the oracle"
+    np.testing.assert_allclose(got.lik_mean, ref["lik_mean"], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(got.lik_var, ref["lik_var"], rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(got.ln_prob, ref["ln_prob"], rtol=RTOL, atol=1e-9)
+    assert got.unexpl_reads == ref["unexpl_reads"]
+    assert abs(got.quality - ref["quality"]) <= RTOL * max(1.0, abs(ref["quality"]))
+    assert list(rng_g) == rng_o.state(), "locus RNG stream diverged"
