@@ -173,6 +173,16 @@ int  lctp_get_stats(lctp_ctx *ctx, lctp_stats *out, int reset);
  * per second, from a DADD microbenchmark run on the context's stream.  The prefilter (a2) issues two FP64-pipe
  * instructions per genotype-read, so rate / 2 is the denominator of its roofline. */
 int  lctp_measure_fp64_rate(lctp_ctx *ctx, double *lane_inst_per_s);
+/* Diagnostic (no reference counterpart, host only, no device needed): builds the work plan of the balanced
+ * prefilter kernel for a diploid full-triangle locus of `n_haps` haplotypes on `n_sm` SMs and checks that every
+ * genotype id of [g_begin, g_end) (the enumeration of src/ext/vec.rs:298-339) is owned by exactly one register
+ * of one lane and that its staged matrix columns are the genotype's two haplotypes.  `pattern` = columns per
+ * lane of the q-th warp of every SM sub-partition (n_pattern entries, each 2..8), or NULL / 0 to let the
+ * planner choose; the chosen pattern (<= 4 entries), the number of CTA regions and the per-sub-partition load
+ * (sum of the pattern) are returned when the pointers are non-NULL. */
+int  lctp_prefilter_plan_check(uint32_t n_haps, uint32_t n_sm, const uint32_t *pattern, uint32_t n_pattern,
+                               uint64_t g_begin, uint64_t g_end, uint32_t *n_regions, uint32_t *load,
+                               uint32_t *pattern_out);
 
 /* ---- locus upload (H2D once per locus; builds M = best_aln_matrix on the device, a1) ------- */
 int  lctp_locus_upload(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h **out);

@@ -76,6 +76,20 @@ struct PinBuf {
     PinBuf &operator=(const PinBuf &) = delete;
 };
 
+// Work plan of the balanced prefilter kernel (prefilter.cu): one region per persistent CTA and round.
+static constexpr int BAL_MAXW = 16;            // warps per CTA
+struct BalWarp { uint32_t row0, col0, ncols, c, a_off, b_off; };       // c == 0: idle slot
+struct BalRegion {
+    uint32_t row_chunks;                       // 16-byte chunks staged per read
+    uint32_t tab_off;                          // first entry of this region in the source-column table
+    BalWarp warp[BAL_MAXW];
+};
+struct BalPlan {
+    std::vector<BalRegion> regions;
+    std::vector<uint32_t> tab, pattern;
+    uint32_t row_len = 0, n_warps = 0, cmax = 0, load = 0;
+};
+
 }  // namespace lctp
 
 struct lctp_ctx {
@@ -137,6 +151,11 @@ struct lctp_locus_h {
     lctp::DevBuf<uint64_t> hap_pos_off;
     lctp::DevBuf<uint8_t> pos_gc;
     bool scores_valid = false;
+    lctp::BalPlan pf_plan;               // balanced prefilter plan of the last (range, pattern), see prefilter.cu
+    lctp::DevBuf<lctp::BalRegion> pf_regions;
+    lctp::DevBuf<uint32_t> pf_tab;
+    bool pf_plan_valid = false, pf_plan_auto = false;
+    uint64_t pf_g_begin = 0, pf_g_end = 0;
     bool mt_nonpositive = false;         // every matrix entry <= +0.0 (integer-pipe max is valid)
 };
 
@@ -146,6 +165,8 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h);
 // prefilter.cu
 int launch_prefilter(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, double *d_scores);
 int measure_fp64_rate(lctp_ctx *ctx, double *lane_inst_per_s);
+int prefilter_plan_check(uint32_t H, uint32_t n_sm, const uint32_t *pattern, uint32_t n_pattern, uint64_t g_begin,
+                         uint64_t g_end, uint32_t *n_regions, uint32_t *load, uint32_t *pattern_out);
 // pairs.cu
 int pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig,
                     double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob,

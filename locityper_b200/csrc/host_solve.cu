@@ -432,6 +432,17 @@ int lctp_measure_fp64_rate(lctp_ctx *ctx, double *lane_inst_per_s) {
     return measure_fp64_rate(ctx, lane_inst_per_s);
 }
 
+int lctp_prefilter_plan_check(uint32_t n_haps, uint32_t n_sm, const uint32_t *pattern, uint32_t n_pattern,
+                              uint64_t g_begin, uint64_t g_end, uint32_t *n_regions, uint32_t *load,
+                              uint32_t *pattern_out) {
+    const uint64_t G = (uint64_t)n_haps * (n_haps + 1) / 2;
+    if (n_haps == 0 || n_sm == 0 || g_begin >= g_end || g_end > G) {
+        set_error("lctp_prefilter_plan_check: invalid arguments");
+        return LCTP_E_INVALID;
+    }
+    return prefilter_plan_check(n_haps, n_sm, pattern, n_pattern, g_begin, g_end, n_regions, load, pattern_out);
+}
+
 int lctp_locus_upload(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h **out) {
     if (!ctx || !in || !out) { set_error("lctp_locus_upload: NULL argument"); return LCTP_E_INVALID; }
     *out = nullptr;

@@ -15,6 +15,9 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <vector>
 
 namespace lctp {
 
@@ -193,6 +196,414 @@ k_prefilter_pairs(const double *__restrict__ Mt, uint32_t R, uint32_t H, uint32_
     }
 }
 
+// ---- balanced persistent variant (large panels) ----------------------------------------------------
+//
+// The tiled kernel above leaves the FP64 pipe idle for structural reasons at the KIR-scale shape: the R loop
+// of a genotype cannot be split (sequential f64 sum), so the only parallelism is the genotype count, and with
+// 4x4 register tiles H = 1,000 gives 977 warp-tiles for 592 SM sub-partitions -- some sub-partitions run two
+// warps, some one, and the kernel lasts as long as the fullest.  This variant plans the work on the host so
+// that EVERY sub-partition gets the same load:
+//   * the triangle is cut into strips of 32 haplotype rows; strip k needs the columns [32k, H);
+//   * the strips' column ranges are concatenated and dealt out, in order, to warp slots; slot w of a CTA owns
+//     4*c_w consecutive columns (c_w = columns per lane, 2..8), so a lane holds a 4 x c_w register tile;
+//   * the per-warp widths repeat with period 4 (the warp -> sub-partition mapping), and the pattern is chosen
+//     so that #CTAs <= #SMs (one persistent CTA per SM) with the smallest per-sub-partition sum of c_w:
+//     H = 1,000 -> 8 warps with c = (4,4,4,4,3,3,3,3): 7 columns x 4 rows per sub-partition lane against an
+//     ideal of 6.6, instead of 8 for the fullest SMs of the tiled kernel.
+// A CTA stages, per read, the 32 row values of every strip it touches plus its column range (one contiguous
+// smem row per read, 3-stage cp.async pipeline, one barrier per chunk).  Sums stay strictly in read order.
+static constexpr int BAL_RC = 32;              // reads per pipeline stage
+static constexpr int BAL_TAB = 256;            // max 16-byte chunks per staged read row (one staging pass of <= 256 threads)
+
+
+// column (within the warp's 4*C-column group) of register column b of lane tx: pairs are interleaved across
+// the four tx lanes (16-byte, bank-conflict-free loads); an odd last column follows the pairs.
+template <int C>
+__device__ __host__ __forceinline__ int bal_col(int tx, int b) {
+    constexpr int NP = C / 2;
+    return b < 2 * NP ? (b / 2) * 8 + 2 * tx + (b & 1) : NP * 8 + tx;
+}
+
+// One warp's share of a region: a 4 x C register tile per lane over all R reads.  The operands of read r+1 are
+// loaded while read r is being accumulated (the row after a stage's last read is still inside the allocation).
+template <int C>
+__device__ __forceinline__ void bal_load(const double *__restrict__ pa, const double *__restrict__ pb, int odd,
+                                         double (&a)[4], double (&b)[C]) {
+    const double2 v0 = *reinterpret_cast<const double2 *>(pa);
+    const double2 v1 = *reinterpret_cast<const double2 *>(pa + 2);
+    a[0] = v0.x; a[1] = v0.y; a[2] = v1.x; a[3] = v1.y;
+#pragma unroll
+    for (int q = 0; q < C / 2; q++) {
+        const double2 v = *reinterpret_cast<const double2 *>(pb + q * 8);
+        b[2 * q] = v.x; b[2 * q + 1] = v.y;
+    }
+    if constexpr (C & 1) b[C - 1] = pb[odd];
+}
+
+template <int C>
+__device__ __forceinline__ void bal_store(const BalWarp &w, int ty, int tx, uint32_t H, const double (&acc)[4][C],
+                                          const double *__restrict__ priors, double *__restrict__ scores,
+                                          uint64_t g_begin, uint64_t g_end) {
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+        const uint32_t i = w.row0 + 4 * ty + x;
+#pragma unroll
+        for (int y = 0; y < C; y++) {
+            const uint32_t cc = bal_col<C>(tx, y);
+            const uint32_t j = w.col0 + cc;
+            if (cc < w.ncols && i <= j && j < H) {
+                const uint64_t g = pair_gid(i, j, H);
+                if (g >= g_begin && g < g_end) scores[g] = __dadd_rn(priors ? priors[g] : 0.0, acc[x][y]);
+            }
+        }
+    }
+}
+
+struct BalStage {                     // per-thread constants of the staging loop of one region
+    const double *src;                // Mt + first row of this thread * Hpad + its source column
+    uint32_t dst;                     // smem offset (doubles) of its 16-byte chunk in its first row
+    uint32_t rc0, rc_step;            // first row and row stride of this thread inside a chunk
+    bool active;
+};
+
+template <int NS>
+__device__ __forceinline__ void bal_issue(const BalStage &sg, const double *__restrict__ Mt, double *smem, int c,
+                                          int n_chunks, int stage, uint32_t R, uint32_t Hpad, uint32_t row_len,
+                                          size_t stage_len) {
+    if (c < n_chunks && sg.active) {
+        const uint32_t r0 = c * BAL_RC;
+        const uint32_t nr = min((uint32_t)BAL_RC, R - r0);
+        const double *src = sg.src + (size_t)r0 * Hpad;
+        double *dst = smem + (size_t)stage * stage_len + sg.dst;
+        const size_t src_step = (size_t)sg.rc_step * Hpad, dst_step = (size_t)sg.rc_step * row_len;
+        for (uint32_t rc = sg.rc0; rc < nr; rc += sg.rc_step) {
+            cp_async16(dst, src);
+            src += src_step; dst += dst_step;
+        }
+    }
+    cp_async_commit();
+}
+
+template <int C, int NS>
+__device__ __forceinline__ void bal_run(const BalWarp &w, const BalStage &sg, const double *__restrict__ Mt,
+                                        double *smem, uint32_t R, uint32_t H, uint32_t Hpad, uint32_t row_len,
+                                        const double *__restrict__ priors, double *__restrict__ scores,
+                                        uint64_t g_begin, uint64_t g_end) {
+    const int lane = threadIdx.x & 31, ty = lane >> 2, tx = lane & 3;
+    const int n_chunks = (R + BAL_RC - 1) / BAL_RC;
+    const size_t stage_len = (size_t)BAL_RC * row_len;
+    const int odd = (C / 2) * 8 - tx;                  // odd last column, relative to pb = b_off + 2 * tx
+    double acc[4][C];
+#pragma unroll
+    for (int x = 0; x < 4; x++)
+#pragma unroll
+        for (int y = 0; y < C; y++) acc[x][y] = 0.0;
+
+#pragma unroll
+    for (int c = 0; c < NS - 1; c++) bal_issue<NS>(sg, Mt, smem, c, n_chunks, c, R, Hpad, row_len, stage_len);
+    int stage = 0, fill = NS - 1;                      // stage of chunk c / of chunk c + NS - 1
+    for (int c = 0; c < n_chunks; c++) {
+        cp_async_wait<NS - 2>();
+        // Every warp of the CTA runs this loop (possibly another instantiation of it): one barrier per chunk.
+        // Chunk c has landed for everyone, and the stage of chunk c - 1 is free to be refilled.
+        __syncthreads();
+        bal_issue<NS>(sg, Mt, smem, c + NS - 1, n_chunks, fill, R, Hpad, row_len, stage_len);
+        const double *pa = smem + (size_t)stage * stage_len + w.a_off + 4 * ty;
+        const double *pb = smem + (size_t)stage * stage_len + w.b_off + 2 * tx;
+        const int nr = min((int)BAL_RC, (int)(R - c * BAL_RC));
+        double a[4], b[C];
+        bal_load<C>(pa, pb, odd, a, b);
+#pragma unroll 2
+        for (int rc = 0; rc < nr; rc++) {
+            pa += row_len; pb += row_len;
+            double an[4], bn[C];
+            bal_load<C>(pa, pb, odd, an, bn);
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < C; y++) acc[x][y] = __dadd_rn(acc[x][y], dmax(a[x], b[y]));
+#pragma unroll
+            for (int x = 0; x < 4; x++) a[x] = an[x];
+#pragma unroll
+            for (int y = 0; y < C; y++) b[y] = bn[y];
+        }
+        stage = stage + 1 == NS ? 0 : stage + 1;
+        fill = fill + 1 == NS ? 0 : fill + 1;
+    }
+    cp_async_wait<0>();
+    bal_store<C>(w, ty, tx, H, acc, priors, scores, g_begin, g_end);
+}
+
+// Idle warp slot of a partly filled region: stages and synchronises like the others, computes nothing.
+template <int NS>
+__device__ __forceinline__ void bal_idle(const BalStage &sg, const double *__restrict__ Mt, double *smem, uint32_t R,
+                                         uint32_t Hpad, uint32_t row_len) {
+    const int n_chunks = (R + BAL_RC - 1) / BAL_RC;
+    const size_t stage_len = (size_t)BAL_RC * row_len;
+#pragma unroll
+    for (int c = 0; c < NS - 1; c++) bal_issue<NS>(sg, Mt, smem, c, n_chunks, c, R, Hpad, row_len, stage_len);
+    int fill = NS - 1;
+    for (int c = 0; c < n_chunks; c++) {
+        cp_async_wait<NS - 2>();
+        __syncthreads();
+        bal_issue<NS>(sg, Mt, smem, c + NS - 1, n_chunks, fill, R, Hpad, row_len, stage_len);
+        fill = fill + 1 == NS ? 0 : fill + 1;
+    }
+    cp_async_wait<0>();
+}
+
+template <int NT, int CMAX, int NS>
+__global__ void __launch_bounds__(NT, 1)
+k_prefilter_bal(const double *__restrict__ Mt, uint32_t R, uint32_t H, uint32_t Hpad,
+                const double *__restrict__ priors, double *__restrict__ scores,
+                const BalRegion *__restrict__ regions, const uint32_t *__restrict__ src_tab_g, uint32_t n_regions,
+                uint32_t row_len, uint64_t g_begin, uint64_t g_end) {
+    extern __shared__ __align__(128) double bal_smem[];          // [NS][BAL_RC][row_len] + one padding row
+    const int tid = threadIdx.x, wid = tid >> 5;
+
+    for (uint32_t reg = blockIdx.x; reg < n_regions; reg += gridDim.x) {
+        const BalRegion *rg = regions + reg;
+        const uint32_t row_chunks = rg->row_chunks;
+        const BalWarp w = rg->warp[wid];
+        // staging: QW = smallest power of two >= row_chunks threads cover one read row, NT / QW rows per pass
+        uint32_t qw = 32;
+        while (qw < row_chunks) qw <<= 1;
+        BalStage sg;
+        {
+            const uint32_t q = tid & (qw - 1), rc0 = tid / qw;
+            sg.active = q < row_chunks && rc0 < (uint32_t)NT / qw;     // launcher guarantees qw <= NT
+            sg.rc0 = rc0; sg.rc_step = NT / qw;
+            sg.dst = rc0 * row_len + 2 * q;
+            sg.src = Mt + (size_t)rc0 * Hpad + (sg.active ? src_tab_g[rg->tab_off + q] : 0u);
+        }
+        switch (w.c) {
+        case 2: bal_run<2, NS>(w, sg, Mt, bal_smem, R, H, Hpad, row_len, priors, scores, g_begin, g_end); break;
+        case 3: bal_run<3, NS>(w, sg, Mt, bal_smem, R, H, Hpad, row_len, priors, scores, g_begin, g_end); break;
+        case 4: bal_run<4, NS>(w, sg, Mt, bal_smem, R, H, Hpad, row_len, priors, scores, g_begin, g_end); break;
+        case 5: if constexpr (CMAX >= 5) { bal_run<5, NS>(w, sg, Mt, bal_smem, R, H, Hpad, row_len, priors, scores, g_begin, g_end); break; }
+        case 6: if constexpr (CMAX >= 6) { bal_run<6, NS>(w, sg, Mt, bal_smem, R, H, Hpad, row_len, priors, scores, g_begin, g_end); break; }
+        case 7: if constexpr (CMAX >= 7) { bal_run<7, NS>(w, sg, Mt, bal_smem, R, H, Hpad, row_len, priors, scores, g_begin, g_end); break; }
+        case 8: if constexpr (CMAX >= 8) { bal_run<8, NS>(w, sg, Mt, bal_smem, R, H, Hpad, row_len, priors, scores, g_begin, g_end); break; }
+        default: bal_idle<NS>(sg, Mt, bal_smem, R, Hpad, row_len); break;
+        }
+        __syncthreads();                           // the stages are reused by the next region
+    }
+}
+
+// Host planner.  `pattern[q]` = columns per lane of the q-th warp of every sub-partition (warp w uses
+// pattern[w / 4]), so the CTA has 4 * n_pattern warps.  Returns the regions in order; region r is processed by
+// CTA r % gridDim.
+
+static void row_of_gid(uint64_t g, uint32_t H, uint32_t *row) {          // largest i with pair_gid(i, i, H) <= g
+    uint32_t lo = 0, hi = H - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) / 2;
+        if (pair_gid(mid, mid, H) <= g) lo = mid; else hi = mid - 1;
+    }
+    *row = lo;
+}
+
+static bool bal_plan(uint32_t H, uint64_t g_begin, uint64_t g_end, const uint32_t *pattern, uint32_t n_pattern,
+                     BalPlan &out) {
+    const uint32_t NW = 4 * n_pattern;
+    if (n_pattern == 0 || NW > (uint32_t)BAL_MAXW || H == 0 || g_begin >= g_end) return false;
+    out.regions.clear(); out.tab.clear();
+    out.n_warps = NW; out.cmax = 0; out.load = 0; out.row_len = 0;
+    out.pattern.assign(pattern, pattern + n_pattern);
+    for (uint32_t q = 0; q < n_pattern; q++) {
+        if (pattern[q] < 2 || pattern[q] > 8) return false;
+        out.cmax = std::max(out.cmax, pattern[q]);
+        out.load += pattern[q];
+    }
+    uint32_t i_lo, i_hi;
+    row_of_gid(g_begin, H, &i_lo);
+    row_of_gid(g_end - 1, H, &i_hi);
+    const uint32_t Hc = (H + 3u) & ~3u;
+    uint32_t k = i_lo / 32, k_end = i_hi / 32, col = 32 * k;
+    while (k <= k_end) {
+        BalRegion rg;
+        std::memset(&rg, 0, sizeof rg);
+        rg.tab_off = (uint32_t)out.tab.size();
+        uint32_t off = 0;                 // smem row offset in doubles
+        uint32_t cur_strip = UINT32_MAX, a_off = 0, b_seg_off = 0, b_seg_col0 = 0;
+        for (uint32_t w = 0; w < NW && k <= k_end; w++) {
+            const uint32_t c = pattern[w / 4];
+            const uint32_t take = std::min(4 * c, Hc - col);
+            if (k != cur_strip) {         // new strip in this region: stage its 32 row values, start a column segment
+                cur_strip = k;
+                a_off = off;
+                for (uint32_t q = 0; q < 16; q++) out.tab.push_back(32 * k + 2 * q);
+                off += 32;
+                b_seg_off = off; b_seg_col0 = col;
+            }
+            BalWarp &bw = rg.warp[w];
+            bw.row0 = 32 * k; bw.col0 = col; bw.ncols = take; bw.c = c; bw.a_off = a_off;
+            bw.b_off = b_seg_off + (col - b_seg_col0);
+            for (uint32_t q = 0; q < take / 2; q++) out.tab.push_back(col + 2 * q);
+            off += take;
+            col += take;
+            if (col >= Hc) { k++; col = 32 * k; }
+        }
+        rg.row_chunks = off / 2;
+        out.row_len = std::max(out.row_len, off);
+        out.regions.push_back(rg);
+    }
+    out.row_len += 4 * 8 + 8;             // lanes past a warp's last valid column still read (and discard) smem
+    out.row_len = (out.row_len + 1u) & ~1u;
+    for (const BalRegion &rg : out.regions)
+        if (rg.row_chunks > (uint32_t)BAL_TAB) return false;
+    return true;
+}
+
+// Chooses the per-sub-partition pattern with the smallest (rounds x load); ties -> fewer warps (wider tiles).
+static bool bal_choose(uint32_t H, uint64_t g_begin, uint64_t g_end, uint32_t n_sm, BalPlan &best) {
+    uint64_t best_cost = UINT64_MAX;
+    BalPlan cur;
+    for (uint32_t np = 1; np <= 3; np++) {
+        uint32_t pat[3];
+        const uint32_t combos = np == 1 ? 3 : np == 2 ? 9 : 27;
+        for (uint32_t m = 0; m < combos; m++) {
+            uint32_t x = m;
+            bool sorted = true;
+            for (uint32_t q = 0; q < np; q++) { pat[q] = 4 - x % 3; x /= 3; if (q && pat[q] > pat[q - 1]) sorted = false; }
+            if (!sorted) continue;        // widest tiles first: they take the long strips
+            if (!bal_plan(H, g_begin, g_end, pat, np, cur)) continue;
+            const uint64_t rounds = (cur.regions.size() + n_sm - 1) / n_sm;
+            const uint64_t cost = rounds * cur.load * 64 + np;
+            if (cost < best_cost) { best_cost = cost; std::swap(best, cur); }
+        }
+    }
+    return best_cost != UINT64_MAX;
+}
+
+static bool parse_pattern(const char *e, uint32_t *pat, uint32_t *np) {
+    *np = 0;
+    while (*e && *np < 4) {
+        char *end = nullptr;
+        const long v = strtol(e, &end, 10);
+        if (end == e) return false;
+        pat[(*np)++] = (uint32_t)v;
+        e = *end == ',' ? end + 1 : end;
+    }
+    return *np > 0 && *e == 0;
+}
+
+template <int NT, int CMAX, int NS>
+static int bal_launch2(lctp_locus_h *h, const BalPlan &plan, const BalRegion *d_regions, const uint32_t *d_tab,
+                       uint64_t g_begin, uint64_t g_end, double *d_scores, size_t smem) {
+    lctp_ctx *ctx = h->ctx;
+    const LocusDev &d = h->dev;
+    LCTP_CUDA_CHECK(cudaFuncSetAttribute(k_prefilter_bal<NT, CMAX, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::min<size_t>(plan.regions.size(), (size_t)ctx->sm_count);
+    k_prefilter_bal<NT, CMAX, NS><<<grid, NT, smem, ctx->stream>>>(d.Mt, d.R, d.H, d.Hpad, d.priors, d_scores, d_regions, d_tab,
+                                                                (uint32_t)plan.regions.size(), plan.row_len, g_begin, g_end);
+    return LCTP_OK;
+}
+
+template <int NT, int CMAX>
+static int bal_launch(lctp_locus_h *h, const BalPlan &plan, const BalRegion *d_regions, const uint32_t *d_tab,
+                      uint64_t g_begin, uint64_t g_end, double *d_scores) {
+    // three stages when they fit (plus the padding row the operand prefetch of the last read touches), else two
+    auto bytes = [&](int ns) { return ((size_t)ns * BAL_RC + 1) * plan.row_len * sizeof(double); };
+    int ns = 3;
+    if (const char *e = getenv("LCTP_PREFILTER_BAL_STAGES")) ns = atoi(e) == 2 ? 2 : 3;
+    if (bytes(ns) > h->ctx->smem_optin) ns = 2;
+    if (bytes(ns) > h->ctx->smem_optin) { set_error("lctp_prefilter: balanced plan needs %zu bytes of shared memory", bytes(ns)); return LCTP_E_CAPACITY; }
+    for (const BalRegion &rg : plan.regions) {
+        uint32_t qw = 32;
+        while (qw < rg.row_chunks) qw <<= 1;
+        if (qw > (uint32_t)NT) { set_error("lctp_prefilter: balanced plan stages %u chunks per read with %d threads", rg.row_chunks, NT); return LCTP_E_CAPACITY; }
+    }
+    return ns == 3 ? bal_launch2<NT, CMAX, 3>(h, plan, d_regions, d_tab, g_begin, g_end, d_scores, bytes(3))
+                   : bal_launch2<NT, CMAX, 2>(h, plan, d_regions, d_tab, g_begin, g_end, d_scores, bytes(2));
+}
+
+// pattern == nullptr: choose automatically.
+static int launch_prefilter_bal(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, double *d_scores,
+                                const uint32_t *pattern, uint32_t n_pattern) {
+    lctp_ctx *ctx = h->ctx;
+    BalPlan &plan = h->pf_plan;
+    std::vector<uint32_t> want(pattern, pattern + (pattern ? n_pattern : 0));
+    const bool cached = h->pf_plan_valid && h->pf_g_begin == g_begin && h->pf_g_end == g_end &&
+                        (pattern ? plan.pattern == want : h->pf_plan_auto);
+    if (!cached) {                        // the plan depends only on (H, genotype range, pattern): keep it with the locus
+        h->pf_plan_valid = false;
+        const bool ok = pattern ? bal_plan(h->dev.H, g_begin, g_end, pattern, n_pattern, plan)
+                                : bal_choose(h->dev.H, g_begin, g_end, (uint32_t)ctx->sm_count, plan);
+        if (!ok) { set_error("lctp_prefilter: no balanced plan for H=%u", h->dev.H); return LCTP_E_INVALID; }
+        int rc;
+        if ((rc = h->pf_regions.ensure(plan.regions.size()))) return rc;
+        if ((rc = h->pf_tab.ensure(plan.tab.size()))) return rc;
+        // pageable sources: the copies are staged by the runtime before the calls return
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(h->pf_regions.p, plan.regions.data(), plan.regions.size() * sizeof(BalRegion),
+                                        cudaMemcpyHostToDevice, ctx->stream));
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(h->pf_tab.p, plan.tab.data(), plan.tab.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        h->pf_plan_valid = true; h->pf_plan_auto = pattern == nullptr;
+        h->pf_g_begin = g_begin; h->pf_g_end = g_end;
+    }
+    const BalRegion *dr = h->pf_regions.p;
+    const uint32_t nt = plan.n_warps * 32;
+    if (plan.cmax <= 4) {
+        switch (nt) {
+        case 128: return bal_launch<128, 4>(h, plan, dr, h->pf_tab.p, g_begin, g_end, d_scores);
+        case 256: return bal_launch<256, 4>(h, plan, dr, h->pf_tab.p, g_begin, g_end, d_scores);
+        case 384: return bal_launch<384, 4>(h, plan, dr, h->pf_tab.p, g_begin, g_end, d_scores);
+        case 512: return bal_launch<512, 4>(h, plan, dr, h->pf_tab.p, g_begin, g_end, d_scores);
+        }
+    } else {
+        switch (nt) {
+        case 128: return bal_launch<128, 8>(h, plan, dr, h->pf_tab.p, g_begin, g_end, d_scores);
+        case 256: return bal_launch<256, 8>(h, plan, dr, h->pf_tab.p, g_begin, g_end, d_scores);
+        }
+    }
+    set_error("lctp_prefilter: unsupported balanced pattern (%u warps, %u columns per lane)", plan.n_warps, plan.cmax);
+    return LCTP_E_INVALID;
+}
+
+// Host-side check of the planner (no device work): every genotype of [g_begin, g_end) is owned by exactly one
+// (region, warp, lane, register) slot.  Diagnostic entry point, see include/lctp.h.
+int prefilter_plan_check(uint32_t H, uint32_t n_sm, const uint32_t *pattern, uint32_t n_pattern, uint64_t g_begin,
+                         uint64_t g_end, uint32_t *n_regions, uint32_t *load, uint32_t *pattern_out) {
+    BalPlan plan;
+    const bool ok = (pattern && n_pattern) ? bal_plan(H, g_begin, g_end, pattern, n_pattern, plan)
+                                           : bal_choose(H, g_begin, g_end, n_sm, plan);
+    if (!ok) { set_error("lctp_prefilter_plan_check: no plan"); return LCTP_E_INVALID; }
+    std::vector<uint8_t> seen(g_end - g_begin, 0);
+    for (const BalRegion &rg : plan.regions) {
+        for (uint32_t w = 0; w < plan.n_warps; w++) {
+            const BalWarp &bw = rg.warp[w];
+            if (bw.c == 0) continue;
+            if (bw.a_off + 32 > plan.row_len || bw.b_off + 4 * bw.c + 8 > plan.row_len) {
+                set_error("lctp_prefilter_plan_check: smem offsets out of range");
+                return LCTP_E_INVALID;
+            }
+            for (int lane = 0; lane < 32; lane++) {
+                const int ty = lane >> 2, tx = lane & 3;
+                for (uint32_t x = 0; x < 4; x++)
+                    for (uint32_t y = 0; y < bw.c; y++) {
+                        const uint32_t np = bw.c / 2;
+                        const uint32_t cc = y < 2 * np ? (y / 2) * 8 + 2 * tx + (y & 1) : np * 8 + tx;
+                        const uint32_t i = bw.row0 + 4 * ty + x, j = bw.col0 + cc;
+                        if (cc >= bw.ncols || i > j || j >= H) continue;
+                        // the staged source column of this register must be the genotype's haplotype
+                        const uint32_t src_b = plan.tab[rg.tab_off + (bw.b_off + cc) / 2] + ((bw.b_off + cc) & 1u);
+                        const uint32_t src_a = plan.tab[rg.tab_off + (bw.a_off + 4 * ty + x) / 2] + ((bw.a_off + 4 * ty + x) & 1u);
+                        if (src_a != i || src_b != j) { set_error("lctp_prefilter_plan_check: staging table mismatch"); return LCTP_E_INVALID; }
+                        const uint64_t g = pair_gid(i, j, H);
+                        if (g < g_begin || g >= g_end) continue;
+                        if (seen[g - g_begin]++) { set_error("lctp_prefilter_plan_check: genotype %llu covered twice", (unsigned long long)g); return LCTP_E_INVALID; }
+                    }
+            }
+        }
+    }
+    for (uint64_t g = g_begin; g < g_end; g++)
+        if (!seen[g - g_begin]) { set_error("lctp_prefilter_plan_check: genotype %llu not covered", (unsigned long long)g); return LCTP_E_INVALID; }
+    if (n_regions) *n_regions = (uint32_t)plan.regions.size();
+    if (load) *load = plan.load;
+    if (pattern_out) for (size_t q = 0; q < plan.pattern.size(); q++) pattern_out[q] = plan.pattern[q];
+    return LCTP_OK;
+}
+
 __device__ inline uint64_t dev_choose(uint64_t n, uint64_t k) {
     if (k > n) return 0;
     uint64_t r = k < n - k ? k : n - k, acc = 1;
@@ -283,6 +694,16 @@ int launch_prefilter(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, double *
         int variant = d.H < 400 ? 0 : d.H < 768 ? 4 : 1;      // measured on B200: profiles/r01_b_prefilter.md
         if (const char *e = getenv("LCTP_PREFILTER_VARIANT")) variant = atoi(e);   // tuning knob
         if (variant >= 7 && variant <= 10 && !h->mt_nonpositive) variant = 1;
+        if (variant == 16) {              // balanced persistent kernel; LCTP_PREFILTER_BAL="4,3" fixes the pattern
+            uint32_t pat[4], np = 0;
+            const char *e = getenv("LCTP_PREFILTER_BAL");
+            if (e && *e && !parse_pattern(e, pat, &np)) { set_error("lctp_prefilter: bad LCTP_PREFILTER_BAL '%s'", e); return LCTP_E_INVALID; }
+            int rc = launch_prefilter_bal(h, g_begin, g_end, d_scores, np ? pat : nullptr, np);
+            if (rc) return rc;
+            ctx->launches++;
+            LCTP_CUDA_CHECK(cudaGetLastError());
+            return LCTP_OK;
+        }
         auto go = [&](auto kern, int TB, int NT) {
             uint32_t nb = (d.H + TB - 1) / TB;
             kern<<<nb * (nb + 1) / 2, NT, 0, ctx->stream>>>(d.Mt, d.R, d.H, d.Hpad, d.priors, d_scores, nb, g_begin, g_end);

@@ -97,6 +97,7 @@ SYMBOLS = {
     "lctp_sync": (C.c_int, [_P]),
     "lctp_get_stats": (C.c_int, [_P, _P, C.c_int]),
     "lctp_measure_fp64_rate": (C.c_int, [_P, _P]),
+    "lctp_prefilter_plan_check": (C.c_int, [C.c_uint32, C.c_uint32, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P, _P, _P]),
     "lctp_pair_alignments": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P]),
     "lctp_sizeof_mates": (C.c_size_t, []),
     "lctp_locus_upload": (C.c_int, [_P, _P, _P]),

@@ -214,6 +214,25 @@ def test_every_prefilter_kernel_variant_is_bit_exact(oracle, gpu_ctx, H, R, monk
     dl.free()
 
 
+@pytest.mark.parametrize("H,R", [(150, 97), (70, 33), (333, 50), (1000, 40)])
+def test_balanced_prefilter_kernel_is_bit_exact(oracle, gpu_ctx, H, R, monkeypatch):
+    """k_prefilter_bal (variant 16: persistent CTAs, host-planned equal load per SM sub-partition) with the planner's
+    own pattern and with explicit per-warp tile widths 2..8, several warps per CTA, R not a multiple of the chunk,
+    panels spanning several rounds / a single partly idle CTA, and shard sub-ranges."""
+    loc = _mk(oracle, H, R, 2500, 900 + H)
+    ref = oracle.prefilter_scores(oracle.OracleLocus(loc))
+    dl = gpu_ctx.upload(loc)
+    G = loc.n_genotypes
+    monkeypatch.setenv("LCTP_PREFILTER_VARIANT", "16")
+    for pattern in ("", "4,3", "4", "2", "3,2", "2,2,2", "4,3,2", "4,4,4,4", "7", "8", "5,6", "6"):
+        monkeypatch.setenv("LCTP_PREFILTER_BAL", pattern)
+        assert np.array_equal(dl.prefilter_scores(), ref), f"pattern '{pattern}'"
+        a, b = G // 4, G // 4 + G // 2
+        assert np.array_equal(dl.prefilter_scores(a, b), ref[a:b]), f"pattern '{pattern}' sub-range"
+        assert np.array_equal(dl.prefilter_scores(G - 3, G), ref[G - 3:]), f"pattern '{pattern}' tail range"
+    dl.free()
+
+
 def test_positive_matrix_entries_disable_the_integer_max(oracle, gpu_ctx, monkeypatch):
     """dmax_nonpos is only valid for entries <= +0.0: a locus with a positive ln-prob must still be exact."""
     loc = _mk(oracle, 40, 60, 2500, 77)
