@@ -79,9 +79,13 @@ struct PinBuf {
 // Work plan of the balanced prefilter kernel (prefilter.cu): one region per persistent CTA and round.
 static constexpr int BAL_MAXW = 16;            // warps per CTA
 struct BalWarp { uint32_t row0, col0, ncols, c, a_off, b_off; };       // c == 0: idle slot
+struct BalSeg { uint32_t src, dst, len; };     // one contiguous run of matrix columns -> offset in the staged read row (doubles)
 struct BalRegion {
     uint32_t row_chunks;                       // 16-byte chunks staged per read
     uint32_t tab_off;                          // first entry of this region in the source-column table
+    uint32_t n_seg;                            // the same staging as contiguous segments (bulk-copy producer)
+    uint32_t n_active;                         // warps with work
+    BalSeg seg[2 * BAL_MAXW];
     BalWarp warp[BAL_MAXW];
 };
 struct BalPlan {

@@ -390,6 +390,175 @@ k_prefilter_bal(const double *__restrict__ Mt, uint32_t R, uint32_t H, uint32_t 
     }
 }
 
+// ---- warp-specialised form of the balanced kernel (variant 17) ------------------------------------------
+// Same plan, same per-warp register tiles; the staging moves to a dedicated producer warp that issues one bulk
+// copy (cp.async.bulk, TMA engine) per read row and column segment and signals a "full" mbarrier per stage;
+// consumer warps wait on it, accumulate, and arrive on the stage's "empty" mbarrier.  No CTA-wide barrier and no
+// staging instructions in the compute warps, and a warp may run up to NS - 1 chunks ahead of a slower one.
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin(uint64_t *bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
+struct BalPipe { int stage; unsigned phase; };     // position in the ring of NS stages, continues across regions
+__device__ __forceinline__ void bal_pipe_next(BalPipe &p, int ns) {
+    if (++p.stage == ns) { p.stage = 0; p.phase ^= 1u; }
+}
+
+template <int C>
+__device__ __forceinline__ void bal_consume(const BalWarp &w, BalPipe &pipe, int ns, double *smem, uint64_t *full_bar,
+                                            uint64_t *empty_bar, uint32_t R, uint32_t H, uint32_t row_len,
+                                            const double *__restrict__ priors, double *__restrict__ scores,
+                                            uint64_t g_begin, uint64_t g_end) {
+    const int lane = threadIdx.x & 31, ty = lane >> 2, tx = lane & 3;
+    const int n_chunks = (R + BAL_RC - 1) / BAL_RC;
+    const size_t stage_len = (size_t)BAL_RC * row_len;
+    const int odd = (C / 2) * 8 - tx;
+    double acc[4][C];
+#pragma unroll
+    for (int x = 0; x < 4; x++)
+#pragma unroll
+        for (int y = 0; y < C; y++) acc[x][y] = 0.0;
+    for (int c = 0; c < n_chunks; c++) {
+        mbar_spin(&full_bar[pipe.stage], pipe.phase);
+        const double *pa = smem + (size_t)pipe.stage * stage_len + w.a_off + 4 * ty;
+        const double *pb = smem + (size_t)pipe.stage * stage_len + w.b_off + 2 * tx;
+        const int nr = min((int)BAL_RC, (int)(R - c * BAL_RC));
+        double a[4], b[C];
+        bal_load<C>(pa, pb, odd, a, b);
+#pragma unroll 2
+        for (int rc = 0; rc < nr; rc++) {
+            pa += row_len; pb += row_len;
+            double an[4], bn[C];
+            bal_load<C>(pa, pb, odd, an, bn);      // row nr of the last chunk row is never used (next stage / padding)
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < C; y++) acc[x][y] = __dadd_rn(acc[x][y], dmax(a[x], b[y]));
+#pragma unroll
+            for (int x = 0; x < 4; x++) a[x] = an[x];
+#pragma unroll
+            for (int y = 0; y < C; y++) b[y] = bn[y];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[pipe.stage]);
+        bal_pipe_next(pipe, ns);
+    }
+    bal_store<C>(w, ty, tx, H, acc, priors, scores, g_begin, g_end);
+}
+
+// BULK: one producer warp issuing cp.async.bulk per row and segment (completion by transaction bytes); otherwise
+// four producer warps (one per SM sub-partition) issuing 16-byte cp.async, each lane signalling the stage's
+// "full" barrier with cp.async.mbarrier.arrive when its copies have landed.
+template <int NW, int CMAX, bool BULK>
+__global__ void __launch_bounds__((NW + (BULK ? 1 : 4)) * 32, 1)
+k_prefilter_bal_ws(const double *__restrict__ Mt, uint32_t R, uint32_t H, uint32_t Hpad,
+                   const double *__restrict__ priors, double *__restrict__ scores,
+                   const BalRegion *__restrict__ regions, const uint32_t *__restrict__ src_tab_g, uint32_t n_regions,
+                   uint32_t row_len, int ns, uint64_t g_begin, uint64_t g_end) {
+    extern __shared__ __align__(128) double bal_smem[];          // [ns][BAL_RC][row_len] + one padding row
+    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8];
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < ns; s++) { mbar_init(&full_bar[s], BULK ? 1 : 4 * 32); mbar_init(&empty_bar[s], NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int n_chunks = (R + BAL_RC - 1) / BAL_RC;
+    const size_t stage_len = (size_t)BAL_RC * row_len;
+    BalPipe pipe{0, 0u};
+
+    if (!BULK && wid >= NW) {
+        // producer warp p of 4: read rows p, p + 4, ... of every chunk; lane l copies the 16-byte chunks l, l + 32, ...
+        const int p = wid - NW;
+        pipe.phase = 1u;
+        for (uint32_t reg = blockIdx.x; reg < n_regions; reg += gridDim.x) {
+            const BalRegion *rg = regions + reg;
+            const uint32_t row_chunks = rg->row_chunks;
+            uint32_t srcc[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) srcc[j] = (uint32_t)(lane + 32 * j) < row_chunks ? src_tab_g[rg->tab_off + lane + 32 * j] : 0u;
+            for (int c = 0; c < n_chunks; c++) {
+                const uint32_t r0 = c * BAL_RC;
+                const uint32_t nr = min((uint32_t)BAL_RC, R - r0);
+                if (lane == 0) mbar_spin(&empty_bar[pipe.stage], pipe.phase);
+                __syncwarp();
+                double *dst = bal_smem + (size_t)pipe.stage * stage_len + (size_t)p * row_len + 2 * lane;
+                const double *src = Mt + (size_t)(r0 + p) * Hpad;
+                for (uint32_t rc = p; rc < nr; rc += 4) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if ((uint32_t)(lane + 32 * j) < row_chunks) cp_async16(dst + 64 * j, src + srcc[j]);
+                    dst += 4 * (size_t)row_len; src += 4 * (size_t)Hpad;
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&full_bar[pipe.stage])) : "memory");
+                bal_pipe_next(pipe, ns);
+            }
+        }
+        return;
+    }
+    if (BULK && wid == NW) {
+        // producer: lane l copies read row l of every chunk
+        pipe.phase = 1u;                           // a fresh "empty" barrier counts as already released
+        for (uint32_t reg = blockIdx.x; reg < n_regions; reg += gridDim.x) {
+            const BalRegion *rg = regions + reg;
+            const uint32_t n_seg = rg->n_seg;
+            uint32_t row_doubles = 0;
+            for (uint32_t k = 0; k < n_seg; k++) row_doubles += rg->seg[k].len;
+            for (int c = 0; c < n_chunks; c++) {
+                const uint32_t r0 = c * BAL_RC;
+                const uint32_t nr = min((uint32_t)BAL_RC, R - r0);
+                if (lane == 0) {
+                    mbar_spin(&empty_bar[pipe.stage], pipe.phase);
+                    mbar_expect_tx(&full_bar[pipe.stage], nr * row_doubles * 8u);
+                }
+                __syncwarp();
+                if ((uint32_t)lane < nr) {
+                    const double *src = Mt + (size_t)(r0 + lane) * Hpad;
+                    double *dst = bal_smem + (size_t)pipe.stage * stage_len + (size_t)lane * row_len;
+                    for (uint32_t k = 0; k < n_seg; k++) {
+                        const BalSeg sgm = rg->seg[k];
+                        bulk_g2s(dst + sgm.dst, src + sgm.src, sgm.len * 8u, &full_bar[pipe.stage]);
+                    }
+                }
+                bal_pipe_next(pipe, ns);
+            }
+        }
+        return;
+    }
+    for (uint32_t reg = blockIdx.x; reg < n_regions; reg += gridDim.x) {
+        const BalWarp w = regions[reg].warp[wid];
+        switch (w.c) {
+        case 2: bal_consume<2>(w, pipe, ns, bal_smem, full_bar, empty_bar, R, H, row_len, priors, scores, g_begin, g_end); break;
+        case 3: bal_consume<3>(w, pipe, ns, bal_smem, full_bar, empty_bar, R, H, row_len, priors, scores, g_begin, g_end); break;
+        case 4: bal_consume<4>(w, pipe, ns, bal_smem, full_bar, empty_bar, R, H, row_len, priors, scores, g_begin, g_end); break;
+        case 5: if constexpr (CMAX >= 5) { bal_consume<5>(w, pipe, ns, bal_smem, full_bar, empty_bar, R, H, row_len, priors, scores, g_begin, g_end); break; }
+        case 6: if constexpr (CMAX >= 6) { bal_consume<6>(w, pipe, ns, bal_smem, full_bar, empty_bar, R, H, row_len, priors, scores, g_begin, g_end); break; }
+        case 7: if constexpr (CMAX >= 7) { bal_consume<7>(w, pipe, ns, bal_smem, full_bar, empty_bar, R, H, row_len, priors, scores, g_begin, g_end); break; }
+        case 8: if constexpr (CMAX >= 8) { bal_consume<8>(w, pipe, ns, bal_smem, full_bar, empty_bar, R, H, row_len, priors, scores, g_begin, g_end); break; }
+        default:                                   // idle slot: keep the ring moving
+            for (int c = 0; c < n_chunks; c++) {
+                mbar_spin(&full_bar[pipe.stage], pipe.phase);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[pipe.stage]);
+                bal_pipe_next(pipe, ns);
+            }
+            break;
+        }
+    }
+}
+
 // Host planner.  `pattern[q]` = columns per lane of the q-th warp of every sub-partition (warp w uses
 // pattern[w / 4]), so the CTA has 4 * n_pattern warps.  Returns the regions in order; region r is processed by
 // CTA r % gridDim.
@@ -433,13 +602,17 @@ static bool bal_plan(uint32_t H, uint64_t g_begin, uint64_t g_end, const uint32_
                 cur_strip = k;
                 a_off = off;
                 for (uint32_t q = 0; q < 16; q++) out.tab.push_back(32 * k + 2 * q);
+                rg.seg[rg.n_seg++] = BalSeg{32 * k, off, 32};
                 off += 32;
                 b_seg_off = off; b_seg_col0 = col;
+                rg.seg[rg.n_seg++] = BalSeg{col, off, 0};
             }
             BalWarp &bw = rg.warp[w];
             bw.row0 = 32 * k; bw.col0 = col; bw.ncols = take; bw.c = c; bw.a_off = a_off;
             bw.b_off = b_seg_off + (col - b_seg_col0);
             for (uint32_t q = 0; q < take / 2; q++) out.tab.push_back(col + 2 * q);
+            rg.seg[rg.n_seg - 1].len += take;
+            rg.n_active++;
             off += take;
             col += take;
             if (col >= Hc) { k++; col = 32 * k; }
@@ -518,9 +691,29 @@ static int bal_launch(lctp_locus_h *h, const BalPlan &plan, const BalRegion *d_r
                    : bal_launch2<NT, CMAX, 2>(h, plan, d_regions, d_tab, g_begin, g_end, d_scores, bytes(2));
 }
 
-// pattern == nullptr: choose automatically.
+template <int NW, int CMAX, bool BULK>
+static int bal_launch_ws(lctp_locus_h *h, const BalPlan &plan, const BalRegion *d_regions, uint64_t g_begin,
+                         uint64_t g_end, double *d_scores) {
+    lctp_ctx *ctx = h->ctx;
+    const LocusDev &d = h->dev;
+    auto bytes = [&](int ns) { return ((size_t)ns * BAL_RC + 1) * plan.row_len * sizeof(double); };
+    int ns = 4;
+    if (const char *e = getenv("LCTP_PREFILTER_BAL_STAGES")) ns = std::min(8, std::max(2, atoi(e)));
+    while (ns > 2 && bytes(ns) + 1024 > ctx->smem_optin) ns--;
+    if (bytes(ns) + 1024 > ctx->smem_optin) { set_error("lctp_prefilter: balanced plan needs %zu bytes of shared memory", bytes(ns)); return LCTP_E_CAPACITY; }
+    for (const BalRegion &rg : plan.regions)
+        if (rg.row_chunks > 256u) { set_error("lctp_prefilter: balanced plan stages %u chunks per read", rg.row_chunks); return LCTP_E_CAPACITY; }
+    LCTP_CUDA_CHECK(cudaFuncSetAttribute(k_prefilter_bal_ws<NW, CMAX, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(ns)));
+    const unsigned grid = (unsigned)std::min<size_t>(plan.regions.size(), (size_t)ctx->sm_count);
+    k_prefilter_bal_ws<NW, CMAX, BULK><<<grid, (NW + (BULK ? 1 : 4)) * 32, bytes(ns), ctx->stream>>>(
+        d.Mt, d.R, d.H, d.Hpad, d.priors, d_scores, d_regions, h->pf_tab.p, (uint32_t)plan.regions.size(), plan.row_len, ns,
+        g_begin, g_end);
+    return LCTP_OK;
+}
+
+// pattern == nullptr: choose automatically.  ws: warp-specialised kernel (bulk-copy producer warp).
 static int launch_prefilter_bal(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, double *d_scores,
-                                const uint32_t *pattern, uint32_t n_pattern) {
+                                const uint32_t *pattern, uint32_t n_pattern, int ws) {
     lctp_ctx *ctx = h->ctx;
     BalPlan &plan = h->pf_plan;
     std::vector<uint32_t> want(pattern, pattern + (pattern ? n_pattern : 0));
@@ -543,6 +736,39 @@ static int launch_prefilter_bal(lctp_locus_h *h, uint64_t g_begin, uint64_t g_en
     }
     const BalRegion *dr = h->pf_regions.p;
     const uint32_t nt = plan.n_warps * 32;
+    if (ws == 1) {
+        if (plan.cmax <= 4) {
+            switch (plan.n_warps) {
+            case 4: return bal_launch_ws<4, 4, true>(h, plan, dr, g_begin, g_end, d_scores);
+            case 8: return bal_launch_ws<8, 4, true>(h, plan, dr, g_begin, g_end, d_scores);
+            case 12: return bal_launch_ws<12, 4, true>(h, plan, dr, g_begin, g_end, d_scores);
+            case 16: return bal_launch_ws<16, 4, true>(h, plan, dr, g_begin, g_end, d_scores);
+            }
+        } else {
+            switch (plan.n_warps) {
+            case 4: return bal_launch_ws<4, 8, true>(h, plan, dr, g_begin, g_end, d_scores);
+            case 8: return bal_launch_ws<8, 8, true>(h, plan, dr, g_begin, g_end, d_scores);
+            }
+        }
+        set_error("lctp_prefilter: unsupported balanced pattern (%u warps, %u columns per lane)", plan.n_warps, plan.cmax);
+        return LCTP_E_INVALID;
+    }
+    if (ws == 2) {
+        if (plan.cmax <= 4) {
+            switch (plan.n_warps) {
+            case 4: return bal_launch_ws<4, 4, false>(h, plan, dr, g_begin, g_end, d_scores);
+            case 8: return bal_launch_ws<8, 4, false>(h, plan, dr, g_begin, g_end, d_scores);
+            case 12: return bal_launch_ws<12, 4, false>(h, plan, dr, g_begin, g_end, d_scores);
+            }
+        } else {
+            switch (plan.n_warps) {
+            case 4: return bal_launch_ws<4, 8, false>(h, plan, dr, g_begin, g_end, d_scores);
+            case 8: return bal_launch_ws<8, 8, false>(h, plan, dr, g_begin, g_end, d_scores);
+            }
+        }
+        set_error("lctp_prefilter: unsupported balanced pattern (%u warps, %u columns per lane)", plan.n_warps, plan.cmax);
+        return LCTP_E_INVALID;
+    }
     if (plan.cmax <= 4) {
         switch (nt) {
         case 128: return bal_launch<128, 4>(h, plan, dr, h->pf_tab.p, g_begin, g_end, d_scores);
@@ -694,11 +920,11 @@ int launch_prefilter(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, double *
         int variant = d.H < 400 ? 0 : d.H < 768 ? 4 : 1;      // measured on B200: profiles/r01_b_prefilter.md
         if (const char *e = getenv("LCTP_PREFILTER_VARIANT")) variant = atoi(e);   // tuning knob
         if (variant >= 7 && variant <= 10 && !h->mt_nonpositive) variant = 1;
-        if (variant == 16) {              // balanced persistent kernel; LCTP_PREFILTER_BAL="4,3" fixes the pattern
+        if (variant >= 16 && variant <= 18) {   // balanced persistent kernels; LCTP_PREFILTER_BAL="4,3" fixes the pattern
             uint32_t pat[4], np = 0;
             const char *e = getenv("LCTP_PREFILTER_BAL");
             if (e && *e && !parse_pattern(e, pat, &np)) { set_error("lctp_prefilter: bad LCTP_PREFILTER_BAL '%s'", e); return LCTP_E_INVALID; }
-            int rc = launch_prefilter_bal(h, g_begin, g_end, d_scores, np ? pat : nullptr, np);
+            int rc = launch_prefilter_bal(h, g_begin, g_end, d_scores, np ? pat : nullptr, np, variant - 16);
             if (rc) return rc;
             ctx->launches++;
             LCTP_CUDA_CHECK(cudaGetLastError());

@@ -223,13 +223,22 @@ def test_balanced_prefilter_kernel_is_bit_exact(oracle, gpu_ctx, H, R, monkeypat
     ref = oracle.prefilter_scores(oracle.OracleLocus(loc))
     dl = gpu_ctx.upload(loc)
     G = loc.n_genotypes
-    monkeypatch.setenv("LCTP_PREFILTER_VARIANT", "16")
-    for pattern in ("", "4,3", "4", "2", "3,2", "2,2,2", "4,3,2", "4,4,4,4", "7", "8", "5,6", "6"):
-        monkeypatch.setenv("LCTP_PREFILTER_BAL", pattern)
-        assert np.array_equal(dl.prefilter_scores(), ref), f"pattern '{pattern}'"
-        a, b = G // 4, G // 4 + G // 2
-        assert np.array_equal(dl.prefilter_scores(a, b), ref[a:b]), f"pattern '{pattern}' sub-range"
-        assert np.array_equal(dl.prefilter_scores(G - 3, G), ref[G - 3:]), f"pattern '{pattern}' tail range"
+    # 16: cp.async staging by every warp + CTA barrier; 17: bulk-copy producer warp + mbarrier ring;
+    # 18: four cp.async producer warps + mbarrier ring
+    for variant in ("16", "17", "18"):
+        monkeypatch.setenv("LCTP_PREFILTER_VARIANT", variant)
+        for pattern in ("", "4,3", "4", "2", "3,2", "2,2,2", "4,3,2", "4,4,4,4", "7", "8", "5,6", "6"):
+            if variant == "18" and pattern == "4,4,4,4":
+                continue                  # 16 consumer + 4 producer warps exceed the register file
+            monkeypatch.setenv("LCTP_PREFILTER_BAL", pattern)
+            what = f"variant {variant} pattern '{pattern}'"
+            assert np.array_equal(dl.prefilter_scores(), ref), what
+            a, b = G // 4, G // 4 + G // 2
+            assert np.array_equal(dl.prefilter_scores(a, b), ref[a:b]), what + " sub-range"
+            assert np.array_equal(dl.prefilter_scores(G - 3, G), ref[G - 3:]), what + " tail range"
+    for stages in ("2", "3", "6"):
+        monkeypatch.setenv("LCTP_PREFILTER_BAL_STAGES", stages)
+        assert np.array_equal(dl.prefilter_scores(), ref), f"variant 18, {stages} stages"
     dl.free()
 
 

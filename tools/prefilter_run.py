@@ -25,7 +25,7 @@ for spec in (a.variants.split(";") if a.variants else [None]):
         v, _, pat = spec.partition(":")
         os.environ["LCTP_PREFILTER_VARIANT"] = v
         os.environ["LCTP_PREFILTER_BAL"] = pat
-        label = f"variant {v}" + (f" pattern {pat or 'auto'}" if v == "16" else "")
+        label = f"variant {v}" + (f" pattern {pat or 'auto'}" if v in ("16", "17", "18") else "")
     for i in range(a.passes):
         if i == 1:
             ctx.stats(reset=True)
