@@ -212,7 +212,17 @@ k_prefilter_pairs(const double *__restrict__ Mt, uint32_t R, uint32_t H, uint32_
 //     ideal of 6.6, instead of 8 for the fullest SMs of the tiled kernel.
 // A CTA stages, per read, the 32 row values of every strip it touches plus its column range (one contiguous
 // smem row per read, 3-stage cp.async pipeline, one barrier per chunk).  Sums stay strictly in read order.
-static constexpr int BAL_RC = 32;              // reads per pipeline stage
+#ifndef LCTP_BAL_RC
+#define LCTP_BAL_RC 32
+#endif
+#ifndef LCTP_BAL_SLEEP
+#define LCTP_BAL_SLEEP 100
+#endif
+#ifndef LCTP_BAL_UNROLL
+#define LCTP_BAL_UNROLL 2
+#endif
+static constexpr int BAL_UNROLL = LCTP_BAL_UNROLL;
+static constexpr int BAL_RC = LCTP_BAL_RC;     // reads per pipeline stage (a multiple of 4: one row in four per producer warp)
 static constexpr int BAL_TAB = 256;            // max 16-byte chunks per staged read row (one staging pass of <= 256 threads)
 
 
@@ -406,8 +416,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
         "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// A consumer that has run ahead of the slowest warp of its CTA waits here; it sleeps between polls so that its
+// polling does not take issue slots from the warp it shares the sub-partition with (the one everybody waits for).
 __device__ __forceinline__ void mbar_spin(uint64_t *bar, unsigned parity) {
-    while (!mbar_try_wait(bar, parity)) {}
+    if (mbar_try_wait(bar, parity)) return;
+    while (!mbar_try_wait(bar, parity)) __nanosleep(LCTP_BAL_SLEEP);
+}
+// Producer side: the ring is usually full, so a producer waits most of the time; sleeping between polls keeps its
+// polling out of the issue slots the compute warps of the same sub-partition need.
+__device__ __forceinline__ void mbar_spin_sleep(uint64_t *bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(200);
 }
 
 struct BalPipe { int stage; unsigned phase; };     // position in the ring of NS stages, continues across regions
@@ -436,7 +454,7 @@ __device__ __forceinline__ void bal_consume(const BalWarp &w, BalPipe &pipe, int
         const int nr = min((int)BAL_RC, (int)(R - c * BAL_RC));
         double a[4], b[C];
         bal_load<C>(pa, pb, odd, a, b);
-#pragma unroll 2
+#pragma unroll BAL_UNROLL
         for (int rc = 0; rc < nr; rc++) {
             pa += row_len; pb += row_len;
             double an[4], bn[C];
@@ -492,7 +510,7 @@ k_prefilter_bal_ws(const double *__restrict__ Mt, uint32_t R, uint32_t H, uint32
             for (int c = 0; c < n_chunks; c++) {
                 const uint32_t r0 = c * BAL_RC;
                 const uint32_t nr = min((uint32_t)BAL_RC, R - r0);
-                if (lane == 0) mbar_spin(&empty_bar[pipe.stage], pipe.phase);
+                if (lane == 0) mbar_spin_sleep(&empty_bar[pipe.stage], pipe.phase);
                 __syncwarp();
                 double *dst = bal_smem + (size_t)pipe.stage * stage_len + (size_t)p * row_len + 2 * lane;
                 const double *src = Mt + (size_t)(r0 + p) * Hpad;
@@ -520,13 +538,13 @@ k_prefilter_bal_ws(const double *__restrict__ Mt, uint32_t R, uint32_t H, uint32
                 const uint32_t r0 = c * BAL_RC;
                 const uint32_t nr = min((uint32_t)BAL_RC, R - r0);
                 if (lane == 0) {
-                    mbar_spin(&empty_bar[pipe.stage], pipe.phase);
+                    mbar_spin_sleep(&empty_bar[pipe.stage], pipe.phase);
                     mbar_expect_tx(&full_bar[pipe.stage], nr * row_doubles * 8u);
                 }
                 __syncwarp();
-                if ((uint32_t)lane < nr) {
-                    const double *src = Mt + (size_t)(r0 + lane) * Hpad;
-                    double *dst = bal_smem + (size_t)pipe.stage * stage_len + (size_t)lane * row_len;
+                for (uint32_t rc = lane; rc < nr; rc += 32) {
+                    const double *src = Mt + (size_t)(r0 + rc) * Hpad;
+                    double *dst = bal_smem + (size_t)pipe.stage * stage_len + (size_t)rc * row_len;
                     for (uint32_t k = 0; k < n_seg; k++) {
                         const BalSeg sgm = rg->seg[k];
                         bulk_g2s(dst + sgm.dst, src + sgm.src, sgm.len * 8u, &full_bar[pipe.stage]);
@@ -917,18 +935,26 @@ int launch_prefilter(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, double *
     if (d.p == 2 && d.gt_tuples == nullptr) {
         // Tile shape by panel size: small panels need many CTAs (the R loop is a sequential chain per
         // genotype), large panels need the 4x4 register tile that keeps the FP64 pipe busy.
-        int variant = d.H < 400 ? 0 : d.H < 768 ? 4 : 1;      // measured on B200: profiles/r01_b_prefilter.md
-        if (const char *e = getenv("LCTP_PREFILTER_VARIANT")) variant = atoi(e);   // tuning knob
+        // Small panels: the tiled kernel with 1x1 register tiles (many CTAs).  From H = 400 up: the balanced
+        // persistent kernel with producer warps (variant 18) -- measured on B200 (profiles/r01_c_summary.md):
+        // H = 500: 0.165 ms against 0.219 (2x2 tiles), H = 1,000: 1.02 ms against 1.24 (4x4 tiles), and the
+        // genotype range of one rank of 2 / 8 at H = 1,000: 0.63 / 0.39 ms against 1.23 / 0.78.
+        int variant = d.H < 400 ? 0 : 18;
+        const char *ev = getenv("LCTP_PREFILTER_VARIANT");         // tuning knob
+        if (ev) variant = atoi(ev);
         if (variant >= 7 && variant <= 10 && !h->mt_nonpositive) variant = 1;
         if (variant >= 16 && variant <= 18) {   // balanced persistent kernels; LCTP_PREFILTER_BAL="4,3" fixes the pattern
             uint32_t pat[4], np = 0;
             const char *e = getenv("LCTP_PREFILTER_BAL");
             if (e && *e && !parse_pattern(e, pat, &np)) { set_error("lctp_prefilter: bad LCTP_PREFILTER_BAL '%s'", e); return LCTP_E_INVALID; }
             int rc = launch_prefilter_bal(h, g_begin, g_end, d_scores, np ? pat : nullptr, np, variant - 16);
-            if (rc) return rc;
-            ctx->launches++;
-            LCTP_CUDA_CHECK(cudaGetLastError());
-            return LCTP_OK;
+            if (rc == LCTP_OK) {
+                ctx->launches++;
+                LCTP_CUDA_CHECK(cudaGetLastError());
+                return LCTP_OK;
+            }
+            if (ev || rc != LCTP_E_CAPACITY) return rc;             // explicit request, or a real error
+            variant = d.H < 768 ? 4 : 1;                            // plan does not fit shared memory: tiled kernel
         }
         auto go = [&](auto kern, int TB, int NT) {
             uint32_t nb = (d.H + TB - 1) / TB;

@@ -7,6 +7,7 @@ from locityper_b200 import genotype, synth
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="C4")
 ap.add_argument("--passes", type=int, default=5)
+ap.add_argument("--shards", type=int, default=1, help="time the genotype range of shard 0 and of the last shard of N (multi-GPU partition)")
 ap.add_argument("--variants", default="", help="e.g. '1;16:;16:4,3' = kernel variants (and balanced patterns) to time")
 a = ap.parse_args()
 t0 = time.time()
@@ -26,6 +27,19 @@ for spec in (a.variants.split(";") if a.variants else [None]):
         os.environ["LCTP_PREFILTER_VARIANT"] = v
         os.environ["LCTP_PREFILTER_BAL"] = pat
         label = f"variant {v}" + (f" pattern {pat or 'auto'}" if v in ("16", "17", "18") else "")
+    if a.shards > 1:
+        from locityper_b200 import dist
+        for rank in (0, a.shards - 1):
+            ga, gb = dist.shard_range(loc.n_genotypes, rank, a.shards)
+            for i in range(a.passes):
+                if i == 1:
+                    ctx.stats(reset=True)
+                s = dl.prefilter_scores(ga, gb)
+            st = ctx.stats()
+            ms = st["prefilter_ms"] / max(1, st["prefilter_launches"])
+            print(f"prefilter [{label}] shard {rank}/{a.shards} ({gb - ga} genotypes): {ms:.4f} ms/launch, "
+                  f"{(gb - ga) * loc.n_reads / ms / 1e9:.3f} T elements/s, checksum {float(s.sum()):.6e}", flush=True)
+        continue
     for i in range(a.passes):
         if i == 1:
             ctx.stats(reset=True)
