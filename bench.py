@@ -438,12 +438,12 @@ def kir_prefilter(ctx, genotype, peak, fp64_rate):
     sec = st["prefilter_ms"] / 1e3
     gp, R, p = st["prefilter_genotypes"], loc.n_reads, loc.ploidy
     ops = gp * p * R
-    return {"kernel": "k_prefilter_pairs", "workload": "configs[3] shape: H=1000, G=500500, R=10000 (one locus, one GPU)",
+    return {"kernel": "k_prefilter_bal_ws", "workload": "configs[3] shape: H=1000, G=500500, R=10000 (one locus, one GPU)",
             "bound": "fp64-pipe", "achieved": ops / sec / 1e12, "peak": fp64_rate / 1e12,
             "unit": "T FP64-pipe lane-instructions/s", "frac": ops / sec / fp64_rate,
             "peak_source": "DADD microbenchmark run live (lctp_measure_fp64_rate)",
             "avg_launch_ms": st["prefilter_ms"] / st["prefilter_launches"],
-            "traffic": ncu_traffic("k_prefilter_pairs_kir"),
+            "traffic": ncu_traffic("k_prefilter_bal_ws_kir"),
             "hbm_reference_pattern": {"achieved": gp * (p * R * 8 + 8) / sec / 1e9, "peak": peak, "unit": "GB/s",
                                       "frac": gp * (p * R * 8 + 8) / sec / 1e9 / peak}}
 
