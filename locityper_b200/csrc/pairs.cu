@@ -7,15 +7,17 @@
 // pairing of that mate (locs.rs:777-790), a stable descending selection of the best `max_alns` within
 // `prob_diff` of the best (locs.rs:793-798), scaled by the read weight (locs.rs:861-863).
 //
-// Device layout: one thread per mate record; the thread of the FIRST mate of a group owns the group (the
-// others exit), so groups are discovered without a host-side index and the output order (read, contig) is
-// the order of the owning records.  Two passes over the same code: pass 0 counts the kept pairs of every
-// group, an exclusive scan of the counts gives each group's output offset (and, read at ma_off[r], the
-// pa_off array), pass 1 recomputes and writes.  The byte traffic is one streaming read of the mate
-// records per pass plus the output: an HBM-bound kernel, no shared-memory staging needed because a
-// group's records are contiguous and read once.
+// Device layout: groups are discovered on the device (head flag per mate record = first record of its read or
+// contig change, exclusive scan -> dense group index, scatter of the group starts), then ONE THREAD PER GROUP
+// evaluates its group, so every lane of a warp has work (the first version ran one thread per record with only
+// the group's first record working: 5 of 32 lanes active).  Two passes over the same code: pass 0 counts the kept
+// pairs of every group, an exclusive scan of the counts gives each group's output offset (and, read at the
+// first group of read r, the pa_off array), pass 1 recomputes and writes.  The output order (read, contig) is
+// the order of the group starts.  The byte traffic is a few streaming reads of the mate records (L2-resident at
+// the sizes of the configs) plus the output; no host round trip between the passes except the total count.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cub/device/device_scan.cuh>
 
 namespace lctp {
@@ -54,29 +56,49 @@ struct TopK {                       // stable descending top-`cap` list (cap <= 
     }
 };
 
+// head[i] = 1 when record i starts a (read, contig) group; read starts are added by k_pair_read_heads
+__global__ void __launch_bounds__(256)
+k_pair_heads(MatesDev D, uint32_t *__restrict__ head) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > D.N) return;
+    head[i] = i < D.N && (i == 0 || D.ma_contig[i] != D.ma_contig[i - 1]) ? 1u : 0u;   // head[N] = 0 (scan sentinel)
+}
+__global__ void __launch_bounds__(256)
+k_pair_read_heads(MatesDev D, uint32_t *__restrict__ head) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= D.R) return;
+    const uint64_t m = D.ma_off[r];
+    if (m < D.N && D.ma_off[r + 1] > m) head[m] = 1u;
+}
+// group_start[gidx[i]] = i for every head; group_start[G] = N
+__global__ void __launch_bounds__(256)
+k_pair_group_starts(MatesDev D, const uint32_t *__restrict__ head, const uint32_t *__restrict__ gidx,
+                    uint32_t *__restrict__ group_start) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > D.N) return;
+    if (i == D.N) group_start[gidx[D.N]] = (uint32_t)D.N;
+    else if (head[i]) group_start[gidx[i]] = (uint32_t)i;
+}
+
 template <bool WRITE>
 __global__ void __launch_bounds__(128)
-k_pair_groups(MatesDev D, uint32_t *__restrict__ counts, const uint64_t *__restrict__ offs,
+k_pair_groups(MatesDev D, const uint32_t *__restrict__ group_start, const uint32_t *__restrict__ gidx,
+              uint32_t *__restrict__ counts, const uint64_t *__restrict__ offs,
               uint32_t *__restrict__ pa_contig, double *__restrict__ pa_ln_prob, uint32_t *__restrict__ pa_mid1,
               uint32_t *__restrict__ pa_mid2, int *__restrict__ err) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= D.N) return;
-    // read of this record: last r with ma_off[r] <= i
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= gidx[D.N]) return;                       // number of groups, still on the device
+    const uint64_t i = group_start[g], e = group_start[g + 1];
+    // read of this group: last r with ma_off[r] <= i
     uint32_t lo = 0, hi = D.R;
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
         if (D.ma_off[mid] <= i) lo = mid; else hi = mid;
     }
     const uint32_t r = lo;
-    const uint64_t rb = D.ma_off[r], re = D.ma_off[r + 1];
+    const uint64_t rb = D.ma_off[r];
     const uint32_t contig = D.ma_contig[i];
-    if (i > rb) {
-        const uint32_t prev = D.ma_contig[i - 1];
-        if (prev == contig) { if (!WRITE) counts[i] = 0; return; }        // not the owner of its group
-        if (prev > contig) atomicOr(err, 1);                               // contigs must ascend within a read
-    }
-    uint64_t e = i + 1;
-    while (e < re && D.ma_contig[e] == contig) e++;
+    if (i > rb && D.ma_contig[i - 1] > contig) atomicOr(err, 1);          // contigs must ascend within a read
     uint64_t f = i;
     while (f < e && (D.ma_flags[f] & 1u) == 0) f++;
     for (uint64_t q = f; q < e; q++) if ((D.ma_flags[q] & 1u) == 0) atomicOr(err, 2);   // first end before second
@@ -122,9 +144,9 @@ k_pair_groups(MatesDev D, uint32_t *__restrict__ counts, const uint64_t *__restr
     const double thresh = __dsub_rn(top.lp[0], D.prob_diff);
     uint32_t keep = 0;
     while (keep < top.n && top.lp[keep] >= thresh) keep++;
-    if (!WRITE) { counts[i] = keep; return; }
+    if (!WRITE) { counts[g] = keep; return; }
     const double weight = D.read_weight ? D.read_weight[r] : 1.0;
-    const uint64_t o = offs[i];
+    const uint64_t o = offs[g];
     for (uint32_t q = 0; q < keep; q++) {
         pa_contig[o + q] = contig;
         pa_ln_prob[o + q] = __dmul_rn(top.lp[q], weight);                  // locs.rs:861-863
@@ -133,13 +155,12 @@ k_pair_groups(MatesDev D, uint32_t *__restrict__ counts, const uint64_t *__restr
     }
 }
 
-// pa_off[r] = offs[ma_off[r]]; unmapped_prob[r] = weight * (2 * unmapped_penalty + insert_penalty) (locs.rs:866)
-__global__ void k_pair_read_outputs(MatesDev D, const uint64_t *__restrict__ offs, uint64_t total,
+// pa_off[r] = offs[first group at or after ma_off[r]]; unmapped_prob[r] = weight * (2 * unmapped_penalty + insert_penalty) (locs.rs:866)
+__global__ void k_pair_read_outputs(MatesDev D, const uint32_t *__restrict__ gidx, const uint64_t *__restrict__ offs,
                                     uint64_t *__restrict__ pa_off, double *__restrict__ unmapped_prob) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r > D.R) return;
-    const uint64_t m = D.ma_off[r];
-    pa_off[r] = m < D.N ? offs[m] : total;
+    pa_off[r] = offs[gidx[D.ma_off[r]]];              // gidx[N] = number of groups, offs[G] = total
     if (r < D.R) {
         const double weight = D.read_weight ? D.read_weight[r] : 1.0;
         unmapped_prob[r] = __dmul_rn(weight, __dadd_rn(__dmul_rn(2.0, D.unmapped_penalty), D.insert_penalty));
@@ -166,12 +187,13 @@ int pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t 
     }
     const uint64_t N = in->ma_off[R];
     DevBuf<uint64_t> d_off, d_offs, d_pa_off;
-    DevBuf<uint32_t> d_contig, d_start, d_end, d_counts, d_oc, d_m1, d_m2;
+    DevBuf<uint32_t> d_contig, d_start, d_end, d_counts, d_oc, d_m1, d_m2, d_head, d_gidx, d_gstart;
     DevBuf<uint8_t> d_flags;
     DevBuf<double> d_lp, d_w, d_ins, d_olp, d_unm;
     DevBuf<int> d_err;
     DevBuf<unsigned char> d_tmp;
     int rc;
+    if (N >= 0xFFFFFFFFull) { set_error("lctp_pair_alignments: %llu mate records (limit 2^32 - 2)", (unsigned long long)N); return LCTP_E_CAPACITY; }
     if ((rc = to_dev(d_off, in->ma_off, (size_t)R + 1, s))) return rc;
     if ((rc = to_dev(d_contig, in->ma_contig, N, s))) return rc;
     if ((rc = to_dev(d_start, in->ma_start, N, s))) return rc;
@@ -180,6 +202,9 @@ int pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t 
     if ((rc = to_dev(d_lp, in->ma_ln_prob, N, s))) return rc;
     if (in->read_weight && (rc = to_dev(d_w, in->read_weight, R, s))) return rc;
     if ((rc = to_dev(d_ins, in->ins_ln_pmf, in->ins_len, s))) return rc;
+    if ((rc = d_head.alloc(N + 1))) return rc;
+    if ((rc = d_gidx.alloc(N + 1))) return rc;
+    if ((rc = d_gstart.alloc(N + 2))) return rc;
     if ((rc = d_counts.alloc(N + 1))) return rc;
     if ((rc = d_offs.alloc(N + 1))) return rc;
     if ((rc = d_err.alloc(1))) return rc;
@@ -196,16 +221,26 @@ int pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t 
     D.unmapped_penalty = in->unmapped_penalty; D.insert_penalty = in->insert_penalty; D.prob_diff = in->prob_diff;
 
     uint64_t total = 0;
-    if (N) {
-        const unsigned grid = (unsigned)((N + 127) / 128);
+    {
+        const unsigned grid_n = (unsigned)((N + 1 + 255) / 256);      // threads over records (+ sentinel)
+        const unsigned grid_g = (unsigned)((N + 127) / 128);          // threads over groups (#groups <= N)
+        size_t tmp32 = 0, tmp64 = 0;
+        LCTP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp32, d_head.p, d_gidx.p, (int)(N + 1), s));
+        LCTP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp64, d_counts.p, d_offs.p, (int)(N + 1), s));
+        if ((rc = d_tmp.alloc(std::max(tmp32, tmp64)))) return rc;
         LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[0], s));
-        k_pair_groups<false><<<grid, 128, 0, s>>>(D, d_counts.p, nullptr, nullptr, nullptr, nullptr, nullptr, d_err.p);
+        k_pair_heads<<<grid_n, 256, 0, s>>>(D, d_head.p);
+        k_pair_read_heads<<<(R + 255) / 256, 256, 0, s>>>(D, d_head.p);
+        LCTP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp32, d_head.p, d_gidx.p, (int)(N + 1), s));
+        k_pair_group_starts<<<grid_n, 256, 0, s>>>(D, d_head.p, d_gidx.p, d_gstart.p);
+        ctx->launches += 4;
+        if (N) {
+            k_pair_groups<false><<<grid_g, 128, 0, s>>>(D, d_gstart.p, d_gidx.p, d_counts.p, nullptr, nullptr, nullptr, nullptr, nullptr, d_err.p);
+            ctx->launches++;
+        }
+        LCTP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp64, d_counts.p, d_offs.p, (int)(N + 1), s));
         ctx->launches++;
-        size_t tmp_bytes = 0;
-        LCTP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts.p, d_offs.p, (int)(N + 1), s));
-        if ((rc = d_tmp.alloc(tmp_bytes))) return rc;
-        LCTP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_counts.p, d_offs.p, (int)(N + 1), s));
-        ctx->launches++;
+        LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[1], s));      // phase A: groups + counts; the host sizes the output next
         LCTP_CUDA_CHECK(cudaMemcpyAsync(&total, d_offs.p + N, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         int err = 0;
         LCTP_CUDA_CHECK(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -225,12 +260,15 @@ int pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t 
         if ((rc = d_olp.alloc(total))) return rc;
         if ((rc = d_m1.alloc(total))) return rc;
         if ((rc = d_m2.alloc(total))) return rc;
-        k_pair_groups<true><<<grid, 128, 0, s>>>(D, nullptr, d_offs.p, d_oc.p, d_olp.p, d_m1.p, d_m2.p, d_err.p);
+        LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[2], s));      // phase B: write pass
+        if (N) {
+            k_pair_groups<true><<<grid_g, 128, 0, s>>>(D, d_gstart.p, d_gidx.p, nullptr, d_offs.p, d_oc.p, d_olp.p, d_m1.p, d_m2.p, d_err.p);
+            ctx->launches++;
+        }
+        k_pair_read_outputs<<<(R + 1 + 255) / 256, 256, 0, s>>>(D, d_gidx.p, d_offs.p, d_pa_off.p, d_unm.p);
         ctx->launches++;
-        LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[1], s));
+        LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[3], s));
     }
-    k_pair_read_outputs<<<(R + 1 + 255) / 256, 256, 0, s>>>(D, d_offs.p, total, d_pa_off.p, d_unm.p);
-    ctx->launches++;
     LCTP_CUDA_CHECK(cudaGetLastError());
     LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_off, d_pa_off.p, ((size_t)R + 1) * 8, cudaMemcpyDeviceToHost, s));
     LCTP_CUDA_CHECK(cudaMemcpyAsync(unmapped_prob, d_unm.p, (size_t)R * 8, cudaMemcpyDeviceToHost, s));
@@ -241,10 +279,11 @@ int pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t 
         LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_mid2, d_m2.p, total * 4, cudaMemcpyDeviceToHost, s));
     }
     LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
-    if (N) {
-        float ms = 0.f;
+    {
+        float ms = 0.f, ms2 = 0.f;
         LCTP_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
-        ctx->stats.pairing_ms += ms;
+        LCTP_CUDA_CHECK(cudaEventElapsedTime(&ms2, ctx->ev[2], ctx->ev[3]));
+        ctx->stats.pairing_ms += ms + ms2;
         ctx->stats.pairing_launches += 1;
         ctx->stats.pairing_mates += N;
         ctx->stats.pairing_pairs += total;

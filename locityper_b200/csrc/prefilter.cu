@@ -215,6 +215,9 @@ k_prefilter_pairs(const double *__restrict__ Mt, uint32_t R, uint32_t H, uint32_
 #ifndef LCTP_BAL_RC
 #define LCTP_BAL_RC 32
 #endif
+#ifndef LCTP_BAL_ORDER
+#define LCTP_BAL_ORDER 0
+#endif
 #ifndef LCTP_BAL_SLEEP
 #define LCTP_BAL_SLEEP 100
 #endif
@@ -459,10 +462,17 @@ __device__ __forceinline__ void bal_consume(const BalWarp &w, BalPipe &pipe, int
             pa += row_len; pb += row_len;
             double an[4], bn[C];
             bal_load<C>(pa, pb, odd, an, bn);      // row nr of the last chunk row is never used (next stage / padding)
+#if LCTP_BAL_ORDER == 0
 #pragma unroll
             for (int x = 0; x < 4; x++)
 #pragma unroll
                 for (int y = 0; y < C; y++) acc[x][y] = __dadd_rn(acc[x][y], dmax(a[x], b[y]));
+#else
+#pragma unroll
+            for (int y = 0; y < C; y++)
+#pragma unroll
+                for (int x = 0; x < 4; x++) acc[x][y] = __dadd_rn(acc[x][y], dmax(a[x], b[y]));
+#endif
 #pragma unroll
             for (int x = 0; x < 4; x++) a[x] = an[x];
 #pragma unroll
