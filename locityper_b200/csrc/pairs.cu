@@ -106,6 +106,50 @@ k_pair_groups(MatesDev D, const uint32_t *__restrict__ group_start, const uint32
     const uint32_t n1 = (uint32_t)min((uint64_t)M, f - i), n2 = (uint32_t)min((uint64_t)M, e - f);
     const double unm_ins = D.unmapped_penalty + D.insert_penalty;          // locs.rs:815-816
 
+    if (f - i <= 1 && e - f <= 1 && M >= 3) {
+        // The common group -- at most one alignment per end: at most three options (pair, first alone, second
+        // alone), kept in registers.  Same pushes in the same order as the general path below.
+        double lp0 = 0, lp1 = 0, lp2 = 0;
+        uint32_t x0 = 0, x1 = 0, x2 = 0, y0 = 0, y1 = 0, y2 = 0, n = 0;
+        auto push = [&](double p, uint32_t x, uint32_t y) {
+            const long long key = pair_total_key(p);
+            uint32_t pos = n;                                  // after every entry >= p: stable
+            if (n == 2) { if (pair_total_key(lp1) < key) { pos = 1; if (pair_total_key(lp0) < key) pos = 0; } }
+            else if (n == 1) { if (pair_total_key(lp0) < key) pos = 0; }
+            if (pos <= 1 && n >= 2) { lp2 = lp1; x2 = x1; y2 = y1; }
+            if (pos == 0 && n >= 1) { lp1 = lp0; x1 = x0; y1 = y0; }
+            if (pos == 0) { lp0 = p; x0 = x; y0 = y; }
+            else if (pos == 1) { lp1 = p; x1 = x; y1 = y; }
+            else { lp2 = p; x2 = x; y2 = y; }
+            n++;
+        };
+        const bool h1 = f > i, h2 = e > f;
+        double l1 = 0, l2 = 0, max1 = -INFINITY, best2 = -INFINITY;
+        uint32_t mid1 = LCTP_NONE_U32, mid2 = LCTP_NONE_U32, s1 = 0, e1 = 0, s2 = 0, e2 = 0;
+        if (h1) { s1 = D.ma_start[i]; e1 = D.ma_end[i]; l1 = D.ma_ln_prob[i]; mid1 = (s1 + e1) / 2; }
+        if (h2) { s2 = D.ma_start[f]; e2 = D.ma_end[f]; l2 = D.ma_ln_prob[f]; mid2 = (s2 + e2) / 2; }
+        if (h1 && h2 && (D.ma_flags[f] & 2u) != (D.ma_flags[i] & 2u)) {
+            const uint32_t insert = max(e1, e2) - min(s1, s2);
+            if (insert >= D.ins_len) atomicOr(err, 8);
+            else {
+                const double prob = __dadd_rn(__dadd_rn(l1, l2), D.ins_ln_pmf[insert]);
+                if (isfinite(prob)) { max1 = prob; best2 = prob; push(prob, mid1, mid2); }
+            }
+        }
+        if (h1) { const double alone1 = __dadd_rn(l1, unm_ins); if (alone1 >= max1) push(alone1, mid1, LCTP_NONE_U32); }
+        if (h2) { const double alone2 = __dadd_rn(l2, unm_ins); if (alone2 >= best2) push(alone2, LCTP_NONE_U32, mid2); }
+        const double thresh = __dsub_rn(lp0, D.prob_diff);
+        uint32_t keep = 0;
+        if (n >= 1 && lp0 >= thresh) { keep = 1; if (n >= 2 && lp1 >= thresh) { keep = 2; if (n >= 3 && lp2 >= thresh) keep = 3; } }
+        if (!WRITE) { counts[g] = keep; return; }
+        const double weight = D.read_weight ? D.read_weight[r] : 1.0;
+        const uint64_t o = offs[g];
+        if (keep >= 1) { pa_contig[o] = contig; pa_ln_prob[o] = __dmul_rn(lp0, weight); pa_mid1[o] = x0; pa_mid2[o] = y0; }
+        if (keep >= 2) { pa_contig[o + 1] = contig; pa_ln_prob[o + 1] = __dmul_rn(lp1, weight); pa_mid1[o + 1] = x1; pa_mid2[o + 1] = y1; }
+        if (keep >= 3) { pa_contig[o + 2] = contig; pa_ln_prob[o + 2] = __dmul_rn(lp2, weight); pa_mid1[o + 2] = x2; pa_mid2[o + 2] = y2; }
+        return;
+    }
+
     TopK top;
     top.n = 0; top.total = 0;
     double best2[PAIR_MAX_ALNS];
