@@ -50,6 +50,8 @@ def parse_args():
                     help="reference -S stages; configs[1] is 'prefilter + greedy'")
     ap.add_argument("--streams", type=int, default=0,
                     help="loci in flight per GPU (one context + CUDA stream + host thread each); 0 = loci per step")
+    ap.add_argument("--max-resident", type=int, default=0,
+                    help="resident logical workers per context (solver grid cap); 0 = every context may fill the device")
     ap.add_argument("--seed", type=int, default=2001)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kir-prefilter", action="store_true",
@@ -257,7 +259,10 @@ def run_ours(args):
     # The loci of a step are independent (genotype.rs:1331-1351): each is solved by its own context (own
     # CUDA stream, own host thread), so kernels, copies and host-side pruning of different loci overlap.
     n_streams = args.streams if args.streams > 0 else len(loci)
-    pool = genotype.ContextPool(device=local, k=n_streams)
+    # Loci in flight share the SMs: the stage kernels of the contexts run side by side, a finishing kernel's free
+    # worker slots are taken by the next one.  --max-resident caps the slots one context may take (0 = no cap).
+    max_res = max(0, args.max_resident)
+    pool = genotype.ContextPool(device=local, k=n_streams, max_resident_workers=max_res)
     fp64_rate = ctx.fp64_rate()
 
     def barrier():

@@ -18,6 +18,9 @@
 #include <cstring>
 #include <algorithm>
 #include <vector>
+#include <mutex>
+#include <map>
+#include <utility>
 
 namespace lctp {
 
@@ -689,12 +692,26 @@ static bool parse_pattern(const char *e, uint32_t *pat, uint32_t *np) {
     return *np > 0 && *e == 0;
 }
 
+// Raise a kernel's dynamic shared-memory limit only when it has to grow: re-setting a function attribute makes the
+// next launch of that function wait for its running instances (it serialised kernels of concurrent contexts).
+template <typename K>
+static cudaError_t ensure_dyn_smem(K kern, int device, size_t bytes) {
+    static std::mutex m;
+    static std::map<std::pair<const void *, int>, size_t> lim;      // (kernel instantiation, device) -> limit set
+    std::lock_guard<std::mutex> lk(m);
+    size_t &l = lim[std::make_pair((const void *)kern, device)];
+    if (bytes <= 48 * 1024 || bytes <= l) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) l = bytes;
+    return e;
+}
+
 template <int NT, int CMAX, int NS>
 static int bal_launch2(lctp_locus_h *h, const BalPlan &plan, const BalRegion *d_regions, const uint32_t *d_tab,
                        uint64_t g_begin, uint64_t g_end, double *d_scores, size_t smem) {
     lctp_ctx *ctx = h->ctx;
     const LocusDev &d = h->dev;
-    LCTP_CUDA_CHECK(cudaFuncSetAttribute(k_prefilter_bal<NT, CMAX, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LCTP_CUDA_CHECK(ensure_dyn_smem(k_prefilter_bal<NT, CMAX, NS>, ctx->device, smem));
     const unsigned grid = (unsigned)std::min<size_t>(plan.regions.size(), (size_t)ctx->sm_count);
     k_prefilter_bal<NT, CMAX, NS><<<grid, NT, smem, ctx->stream>>>(d.Mt, d.R, d.H, d.Hpad, d.priors, d_scores, d_regions, d_tab,
                                                                 (uint32_t)plan.regions.size(), plan.row_len, g_begin, g_end);
@@ -731,7 +748,7 @@ static int bal_launch_ws(lctp_locus_h *h, const BalPlan &plan, const BalRegion *
     if (bytes(ns) + 1024 > ctx->smem_optin) { set_error("lctp_prefilter: balanced plan needs %zu bytes of shared memory", bytes(ns)); return LCTP_E_CAPACITY; }
     for (const BalRegion &rg : plan.regions)
         if (rg.row_chunks > 256u) { set_error("lctp_prefilter: balanced plan stages %u chunks per read", rg.row_chunks); return LCTP_E_CAPACITY; }
-    LCTP_CUDA_CHECK(cudaFuncSetAttribute(k_prefilter_bal_ws<NW, CMAX, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(ns)));
+    LCTP_CUDA_CHECK(ensure_dyn_smem(k_prefilter_bal_ws<NW, CMAX, BULK>, ctx->device, bytes(ns)));
     const unsigned grid = (unsigned)std::min<size_t>(plan.regions.size(), (size_t)ctx->sm_count);
     k_prefilter_bal_ws<NW, CMAX, BULK><<<grid, (NW + (BULK ? 1 : 4)) * 32, bytes(ns), ctx->stream>>>(
         d.Mt, d.R, d.H, d.Hpad, d.priors, d_scores, d_regions, h->pf_tab.p, (uint32_t)plan.regions.size(), plan.row_len, ns,

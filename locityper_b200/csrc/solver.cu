@@ -1219,7 +1219,14 @@ static int launch_stage_gs(lctp_locus_h *h, const StageParams &P, size_t n_worke
     // function attributes are per-device state shared by every context: configure + launch under one lock
     static std::mutex launch_mutex;
     std::lock_guard<std::mutex> lock(launch_mutex);
-    LCTP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // Only raise the limit when needed: re-setting a function attribute makes the next launch of the function wait
+    // for its running instances, which serialised the stage kernels of loci in flight on different contexts.
+    static size_t smem_limit[16] = {0};
+    size_t &lim = smem_limit[(ctx->device & 7) * 2 + (GS == 32 ? 1 : 0)];
+    if (smem > 48 * 1024 && smem > lim) {
+        LCTP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lim = smem;
+    }
     if (const char *e = getenv("LCTP_CARVEOUT"))   // tuning knob: shared-memory carveout percentage
         LCTP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
     int occ = 0;
@@ -1342,6 +1349,14 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
         set_error("lctp_solve_stage: candidate slab overflow (cap=%u, or > 65535 candidates of non-trivial reads "
                   "in one genotype)", cap);
         return LCTP_E_CAPACITY;
+    }
+    if (getenv("LCTP_DEBUG_TIMES")) {      // investigation aid: kernel interval on a process-wide GPU time base
+        static std::mutex m; static cudaEvent_t ref = nullptr;
+        std::lock_guard<std::mutex> lk(m);
+        if (!ref) { cudaEventCreate(&ref); cudaEventRecord(ref, s); cudaEventSynchronize(ref); }
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, ref, ctx->ev[2]); cudaEventElapsedTime(&b, ref, ctx->ev[3]);
+        fprintf(stderr, "[lctp debug] ctx %p stage kernel %.3f .. %.3f ms\n", (void *)ctx, a, b);
     }
     {
         float ms = 0.f;
