@@ -723,6 +723,7 @@ int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_
         set_error("lctp_solve: invalid argument");
         return LCTP_E_INVALID;
     }
+    const double t_in = now_s();
     const uint64_t G = h->dev.G;
     std::memset(res, 0, sizeof(*res));
     threads = std::max<size_t>(1, std::min<size_t>(threads, G));     // genotype.rs:1247
@@ -748,6 +749,7 @@ int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_
         const JumpTable &jt = jump_table();
         for (size_t w = 0; w < threads; w++) { std::memcpy(&wrng[4 * w], rng, 32); jt.apply(rng); }
     }
+    const double t_jump = now_s();
     std::vector<uint64_t> off(threads + 1);
     std::vector<double> lm, lv;
     for (size_t s = 0; s < n_stages; s++) {
@@ -774,6 +776,7 @@ int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_
                                         h->host.prob_thresh, out_size, threads);
     }
     res->t_stages_s = now_s() - t1;
+    const double t_st = now_s();
     const uint64_t n_filtered = res->n_filtered;
     uint64_t n_stage_in[LCTP_MAX_STAGES];
     std::memcpy(n_stage_in, res->n_stage_in, sizeof(n_stage_in));
@@ -783,6 +786,9 @@ int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_
     res->n_filtered = n_filtered;
     std::memcpy(res->n_stage_in, n_stage_in, sizeof(n_stage_in));
     res->t_prefilter_s = tp; res->t_stages_s = ts;
+    if (getenv("LCTP_DEBUG_TIMES"))
+        fprintf(stderr, "[lctp debug] ctx %p lctp_solve host: setup %.3f, prefilter %.3f, worker streams %.3f, stages %.3f, result %.3f ms\n",
+                (void *)h->ctx, (t0 - t_in) * 1e3, (t1 - t0) * 1e3, (t_jump - t1) * 1e3, (t_st - t_jump) * 1e3, (now_s() - t_st) * 1e3);
     return LCTP_OK;
 }
 

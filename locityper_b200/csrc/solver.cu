@@ -26,6 +26,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <mutex>
+#include <chrono>
 
 namespace lctp {
 
@@ -1203,6 +1204,10 @@ static int ensure_rng_mats(lctp_ctx *ctx) {
 
 // ------------------------------------------------------------------ host launch -----------------
 
+static double dbg_now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 template <int GS>
 static int launch_stage_gs(lctp_locus_h *h, const StageParams &P, size_t n_workers, bool want_counts) {
     lctp_ctx *ctx = h->ctx;
@@ -1258,6 +1263,7 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     lctp_ctx *ctx = h->ctx;
     cudaStream_t s = ctx->stream;
     const LocusDev &L = h->dev;
+    const double t_enter = dbg_now();
     if (!st || !worker_ixs || !worker_off || !worker_rng || !lik_mean || !lik_var || n_workers == 0) {
         set_error("lctp_solve_stage: NULL argument");
         return LCTP_E_INVALID;
@@ -1330,6 +1336,7 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     LCTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tuples.p, tuples.data(), n * p * 4, cudaMemcpyHostToDevice, s));
     LCTP_CUDA_CHECK(cudaMemsetAsync(ctx->d_flags.p, 0, 2 * sizeof(int), s));
 
+    const double t_launch = dbg_now();
     int gs = 32;
     if (const char *e = getenv("LCTP_GS")) gs = atoi(e) == 16 ? 16 : 32;   // tuning knob: lanes per worker
     rc = gs == 32 ? launch_stage_gs<32>(h, P, n_workers, want_counts) : launch_stage_gs<16>(h, P, n_workers, want_counts);
@@ -1356,7 +1363,8 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
         if (!ref) { cudaEventCreate(&ref); cudaEventRecord(ref, s); cudaEventSynchronize(ref); }
         float a = 0.f, b = 0.f;
         cudaEventElapsedTime(&a, ref, ctx->ev[2]); cudaEventElapsedTime(&b, ref, ctx->ev[3]);
-        fprintf(stderr, "[lctp debug] ctx %p stage kernel %.3f .. %.3f ms\n", (void *)ctx, a, b);
+        fprintf(stderr, "[lctp debug] ctx %p stage kernel %.3f .. %.3f ms; host before launch %.3f ms, launch -> results on host %.3f ms\n",
+                (void *)ctx, a, b, (t_launch - t_enter) * 1e3, (dbg_now() - t_launch) * 1e3);
     }
     {
         float ms = 0.f;
