@@ -227,6 +227,9 @@ int  lctp_solve_stage(lctp_locus_h *h, const lctp_stage *st,
 /* ---- host-side mirror of the scheduler (a14-a16) ------------------------------------------- */
 void lctp_rng_seed_from_u64(uint64_t state[4], uint64_t seed);   /* src/ext/rand.rs:12 */
 void lctp_rng_jump(uint64_t state[4]);                            /* src/solvers/solve.rs:1017 */
+/* MainWorker::new (src/solvers/solve.rs:1007-1018): worker w gets a clone of the locus stream, which then jumps;
+ * out[4*w..4*w+4] = state of worker w, `state` ends `threads` jumps ahead. */
+void lctp_rng_worker_streams(uint64_t state[4], size_t threads, uint64_t *out);
 void lctp_rng_long_jump(uint64_t state[4]);                       /* src/command/genotype.rs:1345 */
 /* MainWorker::run :1049-1063: shuffle ixs with the locus stream and cut into <= threads chunks.
  * worker_off has threads+1 entries; returns the number of workers that received work. */

@@ -589,6 +589,10 @@ void lctp_rng_seed_from_u64(uint64_t state[4], uint64_t seed) {
     }
 }
 void lctp_rng_jump(uint64_t state[4]) { jump_table().apply(state); }
+void lctp_rng_worker_streams(uint64_t state[4], size_t threads, uint64_t *out) {
+    const JumpTable &jt = jump_table();
+    for (size_t w = 0; w < threads; w++) { std::memcpy(out + 4 * w, state, 32); jt.apply(state); }
+}
 void lctp_rng_long_jump(uint64_t state[4]) {
     HostRng r; std::memcpy(r.s, state, 32); r.jump_poly(kLongJump); std::memcpy(state, r.s, 32);
 }
@@ -746,8 +750,7 @@ int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_
     std::vector<uint64_t> wrng;
     if (threads > 1) {                                               // MainWorker::new, solve.rs:1007-1018
         wrng.resize(threads * 4);
-        const JumpTable &jt = jump_table();
-        for (size_t w = 0; w < threads; w++) { std::memcpy(&wrng[4 * w], rng, 32); jt.apply(rng); }
+        lctp_rng_worker_streams(rng, threads, wrng.data());
     }
     const double t_jump = now_s();
     std::vector<uint64_t> off(threads + 1);

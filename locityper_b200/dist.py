@@ -66,25 +66,44 @@ class Comm:
     def allgather_var(self, arr: np.ndarray) -> list:
         """All-gather 1-D numpy arrays of rank-dependent length (same dtype); returns the list per rank."""
         arr = np.ascontiguousarray(arr)
+        return [b.view(arr.dtype) for b in self.allgather_bytes(arr.view(np.uint8).reshape(-1))]
+
+    def allgather_packed(self, arrays) -> list:
+        """All-gather several 1-D arrays of rank-dependent lengths in ONE exchange (the volumes are KBs, so the
+        cost is the collectives' latency): returns, per rank, the list of that rank's arrays."""
+        arrays = [np.ascontiguousarray(a) for a in arrays]
+        head = np.array([a.size for a in arrays], dtype=np.int64)
+        blob = np.concatenate([head.view(np.uint8)] + [a.view(np.uint8).reshape(-1) for a in arrays])
+        out = []
+        for b in self.allgather_bytes(blob):
+            sizes = b[:8 * len(arrays)].view(np.int64)
+            pos, got = 8 * len(arrays), []
+            for a, n in zip(arrays, sizes):
+                nb = int(n) * a.itemsize
+                got.append(b[pos:pos + nb].view(a.dtype).copy())
+                pos += nb
+            out.append(got)
+        return out
+
+    def allgather_bytes(self, raw: np.ndarray) -> list:
+        """All-gather uint8 arrays of rank-dependent length: one fixed-size exchange of the lengths, one of the
+        payloads padded to the longest."""
         if self.world == 1:
-            return [arr]
+            return [raw]
         import torch
         import torch.distributed as dist
         dev = self.device if self.device is not None else torch.device("cpu")
-        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(self.world)]
-        dist.all_gather(sizes, torch.tensor([arr.size], dtype=torch.int64, device=dev), group=self.group)
-        sizes = [int(s.item()) for s in sizes]
+        sizes = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, torch.tensor([raw.size], dtype=torch.int64, device=dev), group=self.group)
+        sizes = [int(v) for v in sizes.cpu().tolist()]
         cap = max(max(sizes), 1)
-        raw = np.zeros(cap * arr.itemsize, dtype=np.uint8)
-        raw[:arr.nbytes] = arr.view(np.uint8).reshape(-1)
-        mine = torch.from_numpy(raw).to(dev)
-        bufs = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(bufs, mine, group=self.group)
-        self.bytes_gathered += cap * arr.itemsize * self.world
-        out = []
-        for s, b in zip(sizes, bufs):
-            out.append(b.cpu().numpy()[:s * arr.itemsize].view(arr.dtype).copy())
-        return out
+        mine = np.zeros(cap, dtype=np.uint8)
+        mine[:raw.size] = raw
+        bufs = torch.empty(self.world * cap, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(bufs, torch.from_numpy(mine).to(dev), group=self.group)
+        self.bytes_gathered += cap * self.world
+        host = bufs.cpu().numpy()
+        return [host[r * cap:r * cap + sizes[r]].copy() for r in range(self.world)]
 
 
 def prefilter_sharded(backend, min_size: int, threads: int, comm: Comm):
@@ -95,8 +114,9 @@ def prefilter_sharded(backend, min_size: int, threads: int, comm: Comm):
     g0, g1 = shard_range(G, comm.rank, comm.world)
     scores = backend.prefilter_scores(g0, g1) if g1 > g0 else np.zeros(0)
     ids, sc = local_candidates(scores, g0, loc.filt_diff, min_size, threads)
-    all_ids = np.concatenate(comm.allgather_var(ids))
-    all_sc = np.concatenate(comm.allgather_var(sc))
+    parts = comm.allgather_packed([ids, sc])
+    all_ids = np.concatenate([p[0] for p in parts])
+    all_sc = np.concatenate([p[1] for p in parts])
     # exact truncate_ixs on the union: ids ascending (= the order of predictions.ixs, solve.rs:406-411)
     order = np.argsort(all_ids, kind="stable")
     all_ids, all_sc = all_ids[order], all_sc[order]
@@ -111,31 +131,27 @@ def solve_stage_sharded(backend, stage, ixs: np.ndarray, off: np.ndarray, wrng: 
     every rank.  Returns (lik_mean, lik_var) indexed by position in `ixs`."""
     nw = len(off) - 1
     n = int(off[-1])
+    off64 = np.asarray(off, dtype=np.int64)
+    sizes = np.diff(off64)                                                  # genotypes per worker
+    rank_of_pos = np.repeat(np.arange(nw, dtype=np.int64) % comm.world, sizes)   # owner of every list position
+    pos_of = [np.flatnonzero(rank_of_pos == r) for r in range(comm.world)]  # ascending = worker order of rank r
     mine = np.arange(comm.rank, nw, comm.world)
-    my_ixs = [ixs[int(off[w]):int(off[w + 1])] for w in mine]
     my_off = np.zeros(len(mine) + 1, dtype=np.uint64)
-    if len(mine):
-        my_off[1:] = np.cumsum([len(x) for x in my_ixs])
+    my_off[1:] = np.cumsum(sizes[mine])
     my_rng = np.ascontiguousarray(wrng[mine]) if len(mine) else np.zeros((0, 4), dtype=np.uint64)
     if len(mine) and int(my_off[-1]) > 0:
-        out = backend.solve_stage(stage, np.concatenate(my_ixs), my_off, my_rng, want_liks=False)
+        out = backend.solve_stage(stage, np.ascontiguousarray(ixs[pos_of[comm.rank]]), my_off, my_rng, want_liks=False)
         lm, lv = out["lik_mean"], out["lik_var"]
     else:
         lm, lv = np.zeros(0), np.zeros(0)
-    g_lm = comm.allgather_var(lm)
-    g_lv = comm.allgather_var(lv)
-    g_rng = comm.allgather_var(my_rng.reshape(-1))
+    parts = comm.allgather_packed([lm, lv, my_rng.reshape(-1)])             # one exchange per stage
     lik_mean, lik_var = np.empty(n), np.empty(n)
     for r in range(comm.world):
+        lik_mean[pos_of[r]] = parts[r][0]
+        lik_var[pos_of[r]] = parts[r][1]
         ws = np.arange(r, nw, comm.world)
-        pos = 0
-        for j, w in enumerate(ws):
-            a, b = int(off[w]), int(off[w + 1])
-            lik_mean[a:b] = g_lm[r][pos:pos + b - a]
-            lik_var[a:b] = g_lv[r][pos:pos + b - a]
-            pos += b - a
         if len(ws):
-            wrng[ws] = g_rng[r].reshape(-1, 4)
+            wrng[ws] = parts[r][2].reshape(-1, 4)
     return lik_mean, lik_var
 
 
@@ -156,10 +172,7 @@ def solve_sharded(backend, scheme: genotype.Scheme, threads: int, rng: np.ndarra
     lik_var = np.full(G, np.nan)
     attempts = np.zeros(G, dtype=np.uint16)
     if threads > 1:                                                          # MainWorker::new, solve.rs:1007-1018
-        wrng = np.zeros((threads, 4), dtype=np.uint64)
-        for w in range(threads):
-            wrng[w] = rng
-            genotype.rng_jump(rng)
+        wrng = genotype.worker_streams(rng, threads)
     n_stage_in = [0] * 8
     for s, st in enumerate(stages):
         has_next = s + 1 < len(stages)
@@ -176,9 +189,10 @@ def solve_sharded(backend, scheme: genotype.Scheme, threads: int, rng: np.ndarra
                 lm, lv = out["lik_mean"], out["lik_var"]
             else:
                 lm, lv, state = np.zeros(0), np.zeros(0), np.zeros((0, 4), dtype=np.uint64)
-            lm = np.concatenate(comm.allgather_var(lm))
-            lv = np.concatenate(comm.allgather_var(lv))
-            rng[:] = np.concatenate(comm.allgather_var(state.reshape(-1)))[:4]
+            parts = comm.allgather_packed([lm, lv, state.reshape(-1)])
+            lm = np.concatenate([p[0] for p in parts])
+            lv = np.concatenate([p[1] for p in parts])
+            rng[:] = np.concatenate([p[2] for p in parts])[:4]
         else:
             off = genotype.plan_stage(rng, ixs, threads)
             lm, lv = solve_stage_sharded(backend, st, ixs, off, wrng, comm)

@@ -109,6 +109,7 @@ SYMBOLS = {
     "lctp_solve_stage": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P, _P, _P, _P, _P, _P, C.c_uint64, _P, _P]),
     "lctp_rng_seed_from_u64": (None, [_P, C.c_uint64]),
     "lctp_rng_jump": (None, [_P]),
+    "lctp_rng_worker_streams": (None, [_P, C.c_size_t, _P]),
     "lctp_rng_long_jump": (None, [_P]),
     "lctp_plan_stage": (C.c_size_t, [_P, _P, C.c_size_t, C.c_size_t, _P]),
     "lctp_discard_improbable": (C.c_size_t, [_P, C.c_size_t, _P, _P, _P, C.c_double, C.c_size_t, C.c_size_t]),

@@ -195,6 +195,14 @@ def rng_jump(state: np.ndarray) -> None:
     ffi.load().lctp_rng_jump(state.ctypes.data)
 
 
+def worker_streams(state: np.ndarray, threads: int) -> np.ndarray:
+    """MainWorker::new (src/solvers/solve.rs:1007-1018): u64[threads, 4] worker states; `state` (the locus stream)
+    is advanced by `threads` jumps in place."""
+    out = np.zeros((int(threads), 4), dtype=np.uint64)
+    ffi.load().lctp_rng_worker_streams(state.ctypes.data, int(threads), out.ctypes.data)
+    return out
+
+
 class Context:
     """lctp_ctx: one per GPU (Send, not Sync)."""
 

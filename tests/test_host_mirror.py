@@ -138,3 +138,14 @@ def test_genotype_enumeration_order(oracle, small_locus):
         assert loc.genotype_tuple(g) == ref[g] and loc.genotype_index(ref[g]) == g
         oracle.lib().lcto_genotype_tuple(ol.ref, g, out)
         assert tuple(out[:loc.ploidy]) == ref[g]
+
+
+def test_worker_streams_equal_clone_and_jump():
+    """lctp_rng_worker_streams = MainWorker::new (solve.rs:1007-1018): worker w = clone of the locus stream, then jump."""
+    a = genotype.init_rng(321)
+    b = a.copy()
+    ws = genotype.worker_streams(a, 37)
+    for w in range(37):
+        assert np.array_equal(ws[w], b)
+        genotype.rng_jump(b)
+    assert np.array_equal(a, b)
