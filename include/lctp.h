@@ -134,7 +134,29 @@ typedef struct lctp_stats {
     uint64_t pairing_launches;
     uint64_t pairing_mates;        /* mate alignment records read */
     uint64_t pairing_pairs;        /* pair alignments written */
+    double   rescore_ms;           /* sum of the rescoring kernel durations (lctp_rescore_alignments) */
+    uint64_t rescore_launches;
+    uint64_t rescore_alns;         /* alignment records rescored */
+    uint64_t rescore_ops;          /* CIGAR operations read */
 } lctp_stats;
+
+/* Alignment records of one locus before pairing = the per-alignment part of PrelimAlignments::push
+ * (src/model/locs.rs:297-313): count_region_operations_fast (src/seq/aln.rs:298-317, clipping limited to the contig by
+ * limited_clipping :288-296, soft_clipping src/seq/cigar.rs:519-527), OperCounts::edit_distance
+ * (src/bg/err_prof.rs:73-79), ErrorProfile::ln_prob (:212-221) and the `save` decision (locs.rs:308).
+ * SURVEY 8(f) rank 2, first slice; the order-dependent de-duplication of alignment starts (PosCollection,
+ * locs.rs:315-343) stays with the caller, which consumes `save` / `ln_prob` in record order. */
+typedef struct lctp_alns {
+    uint64_t n_alns;
+    const uint64_t *cigar_off;     /* [n_alns+1] into cigar_ops; every alignment has >= 1 operation */
+    const uint32_t *cigar_ops;     /* BAM encoding len << 4 | op; op 1=I 2=D 4=S 7='=' 8=X.  M, N, H, P are rejected like the
+                                      reference's panic "Unsupported CIGAR operation" (extended CIGARs only) */
+    const uint32_t *aln_start;     /* [n_alns] reference interval of the alignment on its contig */
+    const uint32_t *aln_end;       /* [n_alns] */
+    const uint32_t *contig_len;    /* [n_alns] ContigNames::get_len(aln.contig_id()) */
+    const uint32_t *passable_dist; /* [n_alns] PrelimAlignments::passable_dist of the alignment's read end */
+    double ln_match, ln_mismatch, ln_insertion, ln_deletion, ln_clipping;   /* ErrorProfile::oper_probs */
+} lctp_alns;
 
 /* Mate alignments of R read pairs = the input of identify_paired_end_alignments (src/model/locs.rs:805-868):
  * per read sorted by contig ascending, first read end before second, ln_prob descending within an end (the
@@ -199,6 +221,13 @@ int  lctp_pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uin
                           uint32_t *pa_contig, double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2,
                           double *unmapped_prob, uint64_t *n_out);
 size_t lctp_sizeof_mates(void);
+/* SURVEY 8(f) rank 2, first slice: rescore every alignment record under the error profile on the device.
+ * Outputs (caller-allocated, n_alns entries each): ln_prob = Alignment::set_ln_prob value, edit / read_len =
+ * EditDist{edit, read_len}, save = (edit <= passable_dist).  LCTP_E_INVALID on an empty CIGAR or an unsupported
+ * operation (the reference panics). */
+int  lctp_rescore_alignments(lctp_ctx *ctx, const lctp_alns *in, double *ln_prob, uint32_t *edit,
+                             uint32_t *read_len, uint8_t *save);
+size_t lctp_sizeof_alns(void);
 
 /* ---- prefilter (a2 + a3) ------------------------------------------------------------------ */
 /* Scores of genotypes [g_begin, g_end) (src/solvers/solve.rs:105-119) computed on the device into the

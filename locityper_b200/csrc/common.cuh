@@ -175,6 +175,9 @@ int prefilter_plan_check(uint32_t H, uint32_t n_sm, const uint32_t *pattern, uin
 int pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig,
                     double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob,
                     uint64_t *n_out);
+// rescore.cu
+int rescore_alignments(lctp_ctx *ctx, const lctp_alns *in, double *ln_prob, uint32_t *edit, uint32_t *read_len,
+                       uint8_t *save);
 // solver.cu
 int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_ixs,
                  const uint64_t *worker_off, size_t n_workers, uint64_t *worker_rng,

@@ -406,6 +406,21 @@ int lctp_get_stats(lctp_ctx *ctx, lctp_stats *out, int reset) {
 }
 
 size_t lctp_sizeof_mates(void) { return sizeof(lctp_mates); }
+size_t lctp_sizeof_alns(void) { return sizeof(lctp_alns); }
+
+int lctp_rescore_alignments(lctp_ctx *ctx, const lctp_alns *in, double *ln_prob, uint32_t *edit, uint32_t *read_len,
+                            uint8_t *save) {
+    if (!ctx || !in) { set_error("lctp_rescore_alignments: NULL argument"); return LCTP_E_INVALID; }
+    if (in->n_alns && (!in->cigar_off || !in->cigar_ops || !in->aln_start || !in->aln_end || !in->contig_len ||
+                       !in->passable_dist || !ln_prob || !edit || !read_len || !save)) {
+        set_error("lctp_rescore_alignments: NULL array");
+        return LCTP_E_INVALID;
+    }
+    if (in->n_alns && in->cigar_off[in->n_alns] < in->cigar_off[0]) { set_error("lctp_rescore_alignments: cigar_off not ascending"); return LCTP_E_INVALID; }
+    LCTP_CUDA_CHECK(cudaSetDevice(ctx->device));
+    set_alloc_stream(ctx->stream);
+    return rescore_alignments(ctx, in, ln_prob, edit, read_len, save);
+}
 
 int lctp_pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig,
                          double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob,

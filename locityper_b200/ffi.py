@@ -72,7 +72,9 @@ class StatsC(C.Structure):
                 ("stage_ms", C.c_double), ("stage_launches", C.c_uint64), ("stage_genotypes", C.c_uint64),
                 ("stage_attempts", C.c_uint64), ("stage_iters", C.c_uint64), ("stage_alns", C.c_uint64),
                 ("pairing_ms", C.c_double), ("pairing_launches", C.c_uint64), ("pairing_mates", C.c_uint64),
-                ("pairing_pairs", C.c_uint64)]
+                ("pairing_pairs", C.c_uint64),
+                ("rescore_ms", C.c_double), ("rescore_launches", C.c_uint64), ("rescore_alns", C.c_uint64),
+                ("rescore_ops", C.c_uint64)]
 
 
 class MatesC(C.Structure):
@@ -81,6 +83,13 @@ class MatesC(C.Structure):
                 ("ma_end", C.c_void_p), ("ma_ln_prob", C.c_void_p), ("read_weight", C.c_void_p),
                 ("ins_ln_pmf", C.c_void_p),
                 ("unmapped_penalty", C.c_double), ("insert_penalty", C.c_double), ("prob_diff", C.c_double)]
+
+
+class AlnsC(C.Structure):
+    _fields_ = [("n_alns", C.c_uint64), ("cigar_off", C.c_void_p), ("cigar_ops", C.c_void_p), ("aln_start", C.c_void_p),
+                ("aln_end", C.c_void_p), ("contig_len", C.c_void_p), ("passable_dist", C.c_void_p),
+                ("ln_match", C.c_double), ("ln_mismatch", C.c_double), ("ln_insertion", C.c_double),
+                ("ln_deletion", C.c_double), ("ln_clipping", C.c_double)]
 
 
 # Every symbol include/lctp.h declares: name -> (restype, argtypes)
@@ -100,6 +109,8 @@ SYMBOLS = {
     "lctp_prefilter_plan_check": (C.c_int, [C.c_uint32, C.c_uint32, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P, _P, _P]),
     "lctp_pair_alignments": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P]),
     "lctp_sizeof_mates": (C.c_size_t, []),
+    "lctp_rescore_alignments": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "lctp_sizeof_alns": (C.c_size_t, []),
     "lctp_locus_upload": (C.c_int, [_P, _P, _P]),
     "lctp_locus_free": (None, [_P]),
     "lctp_best_aln_matrix": (C.c_int, [_P, _P]),
@@ -149,6 +160,7 @@ def load():
         assert lib.lctp_sizeof_stage() == C.sizeof(StageC)
         assert lib.lctp_sizeof_result() == C.sizeof(ResultC)
         assert lib.lctp_sizeof_mates() == C.sizeof(MatesC)
+        assert lib.lctp_sizeof_alns() == C.sizeof(AlnsC)
         _lib = lib
     return _lib
 

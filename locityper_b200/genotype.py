@@ -307,6 +307,55 @@ def pair_alignments(ctx: "Context", mates: Mates, cap: Optional[int] = None) -> 
                 pa_mid1=pa_mid1[:n].copy(), pa_mid2=pa_mid2[:n].copy(), unmapped_prob=unm)
 
 
+@dataclass
+class Alns:
+    """Alignment records of one locus before pairing: the input of the per-alignment part of
+    PrelimAlignments::push (src/model/locs.rs:297-313).  cigar_ops are BAM-encoded (len << 4 | op; 1=I 2=D 4=S 7='='
+    8=X); `ln_oper` = ErrorProfile::oper_probs (ln of match, mismatch, insertion, deletion, clipping)."""
+
+    cigar_off: np.ndarray
+    cigar_ops: np.ndarray
+    aln_start: np.ndarray
+    aln_end: np.ndarray
+    contig_len: np.ndarray
+    passable_dist: np.ndarray
+    ln_oper: tuple
+
+    @property
+    def n_alns(self) -> int:
+        return len(self.aln_start)
+
+    def to_c(self, keep: list, struct=None):
+        def arr(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data
+        c = (struct or ffi.AlnsC)()
+        c.n_alns = self.n_alns
+        c.cigar_off = arr(self.cigar_off, np.uint64)
+        c.cigar_ops = arr(self.cigar_ops, np.uint32)
+        c.aln_start = arr(self.aln_start, np.uint32)
+        c.aln_end = arr(self.aln_end, np.uint32)
+        c.contig_len = arr(self.contig_len, np.uint32)
+        c.passable_dist = arr(self.passable_dist, np.uint32)
+        c.ln_match, c.ln_mismatch, c.ln_insertion, c.ln_deletion, c.ln_clipping = (float(v) for v in self.ln_oper)
+        return c
+
+
+def rescore_alignments(ctx: "Context", alns: Alns) -> dict:
+    """lctp_rescore_alignments: ln_prob / EditDist / save of every alignment record, computed on the device."""
+    keep: list = []
+    a = alns.to_c(keep)
+    n = alns.n_alns
+    ln_prob = np.zeros(n, dtype=np.float64)
+    edit = np.zeros(n, dtype=np.uint32)
+    read_len = np.zeros(n, dtype=np.uint32)
+    save = np.zeros(n, dtype=np.uint8)
+    ffi.check(ctx.lib.lctp_rescore_alignments(ctx._h, C.byref(a), ln_prob.ctypes.data, edit.ctypes.data,
+                                              read_len.ctypes.data, save.ctypes.data))
+    return dict(ln_prob=ln_prob, edit=edit, read_len=read_len, save=save)
+
+
 class ContextPool:
     """K contexts (one CUDA stream each) on one GPU, one host thread per context.  Loci are independent
     units of work (src/command/genotype.rs:1331-1351: one `analyze_locus` per locus, separate long_jump

@@ -435,3 +435,54 @@ def make_mates(n_haps: int, n_reads: int, locus_len: int, seed: int, *, multi_fr
                 ma_end=end[order].astype(np.uint32), ma_ln_prob=ln_prob[order].astype(np.float64),
                 ins_ln_pmf=ins_ln_pmf, unmapped_penalty=U, insert_penalty=float(ins_ln_pmf.max()),
                 prob_diff=abs(U) + LN10, read_weight=weight.astype(np.float64), max_alns=max_alns)
+
+
+def make_alns(n_alns: int, seed: int, *, tech: str = "illumina", contig_len: int = 3500) -> dict:
+    """Synthetic alignment records (keyword arguments of `genotype.Alns`): extended CIGARs of 1-12 operations
+    ([S] (=|X|I|D)* [S]; some all-soft single-operation records, some clipped at a contig end so that
+    limited_clipping bites), intervals consistent with the CIGARs, error profile of the technology
+    (src/bg/err_prof.rs:88-109), passable edit distance around the typical edit count."""
+    rng = np.random.default_rng(seed)
+    read_len = 150 if tech == "illumina" else 12000
+    n_mid = rng.integers(1, 11, n_alns)
+    has_l = rng.random(n_alns) < 0.25
+    has_r = rng.random(n_alns) < 0.25
+    all_soft = rng.random(n_alns) < 0.01
+    counts = np.where(all_soft, 1, n_mid + has_l + has_r)
+    off = np.zeros(n_alns + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(counts)
+    ops = np.zeros(int(off[-1]), dtype=np.uint32)
+    start = np.zeros(n_alns, dtype=np.uint32)
+    end = np.zeros(n_alns, dtype=np.uint32)
+    mid_codes = np.array([7, 7, 7, 8, 1, 2], dtype=np.uint32)          # '=' three times as likely as X / I / D
+    for i in range(n_alns):
+        b = int(off[i])
+        if all_soft[i]:
+            ops[b] = (read_len << 4) | 4
+            ref = 0
+        else:
+            q = b
+            if has_l[i]:
+                ops[q] = (int(rng.integers(1, 40)) << 4) | 4
+                q += 1
+            codes = mid_codes[rng.integers(0, len(mid_codes), n_mid[i])]
+            codes[0] = 7
+            lens = np.where(codes == 7, rng.integers(5, read_len // 2, n_mid[i]), rng.integers(1, 6, n_mid[i]))
+            ops[q:q + n_mid[i]] = (lens.astype(np.uint32) << 4) | codes
+            q += n_mid[i]
+            if has_r[i]:
+                ops[q] = (int(rng.integers(1, 40)) << 4) | 4
+            ref = int(lens[(codes == 7) | (codes == 8) | (codes == 2)].sum())
+        edge = rng.random()
+        if edge < 0.1:
+            s0 = int(rng.integers(0, 20))                              # near the contig start: left clipping is limited
+        elif edge < 0.2:
+            s0 = max(0, contig_len - ref - int(rng.integers(0, 20)))   # near the contig end
+        else:
+            s0 = int(rng.integers(0, max(1, contig_len - ref)))
+        start[i], end[i] = s0, s0 + ref
+    p_match, p_mm = (0.995, 0.003) if tech == "illumina" else (0.998, 0.001)
+    ln_oper = (np.log(p_match), np.log(p_mm), np.log(p_mm / 2), np.log(p_mm / 3), np.log(p_mm))
+    return dict(cigar_off=off, cigar_ops=ops, aln_start=start, aln_end=end,
+                contig_len=np.full(n_alns, contig_len, dtype=np.uint32),
+                passable_dist=rng.integers(0, 60, n_alns).astype(np.uint32), ln_oper=ln_oper)

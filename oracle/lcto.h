@@ -236,6 +236,18 @@ typedef struct lcto_mates {
 int lcto_pair_alignments(const lcto_mates *in, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig,
                          double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob);
 
+/* ------------------------------------------------ alignment rescoring (lcto_rescore.c; SURVEY 8(f) rank 2, first slice) */
+
+typedef struct lcto_alns {
+    uint64_t n_alns;
+    const uint64_t *cigar_off;     /* [n_alns+1] */
+    const uint32_t *cigar_ops;     /* BAM encoding len << 4 | op (1=I 2=D 4=S 7='=' 8=X) */
+    const uint32_t *aln_start, *aln_end, *contig_len, *passable_dist;   /* [n_alns] each */
+    double ln_match, ln_mismatch, ln_insertion, ln_deletion, ln_clipping;
+} lcto_alns;
+
+int lcto_rescore_alignments(const lcto_alns *in, double *ln_prob, uint32_t *edit, uint32_t *read_len, uint8_t *save);
+
 #ifdef __cplusplus
 }
 #endif

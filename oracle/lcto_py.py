@@ -161,6 +161,8 @@ def lib():
                                  C.c_void_p, C.c_void_p, C.c_void_p]
         L.lcto_pair_alignments.restype = C.c_int
         L.lcto_pair_alignments.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 6
+        L.lcto_rescore_alignments.restype = C.c_int
+        L.lcto_rescore_alignments.argtypes = [C.c_void_p] * 5
         L.lcto_version.restype = C.c_char_p
         _lib = L
     return _lib
@@ -354,3 +356,26 @@ def pair_alignments(mates) -> dict:
     n = int(pa_off[R])
     return dict(pa_off=pa_off, pa_contig=pa_contig[:n].copy(), pa_ln_prob=pa_ln_prob[:n].copy(),
                 pa_mid1=pa_mid1[:n].copy(), pa_mid2=pa_mid2[:n].copy(), unmapped_prob=unm)
+
+
+class AlnsC(C.Structure):
+    _fields_ = [("n_alns", C.c_uint64), ("cigar_off", C.c_void_p), ("cigar_ops", C.c_void_p), ("aln_start", C.c_void_p),
+                ("aln_end", C.c_void_p), ("contig_len", C.c_void_p), ("passable_dist", C.c_void_p),
+                ("ln_match", C.c_double), ("ln_mismatch", C.c_double), ("ln_insertion", C.c_double),
+                ("ln_deletion", C.c_double), ("ln_clipping", C.c_double)]
+
+
+def rescore_alignments(alns) -> dict:
+    """lcto_rescore_alignments on a locityper_b200.genotype.Alns-shaped object (plain data)."""
+    keep: list = []
+    a = alns.to_c(keep, struct=AlnsC)
+    n = alns.n_alns
+    ln_prob = np.zeros(n, dtype=np.float64)
+    edit = np.zeros(n, dtype=np.uint32)
+    read_len = np.zeros(n, dtype=np.uint32)
+    save = np.zeros(n, dtype=np.uint8)
+    rc = lib().lcto_rescore_alignments(C.byref(a), ln_prob.ctypes.data, edit.ctypes.data, read_len.ctypes.data,
+                                       save.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"lcto_rescore_alignments failed: {rc}")
+    return dict(ln_prob=ln_prob, edit=edit, read_len=read_len, save=save)
