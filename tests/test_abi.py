@@ -50,6 +50,23 @@ def test_product_package_never_imports_the_oracle():
                 assert "lcto" not in text and "from oracle" not in text and "import oracle" not in text, f
 
 
+def test_only_tests_smoke_and_the_bench_cpu_arm_touch_the_oracle():
+    """oracle/ is test infrastructure: besides tests/, only __graft_entry__.smoke()/build() and bench.py's CPU arm
+    (cpu_baseline / --impl reference) may import it; the developer tools under tools/ must not."""
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith((".py", ".sh")):
+            text = open(os.path.join(ROOT, "tools", f)).read()
+            assert "lcto" not in text and "from oracle" not in text and "import oracle" not in text, f
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    for i, line in enumerate(bench.split("\n")):
+        if "from oracle" in line or "import oracle" in line:
+            # every import of the oracle sits inside the CPU arm: cpu_run() (one oracle pass, used by cpu_baseline
+            # and by --impl reference) or run_reference() (the --impl reference leg itself)
+            head = bench.split("\n")[:i]
+            fn = [l for l in head if l.startswith("def ")][-1]
+            assert fn.startswith(("def cpu_run(", "def run_reference(")), (i, fn)
+
+
 def test_invalid_arguments_return_error_codes():
     L = ffi.load()
     assert L.lctp_init(None, None) == ffi.E_INVALID

@@ -137,3 +137,24 @@ def test_device_pairs_feed_the_locus_upload(oracle, gpu_ctx, small_locus):
     assert np.array_equal(dl.best_aln_matrix(), oracle.best_aln_matrix(ol))
     assert np.array_equal(dl.prefilter_scores(), oracle.prefilter_scores(ol))
     dl.free()
+
+
+@pytest.mark.gpu
+def test_device_vs_oracle_timing_report(oracle, gpu_ctx, capsys):
+    """Not an assertion on speed: prints kernel / whole-call / single-thread oracle times at the C2 shape (run with
+    -s); the oracle may only be executed from tests/, so the comparison lives here rather than in tools/pairs_run.py."""
+    import time
+    m = genotype.Mates(**synth.make_mates(300, 2000, 3500, 5))
+    genotype.pair_alignments(gpu_ctx, m)
+    gpu_ctx.stats(reset=True)
+    t0 = time.perf_counter()
+    got = genotype.pair_alignments(gpu_ctx, m)
+    wall = time.perf_counter() - t0
+    st = gpu_ctx.stats(reset=True)
+    t1 = time.perf_counter()
+    ref = oracle.pair_alignments(m)
+    cpu = time.perf_counter() - t1
+    assert all(np.array_equal(got[k], ref[k]) for k in got)
+    with capsys.disabled():
+        print(f"\n[pairs] {len(m.ma_contig)} mate records: kernels {st['pairing_ms']:.3f} ms, whole call {wall*1e3:.1f} ms, "
+              f"oracle (1 thread) {cpu*1e3:.1f} ms")

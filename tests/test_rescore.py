@@ -130,3 +130,23 @@ def test_device_rescoring_hand_checked_and_errors(oracle, gpu_ctx):
         genotype.rescore_alignments(gpu_ctx, bad)
     empty = genotype.Alns(**synth.make_alns(0, 1))
     assert len(genotype.rescore_alignments(gpu_ctx, empty)["ln_prob"]) == 0
+
+
+@pytest.mark.gpu
+def test_device_vs_oracle_timing_report(oracle, gpu_ctx, capsys):
+    """Not an assertion on speed: prints kernel / whole-call / single-thread oracle times (run with -s); the oracle
+    may only be executed from tests/, so the timing comparison lives here rather than in tools/rescore_run.py."""
+    import time
+    a = genotype.Alns(**synth.make_alns(300_000, 21))
+    genotype.rescore_alignments(gpu_ctx, a)
+    gpu_ctx.stats(reset=True)
+    t0 = time.perf_counter()
+    got = genotype.rescore_alignments(gpu_ctx, a)
+    wall = time.perf_counter() - t0
+    st = gpu_ctx.stats(reset=True)
+    t1 = time.perf_counter()
+    ref = oracle.rescore_alignments(a)
+    cpu = time.perf_counter() - t1
+    assert _same(got, ref)
+    with capsys.disabled():
+        print(f"\n[rescore] 300k records: kernel {st['rescore_ms']:.3f} ms, whole call {wall*1e3:.1f} ms, oracle (1 thread) {cpu*1e3:.1f} ms")

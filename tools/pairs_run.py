@@ -8,7 +8,6 @@ from locityper_b200 import genotype, synth
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="C2")
 ap.add_argument("--passes", type=int, default=4)
-ap.add_argument("--cpu", action="store_true", help="also time the oracle (single thread)")
 a = ap.parse_args()
 sh = synth.config_shape(a.config)
 t0 = time.time()
@@ -29,11 +28,3 @@ pairs = len(out["pa_contig"])
 bytes_alg = 2 * N * (4 + 1 + 4 + 4 + 8) + pairs * (4 + 8 + 4 + 4) + N * 12   # two passes over the records + output + counts/offsets
 print(f"pairing kernels: {ms:.3f} ms/call, {N/ms/1e6:.2f} G mates/s, {bytes_alg/ms/1e6:.1f} GB/s algorithmic; "
       f"{pairs} pair alignments; whole call incl. H2D/D2H {wall*1e3:.1f} ms")
-if a.cpu:
-    from oracle import lcto_py as O
-    O.pair_alignments(m)
-    t1 = time.time()
-    ref = O.pair_alignments(m)
-    dt = time.time() - t1
-    print(f"oracle (1 thread): {dt*1e3:.1f} ms, {N/dt/1e6:.3f} M mates/s; identical: "
-          f"{all(np.array_equal(out[k], ref[k]) for k in out)}")

@@ -8,7 +8,6 @@ from locityper_b200 import genotype, synth
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=1_500_000, help="alignment records (C2: ~1.5 M mates per locus)")
 ap.add_argument("--passes", type=int, default=5)
-ap.add_argument("--cpu", action="store_true", help="also time the single-thread oracle")
 a = ap.parse_args()
 t0 = time.time()
 al = genotype.Alns(**synth.make_alns(a.n, 7))
@@ -25,10 +24,3 @@ ms = st["rescore_ms"] / max(1, st["rescore_launches"])
 bytes_alg = len(al.cigar_ops) * 4 + a.n * (8 + 16) + a.n * 17
 print(f"rescoring kernel: {ms:.4f} ms/launch, {a.n/ms/1e6:.2f} G alignments/s, {bytes_alg/ms/1e6:.1f} GB/s algorithmic; "
       f"whole call incl. H2D/D2H {wall*1e3:.1f} ms")
-if a.cpu:
-    from oracle import lcto_py as O
-    O.rescore_alignments(al)
-    t2 = time.time()
-    ref = O.rescore_alignments(al)
-    dt = time.time() - t2
-    print(f"oracle (1 thread): {dt*1e3:.1f} ms; identical: {all(np.array_equal(out[k], ref[k]) for k in out)}")
