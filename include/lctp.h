@@ -150,7 +150,8 @@ typedef struct lctp_alns {
     uint64_t n_alns;
     const uint64_t *cigar_off;     /* [n_alns+1] into cigar_ops; every alignment has >= 1 operation */
     const uint32_t *cigar_ops;     /* BAM encoding len << 4 | op; op 1=I 2=D 4=S 7='=' 8=X.  M, N, H, P are rejected like the
-                                      reference's panic "Unsupported CIGAR operation" (extended CIGARs only) */
+                                      reference's panic "Unsupported CIGAR operation" (extended CIGARs only; secondary
+                                      records after Cigar::hard_to_soft, locs.rs:548) */
     const uint32_t *aln_start;     /* [n_alns] reference interval of the alignment on its contig */
     const uint32_t *aln_end;       /* [n_alns] */
     const uint32_t *contig_len;    /* [n_alns] ContigNames::get_len(aln.contig_id()) */
