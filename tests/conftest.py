@@ -32,3 +32,29 @@ def gpu_ctx():
     ctx = genotype.Context(device=0)
     yield ctx
     ctx.close()
+
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden_mates():
+    """(genotype.Mates, expected outputs) of tests/golden/pairs_small.npz (made by tests/golden/make_golden.py)."""
+    import numpy as np
+    from locityper_b200 import genotype
+    z = np.load(os.path.join(GOLDEN_DIR, "pairs_small.npz"))
+    sc = z["_scalars"]
+    m = genotype.Mates(n_reads=int(sc[0]), n_haps=int(sc[1]), max_alns=int(sc[2]), unmapped_penalty=float(sc[3]),
+                       insert_penalty=float(sc[4]), prob_diff=float(sc[5]), ma_off=z["ma_off"], ma_contig=z["ma_contig"],
+                       ma_flags=z["ma_flags"], ma_start=z["ma_start"], ma_end=z["ma_end"], ma_ln_prob=z["ma_ln_prob"],
+                       ins_ln_pmf=z["ins_ln_pmf"], read_weight=z["read_weight"])
+    return m, {k[4:]: z[k] for k in z.files if k.startswith("out_")}
+
+
+def load_golden_alns():
+    """(genotype.Alns, expected outputs) of tests/golden/rescore_small.npz."""
+    import numpy as np
+    from locityper_b200 import genotype
+    z = np.load(os.path.join(GOLDEN_DIR, "rescore_small.npz"))
+    a = genotype.Alns(cigar_off=z["cigar_off"], cigar_ops=z["cigar_ops"], aln_start=z["aln_start"], aln_end=z["aln_end"],
+                      contig_len=z["contig_len"], passable_dist=z["passable_dist"], ln_oper=tuple(z["ln_oper"]))
+    return a, {k[4:]: z[k] for k in z.files if k.startswith("out_")}

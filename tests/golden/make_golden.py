@@ -111,7 +111,32 @@ def make_case(name, spec):
     return out
 
 
+MATES_FIELDS = ("ma_off", "ma_contig", "ma_flags", "ma_start", "ma_end", "ma_ln_prob", "ins_ln_pmf", "read_weight")
+ALNS_FIELDS = ("cigar_off", "cigar_ops", "aln_start", "aln_end", "contig_len", "passable_dist")
+
+
+def make_upstream():
+    """Fixtures of the two upstream slices: inputs AND oracle outputs in one .npz each
+    (f64 arrays are stored raw, so the comparison is bit-exact)."""
+    from locityper_b200 import genotype
+    kw = synth.make_mates(6, 40, 2500, 424242, multi_frac=0.4)
+    kw["read_weight"] = np.linspace(0.5, 1.0, 40)
+    m = genotype.Mates(**kw)
+    out = O.pair_alignments(m)
+    scal = np.array([m.n_reads, m.n_haps, m.max_alns, m.unmapped_penalty, m.insert_penalty, m.prob_diff], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "pairs_small.npz"), _scalars=scal,
+                        **{k: np.asarray(getattr(m, k)) for k in MATES_FIELDS},
+                        **{"out_" + k: v for k, v in out.items()})
+    a = genotype.Alns(**synth.make_alns(600, 434343))
+    out = O.rescore_alignments(a)
+    np.savez_compressed(os.path.join(HERE, "rescore_small.npz"), ln_oper=np.array(a.ln_oper, dtype=np.float64),
+                        **{k: np.asarray(getattr(a, k)) for k in ALNS_FIELDS},
+                        **{"out_" + k: v for k, v in out.items()})
+    return len(m.ma_contig), a.n_alns
+
+
 if __name__ == "__main__":
     for name, spec in CASES.items():
         o = make_case(name, spec)
         print(name, "G =", o["n_genotypes"], "call =", o["solve"][-1]["gt_ix"][:1], "truth =", o["truth"])
+    print("upstream fixtures: %d mate records, %d alignment records" % make_upstream())

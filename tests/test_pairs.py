@@ -158,3 +158,20 @@ def test_device_vs_oracle_timing_report(oracle, gpu_ctx, capsys):
     with capsys.disabled():
         print(f"\n[pairs] {len(m.ma_contig)} mate records: kernels {st['pairing_ms']:.3f} ms, whole call {wall*1e3:.1f} ms, "
               f"oracle (1 thread) {cpu*1e3:.1f} ms")
+
+
+def test_oracle_reproduces_golden_pairs(oracle):
+    from conftest import load_golden_mates
+    m, want = load_golden_mates()
+    got = oracle.pair_alignments(m)
+    assert set(got) == set(want) and all(np.array_equal(got[k], want[k]) for k in want)
+    assert len(want["pa_contig"]) > 200
+
+
+@pytest.mark.gpu
+def test_device_reproduces_golden_pairs(gpu_ctx):
+    """No oracle at run time: the committed fixture (tests/golden/pairs_small.npz) is the reference."""
+    from conftest import load_golden_mates
+    m, want = load_golden_mates()
+    got = genotype.pair_alignments(gpu_ctx, m)
+    assert all(np.array_equal(got[k], want[k]) for k in want)

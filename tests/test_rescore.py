@@ -150,3 +150,17 @@ def test_device_vs_oracle_timing_report(oracle, gpu_ctx, capsys):
     assert _same(got, ref)
     with capsys.disabled():
         print(f"\n[rescore] 300k records: kernel {st['rescore_ms']:.3f} ms, whole call {wall*1e3:.1f} ms, oracle (1 thread) {cpu*1e3:.1f} ms")
+
+
+def test_oracle_reproduces_golden_rescoring(oracle):
+    from conftest import load_golden_alns
+    a, want = load_golden_alns()
+    assert _same(oracle.rescore_alignments(a), want) and a.n_alns == 600
+
+
+@pytest.mark.gpu
+def test_device_reproduces_golden_rescoring(gpu_ctx):
+    """No oracle at run time: the committed fixture (tests/golden/rescore_small.npz) is the reference."""
+    from conftest import load_golden_alns
+    a, want = load_golden_alns()
+    assert _same(genotype.rescore_alignments(gpu_ctx, a), want)
