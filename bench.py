@@ -363,6 +363,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
+            "loci_per_s": world * len(loci) * args.steps / (ms_total / 1e3),
         }
         line.update(rooflines(st_iso, loci, args, peak, peak_src, fp64_rate))
         line["roofline"]["in_step"] = {
@@ -424,7 +425,23 @@ def rooflines(st, loci, args, peak, peak_src, fp64_rate=None):
             out["roofline_prefilter"]["fp64"] = {
                 "achieved": ops / sec / 1e12, "peak": fp64_rate / 1e12, "unit": "T FP64-pipe lane-instructions/s",
                 "frac": ops / sec / fp64_rate, "peak_source": "DADD microbenchmark run live (lctp_measure_fp64_rate)"}
+    out["rates"] = kernel_rates(st)
     return out
+
+
+def kernel_rates(st) -> dict:
+    """the separately reported per-kernel rates, from the library's CUDA-event timings of the isolated
+    pass (one kernel at a time): prefilter genotypes/s, stage genotypes/s, genotype-attempts/s, iterations (greedy)
+    or steps (annealing) per second."""
+    r = {}
+    if st.get("prefilter_launches") and st.get("prefilter_ms", 0) > 0:
+        r["prefilter_genotypes_per_s"] = st["prefilter_genotypes"] / (st["prefilter_ms"] / 1e3)
+    if st.get("stage_launches") and st.get("stage_ms", 0) > 0:
+        sec = st["stage_ms"] / 1e3
+        r["stage_genotypes_per_s"] = st["stage_genotypes"] / sec
+        r["stage_genotype_attempts_per_s"] = st["stage_attempts"] / sec
+        r["stage_iterations_per_s"] = st["stage_iters"] / sec
+    return r
 
 
 def kir_prefilter(ctx, genotype, peak, fp64_rate):

@@ -35,3 +35,25 @@ def test_gpu_arm_fails_loudly_without_a_device():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_rooflines_and_rates_are_pure_functions_of_the_stats():
+    """bench.rooflines / kernel_rates only need the library's stats dictionary: exercised here without a GPU."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    st = dict(prefilter_ms=0.24, prefilter_launches=3, prefilter_genotypes=135450, stage_ms=30.4, stage_launches=3,
+              stage_genotypes=15000, stage_attempts=15000, stage_iters=22_000_000, stage_alns=160_000_000,
+              pairing_ms=0.0, pairing_launches=0, pairing_mates=0, pairing_pairs=0)
+    loc = types.SimpleNamespace(n_reads=2000, ploidy=2)
+    args = types.SimpleNamespace(config="C2")
+    out = bench.rooflines(st, [loc], args, 6550.7, "measured", fp64_rate=18.3e12)
+    assert set(out) >= {"roofline", "roofline_prefilter", "rates"}
+    assert 0 < out["roofline"]["frac"] < 1 and out["roofline"]["unit"] == "GB/s"
+    r = out["rates"]
+    assert abs(r["stage_genotypes_per_s"] - 15000 / 0.0304) < 1e-6 * r["stage_genotypes_per_s"]
+    assert abs(r["prefilter_genotypes_per_s"] - 135450 / 0.00024) < 1e-6 * r["prefilter_genotypes_per_s"]
+    assert r["stage_genotype_attempts_per_s"] == r["stage_genotypes_per_s"] and r["stage_iterations_per_s"] > 1e8
+    assert bench.kernel_rates(dict(prefilter_launches=0, stage_launches=0)) == {}
