@@ -129,3 +129,54 @@ def test_shard_range_and_local_candidates():
             dense[ids.astype(np.int64)] = sc
             merged = genotype.truncate_ixs(np.sort(ids), dense, filt_diff, min_size, threads)
             assert np.array_equal(merged, full)
+
+
+def _packed_main(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = ldist.Comm(rank, world)
+        # rank-dependent lengths (rank 1 sends nothing), three dtypes in one exchange
+        n = 0 if rank == 1 else 5 + 3 * rank
+        parts = comm.allgather_packed([np.arange(n, dtype=np.uint64) + 100 * rank,
+                                       np.linspace(0.0, 1.0, 2 * n) - rank,
+                                       np.full(rank, 7, dtype=np.uint8)])
+        single = comm.allgather_var(np.arange(rank + 1, dtype=np.float64))
+        q.put((rank, [[a.tolist() for a in p_] for p_ in parts], [a.tolist() for a in single], comm.bytes_gathered))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_packed_allgather_roundtrip_three_ranks():
+    """Comm.allgather_packed / allgather_var: rank-dependent lengths (including empty), mixed dtypes, one exchange."""
+    import torch.multiprocessing as mp
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_packed_main, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, parts, single, nbytes in outs:
+        assert len(parts) == world and nbytes > 0
+        for r in range(world):
+            n = 0 if r == 1 else 5 + 3 * r
+            assert parts[r][0] == (np.arange(n, dtype=np.uint64) + 100 * r).tolist()
+            assert parts[r][1] == (np.linspace(0.0, 1.0, 2 * n) - r).tolist()
+            assert parts[r][2] == [7] * r
+            assert single[r] == list(np.arange(r + 1, dtype=np.float64))
+
+
+def test_packed_allgather_single_rank_is_identity():
+    comm = ldist.Comm(0, 1)
+    a, b = np.arange(4, dtype=np.uint64), np.array([0.5, -1.25])
+    (got,) = comm.allgather_packed([a, b])
+    assert np.array_equal(got[0], a) and np.array_equal(got[1], b) and got[0].dtype == a.dtype
+    (one,) = comm.allgather_var(b)
+    assert np.array_equal(one, b)

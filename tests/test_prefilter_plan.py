@@ -61,3 +61,29 @@ def test_bad_arguments_are_rejected():
     assert lib.lctp_prefilter_plan_check(10, 148, None, 0, 0, 56, None, None, None) != 0
     bad = (C.c_uint32 * 1)(9)
     assert lib.lctp_prefilter_plan_check(10, 148, bad, 1, 0, 55, None, None, None) != 0
+
+
+def test_random_panels_ranges_and_patterns_property():
+    """Property (hypothesis): for any panel size, SM count, genotype sub-range and per-sub-partition pattern the plan
+    covers every genotype of the range exactly once with consistent staging tables (the check is exhaustive inside
+    lctp_prefilter_plan_check; hypothesis varies its inputs)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(H=st.integers(1, 700), n_sm=st.sampled_from([1, 7, 132, 148]),
+           pattern=st.one_of(st.none(), st.lists(st.integers(2, 8), min_size=1, max_size=4)),
+           cut=st.tuples(st.floats(0, 1), st.floats(0, 1)))
+    def prop(H, n_sm, pattern, cut):
+        from hypothesis import assume
+        assume(not pattern or sum(pattern) <= 20)      # wider regions can exceed the 256 staged chunks per read (no plan)
+        G = H * (H + 1) // 2
+        a, b = sorted(int(c * G) for c in cut)
+        b = max(b, a + 1)
+        if b > G:
+            a, b = G - 1, G
+        n_regions, load, pat = _check(H, n_sm=n_sm, pattern=pattern, g_begin=a, g_end=b)
+        assert n_regions >= 1 and load == sum(pat)
+        if pattern:
+            assert pat == pattern
+
+    prop()
