@@ -17,6 +17,7 @@
 #include <cstring>
 #include <limits>
 #include <numeric>
+#include <functional>
 
 namespace lctp {
 
@@ -293,7 +294,13 @@ static inline int64_t total_key(double v) {
 // Descending by key with f64::total_cmp; equal keys keep their current order (the reference uses
 // sort_unstable_by, whose tie order is unspecified -- see DESIGN.md "unpinned behaviour").
 static void sort_desc_stable(uint64_t *ixs, size_t n, const double *key) {
-    std::stable_sort(ixs, ixs + n, [key](uint64_t a, uint64_t b) { return total_key(key[a]) > total_key(key[b]); });
+    // (key, current position) pairs sorted with a total order = the stable order, without an indirect load per compare
+    struct Kp { int64_t k; uint64_t pos, ix; };
+    static thread_local std::vector<Kp> kv;
+    kv.resize(n);
+    for (size_t q = 0; q < n; q++) kv[q] = Kp{total_key(key[ixs[q]]), q, ixs[q]};
+    std::sort(kv.begin(), kv.end(), [](const Kp &a, const Kp &b) { return a.k != b.k ? a.k > b.k : a.pos < b.pos; });
+    for (size_t q = 0; q < n; q++) ixs[q] = kv[q].ix;
 }
 
 // compare_two_likelihoods (src/solvers/solve.rs:319-336) with the t-tests of src/math/mod.rs:180-220
@@ -507,33 +514,80 @@ int lctp_prefilter_scores(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, dou
     return LCTP_OK;
 }
 
+// k-th largest (1-based) of key[0..n), all keys in [kmin, kmax]: one histogram pass over linear bins of the actual
+// key range, then nth_element inside the one bin that holds the answer (std::nth_element over all n costs 6 ms at
+// n = 500,500; this is two streaming passes).
+static int64_t kth_largest_key(const int64_t *key, size_t n, size_t k, int64_t kmin, int64_t kmax) {
+    int bits = 8;                                                        // ~n/8 bins, 256 .. 65,536
+    while (bits < 16 && (size_t(1) << (bits + 3)) < n) bits++;
+    const uint64_t range = (uint64_t)kmax - (uint64_t)kmin;              // exact in unsigned arithmetic
+    int shift = 0;
+    while ((range >> shift) >= (1ull << bits)) shift++;
+    static thread_local std::vector<uint32_t> hist;
+    hist.assign((size_t)(range >> shift) + 1, 0);
+    for (size_t q = 0; q < n; q++) hist[((uint64_t)key[q] - (uint64_t)kmin) >> shift]++;
+    size_t above = 0, bin = hist.size() - 1;
+    for (;; bin--) {
+        if (above + hist[bin] >= k) break;
+        above += hist[bin];
+        if (bin == 0) break;                                             // k <= n guarantees we stop before
+    }
+    static thread_local std::vector<int64_t> cand;
+    cand.clear();
+    for (size_t q = 0; q < n; q++)
+        if ((((uint64_t)key[q] - (uint64_t)kmin) >> shift) == bin) cand.push_back(key[q]);
+    const size_t r = k - above;                                          // r-th largest inside the bin, 1-based
+    std::nth_element(cand.begin(), cand.begin() + (r - 1), cand.end(), std::greater<int64_t>());
+    return cand[r - 1];
+}
+
+static inline double key_to_double(int64_t k) {         // inverse of total_key (the transform is an involution)
+    const int64_t b = k ^ (int64_t)(((uint64_t)(k >> 63)) >> 1);
+    double v;
+    std::memcpy(&v, &b, 8);
+    return v;
+}
+
 size_t lctp_truncate_ixs(uint64_t *ixs, size_t n, const double *scores, double filt_diff, size_t min_size,
                          size_t threads) {
     if (n == 0) return 0;
-    // Reference: sort all, then cut (solve.rs:60-81).  Equivalent and much cheaper for large n: find the
-    // cut first, partition the survivors to the front (keeping their order), sort only those.
+    // Reference: sort all, then cut (solve.rs:60-81).  Equivalent and much cheaper for large n: find the cut first,
+    // gather the survivors (keeping their order), sort only those.  The list is read ONCE into contiguous
+    // (value, total_cmp key) arrays; every later pass streams those (G = 500,500 at the KIR scale).
+    // scratch that outlives the call: fresh 8 MB vectors cost more in page faults than the passes over them
+    static thread_local std::vector<double> val_tl;
+    static thread_local std::vector<int64_t> key_tl;
+    if (val_tl.size() < n) { val_tl.resize(n); key_tl.resize(n); }
+    double *val = val_tl.data();
+    int64_t *key = key_tl.data();
     bool ascending = true;
-    for (size_t q = 1; q < n && ascending; q++) ascending = ixs[q - 1] < ixs[q];
-    double best = scores[ixs[0]], worst = best;
-    for (size_t q = 1; q < n; q++) {
-        const double v = scores[ixs[q]];
-        if (total_key(v) > total_key(best)) best = v;
-        if (total_key(v) < total_key(worst)) worst = v;
+    int64_t kbest, kworst;
+    {
+        const double v0 = scores[ixs[0]];
+        val[0] = v0; key[0] = kbest = kworst = total_key(v0);
+        uint64_t prev = ixs[0];
+        for (size_t q = 1; q < n; q++) {
+            const uint64_t ix = ixs[q];
+            ascending &= prev < ix;
+            prev = ix;
+            const double v = scores[ix];
+            const int64_t k = total_key(v);
+            val[q] = v; key[q] = k;
+            kbest = std::max(kbest, k); kworst = std::min(kworst, k);
+        }
     }
+    const double best = key_to_double(kbest), worst = key_to_double(kworst);
     double thresh = best - filt_diff;
-    size_t m;
+    auto count_ge = [&](double th) { size_t c = 0; for (size_t q = 0; q < n; q++) c += val[q] >= th; return c; };
+    size_t m, n_ge = n;
     if (min_size >= n || worst >= thresh) m = n;
     else {
-        auto count_ge = [&](double th) { size_t c = 0; for (size_t q = 0; q < n; q++) c += scores[ixs[q]] >= th; return c; };
         m = count_ge(thresh);
         if (m < min_size) {
-            std::vector<double> tmp(n);
-            for (size_t q = 0; q < n; q++) tmp[q] = scores[ixs[q]];
-            std::nth_element(tmp.begin(), tmp.begin() + (min_size - 1), tmp.end(),
-                             [](double a, double b) { return total_key(a) > total_key(b); });
-            thresh = tmp[min_size - 1];
+            thresh = key_to_double(kth_largest_key(key, n, min_size, kworst, kbest));
             m = count_ge(thresh);
         }
+        n_ge = m;                                  // #{score >= thresh} for the final threshold
         m = std::min(std::max(m, threads), n);
     }
     if (m == n || !ascending) {   // nothing to gain, or arbitrary input order: literal restatement
@@ -543,19 +597,20 @@ size_t lctp_truncate_ixs(uint64_t *ixs, size_t n, const double *scores, double f
     // the m best under (score desc, input order asc): everything >= the m-th best key, ties by position
     std::vector<uint64_t> keep;
     keep.reserve(m + 16);
-    const size_t n_ge = [&] { size_t c = 0; for (size_t q = 0; q < n; q++) c += scores[ixs[q]] >= thresh; return c; }();
     if (n_ge >= m) {
         // m was not raised by `threads`: survivors are exactly {score >= thresh} (m == n_ge)
-        for (size_t q = 0; q < n; q++) if (scores[ixs[q]] >= thresh) keep.push_back(ixs[q]);
+        for (size_t q = 0; q < n; q++) if (val[q] >= thresh) keep.push_back(ixs[q]);
     } else {
-        // raised to `threads`: take the m best overall
-        std::vector<uint64_t> all(ixs, ixs + n);
-        std::nth_element(all.begin(), all.begin() + (m - 1), all.end(), [&](uint64_t a, uint64_t b) {
-            const int64_t ka = total_key(scores[a]), kb = total_key(scores[b]);
-            return ka != kb ? ka > kb : a < b;
-        });
-        keep.assign(all.begin(), all.begin() + m);
-        std::sort(keep.begin(), keep.end());
+        // raised to `threads`: take the m best overall (key desc, id asc)
+        // = every id with key > k_m, plus the first (in id order = list order) m - #above of those with key == k_m
+        const int64_t km = kth_largest_key(key, n, m, kworst, kbest);
+        size_t above = 0;
+        for (size_t q = 0; q < n; q++) above += key[q] > km;
+        size_t ties_left = m - above;
+        for (size_t q = 0; q < n; q++) {
+            if (key[q] > km) keep.push_back(ixs[q]);
+            else if (key[q] == km && ties_left) { keep.push_back(ixs[q]); ties_left--; }
+        }
     }
     sort_desc_stable(keep.data(), keep.size(), scores);
     std::copy(keep.begin(), keep.end(), ixs);
