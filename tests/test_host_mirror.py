@@ -63,6 +63,34 @@ def test_truncate_ixs_matches_oracle(oracle, seed):
     assert np.array_equal(a, b)
 
 
+def test_truncate_ixs_random_shapes_ties_ranges_and_subsets(oracle):
+    """The selection-first implementation (histogram k-th best, (key, position) sort) against the oracle's literal
+    sort-then-cut on many random cases: all-equal scores, heavy ties, values spanning many binades, sub-lists,
+    permuted lists, min_size / threads from 0 to beyond n (the branch that raises the cut to `threads`)."""
+    rs = np.random.default_rng(2024)
+    for it in range(400):
+        n = int(rs.integers(1, 1500))
+        kind = int(rs.integers(0, 5))
+        if kind == 0:
+            sc = -rs.gamma(2.0, 100.0, n)
+        elif kind == 1:
+            sc = -np.round(rs.gamma(2.0, 30.0, n))
+        elif kind == 2:
+            sc = np.full(n, -5.0)
+        elif kind == 3:
+            sc = -rs.gamma(9.0, 400.0, n)
+        else:
+            sc = np.where(rs.random(n) < 0.5, -np.round(rs.gamma(2.0, 3.0, n)), -1e6 * rs.random(n))
+        ids = np.arange(n) if rs.random() < 0.6 else rs.permutation(n)
+        if rs.random() < 0.3 and n > 3:
+            ids = np.sort(rs.choice(n, size=int(rs.integers(1, n)), replace=False))
+        fd = float(rs.choice([0.0, 1.0, 50.0, 230.26, 1e9]))
+        ms, th = int(rs.integers(0, n + 5)), int(rs.integers(0, n + 5))
+        a = genotype.truncate_ixs(ids.astype(np.uint64), sc, fd, ms, th)
+        b = oracle.truncate_ixs(ids.astype(np.uint64), sc, fd, ms, th)
+        assert np.array_equal(a, b), (it, n, kind, fd, ms, th)
+
+
 def test_compare_and_discard_match_oracle(oracle):
     rng = np.random.default_rng(3)
     lib_o, lib_g = oracle.lib(), ffi.load()
