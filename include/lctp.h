@@ -35,7 +35,8 @@ extern "C" {
 
 #define LCTP_NONE_U32 0xFFFFFFFFu
 #define LCTP_GC_BINS 101     /* src/bg/depth.rs:42 */
-#define LCTP_MAX_PLOIDY 8
+#define LCTP_MAX_PLOIDY 16    /* reference: ploidy < 256 (src/model/windows.rs:734); the device packs the contig index of a
+                                 candidate into 4 bits */
 #define LCTP_MAX_STAGES 8
 #define LCTP_MAX_OUT 50      /* MAX_GENOTYPES, src/solvers/solve.rs:486 */
 
@@ -116,6 +117,13 @@ typedef struct lctp_result {
     uint64_t n_filtered;
     uint64_t n_stage_in[LCTP_MAX_STAGES];
     double   t_prefilter_s, t_stages_s;      /* host wall clock, diagnostics */
+    /* Genotyping::find_weighted_dist (src/solvers/solve.rs:616-632); filled by lctp_find_weighted_dist only */
+    uint32_t has_dist;            /* Genotyping::distances.is_some() */
+    uint32_t true_edit_distances; /* Data::true_edit_distances -> "dist_type": "edit" | "minim-div" */
+    uint32_t has_weight_dist;     /* Genotyping::weighted_dist.is_some() (every distance to the primary is known) */
+    uint32_t _pad;
+    double   weight_dist;
+    uint32_t dist_to_primary[LCTP_MAX_OUT];   /* LCTP_NONE_U32 = "unknown" */
 } lctp_result;
 
 /* Device-side timing (CUDA events on the launch stream around each hot kernel) and work counters,
@@ -138,6 +146,8 @@ typedef struct lctp_stats {
     uint64_t rescore_launches;
     uint64_t rescore_alns;         /* alignment records rescored */
     uint64_t rescore_ops;          /* CIGAR operations read */
+    uint64_t h2d_bytes;            /* bytes copied host -> device by the library's calls on this context */
+    uint64_t d2h_bytes;            /* bytes copied device -> host */
 } lctp_stats;
 
 /* Alignment records of one locus before pairing = the per-alignment part of PrelimAlignments::push
@@ -269,7 +279,8 @@ size_t lctp_discard_improbable(uint64_t *ixs, size_t n, const double *lik_mean, 
                                const uint16_t *attempts, double prob_thresh, size_t out_size, size_t threads);
 double lctp_compare_two_likelihoods(double m1, double v1, uint16_t a1, double m2, double v2, uint16_t a2);
 /* DistrCache::new (src/model/distr_cache.rs:61-75): out[101][k_cols] from the preproc NB(n, p) per GC bin. */
-void lctp_build_depth_table(const double *nb_n, const double *nb_p, int is_paired,
+/* n_alt must be < 16 (BayesCalc::new asserts alternatives.len() < N_ALTS, src/math/distr/bayes.rs:16): LCTP_E_INVALID. */
+int  lctp_build_depth_table(const double *nb_n, const double *nb_p, int is_paired,
                             const double *alt_cn, size_t n_alt, uint32_t k_cols, double *out);
 
 /* Predictions::produce_result (src/solvers/solve.rs:482-535) followed by check_first_prob (:637-645),
@@ -278,6 +289,13 @@ void lctp_build_depth_table(const double *nb_n, const double *nb_p, int is_paire
  * Fills every field of `res` except n_filtered / n_stage_in / t_*. */
 int  lctp_produce_result(lctp_locus_h *h, uint64_t *ixs, size_t n, const double *lik_mean,
                          const double *lik_var, const uint16_t *attempts, lctp_result *res);
+
+/* Genotyping::find_weighted_dist (src/solvers/solve.rs:616-632) with genotype_distance (:339-357, permutations
+ * in the order of ext::vec::gen_permutations, src/ext/vec.rs:342-372).  Host only.  `dist` is the linear storage of
+ * Data::contig_distances (TriangleMatrix<Option<u32>>, src/ext/trimat.rs:8-46: pairs i < j, row-major,
+ * n_haps * (n_haps - 1) / 2 entries, LCTP_NONE_U32 = None); `loc` supplies n_haps, ploidy and gt_tuples.
+ * The reference calls it after produce_result when the locus has a distance matrix (solve.rs:973-975). */
+int  lctp_find_weighted_dist(lctp_result *res, const lctp_locus *loc, const uint32_t *dist, int true_edit_distances);
 
 /* solve::solve (src/solvers/solve.rs:926-981) without file output: prefilter -> stages -> result.
  * `rng` is the locus stream (in/out); `threads` is the reference's -@ (number of logical workers). */

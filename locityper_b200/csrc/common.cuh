@@ -126,7 +126,9 @@ struct LocusDev {
     const double *Mt;            // [R][Hpad] best-alignment matrix, read-major (a1)
     const double *unmapped;      // [R]
     const uint32_t *cm_off;      // [H*R+1] contig-major CSR of pair alignments
-    const double *cm_lnprob;     // [NPA]
+    const double *cm_lnprob;     // [NPA + R]: ln_prob of every pair alignment, then unmapped[r] at NPA + r, so that the
+                                 //            ln-probability of any candidate is ONE index into this array
+    uint32_t npa;
     const uint2 *cm_mid;         // [NPA] (middle1, middle2)
     const uint32_t *hap_len, *hap_n_windows, *hap_reg_start;   // [H]
     const uint64_t *hap_pos_off; // [H+1]
@@ -144,6 +146,7 @@ struct lctp_locus_h {
     uint64_t npa = 0;
     uint32_t max_hap_alns = 0;   // max over haplotypes of #pair alignments on that haplotype
     uint32_t max_n_windows = 0;
+    uint32_t max_run = 0;        // longest (read, contig) run of pair alignments
     std::vector<uint32_t> hap_alns;      // [H] #pair alignments per haplotype
     std::vector<uint32_t> gt_tuples_host; // explicit genotype list (host copy), empty = full enumeration
     std::vector<double> priors_host;      // host copy of priors, empty = 0.0

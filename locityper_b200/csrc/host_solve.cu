@@ -12,6 +12,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <charconv>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -502,9 +503,11 @@ int lctp_prefilter_scores(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, dou
     int rc = launch_prefilter(h, g_begin, g_end, h->scores.p);
     if (rc) return rc;
     LCTP_CUDA_CHECK(cudaEventRecord(h->ctx->ev[1], h->ctx->stream));
-    if (scores_out && g_end > g_begin)
+    if (scores_out && g_end > g_begin) {
         LCTP_CUDA_CHECK(cudaMemcpyAsync(scores_out, h->scores.p + g_begin, (g_end - g_begin) * 8,
                                         cudaMemcpyDeviceToHost, h->ctx->stream));
+        h->ctx->stats.d2h_bytes += (g_end - g_begin) * 8;
+    }
     LCTP_CUDA_CHECK(cudaStreamSynchronize(h->ctx->stream));
     float ms = 0.f;
     LCTP_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ctx->ev[0], h->ctx->ev[1]));
@@ -705,10 +708,14 @@ size_t lctp_discard_improbable(uint64_t *ixs, size_t n, const double *lik_mean, 
     return m;
 }
 
-void lctp_build_depth_table(const double *nb_n, const double *nb_p, int is_paired, const double *alt_cn,
-                            size_t n_alt, uint32_t k_cols, double *out) {
+int lctp_build_depth_table(const double *nb_n, const double *nb_p, int is_paired, const double *alt_cn,
+                           size_t n_alt, uint32_t k_cols, double *out) {
+    if (!nb_n || !nb_p || !out || (n_alt && !alt_cn)) { set_error("lctp_build_depth_table: NULL argument"); return LCTP_E_INVALID; }
+    if (n_alt >= 16) {       // BayesCalc::new: assert!(alternatives.len() < N_ALTS), src/math/distr/bayes.rs:16
+        set_error("lctp_build_depth_table: %zu alternative copy numbers; the reference allows at most 15", n_alt);
+        return LCTP_E_INVALID;
+    }
     const double mul_coef = is_paired ? 2.0 : 1.0;           // distr_cache.rs:66
-    if (n_alt > 16) n_alt = 16;
     for (int gc = 0; gc < LCTP_GC_BINS; gc++) {
         const NBinom cn1(nb_n[gc] * mul_coef, nb_p[gc]);     // NBinom::mul, nbinom.rs:68-70
         NBinom alts[16];
@@ -720,6 +727,7 @@ void lctp_build_depth_table(const double *nb_n, const double *nb_p, int is_paire
             out[(size_t)gc * k_cols + k] = null_prob - ln_sum_init(probs, n_alt, null_prob);
         }
     }
+    return LCTP_OK;
 }
 
 static double now_s() {
@@ -865,13 +873,130 @@ int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_
     return LCTP_OK;
 }
 
-// Minimal writer compatible with `json::JsonValue::write_pretty(.., 4)`: keys in insertion order.
+// ---- Genotyping::find_weighted_dist (src/solvers/solve.rs:616-632) ---------------------------------------
+
+// TriangleMatrix::get_symmetric (src/ext/trimat.rs): linear index of (i, j), i != j
+static inline size_t tri_index(size_t side, size_t i, size_t j) {
+    if (i > j) std::swap(i, j);
+    return (2 * side - 3 - i) * i / 2 + j - 1;
+}
+
+// genotype_distance (src/solvers/solve.rs:339-357): minimum over the permutations of gt1 that
+// ext::vec::gen_permutations visits (src/ext/vec.rs:342-372) -- for three or more contigs that is Heap's
+// algorithm WITHOUT the initial arrangement (the reference calls `action` only after each swap).
+static uint32_t genotype_distance(const uint32_t *gt1, const uint32_t *gt2, uint32_t p, uint32_t H, const uint32_t *dist) {
+    uint32_t min_dist = 0xFFFFFFFFu;
+    auto visit = [&](const uint32_t *perm) {
+        uint32_t d = 0;
+        for (uint32_t k = 0; k < p; k++) {
+            if (perm[k] != gt2[k]) {
+                const uint32_t e = dist[tri_index(H, perm[k], gt2[k])];
+                if (e == LCTP_NONE_U32) { d = 0xFFFFFFFFu; break; }
+                d += e;
+            }
+        }
+        min_dist = std::min(min_dist, d);
+    };
+    if (p == 1) visit(gt1);
+    else if (p == 2) {
+        visit(gt1);
+        const uint32_t sw[2] = {gt1[1], gt1[0]};
+        visit(sw);
+    } else if (p >= 3) {
+        std::vector<uint32_t> buffer(gt1, gt1 + p);
+        std::vector<size_t> c(p, 0);
+        size_t i = 1;
+        while (i < p) {
+            if (c[i] < i) {
+                std::swap(buffer[i], buffer[c[i] * (i % 2)]);     // 0 if i is even, c[i] if i is odd
+                visit(buffer.data());
+                c[i] += 1;
+                i = 1;
+            } else {
+                c[i] = 0;
+                i += 1;
+            }
+        }
+    }
+    return min_dist;     // 0xFFFFFFFF = None
+}
+
+int lctp_find_weighted_dist(lctp_result *res, const lctp_locus *loc, const uint32_t *dist, int true_edit_distances) {
+    if (!res || !loc || !dist) { set_error("lctp_find_weighted_dist: NULL argument"); return LCTP_E_INVALID; }
+    if (loc->ploidy == 0 || loc->ploidy > LCTP_MAX_PLOIDY) { set_error("lctp_find_weighted_dist: bad ploidy"); return LCTP_E_INVALID; }
+    if (res->n_out == 0) return LCTP_OK;                   // `let Some(gt0) = self.genotypes.first() else { return }`
+    const uint32_t p = loc->ploidy, H = loc->n_haps;
+    uint32_t gt0[LCTP_MAX_PLOIDY], gt[LCTP_MAX_PLOIDY];
+    genotype_tuple(H, p, loc->gt_tuples, res->gt_ix[0], gt0);
+    double sum_prob = 0.0, sum_dist = 0.0;
+    bool known = true;
+    for (uint64_t i = 0; i < res->n_out; i++) {
+        const double prob = std::exp(res->ln_prob[i]);
+        sum_prob += prob;
+        uint32_t d = 0;
+        if (i > 0) {
+            genotype_tuple(H, p, loc->gt_tuples, res->gt_ix[i], gt);
+            for (uint32_t k = 0; k < p; k++)
+                if (gt[k] >= H || gt0[k] >= H) { set_error("lctp_find_weighted_dist: contig id out of range"); return LCTP_E_INVALID; }
+            d = genotype_distance(gt0, gt, p, H, dist);
+        }
+        if (d == 0xFFFFFFFFu) known = false;               // Option::zip: one None makes the sum None for good
+        else if (known) sum_dist += prob * (double)d;
+        res->dist_to_primary[i] = d;
+    }
+    res->has_dist = 1;
+    res->true_edit_distances = true_edit_distances ? 1 : 0;
+    res->has_weight_dist = known ? 1 : 0;
+    res->weight_dist = known ? sum_dist / sum_prob : std::numeric_limits<double>::quiet_NaN();
+    return LCTP_OK;
+}
+
+// ---- Genotyping::to_json (src/solvers/solve.rs:732-773) as `json::JsonValue::write_pretty(.., 4)` prints it -----
+//
+// Numbers: the `json` crate (0.12) stores an f64 as a decimal (mantissa, exponent) pair of its shortest
+// round-trip digits and prints it with its own rules (util/print_dec.rs): plain digits with the decimal point
+// inserted while fewer than 18 fraction digits are needed, zero-filled integers up to 20 characters, otherwise
+// d.ddd e[-]N; NaN and infinities print as null.  (Restated from the published crate -- it is not vendored by the
+// reference -- so the exact thresholds are unpinned until a Rust toolchain is available.)
 static void json_num(std::string &o, double v) {
-    char b[64];
     if (std::isnan(v) || std::isinf(v)) { o += "null"; return; }
-    if (v == std::floor(v) && std::fabs(v) < 1e15) snprintf(b, sizeof b, "%.0f", v);
-    else snprintf(b, sizeof b, "%.17g", v);
-    o += b;
+    if (std::signbit(v)) { o += '-'; v = -v; }
+    if (v == 0.0) { o += '0'; return; }
+    char b[64];
+    auto r = std::to_chars(b, b + sizeof b - 1, v, std::chars_format::scientific);
+    *r.ptr = 0;
+    std::string digits;
+    int e10 = 0;
+    {
+        const char *q = b;
+        for (; q < r.ptr && *q != 'e'; q++) if (*q != '.') digits += *q;
+        e10 = atoi(q + 1);
+    }
+    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+    const int k = (int)digits.size();
+    const int exponent = e10 - (k - 1);                    // v = digits * 10^exponent
+    char eb[16];
+    if (exponent == 0) o += digits;
+    else if (exponent < 0) {
+        const int e = -exponent;
+        if (e < 18) {
+            if (k > e) { o.append(digits, 0, k - e); o += '.'; o.append(digits, k - e, std::string::npos); }
+            else { o += "0."; o.append((size_t)(e - k), '0'); o += digits; }
+        } else {
+            o += digits[0];
+            if (k > 1) { o += '.'; o.append(digits, 1, std::string::npos); }
+            snprintf(eb, sizeof eb, "e%d", e10);           // e10 = exponent + k - 1 (may have become positive)
+            o += eb;
+        }
+    } else {
+        if (k + exponent <= 20) { o += digits; o.append((size_t)exponent, '0'); }
+        else {
+            o += digits[0];
+            if (k > 1) { o += '.'; o.append(digits, 1, std::string::npos); }
+            snprintf(eb, sizeof eb, "e%d", e10);
+            o += eb;
+        }
+    }
 }
 
 size_t lctp_result_json(const lctp_result *res, const lctp_locus *loc, const char *const *hap_names, char *buf,
@@ -887,6 +1012,8 @@ size_t lctp_result_json(const lctp_result *res, const lctp_locus *loc, const cha
     };
     o += "{\n    \"total_reads\": "; json_num(o, res->total_reads);
     o += ",\n    \"quality\": "; json_num(o, res->quality);
+    if (res->has_dist) o += res->true_edit_distances ? ",\n    \"dist_type\": \"edit\"" : ",\n    \"dist_type\": \"minim-div\"";
+    if (res->has_dist && res->has_weight_dist) { o += ",\n    \"weight_dist\": "; json_num(o, res->weight_dist); }
     o += ",\n    \"unexpl_reads\": "; json_num(o, res->unexpl_reads);
     if (res->n_out) {
         o += ",\n    \"genotype\": \"" + gt_name(res->gt_ix[0]) + "\"";
@@ -898,6 +1025,11 @@ size_t lctp_result_json(const lctp_result *res, const lctp_locus *loc, const cha
             o += ",\n            \"lik_sd\": "; json_num(o, res->lik_var[i] * inv_ln10);   // sic: log10 of the variance (solve.rs:755)
             o += ",\n            \"prob\": "; json_num(o, std::exp(res->ln_prob[i]));
             o += ",\n            \"log10_prob\": "; json_num(o, res->ln_prob[i] * inv_ln10);
+            if (res->has_dist) {
+                o += ",\n            \"dist_to_primary\": ";
+                if (res->dist_to_primary[i] == LCTP_NONE_U32) o += "\"unknown\"";
+                else json_num(o, res->dist_to_primary[i]);
+            }
             o += "\n        }";
         }
         o += "\n    ]";

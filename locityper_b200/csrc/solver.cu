@@ -1,8 +1,8 @@
 // solver.cu -- a5..a13: one solver stage on the device.
 //
-// One lane GROUP (GS = 16 lanes, two groups per warp; GS = 32 selectable) per logical worker (= one
-// xoshiro256++ stream of the reference, src/solvers/solve.rs:1007-1018).  A worker solves its genotypes
-// back to back on that stream exactly like Worker::run (:1104-1145):
+// One warp per logical worker (= one xoshiro256++ stream of the reference, src/solvers/solve.rs:1007-1018),
+// one worker per 32-thread CTA.  A worker solves its genotypes back to back on that stream exactly like
+// Worker::run (:1104-1145):
 //   per genotype: GenotypeAlignments::new (src/model/assgn.rs:41-84, windows.rs:762-797)   -> build_instance
 //   per attempt : apply_tweak (assgn.rs:127-151, windows.rs:123-136,478-486)               -> apply_tweak
 //                 Solver::solve (solvers/mod.rs:61-72) = Greedy (stoch.rs:81-120) | SimAnneal (:197-242)
@@ -13,12 +13,17 @@
 // (__dadd_rn/__dmul_rn/__dsub_rn) in the reference's association order; the file is also compiled with
 // -fmad=false.  Random draws are consumed in exactly the reference's order (see "RNG stream").
 //
-// Data placement per worker:
-//   shared memory : window records (weight, table row, depth), compact offsets + current assignment of
-//                   the non-trivial reads, a 2-stage cp.async staging area for the greedy pipeline;
-//   registers     : the two likelihood accumulators, RNG window;
-//   global slab   : candidate arrays in read order (build / tweak / counts) and a compact copy of the
-//                   non-trivial reads' candidates (what the solver loops touch), RNG draw buffer.
+// Data placement per worker (round 2: sized so that the private state of every resident worker stays in L2):
+//   shared memory : window records (weight, table row, depth, 5 products), candidate offset + current
+//                   assignment of every read, the list of non-trivial reads;
+//   private slab  : per candidate ONE 32-bit record = source byte (contig index << 4 | rank in that contig's run;
+//                   0xFF = the "unmapped" option) | window 1 << 8 | window 2 << 20 (64-bit records when a genotype
+//                   has more than 4096 windows), plus an 8 KB buffer of pre-generated draws;
+//   shared by all workers of a locus (read-only, L2): the ln-probabilities themselves.  A candidate's ln_prob
+//                   is cm_lnprob[cm_off[hap * R + read] + rank] (cm_lnprob[NPA + read] for the unmapped option):
+//                   it is never copied per worker, so the hot private state is 4 bytes per candidate instead
+//                   of round 1's 24 and the slabs of all resident workers fit the L2 (ncu, C2 shape: DRAM
+//                   traffic per launch 8.5 GB -> 63 MB, L2 hit rate 56 % -> 95 %).
 #include "common.cuh"
 
 #include <cmath>
@@ -27,111 +32,95 @@
 #include <cstdlib>
 #include <mutex>
 #include <chrono>
+#include <unordered_map>
 
 namespace lctp {
 
-#ifndef LCTP_CTA_THREADS
-#define LCTP_CTA_THREADS 32
-#endif
-static constexpr int CTA_THREADS = LCTP_CTA_THREADS;
-static constexpr int MAX_SAMPLE = 11;          // Floyd branch of rand::seq::index::sample
+static constexpr int CTA_THREADS = 32;
+static constexpr int MAX_SAMPLE = 11;          // Floyd branch of rand::seq::index::sample on the lane-parallel path
 #ifndef LCTP_HEADS
 #define LCTP_HEADS 2
 #endif
 #ifndef LCTP_RNG_C
-#define LCTP_RNG_C 256
+#define LCTP_RNG_C 32
 #endif
-static constexpr int RNG_C = LCTP_RNG_C;               // stream outputs generated per lane per fill
-static constexpr int RNG_BUF = 32 * RNG_C;     // slab space for one fill (GS * RNG_C <= this)
-static constexpr int N_SETUP_MATS = 5;         // T^(C*2^k), k = 0..4
+static constexpr int RNG_C = LCTP_RNG_C;                // stream outputs generated per lane per fill
+static constexpr uint32_t RNG_FILL = 32u * RNG_C;       // draws per fill (per-worker buffer: 8 KB at C = 32)
+static constexpr int N_JUMP_TABS = 6;                   // T^(C*2^k), k = 0..4 (stream start), T^FILL (refill)
+static constexpr size_t JUMP_TAB_WORDS = 32 * 256 * 4;  // u64 words per table: [32 state bytes][256 values][4]
+static constexpr uint32_t SRC_UNMAPPED = 0xFFu;
+static constexpr uint32_t MAX_RUN = 15;                 // rank in a (read, contig) run must fit 4 bits (reference: <= 10)
 
 struct StageParams {
     uint32_t kind, attempts, best_start, sample_size;
     uint64_t plato_size, anneal_steps, max_iter;
     double ln_init_prob;
-    uint32_t n_workers, cap, Wmax, want_counts;
+    uint32_t n_workers, cap, Wmax, want_counts, narrow_w, _pad;
     uint64_t slab_bytes;
 };
 
+// Candidate record as stored in the slab: source byte and the two windows in ONE word, so that a candidate is one
+// load.  The raw word travels through the prefetch pipelines unchanged and is taken apart where it is used, so that
+// no instruction depends on a load right after it was issued.
+template <bool WIDE> struct RecWord;
+template <> struct RecWord<false> {       // <= 4096 windows per genotype
+    typedef uint32_t T;
+    static __device__ __forceinline__ uint32_t src(T raw) { return raw & 0xFFu; }
+    static __device__ __forceinline__ uint32_t w1(T raw) { return (raw >> 8) & 0xFFFu; }
+    static __device__ __forceinline__ uint32_t w2(T raw) { return raw >> 20; }
+    static __device__ __forceinline__ T make(uint32_t s, uint32_t a, uint32_t b) { return s | (a << 8) | (b << 20); }
+};
+template <> struct RecWord<true> {
+    typedef uint64_t T;
+    static __device__ __forceinline__ uint32_t src(T raw) { return (uint32_t)raw & 0xFFu; }
+    static __device__ __forceinline__ uint32_t w1(T raw) { return (uint32_t)(raw >> 16) & 0xFFFFu; }
+    static __device__ __forceinline__ uint32_t w2(T raw) { return (uint32_t)(raw >> 32) & 0xFFFFu; }
+    static __device__ __forceinline__ T make(uint32_t s, uint32_t a, uint32_t b) { return (T)s | ((T)a << 16) | ((T)b << 32); }
+};
+
+template <bool WIDE>
 struct Slab {
-    // Candidates of every read in read order (the reference's `alns`, a5): only what apply_tweak and the
-    // count output need per candidate -- where it came from and where its solver record lives.
-    uint2 *cmap;           // [cap]  x = index into the cm arrays | contig index << 28 (LCTP_NONE_U32 = the
-                           //        "both mates unmapped" option); y = index of its record in `ntc`, or
-                           //        TRIV_TAG | read id for the single candidate of a trivial read
-    uint32_t *read_off;    // [R+1]
-    uint4 *ntc;            // [cap]  records of the non-trivial reads' candidates, compact, in read order:
-                           //        x,y = ln_prob (f64 bits), z = windows (w1 | w2 << 16), w unused
-    double *triv_lp;       // [R]    ln_prob of the only candidate of a trivial read
-    uint32_t *triv_w;      // [R]    its windows
-    uint64_t *rng_buf;     // [RNG_BUF] pre-generated draws of the worker's stream
+    typedef typename RecWord<WIDE>::T Rec;
+    Rec *rec;              // [cap]  record of every candidate, reads in read order (the reference's `alns`, a5)
+    uint64_t *rng_buf;     // [RNG_FILL] pre-generated draws of the worker's stream
     uint64_t *rng_blk;     // [32*4] block-start generator states of the current fill
 };
-static constexpr uint32_t TRIV_TAG = 0x80000000u;
-static constexpr uint32_t SRC_MASK = 0x0FFFFFFFu;     // cm index bits of cmap.x (the contig index sits above)
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline size_t slab_layout(uint32_t cap, uint32_t R, unsigned char *base, Slab *s) {
-    size_t o = 0;
-    if (s) s->ntc = (uint4 *)(base + o);
-    o += align_up((size_t)cap * 16, 128);
-    if (s) s->cmap = (uint2 *)(base + o);
-    o += align_up((size_t)cap * 8, 128);
-    if (s) s->triv_lp = (double *)(base + o);
-    o += align_up((size_t)R * 8, 128);
-    if (s) s->triv_w = (uint32_t *)(base + o);
-    o += align_up((size_t)R * 4, 128);
-    if (s) s->read_off = (uint32_t *)(base + o);
-    o += align_up(((size_t)R + 1) * 4, 128);
-    if (s) s->rng_buf = (uint64_t *)(base + o);
-    o += (size_t)RNG_BUF * 8;
-    if (s) s->rng_blk = (uint64_t *)(base + o);
-    o += 32 * 4 * 8;
-    return o;
+__host__ __device__ inline size_t slab_bytes_for(uint32_t cap, bool wide) {
+    return (size_t)RNG_FILL * 8 + 32 * 4 * 8 + align_up((size_t)cap * (wide ? 8 : 4), 128);
+}
+template <bool WIDE>
+__device__ __forceinline__ void slab_layout(uint32_t cap, unsigned char *base, Slab<WIDE> &s) {
+    s.rng_buf = (uint64_t *)base;
+    s.rng_blk = (uint64_t *)(base + (size_t)RNG_FILL * 8);
+    s.rec = (typename Slab<WIDE>::Rec *)(base + (size_t)RNG_FILL * 8 + 32 * 4 * 8);
 }
 
-// ------------------------------------------------------------------ lane groups -----------------
+// ------------------------------------------------------------------ warp helpers ----------------
 
-// A worker is served by GS consecutive lanes of a warp.  All collectives are restricted to the group's
-// lane mask, so the two groups of a warp run two independent workers in the same instruction stream.
-template <int GS>
-struct Grp {
-    unsigned mask;
-    int shift, lane;
-    __device__ Grp() {
-        const int wl = threadIdx.x & 31;
-        shift = GS == 32 ? 0 : (wl & ~(GS - 1));
-        mask = GS == 32 ? 0xFFFFFFFFu : (((1u << GS) - 1u) << shift);
-        lane = wl & (GS - 1);
-    }
-    static constexpr unsigned LM = GS == 32 ? 0xFFFFFFFFu : ((1u << GS) - 1u);
-    template <typename T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(mask, v, src, GS); }
-    template <typename T> __device__ __forceinline__ T shfl_up(T v, int d) const { return __shfl_up_sync(mask, v, d, GS); }
-    template <typename T> __device__ __forceinline__ T shfl_xor(T v, int m) const { return __shfl_xor_sync(mask, v, m, GS); }
-    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) >> shift) & LM; }
-    __device__ __forceinline__ bool any(bool p) const { return __any_sync(mask, p) != 0; }
-    __device__ __forceinline__ unsigned match_any(uint32_t v) const { return (__match_any_sync(mask, v) >> shift) & LM; }
-    __device__ __forceinline__ uint32_t rmax(uint32_t v) const { return __reduce_max_sync(mask, v); }
-    __device__ __forceinline__ uint32_t rmin(uint32_t v) const { return __reduce_min_sync(mask, v); }
-    __device__ __forceinline__ uint32_t ror(uint32_t v) const { return __reduce_or_sync(mask, v); }
-    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
-    __device__ __forceinline__ unsigned lt() const { return (1u << lane) - 1u; }
-};
+static constexpr unsigned FULL = 0xFFFFFFFFu;
+__device__ __forceinline__ int lane_id() { return threadIdx.x; }            // CTA = one warp
+__device__ __forceinline__ unsigned lanes_lt() { return (1u << lane_id()) - 1u; }
+template <typename T> __device__ __forceinline__ T wshfl(T v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ unsigned wballot(bool p) { return __ballot_sync(FULL, p); }
+__device__ __forceinline__ bool wany(bool p) { return __any_sync(FULL, p) != 0; }
 
 // ------------------------------------------------------------------ RNG stream -------------------
 //
-// The reference consumes ONE sequential xoshiro256++ stream per worker.  Stepping that generator
-// redundantly in every lane costs ~25 instructions per draw.  Instead the group pre-generates the stream
-// in bulk: xoshiro's state transition is linear over GF(2), so lane l jumps its copy of the state ahead
-// by l*RNG_C steps (256x256 bit-matrix products with host-precomputed powers of the transition matrix)
-// and then generates RNG_C consecutive outputs of the SAME sequential stream into a per-worker buffer:
-// GS lanes produce GS*64 exact draws per fill.  Consumers read the buffer through a GS-entry register
-// window with shuffles, in stream order, so the draw sequence (including the data-dependent extra draw
-// of biased bounded samples) is bit-identical to the sequential generator.  At the end of a worker the
-// exact state at the consumed position is rebuilt from the owning lane's block-start state.
-
-__constant__ uint64_t c_refill_mat[2][256 * 4];   // [0]: T^(15*C) for GS=16, [1]: T^(31*C) for GS=32
+// The reference consumes ONE sequential xoshiro256++ stream per worker.  Stepping that generator redundantly
+// in every lane costs ~25 instructions per draw.  Instead the warp pre-generates the stream in bulk:
+// xoshiro's state transition is linear over GF(2), so lane l jumps its copy of the state ahead by l*RNG_C
+// steps and then generates RNG_C consecutive outputs of the SAME sequential stream into a per-worker buffer:
+// 32 lanes produce 1,024 exact draws per fill.  A jump is a 256x256 bit-matrix product; it is evaluated
+// with byte-indexed tables (entry [b][v] = M * (v << 8b), 32 lookups of 32 bytes, ~450 instructions) instead
+// of round 1's bit-by-bit product (~2,800), which is what makes a fill of 1,024 draws (8 KB per worker,
+// L2-resident) as cheap per draw as round 1's 8,192-draw fill (64 KB per worker, streamed through DRAM).
+// Consumers read the buffer through a 3 x 32-entry register window with shuffles, in stream order, so the
+// draw sequence (including the data-dependent extra draw of biased bounded samples) is bit-identical to the
+// sequential generator.  At the end of a worker the exact state at the consumed position is rebuilt from the
+// owning lane's block-start state.
 
 struct Gen { uint64_t s0, s1, s2, s3; };
 
@@ -146,172 +135,188 @@ __device__ __host__ __forceinline__ uint64_t gen_next(Gen &x) {
     return r;
 }
 
-// state <- M * state over GF(2); M given by its 256 columns (4 words each); `take` selects per lane
-// whether the product replaces the state (all lanes execute the same instruction stream).
-__device__ __forceinline__ void gen_mat_apply(Gen &g, const uint64_t *__restrict__ mat, bool take) {
+// state <- M * state over GF(2), M given as a byte-indexed table (see above)
+__device__ __forceinline__ Gen gen_tab_apply(const Gen &g, const ulonglong2 *__restrict__ tab) {
     uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll 1
+#pragma unroll
     for (int w = 0; w < 4; w++) {
         const uint64_t sw = w == 0 ? g.s0 : w == 1 ? g.s1 : w == 2 ? g.s2 : g.s3;
-#pragma unroll 8
-        for (int b = 0; b < 64; b++) {
-            const uint64_t m = 0ull - ((sw >> b) & 1ull);
-            const uint64_t *c = mat + (size_t)(w * 64 + b) * 4;
-            a0 ^= c[0] & m; a1 ^= c[1] & m; a2 ^= c[2] & m; a3 ^= c[3] & m;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const uint32_t v = (uint32_t)(sw >> (8 * b)) & 0xFFu;
+            const ulonglong2 *e = tab + ((size_t)((w * 8 + b) * 256) + v) * 2;
+            const ulonglong2 lo = __ldg(e), hi = __ldg(e + 1);
+            a0 ^= lo.x; a1 ^= lo.y; a2 ^= hi.x; a3 ^= hi.y;
         }
     }
-    if (take) { g.s0 = a0; g.s1 = a1; g.s2 = a2; g.s3 = a3; }
+    Gen o; o.s0 = a0; o.s1 = a1; o.s2 = a2; o.s3 = a3;
+    return o;
 }
 
-template <int GS>
 struct Xo {                // the worker's stream as seen by the solver code
-    static constexpr uint32_t FILL = GS * RNG_C;
-    Grp<GS> g;
-    Gen gen;               // this lane's generator (positioned at the end of its block after a fill)
-    uint32_t a_lo, a_hi;   // register blocks: A = buf[base + lane], B = buf[base + GS + lane] (B is the
-    uint32_t b_lo, b_hi;   // prefetched successor, so moving the window never waits for memory)
+    // Register blocks: A = buf[base + lane], B = buf[base + 32 + lane], C = buf[base + 64 + lane].  A and B are
+    // what the consumers shuffle from; C is the prefetch in flight and is never read before it has become B one
+    // shift (>= 32 draws) later, so moving the window never waits for memory.
+    uint32_t a_lo, a_hi, b_lo, b_hi, c_lo, c_hi;
     uint32_t pos;          // draws consumed from the current fill
-    uint32_t base;         // stream position of lane 0 of block A (multiple of GS)
-    uint64_t *buf;         // [FILL] per-worker buffer (global, L2-resident)
-    uint64_t *blk;         // [GS][4] block-start states of the current fill
+    uint32_t base;         // stream position of lane 0 of block A (multiple of 32)
+    uint64_t *buf;         // [RNG_FILL] per-worker buffer (global, L2-resident)
+    uint64_t *blk;         // [32][4] block-start states of the current fill
+    const ulonglong2 *tabs;// jump tables
 };
 
-// Generate this lane's block of the next fill; returns the generator positioned at the block end.
-// Out of line and by value so that the caller's stream object never has its address taken (it would be
-// demoted to local memory otherwise).
-__device__ __noinline__ Gen fill_block(Gen gen, uint64_t *buf, uint64_t *blk, int lane, unsigned mask, int jump_mat) {
-    if (jump_mat >= 0) gen_mat_apply(gen, c_refill_mat[jump_mat], true);   // end of own block -> own block of the next fill
-    uint64_t *b = blk + lane * 4;
-    b[0] = gen.s0; b[1] = gen.s1; b[2] = gen.s2; b[3] = gen.s3;
-    uint64_t *o = buf + lane * RNG_C;
-#pragma unroll 4
-    for (int q = 0; q < RNG_C; q++) o[q] = gen_next(gen);
-    __syncwarp(mask);
-    return gen;
+__device__ __forceinline__ uint64_t stream_ld(const Xo &x, uint32_t p) {
+    return __ldcg(x.buf + min(p + (uint32_t)lane_id(), RNG_FILL - 1u));
 }
-template <int GS>
-__device__ __forceinline__ void stream_fill(Xo<GS> &x, int jump_mat) {
-    x.gen = fill_block(x.gen, x.buf, x.blk, x.g.lane, x.g.mask, jump_mat);
-    x.pos = 0;
-    x.base = 0;
-    const uint64_t a = __ldcg(x.buf + x.g.lane), b = __ldcg(x.buf + GS + x.g.lane);
+__device__ __forceinline__ void stream_load_window(Xo &x) {
+    const uint64_t a = stream_ld(x, x.base), b = stream_ld(x, x.base + 32u), c = stream_ld(x, x.base + 64u);
     x.a_lo = (uint32_t)a; x.a_hi = (uint32_t)(a >> 32);
     x.b_lo = (uint32_t)b; x.b_hi = (uint32_t)(b >> 32);
+    x.c_lo = (uint32_t)c; x.c_hi = (uint32_t)(c >> 32);
+}
+
+// Generate this lane's block of a fill from its block-start state (stored in blk); out of line so that the
+// generator state lives in registers only here.  The out-of-line helpers take plain pointers, never the stream
+// object: its address must not escape or it would be demoted to local memory.
+__device__ __noinline__ void fill_block(uint64_t *buf, uint64_t *blk, const ulonglong2 *refill_tab) {
+    const int lane = lane_id();
+    uint64_t *b = blk + lane * 4;
+    Gen gen; gen.s0 = b[0]; gen.s1 = b[1]; gen.s2 = b[2]; gen.s3 = b[3];
+    if (refill_tab) {      // block start of the previous fill -> same block of the next fill (FILL steps ahead)
+        gen = gen_tab_apply(gen, refill_tab);
+        b[0] = gen.s0; b[1] = gen.s1; b[2] = gen.s2; b[3] = gen.s3;
+    }
+    ulonglong2 *o = (ulonglong2 *)(buf + lane * RNG_C);
+#pragma unroll 4
+    for (int q = 0; q < RNG_C / 2; q++) {
+        ulonglong2 v;
+        v.x = gen_next(gen);
+        v.y = gen_next(gen);
+        __stcg(o + q, v);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void stream_refill(Xo &x) {
+    fill_block(x.buf, x.blk, x.tabs + (size_t)5 * (JUMP_TAB_WORDS / 2));
+    x.pos = 0;
+    x.base = 0;
+    stream_load_window(x);
 }
 
 // Start a stream from the scalar state st[4]: lane l jumps ahead by l*RNG_C (binary decomposition of l).
-template <int GS>
-__device__ void stream_begin(Xo<GS> &x, const uint64_t *__restrict__ st, const uint64_t *__restrict__ setup_mats) {
-    x.gen.s0 = st[0]; x.gen.s1 = st[1]; x.gen.s2 = st[2]; x.gen.s3 = st[3];
-    constexpr int ROUNDS = GS == 32 ? 5 : 4;
-    for (int k = 0; k < ROUNDS; k++) gen_mat_apply(x.gen, setup_mats + (size_t)k * 1024, (x.g.lane >> k) & 1);
-    stream_fill(x, -1);
+__device__ __noinline__ void stream_begin_blocks(const uint64_t *__restrict__ st, uint64_t *buf, uint64_t *blk,
+                                                 const ulonglong2 *tabs) {
+    Gen g; g.s0 = st[0]; g.s1 = st[1]; g.s2 = st[2]; g.s3 = st[3];
+    const int lane = lane_id();
+    for (int k = 0; k < 5; k++)
+        if ((lane >> k) & 1) g = gen_tab_apply(g, tabs + (size_t)k * (JUMP_TAB_WORDS / 2));
+    __syncwarp();
+    uint64_t *b = blk + lane * 4;
+    b[0] = g.s0; b[1] = g.s1; b[2] = g.s2; b[3] = g.s3;
+    fill_block(buf, blk, nullptr);
+}
+__device__ __forceinline__ void stream_begin(Xo &x, const uint64_t *__restrict__ st) {
+    stream_begin_blocks(st, x.buf, x.blk, x.tabs);
+    x.pos = 0;
+    x.base = 0;
+    stream_load_window(x);
 }
 
-template <int GS>
-__device__ __forceinline__ void stream_refill(Xo<GS> &x) { stream_fill(x, GS == 32 ? 1 : 0); }
-
-// Exact scalar state after the draws consumed so far (what the sequential generator would hold).
-template <int GS>
-__device__ void stream_end(Xo<GS> &x, uint64_t *__restrict__ out) {
-    x.g.sync();
-    Gen g = x.gen;                                        // pos == FILL: lane GS-1's copy is the state
-    int owner = GS - 1;
-    if (x.pos < Xo<GS>::FILL) {
-        const int blk_owner = x.pos / RNG_C;
-        const uint64_t *b = x.blk + blk_owner * 4;
+// Exact scalar state after `pos` draws of the current fill (what the sequential generator would hold).
+__device__ __noinline__ void stream_end_state(uint32_t pos, const uint64_t *blk, uint64_t *__restrict__ out) {
+    __syncwarp();
+    Gen g;
+    if (pos < RNG_FILL) {
+        const int owner = pos / RNG_C;
+        const uint64_t *b = blk + owner * 4;
         g.s0 = b[0]; g.s1 = b[1]; g.s2 = b[2]; g.s3 = b[3];
-        const int steps = x.pos - blk_owner * RNG_C;
+        const int steps = pos - owner * RNG_C;
         for (int q = 0; q < steps; q++) gen_next(g);
-        owner = 0;                                        // every lane computed the same state
+    } else {                                              // whole fill consumed: end of the last block
+        const uint64_t *b = blk + 31 * 4;
+        g.s0 = b[0]; g.s1 = b[1]; g.s2 = b[2]; g.s3 = b[3];
+        for (int q = 0; q < RNG_C; q++) gen_next(g);
     }
-    if (x.g.lane == owner) { out[0] = g.s0; out[1] = g.s1; out[2] = g.s2; out[3] = g.s3; }
+    if (lane_id() == 0) { out[0] = g.s0; out[1] = g.s1; out[2] = g.s2; out[3] = g.s3; }
 }
+__device__ __forceinline__ void stream_end(Xo &x, uint64_t *__restrict__ out) { stream_end_state(x.pos, x.blk, out); }
 
-// Make the register blocks cover stream positions [pos, pos + count), count <= GS; false = the fill
-// ends first (the caller then uses the one-draw-at-a-time path, which refills).  Position q of the
-// stream lives in lane q % GS: in block A for q < base + GS, else in block B.
-template <int GS>
-__device__ __forceinline__ bool stream_cover(Xo<GS> &x, uint32_t count) {
-    if (x.pos + count > Xo<GS>::FILL) return false;
-    if (x.pos - x.base >= (uint32_t)GS) {                  // A is used up: B becomes A, prefetch the next B
-        x.a_lo = x.b_lo; x.a_hi = x.b_hi;
-        x.base += GS;
-        const uint64_t v = __ldcg(x.buf + min(x.base + GS + (uint32_t)x.g.lane, Xo<GS>::FILL - 1u));
-        x.b_lo = (uint32_t)v; x.b_hi = (uint32_t)(v >> 32);
+// Make the register blocks cover stream positions [pos, pos + count), count <= 32; false = the fill ends
+// first (the caller then uses the one-draw-at-a-time path, which refills).  Position q of the stream lives
+// in lane q % 32: in block A for q < base + 32, else in block B.  `pos` may have been moved arbitrarily
+// (forwards by bulk consumers, backwards by stream_unconsume) since the last call.
+__device__ __forceinline__ bool stream_cover(Xo &x, uint32_t count) {
+    if (x.pos + count > RNG_FILL) return false;
+    const uint32_t d = x.pos - x.base;
+    if (d >= 32u) {
+        if (d < 64u) {                                    // A is used up: B -> A, C -> B, prefetch the next C
+            x.a_lo = x.b_lo; x.a_hi = x.b_hi;
+            x.b_lo = x.c_lo; x.b_hi = x.c_hi;
+            x.base += 32u;
+            const uint64_t v = stream_ld(x, x.base + 64u);
+            x.c_lo = (uint32_t)v; x.c_hi = (uint32_t)(v >> 32);
+        } else {                                          // far jump (or backwards): reload the blocks
+            x.base = x.pos & ~31u;
+            stream_load_window(x);
+        }
     }
     return true;
 }
 // After stream_cover(count): the (pos + rank)-th draw of the stream, for any per-lane rank < count.
-template <int GS>
-__device__ __forceinline__ uint32_t stream_peek_hi(const Xo<GS> &x, uint32_t rank) {
+__device__ __forceinline__ uint32_t stream_peek_hi(const Xo &x, uint32_t rank) {
     const uint32_t off = x.pos - x.base;
-    return x.g.shfl((uint32_t)x.g.lane >= off ? x.a_hi : x.b_hi, (int)((off + rank) & (GS - 1)));
+    return wshfl((uint32_t)lane_id() >= off ? x.a_hi : x.b_hi, (int)((off + rank) & 31u));
 }
-template <int GS>
-__device__ __forceinline__ uint64_t stream_peek64(const Xo<GS> &x, uint32_t rank) {
+__device__ __forceinline__ uint64_t stream_peek64(const Xo &x, uint32_t rank) {
     const uint32_t off = x.pos - x.base;
-    const bool in_a = (uint32_t)x.g.lane >= off;
-    const int src = (int)((off + rank) & (GS - 1));
-    return ((uint64_t)x.g.shfl(in_a ? x.a_hi : x.b_hi, src) << 32) | x.g.shfl(in_a ? x.a_lo : x.b_lo, src);
+    const bool in_a = (uint32_t)lane_id() >= off;
+    const int src = (int)((off + rank) & 31u);
+    return ((uint64_t)wshfl(in_a ? x.a_hi : x.b_hi, src) << 32) | wshfl(in_a ? x.a_lo : x.b_lo, src);
 }
-// Give back the last n draws (n <= GS, all taken from the current fill without a refill in between).
-template <int GS>
-__device__ __forceinline__ void stream_unconsume(Xo<GS> &x, uint32_t n) {
-    x.pos -= n;
-    while (x.pos < x.base) {
-        x.b_lo = x.a_lo; x.b_hi = x.a_hi;
-        x.base -= GS;
-        const uint64_t v = __ldcg(x.buf + x.base + x.g.lane);
-        x.a_lo = (uint32_t)v; x.a_hi = (uint32_t)(v >> 32);
-    }
-}
-template <int GS>
-__device__ __forceinline__ void stream_advance(Xo<GS> &x) {
-    if (x.pos == Xo<GS>::FILL) stream_refill(x);
+// Give back the last n draws (all taken from the current fill without a refill in between).
+__device__ __forceinline__ void stream_unconsume(Xo &x, uint32_t n) { x.pos -= n; }
+
+__device__ __forceinline__ void stream_advance(Xo &x) {
+    if (x.pos == RNG_FILL) stream_refill(x);
     stream_cover(x, 1);
 }
-template <int GS>
-__device__ __forceinline__ uint32_t xo_u32(Xo<GS> &x) {   // next_u32 = upper half of next_u64
+__device__ __forceinline__ uint32_t xo_u32(Xo &x) {   // next_u32 = upper half of next_u64
     stream_advance(x);
     const uint32_t r = stream_peek_hi(x, 0);
     x.pos++;
     return r;
 }
-template <int GS>
-__device__ __forceinline__ uint64_t xo_next(Xo<GS> &x) {
+__device__ __forceinline__ uint64_t xo_next(Xo &x) {
     stream_advance(x);
     const uint64_t r = stream_peek64(x, 0);
     x.pos++;
     return r;
 }
 // rand UniformInt::sample_single_inclusive with a u32 sample type: value in [0, range), range != 0.
-template <int GS>
-__device__ __forceinline__ uint32_t xo_below(Xo<GS> &x, uint32_t range) {
+__device__ __forceinline__ uint32_t xo_below(Xo &x, uint32_t range) {
     const uint64_t m = (uint64_t)xo_u32(x) * (uint64_t)range;
     uint32_t res = (uint32_t)(m >> 32);
     const uint32_t lo = (uint32_t)m;
-    if (lo > 0u - range) {   // biased zone: one extra draw (group-uniform branch)
+    if (lo > 0u - range) {   // biased zone: one extra draw (warp-uniform branch)
         const uint32_t nh = (uint32_t)(((uint64_t)xo_u32(x) * (uint64_t)range) >> 32);
         res += (lo + nh < lo) ? 1u : 0u;
     }
     return res;
 }
 // rand StandardUniform f64 (src/solvers/stoch.rs:216)
-template <int GS>
-__device__ __forceinline__ double xo_f64(Xo<GS> &x) {
-    return (double)(xo_next(x) >> 11) * (1.0 / 9007199254740992.0);
+__device__ __forceinline__ double u64_to_unit_f64(uint64_t v) {
+    return (double)(v >> 11) * (1.0 / 9007199254740992.0);
 }
-// Lane-parallel bounded draws: lanes < count each want random_range(0..range) and lane k must receive
-// the k-th draw of the stream.  Succeeds (and consumes `count` draws) only when no lane lands in the
-// biased zone -- which would consume an extra draw and shift every later lane -- otherwise nothing is
-// consumed and the caller runs the sequential path.  P(fallback) ~ count * range / 2^32.
-template <int GS>
-__device__ __forceinline__ bool xo_below_parallel(Xo<GS> &x, uint32_t count, uint32_t range, uint32_t &res) {
+__device__ __forceinline__ double xo_f64(Xo &x) { return u64_to_unit_f64(xo_next(x)); }
+// Lane-parallel bounded draws: lanes < count each want random_range(0..range_l) and lane k must receive the
+// k-th draw of the stream.  Succeeds (and consumes `count` draws) only when no lane lands in the biased zone
+// -- which would consume an extra draw and shift every later lane -- otherwise nothing is consumed and the
+// caller runs the sequential path.  P(fallback) ~ count * range / 2^32.
+__device__ __forceinline__ bool xo_below_lanes(Xo &x, uint32_t count, uint32_t my_range, uint32_t &res) {
     if (!stream_cover(x, count)) return false;
-    const uint64_t m = (uint64_t)stream_peek_hi(x, (uint32_t)x.g.lane) * (uint64_t)range;
-    const bool biased = (uint32_t)x.g.lane < count && (uint32_t)m > 0u - range;
-    if (x.g.any(biased)) return false;
+    const uint64_t m = (uint64_t)stream_peek_hi(x, (uint32_t)lane_id()) * (uint64_t)my_range;
+    const bool biased = (uint32_t)lane_id() < count && (uint32_t)m > 0u - my_range;
+    if (wany(biased)) return false;
     res = (uint32_t)(m >> 32);
     x.pos += count;
     return true;
@@ -338,8 +343,7 @@ __device__ __forceinline__ unsigned long long ord_key(double v) {
 // extra row of the device table, so 0*0 - 0*0 = +0.0 reproduces the reference's literal 0.0 with no
 // branch; a zero depth change gives p - p = +0.0 the same way.
 // Layout: structure of arrays (five product planes, then weight, row, depth), so that lanes looking up
-// DIFFERENT windows hit different banks -- with one 64-byte record per window every lane of an evaluation
-// pass landed in the same two bank groups (16-way conflicts on the hottest loads of the kernel).
+// DIFFERENT windows hit different banks.
 struct WinState {
     double *base;       // p[5][wp] | weight[wp] | row[wp] (u32) | depth[wp] (u32)
     uint32_t wp;        // plane stride (windows, even)
@@ -352,18 +356,18 @@ __host__ __device__ inline uint32_t win_stride(uint32_t Wmax) { return (Wmax + 1
 
 struct WarpShared {
     WinState win;
-    uint16_t *ntc_start;   // [R+1]  compact candidate offset of every non-trivial read (+ end sentinel)
-    uint8_t *nt_assgn;     // [R]    current assignment of every non-trivial read
+    uint16_t *off;         // [R+1]  first candidate of every read (+ end sentinel)
+    uint16_t *nt_read;     // [R]    read ids of the non-trivial reads (more than one candidate), ascending
+    uint8_t *assgn;        // [R]    current assignment (candidate rank) of every read
+    uint32_t *unm_bits;    // [ceil(R/32)] bit r%32 of word r/32: read r has the "unmapped" option among its candidates
+    uint32_t *haps;        // [LCTP_MAX_PLOIDY] haplotypes of the genotype, then [LCTP_MAX_PLOIDY+1] window shifts
     uint32_t zero_row;     // offset of the all-zero row
     uint32_t depth_k;
 };
 __host__ __device__ inline size_t group_smem_bytes(uint32_t Wmax, uint32_t R) {
-    return (size_t)win_stride(Wmax) * 64 + align_up(((size_t)R + 1) * 2, 16) + align_up((size_t)R, 16);
-}
-
-__device__ __forceinline__ double rec_lp(const uint4 &r) { return __hiloint2double((int)r.y, (int)r.x); }
-__device__ __forceinline__ uint4 make_rec(double lp, uint32_t w) {
-    return make_uint4((uint32_t)__double2loint(lp), (uint32_t)__double2hiint(lp), w, 0u);
+    return (size_t)win_stride(Wmax) * 64 + align_up(((size_t)R + 1) * 2, 16) + align_up((size_t)R * 2, 16) +
+           align_up((size_t)R, 16) + align_up((size_t)((R + 31) / 32) * 4, 16) +
+           align_up((size_t)(2 * LCTP_MAX_PLOIDY + 1) * 4, 16);
 }
 
 // Recompute slice entry k of window w from its (weight, row, depth).
@@ -378,8 +382,7 @@ __device__ __forceinline__ double atomic_diff(const WarpShared &ws, uint32_t w, 
 }
 
 // depth_lik_diff (src/model/assgn.rs:259-284): ((a1 + a2) + a3) + a4, window merging done with selects
-__device__ __forceinline__ double depth_lik_diff(const WarpShared &ws, uint32_t w12, uint32_t w34) {
-    const uint32_t w1 = w12 & 0xFFFFu, w2 = w12 >> 16, w3 = w34 & 0xFFFFu, w4 = w34 >> 16;
+__device__ __forceinline__ double depth_lik_diff(const WarpShared &ws, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4) {
     const int e21 = w2 == w1, e31 = w3 == w1, e32 = (w3 == w2) & !e31;
     const int e41 = w4 == w1, e42 = (w4 == w2) & !e41, e43 = (w4 == w3) & !e41 & !e42;
     const int c1 = -1 - e21 + e31 + e41;
@@ -390,32 +393,52 @@ __device__ __forceinline__ double depth_lik_diff(const WarpShared &ws, uint32_t 
     s = __dadd_rn(s, atomic_diff(ws, w3, c3));
     return __dadd_rn(s, atomic_diff(ws, w4, c4));
 }
+template <bool WIDE>
+__device__ __forceinline__ double depth_lik_diff_raw(const WarpShared &ws, typename RecWord<WIDE>::T raw_old,
+                                                     typename RecWord<WIDE>::T raw_new) {
+    typedef RecWord<WIDE> RW;
+    return depth_lik_diff(ws, RW::w1(raw_old), RW::w2(raw_old), RW::w1(raw_new), RW::w2(raw_new));
+}
 
 // ------------------------------------------------------------------ a5: instance build ----------
 
 struct Instance {
-    uint32_t haps[LCTP_MAX_PLOIDY];
-    uint32_t wshift[LCTP_MAX_PLOIDY + 1];
-    uint32_t W, A, n_nt, A_nt;
+    uint32_t h0, h1;        // first two haplotypes of the genotype (registers); all of them are in ws.haps
+    uint32_t W, A, n_nt;
 };
+__device__ __forceinline__ uint32_t inst_hap(const Instance &I, const WarpShared &ws, uint32_t k) {
+    return k == 0 ? I.h0 : k == 1 ? I.h1 : ws.haps[k];
+}
+__device__ __forceinline__ uint32_t inst_wshift(const WarpShared &ws, uint32_t k) { return ws.haps[LCTP_MAX_PLOIDY + k]; }
+
+// Index into cm_lnprob of the ln-probability of the candidate with source byte s of read r (the reference's
+// ReadGtAlns::ln_prob).  b0 / b1: cm_off of the read on the first two haplotypes (the p <= 2 fast path has them).
+__device__ __forceinline__ uint32_t lp_index2(const LocusDev &L, uint32_t r, uint32_t s, uint32_t b0, uint32_t b1) {
+    return s == SRC_UNMAPPED ? L.npa + r : ((s >> 4) ? b1 : b0) + (s & 15u);
+}
+__device__ __forceinline__ uint32_t lp_index(const LocusDev &L, const Instance &I, const WarpShared &ws, uint32_t r,
+                                             uint32_t s) {
+    if (s == SRC_UNMAPPED) return L.npa + r;
+    return __ldg(L.cm_off + (size_t)inst_hap(I, ws, s >> 4) * L.R + r) + (s & 15u);
+}
 
 // GenotypeAlignments::new: per read, gather candidates of every genotype contig above the running
 // threshold, append the unmapped option, stable-sort descending (here: a p-way merge of the already
 // sorted per-contig lists, ties resolved in insertion order = contig order, unmapped last), cut at the
-// final threshold.  Returns false on slab overflow.
+// final threshold.  Returns false on overflow (more than min(cap, 65535) candidates).
 // HEADS > 0 (ploidy <= 2): the first HEADS ln-probs of each contig's run are fetched up front with
 // independent loads and the threshold / cut / merge run on registers; runs longer than HEADS fall back to
 // memory for the tail.  HEADS == 0: everything from memory (any ploidy).
-template <int GS, int HEADS>
-__device__ bool build_instance(const LocusDev &L, const Slab &S, const WarpShared &ws, uint32_t cap, Instance &I,
-                               const Grp<GS> &g) {
+template <int HEADS, bool WIDE>
+__device__ bool build_instance(const LocusDev &L, const Slab<WIDE> &S, const WarpShared &ws, uint32_t cap, Instance &I) {
     constexpr int PK = HEADS > 0 ? 2 : LCTP_MAX_PLOIDY;
     constexpr int HN = HEADS > 0 ? HEADS : 1;
     const uint32_t R = L.R, p = L.p;
-    const int lane = g.lane;
-    uint32_t base = 0, nt_base = 0, ntc_base = 0;
+    const int lane = lane_id();
+    const uint32_t lim = min(cap, 65535u);
+    uint32_t base = 0, nt_base = 0;
     bool ok = true;
-    for (uint32_t r0 = 0; r0 < R; r0 += GS) {
+    for (uint32_t r0 = 0; r0 < R; r0 += 32) {
         const uint32_t r = r0 + lane;
         const bool valid = r < R;
         uint32_t lb[PK], le[PK], l0[PK];
@@ -438,7 +461,7 @@ __device__ bool build_instance(const LocusDev &L, const Slab &S, const WarpShare
 #pragma unroll
             for (int k = 0; k < PK; k++) {
                 if ((uint32_t)k < p) {
-                    const size_t key = (size_t)I.haps[k] * R + r;
+                    const size_t key = (size_t)inst_hap(I, ws, k) * R + r;
                     lb[k] = l0[k] = L.cm_off[key];
                     le[k] = L.cm_off[key + 1];
                 } else lb[k] = le[k] = l0[k] = 0;
@@ -465,135 +488,168 @@ __device__ bool build_instance(const LocusDev &L, const Slab &S, const WarpShare
             nw += with_unm ? 1u : 0u;
         }
         const bool nt = valid && nw > 1;
-        const uint32_t nw_nt = nt ? nw : 0u;
-        uint32_t incl = nw, incl_nt = nw_nt;
+        uint32_t incl = nw;
 #pragma unroll
-        for (int d = 1; d < GS; d <<= 1) {
-            const uint32_t o = g.shfl_up(incl, d), o2 = g.shfl_up(incl_nt, d);
-            if (lane >= d) { incl += o; incl_nt += o2; }
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += o;
         }
-        const uint32_t total = g.shfl(incl, GS - 1), total_nt = g.shfl(incl_nt, GS - 1);
+        const uint32_t total = wshfl(incl, 31);
         const uint32_t start = base + incl - nw;
-        const uint32_t cstart = ntc_base + incl_nt - nw_nt;
-        const unsigned ntmask = g.ballot(nt);
-        if (valid) S.read_off[r] = start;
-        if (base + total > cap || ntc_base + total_nt > 65535u) ok = false;
+        const unsigned ntmask = wballot(nt);
+        const unsigned unmmask = wballot(with_unm);
+        if (base + total > lim) ok = false;
         if (ok && valid) {
-            if (nt) {
-                const uint32_t pos = nt_base + __popc(ntmask & g.lt());
-                ws.ntc_start[pos] = (uint16_t)cstart;
-                ws.nt_assgn[pos] = 0;
-            }
+            ws.off[r] = (uint16_t)start;
+            ws.assgn[r] = 0;
+            if (nt) ws.nt_read[nt_base + __popc(ntmask & lanes_lt())] = (uint16_t)r;
             bool unm_left = with_unm;
             const long long unm_key = total_key(unm);
             for (uint32_t t = 0; t < nw; t++) {
                 int bk = -1;
                 long long bkey = 0;
-                double bval = 0.0;
 #pragma unroll
                 for (int k = 0; k < PK; k++) {
                     if ((uint32_t)k < p && lb[k] < le[k]) {
-                        const double v = val(k, lb[k]);
-                        const long long key = total_key(v);
-                        if (bk < 0 || key > bkey) { bk = k; bkey = key; bval = v; }
+                        const long long key = total_key(val(k, lb[k]));
+                        if (bk < 0 || key > bkey) { bk = k; bkey = key; }
                     }
                 }
-                double lp;
                 uint32_t src;
                 if (bk >= 0 && !(unm_left && unm_key > bkey)) {
-                    lp = bval;
-                    uint32_t ix = 0;
+                    uint32_t ix = 0, first = 0;
 #pragma unroll
-                    for (int k = 0; k < PK; k++) if (k == bk) { ix = lb[k]; lb[k]++; }
-                    src = ix | ((uint32_t)bk << 28);
+                    for (int k = 0; k < PK; k++) if (k == bk) { ix = lb[k]; first = l0[k]; lb[k]++; }
+                    src = ((uint32_t)bk << 4) | (ix - first);
                 } else {
-                    lp = unm;
-                    src = LCTP_NONE_U32;
+                    src = SRC_UNMAPPED;
                     unm_left = false;
                 }
-                // windows stay [UNMAPPED_WINDOW; 2] = 0 until apply_tweak
-                if (nt) { S.cmap[start + t] = make_uint2(src, cstart + t); S.ntc[cstart + t] = make_rec(lp, 0u); }
-                else { S.cmap[start + t] = make_uint2(src, TRIV_TAG | r); S.triv_lp[r] = lp; S.triv_w[r] = 0u; }
+                S.rec[start + t] = RecWord<WIDE>::make(src, 0u, 0u);
             }
         }
+        if (lane == 0) ws.unm_bits[r0 >> 5] = unmmask;
         base += total;
-        ntc_base += total_nt;
         nt_base += __popc(ntmask);
     }
-    if (lane == 0) { S.read_off[R] = base; if (ok) ws.ntc_start[nt_base] = (uint16_t)ntc_base; }
+    if (lane == 0 && ok) ws.off[R] = (uint16_t)base;
     I.A = base;
     I.n_nt = nt_base;
-    I.A_nt = ntc_base;
-    g.sync();
+    __syncwarp();
     return ok;
 }
 
 // ------------------------------------------------------------------ a6: apply_tweak -------------
 
 // ContigInfo::get_shifted_window_ix (src/model/windows.rs:62-68,465-470)
-__device__ __forceinline__ uint32_t shifted_window(const LocusDev &L, uint32_t hap, uint32_t shift, uint32_t middle) {
-    const uint32_t start = L.hap_reg_start[hap];
-    const uint32_t end = start + L.hap_n_windows[hap] * L.window;
-    if (start <= middle && middle < end) return (middle - start) / L.window + shift;
+__device__ __forceinline__ uint32_t shifted_window(const LocusDev &L, uint32_t reg_start, uint32_t reg_end, uint32_t shift,
+                                                   uint32_t middle) {
+    if (reg_start <= middle && middle < reg_end) return (middle - reg_start) / L.window + shift;
     return 1;   // BOUNDARY_WINDOW
 }
 
-template <int GS>
-__device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I, const WarpShared &ws, Xo<GS> &rng) {
-    const Grp<GS> &g = rng.g;
-    const int lane = g.lane;
-    const uint32_t tweak = L.tweak;
+template <bool WIDE>
+__device__ void apply_tweak(const LocusDev &L, const Slab<WIDE> &S, const Instance &I, const WarpShared &ws, Xo &rng) {
+    typedef RecWord<WIDE> RW;
+    typedef typename RW::T Rec;
+    const int lane = lane_id();
+    const uint32_t tweak = L.tweak, R = L.R, p = L.p;
     const uint32_t span = 2 * tweak + 1;
-    // (i) read middles: one next_u64 per candidate that has a parent, in candidate order
-    for (uint32_t c0 = 0; c0 < I.A; c0 += GS) {
-        const uint32_t c = c0 + lane;
-        const uint2 cm = c < I.A ? S.cmap[c] : make_uint2(LCTP_NONE_U32, 0u);
-        const bool has_parent = cm.x != LCTP_NONE_U32;
-        uint64_t mine = 0;
-        if (tweak != 0) {
-            const unsigned m = g.ballot(has_parent);
-            const int my_rank = __popc(m & g.lt());
-            const int n_draws = __popc(m);
-            if (stream_cover(rng, (uint32_t)n_draws)) {
-                mine = stream_peek64(rng, (uint32_t)my_rank);
-                rng.pos += (uint32_t)n_draws;
-            } else {
-                for (int q = 0; q < n_draws; q++) {
-                    const uint64_t v = xo_next(rng);
-                    if (q == my_rank) mine = v;
+    // (i) read middles: one next_u64 per candidate that has a parent, in candidate order (read-major).
+    // Lanes over reads; a read's candidates take consecutive draws starting at the exclusive prefix sum of the
+    // parented-candidate counts, fetched from the draw buffer by index.  A batch that straddles the end of the
+    // fill is processed in two epochs with the refill in between.  Candidates are handled four at a time so that
+    // the dependent gathers (record -> pair-alignment middles, draw) of different candidates overlap.
+    for (uint32_t r0 = 0; r0 < R; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        const bool valid = r < R;
+        uint32_t o = 0, n = 0, b0 = 0, b1 = 0;
+        if (valid) {
+            o = ws.off[r];
+            n = (uint32_t)ws.off[r + 1] - o;
+            b0 = L.cm_off[(size_t)I.h0 * R + r];
+            if (p > 1) b1 = L.cm_off[(size_t)I.h1 * R + r];
+        }
+        const uint32_t has_unm = (ws.unm_bits[r0 >> 5] >> lane) & 1u;
+        const uint32_t npar = (tweak != 0 && valid) ? n - has_unm : 0u;
+        uint32_t incl = npar;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t total = wshfl(incl, 31);
+        const uint32_t q0 = incl - npar;
+        uint32_t done = 0;
+        for (;;) {
+            if (rng.pos == RNG_FILL && total > done) stream_refill(rng);
+            const uint32_t take = min(total - done, RNG_FILL - rng.pos);
+            uint32_t q = q0;
+            for (uint32_t j0 = 0; j0 < n; j0 += 4) {
+                Rec rc[4];
+                uint2 mid[4];
+                uint64_t draw[4];
+                uint32_t hap[4];
+                bool mine[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) rc[t] = j0 + t < n ? S.rec[o + j0 + t] : RW::make(SRC_UNMAPPED, 0u, 0u);
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const uint32_t sb = RW::src(rc[t]);
+                    const bool par = j0 + t < n && sb != SRC_UNMAPPED;
+                    mine[t] = par && (tweak == 0 ? done == 0 : (q >= done && q < done + take));
+                    mid[t] = make_uint2(0u, 0u); draw[t] = 0; hap[t] = 0;
+                    if (mine[t]) {
+                        const uint32_t k = sb >> 4;
+                        hap[t] = inst_hap(I, ws, k);
+                        const uint32_t cb = k == 0 ? b0 : k == 1 ? b1 : L.cm_off[(size_t)hap[t] * R + r];
+                        mid[t] = L.cm_mid[cb + (sb & 15u)];
+                        if (tweak != 0) draw[t] = __ldcg(rng.buf + rng.pos + (q - done));
+                    }
+                    q += par ? 1u : 0u;
+                }
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    if (j0 + t >= n) continue;
+                    const uint32_t sb = RW::src(rc[t]);
+                    if (sb == SRC_UNMAPPED) {
+                        if (done == 0) S.rec[o + j0 + t] = RW::make(SRC_UNMAPPED, 0u, 0u);   // [UNMAPPED_WINDOW; 2] (windows.rs:99-105)
+                    } else if (mine[t]) {
+                        const uint32_t shift = inst_wshift(ws, sb >> 4);
+                        const uint32_t reg_start = L.hap_reg_start[hap[t]];
+                        const uint32_t reg_end = reg_start + L.hap_n_windows[hap[t]] * L.window;
+                        const uint32_t t1 = tweak ? (uint32_t)(draw[t] >> 32) % span : 0u;
+                        const uint32_t t2 = tweak ? (uint32_t)draw[t] % span : 0u;
+                        const uint32_t w1 = mid[t].x == LCTP_NONE_U32 ? 0u : shifted_window(L, reg_start, reg_end, shift, mid[t].x + t1);
+                        const uint32_t w2 = mid[t].y == LCTP_NONE_U32 ? 0u : shifted_window(L, reg_start, reg_end, shift, mid[t].y + t2);
+                        S.rec[o + j0 + t] = RW::make(sb, w1, w2);
+                    }
                 }
             }
-        }
-        if (has_parent) {
-            const uint32_t k = cm.x >> 28;
-            const uint32_t hap = I.haps[k], shift = I.wshift[k];
-            const uint2 mid = L.cm_mid[cm.x & SRC_MASK];
-            const uint32_t t1 = tweak ? (uint32_t)(mine >> 32) % span : 0u;
-            const uint32_t t2 = tweak ? (uint32_t)mine % span : 0u;
-            const uint32_t w1 = mid.x == LCTP_NONE_U32 ? 0u : shifted_window(L, hap, shift, mid.x + t1);
-            const uint32_t w2 = mid.y == LCTP_NONE_U32 ? 0u : shifted_window(L, hap, shift, mid.y + t2);
-            const uint32_t w = w1 | (w2 << 16);
-            if (cm.y & TRIV_TAG) S.triv_w[cm.y & ~TRIV_TAG] = w;
-            else S.ntc[cm.y].z = w;
+            __syncwarp();            // every lane has read its draws of this epoch before the buffer is refilled
+            rng.pos += take;
+            done += take;
+            if (done >= total) break;
         }
     }
     // (ii) window distributions: one bounded i32 draw per window, contigs in genotype order
     if (lane < 2) { ws.win.weight(lane) = 0.0; ws.win.row(lane) = ws.zero_row; ws.win.depth(lane) = 0; }
-    for (uint32_t k = 0; k < L.p; k++) {
-        const uint32_t hap = I.haps[k];
+    for (uint32_t k = 0; k < p; k++) {
+        const uint32_t hap = inst_hap(I, ws, k);
         const uint32_t nwin = L.hap_n_windows[hap];
         const uint32_t reg_start = L.hap_reg_start[hap], hlen = L.hap_len[hap];
         const uint64_t pos_off = L.hap_pos_off[hap];
-        for (uint32_t i0 = 0; i0 < nwin; i0 += GS) {
-            const uint32_t cnt = min((uint32_t)GS, nwin - i0);
+        const uint32_t wsh = inst_wshift(ws, k);
+        for (uint32_t i0 = 0; i0 < nwin; i0 += 32) {
+            const uint32_t cnt = min(32u, nwin - i0);
             uint32_t my_wstart = 0;
             {
                 // generate_windows (windows.rs:478-486): random_range(-left..=right), one per window
                 const uint32_t start = reg_start + (i0 + min((uint32_t)lane, cnt - 1u)) * L.window;
                 const uint32_t end = start + L.window;
                 const uint32_t left = min(tweak, start), right = min(tweak, hlen - end);
-                uint32_t rr;
-                if (xo_below_parallel(rng, cnt, left + right + 1u, rr)) my_wstart = start + rr - left;
+                uint32_t rr = 0;
+                if (xo_below_lanes(rng, cnt, left + right + 1u, rr)) my_wstart = start + rr - left;
                 else {
                     for (uint32_t q = 0; q < cnt; q++) {
                         const uint32_t st_q = reg_start + (i0 + q) * L.window;
@@ -608,7 +664,7 @@ __device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I,
                 const uint32_t idx = my_wstart > L.left_padding ? my_wstart - L.left_padding : 0u;
                 const double weight = L.pos_weight[pos_off + idx];
                 const uint32_t gc = L.pos_gc[pos_off + idx];
-                const uint32_t w = I.wshift[k] + i0 + lane;
+                const uint32_t w = wsh + i0 + lane;
                 const bool trivial = weight < L.min_weight || weight < 1e-7;
                 ws.win.weight(w) = trivial ? 0.0 : weight;
                 ws.win.row(w) = trivial ? ws.zero_row : gc * L.depth_k;
@@ -616,79 +672,68 @@ __device__ void apply_tweak(const LocusDev &L, const Slab &S, const Instance &I,
             }
         }
     }
-    g.sync();
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------ a8: ReadAssignment::new -----
 
 // Sequentially (in index order) add `count` per-lane terms to acc: reproduces iter().sum() order.
-template <int GS>
-__device__ __forceinline__ void seq_add(const Grp<GS> &g, double &acc, double term, int count) {
-    for (int q = 0; q < count; q++) acc = __dadd_rn(acc, g.shfl(term, q));
+__device__ __forceinline__ void seq_add(double &acc, double term, int count) {
+    for (int q = 0; q < count; q++) acc = __dadd_rn(acc, wshfl(term, q));
 }
 
 // init_mode 0: every read at candidate 0; 1: random_range(0..m) per non-trivial read (read order).
-template <int GS>
-__device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance &I, const WarpShared &ws,
-                                Xo<GS> &rng, int init_mode, double &aln_lik, double &depth_lik) {
-    const Grp<GS> &g = rng.g;
-    const int lane = g.lane;
-    for (uint32_t w = lane; w < I.W; w += GS) ws.win.depth(w) = 0;
-    // assignments of non-trivial reads
-    for (uint32_t i0 = 0; i0 < I.n_nt; i0 += GS) {
-        const uint32_t i = i0 + lane;
-        const uint32_t my_n = i < I.n_nt ? (uint32_t)(ws.ntc_start[i + 1] - ws.ntc_start[i]) : 1u;
-        uint32_t a = 0;
-        if (init_mode == 1) {
-            const int cnt = (int)min((uint32_t)GS, I.n_nt - i0);
-            if (!xo_below_parallel(rng, (uint32_t)cnt, my_n, a)) {
-                for (int q = 0; q < cnt; q++) {
-                    const uint32_t m = g.shfl(my_n, q);
+template <bool WIDE>
+__device__ void init_assignment(const LocusDev &L, const Slab<WIDE> &S, const Instance &I, const WarpShared &ws,
+                                Xo &rng, int init_mode, double &aln_lik, double &depth_lik) {
+    typedef RecWord<WIDE> RW;
+    const int lane = lane_id();
+    const uint32_t R = L.R;
+    for (uint32_t w = lane; w < I.W; w += 32) ws.win.depth(w) = 0;
+    // assignments: trivial reads stay at 0
+    for (uint32_t r = lane; r < R; r += 32) ws.assgn[r] = 0;
+    __syncwarp();
+    if (init_mode == 1) {
+        for (uint32_t i0 = 0; i0 < I.n_nt; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint32_t r = 0, my_n = 1;
+            if (i < I.n_nt) { r = ws.nt_read[i]; my_n = (uint32_t)ws.off[r + 1] - ws.off[r]; }
+            uint32_t a = 0;
+            const uint32_t cnt = min(32u, I.n_nt - i0);
+            if (!xo_below_lanes(rng, cnt, my_n, a)) {
+                for (uint32_t q = 0; q < cnt; q++) {
+                    const uint32_t m = wshfl(my_n, (int)q);
                     const uint32_t v = xo_below(rng, m);
-                    if (lane == q) a = v;
+                    if ((uint32_t)lane == q) a = v;
                 }
             }
+            if (i < I.n_nt) ws.assgn[r] = (uint8_t)a;
         }
-        if (i < I.n_nt) ws.nt_assgn[i] = (uint8_t)a;
+        __syncwarp();
     }
-    g.sync();
     // depth counts + aln_lik in read order (src/model/assgn.rs:205-217,351-353)
     double al = 0.0;
-    uint32_t nt_base = 0;
-    for (uint32_t r0 = 0; r0 < L.R; r0 += GS) {
+    for (uint32_t r0 = 0; r0 < R; r0 += 32) {
         const uint32_t r = r0 + lane;
-        const bool valid = r < L.R;
-        uint32_t start = 0, nw = 0;
-        if (valid) { start = S.read_off[r]; nw = S.read_off[r + 1] - start; }
-        const bool nt = valid && nw > 1;
-        const unsigned ntmask = g.ballot(nt);
         double term = 0.0;
-        if (valid) {
-            uint32_t w12;
-            if (nt) {
-                const uint32_t pos = nt_base + __popc(ntmask & g.lt());
-                const uint4 rec = S.ntc[(uint32_t)ws.ntc_start[pos] + ws.nt_assgn[pos]];
-                term = rec_lp(rec);
-                w12 = rec.z;
-            } else {
-                term = S.triv_lp[r];
-                w12 = S.triv_w[r];
-            }
-            atomicAdd(&ws.win.depth(w12 & 0xFFFFu), 1u);
-            atomicAdd(&ws.win.depth(w12 >> 16), 1u);
+        if (r < R) {
+            const uint32_t c = (uint32_t)ws.off[r] + ws.assgn[r];
+            const typename RW::T raw = S.rec[c];
+            term = __ldg(L.cm_lnprob + lp_index(L, I, ws, r, RW::src(raw)));
+            atomicAdd(&ws.win.depth(RW::w1(raw)), 1u);
+            atomicAdd(&ws.win.depth(RW::w2(raw)), 1u);
         }
-        nt_base += __popc(ntmask);
-        seq_add(g, al, term, (int)min((uint32_t)GS, L.R - r0));
+        seq_add(al, term, (int)min(32u, R - r0));
     }
-    g.sync();
-    for (uint32_t q = lane; q < I.W * 5u; q += GS) win_refresh(ws, L.depth_table, q / 5u, (int)(q % 5u));
-    g.sync();
+    __syncwarp();
+    for (uint32_t q = lane; q < I.W * 5u; q += 32) win_refresh(ws, L.depth_table, q / 5u, (int)(q % 5u));
+    __syncwarp();
     // depth_lik in window order (assgn.rs:347-350)
     double dl = 0.0;
-    for (uint32_t w0 = 0; w0 < I.W; w0 += GS) {
+    for (uint32_t w0 = 0; w0 < I.W; w0 += 32) {
         const uint32_t w = w0 + lane;
         const double term = w < I.W ? ws.win.p(w, 2) : 0.0;
-        seq_add(g, dl, term, (int)min((uint32_t)GS, I.W - w0));
+        seq_add(dl, term, (int)min(32u, I.W - w0));
     }
     aln_lik = al;
     depth_lik = dl;
@@ -696,319 +741,578 @@ __device__ void init_assignment(const LocusDev &L, const Slab &S, const Instance
 
 // ------------------------------------------------------------------ a9: targets -----------------
 
-struct Target { uint32_t idx, n, old_a, new_a, old_ix, new_ix; };   // *_ix index the compact arrays
+template <bool WIDE>
+struct Move { double dld, dlp; typename RecWord<WIDE>::T raw_old, raw_new; };
 
-// ReassignmentTarget::random (src/model/assgn.rs:451-471), group-uniform
-template <int GS>
-__device__ __forceinline__ Target random_target(const WarpShared &ws, const Instance &I, Xo<GS> &rng) {
-    Target t;
-    t.idx = xo_below(rng, I.n_nt);                     // random_range(0..n_nontrivial), usize via the u32 path
-    const uint32_t start = ws.ntc_start[t.idx];
-    t.n = ws.ntc_start[t.idx + 1] - start;
-    t.old_a = ws.nt_assgn[t.idx];
-    if (t.n == 2) t.new_a = 1u - t.old_a;
-    else {
-        const uint32_t i = 1u + xo_below(rng, t.n - 1u);   // random_range(1..n as u16)
-        t.new_a = i <= t.old_a ? i - 1u : i;
+// calculate_improvement (src/model/assgn.rs:321-328) for moving read r (candidates at o..) from rank a to new_a
+template <bool WIDE>
+__device__ __forceinline__ double calc_improvement(const LocusDev &L, const Slab<WIDE> &S, const Instance &I,
+                                                   const WarpShared &ws, uint32_t r, uint32_t o, uint32_t a,
+                                                   uint32_t new_a, Move<WIDE> &mv) {
+    typedef RecWord<WIDE> RW;
+    mv.raw_old = S.rec[o + a];
+    mv.raw_new = S.rec[o + new_a];
+    const uint32_t so = RW::src(mv.raw_old), sn = RW::src(mv.raw_new);
+    uint32_t io, in;
+    if (L.p <= 2) {
+        const uint32_t b0 = __ldg(L.cm_off + (size_t)I.h0 * L.R + r);
+        const uint32_t b1 = L.p > 1 ? __ldg(L.cm_off + (size_t)I.h1 * L.R + r) : 0u;
+        io = lp_index2(L, r, so, b0, b1);
+        in = lp_index2(L, r, sn, b0, b1);
+    } else {
+        io = lp_index(L, I, ws, r, so);
+        in = lp_index(L, I, ws, r, sn);
     }
-    t.old_ix = start + t.old_a;
-    t.new_ix = start + t.new_a;
-    return t;
-}
-
-struct Move { double dld, dlp; uint32_t w12, w34; };
-
-// calculate_improvement (src/model/assgn.rs:321-328)
-__device__ __forceinline__ double calc_improvement(const LocusDev &L, const Slab &S, const WarpShared &ws,
-                                                   const Target &t, Move &mv) {
-    const uint4 ro = __ldcg(S.ntc + t.old_ix), rn = __ldcg(S.ntc + t.new_ix);
-    mv.w12 = ro.z;
-    mv.w34 = rn.z;
-    mv.dld = depth_lik_diff(ws, mv.w12, mv.w34);
-    mv.dlp = __dsub_rn(rec_lp(rn), rec_lp(ro));
+    const double lpo = __ldg(L.cm_lnprob + io), lpn = __ldg(L.cm_lnprob + in);
+    mv.dld = depth_lik_diff_raw<WIDE>(ws, mv.raw_old, mv.raw_new);
+    mv.dlp = __dsub_rn(lpn, lpo);
     return __dadd_rn(__dmul_rn(L.depth_contrib, mv.dld), __dmul_rn(L.aln_contrib, mv.dlp));
 }
 
-// reassign (src/model/assgn.rs:331-343); group-uniform inputs, lane 0 writes
-template <int GS>
-__device__ __forceinline__ void apply_move(const Grp<GS> &g, const WarpShared &ws, const double *__restrict__ table,
-                                           uint32_t idx, uint32_t new_a, const Move &mv, double &aln_lik,
-                                           double &depth_lik) {
+// reassign (src/model/assgn.rs:331-343); warp-uniform inputs, lane 0 writes
+template <bool WIDE>
+__device__ __forceinline__ void apply_move(const WarpShared &ws, const double *__restrict__ table, uint32_t r,
+                                           uint32_t new_a, const Move<WIDE> &mv, double &aln_lik, double &depth_lik) {
+    typedef RecWord<WIDE> RW;
     depth_lik = __dadd_rn(depth_lik, mv.dld);
     aln_lik = __dadd_rn(aln_lik, mv.dlp);
-    if (g.lane == 0) {
-        ws.win.depth(mv.w34 & 0xFFFFu) += 1;
-        ws.win.depth(mv.w34 >> 16) += 1;
-        ws.win.depth(mv.w12 & 0xFFFFu) -= 1;
-        ws.win.depth(mv.w12 >> 16) -= 1;
-        ws.nt_assgn[idx] = (uint8_t)new_a;
+    const uint32_t w1 = RW::w1(mv.raw_old), w2 = RW::w2(mv.raw_old), w3 = RW::w1(mv.raw_new), w4 = RW::w2(mv.raw_new);
+    if (lane_id() == 0) {
+        ws.win.depth(w3) += 1;
+        ws.win.depth(w4) += 1;
+        ws.win.depth(w1) -= 1;
+        ws.win.depth(w2) -= 1;
+        ws.assgn[r] = (uint8_t)new_a;
     }
-    g.sync();
+    __syncwarp();
     // slide the product slices of the (up to four) windows whose depth changed
-    for (int q = g.lane; q < 20; q += GS) {
+    for (int q = lane_id(); q < 20; q += 32) {
         const int j = q / 5;
-        const uint32_t w = j == 0 ? (mv.w12 & 0xFFFFu) : j == 1 ? (mv.w12 >> 16) : j == 2 ? (mv.w34 & 0xFFFFu) : (mv.w34 >> 16);
+        const uint32_t w = j == 0 ? w1 : j == 1 ? w2 : j == 2 ? w3 : w4;
         win_refresh(ws, table, w, q % 5);
     }
-    g.sync();
+    __syncwarp();
 }
 
-// max_abs_random (src/solvers/stoch.rs:19-22) with INIT_ITER = 100
-template <int GS>
-__device__ double max_abs_random(const LocusDev &L, const Slab &S, const Instance &I, const WarpShared &ws, Xo<GS> &rng) {
+// One random reassignment target, warp-uniform: ReassignmentTarget::random (src/model/assgn.rs:451-471)
+struct Target { uint32_t r, o, a, new_a; };
+__device__ __forceinline__ Target random_target(const WarpShared &ws, const Instance &I, Xo &rng) {
+    Target t;
+    const uint32_t idx = xo_below(rng, I.n_nt);              // random_range(0..n_nontrivial), usize via the u32 path
+    t.r = ws.nt_read[idx];
+    t.o = ws.off[t.r];
+    const uint32_t n = (uint32_t)ws.off[t.r + 1] - t.o;
+    t.a = ws.assgn[t.r];
+    if (n == 2) t.new_a = 1u - t.a;
+    else {
+        const uint32_t i = 1u + xo_below(rng, n - 1u);       // random_range(1..n as u16)
+        t.new_a = i <= t.a ? i - 1u : i;
+    }
+    return t;
+}
+
+// Speculative chain of random targets.  The steps of max_abs_random and of the annealing loops each consume a
+// data-dependent number of draws (one for the read, one more when the read has more than two candidates, and in
+// the annealing phase the U(0,1) of a rejected step), so step j+1 starts where step j ended.  Every lane l
+// computes the step that WOULD start at stream position pos + l; the lanes actually on the chain 0 -> next(0)
+// -> ... are found by pointer doubling, and all of them evaluate their target against the CURRENT state in
+// parallel.  That is exact as long as no earlier step of the chain changes the state, i.e. up to and including
+// the first accepted step -- the caller commits exactly that prefix and leaves the rest of the draws in the
+// stream.  A step that would need a bias-correction draw, or that does not fit in the register window, ends
+// the chain; the caller then takes one step on the sequential path (which refills / handles the bias).
+struct Spec {
+    bool usable;                 // this lane holds step `rank` of the chain
+    uint32_t rank, count;        // count = usable steps (a prefix of the chain)
+    uint32_t r, o, a, new_a;     // the step's target
+    uint32_t nd;                 // draws of the target itself (1 or 2)
+    uint64_t udraw;              // the draw after them
+    unsigned umask;              // lanes holding usable steps
+};
+template <bool WITH_U>
+__device__ __forceinline__ void spec_targets(const WarpShared &ws, const Instance &I, Xo &rng, Spec &sp) {
+    const uint32_t lane = (uint32_t)lane_id();
+    sp.usable = false; sp.rank = 0; sp.count = 0; sp.umask = 0u;
+    sp.r = sp.o = sp.a = sp.new_a = 0; sp.nd = 1; sp.udraw = 0;
+    if (rng.pos >= RNG_FILL) return;
+    stream_cover(rng, 1);
+    const uint32_t avail = min(32u, RNG_FILL - rng.pos);
+    const uint64_t d = stream_peek64(rng, lane);
+    const uint64_t d1 = __shfl_down_sync(FULL, d, 1), d2 = __shfl_down_sync(FULL, d, 2);
+    const uint64_t m = (d >> 32) * (uint64_t)I.n_nt;
+    const bool bias1 = (uint32_t)m > 0u - I.n_nt;
+    const uint32_t idx = (uint32_t)(m >> 32);
+    sp.r = ws.nt_read[idx];
+    sp.o = ws.off[sp.r];
+    const uint32_t n = (uint32_t)ws.off[sp.r + 1] - sp.o;
+    sp.a = ws.assgn[sp.r];
+    const bool two = n > 2;
+    const uint64_t m2 = (d1 >> 32) * (uint64_t)(n - 1u);
+    const bool bias2 = two && (uint32_t)m2 > 0u - (n - 1u);
+    const uint32_t i2 = 1u + (uint32_t)(m2 >> 32);
+    sp.new_a = two ? (i2 <= sp.a ? i2 - 1u : i2) : 1u - sp.a;
+    sp.nd = two ? 2u : 1u;
+    sp.udraw = two ? d2 : d1;
+    const uint32_t len = sp.nd + (WITH_U ? 1u : 0u);
+    const bool ok = lane + len <= avail && !bias1 && !bias2;
+    // chain membership by pointer doubling: S_{t+1} = S_t u jump_t(S_t), jump_{t+1} = jump_t o jump_t
+    uint32_t jump = ok ? lane + len : 32u;
+    unsigned chain = 1u;
+#pragma unroll
+    for (int t = 0; t < 5; t++) {
+        const unsigned contrib = (((chain >> lane) & 1u) && jump < 32u) ? (1u << jump) : 0u;
+        chain |= __reduce_or_sync(FULL, contrib);
+        const uint32_t j2 = wshfl(jump, (int)(jump & 31u));
+        jump = jump < 32u ? j2 : 32u;
+    }
+    const bool on = (chain >> lane) & 1u;
+    const unsigned bad = wballot(on && !ok);
+    const uint32_t first_bad = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
+    sp.usable = on && lane < first_bad;
+    sp.umask = wballot(sp.usable);
+    sp.rank = __popc(sp.umask & lanes_lt());
+    sp.count = __popc(sp.umask);
+}
+// stream position (relative to rng.pos) right after the first `e` steps of the chain, e <= count
+__device__ __forceinline__ uint32_t spec_offset_after(const Spec &sp, uint32_t e, uint32_t len_mine) {
+    if (e == 0) return 0u;
+    const unsigned sel = wballot(sp.usable && sp.rank == e - 1u);
+    const int src = __ffs(sel) - 1;
+    return wshfl((uint32_t)lane_id() + len_mine, src);
+}
+
+// max_abs_random (src/solvers/stoch.rs:19-22) with INIT_ITER = 100: the state does not change, so whole
+// chains are consumed.
+template <bool WIDE>
+__device__ double max_abs_random(const LocusDev &L, const Slab<WIDE> &S, const Instance &I, const WarpShared &ws, Xo &rng) {
     double acc = 0.0;
-    for (int q = 0; q < 100; q++) {
-        const Target t = random_target(ws, I, rng);
-        Move mv;
-        acc = fmax(acc, fabs(calc_improvement(L, S, ws, t, mv)));
+    uint32_t left = 100;
+    while (left > 0) {
+        Spec sp;
+        spec_targets<false>(ws, I, rng, sp);
+        if (sp.count == 0) {
+            const Target t = random_target(ws, I, rng);
+            Move<WIDE> mv;
+            acc = fmax(acc, fabs(calc_improvement<WIDE>(L, S, I, ws, t.r, t.o, t.a, t.new_a, mv)));
+            left--;
+            continue;
+        }
+        const uint32_t e = min(sp.count, left);
+        double v = 0.0;
+        if (sp.usable && sp.rank < e) {
+            Move<WIDE> mv;
+            v = fabs(calc_improvement<WIDE>(L, S, I, ws, sp.r, sp.o, sp.a, sp.new_a, mv));
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, d));
+        acc = fmax(acc, v);
+        rng.pos += spec_offset_after(sp, e, sp.nd);
+        left -= e;
     }
     return acc;
 }
 
 // ------------------------------------------------------------------ a10: Greedy -----------------
 
-// Lane layout of the greedy loop: the `amount` sampled reads ("slots") each own LPS = GS / amount
-// consecutive lanes; lane (slot, rank) evaluates the rank-th alternative candidate of its slot's read
-// (further alternatives, when a read has more than LPS of them, in extra passes).  The mapping is fixed
-// for the whole solve, so an iteration needs no scan / flattening, and the candidate records of the NEXT
-// sample are prefetched into registers while the current sample is evaluated.
-struct SlotMap {
-    uint32_t lps, slot, rank, range;     // range = j_slot + 1 of Floyd's draw for this slot
-    bool valid;
-    unsigned lead_mask;                  // group-relative mask of the rank-0 lanes of the valid slots
-};
-
 // One sample of `amount` distinct non-trivial reads (IndexedRandom::sample -> index::sample_floyd):
 // draw k is random_range(..=j_k), j_k = n_nt - amount + k; a draw equal to an earlier entry replaces
-// that entry by j_k.  Every lane of slot k receives entry k.  `fast_only`: succeed only through the
-// lane-parallel path (no refill, no biased draw), so the caller can un-consume the draws again with
-// `rng.pos -= amount`.
-template <int GS>
-__device__ __forceinline__ bool sample_reads(Xo<GS> &rng, const SlotMap &sm, uint32_t n_nt, uint32_t amount,
-                                             bool fast_only, uint32_t &myv) {
-    const Grp<GS> &g = rng.g;
-    bool fast = false;
-    if (stream_cover(rng, amount)) {
-        const uint64_t m = (uint64_t)stream_peek_hi(rng, sm.slot) * (uint64_t)sm.range;
-        if (!g.any(sm.valid && (uint32_t)m > 0u - sm.range)) {
-            myv = (uint32_t)(m >> 32);
-            rng.pos += amount;
-            fast = true;
-        }
-    }
-    if (!fast) {
-        if (fast_only) return false;
-        for (uint32_t k = 0; k < amount; k++) {
-            const uint32_t t = xo_below(rng, n_nt - amount + k + 1u);
-            if (sm.slot == k) myv = t;
-        }
-    }
-    const unsigned peers = g.match_any(sm.valid ? myv : 0xFFFFFFFFu);
-    if (g.any(sm.valid && (peers & sm.lead_mask) != (1u << (sm.slot * sm.lps)))) {
-        for (uint32_t k = 1; k < amount; k++) {
-            const uint32_t t = g.shfl(myv, (int)(k * sm.lps));
-            if (sm.slot < k && myv == t) myv = n_nt - amount + k;
-        }
+// that entry by j_k.  Lane k < amount receives draw k; sample_resolve applies the replacements.
+// `slow`: take the draws one at a time (refills, bias correction) instead of through the lane-parallel path;
+// the lane-parallel path consumes exactly `amount` draws of the current fill or nothing at all.
+__device__ __forceinline__ bool sample_draw(Xo &rng, uint32_t n_nt, uint32_t amount, bool slow, uint32_t &myv) {
+    const uint32_t lane = (uint32_t)lane_id();
+    if (!slow) return xo_below_lanes(rng, amount, n_nt - amount + min(lane, amount - 1u) + 1u, myv);
+    for (uint32_t k = 0; k < amount; k++) {
+        const uint32_t t = xo_below(rng, n_nt - amount + k + 1u);
+        if (lane == k) myv = t;
     }
     return true;
 }
+// lanes holding equal draws (evaluated one pipeline stage after it is issued: MATCH.ANY takes ~250 cycles)
+__device__ __forceinline__ unsigned sample_peers(uint32_t amount, uint32_t myv) {
+    const uint32_t lane = (uint32_t)lane_id();
+    return __match_any_sync(FULL, lane < amount ? myv : 0xFFFFFF00u + lane);
+}
+__device__ __forceinline__ void sample_resolve(uint32_t n_nt, uint32_t amount, unsigned peers, uint32_t &myv) {
+    const uint32_t lane = (uint32_t)lane_id();
+    if (wany(lane < amount && peers != (1u << lane))) {
+        for (uint32_t k = 1; k < amount; k++) {
+            const uint32_t t = wshfl(myv, (int)k);
+            if (lane < k && myv == t) myv = n_nt - amount + k;
+        }
+    }
+}
+
+// job word of a lane: read id | slot << 16 | candidate rank << 24 (slot < 16, rank < 256)
+__device__ __forceinline__ uint32_t job_r(uint32_t j) { return j & 0xFFFFu; }
+__device__ __forceinline__ uint32_t job_slot(uint32_t j) { return (j >> 16) & 0xFFu; }
+__device__ __forceinline__ uint32_t job_c(uint32_t j) { return j >> 24; }
+__device__ __forceinline__ uint32_t alt_rank(uint32_t rank, uint32_t a) { return rank < a ? rank : rank + 1u; }
 
 // A candidate move as seen by one lane, ordered like the reference's two nested strict-'>' scans:
 // larger improvement `s` first; among equal `s` the earlier sampled read (slot); inside that read the
 // larger `improv` (pre-scaling value compared by best_read_improvement), then the lower candidate index.
+template <bool WIDE>
 struct Cand {
     double s, improv, dld, dlp;
-    uint32_t slot, c, w12, w34;
+    uint32_t job;
+    typename RecWord<WIDE>::T raw_old, raw_new;
 };
-__device__ __forceinline__ bool cand_better(const Cand &a, const Cand &b) {
+template <bool WIDE>
+__device__ __forceinline__ bool cand_better(const Cand<WIDE> &a, const Cand<WIDE> &b) {
     if (a.s != b.s) return a.s > b.s;
-    if (a.slot != b.slot) return a.slot < b.slot;
+    if (job_slot(a.job) != job_slot(b.job)) return job_slot(a.job) < job_slot(b.job);
     if (a.improv != b.improv) return a.improv > b.improv;
-    return a.c < b.c;
+    return job_c(a.job) < job_c(b.job);
 }
 
-// The sampled read of this lane's slot and the two candidate records the lane works on.
-struct SlotRead {
-    uint32_t idx, start, n, old_a;
-    uint4 ro, rn;       // current candidate, and alternative #rank (valid when rank < n - 1)
+// Prefetch pipeline of the greedy loop.  The jobs of an iteration -- every (sampled read, alternative candidate)
+// pair, "flattened" best_read_improvement (src/model/assgn.rs:287-317) -- are dealt to the lanes by an exclusive
+// prefix sum over the sampled reads' alternative counts, so that (almost always) ONE evaluation pass covers the
+// whole sample whatever the candidate counts are.  A job's data is two dependent hops away (private candidate
+// records + the read's run offsets, then the shared ln-probabilities), so samples are drawn three iterations
+// ahead and move through four stages, one per loop round:
+//   S  sample drawn, duplicate check (MATCH.ANY) in flight
+//   A  jobs dealt, first-hop loads in flight
+//   B  second-hop loads in flight
+//   C  evaluated: touches only registers and shared memory
+// The loop body has exactly one site for each group of loads (a stage that has nothing to do is skipped, an empty
+// pipeline refills through the same code), so that the hardware scoreboard slots of one group never alias
+// another's: with several code paths issuing the same loads the evaluation waited on loads issued a few
+// instructions earlier (ncu: 10 % of the kernel in one DADD).
+template <bool WIDE>
+struct SlotA {
+    uint32_t job;               // this lane's job (valid for lanes < min(total, 32))
+    typename RecWord<WIDE>::T ro, rn;   // records of the current / this lane's alternative candidate
+    uint32_t b0, b1;            // cm_off of the read on the genotype's first two haplotypes
+    uint32_t lead;              // lanes < amount: sampled non-trivial read index | first job position << 16
+    uint32_t total;             // jobs of the sample (warp-uniform)
 };
-template <int GS>
-__device__ __forceinline__ void load_slot(const Slab &S, const WarpShared &ws, const SlotMap &sm, uint32_t idx,
-                                          SlotRead &r) {
-    r.idx = idx;
-    r.start = ws.ntc_start[idx];
-    r.n = ws.ntc_start[idx + 1] - r.start;
-    r.old_a = ws.nt_assgn[idx];
-    const uint32_t c = sm.rank < r.old_a ? sm.rank : sm.rank + 1u;
-    r.ro = __ldcg(S.ntc + r.start + r.old_a);
-    r.rn = __ldcg(S.ntc + r.start + min(c, r.n - 1u));
+template <bool WIDE>
+struct SlotB {
+    uint32_t job, lead, total;
+    typename RecWord<WIDE>::T ro, rn;
+    double lpo, lpn;
+};
+
+// Deal the jobs of the sample `myv` (lane k < amount holds the k-th sampled read) and issue the first-hop loads.
+template <bool WIDE>
+__device__ __forceinline__ void load_slot_a(const LocusDev &L, const Slab<WIDE> &S, const Instance &I,
+                                            const WarpShared &ws, uint32_t amount, uint32_t myv, SlotA<WIDE> &x) {
+    const uint32_t lane = (uint32_t)lane_id();
+    const bool lead = lane < amount;
+    uint32_t lr = 0, n_alt = 0;
+    if (lead) {
+        lr = ws.nt_read[myv];
+        n_alt = (uint32_t)ws.off[lr + 1] - ws.off[lr] - 1u;
+    }
+    uint32_t incl = n_alt;
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {              // amount <= 11: four rounds
+        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
+    }
+    x.total = wshfl(incl, (int)amount - 1);
+    const uint32_t first = incl - n_alt;
+    x.lead = myv | (first << 16);
+    const unsigned starts = __reduce_or_sync(FULL, (lead && first < 32u) ? (1u << first) : 0u);
+    const uint32_t slot = (uint32_t)__popc(starts & (0xFFFFFFFFu >> (31u - lane))) - 1u;   // starts has bit 0 set
+    const uint32_t r = wshfl(lr, (int)slot);
+    const uint32_t alt = lane - wshfl(first, (int)slot);
+    const uint32_t o = ws.off[r];
+    const uint32_t n = (uint32_t)ws.off[r + 1] - o;
+    const uint32_t a = ws.assgn[r];
+    const uint32_t c = min(alt_rank(alt, a), n - 1u);     // lanes >= total: clamped, loaded, never evaluated
+    x.job = r | (slot << 16) | (c << 24);
+    x.ro = S.rec[o + a];
+    x.rn = S.rec[o + c];
+    x.b0 = __ldg(L.cm_off + (size_t)I.h0 * L.R + r);
+    x.b1 = L.p > 1 ? __ldg(L.cm_off + (size_t)I.h1 * L.R + r) : 0u;
+}
+template <bool WIDE>
+__device__ __forceinline__ void load_slot_b(const LocusDev &L, const Instance &I, const WarpShared &ws,
+                                            const SlotA<WIDE> &x, SlotB<WIDE> &y) {
+    typedef RecWord<WIDE> RW;
+    y.job = x.job; y.ro = x.ro; y.rn = x.rn; y.lead = x.lead; y.total = x.total;
+    const uint32_t r = job_r(x.job);
+    uint32_t io, in;
+    if (L.p <= 2) { io = lp_index2(L, r, RW::src(x.ro), x.b0, x.b1); in = lp_index2(L, r, RW::src(x.rn), x.b0, x.b1); }
+    else { io = lp_index(L, I, ws, r, RW::src(x.ro)); in = lp_index(L, I, ws, r, RW::src(x.rn)); }
+    y.lpo = __ldg(L.cm_lnprob + io);
+    y.lpn = __ldg(L.cm_lnprob + in);
+}
+// A move of read w_r was applied: the in-flight jobs on that read saw its old assignment.
+template <bool WIDE>
+__device__ __forceinline__ void reload_slot_a(const Slab<WIDE> &S, const WarpShared &ws, uint32_t w_r, uint32_t old_a,
+                                              SlotA<WIDE> &x) {
+    if (job_r(x.job) == w_r) {
+        const uint32_t o = ws.off[w_r], n = (uint32_t)ws.off[w_r + 1] - o, a = ws.assgn[w_r];
+        // this lane's alternative number: invert alt_rank under the old assignment, redo it under the new one
+        const uint32_t c_old = job_c(x.job);
+        const uint32_t alt = c_old > old_a ? c_old - 1u : c_old;
+        const uint32_t c = min(alt_rank(alt, a), n - 1u);
+        x.job = (x.job & 0x00FFFFFFu) | (c << 24);
+        x.ro = S.rec[o + a];
+        x.rn = S.rec[o + c];
+    }
 }
 
-__device__ __forceinline__ void eval_cand(const LocusDev &L, const WarpShared &ws, const uint4 &ro, const uint4 &rn,
-                                          uint32_t slot, uint32_t c, Cand &cd) {
-    const double lp_old = rec_lp(ro), lp = rec_lp(rn);
-    cd.dld = depth_lik_diff(ws, ro.z, rn.z);
+template <bool WIDE>
+__device__ __forceinline__ void eval_cand(const LocusDev &L, const WarpShared &ws, double lp_old, double lp,
+                                          typename RecWord<WIDE>::T raw_old, typename RecWord<WIDE>::T raw_new,
+                                          uint32_t job, Cand<WIDE> &cd) {
+    cd.dld = depth_lik_diff_raw<WIDE>(ws, raw_old, raw_new);
     cd.improv = __dadd_rn(lp, __dmul_rn(L.rel_contrib, cd.dld));          // assgn.rs:303
     cd.s = __dmul_rn(L.aln_contrib, __dsub_rn(cd.improv, lp_old));        // assgn.rs:310
     cd.dlp = __dsub_rn(lp, lp_old);
-    cd.slot = slot; cd.c = c; cd.w12 = ro.z; cd.w34 = rn.z;
+    cd.job = job; cd.raw_old = raw_old; cd.raw_new = raw_new;
 }
 
-// Greedy::solve_nontrivial (src/solvers/stoch.rs:81-120).
-// Every (sampled read, alternative candidate) pair of an iteration is one lane's job ("flattened"
-// best_read_improvement, src/model/assgn.rs:287-317); the winner is found with REDUX reductions in the
-// reference's tie order.  Software pipeline: the sample of iteration i+1 is drawn and its (static)
-// candidate records are loaded into registers while iteration i is evaluated, so the evaluation itself
-// touches only registers and shared memory.
-template <int GS>
-__device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab &S, const Instance &I,
-                             const WarpShared &ws, Xo<GS> &rng, double &aln_lik, double &depth_lik,
+// Greedy::solve_nontrivial (src/solvers/stoch.rs:81-120).  The winner of an iteration is found with REDUX
+// reductions in the reference's tie order.
+template <bool WIDE>
+__device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab<WIDE> &S, const Instance &I,
+                             const WarpShared &ws, Xo &rng, double &aln_lik, double &depth_lik,
                              uint64_t &iters_out) {
-    const Grp<GS> &g = rng.g;
-    const uint32_t lane = (uint32_t)g.lane;
+    typedef RecWord<WIDE> RW;
+    const uint32_t lane = (uint32_t)lane_id();
     const uint32_t amount = min(P.sample_size, I.n_nt);
-    init_assignment(L, S, I, ws, rng, P.best_start ? 0 : 1, aln_lik, depth_lik);
-    const double min_diff = fmax(__dmul_rn(1e-10, max_abs_random(L, S, I, ws, rng)), 1e-14);
-    SlotMap sm;
-    sm.lps = (uint32_t)GS / amount;
-    {
-        const uint32_t s = lane / sm.lps;
-        sm.valid = s < amount;
-        sm.slot = sm.valid ? s : amount - 1u;
-        sm.rank = lane - s * sm.lps;
-        sm.range = I.n_nt - amount + sm.slot + 1u;
-        sm.lead_mask = g.ballot(sm.valid && sm.rank == 0u);
-    }
+    init_assignment<WIDE>(L, S, I, ws, rng, P.best_start ? 0 : 1, aln_lik, depth_lik);
+    const double min_diff = fmax(__dmul_rn(1e-10, max_abs_random<WIDE>(L, S, I, ws, rng)), 1e-14);
     uint64_t curr_plato = 0, it = 0;
-    // Sample pipeline: `nx` = sample of iteration i+1 with its records in registers, `idx2` = sample of
-    // iteration i+2 (drawn, its slab lines prefetched into L2).
-    bool have1 = false, have2 = false;
-    uint32_t idx2 = 0;
-    SlotRead nx;
-    nx.idx = nx.start = nx.old_a = 0; nx.n = 1; nx.ro = nx.rn = make_uint4(0, 0, 0, 0);
-    for (; it < P.max_iter; it++) {
-        SlotRead cur;
-        if (have1) cur = nx;
-        else {
-            uint32_t v = 0;
-            sample_reads(rng, sm, I.n_nt, amount, false, v);
-            load_slot<GS>(S, ws, sm, v, cur);
-        }
-        if (have2) { load_slot<GS>(S, ws, sm, idx2, nx); have1 = true; have2 = false; }
-        else {
-            uint32_t v = 0;
-            have1 = sample_reads(rng, sm, I.n_nt, amount, true, v);
-            if (have1) load_slot<GS>(S, ws, sm, v, nx);
-        }
-        if (have1) {
-            have2 = sample_reads(rng, sm, I.n_nt, amount, true, idx2);
-            if (have2 && sm.rank < 2u) {
-                const uint32_t st2 = ws.ntc_start[idx2];
-                const uint32_t off2 = sm.rank == 0u ? 0u : (uint32_t)ws.ntc_start[idx2 + 1] - st2 - 1u;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(S.ntc + st2 + off2));
-            }
-        }
-        Cand best;
-        best.s = -INFINITY; best.improv = -INFINITY; best.dld = 0.0; best.dlp = 0.0;
-        best.slot = 0xFFFFu; best.c = 0; best.w12 = 0; best.w34 = 0;
-        const uint32_t n_alt = cur.n - 1u;
-        // Keep the (unused) padding word of the prefetched records live until here: otherwise its register
-        // is recycled right after the load is issued and that write has to wait for the load (WAW).
-        asm volatile("" ::"r"(cur.ro.w), "r"(cur.rn.w));
-        if (sm.valid && sm.rank < n_alt)
-            eval_cand(L, ws, cur.ro, cur.rn, sm.slot, sm.rank < cur.old_a ? sm.rank : sm.rank + 1u, best);
-        if (g.any(sm.valid && n_alt > sm.lps)) {
-            // reads with more alternatives than lanes per slot: extra passes straight from the slab
-            for (uint32_t j = sm.rank + sm.lps; g.any(sm.valid && j < n_alt); j += sm.lps) {
-                if (sm.valid && j < n_alt) {
-                    const uint32_t c = j < cur.old_a ? j : j + 1u;
-                    const uint4 rn = __ldcg(S.ntc + cur.start + c);
-                    Cand cd;
-                    eval_cand(L, ws, cur.ro, rn, sm.slot, c, cd);
-                    if (cand_better(cd, best)) best = cd;
+    bool vS = false, vA = false, vB = false, vC = false;
+    uint32_t s_myv = 0;
+    unsigned s_peers = 0;
+    SlotA<WIDE> sa;
+    SlotB<WIDE> sb, cur;
+    sa.job = sa.b0 = sa.b1 = sa.lead = sa.total = 0; sa.ro = sa.rn = 0;
+    sb.job = sb.lead = sb.total = 0; sb.ro = sb.rn = 0; sb.lpo = sb.lpn = 0.0;
+    cur = sb;
+    for (;;) {
+        if (vC) {
+            // ---- stage C: evaluate the sample of this iteration
+            Cand<WIDE> best;
+            best.s = -INFINITY; best.improv = -INFINITY; best.dld = 0.0; best.dlp = 0.0;
+            best.job = 0x00FF0000u; best.raw_old = 0; best.raw_new = 0;
+            if (lane < cur.total)
+                eval_cand<WIDE>(L, ws, cur.lpo, cur.lpn, cur.ro, cur.rn, cur.job, best);
+            if (cur.total > 32u) {
+                // more jobs than lanes (rare): the remaining ones in further passes straight from memory.  Job f of
+                // the sample belongs to the last sampled read whose first job position is <= f.
+                const uint32_t first = cur.lead >> 16;
+                uint32_t starts_before = (uint32_t)__popc(wballot(lane < amount && first < 32u));
+                for (uint32_t f0 = 32u; f0 < cur.total; f0 += 32u) {
+                    const unsigned starts = __reduce_or_sync(FULL, (lane < amount && first >= f0 && first < f0 + 32u) ? (1u << (first - f0)) : 0u);
+                    const uint32_t slot = starts_before + (uint32_t)__popc(starts & (0xFFFFFFFFu >> (31u - lane))) - 1u;
+                    const uint32_t idx = wshfl(cur.lead & 0xFFFFu, (int)slot);
+                    const uint32_t sfirst = wshfl(first, (int)slot);
+                    if (f0 + lane < cur.total) {
+                        const uint32_t r = ws.nt_read[idx];
+                        const uint32_t o = ws.off[r], a = ws.assgn[r];
+                        const uint32_t c = alt_rank(f0 + lane - sfirst, a);
+                        const typename RW::T ro = S.rec[o + a], rn = S.rec[o + c];
+                        const double lpo = __ldg(L.cm_lnprob + lp_index(L, I, ws, r, RW::src(ro)));
+                        const double lpn = __ldg(L.cm_lnprob + lp_index(L, I, ws, r, RW::src(rn)));
+                        Cand<WIDE> cd;
+                        eval_cand<WIDE>(L, ws, lpo, lpn, ro, rn, r | (slot << 16) | (c << 24), cd);
+                        if (cand_better<WIDE>(cd, best)) best = cd;
+                    }
+                    starts_before += (uint32_t)__popc(starts);
                 }
             }
-        }
-        // winner over the lanes' bests, in the order of cand_better
-        int wl;
-        {
-            const unsigned long long ks = ord_key(best.s);
-            const uint32_t h1 = g.rmax((uint32_t)(ks >> 32));
-            bool m = (uint32_t)(ks >> 32) == h1;
-            const uint32_t l1 = g.rmax(m ? (uint32_t)ks : 0u);
-            m = m && (uint32_t)ks == l1;
-            const unsigned tied = g.ballot(m);
-            if ((tied & (tied - 1u)) == 0u) wl = __ffs(tied) - 1;      // unique maximum (the usual case)
-            else {
-                const uint32_t sl = g.rmin(m ? best.slot : 0xFFFFFFFFu);
-                m = m && best.slot == sl;
-                const unsigned long long ki = ord_key(best.improv);
-                const uint32_t h2 = g.rmax(m ? (uint32_t)(ki >> 32) : 0u);
-                m = m && (uint32_t)(ki >> 32) == h2;
-                const uint32_t l2 = g.rmax(m ? (uint32_t)ki : 0u);
-                m = m && (uint32_t)ki == l2;
-                const uint32_t cm = g.rmin(m ? best.c : 0xFFFFFFFFu);
-                wl = __ffs(g.ballot(m && best.c == cm)) - 1;
+            // winner over the lanes' bests, in the order of cand_better
+            int wl;
+            {
+                const unsigned long long ks = ord_key(best.s);
+                const uint32_t h1 = __reduce_max_sync(FULL, (uint32_t)(ks >> 32));
+                bool m = (uint32_t)(ks >> 32) == h1;
+                const uint32_t l1 = __reduce_max_sync(FULL, m ? (uint32_t)ks : 0u);
+                m = m && (uint32_t)ks == l1;
+                const unsigned tied = wballot(m);
+                if ((tied & (tied - 1u)) == 0u) wl = __ffs(tied) - 1;      // unique maximum (the usual case)
+                else {
+                    const uint32_t sl = __reduce_min_sync(FULL, m ? job_slot(best.job) : 0xFFFFFFFFu);
+                    m = m && job_slot(best.job) == sl;
+                    const unsigned long long ki = ord_key(best.improv);
+                    const uint32_t h2 = __reduce_max_sync(FULL, m ? (uint32_t)(ki >> 32) : 0u);
+                    m = m && (uint32_t)(ki >> 32) == h2;
+                    const uint32_t l2 = __reduce_max_sync(FULL, m ? (uint32_t)ki : 0u);
+                    m = m && (uint32_t)ki == l2;
+                    const uint32_t cm = __reduce_min_sync(FULL, m ? job_c(best.job) : 0xFFFFFFFFu);
+                    wl = __ffs(wballot(m && job_c(best.job) == cm)) - 1;
+                }
             }
+            const double s_best = wshfl(best.s, wl);
+            it++;
+            if (s_best > min_diff) {
+                Move<WIDE> mv;
+                mv.dld = wshfl(best.dld, wl);
+                mv.dlp = wshfl(best.dlp, wl);
+                mv.raw_old = wshfl(best.raw_old, wl);
+                mv.raw_new = wshfl(best.raw_new, wl);
+                const uint32_t w_job = wshfl(best.job, wl);
+                const uint32_t w_r = job_r(w_job), w_c = job_c(w_job);
+                const uint32_t old_a = ws.assgn[w_r];
+                apply_move<WIDE>(ws, L.depth_table, w_r, w_c, mv, aln_lik, depth_lik);
+                curr_plato = 0;
+                // samples in flight saw the old assignment of the moved read: redo their loads (rare)
+                if (vB && wany(lane < sb.total && job_r(sb.job) == w_r)) {
+                    SlotA<WIDE> t;
+                    t.job = sb.job; t.lead = sb.lead; t.total = sb.total; t.ro = sb.ro; t.rn = sb.rn;
+                    t.b0 = __ldg(L.cm_off + (size_t)I.h0 * L.R + job_r(sb.job));
+                    t.b1 = L.p > 1 ? __ldg(L.cm_off + (size_t)I.h1 * L.R + job_r(sb.job)) : 0u;
+                    const bool mine = job_r(sb.job) == w_r;
+                    reload_slot_a<WIDE>(S, ws, w_r, old_a, t);
+                    SlotB<WIDE> nb;
+                    load_slot_b<WIDE>(L, I, ws, t, nb);
+                    if (mine) sb = nb;
+                }
+                if (vA && wany(lane < sa.total && job_r(sa.job) == w_r)) reload_slot_a<WIDE>(S, ws, w_r, old_a, sa);
+            } else {
+                curr_plato += 1;
+                if (curr_plato > P.plato_size) break;
+            }
+            if (it >= P.max_iter) break;
         }
-        const double s_best = g.shfl(best.s, wl);
-        if (s_best > min_diff) {
-            Move mv;
-            mv.dld = g.shfl(best.dld, wl);
-            mv.dlp = g.shfl(best.dlp, wl);
-            mv.w12 = g.shfl(best.w12, wl);
-            mv.w34 = g.shfl(best.w34, wl);
-            const uint32_t w_c = g.shfl(best.c, wl);
-            const uint32_t w_idx = g.shfl(cur.idx, wl);
-            apply_move(g, ws, L.depth_table, w_idx, w_c, mv, aln_lik, depth_lik);
-            curr_plato = 0;
-            // the prefetched sample saw the old assignment of the moved read
-            if (have1 && g.any(sm.valid && nx.idx == w_idx)) load_slot<GS>(S, ws, sm, nx.idx, nx);
-        } else {
-            curr_plato += 1;
-            if (curr_plato > P.plato_size) { it++; break; }
+        // ---- advance the pipeline by one stage
+        cur = sb; vC = vB;
+        if (vA) load_slot_b<WIDE>(L, I, ws, sa, sb);
+        vB = vA;
+        if (vS) {
+            sample_resolve(I.n_nt, amount, s_peers, s_myv);
+            load_slot_a<WIDE>(L, S, I, ws, amount, s_myv, sa);
         }
+        vA = vS;
+        // ---- stage S: draw the next sample.  The refilling path may only run on an empty pipeline: the samples in
+        // flight are given back to the stream when the loop ends, which cannot cross a refill.
+        vS = sample_draw(rng, I.n_nt, amount, false, s_myv);
+        if (!vS && !vA && !vB && !vC) vS = sample_draw(rng, I.n_nt, amount, true, s_myv);
+        if (vS) s_peers = sample_peers(amount, s_myv);
     }
-    if (have2) stream_unconsume(rng, amount);   // the pre-drawn samples of iterations that never ran
-    if (have1) stream_unconsume(rng, amount);
+    // the pre-drawn samples of iterations that never ran
+    stream_unconsume(rng, amount * ((vS ? 1u : 0u) + (vA ? 1u : 0u) + (vB ? 1u : 0u)));
     iters_out += it;
 }
 
 // ------------------------------------------------------------------ a11: SimAnneal --------------
 
-// SimAnneal::solve_nontrivial (src/solvers/stoch.rs:197-242): one candidate per step, group-uniform.
-template <int GS>
-__device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab &S, const Instance &I,
-                             const WarpShared &ws, Xo<GS> &rng, double &aln_lik, double &depth_lik,
+// SimAnneal::solve_nontrivial (src/solvers/stoch.rs:197-242).  One candidate per step in the reference; here
+// whole chains of steps are evaluated speculatively against the current state (spec_targets) and committed up
+// to the first accepted step, which reproduces the sequential result exactly: a rejected step changes nothing
+// but the plateau counter.
+template <bool WIDE>
+__device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab<WIDE> &S, const Instance &I,
+                             const WarpShared &ws, Xo &rng, double &aln_lik, double &depth_lik,
                              uint64_t &iters_out) {
-    const Grp<GS> &g = rng.g;
-    init_assignment(L, S, I, ws, rng, 1, aln_lik, depth_lik);
-    const double max_abs = max_abs_random(L, S, I, ws, rng);
+    init_assignment<WIDE>(L, S, I, ws, rng, 1, aln_lik, depth_lik);
+    const double max_abs = max_abs_random<WIDE>(L, S, I, ws, rng);
     const double min_diff = fmax(__dmul_rn(1e-10, max_abs), 1e-14);
     const double start_temp = fmax(__ddiv_rn(-max_abs, P.ln_init_prob), 1e-5);
     const double temp_step = __ddiv_rn(start_temp, (double)P.anneal_steps);
     uint64_t curr_plato = 0, steps = 0;
-    for (uint64_t i = P.anneal_steps; i >= 1; i--) {
-        const Target t = random_target(ws, I, rng);
-        Move mv;
-        const double diff = __dsub_rn(calc_improvement(L, S, ws, t, mv), min_diff);
-        steps++;
-        bool accept = diff >= 0.0;
-        if (!accept) {
-            const double u = xo_f64(rng);
-            accept = u <= exp(__ddiv_rn(diff, __dmul_rn(temp_step, (double)i)));
+    // phase 1: annealing, i = anneal_steps .. 1
+    uint64_t i = P.anneal_steps;
+    while (i >= 1) {
+        Spec sp;
+        spec_targets<true>(ws, I, rng, sp);
+        if (sp.count == 0) {               // sequential step (refill / biased draw / end of the register window)
+            const Target t = random_target(ws, I, rng);
+            Move<WIDE> mv;
+            const double diff = __dsub_rn(calc_improvement<WIDE>(L, S, I, ws, t.r, t.o, t.a, t.new_a, mv), min_diff);
+            steps++;
+            bool accept = diff >= 0.0;
+            if (!accept) {
+                const double u = xo_f64(rng);
+                accept = u <= exp(__ddiv_rn(diff, __dmul_rn(temp_step, (double)i)));
+            }
+            i--;
+            if (accept) { apply_move<WIDE>(ws, L.depth_table, t.r, t.new_a, mv, aln_lik, depth_lik); curr_plato = 0; }
+            else { curr_plato += 1; if (curr_plato >= P.plato_size) break; }
+            continue;
         }
-        if (accept) { apply_move(g, ws, L.depth_table, t.idx, t.new_a, mv, aln_lik, depth_lik); curr_plato = 0; }
-        else { curr_plato += 1; if (curr_plato >= P.plato_size) break; }
+        const uint32_t limit = (uint32_t)min((uint64_t)sp.count, i);
+        Move<WIDE> mv;
+        mv.dld = mv.dlp = 0.0; mv.raw_old = mv.raw_new = 0;
+        bool acc = false, neg = false;
+        if (sp.usable && sp.rank < limit) {
+            const double diff = __dsub_rn(calc_improvement<WIDE>(L, S, I, ws, sp.r, sp.o, sp.a, sp.new_a, mv), min_diff);
+            neg = !(diff >= 0.0);
+            acc = !neg;
+            if (neg) {
+                const double u = u64_to_unit_f64(sp.udraw);
+                acc = u <= exp(__ddiv_rn(diff, __dmul_rn(temp_step, (double)(i - sp.rank))));
+            }
+        }
+        const unsigned accmask = wballot(acc);
+        const uint32_t first_acc = accmask ? (uint32_t)__popc(sp.umask & ((1u << (__ffs(accmask) - 1)) - 1u)) : 0xFFFFFFFFu;
+        const uint32_t n_rej = min(first_acc, limit);              // leading rejected steps available
+        // the plato_left-th reject from here breaks the loop (the check follows the increment, stoch.rs:219-222)
+        const uint64_t plato_left = P.plato_size > curr_plato ? P.plato_size - curr_plato : 1;
+        if ((uint64_t)n_rej >= plato_left) {
+            const uint32_t e = (uint32_t)plato_left;
+            rng.pos += spec_offset_after(sp, e, sp.nd + 1u);
+            steps += e; i -= e; curr_plato += e;
+            break;
+        }
+        steps += n_rej; i -= n_rej; curr_plato += n_rej;
+        if (first_acc < limit) {
+            const int src = __ffs(accmask) - 1;
+            // the accepted step consumed its U(0,1) only if its diff was negative (short-circuit, stoch.rs:216)
+            const uint32_t off_acc = wshfl(lane_id() + sp.nd + (neg ? 1u : 0u), src);
+            Move<WIDE> w;
+            w.dld = wshfl(mv.dld, src); w.dlp = wshfl(mv.dlp, src);
+            w.raw_old = wshfl(mv.raw_old, src); w.raw_new = wshfl(mv.raw_new, src);
+            const uint32_t w_r = wshfl(sp.r, src), w_new = wshfl(sp.new_a, src);
+            rng.pos += off_acc;
+            apply_move<WIDE>(ws, L.depth_table, w_r, w_new, w, aln_lik, depth_lik);
+            steps++; i--; curr_plato = 0;
+        } else {
+            rng.pos += spec_offset_after(sp, n_rej, sp.nd + 1u);
+        }
     }
-    for (uint64_t k = 0; k < P.max_iter; k++) {
-        if (curr_plato >= P.plato_size) break;
-        const Target t = random_target(ws, I, rng);
-        Move mv;
-        const double diff = calc_improvement(L, S, ws, t, mv);
-        steps++;
-        if (diff > min_diff) { apply_move(g, ws, L.depth_table, t.idx, t.new_a, mv, aln_lik, depth_lik); curr_plato = 0; }
-        else curr_plato += 1;
+    // phase 2: hill climbing until the plateau
+    uint64_t k = 0;
+    while (k < P.max_iter && curr_plato < P.plato_size) {
+        Spec sp;
+        spec_targets<false>(ws, I, rng, sp);
+        if (sp.count == 0) {
+            const Target t = random_target(ws, I, rng);
+            Move<WIDE> mv;
+            const double diff = calc_improvement<WIDE>(L, S, I, ws, t.r, t.o, t.a, t.new_a, mv);
+            steps++; k++;
+            if (diff > min_diff) { apply_move<WIDE>(ws, L.depth_table, t.r, t.new_a, mv, aln_lik, depth_lik); curr_plato = 0; }
+            else curr_plato += 1;
+            continue;
+        }
+        const uint32_t limit = (uint32_t)min((uint64_t)sp.count, P.max_iter - k);
+        Move<WIDE> mv;
+        mv.dld = mv.dlp = 0.0; mv.raw_old = mv.raw_new = 0;
+        bool acc = false;
+        if (sp.usable && sp.rank < limit)
+            acc = calc_improvement<WIDE>(L, S, I, ws, sp.r, sp.o, sp.a, sp.new_a, mv) > min_diff;
+        const unsigned accmask = wballot(acc);
+        const uint32_t first_acc = accmask ? (uint32_t)__popc(sp.umask & ((1u << (__ffs(accmask) - 1)) - 1u)) : 0xFFFFFFFFu;
+        const uint32_t n_rej = min(first_acc, limit);
+        const uint64_t plato_left = P.plato_size - curr_plato;
+        if ((uint64_t)n_rej >= plato_left) {
+            const uint32_t e = (uint32_t)plato_left;
+            rng.pos += spec_offset_after(sp, e, sp.nd);
+            steps += e; k += e; curr_plato = P.plato_size;
+            break;
+        }
+        steps += n_rej; k += n_rej; curr_plato += n_rej;
+        if (first_acc < limit) {
+            const int src = __ffs(accmask) - 1;
+            const uint32_t off_acc = wshfl(lane_id() + sp.nd, src);
+            Move<WIDE> w;
+            w.dld = wshfl(mv.dld, src); w.dlp = wshfl(mv.dlp, src);
+            w.raw_old = wshfl(mv.raw_old, src); w.raw_new = wshfl(mv.raw_new, src);
+            const uint32_t w_r = wshfl(sp.r, src), w_new = wshfl(sp.new_a, src);
+            rng.pos += off_acc;
+            apply_move<WIDE>(ws, L.depth_table, w_r, w_new, w, aln_lik, depth_lik);
+            steps++; k++; curr_plato = 0;
+        } else {
+            rng.pos += spec_offset_after(sp, n_rej, sp.nd);
+        }
     }
     iters_out += steps;
 }
@@ -1016,9 +1320,9 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
 // ------------------------------------------------------------------ stage kernel ----------------
 
 #ifndef LCTP_MIN_CTAS
-#define LCTP_MIN_CTAS 17
+#define LCTP_MIN_CTAS 16
 #endif
-template <int GS>
+template <bool WIDE>
 __global__ void __launch_bounds__(CTA_THREADS, LCTP_MIN_CTAS)
 k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs,
               const uint64_t *__restrict__ worker_off, const uint32_t *__restrict__ tuples,
@@ -1026,85 +1330,78 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
               double *__restrict__ liks, uint64_t *__restrict__ n_alns, uint64_t *__restrict__ iters,
               uint16_t *__restrict__ counts, unsigned char *__restrict__ scratch,
               unsigned int *__restrict__ work_counter, int *__restrict__ err,
-              const uint64_t *__restrict__ setup_mats) {
+              const ulonglong2 *__restrict__ jump_tabs) {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int GROUPS = CTA_THREADS / GS;
-    const int gib = threadIdx.x / GS;
-    Xo<GS> rng;
-    const Grp<GS> &g = rng.g;
-    const int lane = g.lane;
+    const int lane = lane_id();
     WarpShared ws;
     {
-        unsigned char *base = smem + (size_t)gib * group_smem_bytes(P.Wmax, L.R);
+        unsigned char *base = smem;
         ws.win.base = (double *)base;          ws.win.wp = win_stride(P.Wmax);
         base += (size_t)ws.win.wp * 64;
-        ws.ntc_start = (uint16_t *)base;       base += align_up(((size_t)L.R + 1) * 2, 16);
-        ws.nt_assgn = (uint8_t *)base;
+        ws.off = (uint16_t *)base;             base += align_up(((size_t)L.R + 1) * 2, 16);
+        ws.nt_read = (uint16_t *)base;         base += align_up((size_t)L.R * 2, 16);
+        ws.assgn = (uint8_t *)base;            base += align_up((size_t)L.R, 16);
+        ws.unm_bits = (uint32_t *)base;        base += align_up((size_t)((L.R + 31) / 32) * 4, 16);
+        ws.haps = (uint32_t *)base;
         ws.zero_row = LCTP_GC_BINS * L.depth_k;
         ws.depth_k = L.depth_k;
     }
-    Slab S;
-    slab_layout(P.cap, L.R, scratch + (size_t)(blockIdx.x * GROUPS + gib) * P.slab_bytes, &S);
-    rng.buf = S.rng_buf; rng.blk = S.rng_blk;
+    Slab<WIDE> S;
+    slab_layout<WIDE>(P.cap, scratch + (size_t)blockIdx.x * P.slab_bytes, S);
+    Xo rng;
+    rng.buf = S.rng_buf; rng.blk = S.rng_blk; rng.tabs = jump_tabs;
 
     for (;;) {
         uint32_t w = 0;
         if (lane == 0) w = atomicAdd(work_counter, 1u);
-        w = g.shfl(w, 0);
+        w = wshfl(w, 0);
         if (w >= P.n_workers) break;
-        stream_begin(rng, rng_states + 4 * (size_t)w, setup_mats);
+        stream_begin(rng, rng_states + 4 * (size_t)w);
         for (uint64_t j = worker_off[w]; j < worker_off[w + 1]; j++) {
             const uint64_t gt = worker_ixs[j];
             const double prior = L.priors ? L.priors[gt] : 0.0;
             Instance I;
-            uint32_t wsft = 2;
-            I.wshift[0] = wsft;
-            for (uint32_t k = 0; k < L.p; k++) {
-                I.haps[k] = tuples[j * L.p + k];
-                wsft += L.hap_n_windows[I.haps[k]];
-                I.wshift[k + 1] = wsft;
+            __syncwarp();
+            if (lane == 0) {
+                uint32_t wsft = 2;
+                for (uint32_t k = 0; k < L.p; k++) {
+                    const uint32_t h = tuples[j * L.p + k];
+                    ws.haps[k] = h;
+                    ws.haps[LCTP_MAX_PLOIDY + k] = wsft;
+                    wsft += L.hap_n_windows[h];
+                }
+                ws.haps[LCTP_MAX_PLOIDY + L.p] = wsft;
             }
-            I.W = wsft;
-            const bool ok = L.p <= 2 ? build_instance<GS, LCTP_HEADS>(L, S, ws, P.cap, I, g)
-                                     : build_instance<GS, 0>(L, S, ws, P.cap, I, g);
+            __syncwarp();
+            I.h0 = ws.haps[0];
+            I.h1 = L.p > 1 ? ws.haps[1] : 0u;
+            I.W = ws.haps[LCTP_MAX_PLOIDY + L.p];
+            const bool ok = L.p <= 2 ? build_instance<LCTP_HEADS, WIDE>(L, S, ws, P.cap, I)
+                                     : build_instance<0, WIDE>(L, S, ws, P.cap, I);
             if (!ok) {
                 if (lane == 0) { atomicOr(err, 1); lik_mean[j] = NAN; lik_var[j] = NAN; n_alns[j] = I.A; iters[j] = 0; }
                 continue;
             }
             uint16_t *cnt = P.want_counts ? counts + (size_t)j * P.cap : nullptr;
-            if (cnt) { for (uint32_t c = lane; c < I.A; c += GS) cnt[c] = 0; }
+            if (cnt) { for (uint32_t c = lane; c < I.A; c += 32) cnt[c] = 0; }
             uint64_t it_total = 0;
             for (uint32_t a = 0; a < P.attempts; a++) {
-                apply_tweak(L, S, I, ws, rng);
+                apply_tweak<WIDE>(L, S, I, ws, rng);
                 double aln_lik = 0.0, depth_lik = 0.0;
-                if (I.n_nt == 0) init_assignment(L, S, I, ws, rng, 0, aln_lik, depth_lik);
-                else if (P.kind == 0) greedy_solve(L, P, S, I, ws, rng, aln_lik, depth_lik, it_total);
-                else anneal_solve(L, P, S, I, ws, rng, aln_lik, depth_lik, it_total);
+                if (I.n_nt == 0) init_assignment<WIDE>(L, S, I, ws, rng, 0, aln_lik, depth_lik);
+                else if (P.kind == 0) greedy_solve<WIDE>(L, P, S, I, ws, rng, aln_lik, depth_lik, it_total);
+                else anneal_solve<WIDE>(L, P, S, I, ws, rng, aln_lik, depth_lik, it_total);
                 // likelihood (assgn.rs:235-237) + prior (solve.rs:1126)
                 const double lik = __dadd_rn(prior, __dadd_rn(__dmul_rn(L.depth_contrib, depth_lik),
                                                               __dmul_rn(L.aln_contrib, aln_lik)));
                 if (lane == 0) liks[j * P.attempts + a] = lik;
                 if (cnt) {   // update_counts (assgn.rs:374-378)
-                    g.sync();
-                    uint32_t nt_base = 0;
-                    for (uint32_t r0 = 0; r0 < L.R; r0 += GS) {
-                        const uint32_t r = r0 + lane;
-                        const bool valid = r < L.R;
-                        uint32_t start = 0, nw = 0;
-                        if (valid) { start = S.read_off[r]; nw = S.read_off[r + 1] - start; }
-                        const bool nt = valid && nw > 1;
-                        const unsigned ntmask = g.ballot(nt);
-                        if (valid) {
-                            uint32_t as = 0;
-                            if (nt) as = ws.nt_assgn[nt_base + __popc(ntmask & g.lt())];
-                            cnt[start + as] += 1;
-                        }
-                        nt_base += __popc(ntmask);
-                    }
+                    __syncwarp();
+                    for (uint32_t r = lane; r < L.R; r += 32) cnt[(uint32_t)ws.off[r] + ws.assgn[r]] += 1;
                 }
-                g.sync();
+                __syncwarp();
             }
-            g.sync();
+            __syncwarp();
             // mean_variance_or_nan (ext/vec.rs:74-78,86-93,109-116)
             if (lane == 0) {
                 const double *x = liks + j * P.attempts;
@@ -1125,14 +1422,14 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
                 n_alns[j] = I.A;
                 iters[j] = it_total;
             }
-            g.sync();
+            __syncwarp();
         }
         stream_end(rng, rng_states + 4 * (size_t)w);
-        g.sync();
+        __syncwarp();
     }
 }
 
-// ------------------------------------------------------------------ host: jump matrices ---------
+// ------------------------------------------------------------------ host: jump tables -----------
 
 // 256x256 matrices over GF(2) stored by columns (4 words per column).
 struct BitMat { uint64_t c[256][4]; };
@@ -1164,40 +1461,45 @@ static void bm_pow(const BitMat &T, unsigned e, BitMat &out) {
     }
     out = acc;
 }
+// Byte-indexed form of M: tab[(b * 256 + v) * 4 .. +4] = M * (v << 8b), b = state byte 0..31.
+static void bm_to_table(const BitMat &M, uint64_t *tab) {
+    for (int b = 0; b < 32; b++) {
+        uint64_t *t = tab + (size_t)b * 256 * 4;
+        t[0] = t[1] = t[2] = t[3] = 0;
+        for (int v = 1; v < 256; v++) {
+            const int low = __builtin_ctz(v);
+            const uint64_t *prev = t + (size_t)(v & (v - 1)) * 4;
+            const uint64_t *col = M.c[b * 8 + low];
+            for (int k = 0; k < 4; k++) t[(size_t)v * 4 + k] = prev[k] ^ col[k];
+        }
+    }
+}
 
-// The jump matrices depend only on the generator: computed once per process (contexts on several host
+// The jump tables depend only on the generator: computed once per process (contexts on several host
 // threads share them), uploaded once per context.
-struct RngMats {
-    std::vector<uint64_t> setup;     // N_SETUP_MATS matrices T^(C*2^k)
-    BitMat refill[2];                // T^(15*C), T^(31*C)
-};
-static const RngMats &rng_mats() {
+static const std::vector<uint64_t> &jump_tables() {
     static std::once_flag once;
-    static RngMats m;
+    static std::vector<uint64_t> tabs;
     std::call_once(once, [] {
         static BitMat T, M;
         bm_step(T);
-        m.setup.resize((size_t)N_SETUP_MATS * 1024);
-        for (int k = 0; k < N_SETUP_MATS; k++) {
+        tabs.resize((size_t)N_JUMP_TABS * JUMP_TAB_WORDS);
+        for (int k = 0; k < 5; k++) {
             bm_pow(T, (unsigned)RNG_C << k, M);
-            std::memcpy(&m.setup[(size_t)k * 1024], M.c, sizeof(M.c));
+            bm_to_table(M, &tabs[(size_t)k * JUMP_TAB_WORDS]);
         }
-        bm_pow(T, 15u * RNG_C, m.refill[0]);
-        bm_pow(T, 31u * RNG_C, m.refill[1]);
+        bm_pow(T, RNG_FILL, M);
+        bm_to_table(M, &tabs[(size_t)5 * JUMP_TAB_WORDS]);
     });
-    return m;
+    return tabs;
 }
 
-static int ensure_rng_mats(lctp_ctx *ctx) {
+static int ensure_jump_tables(lctp_ctx *ctx) {
     if (ctx->d_rng_mats.p) return LCTP_OK;
-    const RngMats &m = rng_mats();
-    static std::mutex symbol_mutex;      // c_refill_mat is one symbol per device
-    std::lock_guard<std::mutex> lock(symbol_mutex);
-    int rc = ctx->d_rng_mats.alloc(m.setup.size());
+    const std::vector<uint64_t> &t = jump_tables();
+    int rc = ctx->d_rng_mats.alloc(t.size());
     if (rc) return rc;
-    LCTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_rng_mats.p, m.setup.data(), m.setup.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    LCTP_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_refill_mat, m.refill[0].c, sizeof(m.refill[0].c), 0, cudaMemcpyHostToDevice, ctx->stream));
-    LCTP_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_refill_mat, m.refill[1].c, sizeof(m.refill[1].c), sizeof(m.refill[0].c), cudaMemcpyHostToDevice, ctx->stream));
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_rng_mats.p, t.data(), t.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     LCTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return LCTP_OK;
 }
@@ -1208,48 +1510,58 @@ static double dbg_now() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-template <int GS>
-static int launch_stage_gs(lctp_locus_h *h, const StageParams &P, size_t n_workers, bool want_counts) {
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+static int launch_stage_kernel(lctp_locus_h *h, const StageParams &P, size_t n_workers, bool want_counts) {
     lctp_ctx *ctx = h->ctx;
     cudaStream_t s = ctx->stream;
     const LocusDev &L = h->dev;
-    constexpr int GROUPS = CTA_THREADS / GS;
-    const size_t smem = (size_t)GROUPS * group_smem_bytes(P.Wmax, L.R);
+    const size_t smem = group_smem_bytes(P.Wmax, L.R);
     if (smem > ctx->smem_optin) {
-        set_error("lctp_solve_stage: %zu bytes of shared memory per CTA needed (R=%u reads, %u windows); "
-                  "loci this large are not supported by the shared-memory resident solver yet", smem, L.R, P.Wmax);
+        set_error("lctp_solve_stage: %zu bytes of shared memory per worker needed (R=%u reads, %u windows); "
+                  "loci this large are not supported by the shared-memory resident solver", smem, L.R, P.Wmax);
         return LCTP_E_CAPACITY;
     }
-    auto kern = k_solve_stage<GS>;
+    auto kern = P.narrow_w ? k_solve_stage<false> : k_solve_stage<true>;
     // function attributes are per-device state shared by every context: configure + launch under one lock
     static std::mutex launch_mutex;
     std::lock_guard<std::mutex> lock(launch_mutex);
     // Only raise the limit when needed: re-setting a function attribute makes the next launch of the function wait
     // for its running instances, which serialised the stage kernels of loci in flight on different contexts.
-    static size_t smem_limit[16] = {0};
-    size_t &lim = smem_limit[(ctx->device & 7) * 2 + (GS == 32 ? 1 : 0)];
+    static std::unordered_map<int, size_t> smem_limit;     // by device ordinal and kernel instantiation
+    size_t &lim = smem_limit[ctx->device * 2 + (P.narrow_w ? 1 : 0)];
     if (smem > 48 * 1024 && smem > lim) {
         LCTP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lim = smem;
     }
-    if (const char *e = getenv("LCTP_CARVEOUT"))   // tuning knob: shared-memory carveout percentage
-        LCTP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
     int occ = 0;
     LCTP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA_THREADS, smem));
     if (occ < 1) occ = 1;
-    if (const char *e = getenv("LCTP_MAX_CTAS_PER_SM")) occ = std::min(occ, std::max(1, atoi(e)));
-    uint32_t resident = (uint32_t)ctx->sm_count * occ * GROUPS;
+    occ = std::min(occ, std::max(1, env_int("LCTP_MAX_CTAS_PER_SM", 1 << 20)));
+    uint32_t resident = (uint32_t)ctx->sm_count * occ;
+    // Keep the private slabs of the resident workers inside the L2 (126 MB on B200, shared with the locus'
+    // read-only arrays and with the other loci in flight): the slab is what the greedy / annealing loops gather
+    // from at random, and a worker whose slab has been evicted runs at DRAM latency.  Never fewer than one
+    // worker per SM sub-partition.
+    {
+        const size_t budget = (size_t)std::max(1, env_int("LCTP_L2_BUDGET_MB", 72)) << 20;
+        const size_t per = std::max<size_t>(1, P.slab_bytes);
+        const uint32_t by_l2 = (uint32_t)std::max<size_t>(budget / per, (size_t)ctx->sm_count * 4);
+        resident = std::min(resident, by_l2);
+    }
     if (ctx->max_resident_workers && ctx->max_resident_workers < resident) resident = ctx->max_resident_workers;
-    const uint32_t groups = (uint32_t)std::min<size_t>(n_workers, resident);
-    const uint32_t grid = (groups + GROUPS - 1) / GROUPS;
+    const uint32_t grid = (uint32_t)std::min<size_t>(n_workers, resident);
 
     int rc;
-    if ((rc = ctx->scratch.ensure((size_t)grid * GROUPS * P.slab_bytes))) return rc;
+    if ((rc = ctx->scratch.ensure((size_t)grid * P.slab_bytes))) return rc;
     LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[2], s));
     kern<<<grid, CTA_THREADS, smem, s>>>(
         L, P, ctx->d_worker_ixs.p, ctx->d_worker_off.p, ctx->d_tuples.p, ctx->d_rng.p, ctx->d_lik_mean.p,
         ctx->d_lik_var.p, ctx->d_liks.p, ctx->d_nalns.p, ctx->d_iters.p, want_counts ? ctx->d_counts.p : nullptr,
-        ctx->scratch.p, (unsigned int *)(ctx->d_flags.p + 1), ctx->d_flags.p, ctx->d_rng_mats.p);
+        ctx->scratch.p, (unsigned int *)(ctx->d_flags.p + 1), ctx->d_flags.p, (const ulonglong2 *)ctx->d_rng_mats.p);
     ctx->launches++;
     LCTP_CUDA_CHECK(cudaGetLastError());
     LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[3], s));
@@ -1283,9 +1595,13 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
         set_error("lctp_solve_stage: invalid annealing parameters");
         return LCTP_E_INVALID;
     }
-    if (h->npa > (uint64_t)SRC_MASK) {
-        set_error("lctp_solve_stage: %llu pair alignments exceed the 2^28 the candidate map can address",
-                  (unsigned long long)h->npa);
+    if (L.R > 65535u) {
+        set_error("lctp_solve_stage: %u reads exceed the 65535 the shared-memory read tables can index", L.R);
+        return LCTP_E_CAPACITY;
+    }
+    if (h->max_run > MAX_RUN) {
+        set_error("lctp_solve_stage: %u pair alignments of one read on one contig exceed %u (the reference keeps at "
+                  "most 10, MAX_USED_ALNS, src/model/locs.rs:741)", h->max_run, MAX_RUN);
         return LCTP_E_CAPACITY;
     }
     const size_t n = (size_t)worker_off[n_workers];
@@ -1303,8 +1619,9 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
         for (uint32_t k = 0; k < p; k++) a += h->hap_alns[tuples[j * p + k]];
         cap64 = std::max(cap64, a);
     }
-    if (cap64 > 0x7FFFFFF0ull) { set_error("lctp_solve_stage: candidate capacity overflow"); return LCTP_E_CAPACITY; }
-    const uint32_t cap = (uint32_t)cap64;
+    // a genotype with more than 65535 candidates is refused by the kernel (u16 offsets, like the reference's
+    // assert at src/model/assgn.rs:58 per read); do not reserve more than that
+    const uint32_t cap = (uint32_t)std::min<uint64_t>(cap64, 65535);
 
     StageParams P;
     P.kind = st->kind; P.attempts = st->attempts; P.best_start = st->best_start; P.sample_size = (uint32_t)st->sample_size;
@@ -1314,10 +1631,13 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     P.n_workers = (uint32_t)n_workers; P.cap = cap; P.Wmax = 2 + p * h->max_n_windows;
     const bool want_counts = counts != nullptr && counts_off != nullptr;
     P.want_counts = want_counts ? 1 : 0;
-    P.slab_bytes = slab_layout(cap, L.R, nullptr, nullptr);
+    P.narrow_w = P.Wmax <= 4096 ? 1 : 0;                       // 32-bit candidate records (12-bit windows)
+    if (env_int("LCTP_WIDE_WINDOWS", 0)) P.narrow_w = 0;       // test knob: exercise the 64-bit candidate records
+    P._pad = 0;
+    P.slab_bytes = slab_bytes_for(cap, P.narrow_w == 0);
 
     int rc;
-    if ((rc = ensure_rng_mats(ctx))) return rc;
+    if ((rc = ensure_jump_tables(ctx))) return rc;
     if ((rc = ctx->d_worker_ixs.ensure(n))) return rc;
     if ((rc = ctx->d_worker_off.ensure(n_workers + 1))) return rc;
     if ((rc = ctx->d_rng.ensure(n_workers * 4))) return rc;
@@ -1335,11 +1655,10 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     LCTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_rng.p, worker_rng, n_workers * 32, cudaMemcpyHostToDevice, s));
     LCTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tuples.p, tuples.data(), n * p * 4, cudaMemcpyHostToDevice, s));
     LCTP_CUDA_CHECK(cudaMemsetAsync(ctx->d_flags.p, 0, 2 * sizeof(int), s));
+    ctx->stats.h2d_bytes += n * 8 + (n_workers + 1) * 8 + n_workers * 32 + n * p * 4;
 
     const double t_launch = dbg_now();
-    int gs = 32;
-    if (const char *e = getenv("LCTP_GS")) gs = atoi(e) == 16 ? 16 : 32;   // tuning knob: lanes per worker
-    rc = gs == 32 ? launch_stage_gs<32>(h, P, n_workers, want_counts) : launch_stage_gs<16>(h, P, n_workers, want_counts);
+    rc = launch_stage_kernel(h, P, n_workers, want_counts);
     if (rc) return rc;
 
     int flags[2] = {0, 0};
@@ -1352,9 +1671,9 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     LCTP_CUDA_CHECK(cudaMemcpyAsync(its.data(), ctx->d_iters.p, n * 8, cudaMemcpyDeviceToHost, s));
     LCTP_CUDA_CHECK(cudaMemcpyAsync(flags, ctx->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
+    ctx->stats.d2h_bytes += n * 8 * 4 + n_workers * 32 + (liks ? n * st->attempts * 8 : 0) + sizeof(int);
     if (flags[0]) {
-        set_error("lctp_solve_stage: candidate slab overflow (cap=%u, or > 65535 candidates of non-trivial reads "
-                  "in one genotype)", cap);
+        set_error("lctp_solve_stage: candidate overflow (more than %u candidates in one genotype)", cap);
         return LCTP_E_CAPACITY;
     }
     if (getenv("LCTP_DEBUG_TIMES")) {      // investigation aid: kernel interval on a process-wide GPU time base
@@ -1387,6 +1706,7 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
             off += nal[j];
         }
         counts_off[n] = off;
+        ctx->stats.d2h_bytes += off * 2;
         LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
     }
     return LCTP_OK;

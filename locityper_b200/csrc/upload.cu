@@ -46,6 +46,7 @@ __global__ void k_group_runs(const uint64_t *__restrict__ pa_off, const uint32_t
         while (i + len < e && pa_contig[i + len] == h) len++;
         size_t key = (size_t)h * R + r;
         if (!SCATTER) {
+            if (len > 15) atomicOr(err, 16);        // the solver packs the rank inside a run into 4 bits
             cnt_or_off[key] = len;
             Mt[(size_t)r * Hpad + h] = pa_lnprob[i];
             if (!(pa_lnprob[i] <= 0.0)) atomicOr(err, 8);
@@ -60,10 +61,13 @@ __global__ void k_group_runs(const uint64_t *__restrict__ pa_off, const uint32_t
     }
 }
 
+static thread_local uint64_t g_h2d_bytes = 0;     // bytes of the upload in progress on this thread (lctp_stats.h2d_bytes)
+
 template <typename T>
 static int h2d(DevBuf<T> &dst, const T *src, size_t n, cudaStream_t s) {
     int rc = dst.alloc(n);
     if (rc) return rc;
+    g_h2d_bytes += n * sizeof(T);
     if (n) LCTP_CUDA_CHECK(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
     return LCTP_OK;
 }
@@ -144,6 +148,7 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h) {
     const uint32_t Hpad = (H + 63u) & ~63u;
 
     int rc;
+    g_h2d_bytes = 0;
     DevBuf<uint64_t> d_pa_off;
     DevBuf<uint32_t> d_pa_contig, d_mid1, d_mid2;
     DevBuf<double> d_pa_lnprob;
@@ -165,6 +170,7 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h) {
         const size_t nt = (size_t)LCTP_GC_BINS * in->depth_k;
         if ((rc = h->depth_table.alloc(nt + in->depth_k))) return rc;
         LCTP_CUDA_CHECK(cudaMemcpyAsync(h->depth_table.p, in->depth_table, nt * 8, cudaMemcpyHostToDevice, s));
+        g_h2d_bytes += nt * 8;
         LCTP_CUDA_CHECK(cudaMemsetAsync(h->depth_table.p + nt, 0, (size_t)in->depth_k * 8, s));
     }
     if (in->gt_tuples) {
@@ -180,7 +186,7 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h) {
     DevBuf<uint32_t> d_cnt;
     if ((rc = d_cnt.alloc(n_keys))) return rc;
     if ((rc = h->cm_off.alloc(n_keys))) return rc;
-    if ((rc = h->cm_lnprob.alloc(npa ? npa : 1))) return rc;
+    if ((rc = h->cm_lnprob.alloc(npa + R))) return rc;          // + the unmapped probabilities (see LocusDev::npa)
     if ((rc = h->cm_mid.alloc(npa ? npa : 1))) return rc;
     if ((rc = h->Mt.alloc((size_t)R * Hpad))) return rc;
     if ((rc = h->scores.alloc((size_t)in->n_genotypes))) return rc;
@@ -207,6 +213,7 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h) {
                                                               d_mid2.p, R, H, Hpad, h->cm_off.p, nullptr,
                                                               h->cm_lnprob.p, h->cm_mid.p, d_err.p);
     ctx->launches++;
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(h->cm_lnprob.p + npa, h->unmapped.p, (size_t)R * 8, cudaMemcpyDeviceToDevice, s));
     LCTP_CUDA_CHECK(cudaGetLastError());
 
     // per-haplotype number of pair alignments = cm_off[(k+1)R] - cm_off[kR]: strided D2H of H+1 words
@@ -216,7 +223,10 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h) {
     int err = 0;
     LCTP_CUDA_CHECK(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
+    ctx->stats.h2d_bytes += g_h2d_bytes;
+    ctx->stats.d2h_bytes += (uint64_t)(H + 1) * 4 + 4;
     h->mt_nonpositive = !(err & 8);
+    h->max_run = (err & 16) ? 16 : 15;           // > 15: lctp_solve_stage refuses (prefilter still works)
     err &= 7;
     if (err) {
         set_error("lctp_locus_upload: malformed pair alignments (flags=%d: 1=contig id >= H, 2=contigs not "
@@ -231,7 +241,7 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h) {
     }
 
     LocusDev &d = h->dev;
-    d.H = H; d.R = R; d.p = p; d.Hpad = Hpad; d.G = in->n_genotypes;
+    d.H = H; d.R = R; d.p = p; d.Hpad = Hpad; d.G = in->n_genotypes; d.npa = (uint32_t)npa;
     d.window = in->window; d.left_padding = in->left_padding; d.tweak = in->tweak; d.depth_k = in->depth_k;
     d.prob_diff = in->prob_diff;
     d.aln_contrib = 1.0 - in->lik_skew;                 // src/model/assgn.rs:80-81

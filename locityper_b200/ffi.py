@@ -64,6 +64,8 @@ class ResultC(C.Structure):
         ("warn_no_probable", C.c_uint32), ("warn_few_reads", C.c_uint32),
         ("n_filtered", C.c_uint64), ("n_stage_in", C.c_uint64 * MAX_STAGES),
         ("t_prefilter_s", C.c_double), ("t_stages_s", C.c_double),
+        ("has_dist", C.c_uint32), ("true_edit_distances", C.c_uint32), ("has_weight_dist", C.c_uint32),
+        ("_pad", C.c_uint32), ("weight_dist", C.c_double), ("dist_to_primary", C.c_uint32 * MAX_OUT),
     ]
 
 
@@ -74,7 +76,7 @@ class StatsC(C.Structure):
                 ("pairing_ms", C.c_double), ("pairing_launches", C.c_uint64), ("pairing_mates", C.c_uint64),
                 ("pairing_pairs", C.c_uint64),
                 ("rescore_ms", C.c_double), ("rescore_launches", C.c_uint64), ("rescore_alns", C.c_uint64),
-                ("rescore_ops", C.c_uint64)]
+                ("rescore_ops", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 class MatesC(C.Structure):
@@ -125,7 +127,8 @@ SYMBOLS = {
     "lctp_plan_stage": (C.c_size_t, [_P, _P, C.c_size_t, C.c_size_t, _P]),
     "lctp_discard_improbable": (C.c_size_t, [_P, C.c_size_t, _P, _P, _P, C.c_double, C.c_size_t, C.c_size_t]),
     "lctp_compare_two_likelihoods": (C.c_double, [C.c_double, C.c_double, C.c_uint16, C.c_double, C.c_double, C.c_uint16]),
-    "lctp_build_depth_table": (None, [_P, _P, C.c_int, _P, C.c_size_t, C.c_uint32, _P]),
+    "lctp_build_depth_table": (C.c_int, [_P, _P, C.c_int, _P, C.c_size_t, C.c_uint32, _P]),
+    "lctp_find_weighted_dist": (C.c_int, [_P, _P, _P, C.c_int]),
     "lctp_produce_result": (C.c_int, [_P, _P, C.c_size_t, _P, _P, _P, _P]),
     "lctp_solve": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, _P]),
     "lctp_result_json": (C.c_size_t, [_P, _P, _P, _P, C.c_size_t]),

@@ -172,8 +172,8 @@ def build_depth_table(nb_n, nb_p, is_paired, alt_cn, k_cols: int) -> np.ndarray:
     nb_p = np.ascontiguousarray(nb_p, dtype=np.float64)
     alt = np.ascontiguousarray(alt_cn, dtype=np.float64)
     out = np.empty((ffi_GC_BINS, int(k_cols)), dtype=np.float64)
-    ffi.load().lctp_build_depth_table(nb_n.ctypes.data, nb_p.ctypes.data, int(bool(is_paired)), alt.ctypes.data,
-                                      len(alt), int(k_cols), out.ctypes.data)
+    ffi.check(ffi.load().lctp_build_depth_table(nb_n.ctypes.data, nb_p.ctypes.data, int(bool(is_paired)),
+                                                alt.ctypes.data, len(alt), int(k_cols), out.ctypes.data))
     return out
 
 
@@ -451,6 +451,8 @@ class Genotyping:
     t_prefilter_s: float
     t_stages_s: float
     json_text: str = ""
+    weight_dist: Optional[float] = None          # Genotyping::weighted_dist
+    distances: Optional[List[Optional[int]]] = None   # Genotyping::distances (None entry = "unknown")
 
     def to_json(self) -> dict:
         return json.loads(self.json_text)
@@ -537,11 +539,18 @@ class DeviceLocus:
                     unexpl_reads=res.unexpl_reads, warn_no_probable=bool(res.warn_no_probable),
                     warn_few_reads=bool(res.warn_few_reads))
 
-    def solve(self, scheme: Scheme, threads: int, rng: np.ndarray, hap_names: Optional[Sequence[str]] = None) -> Genotyping:
-        """solve::solve: prefilter -> stages -> result.  `rng` (u64[4], the locus stream) is updated in place."""
+    def solve(self, scheme: Scheme, threads: int, rng: np.ndarray, hap_names: Optional[Sequence[str]] = None,
+              contig_distances: Optional[np.ndarray] = None, true_edit_distances: bool = False) -> Genotyping:
+        """solve::solve: prefilter -> stages -> result.  `rng` (u64[4], the locus stream) is updated in place.
+        `contig_distances`: Data::contig_distances as the linear upper triangle (u32, 0xFFFFFFFF = None)."""
         st = scheme.to_c()
         res = ffi.ResultC()
         ffi.check(self.lib.lctp_solve(self._h, st, len(scheme.stages), threads, rng.ctypes.data, C.byref(res)))
+        if contig_distances is not None:
+            cd = np.ascontiguousarray(contig_distances, dtype=np.uint32)
+            assert len(cd) == self.loc.n_haps * (self.loc.n_haps - 1) // 2
+            ffi.check(self.lib.lctp_find_weighted_dist(C.byref(res), C.byref(self.c), cd.ctypes.data,
+                                                       int(true_edit_distances)))
         n = int(res.n_out)
         names = list(hap_names) if hap_names is not None else [f"hap{i}" for i in range(self.loc.n_haps)]
         cn = (C.c_char_p * len(names))(*[s.encode() for s in names])
@@ -559,7 +568,10 @@ class DeviceLocus:
             ln_prob=np.array(res.ln_prob[:n]), quality=res.quality, total_reads=res.total_reads,
             unexpl_reads=res.unexpl_reads, warnings=warnings, n_filtered=int(res.n_filtered),
             n_stage_in=[int(x) for x in res.n_stage_in], t_prefilter_s=res.t_prefilter_s,
-            t_stages_s=res.t_stages_s, json_text=buf.value.decode())
+            t_stages_s=res.t_stages_s, json_text=buf.value.decode(),
+            weight_dist=(res.weight_dist if res.has_dist and res.has_weight_dist else None),
+            distances=([None if d == 0xFFFFFFFF else int(d) for d in res.dist_to_primary[:n]]
+                       if res.has_dist else None))
 
 
 def truncate_ixs(ixs, scores, filt_diff: float, min_size: int, threads: int) -> np.ndarray:

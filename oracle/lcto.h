@@ -34,7 +34,7 @@ extern "C" {
 
 #define LCTO_NONE_U32 0xFFFFFFFFu
 #define LCTO_GC_BINS 101          /* src/bg/depth.rs:42 */
-#define LCTO_MAX_PLOIDY 8
+#define LCTO_MAX_PLOIDY 16
 
 /* ------------------------------------------------------------------ RNG (lcto_rng.c) */
 
@@ -206,7 +206,15 @@ typedef struct lcto_result {
     uint64_t n_filtered;       /* survivors of the prefilter */
     uint64_t n_stage_in[8];    /* genotypes entering each executed stage (0 = skipped) */
     double   t_prefilter_s, t_stages_s;
+    /* Genotyping::find_weighted_dist, src/solvers/solve.rs:616-632 (filled by lcto_find_weighted_dist) */
+    uint32_t has_dist, true_edit_distances, has_weight_dist, _pad;
+    double   weight_dist;
+    uint32_t dist_to_primary[50];   /* LCTO_NONE_U32 = None */
 } lcto_result;
+
+/* Genotyping::find_weighted_dist (src/solvers/solve.rs:616-632) + genotype_distance (:339-357) over the linear
+ * storage of TriangleMatrix<Option<u32>> (src/ext/trimat.rs), LCTO_NONE_U32 = None. */
+void lcto_find_weighted_dist(const lcto_locus *L, lcto_result *res, const uint32_t *dist, int true_edit_distances);
 
 int lcto_solve(const lcto_locus *L, const lcto_stage *stages, size_t n_stages, size_t threads,
                lcto_rng *rng, int os_threads, lcto_result *res,

@@ -81,6 +81,8 @@ class ResultC(C.Structure):
         ("warn_no_probable", C.c_uint32), ("warn_few_reads", C.c_uint32),
         ("n_filtered", C.c_uint64), ("n_stage_in", C.c_uint64 * 8),
         ("t_prefilter_s", C.c_double), ("t_stages_s", C.c_double),
+        ("has_dist", C.c_uint32), ("true_edit_distances", C.c_uint32), ("has_weight_dist", C.c_uint32),
+        ("_pad", C.c_uint32), ("weight_dist", C.c_double), ("dist_to_primary", C.c_uint32 * 50),
     ]
 
 
@@ -93,7 +95,7 @@ class InstanceC(C.Structure):
     _fields_ = [
         ("n_reads", C.c_uint32), ("ploidy", C.c_uint32), ("total_windows", C.c_uint32),
         ("n_alns", C.c_uint32), ("n_nontrivial", C.c_uint32),
-        ("haps", C.c_uint32 * 8), ("wshift", C.c_uint32 * 9),
+        ("haps", C.c_uint32 * 16), ("wshift", C.c_uint32 * 17),
         ("read_ixs", C.POINTER(C.c_uint32)), ("nontrivial", C.POINTER(C.c_uint32)),
         ("aln_ln_prob", C.POINTER(C.c_double)), ("aln_contig_ix", C.POINTER(C.c_uint8)),
         ("aln_pa", C.POINTER(C.c_uint32)), ("aln_w", C.POINTER(C.c_uint32)),
@@ -302,7 +304,7 @@ def solve_stage(ol: OracleLocus, stage: Stage, worker_ixs, worker_off, worker_rn
 
 
 def solve(ol: OracleLocus, scheme: Sequence[Stage], threads: int, rng: Rng, os_threads: int = 1,
-          want_scores: bool = False):
+          want_scores: bool = False, contig_distances: Optional[np.ndarray] = None, true_edit_distances: bool = False):
     G = ol.loc.n_genotypes
     st = (StageC * len(scheme))(*[s.to_c() for s in scheme])
     res = ResultC()
@@ -312,6 +314,9 @@ def solve(ol: OracleLocus, scheme: Sequence[Stage], threads: int, rng: Rng, os_t
                           _ptr(scores), _ptr(filt))
     if rc != 0:
         raise RuntimeError(f"lcto_solve failed: {rc}")
+    if contig_distances is not None:
+        cd = np.ascontiguousarray(contig_distances, dtype=np.uint32)
+        lib().lcto_find_weighted_dist(ol.ref, C.byref(res), _ptr(cd), int(true_edit_distances))
     n = int(res.n_out)
     out = dict(
         gt_ix=np.array(res.gt_ix[:n], dtype=np.uint64), lik_mean=np.array(res.lik_mean[:n]),
@@ -321,11 +326,92 @@ def solve(ol: OracleLocus, scheme: Sequence[Stage], threads: int, rng: Rng, os_t
         warn_few_reads=bool(res.warn_few_reads), n_filtered=int(res.n_filtered),
         n_stage_in=[int(x) for x in res.n_stage_in], t_prefilter_s=res.t_prefilter_s,
         t_stages_s=res.t_stages_s,
+        has_dist=bool(res.has_dist), true_edit_distances=bool(res.true_edit_distances),
+        weight_dist=(res.weight_dist if res.has_dist and res.has_weight_dist else None),
+        distances=([None if d == 0xFFFFFFFF else int(d) for d in res.dist_to_primary[:n]] if res.has_dist else None),
     )
     if want_scores:
         out["scores"] = scores
         out["filtered_ixs"] = filt[:out["n_filtered"]].copy()
     return out
+
+
+# ---- Genotyping::to_json as text (src/solvers/solve.rs:732-773; written with write_pretty(.., 4),
+# src/command/genotype.rs:1256).  Independent of the C++ writer in the product: Python's repr() supplies the
+# shortest round-trip digits, the printing rules are the `json` crate's (util/print_dec.rs, restated).
+
+def json_number(v) -> str:
+    import math
+    if isinstance(v, (int, np.integer)):
+        return str(int(v))
+    v = float(v)
+    if math.isnan(v) or math.isinf(v):
+        return "null"
+    sign = "-" if math.copysign(1.0, v) < 0 else ""
+    v = abs(v)
+    if v == 0.0:
+        return sign + "0"
+    rp = repr(v)                                       # shortest round-trip digits
+    mant, _, ex = rp.partition("e") if "e" in rp else (rp, "", "0")
+    ip, _, fp = mant.partition(".")
+    exponent = int(ex) - len(fp)                       # v = int(ip + fp) * 10^exponent
+    digits = (ip + fp).lstrip("0")
+    stripped = digits.rstrip("0")
+    exponent += len(digits) - len(stripped)
+    digits = stripped
+    k = len(digits)
+    e10 = exponent + k - 1
+    if exponent == 0:
+        return sign + digits
+    if exponent < 0:
+        e = -exponent
+        if e < 18:
+            if k > e:
+                return sign + digits[:k - e] + "." + digits[k - e:]
+            return sign + "0." + "0" * (e - k) + digits
+        return sign + digits[0] + ("." + digits[1:] if k > 1 else "") + "e" + str(e10)
+    if k + exponent <= 20:
+        return sign + digits + "0" * exponent
+    return sign + digits[0] + ("." + digits[1:] if k > 1 else "") + "e" + str(e10)
+
+
+def to_json_text(res: dict, loc, hap_names: Sequence[str]) -> str:
+    import math
+    INV_LN10 = 0.4342944819032518277
+    ind = "    "
+
+    def name(g):
+        return ",".join(hap_names[h] for h in loc.genotype_tuple(int(g)))
+
+    items = [("total_reads", str(int(res["total_reads"]))), ("quality", json_number(res["quality"]))]
+    if res.get("distances") is not None:
+        items.append(("dist_type", '"edit"' if res["true_edit_distances"] else '"minim-div"'))
+    if res.get("weight_dist") is not None:
+        items.append(("weight_dist", json_number(res["weight_dist"])))
+    items.append(("unexpl_reads", str(int(res["unexpl_reads"]))))
+    n = len(res["gt_ix"])
+    if n:
+        items.append(("genotype", '"%s"' % name(res["gt_ix"][0])))
+        opts = []
+        for i in range(n):
+            o = [("genotype", '"%s"' % name(res["gt_ix"][i])),
+                 ("lik_mean", json_number(float(res["lik_mean"][i]) * INV_LN10)),
+                 ("lik_sd", json_number(float(res["lik_var"][i]) * INV_LN10)),
+                 ("prob", json_number(math.exp(float(res["ln_prob"][i])))),
+                 ("log10_prob", json_number(float(res["ln_prob"][i]) * INV_LN10))]
+            if res.get("distances") is not None:
+                d = res["distances"][i]
+                o.append(("dist_to_primary", '"unknown"' if d is None else str(d)))
+            opts.append("{\n" + ",\n".join(f'{ind * 3}"{k}": {v}' for k, v in o) + "\n" + ind * 2 + "}")
+        items.append(("options", "[\n" + ",\n".join(ind * 2 + x for x in opts) + "\n" + ind + "]"))
+    warns = []
+    if res.get("warn_no_probable"):
+        warns.append('"NoProbableGenotype"')
+    if res.get("warn_few_reads"):
+        warns.append('"FewReads(%d)"' % int(res["total_reads"]))
+    if warns:
+        items.append(("warnings", "[\n" + ",\n".join(ind * 2 + w for w in warns) + "\n" + ind + "]"))
+    return "{\n" + ",\n".join(f'{ind}"{k}": {v}' for k, v in items) + "\n}"
 
 
 class MatesC(C.Structure):

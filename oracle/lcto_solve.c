@@ -428,3 +428,82 @@ int lcto_solve(const lcto_locus *L, const lcto_stage *stages, size_t n_stages, s
     free(ixs); free(lik_mean); free(lik_var); free(attempts); free(wrng);
     return rc;
 }
+
+/* ------------------------------------------------------------------ weighted distance */
+
+/* TriangleMatrix::to_linear_index via get_symmetric (src/ext/trimat.rs:41-45) */
+static size_t tri_ix(size_t side, size_t i, size_t j) {
+    if (i > j) { size_t t = i; i = j; j = t; }
+    return (2 * side - 3 - i) * i / 2 + j - 1;
+}
+
+static void perm_visit(const uint32_t *perm, const uint32_t *gt2, uint32_t p, uint32_t H, const uint32_t *dist,
+                       uint32_t *min_dist) {
+    /* closure body of genotype_distance, src/solvers/solve.rs:342-355 */
+    uint32_t d = 0;
+    for (uint32_t k = 0; k < p; k++) {
+        if (perm[k] != gt2[k]) {
+            uint32_t e = dist[tri_ix(H, perm[k], gt2[k])];
+            if (e == LCTO_NONE_U32) { d = UINT32_MAX; break; }
+            d += e;
+        }
+    }
+    if (d < *min_dist) *min_dist = d;
+}
+
+/* genotype_distance (src/solvers/solve.rs:339-357) with ext::vec::gen_permutations (src/ext/vec.rs:342-372):
+ * n == 1: the tuple; n == 2: the tuple and its swap; n >= 3: Heap's algorithm, where `action` runs after every
+ * swap only -- the initial arrangement itself is never visited. */
+static uint32_t genotype_distance(const uint32_t *gt1, const uint32_t *gt2, uint32_t p, uint32_t H, const uint32_t *dist) {
+    uint32_t min_dist = UINT32_MAX;
+    if (p == 1) perm_visit(gt1, gt2, p, H, dist, &min_dist);
+    else if (p == 2) {
+        uint32_t sw[2] = { gt1[1], gt1[0] };
+        perm_visit(gt1, gt2, p, H, dist, &min_dist);
+        perm_visit(sw, gt2, p, H, dist, &min_dist);
+    } else {
+        uint32_t buffer[LCTO_MAX_PLOIDY];
+        size_t c[LCTO_MAX_PLOIDY];
+        for (uint32_t k = 0; k < p; k++) { buffer[k] = gt1[k]; c[k] = 0; }
+        size_t i = 1;
+        while (i < p) {
+            if (c[i] < i) {
+                size_t j = c[i] * (i % 2);
+                uint32_t t = buffer[i]; buffer[i] = buffer[j]; buffer[j] = t;
+                perm_visit(buffer, gt2, p, H, dist, &min_dist);
+                c[i] += 1;
+                i = 1;
+            } else {
+                c[i] = 0;
+                i += 1;
+            }
+        }
+    }
+    return min_dist;
+}
+
+void lcto_find_weighted_dist(const lcto_locus *L, lcto_result *res, const uint32_t *dist, int true_edit_distances) {
+    if (res->n_out == 0) return;
+    uint32_t p = L->ploidy, H = L->n_haps;
+    uint32_t gt0[LCTO_MAX_PLOIDY], gt[LCTO_MAX_PLOIDY];
+    lcto_genotype_tuple(L, res->gt_ix[0], gt0);
+    double sum_prob = 0.0, sum_dist = 0.0;
+    int known = 1;
+    for (uint64_t i = 0; i < res->n_out; i++) {
+        double prob = exp(res->ln_prob[i]);
+        sum_prob += prob;
+        uint32_t d = 0;
+        if (i > 0) {
+            lcto_genotype_tuple(L, res->gt_ix[i], gt);
+            d = genotype_distance(gt0, gt, p, H, dist);
+        }
+        /* sum_dist.zip(dist).map(|(s, d)| s + prob * d): None once any distance is None */
+        if (d == UINT32_MAX) known = 0;
+        else if (known) sum_dist += prob * (double)d;
+        res->dist_to_primary[i] = d;
+    }
+    res->has_dist = 1;
+    res->true_edit_distances = true_edit_distances ? 1 : 0;
+    res->has_weight_dist = (uint32_t)known;
+    res->weight_dist = known ? sum_dist / sum_prob : NAN;
+}
