@@ -101,8 +101,10 @@ __device__ __forceinline__ void slab_layout(uint32_t cap, unsigned char *base, S
 // ------------------------------------------------------------------ warp helpers ----------------
 
 static constexpr unsigned FULL = 0xFFFFFFFFu;
-__device__ __forceinline__ int lane_id() { return threadIdx.x; }            // CTA = one warp
-__device__ __forceinline__ unsigned lanes_lt() { return (1u << lane_id()) - 1u; }
+// CTA = one warp.  The hot code takes the lane from WarpShared::lane / Xo::lane (read once per kernel through a
+// volatile asm): left to itself the compiler re-reads SR_TID.X at every use (S2R, ~20 cycles; 3.6 % of the kernel's
+// instructions in the ncu capture of the previous build).
+__device__ __forceinline__ int lane_id() { return threadIdx.x; }
 template <typename T> __device__ __forceinline__ T wshfl(T v, int src) { return __shfl_sync(FULL, v, src); }
 __device__ __forceinline__ unsigned wballot(bool p) { return __ballot_sync(FULL, p); }
 __device__ __forceinline__ bool wany(bool p) { return __any_sync(FULL, p) != 0; }
@@ -117,7 +119,7 @@ __device__ __forceinline__ bool wany(bool p) { return __any_sync(FULL, p) != 0; 
 // with byte-indexed tables (entry [b][v] = M * (v << 8b), 32 lookups of 32 bytes, ~450 instructions) instead
 // of round 1's bit-by-bit product (~2,800), which is what makes a fill of 1,024 draws (8 KB per worker,
 // L2-resident) as cheap per draw as round 1's 8,192-draw fill (64 KB per worker, streamed through DRAM).
-// Consumers read the buffer through a 3 x 32-entry register window with shuffles, in stream order, so the
+// Consumers read the buffer through a 128-entry shared-memory ring (cp.async), in stream order, so the
 // draw sequence (including the data-dependent extra draw of biased bounded samples) is bit-identical to the
 // sequential generator.  At the end of a worker the exact state at the consumed position is rebuilt from the
 // owning lane's block-start state.
@@ -154,25 +156,42 @@ __device__ __forceinline__ Gen gen_tab_apply(const Gen &g, const ulonglong2 *__r
 }
 
 struct Xo {                // the worker's stream as seen by the solver code
-    // Register blocks: A = buf[base + lane], B = buf[base + 32 + lane], C = buf[base + 64 + lane].  A and B are
-    // what the consumers shuffle from; C is the prefetch in flight and is never read before it has become B one
-    // shift (>= 32 draws) later, so moving the window never waits for memory.
-    uint32_t a_lo, a_hi, b_lo, b_hi, c_lo, c_hi;
+    // Consumers read the draws from a 128-entry ring in shared memory holding stream positions [base, base + 128)
+    // of the current fill (position q at ring[q & 127]).  The ring is filled 64 draws at a time by cp.async
+    // (global -> shared, no destination registers, so no scoreboard slot is held while the copy is in flight: with
+    // the register window of the previous builds the compiler's slot sharing made consumers wait on the prefetch
+    // that had just been issued -- 10 % of the kernel in the ncu captures).  The copy of the second half is issued
+    // when the first half is entered, i.e. at least 32 draws before anything can read it.
     uint32_t pos;          // draws consumed from the current fill
-    uint32_t base;         // stream position of lane 0 of block A (multiple of 32)
+    uint32_t base;         // stream position of ring half 0 or 1 that `pos` is in (multiple of 64)
+    uint32_t pend;         // 1 = the copy of [base + 64, base + 128) may still be in flight
+    uint32_t lane;
     uint64_t *buf;         // [RNG_FILL] per-worker buffer (global, L2-resident)
     uint64_t *blk;         // [32][4] block-start states of the current fill
+    uint64_t *ring;        // [128] shared memory
     const ulonglong2 *tabs;// jump tables
 };
 
-__device__ __forceinline__ uint64_t stream_ld(const Xo &x, uint32_t p) {
-    return __ldcg(x.buf + min(p + (uint32_t)lane_id(), RNG_FILL - 1u));
+// copy buf[half .. half + 64) into its ring slot: 32 lanes x 16 bytes (a half beyond the fill is skipped)
+__device__ __forceinline__ void ring_issue(const Xo &x, uint32_t half) {
+    if (half < RNG_FILL) {
+        const uint64_t *src = x.buf + half + 2u * x.lane;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(x.ring + (half & 64u) + 2u * x.lane);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void stream_load_window(Xo &x) {
-    const uint64_t a = stream_ld(x, x.base), b = stream_ld(x, x.base + 32u), c = stream_ld(x, x.base + 64u);
-    x.a_lo = (uint32_t)a; x.a_hi = (uint32_t)(a >> 32);
-    x.b_lo = (uint32_t)b; x.b_hi = (uint32_t)(b >> 32);
-    x.c_lo = (uint32_t)c; x.c_hi = (uint32_t)(c >> 32);
+__device__ __forceinline__ void ring_wait() {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();          // the halves are copied by all lanes together
+}
+__device__ __forceinline__ void stream_resync(Xo &x) {
+    __syncwarp();
+    x.base = x.pos & ~63u;
+    ring_issue(x, x.base);
+    ring_issue(x, x.base + 64u);
+    ring_wait();
+    x.pend = 0;
 }
 
 // Generate this lane's block of a fill from its block-start state (stored in blk); out of line so that the
@@ -197,10 +216,10 @@ __device__ __noinline__ void fill_block(uint64_t *buf, uint64_t *blk, const ulon
     __syncwarp();
 }
 __device__ __forceinline__ void stream_refill(Xo &x) {
+    if (x.pend) ring_wait();
     fill_block(x.buf, x.blk, x.tabs + (size_t)5 * (JUMP_TAB_WORDS / 2));
     x.pos = 0;
-    x.base = 0;
-    stream_load_window(x);
+    stream_resync(x);
 }
 
 // Start a stream from the scalar state st[4]: lane l jumps ahead by l*RNG_C (binary decomposition of l).
@@ -218,8 +237,8 @@ __device__ __noinline__ void stream_begin_blocks(const uint64_t *__restrict__ st
 __device__ __forceinline__ void stream_begin(Xo &x, const uint64_t *__restrict__ st) {
     stream_begin_blocks(st, x.buf, x.blk, x.tabs);
     x.pos = 0;
-    x.base = 0;
-    stream_load_window(x);
+    x.pend = 0;
+    stream_resync(x);
 }
 
 // Exact scalar state after `pos` draws of the current fill (what the sequential generator would hold).
@@ -239,39 +258,38 @@ __device__ __noinline__ void stream_end_state(uint32_t pos, const uint64_t *blk,
     }
     if (lane_id() == 0) { out[0] = g.s0; out[1] = g.s1; out[2] = g.s2; out[3] = g.s3; }
 }
-__device__ __forceinline__ void stream_end(Xo &x, uint64_t *__restrict__ out) { stream_end_state(x.pos, x.blk, out); }
+__device__ __forceinline__ void stream_end(Xo &x, uint64_t *__restrict__ out) {
+    if (x.pend) { ring_wait(); x.pend = 0; }
+    stream_end_state(x.pos, x.blk, out);
+}
 
-// Make the register blocks cover stream positions [pos, pos + count), count <= 32; false = the fill ends
-// first (the caller then uses the one-draw-at-a-time path, which refills).  Position q of the stream lives
-// in lane q % 32: in block A for q < base + 32, else in block B.  `pos` may have been moved arbitrarily
-// (forwards by bulk consumers, backwards by stream_unconsume) since the last call.
+// Make the ring cover stream positions [pos, pos + count), count <= 32; false = the fill ends first (the caller
+// then uses the one-draw-at-a-time path, which refills).  `pos` may have been moved arbitrarily (forwards by bulk
+// consumers, backwards by stream_unconsume) since the last call.
 __device__ __forceinline__ bool stream_cover(Xo &x, uint32_t count) {
     if (x.pos + count > RNG_FILL) return false;
     const uint32_t d = x.pos - x.base;
-    if (d >= 32u) {
-        if (d < 64u) {                                    // A is used up: B -> A, C -> B, prefetch the next C
-            x.a_lo = x.b_lo; x.a_hi = x.b_hi;
-            x.b_lo = x.c_lo; x.b_hi = x.c_hi;
-            x.base += 32u;
-            const uint64_t v = stream_ld(x, x.base + 64u);
-            x.c_lo = (uint32_t)v; x.c_hi = (uint32_t)(v >> 32);
-        } else {                                          // far jump (or backwards): reload the blocks
-            x.base = x.pos & ~31u;
-            stream_load_window(x);
+    if (d >= 64u) {
+        if (d < 128u) {                                   // entered the second half: it becomes the first one
+            if (x.pend) ring_wait();                      // (issued >= 64 draws ago: done long since)
+            else __syncwarp();                            // every lane is done reading the half that is overwritten
+            x.base += 64u;
+            ring_issue(x, x.base + 64u);
+            x.pend = 1;
+        } else {                                          // far jump (or backwards)
+            if (x.pend) ring_wait();
+            stream_resync(x);
         }
     }
+    if (x.pend && x.pos + count > x.base + 64u) { ring_wait(); x.pend = 0; }
     return true;
 }
 // After stream_cover(count): the (pos + rank)-th draw of the stream, for any per-lane rank < count.
 __device__ __forceinline__ uint32_t stream_peek_hi(const Xo &x, uint32_t rank) {
-    const uint32_t off = x.pos - x.base;
-    return wshfl((uint32_t)lane_id() >= off ? x.a_hi : x.b_hi, (int)((off + rank) & 31u));
+    return ((const uint32_t *)x.ring)[2u * ((x.pos + rank) & 127u) + 1u];
 }
 __device__ __forceinline__ uint64_t stream_peek64(const Xo &x, uint32_t rank) {
-    const uint32_t off = x.pos - x.base;
-    const bool in_a = (uint32_t)lane_id() >= off;
-    const int src = (int)((off + rank) & 31u);
-    return ((uint64_t)wshfl(in_a ? x.a_hi : x.b_hi, src) << 32) | wshfl(in_a ? x.a_lo : x.b_lo, src);
+    return x.ring[(x.pos + rank) & 127u];
 }
 // Give back the last n draws (all taken from the current fill without a refill in between).
 __device__ __forceinline__ void stream_unconsume(Xo &x, uint32_t n) { x.pos -= n; }
@@ -314,8 +332,8 @@ __device__ __forceinline__ double xo_f64(Xo &x) { return u64_to_unit_f64(xo_next
 // caller runs the sequential path.  P(fallback) ~ count * range / 2^32.
 __device__ __forceinline__ bool xo_below_lanes(Xo &x, uint32_t count, uint32_t my_range, uint32_t &res) {
     if (!stream_cover(x, count)) return false;
-    const uint64_t m = (uint64_t)stream_peek_hi(x, (uint32_t)lane_id()) * (uint64_t)my_range;
-    const bool biased = (uint32_t)lane_id() < count && (uint32_t)m > 0u - my_range;
+    const uint64_t m = (uint64_t)stream_peek_hi(x, x.lane) * (uint64_t)my_range;
+    const bool biased = x.lane < count && (uint32_t)m > 0u - my_range;
     if (wany(biased)) return false;
     res = (uint32_t)(m >> 32);
     x.pos += count;
@@ -335,7 +353,7 @@ __device__ __forceinline__ unsigned long long ord_key(double v) {
     return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
 }
 
-// Per-window state in shared memory, 64 bytes per window: the window's weight, its depth-table row, the
+// Per-window state in shared memory, 56 bytes per window: the window's weight, its depth-table row, the
 // current read depth d and the five products weight * table[row][d-2 .. d+2] (rounded once, exactly as
 // WindowDistr::ln_prob computes them, src/model/distr_cache.rs:34-39).  Every likelihood delta of the
 // solver loops is then a difference of two shared-memory values: no global loads.
@@ -361,13 +379,15 @@ struct WarpShared {
     uint8_t *assgn;        // [R]    current assignment (candidate rank) of every read
     uint32_t *unm_bits;    // [ceil(R/32)] bit r%32 of word r/32: read r has the "unmapped" option among its candidates
     uint32_t *haps;        // [LCTP_MAX_PLOIDY] haplotypes of the genotype, then [LCTP_MAX_PLOIDY+1] window shifts
+    uint32_t *samp;        // [12] scratch of sample_resolve
     uint32_t zero_row;     // offset of the all-zero row
     uint32_t depth_k;
+    uint32_t lane;
 };
 __host__ __device__ inline size_t group_smem_bytes(uint32_t Wmax, uint32_t R) {
-    return (size_t)win_stride(Wmax) * 64 + align_up(((size_t)R + 1) * 2, 16) + align_up((size_t)R * 2, 16) +
+    return align_up((size_t)win_stride(Wmax) * 56, 16) + align_up(((size_t)R + 1) * 2, 16) + align_up((size_t)R * 2, 16) +
            align_up((size_t)R, 16) + align_up((size_t)((R + 31) / 32) * 4, 16) +
-           align_up((size_t)(2 * LCTP_MAX_PLOIDY + 1) * 4, 16);
+           align_up((size_t)(2 * LCTP_MAX_PLOIDY + 1) * 4, 16) + 64 /* samp */ + 1024 /* draw ring */;
 }
 
 // Recompute slice entry k of window w from its (weight, row, depth).
@@ -434,7 +454,7 @@ __device__ bool build_instance(const LocusDev &L, const Slab<WIDE> &S, const War
     constexpr int PK = HEADS > 0 ? 2 : LCTP_MAX_PLOIDY;
     constexpr int HN = HEADS > 0 ? HEADS : 1;
     const uint32_t R = L.R, p = L.p;
-    const int lane = lane_id();
+    const int lane = (int)ws.lane;
     const uint32_t lim = min(cap, 65535u);
     uint32_t base = 0, nt_base = 0;
     bool ok = true;
@@ -502,7 +522,7 @@ __device__ bool build_instance(const LocusDev &L, const Slab<WIDE> &S, const War
         if (ok && valid) {
             ws.off[r] = (uint16_t)start;
             ws.assgn[r] = 0;
-            if (nt) ws.nt_read[nt_base + __popc(ntmask & lanes_lt())] = (uint16_t)r;
+            if (nt) ws.nt_read[nt_base + __popc(ntmask & ((1u << ws.lane) - 1u))] = (uint16_t)r;
             bool unm_left = with_unm;
             const long long unm_key = total_key(unm);
             for (uint32_t t = 0; t < nw; t++) {
@@ -552,7 +572,7 @@ template <bool WIDE>
 __device__ void apply_tweak(const LocusDev &L, const Slab<WIDE> &S, const Instance &I, const WarpShared &ws, Xo &rng) {
     typedef RecWord<WIDE> RW;
     typedef typename RW::T Rec;
-    const int lane = lane_id();
+    const int lane = (int)ws.lane;
     const uint32_t tweak = L.tweak, R = L.R, p = L.p;
     const uint32_t span = 2 * tweak + 1;
     // (i) read middles: one next_u64 per candidate that has a parent, in candidate order (read-major).
@@ -687,7 +707,7 @@ template <bool WIDE>
 __device__ void init_assignment(const LocusDev &L, const Slab<WIDE> &S, const Instance &I, const WarpShared &ws,
                                 Xo &rng, int init_mode, double &aln_lik, double &depth_lik) {
     typedef RecWord<WIDE> RW;
-    const int lane = lane_id();
+    const int lane = (int)ws.lane;
     const uint32_t R = L.R;
     for (uint32_t w = lane; w < I.W; w += 32) ws.win.depth(w) = 0;
     // assignments: trivial reads stay at 0
@@ -777,7 +797,7 @@ __device__ __forceinline__ void apply_move(const WarpShared &ws, const double *_
     depth_lik = __dadd_rn(depth_lik, mv.dld);
     aln_lik = __dadd_rn(aln_lik, mv.dlp);
     const uint32_t w1 = RW::w1(mv.raw_old), w2 = RW::w2(mv.raw_old), w3 = RW::w1(mv.raw_new), w4 = RW::w2(mv.raw_new);
-    if (lane_id() == 0) {
+    if (ws.lane == 0) {
         ws.win.depth(w3) += 1;
         ws.win.depth(w4) += 1;
         ws.win.depth(w1) -= 1;
@@ -786,7 +806,7 @@ __device__ __forceinline__ void apply_move(const WarpShared &ws, const double *_
     }
     __syncwarp();
     // slide the product slices of the (up to four) windows whose depth changed
-    for (int q = lane_id(); q < 20; q += 32) {
+    for (int q = (int)ws.lane; q < 20; q += 32) {
         const int j = q / 5;
         const uint32_t w = j == 0 ? w1 : j == 1 ? w2 : j == 2 ? w3 : w4;
         win_refresh(ws, table, w, q % 5);
@@ -830,7 +850,7 @@ struct Spec {
 };
 template <bool WITH_U>
 __device__ __forceinline__ void spec_targets(const WarpShared &ws, const Instance &I, Xo &rng, Spec &sp) {
-    const uint32_t lane = (uint32_t)lane_id();
+    const uint32_t lane = ws.lane;
     sp.usable = false; sp.rank = 0; sp.count = 0; sp.umask = 0u;
     sp.r = sp.o = sp.a = sp.new_a = 0; sp.nd = 1; sp.udraw = 0;
     if (rng.pos >= RNG_FILL) return;
@@ -869,15 +889,15 @@ __device__ __forceinline__ void spec_targets(const WarpShared &ws, const Instanc
     const uint32_t first_bad = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
     sp.usable = on && lane < first_bad;
     sp.umask = wballot(sp.usable);
-    sp.rank = __popc(sp.umask & lanes_lt());
+    sp.rank = __popc(sp.umask & ((1u << ws.lane) - 1u));
     sp.count = __popc(sp.umask);
 }
 // stream position (relative to rng.pos) right after the first `e` steps of the chain, e <= count
-__device__ __forceinline__ uint32_t spec_offset_after(const Spec &sp, uint32_t e, uint32_t len_mine) {
+__device__ __forceinline__ uint32_t spec_offset_after(const Spec &sp, uint32_t lane, uint32_t e, uint32_t len_mine) {
     if (e == 0) return 0u;
     const unsigned sel = wballot(sp.usable && sp.rank == e - 1u);
     const int src = __ffs(sel) - 1;
-    return wshfl((uint32_t)lane_id() + len_mine, src);
+    return wshfl(lane + len_mine, src);
 }
 
 // max_abs_random (src/solvers/stoch.rs:19-22) with INIT_ITER = 100: the state does not change, so whole
@@ -905,7 +925,7 @@ __device__ double max_abs_random(const LocusDev &L, const Slab<WIDE> &S, const I
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, d));
         acc = fmax(acc, v);
-        rng.pos += spec_offset_after(sp, e, sp.nd);
+        rng.pos += spec_offset_after(sp, ws.lane, e, sp.nd);
         left -= e;
     }
     return acc;
@@ -919,7 +939,10 @@ __device__ double max_abs_random(const LocusDev &L, const Slab<WIDE> &S, const I
 // `slow`: take the draws one at a time (refills, bias correction) instead of through the lane-parallel path;
 // the lane-parallel path consumes exactly `amount` draws of the current fill or nothing at all.
 __device__ __forceinline__ bool sample_draw(Xo &rng, uint32_t n_nt, uint32_t amount, bool slow, uint32_t &myv) {
-    const uint32_t lane = (uint32_t)lane_id();
+    const uint32_t lane = rng.lane;
+    // the range is recomputed every round on purpose: hoisted out of the greedy loop it is one more live register,
+    // and the allocator answered by spilling it (a local-memory reload per round; the L1 is carved down to ~30 KB)
+    asm volatile("" : "+r"(n_nt));
     if (!slow) return xo_below_lanes(rng, amount, n_nt - amount + min(lane, amount - 1u) + 1u, myv);
     for (uint32_t k = 0; k < amount; k++) {
         const uint32_t t = xo_below(rng, n_nt - amount + k + 1u);
@@ -927,19 +950,24 @@ __device__ __forceinline__ bool sample_draw(Xo &rng, uint32_t n_nt, uint32_t amo
     }
     return true;
 }
-// lanes holding equal draws (evaluated one pipeline stage after it is issued: MATCH.ANY takes ~250 cycles)
-__device__ __forceinline__ unsigned sample_peers(uint32_t amount, uint32_t myv) {
-    const uint32_t lane = (uint32_t)lane_id();
-    return __match_any_sync(FULL, lane < amount ? myv : 0xFFFFFF00u + lane);
-}
-__device__ __forceinline__ void sample_resolve(uint32_t n_nt, uint32_t amount, unsigned peers, uint32_t &myv) {
-    const uint32_t lane = (uint32_t)lane_id();
-    if (wany(lane < amount && peers != (1u << lane))) {
+// Equal draws are found through a 12-entry scratch array in shared memory (three 16-byte loads per lane); MATCH.ANY
+// did it in one instruction but took ~250 cycles to deliver (ncu: 6-8 % of the kernel waiting on it).
+__device__ __forceinline__ void sample_resolve(const WarpShared &ws, uint32_t n_nt, uint32_t amount, uint32_t &myv) {
+    const uint32_t lane = ws.lane;
+    if (lane < 12u) ws.samp[lane] = lane < amount ? myv : 0xFFFFFF00u + lane;
+    __syncwarp();
+    const uint4 q0 = ((const uint4 *)ws.samp)[0], q1 = ((const uint4 *)ws.samp)[1], q2 = ((const uint4 *)ws.samp)[2];
+    const uint32_t e[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+    bool dup = false;
+#pragma unroll
+    for (int k = 0; k < 11; k++) dup |= (uint32_t)k < lane && e[k] == myv;
+    if (wany(dup && lane < amount)) {
         for (uint32_t k = 1; k < amount; k++) {
             const uint32_t t = wshfl(myv, (int)k);
             if (lane < k && myv == t) myv = n_nt - amount + k;
         }
     }
+    __syncwarp();
 }
 
 // job word of a lane: read id | slot << 16 | candidate rank << 24 (slot < 16, rank < 256)
@@ -971,7 +999,7 @@ __device__ __forceinline__ bool cand_better(const Cand<WIDE> &a, const Cand<WIDE
 // whole sample whatever the candidate counts are.  A job's data is two dependent hops away (private candidate
 // records + the read's run offsets, then the shared ln-probabilities), so samples are drawn three iterations
 // ahead and move through four stages, one per loop round:
-//   S  sample drawn, duplicate check (MATCH.ANY) in flight
+//   S  sample drawn
 //   A  jobs dealt, first-hop loads in flight
 //   B  second-hop loads in flight
 //   C  evaluated: touches only registers and shared memory
@@ -998,7 +1026,7 @@ struct SlotB {
 template <bool WIDE>
 __device__ __forceinline__ void load_slot_a(const LocusDev &L, const Slab<WIDE> &S, const Instance &I,
                                             const WarpShared &ws, uint32_t amount, uint32_t myv, SlotA<WIDE> &x) {
-    const uint32_t lane = (uint32_t)lane_id();
+    const uint32_t lane = ws.lane;
     const bool lead = lane < amount;
     uint32_t lr = 0, n_alt = 0;
     if (lead) {
@@ -1074,14 +1102,13 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
                              const WarpShared &ws, Xo &rng, double &aln_lik, double &depth_lik,
                              uint64_t &iters_out) {
     typedef RecWord<WIDE> RW;
-    const uint32_t lane = (uint32_t)lane_id();
+    const uint32_t lane = ws.lane;
     const uint32_t amount = min(P.sample_size, I.n_nt);
     init_assignment<WIDE>(L, S, I, ws, rng, P.best_start ? 0 : 1, aln_lik, depth_lik);
     const double min_diff = fmax(__dmul_rn(1e-10, max_abs_random<WIDE>(L, S, I, ws, rng)), 1e-14);
     uint64_t curr_plato = 0, it = 0;
     bool vS = false, vA = false, vB = false, vC = false;
     uint32_t s_myv = 0;
-    unsigned s_peers = 0;
     SlotA<WIDE> sa;
     SlotB<WIDE> sb, cur;
     sa.job = sa.b0 = sa.b1 = sa.lead = sa.total = 0; sa.ro = sa.rn = 0;
@@ -1173,20 +1200,20 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
             }
             if (it >= P.max_iter) break;
         }
-        // ---- advance the pipeline by one stage
+        // ---- advance the pipeline by one stage.  Unconditionally: a stage that holds nothing valid (start-up, the
+        // rounds after the fill ran out) moves harmless stale values.  With the loads under `if (valid)` the compiler
+        // cannot see that last round's loads were consumed on every path and guards each re-issued load with a wait
+        // on its scoreboard slot -- the slot the loads issued just before it share (ncu: 7 % of the kernel).
         cur = sb; vC = vB;
-        if (vA) load_slot_b<WIDE>(L, I, ws, sa, sb);
+        load_slot_b<WIDE>(L, I, ws, sa, sb);
         vB = vA;
-        if (vS) {
-            sample_resolve(I.n_nt, amount, s_peers, s_myv);
-            load_slot_a<WIDE>(L, S, I, ws, amount, s_myv, sa);
-        }
+        sample_resolve(ws, I.n_nt, amount, s_myv);
+        load_slot_a<WIDE>(L, S, I, ws, amount, s_myv, sa);
         vA = vS;
         // ---- stage S: draw the next sample.  The refilling path may only run on an empty pipeline: the samples in
         // flight are given back to the stream when the loop ends, which cannot cross a refill.
         vS = sample_draw(rng, I.n_nt, amount, false, s_myv);
         if (!vS && !vA && !vB && !vC) vS = sample_draw(rng, I.n_nt, amount, true, s_myv);
-        if (vS) s_peers = sample_peers(amount, s_myv);
     }
     // the pre-drawn samples of iterations that never ran
     stream_unconsume(rng, amount * ((vS ? 1u : 0u) + (vA ? 1u : 0u) + (vB ? 1u : 0u)));
@@ -1249,7 +1276,7 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
         const uint64_t plato_left = P.plato_size > curr_plato ? P.plato_size - curr_plato : 1;
         if ((uint64_t)n_rej >= plato_left) {
             const uint32_t e = (uint32_t)plato_left;
-            rng.pos += spec_offset_after(sp, e, sp.nd + 1u);
+            rng.pos += spec_offset_after(sp, ws.lane, e, sp.nd + 1u);
             steps += e; i -= e; curr_plato += e;
             break;
         }
@@ -1257,7 +1284,7 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
         if (first_acc < limit) {
             const int src = __ffs(accmask) - 1;
             // the accepted step consumed its U(0,1) only if its diff was negative (short-circuit, stoch.rs:216)
-            const uint32_t off_acc = wshfl(lane_id() + sp.nd + (neg ? 1u : 0u), src);
+            const uint32_t off_acc = wshfl(ws.lane + sp.nd + (neg ? 1u : 0u), src);
             Move<WIDE> w;
             w.dld = wshfl(mv.dld, src); w.dlp = wshfl(mv.dlp, src);
             w.raw_old = wshfl(mv.raw_old, src); w.raw_new = wshfl(mv.raw_new, src);
@@ -1266,7 +1293,7 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
             apply_move<WIDE>(ws, L.depth_table, w_r, w_new, w, aln_lik, depth_lik);
             steps++; i--; curr_plato = 0;
         } else {
-            rng.pos += spec_offset_after(sp, n_rej, sp.nd + 1u);
+            rng.pos += spec_offset_after(sp, ws.lane, n_rej, sp.nd + 1u);
         }
     }
     // phase 2: hill climbing until the plateau
@@ -1295,14 +1322,14 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
         const uint64_t plato_left = P.plato_size - curr_plato;
         if ((uint64_t)n_rej >= plato_left) {
             const uint32_t e = (uint32_t)plato_left;
-            rng.pos += spec_offset_after(sp, e, sp.nd);
+            rng.pos += spec_offset_after(sp, ws.lane, e, sp.nd);
             steps += e; k += e; curr_plato = P.plato_size;
             break;
         }
         steps += n_rej; k += n_rej; curr_plato += n_rej;
         if (first_acc < limit) {
             const int src = __ffs(accmask) - 1;
-            const uint32_t off_acc = wshfl(lane_id() + sp.nd, src);
+            const uint32_t off_acc = wshfl(ws.lane + sp.nd, src);
             Move<WIDE> w;
             w.dld = wshfl(mv.dld, src); w.dlp = wshfl(mv.dlp, src);
             w.raw_old = wshfl(mv.raw_old, src); w.raw_new = wshfl(mv.raw_new, src);
@@ -1311,7 +1338,7 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
             apply_move<WIDE>(ws, L.depth_table, w_r, w_new, w, aln_lik, depth_lik);
             steps++; k++; curr_plato = 0;
         } else {
-            rng.pos += spec_offset_after(sp, n_rej, sp.nd);
+            rng.pos += spec_offset_after(sp, ws.lane, n_rej, sp.nd);
         }
     }
     iters_out += steps;
@@ -1319,8 +1346,11 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
 
 // ------------------------------------------------------------------ stage kernel ----------------
 
+// Resident CTAs per SM the register allocation is sized for.  Shared memory allows 14 at the C2 shape (15 KB per
+// worker); with 16 the 128-register cap spilled min_diff and the sampling ranges into local memory inside the greedy
+// loop, and with the L1 carved down to ~30 KB those reloads go to the L2 (ncu: 10 % of the kernel).
 #ifndef LCTP_MIN_CTAS
-#define LCTP_MIN_CTAS 16
+#define LCTP_MIN_CTAS 14
 #endif
 template <bool WIDE>
 __global__ void __launch_bounds__(CTA_THREADS, LCTP_MIN_CTAS)
@@ -1332,12 +1362,17 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
               unsigned int *__restrict__ work_counter, int *__restrict__ err,
               const ulonglong2 *__restrict__ jump_tabs) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int lane = lane_id();
+    uint32_t lane_reg;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_reg));      // read once (see lane_id)
+    const int lane = (int)lane_reg;
     WarpShared ws;
+    Xo rng;
     {
         unsigned char *base = smem;
+        rng.ring = (uint64_t *)base;           base += 1024;
+        ws.samp = (uint32_t *)base;            base += 64;
         ws.win.base = (double *)base;          ws.win.wp = win_stride(P.Wmax);
-        base += (size_t)ws.win.wp * 64;
+        base += align_up((size_t)ws.win.wp * 56, 16);
         ws.off = (uint16_t *)base;             base += align_up(((size_t)L.R + 1) * 2, 16);
         ws.nt_read = (uint16_t *)base;         base += align_up((size_t)L.R * 2, 16);
         ws.assgn = (uint8_t *)base;            base += align_up((size_t)L.R, 16);
@@ -1345,11 +1380,12 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
         ws.haps = (uint32_t *)base;
         ws.zero_row = LCTP_GC_BINS * L.depth_k;
         ws.depth_k = L.depth_k;
+        ws.lane = lane_reg;
     }
     Slab<WIDE> S;
     slab_layout<WIDE>(P.cap, scratch + (size_t)blockIdx.x * P.slab_bytes, S);
-    Xo rng;
-    rng.buf = S.rng_buf; rng.blk = S.rng_blk; rng.tabs = jump_tabs;
+    rng.buf = S.rng_buf; rng.blk = S.rng_blk; rng.tabs = jump_tabs; rng.lane = lane_reg;
+    rng.pos = 0; rng.base = 0; rng.pend = 0;
 
     for (;;) {
         uint32_t w = 0;

@@ -221,6 +221,12 @@ int lcto_solve(const lcto_locus *L, const lcto_stage *stages, size_t n_stages, s
                /* optional dumps (may be NULL): */
                double *scores_out /* [G] */, uint64_t *filtered_ixs_out /* [G] */);
 
+/* Debug dumps in the reference's `--debug 2` formats (sol.csv, sol_ext.csv; uncompressed): rows are appended by
+ * lcto_solve / lcto_solve_stage between open and close.  hap_names[H] must outlive the sink.  Not thread-safe across
+ * concurrent lcto_solve calls (tools/rust_diff.sh runs one locus at a time). */
+int  lcto_debug_open(const char *sol_path, const char *sol_ext_path, const char *const *hap_names);
+void lcto_debug_close(void);
+
 const char *lcto_version(void);
 
 /* ------------------------------------------------ pair alignments (lcto_pairs.c) */

@@ -100,6 +100,43 @@ size_t lcto_truncate_ixs(uint64_t *ixs, size_t n, const double *scores, double f
     return m;
 }
 
+/* ------------------------------------------------------------ debug dumps (--debug 2 of the reference) */
+
+/* sol.csv / sol_ext.csv in the reference's own row formats (src/solvers/solve.rs:115-117,1074-1075,938,895-896;
+ * src/model/assgn.rs:413-425), written by lcto_solve / lcto_solve_stage while a sink is open.  This is what
+ * tools/rust_diff.sh diffs against the files of a real `locityper genotype --debug 2` run.  Row order inside a stage
+ * depends on thread timing in the reference, so the comparison sorts the rows. */
+#include <stdio.h>
+static FILE *g_sol = NULL, *g_sol_ext = NULL;
+static const char *const *g_hap_names = NULL;
+static unsigned g_stage_no = 0;                      /* 1-based stage of the rows being written */
+static pthread_mutex_t g_dbg_mutex = PTHREAD_MUTEX_INITIALIZER;
+
+static void fprint_gt(FILE *f, const lcto_locus *L, uint64_t g) {
+    uint32_t ids[LCTO_MAX_PLOIDY];
+    lcto_genotype_tuple(L, g, ids);
+    for (uint32_t k = 0; k < L->ploidy; k++) fprintf(f, "%s%s", k ? "," : "", g_hap_names[ids[k]]);   /* Genotype::new, contigs.rs:412-424 */
+}
+
+int lcto_debug_open(const char *sol_path, const char *sol_ext_path, const char *const *hap_names) {
+    g_sol = fopen(sol_path, "w");
+    g_sol_ext = fopen(sol_ext_path, "w");
+    if (!g_sol || !g_sol_ext) return -1;
+    g_hap_names = hap_names;
+    fprintf(g_sol, "stage\tgenotype\tscore\n");                                             /* solve.rs:938 */
+    fprintf(g_sol_ext, "stage\tgenotype\tattempt\ttotal_reads\tunmapped\tout_of_bounds\taln_lik\tdepth_lik\tlik\n");
+    return 0;
+}
+
+void lcto_debug_close(void) {
+    if (g_sol) fclose(g_sol);
+    if (g_sol_ext) fclose(g_sol_ext);
+    g_sol = g_sol_ext = NULL;
+    g_hap_names = NULL;
+}
+
+#define LCTO_INV_LN10 0.4342944819032518277        /* Ln::INV_LN10, src/math/mod.rs:14 */
+
 /* ------------------------------------------------------------ a13/a14: stage over workers */
 
 typedef struct {
@@ -149,12 +186,27 @@ static int run_worker(stage_ctx *C, size_t w) {
                 return -1;
             }
             liks[a] = prior + out.lik;                              /* solve.rs:1126 */
+            if (g_sol_ext) {                                        /* ReadAssignment::summarize, assgn.rs:416-425 */
+                pthread_mutex_lock(&g_dbg_mutex);
+                fprintf(g_sol_ext, "%u\t", g_stage_no);
+                fprint_gt(g_sol_ext, L, g);
+                fprintf(g_sol_ext, "\t%u\t%u\t%u\t%u\t%.7f\t%.7f\t%.7f\n", a + 1, I->n_reads, depth[0], depth[1],
+                        out.aln_lik * LCTO_INV_LN10, out.depth_lik * LCTO_INV_LN10, out.lik * LCTO_INV_LN10);
+                pthread_mutex_unlock(&g_dbg_mutex);
+            }
             iters += out.iterations;
             for (uint32_t r = 0; r < I->n_reads; r++)               /* update_counts, assgn.rs:374-378 */
                 counts[I->read_ixs[r] + read_assgn[r]] += 1;
             if (C->liks) C->liks[j * attempts + a] = liks[a];
         }
         mean_variance_or_nan(liks, attempts, &C->lik_mean[j], &C->lik_var[j]);
+        if (g_sol) {                                                /* MainWorker::run, solve.rs:1074-1075 */
+            pthread_mutex_lock(&g_dbg_mutex);
+            fprintf(g_sol, "%u\t", g_stage_no);
+            fprint_gt(g_sol, L, g);
+            fprintf(g_sol, "\t%.4f\n", C->lik_mean[j] * LCTO_INV_LN10);
+            pthread_mutex_unlock(&g_dbg_mutex);
+        }
         if (C->n_alns_out) C->n_alns_out[j] = I->n_alns;
         if (C->iters_out) C->iters_out[j] = iters;
         if (C->want_counts) C->counts_tmp[j] = counts; else free(counts);
@@ -335,6 +387,12 @@ int lcto_solve(const lcto_locus *L, const lcto_stage *stages, size_t n_stages, s
         double *scores = (double *)malloc(sizeof(double) * G);
         lcto_best_aln_matrix(L, M);
         lcto_prefilter_scores(L, M, ixs, n, scores);
+        if (g_sol)                                     /* run_filter, solve.rs:115-117 */
+            for (size_t q = 0; q < n; q++) {
+                fprintf(g_sol, "0\t");
+                fprint_gt(g_sol, L, ixs[q]);
+                fprintf(g_sol, "\t%.3f\n", scores[ixs[q]] * LCTO_INV_LN10);
+            }
         n = lcto_truncate_ixs(ixs, n, scores, L->filt_diff, out_size0, threads);
         if (scores_out) memcpy(scores_out, scores, sizeof(double) * G);
         free(M); free(scores);
@@ -357,6 +415,7 @@ int lcto_solve(const lcto_locus *L, const lcto_stage *stages, size_t n_stages, s
         size_t out_size = has_next ? stages[s + 1].in_size : 0;
         if (!(L->dont_skip || !has_next || out_size < n)) continue;     /* solve.rs:1041-1045 */
         res->n_stage_in[s] = n;
+        g_stage_no = (unsigned)s + 1;
         double *lm = (double *)malloc(sizeof(double) * n);
         double *lv = (double *)malloc(sizeof(double) * n);
         uint64_t *off;
