@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--no-kir-prefilter", action="store_true",
                     help="skip the extra prefilter-only measurement at the KIR-scale shape (configs[3])")
     ap.add_argument("--cpu-loci", type=int, default=0, help="loci in the bounded CPU sample (0 = auto)")
+    ap.add_argument("--no-shard-kir", action="store_true", help="skip the sharded KIR-scale solve (configs[3])")
+    ap.add_argument("--no-t-sweep", action="store_true", help="skip the T = 8 / 64 / bench-T rows")
     return ap.parse_args()
 
 
@@ -178,9 +180,14 @@ def cpu_run(args, loci, T, os_threads):
     g = 0
     for i, ol in enumerate(ols):
         rng = O.Rng.from_seed(args.seed + i)
-        O.solve(ol, scheme, T, rng, os_threads=os_threads)
+        r = O.solve(ol, scheme, T, rng, os_threads=os_threads)
+        CPU_SPLIT[0] += r["t_prefilter_s"]
+        CPU_SPLIT[1] += r["t_stages_s"]
         g += ol.loc.n_genotypes
     return g, time.perf_counter() - t0
+
+
+CPU_SPLIT = [0.0, 0.0]      # seconds the CPU arm spent in the (single-threaded) prefilter / in the threaded stages
 
 
 def run_reference(args):
@@ -208,7 +215,8 @@ def run_reference(args):
         "config": workload_config(args, T, 1),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.loci} loci x {args.steps} steps, T={T} logical workers on {cores} pthreads "
-                                   "(prefilter single-threaded like the reference)"},
+                                   "(prefilter single-threaded like the reference)",
+                         "prefilter_share": CPU_SPLIT[0] / max(1e-12, CPU_SPLIT[0] + CPU_SPLIT[1])},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is Rust and cannot be built here (no cargo); this is the plain-C oracle port of the same path",
     }
@@ -226,8 +234,8 @@ def workload_config(args, T, world):
             "shape": args.config, "loci_per_step_per_gpu": args.loci, "threads_T": T, "mode": args.mode,
             "parallelism": f"loci x{world}" if args.mode == "loci" else f"genotype-shard x{world}",
             "loci_in_flight_per_gpu": (args.streams if args.streams > 0 else args.loci) if args.mode == "loci" else 1,
-            "l2": "per-step working set (per-worker candidate slabs, ~0.7 GB) exceeds the 126 MB L2; "
-                  "an L2 flush buffer (256 MB) is also written between timed steps"}
+            "l2": "an L2 flush buffer (256 MB > 126 MB) is written between timed steps; inputs (3 loci x ~26 MB) are "
+                  "re-read from HBM every step"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -332,6 +340,7 @@ def run_ours(args):
     # ---- e2e: host buffers in, host results out, through the public API, copies inside the timed region
     for _ in range(max(1, args.warmup - 1)):
         step_e2e()
+    pool.stats(reset=True)
     barrier()
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for k in range(args.steps):
@@ -344,8 +353,9 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * G_step * args.steps / (float(t2.item()) / 1e3)
-    n_surv = sum(c.n_filtered for c in calls)
-    d2h = int(n_surv * 16 + min(T, n_surv) * 32 + n_surv * 16 + len(loci) * 2000 * 8 * 2)
+    st_e2e = pool.stats(reset=True)             # the library counts the bytes of every copy it issues
+    h2d = st_e2e["h2d_bytes"] // args.steps
+    d2h = st_e2e["d2h_bytes"] // args.steps
 
     # all ranks exchange their calls (tiny) -- the only cross-GPU traffic of the loci mode
     my = torch.tensor([int(c.gt_ix[0]) for c in calls], dtype=torch.int64, device=dev)
@@ -375,9 +385,93 @@ def run_ours(args):
             line["roofline_prefilter_kir"] = kir_prefilter(ctx, genotype, peak, fp64_rate)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args, loci, T)
+            if not args.no_t_sweep:
+                line["t_sweep"] = t_sweep(args, ctx, genotype, loci[0])
+    # ---- configs[3]: the KIR-scale locus sharded over the N GPUs INSIDE the library (lctp_dist_*), at every N
+    kir = None if args.no_shard_kir else shard_kir(args, ctx, genotype, rank, world, dev)
+    if rank == 0:
+        if kir is not None:
+            line["shard_kir"] = kir
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def t_sweep(args, ctx, genotype, loc):
+    """`-@ T` changes results in the reference (survivor floors solve.rs:80,433, chunking :1057, RNG streams) and it is
+    what gives the GPU its parallel work: one C2 locus at the reference's default T = 8, at 64 and at the bench's T, both
+    arms (GPU: locus resident, CUDA events around lctp_solve; CPU: the oracle port on min(T, cores) pthreads)."""
+    import torch
+    cores = os.cpu_count() or 1
+    scheme = genotype.Scheme.parse(args.scheme)
+    dl = ctx.upload(loc)
+    rows = []
+    for T in (8, 64, auto_threads(args)):
+        dl.solve(scheme, T, genotype.init_rng(args.seed))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(torch.cuda.current_stream())
+        reps = 3
+        for _ in range(reps):
+            res = dl.solve(scheme, T, genotype.init_rng(args.seed))
+        b.record(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        g, dt = cpu_run(args, [loc], T, min(T, cores))
+        rows.append({"T": T, "gpu_ms_per_locus": ms, "gpu_genotypes_per_s": loc.n_genotypes / (ms / 1e3),
+                     "cpu_genotypes_per_s": g / dt, "cpu_threads": min(T, cores),
+                     "call": list(loc.genotype_tuple(int(res.gt_ix[0]))), "truth": list(loc.truth)})
+    dl.free()
+    return rows
+
+
+def shard_kir(args, ctx, genotype, rank, world, dev):
+    """BASELINE configs[3]: one KIR-scale locus (H = 1,000, 500,500 genotypes, 10,000 read pairs), genotype list sharded
+    over the `world` GPUs by the library itself: lctp_dist_solve = prefilter by id ranges + device-side candidate selection
+    + fixed-capacity ncclAllGather, greedy stage by logical workers modulo world + ncclAllGather (csrc/dist.cu).
+    Strong scaling: the same solve at every N, including N = 1."""
+    import torch
+    import torch.distributed as dist
+    from locityper_b200 import synth
+    T = auto_threads(args)
+    loc = synth.make_locus(**synth.config_shape("C4"), seed=4001, table_builder=genotype.build_depth_table)
+    dl = ctx.upload(loc)
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(genotype.dist_unique_id()), dtype=torch.uint8).to(dev)
+    if world > 1:
+        dist.broadcast(idt, 0)
+    d = genotype.Dist(ctx, bytes(idt.cpu().numpy().tobytes()), rank, world)
+    scheme = genotype.Scheme.parse(["greedy:i=5k,a=1"])
+    stream = torch.cuda.current_stream(dev)
+    d.solve(dl, scheme, T, genotype.init_rng(4001))
+    d.timing(reset=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    reps = 3
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(reps):
+        res = d.solve(dl, scheme, T, genotype.init_rng(4001))
+    b.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+    tm = d.timing()
+    parts = torch.tensor([tm["kernel_ms"] / reps, tm["collective_ms"] / reps, tm["host_ms"] / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(parts, op=dist.ReduceOp.MAX)
+    d.close()
+    dl.free()
+    ms = float(t.item())
+    return {"workload": "configs[3]: H=1000, G=500500, R=10000, one locus sharded by lctp_dist_solve, scheme greedy:i=5k,a=1",
+            "n_gpus": world, "threads_T": T, "ms_per_solve": ms, "genotypes_per_s": loc.n_genotypes / (ms / 1e3),
+            "kernel_ms": float(parts[0]), "collective_ms": float(parts[1]), "host_ms": float(parts[2]),
+            "collectives_per_solve": tm["collectives"] / reps, "gathered_bytes_per_solve": tm["gathered_bytes"] / reps,
+            "note": "max over ranks of each part (CUDA events for kernels and ncclAllGather, wall clock for the rest)",
+            "call": list(loc.genotype_tuple(int(res.gt_ix[0]))), "truth": list(loc.truth), "scaling": "strong"}
 
 
 def ncu_traffic(kernel):
@@ -474,12 +568,16 @@ def cpu_baseline(args, loci, T):
     cores = os.cpu_count() or 1
     n = args.cpu_loci or len(loci)
     cpu_run(args, loci[:1], T, cores)           # warm-up (page-in, thread pool)
+    CPU_SPLIT[0] = CPU_SPLIT[1] = 0.0
     g, dt, reps = 0, 0.0, 0
     while dt < 10.0 and reps < 8:               # bounded sample: ~10-30 s of CPU work
         gi, di = cpu_run(args, loci[:n], T, cores)
         g += gi; dt += di; reps += 1
     return {"value": g / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} loci x {reps} passes of the same workload, T={T} logical workers on {cores} pthreads"}
+            "sample": f"{n} loci x {reps} passes of the same workload, T={T} logical workers on {cores} pthreads",
+            # the reference's prefilter is a plain loop on the calling thread (solve.rs:105-119) and the port keeps it so:
+            # this is the share of the CPU arm's time that no amount of host cores would shorten
+            "prefilter_share": CPU_SPLIT[0] / max(1e-12, CPU_SPLIT[0] + CPU_SPLIT[1])}
 
 
 def run_shard(args, ctx, scheme, T, rank, world, dev):

@@ -301,6 +301,46 @@ int  lctp_find_weighted_dist(lctp_result *res, const lctp_locus *loc, const uint
  * `rng` is the locus stream (in/out); `threads` is the reference's -@ (number of logical workers). */
 int  lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_t threads,
                 uint64_t rng[4], lctp_result *res);
+/* ---- one locus sharded over the GPUs of a box ----------------------------------------
+ * One process (or thread) per GPU, each with its own lctp_ctx and the same locus uploaded.  Genotypes are independent
+ * units of both phases (src/solvers/solve.rs:105-119, :1116-1142): the prefilter is split by contiguous genotype id
+ * ranges, the stages by logical workers (w mod world); the two exchanges are ncclAllGather calls over NVLink, issued
+ * by the library on the context's stream (NCCL is dlopen'ed at lctp_dist_init: single-GPU users do not need it).
+ * Results are identical on every rank and identical to the single-GPU calls. */
+#define LCTP_DIST_ID_BYTES 128   /* sizeof(ncclUniqueId) */
+typedef struct lctp_dist lctp_dist;
+typedef struct lctp_dist_timing {        /* accumulated since the last reset, this rank */
+    double   kernel_ms;                  /* prefilter + stage kernels (CUDA events) */
+    double   collective_ms;              /* ncclAllGather calls (CUDA events on the launch stream) */
+    double   host_ms;                    /* lctp_dist_solve wall time minus the two above */
+    double   wall_ms;                    /* lctp_dist_solve wall time */
+    uint64_t collectives, gathered_bytes, overflow_rounds, solves;
+} lctp_dist_timing;
+/* ncclGetUniqueId: call on one rank, hand the 128 bytes to the others out of band (MPI, torch.distributed, a file). */
+int  lctp_dist_unique_id(uint8_t id[LCTP_DIST_ID_BYTES]);
+/* ncclCommInitRank on the context's device; collective over all `world` ranks. */
+int  lctp_dist_init(lctp_ctx *ctx, const uint8_t id[LCTP_DIST_ID_BYTES], int rank, int world, lctp_dist **out);
+void lctp_dist_destroy(lctp_dist *d);
+int  lctp_dist_rank(const lctp_dist *d);
+int  lctp_dist_world(const lctp_dist *d);
+int  lctp_dist_get_timing(lctp_dist *d, lctp_dist_timing *out, int reset);
+/* run_filter (src/solvers/solve.rs:87-122) over all G genotypes, sharded: this rank scores its id range, selects on
+ * the device the candidates that can survive truncate_ixs (:52-84) -- everything >= min(local best - filt_diff,
+ * K-th best local), K = max(min_size, threads) -- and the ranks all-gather fixed-capacity buffers of (score f64,
+ * id u64) + {count, overflow}; a second, larger exchange only when some rank overflowed.  ixs_out (capacity cap_out,
+ * world * max(min_size, threads) is always enough when nothing ties) receives the sorted survivors. */
+int  lctp_dist_prefilter(lctp_dist *d, lctp_locus_h *h, size_t min_size, size_t threads, uint64_t *ixs_out,
+                         size_t cap_out, size_t *n_out);
+/* lctp_solve_stage, sharded: same arguments on every rank (the caller shuffles / partitions with the shared locus
+ * stream, e.g. lctp_plan_stage); this rank solves workers w = rank (mod world); lik_mean / lik_var / worker_rng come
+ * back complete on every rank. */
+int  lctp_dist_solve_stage(lctp_dist *d, lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_ixs,
+                           const uint64_t *worker_off, size_t n_workers, uint64_t *worker_rng, double *lik_mean,
+                           double *lik_var);
+/* lctp_solve, sharded (collective; every rank passes the same arguments and receives the same result and rng). */
+int  lctp_dist_solve(lctp_dist *d, lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_t threads,
+                     uint64_t rng[4], lctp_result *res);
+
 /* Genotyping::to_json (src/solvers/solve.rs:732-773), pretty-printed with indent 4 like
  * src/command/genotype.rs:1256.  hap_names[H]; returns bytes needed (excluding NUL). */
 size_t lctp_result_json(const lctp_result *res, const lctp_locus *loc, const char *const *hap_names,

@@ -186,6 +186,10 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
                  const uint64_t *worker_off, size_t n_workers, uint64_t *worker_rng,
                  double *lik_mean, double *lik_var, double *liks, uint64_t *counts_off,
                  uint16_t *counts, uint64_t counts_cap, uint64_t *n_alns_out, uint64_t *iters_out);
+int launch_stage_ex(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_ixs,
+                    const uint64_t *worker_off, size_t n_workers, uint64_t *worker_rng,
+                    double *lik_mean, double *lik_var, double *liks, uint64_t *counts_off,
+                    uint16_t *counts, uint64_t counts_cap, uint64_t *n_alns_out, uint64_t *iters_out, bool device_only);
 // host_solve.cpp
 void genotype_tuple(uint32_t H, uint32_t p, const uint32_t *gt_tuples, uint64_t g, uint32_t *out);
 }  // namespace lctp

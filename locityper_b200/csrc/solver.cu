@@ -55,7 +55,7 @@ struct StageParams {
     uint32_t kind, attempts, best_start, sample_size;
     uint64_t plato_size, anneal_steps, max_iter;
     double ln_init_prob;
-    uint32_t n_workers, cap, Wmax, want_counts, narrow_w, _pad;
+    uint32_t n_workers, cap, Wmax, want_counts, narrow_w, nt_global;
     uint64_t slab_bytes;
 };
 
@@ -82,20 +82,23 @@ template <bool WIDE>
 struct Slab {
     typedef typename RecWord<WIDE>::T Rec;
     Rec *rec;              // [cap]  record of every candidate, reads in read order (the reference's `alns`, a5)
+    uint16_t *nt_read;     // [R]    list of the non-trivial reads when it does not fit shared memory (StageParams::nt_global)
     uint64_t *rng_buf;     // [RNG_FILL] pre-generated draws of the worker's stream
     uint64_t *rng_blk;     // [32*4] block-start generator states of the current fill
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline size_t slab_bytes_for(uint32_t cap, bool wide) {
-    return (size_t)RNG_FILL * 8 + 32 * 4 * 8 + align_up((size_t)cap * (wide ? 8 : 4), 128);
+__host__ __device__ inline size_t slab_bytes_for(uint32_t cap, bool wide, uint32_t nt_global_reads) {
+    return (size_t)RNG_FILL * 8 + 32 * 4 * 8 + align_up((size_t)cap * (wide ? 8 : 4), 128) +
+           align_up((size_t)nt_global_reads * 2, 128);
 }
 template <bool WIDE>
 __device__ __forceinline__ void slab_layout(uint32_t cap, unsigned char *base, Slab<WIDE> &s) {
     s.rng_buf = (uint64_t *)base;
     s.rng_blk = (uint64_t *)(base + (size_t)RNG_FILL * 8);
     s.rec = (typename Slab<WIDE>::Rec *)(base + (size_t)RNG_FILL * 8 + 32 * 4 * 8);
+    s.nt_read = (uint16_t *)(base + (size_t)RNG_FILL * 8 + 32 * 4 * 8 + align_up((size_t)cap * (WIDE ? 8 : 4), 128));
 }
 
 // ------------------------------------------------------------------ warp helpers ----------------
@@ -375,19 +378,23 @@ __host__ __device__ inline uint32_t win_stride(uint32_t Wmax) { return (Wmax + 1
 struct WarpShared {
     WinState win;
     uint16_t *off;         // [R+1]  first candidate of every read (+ end sentinel)
-    uint16_t *nt_read;     // [R]    read ids of the non-trivial reads (more than one candidate), ascending
+    uint16_t *nt_read;     // [R]    read ids of the non-trivial reads (more than one candidate), ascending; GENERIC
+                           //        pointer: shared memory, or the worker's slab when R is large (nt_global)
     uint8_t *assgn;        // [R]    current assignment (candidate rank) of every read
     uint32_t *unm_bits;    // [ceil(R/32)] bit r%32 of word r/32: read r has the "unmapped" option among its candidates
     uint32_t *haps;        // [LCTP_MAX_PLOIDY] haplotypes of the genotype, then [LCTP_MAX_PLOIDY+1] window shifts
-    uint32_t *samp;        // [12] scratch of sample_resolve
+    uint32_t *samp;        // [12] scratch of sample_resolve; [12..16) spare
+    double *lik;           // [0] aln_lik, [1] depth_lik of the assignment being solved (lane 0 updates them: two fewer
+                           //     64-bit values live in the solver loops), [2] = iterations of the genotype as u64
     uint32_t zero_row;     // offset of the all-zero row
     uint32_t depth_k;
     uint32_t lane;
 };
-__host__ __device__ inline size_t group_smem_bytes(uint32_t Wmax, uint32_t R) {
-    return align_up((size_t)win_stride(Wmax) * 56, 16) + align_up(((size_t)R + 1) * 2, 16) + align_up((size_t)R * 2, 16) +
+__host__ __device__ inline size_t group_smem_bytes(uint32_t Wmax, uint32_t R, bool nt_global) {
+    return align_up((size_t)win_stride(Wmax) * 56, 16) + align_up(((size_t)R + 1) * 2, 16) +
+           (nt_global ? 0 : align_up((size_t)R * 2, 16)) +
            align_up((size_t)R, 16) + align_up((size_t)((R + 31) / 32) * 4, 16) +
-           align_up((size_t)(2 * LCTP_MAX_PLOIDY + 1) * 4, 16) + 64 /* samp */ + 1024 /* draw ring */;
+           align_up((size_t)(2 * LCTP_MAX_PLOIDY + 1) * 4, 16) + 64 /* samp */ + 32 /* lik */ + 1024 /* draw ring */;
 }
 
 // Recompute slice entry k of window w from its (weight, row, depth).
@@ -705,7 +712,7 @@ __device__ __forceinline__ void seq_add(double &acc, double term, int count) {
 // init_mode 0: every read at candidate 0; 1: random_range(0..m) per non-trivial read (read order).
 template <bool WIDE>
 __device__ void init_assignment(const LocusDev &L, const Slab<WIDE> &S, const Instance &I, const WarpShared &ws,
-                                Xo &rng, int init_mode, double &aln_lik, double &depth_lik) {
+                                Xo &rng, int init_mode) {
     typedef RecWord<WIDE> RW;
     const int lane = (int)ws.lane;
     const uint32_t R = L.R;
@@ -755,8 +762,8 @@ __device__ void init_assignment(const LocusDev &L, const Slab<WIDE> &S, const In
         const double term = w < I.W ? ws.win.p(w, 2) : 0.0;
         seq_add(dl, term, (int)min(32u, I.W - w0));
     }
-    aln_lik = al;
-    depth_lik = dl;
+    if (lane == 0) { ws.lik[0] = al; ws.lik[1] = dl; }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------ a9: targets -----------------
@@ -792,10 +799,8 @@ __device__ __forceinline__ double calc_improvement(const LocusDev &L, const Slab
 // reassign (src/model/assgn.rs:331-343); warp-uniform inputs, lane 0 writes
 template <bool WIDE>
 __device__ __forceinline__ void apply_move(const WarpShared &ws, const double *__restrict__ table, uint32_t r,
-                                           uint32_t new_a, const Move<WIDE> &mv, double &aln_lik, double &depth_lik) {
+                                           uint32_t new_a, const Move<WIDE> &mv) {
     typedef RecWord<WIDE> RW;
-    depth_lik = __dadd_rn(depth_lik, mv.dld);
-    aln_lik = __dadd_rn(aln_lik, mv.dlp);
     const uint32_t w1 = RW::w1(mv.raw_old), w2 = RW::w2(mv.raw_old), w3 = RW::w1(mv.raw_new), w4 = RW::w2(mv.raw_new);
     if (ws.lane == 0) {
         ws.win.depth(w3) += 1;
@@ -803,6 +808,8 @@ __device__ __forceinline__ void apply_move(const WarpShared &ws, const double *_
         ws.win.depth(w1) -= 1;
         ws.win.depth(w2) -= 1;
         ws.assgn[r] = (uint8_t)new_a;
+        ws.lik[1] = __dadd_rn(ws.lik[1], mv.dld);       // depth_lik += ..., aln_lik += ... (assgn.rs:336-337)
+        ws.lik[0] = __dadd_rn(ws.lik[0], mv.dlp);
     }
     __syncwarp();
     // slide the product slices of the (up to four) windows whose depth changed
@@ -940,9 +947,6 @@ __device__ double max_abs_random(const LocusDev &L, const Slab<WIDE> &S, const I
 // the lane-parallel path consumes exactly `amount` draws of the current fill or nothing at all.
 __device__ __forceinline__ bool sample_draw(Xo &rng, uint32_t n_nt, uint32_t amount, bool slow, uint32_t &myv) {
     const uint32_t lane = rng.lane;
-    // the range is recomputed every round on purpose: hoisted out of the greedy loop it is one more live register,
-    // and the allocator answered by spilling it (a local-memory reload per round; the L1 is carved down to ~30 KB)
-    asm volatile("" : "+r"(n_nt));
     if (!slow) return xo_below_lanes(rng, amount, n_nt - amount + min(lane, amount - 1u) + 1u, myv);
     for (uint32_t k = 0; k < amount; k++) {
         const uint32_t t = xo_below(rng, n_nt - amount + k + 1u);
@@ -999,7 +1003,7 @@ __device__ __forceinline__ bool cand_better(const Cand<WIDE> &a, const Cand<WIDE
 // whole sample whatever the candidate counts are.  A job's data is two dependent hops away (private candidate
 // records + the read's run offsets, then the shared ln-probabilities), so samples are drawn three iterations
 // ahead and move through four stages, one per loop round:
-//   S  sample drawn
+//   S  sample drawn, the read ids of the sampled non-trivial reads in flight
 //   A  jobs dealt, first-hop loads in flight
 //   B  second-hop loads in flight
 //   C  evaluated: touches only registers and shared memory
@@ -1025,14 +1029,12 @@ struct SlotB {
 // Deal the jobs of the sample `myv` (lane k < amount holds the k-th sampled read) and issue the first-hop loads.
 template <bool WIDE>
 __device__ __forceinline__ void load_slot_a(const LocusDev &L, const Slab<WIDE> &S, const Instance &I,
-                                            const WarpShared &ws, uint32_t amount, uint32_t myv, SlotA<WIDE> &x) {
+                                            const WarpShared &ws, uint32_t amount, uint32_t myv, uint32_t lr,
+                                            SlotA<WIDE> &x) {
     const uint32_t lane = ws.lane;
     const bool lead = lane < amount;
-    uint32_t lr = 0, n_alt = 0;
-    if (lead) {
-        lr = ws.nt_read[myv];
-        n_alt = (uint32_t)ws.off[lr + 1] - ws.off[lr] - 1u;
-    }
+    uint32_t n_alt = 0;
+    if (lead) n_alt = (uint32_t)ws.off[lr + 1] - ws.off[lr] - 1u;
     uint32_t incl = n_alt;
 #pragma unroll
     for (int d = 1; d < 16; d <<= 1) {              // amount <= 11: four rounds
@@ -1099,16 +1101,28 @@ __device__ __forceinline__ void eval_cand(const LocusDev &L, const WarpShared &w
 // reductions in the reference's tie order.
 template <bool WIDE>
 __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab<WIDE> &S, const Instance &I,
-                             const WarpShared &ws, Xo &rng, double &aln_lik, double &depth_lik,
-                             uint64_t &iters_out) {
+                             const WarpShared &ws, Xo &rng) {
     typedef RecWord<WIDE> RW;
     const uint32_t lane = ws.lane;
     const uint32_t amount = min(P.sample_size, I.n_nt);
-    init_assignment<WIDE>(L, S, I, ws, rng, P.best_start ? 0 : 1, aln_lik, depth_lik);
-    const double min_diff = fmax(__dmul_rn(1e-10, max_abs_random<WIDE>(L, S, I, ws, rng)), 1e-14);
-    uint64_t curr_plato = 0, it = 0;
+    init_assignment<WIDE>(L, S, I, ws, rng, P.best_start ? 0 : 1);
+    // Loop-invariant scalars of the greedy loop (min_diff, the number of non-trivial reads) are parked in shared
+    // memory and re-read every round through volatile pointers: kept in registers across the loop the allocator
+    // spilled them to local memory, and with the L1 carved down to ~30 KB those reloads come from the L2
+    // (ncu: 5 % + 5 % of the kernel waiting on two LDL).
+    {
+        const double md = fmax(__dmul_rn(1e-10, max_abs_random<WIDE>(L, S, I, ws, rng)), 1e-14);
+        if (lane == 0) { ws.lik[3] = md; ws.samp[12] = I.n_nt; }
+        __syncwarp();
+    }
+    const volatile double *v_min_diff = ws.lik + 3;
+    const volatile uint32_t *v_n_nt = ws.samp + 12;
+    // 32-bit counters: lctp_solve_stage refuses plateau sizes that would need more
+    uint32_t curr_plato = 0, it = 0;
+    const uint32_t plato_size = (uint32_t)P.plato_size, max_iter = (uint32_t)P.max_iter;
     bool vS = false, vA = false, vB = false, vC = false;
-    uint32_t s_myv = 0;
+    uint32_t s_myv = 0, s_r = ws.nt_read[0];       // sampled index / its read id (lanes < amount)
+    __syncwarp();
     SlotA<WIDE> sa;
     SlotB<WIDE> sb, cur;
     sa.job = sa.b0 = sa.b1 = sa.lead = sa.total = 0; sa.ro = sa.rn = 0;
@@ -1170,7 +1184,7 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
             }
             const double s_best = wshfl(best.s, wl);
             it++;
-            if (s_best > min_diff) {
+            if (s_best > *v_min_diff) {
                 Move<WIDE> mv;
                 mv.dld = wshfl(best.dld, wl);
                 mv.dlp = wshfl(best.dlp, wl);
@@ -1179,7 +1193,7 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
                 const uint32_t w_job = wshfl(best.job, wl);
                 const uint32_t w_r = job_r(w_job), w_c = job_c(w_job);
                 const uint32_t old_a = ws.assgn[w_r];
-                apply_move<WIDE>(ws, L.depth_table, w_r, w_c, mv, aln_lik, depth_lik);
+                apply_move<WIDE>(ws, L.depth_table, w_r, w_c, mv);
                 curr_plato = 0;
                 // samples in flight saw the old assignment of the moved read: redo their loads (rare)
                 if (vB && wany(lane < sb.total && job_r(sb.job) == w_r)) {
@@ -1196,9 +1210,9 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
                 if (vA && wany(lane < sa.total && job_r(sa.job) == w_r)) reload_slot_a<WIDE>(S, ws, w_r, old_a, sa);
             } else {
                 curr_plato += 1;
-                if (curr_plato > P.plato_size) break;
+                if (curr_plato > plato_size) break;
             }
-            if (it >= P.max_iter) break;
+            if (it >= max_iter) break;
         }
         // ---- advance the pipeline by one stage.  Unconditionally: a stage that holds nothing valid (start-up, the
         // rounds after the fill ran out) moves harmless stale values.  With the loads under `if (valid)` the compiler
@@ -1207,17 +1221,25 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
         cur = sb; vC = vB;
         load_slot_b<WIDE>(L, I, ws, sa, sb);
         vB = vA;
-        sample_resolve(ws, I.n_nt, amount, s_myv);
-        load_slot_a<WIDE>(L, S, I, ws, amount, s_myv, sa);
+        load_slot_a<WIDE>(L, S, I, ws, amount, s_myv, s_r, sa);
         vA = vS;
         // ---- stage S: draw the next sample.  The refilling path may only run on an empty pipeline: the samples in
         // flight are given back to the stream when the loop ends, which cannot cross a refill.
-        vS = sample_draw(rng, I.n_nt, amount, false, s_myv);
-        if (!vS && !vA && !vB && !vC) vS = sample_draw(rng, I.n_nt, amount, true, s_myv);
+        const uint32_t n_nt = *v_n_nt;
+        vS = sample_draw(rng, n_nt, amount, false, s_myv);
+        if (!vS && !vA && !vB && !vC) vS = sample_draw(rng, n_nt, amount, true, s_myv);
+        sample_resolve(ws, n_nt, amount, s_myv);            // a stale sample is already free of duplicates
+        // The list may live in the slab: its entries are fetched a round ahead.  Through asm, as a 32-bit value: the
+        // compiler's own 16-bit load is followed by a zero-extension that it scheduled at the top of the next round,
+        // i.e. right behind the load (ncu: 7 % of the kernel).
+        {
+            const uint16_t *ptr = ws.nt_read + (lane < amount ? s_myv : 0u);
+            asm volatile("ld.u16 %0, [%1];" : "=r"(s_r) : "l"(ptr));
+        }
     }
     // the pre-drawn samples of iterations that never ran
     stream_unconsume(rng, amount * ((vS ? 1u : 0u) + (vA ? 1u : 0u) + (vB ? 1u : 0u)));
-    iters_out += it;
+    if (lane == 0) ((uint64_t *)ws.lik)[2] += it;
 }
 
 // ------------------------------------------------------------------ a11: SimAnneal --------------
@@ -1228,9 +1250,8 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
 // but the plateau counter.
 template <bool WIDE>
 __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab<WIDE> &S, const Instance &I,
-                             const WarpShared &ws, Xo &rng, double &aln_lik, double &depth_lik,
-                             uint64_t &iters_out) {
-    init_assignment<WIDE>(L, S, I, ws, rng, 1, aln_lik, depth_lik);
+                             const WarpShared &ws, Xo &rng) {
+    init_assignment<WIDE>(L, S, I, ws, rng, 1);
     const double max_abs = max_abs_random<WIDE>(L, S, I, ws, rng);
     const double min_diff = fmax(__dmul_rn(1e-10, max_abs), 1e-14);
     const double start_temp = fmax(__ddiv_rn(-max_abs, P.ln_init_prob), 1e-5);
@@ -1252,7 +1273,7 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
                 accept = u <= exp(__ddiv_rn(diff, __dmul_rn(temp_step, (double)i)));
             }
             i--;
-            if (accept) { apply_move<WIDE>(ws, L.depth_table, t.r, t.new_a, mv, aln_lik, depth_lik); curr_plato = 0; }
+            if (accept) { apply_move<WIDE>(ws, L.depth_table, t.r, t.new_a, mv); curr_plato = 0; }
             else { curr_plato += 1; if (curr_plato >= P.plato_size) break; }
             continue;
         }
@@ -1290,7 +1311,7 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
             w.raw_old = wshfl(mv.raw_old, src); w.raw_new = wshfl(mv.raw_new, src);
             const uint32_t w_r = wshfl(sp.r, src), w_new = wshfl(sp.new_a, src);
             rng.pos += off_acc;
-            apply_move<WIDE>(ws, L.depth_table, w_r, w_new, w, aln_lik, depth_lik);
+            apply_move<WIDE>(ws, L.depth_table, w_r, w_new, w);
             steps++; i--; curr_plato = 0;
         } else {
             rng.pos += spec_offset_after(sp, ws.lane, n_rej, sp.nd + 1u);
@@ -1306,7 +1327,7 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
             Move<WIDE> mv;
             const double diff = calc_improvement<WIDE>(L, S, I, ws, t.r, t.o, t.a, t.new_a, mv);
             steps++; k++;
-            if (diff > min_diff) { apply_move<WIDE>(ws, L.depth_table, t.r, t.new_a, mv, aln_lik, depth_lik); curr_plato = 0; }
+            if (diff > min_diff) { apply_move<WIDE>(ws, L.depth_table, t.r, t.new_a, mv); curr_plato = 0; }
             else curr_plato += 1;
             continue;
         }
@@ -1335,13 +1356,13 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
             w.raw_old = wshfl(mv.raw_old, src); w.raw_new = wshfl(mv.raw_new, src);
             const uint32_t w_r = wshfl(sp.r, src), w_new = wshfl(sp.new_a, src);
             rng.pos += off_acc;
-            apply_move<WIDE>(ws, L.depth_table, w_r, w_new, w, aln_lik, depth_lik);
+            apply_move<WIDE>(ws, L.depth_table, w_r, w_new, w);
             steps++; k++; curr_plato = 0;
         } else {
             rng.pos += spec_offset_after(sp, ws.lane, n_rej, sp.nd);
         }
     }
-    iters_out += steps;
+    if (ws.lane == 0) ((uint64_t *)ws.lik)[2] += steps;
 }
 
 // ------------------------------------------------------------------ stage kernel ----------------
@@ -1350,7 +1371,7 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
 // worker); with 16 the 128-register cap spilled min_diff and the sampling ranges into local memory inside the greedy
 // loop, and with the L1 carved down to ~30 KB those reloads go to the L2 (ncu: 10 % of the kernel).
 #ifndef LCTP_MIN_CTAS
-#define LCTP_MIN_CTAS 14
+#define LCTP_MIN_CTAS 16
 #endif
 template <bool WIDE>
 __global__ void __launch_bounds__(CTA_THREADS, LCTP_MIN_CTAS)
@@ -1367,14 +1388,18 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
     const int lane = (int)lane_reg;
     WarpShared ws;
     Xo rng;
+    Slab<WIDE> S;
+    slab_layout<WIDE>(P.cap, scratch + (size_t)blockIdx.x * P.slab_bytes, S);
     {
         unsigned char *base = smem;
         rng.ring = (uint64_t *)base;           base += 1024;
         ws.samp = (uint32_t *)base;            base += 64;
+        ws.lik = (double *)base;               base += 32;
         ws.win.base = (double *)base;          ws.win.wp = win_stride(P.Wmax);
         base += align_up((size_t)ws.win.wp * 56, 16);
         ws.off = (uint16_t *)base;             base += align_up(((size_t)L.R + 1) * 2, 16);
-        ws.nt_read = (uint16_t *)base;         base += align_up((size_t)L.R * 2, 16);
+        if (P.nt_global) ws.nt_read = S.nt_read;
+        else { ws.nt_read = (uint16_t *)base;  base += align_up((size_t)L.R * 2, 16); }
         ws.assgn = (uint8_t *)base;            base += align_up((size_t)L.R, 16);
         ws.unm_bits = (uint32_t *)base;        base += align_up((size_t)((L.R + 31) / 32) * 4, 16);
         ws.haps = (uint32_t *)base;
@@ -1382,11 +1407,11 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
         ws.depth_k = L.depth_k;
         ws.lane = lane_reg;
     }
-    Slab<WIDE> S;
-    slab_layout<WIDE>(P.cap, scratch + (size_t)blockIdx.x * P.slab_bytes, S);
     rng.buf = S.rng_buf; rng.blk = S.rng_blk; rng.tabs = jump_tabs; rng.lane = lane_reg;
     rng.pos = 0; rng.base = 0; rng.pend = 0;
 
+    // Everything that is only needed between genotypes (position, prior, count pointer, iteration total) is re-read
+    // or kept in shared memory instead of living in registers across the solver loops.
     for (;;) {
         uint32_t w = 0;
         if (lane == 0) w = atomicAdd(work_counter, 1u);
@@ -1394,8 +1419,6 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
         if (w >= P.n_workers) break;
         stream_begin(rng, rng_states + 4 * (size_t)w);
         for (uint64_t j = worker_off[w]; j < worker_off[w + 1]; j++) {
-            const uint64_t gt = worker_ixs[j];
-            const double prior = L.priors ? L.priors[gt] : 0.0;
             Instance I;
             __syncwarp();
             if (lane == 0) {
@@ -1407,6 +1430,7 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
                     wsft += L.hap_n_windows[h];
                 }
                 ws.haps[LCTP_MAX_PLOIDY + L.p] = wsft;
+                ((uint64_t *)ws.lik)[2] = 0;
             }
             __syncwarp();
             I.h0 = ws.haps[0];
@@ -1414,30 +1438,33 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
             I.W = ws.haps[LCTP_MAX_PLOIDY + L.p];
             const bool ok = L.p <= 2 ? build_instance<LCTP_HEADS, WIDE>(L, S, ws, P.cap, I)
                                      : build_instance<0, WIDE>(L, S, ws, P.cap, I);
+            if (lane == 0) n_alns[j] = I.A;
             if (!ok) {
-                if (lane == 0) { atomicOr(err, 1); lik_mean[j] = NAN; lik_var[j] = NAN; n_alns[j] = I.A; iters[j] = 0; }
+                if (lane == 0) { atomicOr(err, 1); lik_mean[j] = NAN; lik_var[j] = NAN; iters[j] = 0; }
                 continue;
             }
-            uint16_t *cnt = P.want_counts ? counts + (size_t)j * P.cap : nullptr;
-            if (cnt) { for (uint32_t c = lane; c < I.A; c += 32) cnt[c] = 0; }
-            uint64_t it_total = 0;
+            if (P.want_counts) {
+                uint16_t *cnt = counts + (size_t)j * P.cap;
+                for (uint32_t c = lane; c < I.A; c += 32) cnt[c] = 0;
+            }
             for (uint32_t a = 0; a < P.attempts; a++) {
                 apply_tweak<WIDE>(L, S, I, ws, rng);
-                double aln_lik = 0.0, depth_lik = 0.0;
-                if (I.n_nt == 0) init_assignment<WIDE>(L, S, I, ws, rng, 0, aln_lik, depth_lik);
-                else if (P.kind == 0) greedy_solve<WIDE>(L, P, S, I, ws, rng, aln_lik, depth_lik, it_total);
-                else anneal_solve<WIDE>(L, P, S, I, ws, rng, aln_lik, depth_lik, it_total);
-                // likelihood (assgn.rs:235-237) + prior (solve.rs:1126)
-                const double lik = __dadd_rn(prior, __dadd_rn(__dmul_rn(L.depth_contrib, depth_lik),
-                                                              __dmul_rn(L.aln_contrib, aln_lik)));
-                if (lane == 0) liks[j * P.attempts + a] = lik;
-                if (cnt) {   // update_counts (assgn.rs:374-378)
-                    __syncwarp();
+                if (I.n_nt == 0) init_assignment<WIDE>(L, S, I, ws, rng, 0);
+                else if (P.kind == 0) greedy_solve<WIDE>(L, P, S, I, ws, rng);
+                else anneal_solve<WIDE>(L, P, S, I, ws, rng);
+                __syncwarp();
+                if (lane == 0) {
+                    // likelihood (assgn.rs:235-237) + prior (solve.rs:1126)
+                    const double prior = L.priors ? L.priors[worker_ixs[j]] : 0.0;
+                    liks[j * P.attempts + a] = __dadd_rn(prior, __dadd_rn(__dmul_rn(L.depth_contrib, ws.lik[1]),
+                                                                          __dmul_rn(L.aln_contrib, ws.lik[0])));
+                }
+                if (P.want_counts) {   // update_counts (assgn.rs:374-378)
+                    uint16_t *cnt = counts + (size_t)j * P.cap;
                     for (uint32_t r = lane; r < L.R; r += 32) cnt[(uint32_t)ws.off[r] + ws.assgn[r]] += 1;
                 }
                 __syncwarp();
             }
-            __syncwarp();
             // mean_variance_or_nan (ext/vec.rs:74-78,86-93,109-116)
             if (lane == 0) {
                 const double *x = liks + j * P.attempts;
@@ -1455,8 +1482,7 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
                 }
                 lik_mean[j] = mean;
                 lik_var[j] = var;
-                n_alns[j] = I.A;
-                iters[j] = it_total;
+                iters[j] = ((const uint64_t *)ws.lik)[2];
             }
             __syncwarp();
         }
@@ -1555,7 +1581,7 @@ static int launch_stage_kernel(lctp_locus_h *h, const StageParams &P, size_t n_w
     lctp_ctx *ctx = h->ctx;
     cudaStream_t s = ctx->stream;
     const LocusDev &L = h->dev;
-    const size_t smem = group_smem_bytes(P.Wmax, L.R);
+    const size_t smem = group_smem_bytes(P.Wmax, L.R, P.nt_global != 0);
     if (smem > ctx->smem_optin) {
         set_error("lctp_solve_stage: %zu bytes of shared memory per worker needed (R=%u reads, %u windows); "
                   "loci this large are not supported by the shared-memory resident solver", smem, L.R, P.Wmax);
@@ -1583,7 +1609,7 @@ static int launch_stage_kernel(lctp_locus_h *h, const StageParams &P, size_t n_w
     // from at random, and a worker whose slab has been evicted runs at DRAM latency.  Never fewer than one
     // worker per SM sub-partition.
     {
-        const size_t budget = (size_t)std::max(1, env_int("LCTP_L2_BUDGET_MB", 72)) << 20;
+        const size_t budget = (size_t)std::max(1, env_int("LCTP_L2_BUDGET_MB", 96)) << 20;
         const size_t per = std::max<size_t>(1, P.slab_bytes);
         const uint32_t by_l2 = (uint32_t)std::max<size_t>(budget / per, (size_t)ctx->sm_count * 4);
         resident = std::min(resident, by_l2);
@@ -1608,11 +1634,22 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
                  size_t n_workers, uint64_t *worker_rng, double *lik_mean, double *lik_var, double *liks,
                  uint64_t *counts_off, uint16_t *counts, uint64_t counts_cap, uint64_t *n_alns_out,
                  uint64_t *iters_out) {
+    return launch_stage_ex(h, st, worker_ixs, worker_off, n_workers, worker_rng, lik_mean, lik_var, liks, counts_off,
+                           counts, counts_cap, n_alns_out, iters_out, false);
+}
+
+// device_only: validate, upload, launch and return; the results stay on the device (ctx->d_lik_mean / d_lik_var /
+// d_rng / d_flags, indexed like the host outputs) for the multi-GPU exchange (dist.cu), which never needs them on
+// the host of the rank that computed them.
+int launch_stage_ex(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_ixs, const uint64_t *worker_off,
+                    size_t n_workers, uint64_t *worker_rng, double *lik_mean, double *lik_var, double *liks,
+                    uint64_t *counts_off, uint16_t *counts, uint64_t counts_cap, uint64_t *n_alns_out,
+                    uint64_t *iters_out, bool device_only) {
     lctp_ctx *ctx = h->ctx;
     cudaStream_t s = ctx->stream;
     const LocusDev &L = h->dev;
     const double t_enter = dbg_now();
-    if (!st || !worker_ixs || !worker_off || !worker_rng || !lik_mean || !lik_var || n_workers == 0) {
+    if (!st || !worker_ixs || !worker_off || !worker_rng || (!device_only && (!lik_mean || !lik_var)) || n_workers == 0) {
         set_error("lctp_solve_stage: NULL argument");
         return LCTP_E_INVALID;
     }
@@ -1630,6 +1667,10 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     if (st->kind == 1 && (!(st->init_prob > 0.0 && st->init_prob <= 1.0) || st->anneal_steps == 0)) {
         set_error("lctp_solve_stage: invalid annealing parameters");
         return LCTP_E_INVALID;
+    }
+    if (st->plato_size >= 0x40000000ull) {
+        set_error("lctp_solve_stage: plateau size %llu too large (device counters are 32-bit)", (unsigned long long)st->plato_size);
+        return LCTP_E_CAPACITY;
     }
     if (L.R > 65535u) {
         set_error("lctp_solve_stage: %u reads exceed the 65535 the shared-memory read tables can index", L.R);
@@ -1669,8 +1710,16 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     P.want_counts = want_counts ? 1 : 0;
     P.narrow_w = P.Wmax <= 4096 ? 1 : 0;                       // 32-bit candidate records (12-bit windows)
     if (env_int("LCTP_WIDE_WINDOWS", 0)) P.narrow_w = 0;       // test knob: exercise the 64-bit candidate records
-    P._pad = 0;
-    P.slab_bytes = slab_bytes_for(cap, P.narrow_w == 0);
+    // The list of non-trivial reads (2 bytes per read) stays in shared memory while 16 workers per SM still fit
+    // (the register file allows no more); for larger R it moves to the worker's slab -- the greedy loop fetches
+    // its entries one round ahead either way.
+    {
+        const size_t per_sm = ctx->smem_optin + 1024;            // opt-in limit per CTA = SM capacity - 1 KB
+        const size_t with_nt = group_smem_bytes(P.Wmax, L.R, false) + 1024;
+        P.nt_global = (16 * with_nt > per_sm) ? 1 : 0;
+        if (const char *e = getenv("LCTP_NT_GLOBAL")) P.nt_global = atoi(e) ? 1 : 0;      // test / tuning knob
+    }
+    P.slab_bytes = slab_bytes_for(cap, P.narrow_w == 0, P.nt_global ? L.R : 0);
 
     int rc;
     if ((rc = ensure_jump_tables(ctx))) return rc;
@@ -1696,6 +1745,12 @@ int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_i
     const double t_launch = dbg_now();
     rc = launch_stage_kernel(h, P, n_workers, want_counts);
     if (rc) return rc;
+    if (device_only) {
+        ctx->stats.stage_launches += 1;
+        ctx->stats.stage_genotypes += n;
+        ctx->stats.stage_attempts += n * st->attempts;
+        return LCTP_OK;
+    }
 
     int flags[2] = {0, 0};
     std::vector<uint64_t> nal(n), its(n);

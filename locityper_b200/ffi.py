@@ -79,6 +79,12 @@ class StatsC(C.Structure):
                 ("rescore_ops", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
+class DistTimingC(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double), ("collective_ms", C.c_double), ("host_ms", C.c_double),
+                ("wall_ms", C.c_double), ("collectives", C.c_uint64), ("gathered_bytes", C.c_uint64),
+                ("overflow_rounds", C.c_uint64), ("solves", C.c_uint64)]
+
+
 class MatesC(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_haps", C.c_uint32), ("max_alns", C.c_uint32), ("ins_len", C.c_uint32),
                 ("ma_off", C.c_void_p), ("ma_contig", C.c_void_p), ("ma_flags", C.c_void_p), ("ma_start", C.c_void_p),
@@ -132,6 +138,15 @@ SYMBOLS = {
     "lctp_produce_result": (C.c_int, [_P, _P, C.c_size_t, _P, _P, _P, _P]),
     "lctp_solve": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, _P]),
     "lctp_result_json": (C.c_size_t, [_P, _P, _P, _P, C.c_size_t]),
+    "lctp_dist_unique_id": (C.c_int, [_P]),
+    "lctp_dist_init": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    "lctp_dist_destroy": (None, [_P]),
+    "lctp_dist_rank": (C.c_int, [_P]),
+    "lctp_dist_world": (C.c_int, [_P]),
+    "lctp_dist_get_timing": (C.c_int, [_P, _P, C.c_int]),
+    "lctp_dist_prefilter": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, C.c_size_t, _P]),
+    "lctp_dist_solve_stage": (C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, _P, _P, _P]),
+    "lctp_dist_solve": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_size_t, _P, _P]),
 }
 
 _lib = None

@@ -551,6 +551,9 @@ class DeviceLocus:
             assert len(cd) == self.loc.n_haps * (self.loc.n_haps - 1) // 2
             ffi.check(self.lib.lctp_find_weighted_dist(C.byref(res), C.byref(self.c), cd.ctypes.data,
                                                        int(true_edit_distances)))
+        return self._genotyping(res, hap_names)
+
+    def _genotyping(self, res, hap_names=None) -> "Genotyping":
         n = int(res.n_out)
         names = list(hap_names) if hap_names is not None else [f"hap{i}" for i in range(self.loc.n_haps)]
         cn = (C.c_char_p * len(names))(*[s.encode() for s in names])
@@ -572,6 +575,72 @@ class DeviceLocus:
             weight_dist=(res.weight_dist if res.has_dist and res.has_weight_dist else None),
             distances=([None if d == 0xFFFFFFFF else int(d) for d in res.dist_to_primary[:n]]
                        if res.has_dist else None))
+
+
+def _nccl_before_lctp() -> None:
+    """The library dlopen()s "libnccl.so.2" on first use.  In a Python process that will also import torch, torch's own
+    NCCL must be the copy that gets loaded under that name (a later `import torch` would otherwise be handed the
+    system copy and fail on missing symbols): import torch first when it is installed."""
+    try:
+        import torch  # noqa: F401
+    except ImportError:
+        pass
+
+
+def dist_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it, the 128 bytes travel to the other ranks out of band)."""
+    _nccl_before_lctp()
+    buf = (C.c_uint8 * 128)()
+    ffi.check(ffi.load().lctp_dist_unique_id(buf))
+    return bytes(buf)
+
+
+class Dist:
+    """lctp_dist: this rank's membership in the NCCL communicator that shards one locus over the GPUs of a box
+    (SURVEY.md section 8e).  Every method is collective: all ranks call it with the same arguments."""
+
+    def __init__(self, ctx: "Context", unique_id: bytes, rank: int, world: int):
+        _nccl_before_lctp()
+        self.lib = ffi.load()
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self._h = C.c_void_p()
+        idb = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        ffi.check(self.lib.lctp_dist_init(ctx._h, idb, rank, world, C.byref(self._h)))
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.lctp_dist_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def timing(self, reset: bool = False) -> dict:
+        t = ffi.DistTimingC()
+        ffi.check(self.lib.lctp_dist_get_timing(self._h, C.byref(t), int(reset)))
+        return {k: getattr(t, k) for k, _ in ffi.DistTimingC._fields_}
+
+    def prefilter(self, dl: "DeviceLocus", min_size: int, threads: int) -> np.ndarray:
+        cap = dl.loc.n_genotypes
+        ixs = np.zeros(cap, dtype=np.uint64)
+        n = C.c_size_t(0)
+        ffi.check(self.lib.lctp_dist_prefilter(self._h, dl._h, min_size, threads, ixs.ctypes.data, cap, C.byref(n)))
+        return ixs[:n.value].copy()
+
+    def solve_stage(self, dl: "DeviceLocus", stage: Stage, worker_ixs, worker_off, worker_rng: np.ndarray):
+        worker_ixs = np.ascontiguousarray(worker_ixs, dtype=np.uint64)
+        worker_off = np.ascontiguousarray(worker_off, dtype=np.uint64)
+        n = int(worker_off[-1])
+        lm, lv = np.empty(n), np.empty(n)
+        st = stage.to_c()
+        ffi.check(self.lib.lctp_dist_solve_stage(self._h, dl._h, C.byref(st), worker_ixs.ctypes.data,
+                                                 worker_off.ctypes.data, len(worker_off) - 1, worker_rng.ctypes.data,
+                                                 lm.ctypes.data, lv.ctypes.data))
+        return lm, lv
+
+    def solve(self, dl: "DeviceLocus", scheme: Scheme, threads: int, rng: np.ndarray,
+              hap_names: Optional[Sequence[str]] = None) -> "Genotyping":
+        st = scheme.to_c()
+        res = ffi.ResultC()
+        ffi.check(self.lib.lctp_dist_solve(self._h, dl._h, st, len(scheme.stages), threads, rng.ctypes.data, C.byref(res)))
+        return dl._genotyping(res, hap_names)
 
 
 def truncate_ixs(ixs, scores, filt_diff: float, min_size: int, threads: int) -> np.ndarray:

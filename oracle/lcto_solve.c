@@ -104,7 +104,7 @@ size_t lcto_truncate_ixs(uint64_t *ixs, size_t n, const double *scores, double f
 
 /* sol.csv / sol_ext.csv in the reference's own row formats (src/solvers/solve.rs:115-117,1074-1075,938,895-896;
  * src/model/assgn.rs:413-425), written by lcto_solve / lcto_solve_stage while a sink is open.  This is what
- * tools/rust_diff.sh diffs against the files of a real `locityper genotype --debug 2` run.  Row order inside a stage
+ * oracle/rust_diff.sh diffs against the files of a real `locityper genotype --debug 2` run.  Row order inside a stage
  * depends on thread timing in the reference, so the comparison sorts the rows. */
 #include <stdio.h>
 static FILE *g_sol = NULL, *g_sol_ext = NULL;

@@ -2,7 +2,7 @@
 # SURVEY.md Appendix D, executable: pin the oracle (and through it the CUDA path) against the REAL reference the day a
 # Rust toolchain is available.  Nothing here runs in the build image of this repository (no cargo / rustc / network).
 #
-#   tools/rust_diff.sh REF_SRC DB_DIR PREPROC_DIR READS_ARGS... -- [-s SEED] [-@ T]
+#   oracle/rust_diff.sh REF_SRC DB_DIR PREPROC_DIR READS_ARGS... -- [-s SEED] [-@ T]
 #     REF_SRC      checkout of tprodanov/locityper v1.7.2 with WFA2/ cloned (build.rs:5,28-40)
 #     DB_DIR       locus database (`locityper target` output), PREPROC_DIR = `locityper preproc` output
 #     READS_ARGS   the input arguments of `locityper genotype` (-i reads1.fq reads2.fq ...)
@@ -13,7 +13,7 @@
 #      deleting the #![cfg] line: the dump only needs FlatLocus).
 #   2. run `locityper genotype --debug 2 -s SEED -@ T` with LCTP_DUMP_LCTI=$OUT/lcti: every locus leaves its
 #      solve::Data as a .lcti directory (tools/lcti.py) next to the reference's own sol.csv.br / sol_ext.csv.br.
-#   3. for every locus: `python tools/lcti.py solve` re-runs the oracle from the dumped RNG state with the same T and
+#   3. for every locus: `python oracle/lcti_solve.py` re-runs the oracle from the dumped RNG state with the same T and
 #      scheme and writes sol.csv / sol_ext.csv in the reference's row formats.
 #   4. diff (rows sorted: their order inside a stage depends on thread timing in the reference).
 # A clean diff pins, in one go: rand 0.10 bounded sampling / shuffle / Floyd order, xoshiro seeding and jumps, the
@@ -39,7 +39,7 @@ LCTP_DUMP_LCTI="$OUT/lcti" "$REF_SRC/target/release/locityper" genotype "${READS
 status=0
 for d in "$OUT"/lcti/*/; do
     locus=$(basename "$d")
-    python "$HERE/tools/lcti.py" solve "$d" --threads "$T" --out "$OUT/oracle/$locus"
+    python "$HERE/oracle/lcti_solve.py" "$d" --threads "$T" --out "$OUT/oracle/$locus"
     for f in sol sol_ext; do
         brotli -dc "$OUT/ref/loci/$locus/$f.csv.br" | sort > "$OUT/oracle/$locus/$f.ref.sorted"
         sort "$OUT/oracle/$locus/$f.csv" > "$OUT/oracle/$locus/$f.oracle.sorted"

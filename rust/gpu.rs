@@ -2,7 +2,7 @@
 //!
 //! NOT COMPILED IN THE BUILD IMAGE OF THIS REPOSITORY (no cargo / rustc there): written against the reference sources,
 //! every field access cites the reference file:line it reads.  The same ABI is exercised end to end by the
-//! Python/ctypes mirror (locityper_b200/ffi.py, genotype.py) in the test suite, and `tools/rust_diff.sh` is the
+//! Python/ctypes mirror (locityper_b200/ffi.py, genotype.py) in the test suite, and `oracle/rust_diff.sh` is the
 //! procedure that compiles this file into the reference and diffs its debug CSVs against the oracle's.
 //!
 //! Place next to `src/solvers/solve.rs`, add `#[cfg(feature = "cuda")] pub mod gpu;` to `src/solvers/mod.rs`, apply

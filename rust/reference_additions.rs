@@ -47,7 +47,7 @@ pub fn state_of(rng: &XoshiroRng) -> [u64; 4] {
 }
 
 // (6) src/command/genotype.rs, analyze_locus, right before `solve::solve(&data, ...)` (:1251): the dump that
-// tools/rust_diff.sh diffs against.  Environment-driven so that no CLI flag changes.
+// oracle/rust_diff.sh diffs against.  Environment-driven so that no CLI flag changes.
 if let Ok(dir) = std::env::var("LCTP_DUMP_LCTI") {
     let flat = crate::solvers::gpu::FlatLocus::from_data(&data)?;
     flat.dump(&std::path::Path::new(&dir).join(locus.set.tag()))?;

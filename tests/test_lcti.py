@@ -1,5 +1,5 @@
 """tools/lcti.py: the `.lcti` dump format that rust/gpu.rs `FlatLocus::dump` writes from inside the reference
-(SURVEY.md Appendix D / tools/rust_diff.sh).  Round trip and the oracle's debug dumps in the reference's row formats."""
+(SURVEY.md Appendix D / oracle/rust_diff.sh).  Round trip and the oracle's debug dumps in the reference's row formats."""
 import os
 import subprocess
 import sys
@@ -25,7 +25,7 @@ def test_lcti_round_trip_and_debug_dumps(oracle, small_locus, tmp_path):
               "min_weight", "filt_diff", "prob_thresh"):
         assert getattr(loc, k) == getattr(small_locus, k), k          # floats travel as bit patterns: exact
     out = str(tmp_path / "out")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "lcti.py"), "solve", d, "--threads", "4", "--out", out,
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "lcti_solve.py"), d, "--threads", "4", "--out", out,
                         "--scheme", "greedy:i=50,a=2", "anneal:i=5,a=3,n=500,p=200", "--os-threads", "2"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr

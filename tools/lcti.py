@@ -4,8 +4,8 @@ writes from Python.  Used by tools/rust_diff.sh to run th
 `solve::Data` a real `locityper genotype` run saw.
 
     python tools/lcti.py write DIR --config C1 --seed 1001     # synthetic locus -> dump (round-trip / demo)
-    python tools/lcti.py solve DIR --threads 8 --out OUT        # oracle: OUT/sol.csv, OUT/sol_ext.csv, OUT/res.json
-    python tools/lcti.py solve DIR --threads 8 --out OUT --gpu  # same through liblctp (needs a B200); compares calls
+    python tools/lcti.py solve DIR --threads 8 --out OUT        # through liblctp (needs a B200): OUT/res.json
+The oracle-side counterpart (sol.csv / sol_ext.csv in the reference's formats) is oracle/lcti_solve.py.
 """
 import argparse
 import ctypes as C
@@ -75,16 +75,6 @@ def read(path: str):
     return loc, meta["hap_names"], rng
 
 
-def _scheme(oracle, specs):
-    from locityper_b200 import genotype
-    out = []
-    for st in genotype.Scheme.parse(specs).stages:
-        out.append(oracle.Stage(st.kind, attempts=st.attempts, in_size=st.in_size, best_start=st.best_start,
-                                sample_size=st.sample_size, plato_size=st.plato_size, anneal_steps=st.anneal_steps,
-                                init_prob=st.init_prob))
-    return out
-
-
 def main():
     ap = argparse.ArgumentParser()
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -94,42 +84,22 @@ def main():
     s.add_argument("dir"); s.add_argument("--threads", type=int, default=8); s.add_argument("--out", required=True)
     s.add_argument("--seed", type=int, default=None, help="-s SEED of the run when the dump carries no rng_state.u64")
     s.add_argument("--scheme", nargs="*", default=["greedy:i=5k,a=1", "anneal:i=20,a=20"])
-    s.add_argument("--os-threads", type=int, default=os.cpu_count() or 4)
-    s.add_argument("--gpu", action="store_true")
     a = ap.parse_args()
-    from oracle import lcto_py as oracle
+    from locityper_b200 import genotype
     if a.cmd == "write":
-        loc = synth.make_locus(**synth.config_shape(a.config), seed=a.seed, table_builder=oracle.build_depth_table)
-        st = oracle.Rng.from_seed(a.seed).state()
-        write(loc, a.dir, rng_state=st)
+        loc = synth.make_locus(**synth.config_shape(a.config), seed=a.seed, table_builder=genotype.build_depth_table)
+        write(loc, a.dir, rng_state=genotype.init_rng(a.seed))
         print(f"wrote {a.dir}: H={loc.n_haps} R={loc.n_reads} G={loc.n_genotypes}")
         return
     loc, names, st = read(a.dir)
     os.makedirs(a.out, exist_ok=True)
-    rng = oracle.Rng.from_state(st) if st is not None else oracle.Rng.from_seed(a.seed)
-    start_state = rng.state()
-    cn = (C.c_char_p * len(names))(*[n.encode() for n in names])
-    lib = oracle.lib()
-    lib.lcto_debug_open.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p]
-    rc = lib.lcto_debug_open(os.path.join(a.out, "sol.csv").encode(), os.path.join(a.out, "sol_ext.csv").encode(), cn)
-    assert rc == 0
-    ol = oracle.OracleLocus(loc)
-    res = oracle.solve(ol, _scheme(oracle, a.scheme), a.threads, rng, os_threads=a.os_threads)
-    lib.lcto_debug_close()
+    rng = np.array(st, dtype=np.uint64) if st is not None else genotype.init_rng(a.seed)
+    ctx = genotype.Context(0)
+    dl = ctx.upload(loc)
+    got = dl.solve(genotype.Scheme.parse(a.scheme), a.threads, rng, hap_names=names)
     with open(os.path.join(a.out, "res.json"), "w") as f:
-        f.write(oracle.to_json_text(res, loc, names))
-    print("oracle call:", ",".join(names[h] for h in loc.genotype_tuple(int(res["gt_ix"][0]))), "quality", res["quality"])
-    if a.gpu:
-        from locityper_b200 import genotype
-        ctx = genotype.Context(0)
-        dl = ctx.upload(loc)
-        got = dl.solve(genotype.Scheme.parse(a.scheme), a.threads, np.array(start_state, dtype=np.uint64), hap_names=names)
-        with open(os.path.join(a.out, "res_gpu.json"), "w") as f:
-            f.write(got.json_text)
-        same = list(got.gt_ix) == list(res["gt_ix"])
-        print("gpu call identical ranking:", same)
-        if not same:
-            sys.exit(1)
+        f.write(got.json_text)
+    print("call:", got.to_json()["genotype"], "quality", got.quality)
 
 
 if __name__ == "__main__":
