@@ -633,6 +633,17 @@ def run_shard(args, ctx, scheme, T, rank, world, dev):
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr
+    global print
+    real_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*a, **k):                      # noqa: A001  (json line -> the real stdout)
+        k.pop("flush", None)
+        _print(*a, file=real_out, **k)
+        real_out.flush()
+    globals()["print"] = print
     if args.impl == "reference":
         run_reference(args)
     else:

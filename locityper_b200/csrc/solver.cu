@@ -56,7 +56,7 @@ struct StageParams {
     uint64_t plato_size, anneal_steps, max_iter;
     double ln_init_prob;
     uint32_t n_workers, cap, Wmax, want_counts, narrow_w, nt_global;
-    uint64_t slab_bytes;
+    uint64_t slab_bytes, big_bytes;
 };
 
 // Candidate record as stored in the slab: source byte and the two windows in ONE word, so that a candidate is one
@@ -82,23 +82,25 @@ template <bool WIDE>
 struct Slab {
     typedef typename RecWord<WIDE>::T Rec;
     Rec *rec;              // [cap]  record of every candidate, reads in read order (the reference's `alns`, a5)
-    uint16_t *nt_read;     // [R]    list of the non-trivial reads when it does not fit shared memory (StageParams::nt_global)
+    uint16_t *off;         // [R+1]  slab mode (StageParams::nt_global): first candidate of every read
+    uint2 *ntinfo;         // [R]    slab mode: per non-trivial read (first candidate | candidates << 16, read id)
     uint64_t *rng_buf;     // [RNG_FILL] pre-generated draws of the worker's stream
     uint64_t *rng_blk;     // [32*4] block-start generator states of the current fill
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline size_t slab_bytes_for(uint32_t cap, bool wide, uint32_t nt_global_reads) {
+__host__ __device__ inline size_t slab_bytes_for(uint32_t cap, bool wide, uint32_t slab_reads) {
     return (size_t)RNG_FILL * 8 + 32 * 4 * 8 + align_up((size_t)cap * (wide ? 8 : 4), 128) +
-           align_up((size_t)nt_global_reads * 2, 128);
+           (slab_reads ? align_up(((size_t)slab_reads + 1) * 2, 128) + align_up((size_t)slab_reads * 8, 128) : 0);
 }
 template <bool WIDE>
 __device__ __forceinline__ void slab_layout(uint32_t cap, unsigned char *base, Slab<WIDE> &s) {
     s.rng_buf = (uint64_t *)base;
     s.rng_blk = (uint64_t *)(base + (size_t)RNG_FILL * 8);
     s.rec = (typename Slab<WIDE>::Rec *)(base + (size_t)RNG_FILL * 8 + 32 * 4 * 8);
-    s.nt_read = (uint16_t *)(base + (size_t)RNG_FILL * 8 + 32 * 4 * 8 + align_up((size_t)cap * (WIDE ? 8 : 4), 128));
+    s.off = (uint16_t *)(base + (size_t)RNG_FILL * 8 + 32 * 4 * 8 + align_up((size_t)cap * (WIDE ? 8 : 4), 128));
+    s.ntinfo = nullptr;    // set by the kernel in slab mode (it follows `off`, whose length depends on R)
 }
 
 // ------------------------------------------------------------------ warp helpers ----------------
@@ -377,9 +379,14 @@ __host__ __device__ inline uint32_t win_stride(uint32_t Wmax) { return (Wmax + 1
 
 struct WarpShared {
     WinState win;
-    uint16_t *off;         // [R+1]  first candidate of every read (+ end sentinel)
-    uint16_t *nt_read;     // [R]    read ids of the non-trivial reads (more than one candidate), ascending; GENERIC
-                           //        pointer: shared memory, or the worker's slab when R is large (nt_global)
+    // Two placements of the per-read index, chosen by the host (StageParams::nt_global = "slab mode"):
+    //   shared memory (R small enough for 16 workers per SM): off[R+1] + nt_read[n_nt];
+    //   the worker's slab (large R: what remains in shared memory is the window state and `assgn`, so twice as
+    //   many workers fit): off[R+1] + ntinfo[n_nt] = everything the greedy loop needs about a sampled read in ONE
+    //   8-byte load, which the loop issues a round ahead.
+    uint16_t *off;         // [R+1]  first candidate of every read (+ end sentinel); generic pointer
+    uint16_t *nt_read;     // [R]    shared-memory mode: read ids of the non-trivial reads, ascending
+    uint2 *ntinfo;         // [R]    slab mode: (first candidate | candidates << 16, read id) per non-trivial read
     uint8_t *assgn;        // [R]    current assignment (candidate rank) of every read
     uint32_t *unm_bits;    // [ceil(R/32)] bit r%32 of word r/32: read r has the "unmapped" option among its candidates
     uint32_t *haps;        // [LCTP_MAX_PLOIDY] haplotypes of the genotype, then [LCTP_MAX_PLOIDY+1] window shifts
@@ -391,8 +398,8 @@ struct WarpShared {
     uint32_t lane;
 };
 __host__ __device__ inline size_t group_smem_bytes(uint32_t Wmax, uint32_t R, bool nt_global) {
-    return align_up((size_t)win_stride(Wmax) * 56, 16) + align_up(((size_t)R + 1) * 2, 16) +
-           (nt_global ? 0 : align_up((size_t)R * 2, 16)) +
+    return align_up((size_t)win_stride(Wmax) * 56, 16) +
+           (nt_global ? 0 : align_up(((size_t)R + 1) * 2, 16) + align_up((size_t)R * 2, 16)) +
            align_up((size_t)R, 16) + align_up((size_t)((R + 31) / 32) * 4, 16) +
            align_up((size_t)(2 * LCTP_MAX_PLOIDY + 1) * 4, 16) + 64 /* samp */ + 32 /* lik */ + 1024 /* draw ring */;
 }
@@ -437,6 +444,14 @@ __device__ __forceinline__ uint32_t inst_hap(const Instance &I, const WarpShared
     return k == 0 ? I.h0 : k == 1 ? I.h1 : ws.haps[k];
 }
 __device__ __forceinline__ uint32_t inst_wshift(const WarpShared &ws, uint32_t k) { return ws.haps[LCTP_MAX_PLOIDY + k]; }
+
+// (first candidate | candidate count << 16, read id) of the idx-th non-trivial read
+__device__ __forceinline__ uint2 nt_info(const WarpShared &ws, uint32_t idx) {
+    if (ws.ntinfo) return ws.ntinfo[idx];
+    const uint32_t r = ws.nt_read[idx];
+    const uint32_t o = ws.off[r];
+    return make_uint2(o | (((uint32_t)ws.off[r + 1] - o) << 16), r);
+}
 
 // Index into cm_lnprob of the ln-probability of the candidate with source byte s of read r (the reference's
 // ReadGtAlns::ln_prob).  b0 / b1: cm_off of the read on the first two haplotypes (the p <= 2 fast path has them).
@@ -529,7 +544,11 @@ __device__ bool build_instance(const LocusDev &L, const Slab<WIDE> &S, const War
         if (ok && valid) {
             ws.off[r] = (uint16_t)start;
             ws.assgn[r] = 0;
-            if (nt) ws.nt_read[nt_base + __popc(ntmask & ((1u << ws.lane) - 1u))] = (uint16_t)r;
+            if (nt) {
+                const uint32_t pos = nt_base + __popc(ntmask & ((1u << ws.lane) - 1u));
+                if (ws.ntinfo) ws.ntinfo[pos] = make_uint2(start | (nw << 16), r);
+                else ws.nt_read[pos] = (uint16_t)r;
+            }
             bool unm_left = with_unm;
             const long long unm_key = total_key(unm);
             for (uint32_t t = 0; t < nw; t++) {
@@ -724,7 +743,7 @@ __device__ void init_assignment(const LocusDev &L, const Slab<WIDE> &S, const In
         for (uint32_t i0 = 0; i0 < I.n_nt; i0 += 32) {
             const uint32_t i = i0 + lane;
             uint32_t r = 0, my_n = 1;
-            if (i < I.n_nt) { r = ws.nt_read[i]; my_n = (uint32_t)ws.off[r + 1] - ws.off[r]; }
+            if (i < I.n_nt) { const uint2 inf = nt_info(ws, i); r = inf.y; my_n = inf.x >> 16; }
             uint32_t a = 0;
             const uint32_t cnt = min(32u, I.n_nt - i0);
             if (!xo_below_lanes(rng, cnt, my_n, a)) {
@@ -826,9 +845,10 @@ struct Target { uint32_t r, o, a, new_a; };
 __device__ __forceinline__ Target random_target(const WarpShared &ws, const Instance &I, Xo &rng) {
     Target t;
     const uint32_t idx = xo_below(rng, I.n_nt);              // random_range(0..n_nontrivial), usize via the u32 path
-    t.r = ws.nt_read[idx];
-    t.o = ws.off[t.r];
-    const uint32_t n = (uint32_t)ws.off[t.r + 1] - t.o;
+    const uint2 inf = nt_info(ws, idx);
+    t.r = inf.y;
+    t.o = inf.x & 0xFFFFu;
+    const uint32_t n = inf.x >> 16;
     t.a = ws.assgn[t.r];
     if (n == 2) t.new_a = 1u - t.a;
     else {
@@ -868,9 +888,10 @@ __device__ __forceinline__ void spec_targets(const WarpShared &ws, const Instanc
     const uint64_t m = (d >> 32) * (uint64_t)I.n_nt;
     const bool bias1 = (uint32_t)m > 0u - I.n_nt;
     const uint32_t idx = (uint32_t)(m >> 32);
-    sp.r = ws.nt_read[idx];
-    sp.o = ws.off[sp.r];
-    const uint32_t n = (uint32_t)ws.off[sp.r + 1] - sp.o;
+    const uint2 inf = nt_info(ws, idx);
+    sp.r = inf.y;
+    sp.o = inf.x & 0xFFFFu;
+    const uint32_t n = inf.x >> 16;
     sp.a = ws.assgn[sp.r];
     const bool two = n > 2;
     const uint64_t m2 = (d1 >> 32) * (uint64_t)(n - 1u);
@@ -1029,12 +1050,11 @@ struct SlotB {
 // Deal the jobs of the sample `myv` (lane k < amount holds the k-th sampled read) and issue the first-hop loads.
 template <bool WIDE>
 __device__ __forceinline__ void load_slot_a(const LocusDev &L, const Slab<WIDE> &S, const Instance &I,
-                                            const WarpShared &ws, uint32_t amount, uint32_t myv, uint32_t lr,
+                                            const WarpShared &ws, uint32_t amount, uint32_t myv, uint2 linfo,
                                             SlotA<WIDE> &x) {
     const uint32_t lane = ws.lane;
     const bool lead = lane < amount;
-    uint32_t n_alt = 0;
-    if (lead) n_alt = (uint32_t)ws.off[lr + 1] - ws.off[lr] - 1u;
+    const uint32_t n_alt = lead ? (linfo.x >> 16) - 1u : 0u;
     uint32_t incl = n_alt;
 #pragma unroll
     for (int d = 1; d < 16; d <<= 1) {              // amount <= 11: four rounds
@@ -1046,10 +1066,10 @@ __device__ __forceinline__ void load_slot_a(const LocusDev &L, const Slab<WIDE> 
     x.lead = myv | (first << 16);
     const unsigned starts = __reduce_or_sync(FULL, (lead && first < 32u) ? (1u << first) : 0u);
     const uint32_t slot = (uint32_t)__popc(starts & (0xFFFFFFFFu >> (31u - lane))) - 1u;   // starts has bit 0 set
-    const uint32_t r = wshfl(lr, (int)slot);
+    const uint32_t r = wshfl(linfo.y, (int)slot);
+    const uint32_t on = wshfl(linfo.x, (int)slot);
     const uint32_t alt = lane - wshfl(first, (int)slot);
-    const uint32_t o = ws.off[r];
-    const uint32_t n = (uint32_t)ws.off[r + 1] - o;
+    const uint32_t o = on & 0xFFFFu, n = on >> 16;
     const uint32_t a = ws.assgn[r];
     const uint32_t c = min(alt_rank(alt, a), n - 1u);     // lanes >= total: clamped, loaded, never evaluated
     x.job = r | (slot << 16) | (c << 24);
@@ -1121,7 +1141,8 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
     uint32_t curr_plato = 0, it = 0;
     const uint32_t plato_size = (uint32_t)P.plato_size, max_iter = (uint32_t)P.max_iter;
     bool vS = false, vA = false, vB = false, vC = false;
-    uint32_t s_myv = 0, s_r = ws.nt_read[0];       // sampled index / its read id (lanes < amount)
+    uint32_t s_myv = 0;                 // sampled index (lanes < amount) ...
+    uint2 s_info = nt_info(ws, 0);      // ... and what the index says about that read
     __syncwarp();
     SlotA<WIDE> sa;
     SlotB<WIDE> sb, cur;
@@ -1147,8 +1168,8 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
                     const uint32_t idx = wshfl(cur.lead & 0xFFFFu, (int)slot);
                     const uint32_t sfirst = wshfl(first, (int)slot);
                     if (f0 + lane < cur.total) {
-                        const uint32_t r = ws.nt_read[idx];
-                        const uint32_t o = ws.off[r], a = ws.assgn[r];
+                        const uint2 inf = nt_info(ws, idx);
+                        const uint32_t r = inf.y, o = inf.x & 0xFFFFu, a = ws.assgn[r];
                         const uint32_t c = alt_rank(f0 + lane - sfirst, a);
                         const typename RW::T ro = S.rec[o + a], rn = S.rec[o + c];
                         const double lpo = __ldg(L.cm_lnprob + lp_index(L, I, ws, r, RW::src(ro)));
@@ -1221,7 +1242,7 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
         cur = sb; vC = vB;
         load_slot_b<WIDE>(L, I, ws, sa, sb);
         vB = vA;
-        load_slot_a<WIDE>(L, S, I, ws, amount, s_myv, s_r, sa);
+        load_slot_a<WIDE>(L, S, I, ws, amount, s_myv, s_info, sa);
         vA = vS;
         // ---- stage S: draw the next sample.  The refilling path may only run on an empty pipeline: the samples in
         // flight are given back to the stream when the loop ends, which cannot cross a refill.
@@ -1229,17 +1250,137 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
         vS = sample_draw(rng, n_nt, amount, false, s_myv);
         if (!vS && !vA && !vB && !vC) vS = sample_draw(rng, n_nt, amount, true, s_myv);
         sample_resolve(ws, n_nt, amount, s_myv);            // a stale sample is already free of duplicates
-        // The list may live in the slab: its entries are fetched a round ahead.  Through asm, as a 32-bit value: the
-        // compiler's own 16-bit load is followed by a zero-extension that it scheduled at the top of the next round,
-        // i.e. right behind the load (ncu: 7 % of the kernel).
+        // The index of the sampled reads may live in the slab: it is fetched a round ahead.  Through asm: whatever
+        // the compiler derives from its own load (a zero-extension, a field extraction) it schedules at the top of
+        // the next round, i.e. right behind the load (ncu: 7 % of the kernel waiting there).
         {
-            const uint16_t *ptr = ws.nt_read + (lane < amount ? s_myv : 0u);
-            asm volatile("ld.u16 %0, [%1];" : "=r"(s_r) : "l"(ptr));
+            const uint32_t q = lane < amount ? s_myv : 0u;
+            if (ws.ntinfo) asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(s_info.x), "=r"(s_info.y) : "l"(ws.ntinfo + q));
+            else s_info = nt_info(ws, q);
         }
     }
     // the pre-drawn samples of iterations that never ran
     stream_unconsume(rng, amount * ((vS ? 1u : 0u) + (vA ? 1u : 0u) + (vB ? 1u : 0u)));
     if (lane == 0) ((uint64_t *)ws.lik)[2] += it;
+}
+
+// ------------------------------------------------------------------ a10: Greedy, samples of more than 11 reads ---
+//
+// `-S greedy:s=N` with N > 11 (Greedy::set_sample_size accepts any N >= 1, src/solvers/stoch.rs:65-72).  rand 0.10's
+// seq::index::sample then chooses between Floyd's algorithm and a partial Fisher-Yates shuffle of 0..length
+// ("sample_inplace") by the published rule  amount > 11 && length < (C1 + 1.6 * amount) * amount  (f32 arithmetic;
+// C1 = 10 for length < 500,000), and for amount >= 163 between sample_inplace (length < 270 * amount) and
+// sample_rejection.  The rejection branch (a HashSet loop over a differently biased sampler) is not restated: a
+// genotype that would take it sets bit 2 of the stage's error word and lctp_solve_stage reports LCTP_E_CAPACITY.
+// This path is correct, not fast: draws are taken one at a time, each sampled read is one lane's job.
+struct BigCand {
+    double s, improv, dld, dlp;
+    uint32_t slot, r, c;
+};
+__device__ __forceinline__ bool bigcand_better(const BigCand &a, const BigCand &b) {
+    if (a.s != b.s) return a.s > b.s;
+    if (a.slot != b.slot) return a.slot < b.slot;
+    if (a.improv != b.improv) return a.improv > b.improv;
+    return a.c < b.c;
+}
+// 0 = Floyd, 1 = in place, 2 = rejection (unsupported); restates the choice of rand::seq::index::sample
+__device__ __forceinline__ int big_sample_algo(uint32_t length, uint32_t amount) {
+    if (amount < 163u) {
+        const float m4 = 1.6f * (float)amount;
+        const float c1 = length >= 500000u ? 70.0f / 9.0f : 10.0f;
+        const float c0 = length >= 500000u ? 8.0f / 45.0f * (float)amount : m4;
+        return (amount > 11u && (float)length < (c1 + c0) * (float)amount) ? 1 : 0;
+    }
+    const float c = length < 500000u ? 270.0f : 330.0f / 9.0f;
+    return (float)length < c * (float)amount ? 1 : 2;
+}
+
+template <bool WIDE>
+__device__ bool greedy_solve_big(const LocusDev &L, const StageParams &P, const Slab<WIDE> &S, const Instance &I,
+                                 const WarpShared &ws, Xo &rng, uint32_t *__restrict__ big) {
+    typedef RecWord<WIDE> RW;
+    const uint32_t lane = ws.lane;
+    const uint32_t n_nt = I.n_nt, amount = min(P.sample_size, n_nt);
+    init_assignment<WIDE>(L, S, I, ws, rng, P.best_start ? 0 : 1);
+    const double min_diff = fmax(__dmul_rn(1e-10, max_abs_random<WIDE>(L, S, I, ws, rng)), 1e-14);
+    const int algo = big_sample_algo(n_nt, amount);
+    if (algo == 2) return false;
+    uint32_t *sample = big;                  // [amount]
+    uint32_t *swp = big + amount;            // [amount]  in-place: the partner of every swap (to undo it)
+    uint32_t *perm = big + 2 * amount;       // [n_nt]    in-place: the index vector 0..length, restored after each sample
+    if (algo == 1) { for (uint32_t i = lane; i < n_nt; i += 32) perm[i] = i; }
+    __syncwarp();
+    uint32_t curr_plato = 0, it = 0;
+    const uint32_t plato_size = (uint32_t)P.plato_size, max_iter = (uint32_t)P.max_iter;
+    for (; it < max_iter; it++) {
+        // ---- the sample (all lanes run the same scalar code; lane 0 writes)
+        if (algo == 1) {                     // sample_inplace: for i in 0..amount { j = random_range(i..length); swap(i, j) }
+            for (uint32_t i = 0; i < amount; i++) {
+                const uint32_t j = i + xo_below(rng, n_nt - i);
+                if (lane == 0) { const uint32_t a = perm[i], b = perm[j]; perm[i] = b; perm[j] = a; swp[i] = j; sample[i] = b; }
+                __syncwarp();
+            }
+        } else {                             // sample_floyd
+            for (uint32_t k = 0; k < amount; k++) {
+                const uint32_t j = n_nt - amount + k;
+                const uint32_t t = xo_below(rng, j + 1u);
+                bool hit = false;
+                uint32_t pos = 0;
+                for (uint32_t e = lane; e < k; e += 32) if (sample[e] == t) { hit = true; pos = e; }
+                const unsigned m = wballot(hit);
+                if (m) { const uint32_t p0 = wshfl(pos, __ffs(m) - 1); if (lane == 0) sample[p0] = j; }
+                if (lane == 0) sample[k] = t;
+                __syncwarp();
+            }
+        }
+        // ---- best_read_improvement of every sampled read (src/model/assgn.rs:287-317), one read per lane
+        BigCand best;
+        best.s = -INFINITY; best.improv = -INFINITY; best.dld = best.dlp = 0.0; best.slot = 0xFFFFFFFFu; best.r = best.c = 0;
+        for (uint32_t k = lane; k < amount; k += 32) {
+            const uint2 inf = nt_info(ws, sample[k]);
+            const uint32_t r = inf.y, o = inf.x & 0xFFFFu, n = inf.x >> 16, a = ws.assgn[r];
+            const typename RW::T ro = S.rec[o + a];
+            const double lpo = __ldg(L.cm_lnprob + lp_index(L, I, ws, r, RW::src(ro)));
+            for (uint32_t c = 0; c < n; c++) {
+                if (c == a) continue;
+                const typename RW::T rn = S.rec[o + c];
+                const double lpn = __ldg(L.cm_lnprob + lp_index(L, I, ws, r, RW::src(rn)));
+                BigCand cd;
+                cd.dld = depth_lik_diff_raw<WIDE>(ws, ro, rn);
+                cd.improv = __dadd_rn(lpn, __dmul_rn(L.rel_contrib, cd.dld));
+                cd.s = __dmul_rn(L.aln_contrib, __dsub_rn(cd.improv, lpo));
+                cd.dlp = __dsub_rn(lpn, lpo);
+                cd.slot = k; cd.r = r; cd.c = c;
+                if (bigcand_better(cd, best)) best = cd;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            BigCand o;
+            o.s = __shfl_xor_sync(FULL, best.s, d); o.improv = __shfl_xor_sync(FULL, best.improv, d);
+            o.dld = __shfl_xor_sync(FULL, best.dld, d); o.dlp = __shfl_xor_sync(FULL, best.dlp, d);
+            o.slot = __shfl_xor_sync(FULL, best.slot, d); o.r = __shfl_xor_sync(FULL, best.r, d);
+            o.c = __shfl_xor_sync(FULL, best.c, d);
+            if (bigcand_better(o, best)) best = o;
+        }
+        if (algo == 1) {                     // put the index vector back (reverse order of the swaps)
+            if (lane == 0)
+                for (uint32_t i = amount; i-- > 0;) { const uint32_t j = swp[i]; const uint32_t a = perm[i], b = perm[j]; perm[i] = b; perm[j] = a; }
+            __syncwarp();
+        }
+        if (best.s > min_diff) {
+            const uint32_t o = ws.off[best.r], a = ws.assgn[best.r];
+            Move<WIDE> mv;
+            mv.dld = best.dld; mv.dlp = best.dlp; mv.raw_old = S.rec[o + a]; mv.raw_new = S.rec[o + best.c];
+            apply_move<WIDE>(ws, L.depth_table, best.r, best.c, mv);
+            curr_plato = 0;
+        } else {
+            curr_plato += 1;
+            if (curr_plato > plato_size) { it++; break; }
+        }
+    }
+    if (lane == 0) ((uint64_t *)ws.lik)[2] += it;
+    return true;
 }
 
 // ------------------------------------------------------------------ a11: SimAnneal --------------
@@ -1373,7 +1514,7 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
 #ifndef LCTP_MIN_CTAS
 #define LCTP_MIN_CTAS 16
 #endif
-template <bool WIDE>
+template <bool WIDE, bool BIG>
 __global__ void __launch_bounds__(CTA_THREADS, LCTP_MIN_CTAS)
 k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs,
               const uint64_t *__restrict__ worker_off, const uint32_t *__restrict__ tuples,
@@ -1397,9 +1538,15 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
         ws.lik = (double *)base;               base += 32;
         ws.win.base = (double *)base;          ws.win.wp = win_stride(P.Wmax);
         base += align_up((size_t)ws.win.wp * 56, 16);
-        ws.off = (uint16_t *)base;             base += align_up(((size_t)L.R + 1) * 2, 16);
-        if (P.nt_global) ws.nt_read = S.nt_read;
-        else { ws.nt_read = (uint16_t *)base;  base += align_up((size_t)L.R * 2, 16); }
+        if (P.nt_global) {
+            ws.off = S.off;
+            ws.ntinfo = (uint2 *)((unsigned char *)S.off + align_up(((size_t)L.R + 1) * 2, 128));
+            ws.nt_read = nullptr;
+        } else {
+            ws.off = (uint16_t *)base;         base += align_up(((size_t)L.R + 1) * 2, 16);
+            ws.nt_read = (uint16_t *)base;     base += align_up((size_t)L.R * 2, 16);
+            ws.ntinfo = nullptr;
+        }
         ws.assgn = (uint8_t *)base;            base += align_up((size_t)L.R, 16);
         ws.unm_bits = (uint32_t *)base;        base += align_up((size_t)((L.R + 31) / 32) * 4, 16);
         ws.haps = (uint32_t *)base;
@@ -1450,8 +1597,13 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
             for (uint32_t a = 0; a < P.attempts; a++) {
                 apply_tweak<WIDE>(L, S, I, ws, rng);
                 if (I.n_nt == 0) init_assignment<WIDE>(L, S, I, ws, rng, 0);
-                else if (P.kind == 0) greedy_solve<WIDE>(L, P, S, I, ws, rng);
-                else anneal_solve<WIDE>(L, P, S, I, ws, rng);
+                else if (P.kind == 0) {
+                    if (BIG) {
+                        // scratch behind the worker's slab: sample, swap partners, index vector
+                        uint32_t *big = (uint32_t *)(scratch + (size_t)blockIdx.x * P.slab_bytes + P.slab_bytes - P.big_bytes);
+                        if (!greedy_solve_big<WIDE>(L, P, S, I, ws, rng, big) && lane == 0) atomicOr(err, 4);
+                    } else greedy_solve<WIDE>(L, P, S, I, ws, rng);
+                } else anneal_solve<WIDE>(L, P, S, I, ws, rng);
                 __syncwarp();
                 if (lane == 0) {
                     // likelihood (assgn.rs:235-237) + prior (solve.rs:1126)
@@ -1587,14 +1739,16 @@ static int launch_stage_kernel(lctp_locus_h *h, const StageParams &P, size_t n_w
                   "loci this large are not supported by the shared-memory resident solver", smem, L.R, P.Wmax);
         return LCTP_E_CAPACITY;
     }
-    auto kern = P.narrow_w ? k_solve_stage<false> : k_solve_stage<true>;
+    const bool bigs = P.kind == 0 && P.sample_size > (uint32_t)MAX_SAMPLE;
+    auto kern = P.narrow_w ? (bigs ? k_solve_stage<false, true> : k_solve_stage<false, false>)
+                           : (bigs ? k_solve_stage<true, true> : k_solve_stage<true, false>);
     // function attributes are per-device state shared by every context: configure + launch under one lock
     static std::mutex launch_mutex;
     std::lock_guard<std::mutex> lock(launch_mutex);
     // Only raise the limit when needed: re-setting a function attribute makes the next launch of the function wait
     // for its running instances, which serialised the stage kernels of loci in flight on different contexts.
     static std::unordered_map<int, size_t> smem_limit;     // by device ordinal and kernel instantiation
-    size_t &lim = smem_limit[ctx->device * 2 + (P.narrow_w ? 1 : 0)];
+    size_t &lim = smem_limit[ctx->device * 4 + (P.narrow_w ? 1 : 0) + (bigs ? 2 : 0)];
     if (smem > 48 * 1024 && smem > lim) {
         LCTP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lim = smem;
@@ -1657,12 +1811,9 @@ int launch_stage_ex(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worke
         set_error("lctp_solve_stage: invalid stage (kind=%u attempts=%u)", st->kind, st->attempts);
         return LCTP_E_INVALID;
     }
-    if (st->kind == 0 && (st->sample_size == 0 || st->sample_size > MAX_SAMPLE)) {
-        // rand::seq::index::sample switches from Floyd's to the in-place algorithm for amount > 11 on
-        // short lists; only the Floyd branch is implemented on the device.
-        set_error("lctp_solve_stage: greedy sample size %llu unsupported on device (1..=11)",
-                  (unsigned long long)st->sample_size);
-        return LCTP_E_CAPACITY;
+    if (st->kind == 0 && (st->sample_size == 0 || st->sample_size > 0x7FFFFFFFull)) {
+        set_error("lctp_solve_stage: invalid greedy sample size %llu", (unsigned long long)st->sample_size);
+        return LCTP_E_INVALID;
     }
     if (st->kind == 1 && (!(st->init_prob > 0.0 && st->init_prob <= 1.0) || st->anneal_steps == 0)) {
         set_error("lctp_solve_stage: invalid annealing parameters");
@@ -1710,16 +1861,21 @@ int launch_stage_ex(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worke
     P.want_counts = want_counts ? 1 : 0;
     P.narrow_w = P.Wmax <= 4096 ? 1 : 0;                       // 32-bit candidate records (12-bit windows)
     if (env_int("LCTP_WIDE_WINDOWS", 0)) P.narrow_w = 0;       // test knob: exercise the 64-bit candidate records
-    // The list of non-trivial reads (2 bytes per read) stays in shared memory while 16 workers per SM still fit
-    // (the register file allows no more); for larger R it moves to the worker's slab -- the greedy loop fetches
-    // its entries one round ahead either way.
+    // The per-read index (candidate offsets + the list of non-trivial reads, 4 bytes per read) stays in shared memory
+    // while 16 workers per SM still fit (the register file allows no more); for larger R it moves to the worker's
+    // slab ("slab mode": 10 bytes per read there) and shared memory keeps the window state and the assignments only --
+    // at the KIR-scale shape 8 workers per SM instead of 4.  The greedy loop fetches its entries a round ahead.
     {
         const size_t per_sm = ctx->smem_optin + 1024;            // opt-in limit per CTA = SM capacity - 1 KB
         const size_t with_nt = group_smem_bytes(P.Wmax, L.R, false) + 1024;
-        P.nt_global = (16 * with_nt > per_sm) ? 1 : 0;
+        P.nt_global = (12 * with_nt > per_sm) ? 1 : 0;       // (the C2 shape keeps its index in shared memory: 14 per SM)
         if (const char *e = getenv("LCTP_NT_GLOBAL")) P.nt_global = atoi(e) ? 1 : 0;      // test / tuning knob
     }
     P.slab_bytes = slab_bytes_for(cap, P.narrow_w == 0, P.nt_global ? L.R : 0);
+    // samples of more than 11 reads (greedy_solve_big): sample + swap partners + index vector behind the slab
+    P.big_bytes = (st->kind == 0 && st->sample_size > (uint64_t)MAX_SAMPLE)
+                      ? align_up(((size_t)2 * std::min<uint64_t>(st->sample_size, L.R) + L.R) * 4, 128) : 0;
+    P.slab_bytes += P.big_bytes;
 
     int rc;
     if ((rc = ensure_jump_tables(ctx))) return rc;
@@ -1763,6 +1919,12 @@ int launch_stage_ex(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worke
     LCTP_CUDA_CHECK(cudaMemcpyAsync(flags, ctx->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
     ctx->stats.d2h_bytes += n * 8 * 4 + n_workers * 32 + (liks ? n * st->attempts * 8 : 0) + sizeof(int);
+    if (flags[0] & 4) {
+        set_error("lctp_solve_stage: greedy sample size %llu on a genotype with so many non-trivial reads that rand's "
+                  "index::sample would use its rejection branch (amount >= 163 and length >= 270 * amount), which is not "
+                  "implemented", (unsigned long long)st->sample_size);
+        return LCTP_E_CAPACITY;
+    }
     if (flags[0]) {
         set_error("lctp_solve_stage: candidate overflow (more than %u candidates in one genotype)", cap);
         return LCTP_E_CAPACITY;

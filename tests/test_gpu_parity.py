@@ -110,6 +110,16 @@ def test_greedy_random_start_and_small_sample(oracle, gpu_ctx, small_locus):
                                                      plato_size=30), 3, gts)
 
 
+@pytest.mark.parametrize("R,s", [(300, 12), (300, 40), (300, 1000), (700, 12), (700, 13)])
+def test_greedy_samples_of_more_than_11_reads(oracle, gpu_ctx, R, s):
+    """Greedy::set_sample_size accepts any s >= 1 (src/solvers/stoch.rs:65-72); beyond 11 rand's index::sample switches
+    between Floyd's algorithm (long lists: R = 700) and the in-place partial shuffle (short lists; s >= the number of
+    non-trivial reads makes it a full permutation).  Iterations, RNG streams, counts and likelihoods must still match."""
+    loc = _mk(oracle, 16, R, 2500, 41 + R)
+    gts = list(range(0, loc.n_genotypes, 11))
+    _stage_parity(oracle, gpu_ctx, loc, dict(kind="greedy", attempts=2, sample_size=s, plato_size=20), 3, gts)
+
+
 def test_anneal_stage_parity(oracle, gpu_ctx, small_locus):
     gts = list(range(1, small_locus.n_genotypes, 61))
     _stage_parity(oracle, gpu_ctx, small_locus, dict(kind="anneal", attempts=3, anneal_steps=3000, plato_size=1500),
