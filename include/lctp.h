@@ -188,6 +188,15 @@ typedef struct lctp_mates {
     double unmapped_penalty;       /* Params::unmapped_penalty (src/model/mod.rs:55-60) */
     double insert_penalty;         /* InsertDistr::insert_penalty (insertsz.rs:171-173) */
     double prob_diff;              /* Params::prob_diff */
+    /* single-end reads (identify_single_end_alignments, src/model/locs.rs:870-911): every record is a "first end" record,
+     * per (read, contig) in descending ln_prob; ins_ln_pmf / insert_penalty are not used */
+    uint32_t single_end;
+    uint32_t window;               /* window size (ContigInfo::window_size), needed with explicit weights only */
+    /* explicit region weights (ContigInfos::explicit_read_weight, src/model/windows.rs:683-693; ExplicitWeights::at,
+     * :226-229): per contig the weight of every position, contig_len + 1 entries each (the reference appends the last
+     * value once more); NULL = no explicit weights (weight 1) */
+    const uint64_t *exp_off;       /* [H+1] */
+    const double   *exp_weight;
 } lctp_mates;
 
 /* ---- library / context -------------------------------------------------------------------- */
@@ -232,6 +241,17 @@ int  lctp_pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uin
                           uint32_t *pa_contig, double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2,
                           double *unmapped_prob, uint64_t *n_out);
 size_t lctp_sizeof_mates(void);
+/* Same, leaving the result on the device: the handle replaces the pa_* / unmapped_prob fields of lctp_locus in
+ * lctp_locus_upload_pairs (no host round trip between pairing and the solver), lctp_pairs_fetch copies it to the host
+ * when it is needed there (BAM output). */
+typedef struct lctp_pairs_h lctp_pairs_h;
+int  lctp_pair_alignments_dev(lctp_ctx *ctx, const lctp_mates *in, lctp_pairs_h **out, uint64_t *n_out);
+int  lctp_pairs_fetch(lctp_pairs_h *p, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig, double *pa_ln_prob,
+                      uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob);
+uint64_t lctp_pairs_count(const lctp_pairs_h *p);
+void lctp_pairs_free(lctp_pairs_h *p);
+int  lctp_locus_upload_pairs(lctp_ctx *ctx, const lctp_locus *in /* pa_*, unmapped_prob ignored */,
+                             lctp_pairs_h *pairs, lctp_locus_h **out);
 /* SURVEY 8(f) rank 2, first slice: rescore every alignment record under the error profile on the device.
  * Outputs (caller-allocated, n_alns entries each): ln_prob = Alignment::set_ln_prob value, edit / read_len =
  * EditDist{edit, read_len}, save = (edit <= passable_dist).  LCTP_E_INVALID on an empty CIGAR or an unsupported

@@ -166,18 +166,29 @@ struct lctp_locus_h {
     bool mt_nonpositive = false;         // every matrix entry <= +0.0 (integer-pipe max is valid)
 };
 
+// Pair alignments of a locus left resident on the device by lctp_pair_alignments_dev: the pa_* / unmapped_prob section of
+// lctp_locus without a host round trip (consumed by lctp_locus_upload_pairs).
+struct lctp_pairs_h {
+    lctp_ctx *ctx = nullptr;
+    uint32_t n_reads = 0, n_haps = 0;
+    uint64_t n_pairs = 0;
+    lctp::DevBuf<uint64_t> pa_off;
+    lctp::DevBuf<uint32_t> contig, mid1, mid2;
+    lctp::DevBuf<double> lnprob, unmapped;
+};
+
 namespace lctp {
 // upload.cu
-int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h);
+int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h, const lctp_pairs_h *pairs);
 // prefilter.cu
 int launch_prefilter(lctp_locus_h *h, uint64_t g_begin, uint64_t g_end, double *d_scores);
 int measure_fp64_rate(lctp_ctx *ctx, double *lane_inst_per_s);
 int prefilter_plan_check(uint32_t H, uint32_t n_sm, const uint32_t *pattern, uint32_t n_pattern, uint64_t g_begin,
                          uint64_t g_end, uint32_t *n_regions, uint32_t *load, uint32_t *pattern_out);
 // pairs.cu
-int pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig,
-                    double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob,
-                    uint64_t *n_out);
+int pair_alignments_dev(lctp_ctx *ctx, const lctp_mates *in, lctp_pairs_h *out);
+int pairs_fetch(lctp_pairs_h *p, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig, double *pa_ln_prob,
+                uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob);
 // rescore.cu
 int rescore_alignments(lctp_ctx *ctx, const lctp_alns *in, double *ln_prob, uint32_t *edit, uint32_t *read_len,
                        uint8_t *save);

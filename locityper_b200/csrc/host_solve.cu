@@ -433,9 +433,23 @@ int lctp_rescore_alignments(lctp_ctx *ctx, const lctp_alns *in, double *ln_prob,
 int lctp_pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig,
                          double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob,
                          uint64_t *n_out) {
-    if (!ctx || !in || !pa_off || !unmapped_prob || (cap && (!pa_contig || !pa_ln_prob || !pa_mid1 || !pa_mid2)) ||
-        !in->ins_ln_pmf || in->ins_len == 0) {
+    if (!ctx || !in || !pa_off || !unmapped_prob || (cap && (!pa_contig || !pa_ln_prob || !pa_mid1 || !pa_mid2))) {
         set_error("lctp_pair_alignments: NULL argument");
+        return LCTP_E_INVALID;
+    }
+    lctp_pairs_h *p = nullptr;
+    int rc = lctp_pair_alignments_dev(ctx, in, &p, n_out);
+    if (rc) return rc;
+    rc = pairs_fetch(p, cap, pa_off, pa_contig, pa_ln_prob, pa_mid1, pa_mid2, unmapped_prob);
+    lctp_pairs_free(p);
+    return rc;
+}
+
+int lctp_pair_alignments_dev(lctp_ctx *ctx, const lctp_mates *in, lctp_pairs_h **out, uint64_t *n_out) {
+    if (!ctx || !in || !out) { set_error("lctp_pair_alignments: NULL argument"); return LCTP_E_INVALID; }
+    *out = nullptr;
+    if (!in->single_end && (!in->ins_ln_pmf || in->ins_len == 0)) {
+        set_error("lctp_pair_alignments: NULL insert-size table");
         return LCTP_E_INVALID;
     }
     if (in->n_reads && in->ma_off && in->ma_off[in->n_reads] &&
@@ -445,7 +459,47 @@ int lctp_pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint
     }
     LCTP_CUDA_CHECK(cudaSetDevice(ctx->device));
     set_alloc_stream(ctx->stream);
-    return pair_alignments(ctx, in, cap, pa_off, pa_contig, pa_ln_prob, pa_mid1, pa_mid2, unmapped_prob, n_out);
+    lctp_pairs_h *p = new lctp_pairs_h();
+    const int rc = pair_alignments_dev(ctx, in, p);
+    if (rc) { delete p; return rc; }
+    if (n_out) *n_out = p->n_pairs;
+    *out = p;
+    return LCTP_OK;
+}
+
+int lctp_pairs_fetch(lctp_pairs_h *p, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig, double *pa_ln_prob,
+                     uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob) {
+    if (!p || !pa_off || !unmapped_prob || (cap && (!pa_contig || !pa_ln_prob || !pa_mid1 || !pa_mid2))) {
+        set_error("lctp_pairs_fetch: NULL argument");
+        return LCTP_E_INVALID;
+    }
+    LCTP_CUDA_CHECK(cudaSetDevice(p->ctx->device));
+    return pairs_fetch(p, cap, pa_off, pa_contig, pa_ln_prob, pa_mid1, pa_mid2, unmapped_prob);
+}
+
+uint64_t lctp_pairs_count(const lctp_pairs_h *p) { return p ? p->n_pairs : 0; }
+
+void lctp_pairs_free(lctp_pairs_h *p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    set_alloc_stream(p->ctx->stream);
+    delete p;
+}
+
+int lctp_locus_upload_pairs(lctp_ctx *ctx, const lctp_locus *in, lctp_pairs_h *pairs, lctp_locus_h **out) {
+    if (!ctx || !in || !pairs || !out) { set_error("lctp_locus_upload_pairs: NULL argument"); return LCTP_E_INVALID; }
+    *out = nullptr;
+    if (pairs->ctx != ctx || pairs->n_reads != in->n_reads) {
+        set_error("lctp_locus_upload_pairs: pair alignments of another context / read count");
+        return LCTP_E_INVALID;
+    }
+    LCTP_CUDA_CHECK(cudaSetDevice(ctx->device));
+    set_alloc_stream(ctx->stream);
+    lctp_locus_h *h = new lctp_locus_h();
+    int rc = upload_locus(ctx, in, h, pairs);
+    if (rc != LCTP_OK) { delete h; return rc; }
+    *out = h;
+    return LCTP_OK;
 }
 
 int lctp_measure_fp64_rate(lctp_ctx *ctx, double *lane_inst_per_s) {
@@ -472,7 +526,7 @@ int lctp_locus_upload(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h **out) {
     LCTP_CUDA_CHECK(cudaSetDevice(ctx->device));
     set_alloc_stream(ctx->stream);
     lctp_locus_h *h = new lctp_locus_h();
-    int rc = upload_locus(ctx, in, h);
+    int rc = upload_locus(ctx, in, h, nullptr);
     if (rc != LCTP_OK) { delete h; return rc; }
     *out = h;
     return LCTP_OK;

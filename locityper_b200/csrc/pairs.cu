@@ -25,12 +25,14 @@ namespace lctp {
 static constexpr int PAIR_MAX_ALNS = 16;     // per read end and contig; the reference uses 10 (locs.rs:741)
 
 struct MatesDev {
-    uint32_t R, max_alns, ins_len;
+    uint32_t R, max_alns, ins_len, single_end, window;
     uint64_t N;
     const uint64_t *ma_off;
     const uint32_t *ma_contig, *ma_start, *ma_end;
     const uint8_t *ma_flags;
     const double *ma_ln_prob, *read_weight, *ins_ln_pmf;
+    const uint64_t *exp_off;         // [H+1] explicit region weights per contig position, or nullptr
+    const double *exp_weight;
     double unmapped_penalty, insert_penalty, prob_diff;
 };
 
@@ -103,6 +105,26 @@ k_pair_groups(MatesDev D, const uint32_t *__restrict__ group_start, const uint32
     while (f < e && (D.ma_flags[f] & 1u) == 0) f++;
     for (uint64_t q = f; q < e; q++) if ((D.ma_flags[q] & 1u) == 0) atomicOr(err, 2);   // first end before second
     const uint32_t M = D.max_alns;
+    if (D.single_end) {
+        // identify_single_end_alignments (locs.rs:870-911): the records of the contig in descending ln_prob; the best
+        // one sets the threshold, at most max_alns within prob_diff of it are kept as "first mate only" pairs.
+        if (f != e) atomicOr(err, 16);                                     // a second-end record in single-end data
+        const double thresh = __dsub_rn(D.ma_ln_prob[i], D.prob_diff);
+        uint32_t keep = 0;
+        for (uint64_t q = i; q < e && keep < M; q++) {
+            const double lp = D.ma_ln_prob[q];
+            if (q > i && lp > D.ma_ln_prob[q - 1]) atomicOr(err, 4);
+            if (!(lp >= thresh)) break;                                    // sorted: nothing further passes either
+            if (WRITE) {
+                const uint64_t o = offs[g] + keep;
+                pa_contig[o] = contig; pa_ln_prob[o] = lp;
+                pa_mid1[o] = (D.ma_start[q] + D.ma_end[q]) / 2; pa_mid2[o] = LCTP_NONE_U32;
+            }
+            keep++;
+        }
+        if (!WRITE) counts[g] = keep;
+        return;
+    }
     const uint32_t n1 = (uint32_t)min((uint64_t)M, f - i), n2 = (uint32_t)min((uint64_t)M, e - f);
     const double unm_ins = D.unmapped_penalty + D.insert_penalty;          // locs.rs:815-816
 
@@ -142,11 +164,11 @@ k_pair_groups(MatesDev D, const uint32_t *__restrict__ group_start, const uint32
         uint32_t keep = 0;
         if (n >= 1 && lp0 >= thresh) { keep = 1; if (n >= 2 && lp1 >= thresh) { keep = 2; if (n >= 3 && lp2 >= thresh) keep = 3; } }
         if (!WRITE) { counts[g] = keep; return; }
-        const double weight = D.read_weight ? D.read_weight[r] : 1.0;
+        // unscaled: the read's weight needs all of its kept pairs (k_pair_read_finish)
         const uint64_t o = offs[g];
-        if (keep >= 1) { pa_contig[o] = contig; pa_ln_prob[o] = __dmul_rn(lp0, weight); pa_mid1[o] = x0; pa_mid2[o] = y0; }
-        if (keep >= 2) { pa_contig[o + 1] = contig; pa_ln_prob[o + 1] = __dmul_rn(lp1, weight); pa_mid1[o + 1] = x1; pa_mid2[o + 1] = y1; }
-        if (keep >= 3) { pa_contig[o + 2] = contig; pa_ln_prob[o + 2] = __dmul_rn(lp2, weight); pa_mid1[o + 2] = x2; pa_mid2[o + 2] = y2; }
+        if (keep >= 1) { pa_contig[o] = contig; pa_ln_prob[o] = lp0; pa_mid1[o] = x0; pa_mid2[o] = y0; }
+        if (keep >= 2) { pa_contig[o + 1] = contig; pa_ln_prob[o + 1] = lp1; pa_mid1[o + 1] = x1; pa_mid2[o + 1] = y1; }
+        if (keep >= 3) { pa_contig[o + 2] = contig; pa_ln_prob[o + 2] = lp2; pa_mid1[o + 2] = x2; pa_mid2[o + 2] = y2; }
         return;
     }
 
@@ -189,26 +211,55 @@ k_pair_groups(MatesDev D, const uint32_t *__restrict__ group_start, const uint32
     uint32_t keep = 0;
     while (keep < top.n && top.lp[keep] >= thresh) keep++;
     if (!WRITE) { counts[g] = keep; return; }
-    const double weight = D.read_weight ? D.read_weight[r] : 1.0;
     const uint64_t o = offs[g];
     for (uint32_t q = 0; q < keep; q++) {
         pa_contig[o + q] = contig;
-        pa_ln_prob[o + q] = __dmul_rn(top.lp[q], weight);                  // locs.rs:861-863
+        pa_ln_prob[o + q] = top.lp[q];
         pa_mid1[o + q] = top.m1[q];
         pa_mid2[o + q] = top.m2[q];
     }
 }
 
-// pa_off[r] = offs[first group at or after ma_off[r]]; unmapped_prob[r] = weight * (2 * unmapped_penalty + insert_penalty) (locs.rs:866)
+// pa_off[r] = offs[first group at or after ma_off[r]]
 __global__ void k_pair_read_outputs(MatesDev D, const uint32_t *__restrict__ gidx, const uint64_t *__restrict__ offs,
-                                    uint64_t *__restrict__ pa_off, double *__restrict__ unmapped_prob) {
+                                    uint64_t *__restrict__ pa_off) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r > D.R) return;
     pa_off[r] = offs[gidx[D.ma_off[r]]];              // gidx[N] = number of groups, offs[G] = total
-    if (r < D.R) {
-        const double weight = D.read_weight ? D.read_weight[r] : 1.0;
-        unmapped_prob[r] = __dmul_rn(weight, __dadd_rn(__dmul_rn(2.0, D.unmapped_penalty), D.insert_penalty));
+}
+
+// ContigInfo::read_end_weight (src/model/windows.rs:495-504): the largest explicit weight at the middle of the read end
+// and half a window to either side; an unmapped end weighs 0.
+__device__ __forceinline__ double read_end_weight(const MatesDev &D, uint32_t contig, uint32_t middle) {
+    if (middle == LCTP_NONE_U32) return 0.0;
+    const double *w = D.exp_weight + D.exp_off[contig];
+    const uint32_t n = (uint32_t)(D.exp_off[contig + 1] - D.exp_off[contig]);
+    const uint32_t u = D.window / 2;
+    return fmax(fmax(w[middle], w[middle > u ? middle - u : 0u]), w[min(middle + u, n - 1u)]);
+}
+
+// The tail of identify_paired_end_alignments / identify_single_end_alignments (locs.rs:860-867, 904-910), one thread
+// per read: weight = ReadData::weight * ContigInfos::explicit_read_weight (windows.rs:683-693: the mean over the
+// read's kept pair alignments of max(read_end_weight(mate 1), read_end_weight(mate 2)), 1 without explicit
+// weights), every ln_prob *= weight, unmapped_prob = weight * (2 * unmapped_penalty + insert_penalty) for pairs,
+// weight * unmapped_penalty for single-end reads.
+__global__ void k_pair_read_finish(MatesDev D, const uint64_t *__restrict__ pa_off, const uint32_t *__restrict__ pa_contig,
+                                   double *__restrict__ pa_ln_prob, const uint32_t *__restrict__ pa_mid1,
+                                   const uint32_t *__restrict__ pa_mid2, double *__restrict__ unmapped_prob) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= D.R) return;
+    const uint64_t b = pa_off[r], e = pa_off[r + 1];
+    double expl = 1.0;
+    if (D.exp_weight) {
+        double s = 0.0;
+        for (uint64_t q = b; q < e; q++)
+            s = __dadd_rn(s, fmax(read_end_weight(D, pa_contig[q], pa_mid1[q]), read_end_weight(D, pa_contig[q], pa_mid2[q])));
+        expl = __ddiv_rn(s, (double)(e - b));
     }
+    const double weight = __dmul_rn(D.read_weight ? D.read_weight[r] : 1.0, expl);
+    for (uint64_t q = b; q < e; q++) pa_ln_prob[q] = __dmul_rn(pa_ln_prob[q], weight);
+    unmapped_prob[r] = D.single_end ? __dmul_rn(weight, D.unmapped_penalty)
+                                    : __dmul_rn(weight, __dadd_rn(__dmul_rn(2.0, D.unmapped_penalty), D.insert_penalty));
 }
 
 template <typename T>
@@ -219,9 +270,7 @@ static int to_dev(DevBuf<T> &dst, const T *src, size_t n, cudaStream_t s) {
     return LCTP_OK;
 }
 
-int pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig,
-                    double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob,
-                    uint64_t *n_out) {
+int pair_alignments_dev(lctp_ctx *ctx, const lctp_mates *in, lctp_pairs_h *P) {
     cudaStream_t s = ctx->stream;
     const uint32_t R = in->n_reads;
     if (R == 0 || !in->ma_off) { set_error("lctp_pair_alignments: no reads"); return LCTP_E_INVALID; }
@@ -229,39 +278,55 @@ int pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t 
         set_error("lctp_pair_alignments: max_alns %u unsupported (1..=%d)", in->max_alns, PAIR_MAX_ALNS);
         return LCTP_E_CAPACITY;
     }
+    if ((in->exp_weight != nullptr) != (in->exp_off != nullptr) || (in->exp_weight && in->window == 0)) {
+        set_error("lctp_pair_alignments: explicit weights need exp_off, exp_weight and the window size");
+        return LCTP_E_INVALID;
+    }
+    if (!in->single_end && !in->ins_ln_pmf) { set_error("lctp_pair_alignments: NULL insert-size table"); return LCTP_E_INVALID; }
     const uint64_t N = in->ma_off[R];
-    DevBuf<uint64_t> d_off, d_offs, d_pa_off;
-    DevBuf<uint32_t> d_contig, d_start, d_end, d_counts, d_oc, d_m1, d_m2, d_head, d_gidx, d_gstart;
+    DevBuf<uint64_t> d_off, d_offs, d_exp_off;
+    DevBuf<uint32_t> d_contig, d_start, d_end, d_counts, d_head, d_gidx, d_gstart;
     DevBuf<uint8_t> d_flags;
-    DevBuf<double> d_lp, d_w, d_ins, d_olp, d_unm;
+    DevBuf<double> d_lp, d_w, d_ins, d_exp;
     DevBuf<int> d_err;
     DevBuf<unsigned char> d_tmp;
     int rc;
     if (N >= 0xFFFFFFFFull) { set_error("lctp_pair_alignments: %llu mate records (limit 2^32 - 2)", (unsigned long long)N); return LCTP_E_CAPACITY; }
+    uint64_t h2d = 0;
     if ((rc = to_dev(d_off, in->ma_off, (size_t)R + 1, s))) return rc;
     if ((rc = to_dev(d_contig, in->ma_contig, N, s))) return rc;
     if ((rc = to_dev(d_start, in->ma_start, N, s))) return rc;
     if ((rc = to_dev(d_end, in->ma_end, N, s))) return rc;
     if ((rc = to_dev(d_flags, in->ma_flags, N, s))) return rc;
     if ((rc = to_dev(d_lp, in->ma_ln_prob, N, s))) return rc;
-    if (in->read_weight && (rc = to_dev(d_w, in->read_weight, R, s))) return rc;
-    if ((rc = to_dev(d_ins, in->ins_ln_pmf, in->ins_len, s))) return rc;
+    h2d += ((size_t)R + 1) * 8 + N * (4 + 4 + 4 + 1 + 8);
+    if (in->read_weight) { if ((rc = to_dev(d_w, in->read_weight, R, s))) return rc; h2d += (uint64_t)R * 8; }
+    if (!in->single_end) { if ((rc = to_dev(d_ins, in->ins_ln_pmf, in->ins_len, s))) return rc; h2d += (uint64_t)in->ins_len * 8; }
+    if (in->exp_weight) {
+        const uint64_t tot = in->exp_off[in->n_haps];
+        if ((rc = to_dev(d_exp_off, in->exp_off, (size_t)in->n_haps + 1, s))) return rc;
+        if ((rc = to_dev(d_exp, in->exp_weight, tot, s))) return rc;
+        h2d += ((uint64_t)in->n_haps + 1) * 8 + tot * 8;
+    }
+    ctx->stats.h2d_bytes += h2d;
     if ((rc = d_head.alloc(N + 1))) return rc;
     if ((rc = d_gidx.alloc(N + 1))) return rc;
     if ((rc = d_gstart.alloc(N + 2))) return rc;
     if ((rc = d_counts.alloc(N + 1))) return rc;
     if ((rc = d_offs.alloc(N + 1))) return rc;
     if ((rc = d_err.alloc(1))) return rc;
-    if ((rc = d_pa_off.alloc((size_t)R + 1))) return rc;
-    if ((rc = d_unm.alloc(R))) return rc;
+    if ((rc = P->pa_off.alloc((size_t)R + 1))) return rc;
+    if ((rc = P->unmapped.alloc(R))) return rc;
     LCTP_CUDA_CHECK(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
     LCTP_CUDA_CHECK(cudaMemsetAsync(d_counts.p, 0, (N + 1) * sizeof(uint32_t), s));
 
     MatesDev D;
     D.R = R; D.max_alns = in->max_alns; D.ins_len = in->ins_len; D.N = N;
+    D.single_end = in->single_end ? 1u : 0u; D.window = in->window;
     D.ma_off = d_off.p; D.ma_contig = d_contig.p; D.ma_start = d_start.p; D.ma_end = d_end.p;
     D.ma_flags = d_flags.p; D.ma_ln_prob = d_lp.p; D.read_weight = in->read_weight ? d_w.p : nullptr;
     D.ins_ln_pmf = d_ins.p;
+    D.exp_off = in->exp_weight ? d_exp_off.p : nullptr; D.exp_weight = in->exp_weight ? d_exp.p : nullptr;
     D.unmapped_penalty = in->unmapped_penalty; D.insert_penalty = in->insert_penalty; D.prob_diff = in->prob_diff;
 
     uint64_t total = 0;
@@ -289,39 +354,29 @@ int pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t 
         int err = 0;
         LCTP_CUDA_CHECK(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
         LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
+        ctx->stats.d2h_bytes += 12;
         if (err) {
             set_error("lctp_pair_alignments: malformed mate alignments (flags=%d: 1=contigs not ascending within a "
                       "read, 2=second-end record before a first-end record of the same contig, 4=ln_prob not "
-                      "descending within a (read, contig, end) run, 8=insert size outside the ln-pmf table)", err);
+                      "descending within a (read, contig, end) run, 8=insert size outside the ln-pmf table, "
+                      "16=second-end record in single-end input)", err);
             return LCTP_E_INVALID;
         }
-        if (total > cap) {
-            set_error("lctp_pair_alignments: output capacity %llu too small (%llu pair alignments)",
-                      (unsigned long long)cap, (unsigned long long)total);
-            return LCTP_E_CAPACITY;
-        }
-        if ((rc = d_oc.alloc(total))) return rc;
-        if ((rc = d_olp.alloc(total))) return rc;
-        if ((rc = d_m1.alloc(total))) return rc;
-        if ((rc = d_m2.alloc(total))) return rc;
-        LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[2], s));      // phase B: write pass
+        if ((rc = P->contig.alloc(total))) return rc;
+        if ((rc = P->lnprob.alloc(total))) return rc;
+        if ((rc = P->mid1.alloc(total))) return rc;
+        if ((rc = P->mid2.alloc(total))) return rc;
+        LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[2], s));      // phase B: write pass + per-read weights
         if (N) {
-            k_pair_groups<true><<<grid_g, 128, 0, s>>>(D, d_gstart.p, d_gidx.p, nullptr, d_offs.p, d_oc.p, d_olp.p, d_m1.p, d_m2.p, d_err.p);
+            k_pair_groups<true><<<grid_g, 128, 0, s>>>(D, d_gstart.p, d_gidx.p, nullptr, d_offs.p, P->contig.p, P->lnprob.p, P->mid1.p, P->mid2.p, d_err.p);
             ctx->launches++;
         }
-        k_pair_read_outputs<<<(R + 1 + 255) / 256, 256, 0, s>>>(D, d_gidx.p, d_offs.p, d_pa_off.p, d_unm.p);
-        ctx->launches++;
+        k_pair_read_outputs<<<(R + 1 + 255) / 256, 256, 0, s>>>(D, d_gidx.p, d_offs.p, P->pa_off.p);
+        k_pair_read_finish<<<(R + 255) / 256, 256, 0, s>>>(D, P->pa_off.p, P->contig.p, P->lnprob.p, P->mid1.p, P->mid2.p, P->unmapped.p);
+        ctx->launches += 2;
         LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[3], s));
     }
     LCTP_CUDA_CHECK(cudaGetLastError());
-    LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_off, d_pa_off.p, ((size_t)R + 1) * 8, cudaMemcpyDeviceToHost, s));
-    LCTP_CUDA_CHECK(cudaMemcpyAsync(unmapped_prob, d_unm.p, (size_t)R * 8, cudaMemcpyDeviceToHost, s));
-    if (total) {
-        LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_contig, d_oc.p, total * 4, cudaMemcpyDeviceToHost, s));
-        LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_ln_prob, d_olp.p, total * 8, cudaMemcpyDeviceToHost, s));
-        LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_mid1, d_m1.p, total * 4, cudaMemcpyDeviceToHost, s));
-        LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_mid2, d_m2.p, total * 4, cudaMemcpyDeviceToHost, s));
-    }
     LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
     {
         float ms = 0.f, ms2 = 0.f;
@@ -332,7 +387,29 @@ int pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t 
         ctx->stats.pairing_mates += N;
         ctx->stats.pairing_pairs += total;
     }
-    if (n_out) *n_out = total;
+    P->ctx = ctx; P->n_reads = R; P->n_pairs = total; P->n_haps = in->n_haps;
+    return LCTP_OK;
+}
+
+int pairs_fetch(lctp_pairs_h *P, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig, double *pa_ln_prob,
+                uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob) {
+    cudaStream_t s = P->ctx->stream;
+    const uint64_t total = P->n_pairs;
+    if (total > cap) {
+        set_error("lctp_pair_alignments: output capacity %llu too small (%llu pair alignments)",
+                  (unsigned long long)cap, (unsigned long long)total);
+        return LCTP_E_CAPACITY;
+    }
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_off, P->pa_off.p, ((size_t)P->n_reads + 1) * 8, cudaMemcpyDeviceToHost, s));
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(unmapped_prob, P->unmapped.p, (size_t)P->n_reads * 8, cudaMemcpyDeviceToHost, s));
+    if (total) {
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_contig, P->contig.p, total * 4, cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_ln_prob, P->lnprob.p, total * 8, cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_mid1, P->mid1.p, total * 4, cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(pa_mid2, P->mid2.p, total * 4, cudaMemcpyDeviceToHost, s));
+    }
+    LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
+    P->ctx->stats.d2h_bytes += ((size_t)P->n_reads + 1) * 8 + (size_t)P->n_reads * 8 + total * 20;
     return LCTP_OK;
 }
 

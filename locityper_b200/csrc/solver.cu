@@ -1763,7 +1763,7 @@ static int launch_stage_kernel(lctp_locus_h *h, const StageParams &P, size_t n_w
     // from at random, and a worker whose slab has been evicted runs at DRAM latency.  Never fewer than one
     // worker per SM sub-partition.
     {
-        const size_t budget = (size_t)std::max(1, env_int("LCTP_L2_BUDGET_MB", 96)) << 20;
+        const size_t budget = (size_t)std::max(1, env_int("LCTP_L2_BUDGET_MB", 1024)) << 20;
         const size_t per = std::max<size_t>(1, P.slab_bytes);
         const uint32_t by_l2 = (uint32_t)std::max<size_t>(budget / per, (size_t)ctx->sm_count * 4);
         resident = std::min(resident, by_l2);

@@ -72,7 +72,9 @@ static int h2d(DevBuf<T> &dst, const T *src, size_t n, cudaStream_t s) {
     return LCTP_OK;
 }
 
-int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h) {
+// `pairs`: the pa_* / unmapped_prob section comes from lctp_pair_alignments_dev, already on the device (the fields of
+// `in` are ignored for it); nullptr = copy it from the host arrays of `in`.
+int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h, const lctp_pairs_h *pairs) {
     cudaStream_t s = ctx->stream;
     const uint32_t H = in->n_haps, R = in->n_reads, p = in->ploidy;
     if (H == 0 || R == 0 || p == 0 || in->n_genotypes == 0) {
@@ -84,17 +86,17 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h) {
         set_error("lctp_locus_upload: ploidy %u > %d unsupported", p, LCTP_MAX_PLOIDY);
         return LCTP_E_CAPACITY;
     }
-    if (!in->unmapped_prob || !in->pa_off || !in->hap_len || !in->hap_n_windows || !in->hap_reg_start ||
+    if ((!pairs && (!in->unmapped_prob || !in->pa_off)) || !in->hap_len || !in->hap_n_windows || !in->hap_reg_start ||
         !in->hap_pos_off || !in->pos_weight || !in->pos_gc || !in->depth_table) {
         set_error("lctp_locus_upload: NULL input array");
         return LCTP_E_INVALID;
     }
-    const uint64_t npa = in->pa_off[R];
+    const uint64_t npa = pairs ? pairs->n_pairs : in->pa_off[R];
     if (npa >= 0xFFFFFFF0ull || (uint64_t)H * R >= 0xFFFFFFF0ull) {
         set_error("lctp_locus_upload: too many pair alignments (%llu) or H*R too large", (unsigned long long)npa);
         return LCTP_E_CAPACITY;
     }
-    if (npa && (!in->pa_contig || !in->pa_ln_prob || !in->pa_mid1 || !in->pa_mid2)) {
+    if (!pairs && npa && (!in->pa_contig || !in->pa_ln_prob || !in->pa_mid1 || !in->pa_mid2)) {
         set_error("lctp_locus_upload: NULL pair-alignment array");
         return LCTP_E_INVALID;
     }
@@ -144,7 +146,7 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h) {
     h->hap_n_windows.assign(in->hap_n_windows, in->hap_n_windows + H);
     if (in->gt_tuples) h->gt_tuples_host.assign(in->gt_tuples, in->gt_tuples + (size_t)in->n_genotypes * p);
     if (in->priors) h->priors_host.assign(in->priors, in->priors + (size_t)in->n_genotypes);
-    h->unmapped_host.assign(in->unmapped_prob, in->unmapped_prob + R);
+    if (!pairs) h->unmapped_host.assign(in->unmapped_prob, in->unmapped_prob + R);
     const uint32_t Hpad = (H + 63u) & ~63u;
 
     int rc;
@@ -153,12 +155,24 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h) {
     DevBuf<uint32_t> d_pa_contig, d_mid1, d_mid2;
     DevBuf<double> d_pa_lnprob;
     DevBuf<int> d_err;
-    if ((rc = h2d(d_pa_off, in->pa_off, (size_t)R + 1, s))) return rc;
-    if ((rc = h2d(d_pa_contig, in->pa_contig, npa, s))) return rc;
-    if ((rc = h2d(d_pa_lnprob, in->pa_ln_prob, npa, s))) return rc;
-    if ((rc = h2d(d_mid1, in->pa_mid1, npa, s))) return rc;
-    if ((rc = h2d(d_mid2, in->pa_mid2, npa, s))) return rc;
-    if ((rc = h2d(h->unmapped, in->unmapped_prob, R, s))) return rc;
+    const uint64_t *p_off; const uint32_t *p_contig, *p_mid1, *p_mid2; const double *p_lnprob;
+    if (pairs) {
+        p_off = pairs->pa_off.p; p_contig = pairs->contig.p; p_lnprob = pairs->lnprob.p;
+        p_mid1 = pairs->mid1.p; p_mid2 = pairs->mid2.p;
+        if ((rc = h->unmapped.alloc(R))) return rc;
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(h->unmapped.p, pairs->unmapped.p, (size_t)R * 8, cudaMemcpyDeviceToDevice, s));
+        h->unmapped_host.resize(R);                    // count_unexplained_reads reads it on the host (R x 8 bytes)
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(h->unmapped_host.data(), pairs->unmapped.p, (size_t)R * 8, cudaMemcpyDeviceToHost, s));
+        ctx->stats.d2h_bytes += (uint64_t)R * 8;
+    } else {
+        if ((rc = h2d(d_pa_off, in->pa_off, (size_t)R + 1, s))) return rc;
+        if ((rc = h2d(d_pa_contig, in->pa_contig, npa, s))) return rc;
+        if ((rc = h2d(d_pa_lnprob, in->pa_ln_prob, npa, s))) return rc;
+        if ((rc = h2d(d_mid1, in->pa_mid1, npa, s))) return rc;
+        if ((rc = h2d(d_mid2, in->pa_mid2, npa, s))) return rc;
+        if ((rc = h2d(h->unmapped, in->unmapped_prob, R, s))) return rc;
+        p_off = d_pa_off.p; p_contig = d_pa_contig.p; p_lnprob = d_pa_lnprob.p; p_mid1 = d_mid1.p; p_mid2 = d_mid2.p;
+    }
     if ((rc = h2d(h->hap_len, in->hap_len, H, s))) return rc;
     if ((rc = h2d(h->hap_nw, in->hap_n_windows, H, s))) return rc;
     if ((rc = h2d(h->hap_rs, in->hap_reg_start, H, s))) return rc;
@@ -199,8 +213,8 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h) {
     }
     const unsigned warps_per_block = 8;
     const unsigned grid = (R + warps_per_block - 1) / warps_per_block;
-    k_group_runs<false><<<grid, warps_per_block * 32, 0, s>>>(d_pa_off.p, d_pa_contig.p, d_pa_lnprob.p, d_mid1.p,
-                                                               d_mid2.p, R, H, Hpad, d_cnt.p, h->Mt.p, nullptr,
+    k_group_runs<false><<<grid, warps_per_block * 32, 0, s>>>(p_off, p_contig, p_lnprob, p_mid1,
+                                                               p_mid2, R, H, Hpad, d_cnt.p, h->Mt.p, nullptr,
                                                                nullptr, d_err.p);
     ctx->launches++;
     size_t tmp_bytes = 0;
@@ -209,8 +223,8 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h) {
     if ((rc = d_tmp.alloc(tmp_bytes))) return rc;
     LCTP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_cnt.p, h->cm_off.p, (int)n_keys, s));
     ctx->launches++;
-    k_group_runs<true><<<grid, warps_per_block * 32, 0, s>>>(d_pa_off.p, d_pa_contig.p, d_pa_lnprob.p, d_mid1.p,
-                                                              d_mid2.p, R, H, Hpad, h->cm_off.p, nullptr,
+    k_group_runs<true><<<grid, warps_per_block * 32, 0, s>>>(p_off, p_contig, p_lnprob, p_mid1,
+                                                              p_mid2, R, H, Hpad, h->cm_off.p, nullptr,
                                                               h->cm_lnprob.p, h->cm_mid.p, d_err.p);
     ctx->launches++;
     LCTP_CUDA_CHECK(cudaMemcpyAsync(h->cm_lnprob.p + npa, h->unmapped.p, (size_t)R * 8, cudaMemcpyDeviceToDevice, s));

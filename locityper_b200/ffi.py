@@ -90,7 +90,8 @@ class MatesC(C.Structure):
                 ("ma_off", C.c_void_p), ("ma_contig", C.c_void_p), ("ma_flags", C.c_void_p), ("ma_start", C.c_void_p),
                 ("ma_end", C.c_void_p), ("ma_ln_prob", C.c_void_p), ("read_weight", C.c_void_p),
                 ("ins_ln_pmf", C.c_void_p),
-                ("unmapped_penalty", C.c_double), ("insert_penalty", C.c_double), ("prob_diff", C.c_double)]
+                ("unmapped_penalty", C.c_double), ("insert_penalty", C.c_double), ("prob_diff", C.c_double),
+                ("single_end", C.c_uint32), ("window", C.c_uint32), ("exp_off", C.c_void_p), ("exp_weight", C.c_void_p)]
 
 
 class AlnsC(C.Structure):
@@ -117,6 +118,11 @@ SYMBOLS = {
     "lctp_prefilter_plan_check": (C.c_int, [C.c_uint32, C.c_uint32, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P, _P, _P]),
     "lctp_pair_alignments": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P]),
     "lctp_sizeof_mates": (C.c_size_t, []),
+    "lctp_pair_alignments_dev": (C.c_int, [_P, _P, _P, _P]),
+    "lctp_pairs_fetch": (C.c_int, [_P, C.c_uint64, _P, _P, _P, _P, _P, _P]),
+    "lctp_pairs_count": (C.c_uint64, [_P]),
+    "lctp_pairs_free": (None, [_P]),
+    "lctp_locus_upload_pairs": (C.c_int, [_P, _P, _P, _P]),
     "lctp_rescore_alignments": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "lctp_sizeof_alns": (C.c_size_t, []),
     "lctp_locus_upload": (C.c_int, [_P, _P, _P]),

@@ -229,8 +229,10 @@ class Context:
         ffi.check(self.lib.lctp_measure_fp64_rate(self._h, C.byref(v)))
         return float(v.value)
 
-    def upload(self, loc: Locus) -> "DeviceLocus":
-        return DeviceLocus(self, loc)
+    def upload(self, loc: Locus, pairs: Optional["DevicePairs"] = None) -> "DeviceLocus":
+        """lctp_locus_upload; with `pairs` (lctp_locus_upload_pairs) the pa_* / unmapped_prob arrays of `loc` are
+        ignored and the device-resident pair alignments are used instead."""
+        return DeviceLocus(self, loc, pairs)
 
     def close(self) -> None:
         if self._h:
@@ -263,6 +265,10 @@ class Mates:
     prob_diff: float
     read_weight: Optional[np.ndarray] = None
     max_alns: int = 10
+    single_end: bool = False                      # identify_single_end_alignments (locs.rs:870-911)
+    window: int = 0                               # window size, with explicit weights
+    exp_off: Optional[np.ndarray] = None          # u64[H+1]: explicit region weights per contig position
+    exp_weight: Optional[np.ndarray] = None       # f64 (contig_len + 1 entries per contig)
 
     def to_c(self, keep: list, struct=None):
         def arr(a, dt):
@@ -282,6 +288,9 @@ class Mates:
         m.read_weight = arr(self.read_weight, np.float64)
         m.ins_ln_pmf = arr(self.ins_ln_pmf, np.float64)
         m.unmapped_penalty, m.insert_penalty, m.prob_diff = self.unmapped_penalty, self.insert_penalty, self.prob_diff
+        m.single_end, m.window = int(self.single_end), int(self.window)
+        m.exp_off = arr(self.exp_off, np.uint64)
+        m.exp_weight = arr(self.exp_weight, np.float64)
         return m
 
 
@@ -305,6 +314,42 @@ def pair_alignments(ctx: "Context", mates: Mates, cap: Optional[int] = None) -> 
     n = int(n_out.value)
     return dict(pa_off=pa_off, pa_contig=pa_contig[:n].copy(), pa_ln_prob=pa_ln_prob[:n].copy(),
                 pa_mid1=pa_mid1[:n].copy(), pa_mid2=pa_mid2[:n].copy(), unmapped_prob=unm)
+
+
+class DevicePairs:
+    """lctp_pairs_h: the pair alignments of a locus, resident on the device (lctp_pair_alignments_dev).  Feed it to
+    `Context.upload(loc, pairs=...)` instead of the pa_* arrays; `fetch()` copies it to the host when needed."""
+
+    def __init__(self, ctx: "Context", mates: Mates):
+        self.ctx, self.lib, self.n_reads = ctx, ctx.lib, mates.n_reads
+        keep: list = []
+        m = mates.to_c(keep)
+        self._h = C.c_void_p()
+        n = C.c_uint64(0)
+        ffi.check(self.lib.lctp_pair_alignments_dev(ctx._h, C.byref(m), C.byref(self._h), C.byref(n)))
+        self.n_pairs = int(n.value)
+
+    def fetch(self) -> dict:
+        R, n = self.n_reads, self.n_pairs
+        pa_off = np.zeros(R + 1, dtype=np.uint64)
+        con, lp = np.zeros(max(1, n), dtype=np.uint32), np.zeros(max(1, n))
+        m1, m2 = np.zeros(max(1, n), dtype=np.uint32), np.zeros(max(1, n), dtype=np.uint32)
+        unm = np.zeros(R)
+        ffi.check(self.lib.lctp_pairs_fetch(self._h, n, pa_off.ctypes.data, con.ctypes.data, lp.ctypes.data,
+                                            m1.ctypes.data, m2.ctypes.data, unm.ctypes.data))
+        return dict(pa_off=pa_off, pa_contig=con[:n].copy(), pa_ln_prob=lp[:n].copy(), pa_mid1=m1[:n].copy(),
+                    pa_mid2=m2[:n].copy(), unmapped_prob=unm)
+
+    def free(self) -> None:
+        if self._h:
+            self.lib.lctp_pairs_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 @dataclass
@@ -461,12 +506,15 @@ class Genotyping:
 class DeviceLocus:
     """lctp_locus_h: a locus resident in HBM."""
 
-    def __init__(self, ctx: Context, loc: Locus):
+    def __init__(self, ctx: Context, loc: Locus, pairs: Optional["DevicePairs"] = None):
         self.ctx, self.loc, self.lib = ctx, loc, ctx.lib
         self._keep: list = []
         self.c = locus_to_c(loc, self._keep)
         self._h = C.c_void_p()
-        ffi.check(self.lib.lctp_locus_upload(ctx._h, C.byref(self.c), C.byref(self._h)))
+        if pairs is None:
+            ffi.check(self.lib.lctp_locus_upload(ctx._h, C.byref(self.c), C.byref(self._h)))
+        else:
+            ffi.check(self.lib.lctp_locus_upload_pairs(ctx._h, C.byref(self.c), pairs._h, C.byref(self._h)))
 
     def free(self) -> None:
         if self._h:

@@ -243,6 +243,10 @@ typedef struct lcto_mates {
     const double   *read_weight; /* [R] or NULL (= 1.0) */
     const double   *ins_ln_pmf;  /* [ins_len] InsertDistr::ln_prob(size) */
     double unmapped_penalty, insert_penalty, prob_diff;
+    uint32_t single_end;         /* identify_single_end_alignments, src/model/locs.rs:870-911 */
+    uint32_t window;             /* ContigInfo::window_size (explicit weights) */
+    const uint64_t *exp_off;     /* [H+1] explicit weights per contig position (ExplicitWeights::at), or NULL */
+    const double   *exp_weight;
 } lcto_mates;
 
 /* identify_paired_end_alignments for every read (src/model/locs.rs:805-868). Outputs are the `pa_*` /

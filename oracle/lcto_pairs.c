@@ -19,8 +19,8 @@
  * restated.  The per-contig sort of the candidate pairs (locs.rs:793) IS restated, as a STABLE descending
  * sort by f64::total_cmp in generation order (Rust's sort_unstable on <= 20 elements is an insertion sort;
  * longer lists can only differ between exactly tied ln-probs -- "parity unpinned", like the rest of lcto).
- * Explicit region weights (ContigInfos::explicit_read_weight, src/model/windows.rs:619-629) are not part
- * of this row: the weight is read_weight[r] alone.
+ *   identify_single_end_alignments  src/model/locs.rs:870-911   (per contig: within prob_diff of the best, <= max_alns)
+ *   ContigInfos::explicit_read_weight src/model/windows.rs:683-693, ContigInfo::read_end_weight :495-504
  */
 #include "lcto.h"
 
@@ -82,8 +82,69 @@ static int contig_pairs(const lcto_mates *in, uint64_t i, uint64_t j, uint64_t k
     return (int)keep;
 }
 
+/* ContigInfo::read_end_weight (windows.rs:495-504) */
+static double read_end_weight(const lcto_mates *in, uint32_t contig, uint32_t middle) {
+    if (middle == LCTO_NONE_U32) return 0.0;
+    const double *w = in->exp_weight + in->exp_off[contig];
+    const uint32_t n = (uint32_t)(in->exp_off[contig + 1] - in->exp_off[contig]);
+    const uint32_t u = in->window / 2;
+    double v = w[middle];
+    const double a = w[middle > u ? middle - u : 0u];           /* i.saturating_sub(u) */
+    const double b = w[middle + u < n - 1 ? middle + u : n - 1];
+    if (a > v) v = a;                                            /* f64::max */
+    if (b > v) v = b;
+    return v;
+}
+
+/* tail of identify_{paired,single}_end_alignments: weight = read weight * explicit_read_weight, scale, unmapped_prob */
+static void finish_read(const lcto_mates *in, uint32_t r, uint64_t b, uint64_t e, const uint32_t *pa_contig,
+                        double *pa_ln_prob, const uint32_t *pa_mid1, const uint32_t *pa_mid2, double *unmapped_prob) {
+    double expl = 1.0;
+    if (in->exp_weight) {                                        /* explicit_read_weight, windows.rs:683-693 */
+        double s = 0.0;
+        for (uint64_t q = b; q < e; q++) {
+            const double w1 = read_end_weight(in, pa_contig[q], pa_mid1[q]), w2 = read_end_weight(in, pa_contig[q], pa_mid2[q]);
+            s += w1 > w2 ? w1 : w2;
+        }
+        expl = s / (double)(e - b);
+    }
+    const double weight = (in->read_weight ? in->read_weight[r] : 1.0) * expl;
+    for (uint64_t q = b; q < e; q++) pa_ln_prob[q] *= weight;                        /* locs.rs:861-863, 905-907 */
+    unmapped_prob[r] = in->single_end ? weight * in->unmapped_penalty                 /* locs.rs:909 */
+                                      : weight * (2.0 * in->unmapped_penalty + in->insert_penalty);   /* locs.rs:866 */
+}
+
+/* identify_single_end_alignments (locs.rs:870-911) for every read */
+static int single_end_alignments(const lcto_mates *in, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig,
+                                 double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob) {
+    uint64_t n_out = 0;
+    for (uint32_t r = 0; r < in->n_reads; r++) {
+        pa_off[r] = n_out;
+        int have = 0;
+        uint32_t curr_contig = 0, curr_saved = 0;
+        double thresh = NAN;
+        for (uint64_t a = in->ma_off[r]; a < in->ma_off[r + 1]; a++) {
+            if (!have || curr_contig != in->ma_contig[a]) {
+                have = 1; curr_contig = in->ma_contig[a];
+                thresh = in->ma_ln_prob[a] - in->prob_diff;
+                curr_saved = 0;
+            }
+            if (in->ma_ln_prob[a] >= thresh && curr_saved < in->max_alns) {
+                if (n_out >= cap) return -3;
+                pa_contig[n_out] = curr_contig; pa_ln_prob[n_out] = in->ma_ln_prob[a];
+                pa_mid1[n_out] = (in->ma_start[a] + in->ma_end[a]) / 2; pa_mid2[n_out] = LCTO_NONE_U32;
+                n_out++; curr_saved++;
+            }
+        }
+        finish_read(in, r, pa_off[r], n_out, pa_contig, pa_ln_prob, pa_mid1, pa_mid2, unmapped_prob);
+    }
+    pa_off[in->n_reads] = n_out;
+    return 0;
+}
+
 int lcto_pair_alignments(const lcto_mates *in, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig,
                          double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob) {
+    if (in->single_end) return single_end_alignments(in, cap, pa_off, pa_contig, pa_ln_prob, pa_mid1, pa_mid2, unmapped_prob);
     const uint32_t M = in->max_alns;
     pair_cand *cands = (pair_cand *)malloc(sizeof(pair_cand) * ((size_t)M * M + 2 * M));
     pair_cand *kept = (pair_cand *)malloc(sizeof(pair_cand) * M);
@@ -94,7 +155,6 @@ int lcto_pair_alignments(const lcto_mates *in, uint64_t cap, uint64_t *pa_off, u
     uint64_t n_out = 0;
     int rc = 0;
     for (uint32_t r = 0; r < in->n_reads && rc == 0; r++) {
-        const double weight = in->read_weight ? in->read_weight[r] : 1.0;
         pa_off[r] = n_out;
         uint64_t a = in->ma_off[r];
         const uint64_t end = in->ma_off[r + 1];
@@ -125,14 +185,14 @@ int lcto_pair_alignments(const lcto_mates *in, uint64_t cap, uint64_t *pa_off, u
             if (n_out + (uint64_t)keep > cap) { rc = -3; break; }
             for (int q = 0; q < keep; q++) {
                 pa_contig[n_out] = contig;
-                pa_ln_prob[n_out] = kept[q].ln_prob * weight;                       /* locs.rs:861-863 */
+                pa_ln_prob[n_out] = kept[q].ln_prob;
                 pa_mid1[n_out] = kept[q].mid1;
                 pa_mid2[n_out] = kept[q].mid2;
                 n_out++;
             }
             a = b;
         }
-        unmapped_prob[r] = weight * (2.0 * in->unmapped_penalty + insert_penalty);  /* locs.rs:866 */
+        if (rc == 0) finish_read(in, r, pa_off[r], n_out, pa_contig, pa_ln_prob, pa_mid1, pa_mid2, unmapped_prob);
     }
     pa_off[in->n_reads] = n_out;
     free(cands); free(kept); free(buffer); free(sel);

@@ -419,7 +419,8 @@ class MatesC(C.Structure):
                 ("ma_off", C.c_void_p), ("ma_contig", C.c_void_p), ("ma_flags", C.c_void_p), ("ma_start", C.c_void_p),
                 ("ma_end", C.c_void_p), ("ma_ln_prob", C.c_void_p), ("read_weight", C.c_void_p),
                 ("ins_ln_pmf", C.c_void_p),
-                ("unmapped_penalty", C.c_double), ("insert_penalty", C.c_double), ("prob_diff", C.c_double)]
+                ("unmapped_penalty", C.c_double), ("insert_penalty", C.c_double), ("prob_diff", C.c_double),
+                ("single_end", C.c_uint32), ("window", C.c_uint32), ("exp_off", C.c_void_p), ("exp_weight", C.c_void_p)]
 
 
 def pair_alignments(mates) -> dict:

@@ -58,6 +58,65 @@ def _python_reference(m: genotype.Mates) -> dict:
                 unmapped_prob=np.array(unm))
 
 
+def _python_single_end(m: genotype.Mates) -> dict:
+    """identify_single_end_alignments (src/model/locs.rs:870-911) + explicit_read_weight, statement by statement."""
+    off, con, lp, m1, m2, unm = [0], [], [], [], [], []
+    for r in range(m.n_reads):
+        curr, thresh, saved, start = None, math.nan, 0, len(con)
+        for a in range(int(m.ma_off[r]), int(m.ma_off[r + 1])):
+            if curr != m.ma_contig[a]:
+                curr, thresh, saved = m.ma_contig[a], float(m.ma_ln_prob[a]) - m.prob_diff, 0
+            if float(m.ma_ln_prob[a]) >= thresh and saved < m.max_alns:
+                con.append(curr); lp.append(float(m.ma_ln_prob[a]))
+                m1.append((int(m.ma_start[a]) + int(m.ma_end[a])) // 2); m2.append(NONE)
+                saved += 1
+        w = (1.0 if m.read_weight is None else float(m.read_weight[r])) * _python_explicit(m, con[start:], m1[start:], m2[start:])
+        for q in range(start, len(con)):
+            lp[q] *= w
+        off.append(len(con))
+        unm.append(w * m.unmapped_penalty)
+    return dict(pa_off=np.array(off, dtype=np.uint64), pa_contig=np.array(con, dtype=np.uint32),
+                pa_ln_prob=np.array(lp), pa_mid1=np.array(m1, dtype=np.uint32), pa_mid2=np.array(m2, dtype=np.uint32),
+                unmapped_prob=np.array(unm))
+
+
+def _python_explicit(m, con, mid1, mid2) -> float:
+    """ContigInfos::explicit_read_weight (src/model/windows.rs:683-693) with read_end_weight (:495-504)."""
+    if m.exp_weight is None:
+        return 1.0
+
+    def rew(c, mid):
+        if mid == NONE:
+            return 0.0
+        w = m.exp_weight[int(m.exp_off[c]):int(m.exp_off[c + 1])]
+        u = m.window // 2
+        return max(float(w[mid]), float(w[max(mid - u, 0)]), float(w[min(mid + u, len(w) - 1)]))
+    s = 0.0
+    for c, a, b in zip(con, mid1, mid2):
+        s += max(rew(c, a), rew(c, b))
+    return s / len(con) if len(con) else math.nan
+
+
+def _single_end(H, R, L, seed):
+    """Single-end records: every record a first-end record, per (read, contig) in descending ln_prob."""
+    kw = synth.make_mates(H, R, L, seed, multi_frac=0.4, over_cap_frac=0.05)
+    first = (kw["ma_flags"] & 1) == 0
+    cnt = np.array([first[int(kw["ma_off"][r]):int(kw["ma_off"][r + 1])].sum() for r in range(R)])
+    for f in ("ma_contig", "ma_flags", "ma_start", "ma_end", "ma_ln_prob"):
+        kw[f] = kw[f][first]
+    kw["ma_off"] = np.r_[0, np.cumsum(cnt)].astype(np.uint64)
+    kw["single_end"] = True
+    return kw
+
+
+def _explicit_weights(H, L, seed, window=100):
+    rng = np.random.default_rng(seed)
+    lens = np.full(H, L + 1)
+    off = np.r_[0, np.cumsum(lens)].astype(np.uint64)
+    w = np.repeat(rng.choice([1.0, 1.0, 0.5, 2.0, 0.0], size=(H * (L + 1)) // 50 + 1), 50)[:int(off[-1])]
+    return dict(exp_off=off, exp_weight=np.ascontiguousarray(w, dtype=np.float64), window=window)
+
+
 def _same(a: dict, b: dict):
     for k in ("pa_off", "pa_contig", "pa_mid1", "pa_mid2", "pa_ln_prob", "unmapped_prob"):
         assert np.array_equal(a[k], b[k]), k
@@ -67,6 +126,65 @@ def _same(a: dict, b: dict):
 def test_oracle_pairing_equals_python_transcription(oracle, H, R, seed, multi):
     m = genotype.Mates(**synth.make_mates(H, R, 4000, seed, multi_frac=multi, over_cap_frac=0.05))
     _same(oracle.pair_alignments(m), _python_reference(m))
+
+
+@pytest.mark.parametrize("H,R,seed", [(5, 40, 11), (12, 25, 12)])
+def test_oracle_single_end_and_explicit_weights_equal_python_transcription(oracle, H, R, seed):
+    m = genotype.Mates(**_single_end(H, R, 4000, seed))
+    _same(oracle.pair_alignments(m), _python_single_end(m))
+    me = genotype.Mates(**_single_end(H, R, 4000, seed), **_explicit_weights(H, 4000, seed))
+    _same(oracle.pair_alignments(me), _python_single_end(me))
+    # paired-end reads with explicit weights: the paired transcription, rescaled per read
+    kw = synth.make_mates(H, R, 4000, seed, multi_frac=0.3)
+    mp = genotype.Mates(**kw, **_explicit_weights(H, 4000, seed + 1))
+    got = oracle.pair_alignments(mp)
+    base = _python_reference(genotype.Mates(**{**kw, "read_weight": None}))
+    for r in range(R):
+        b, e = int(base["pa_off"][r]), int(base["pa_off"][r + 1])
+        w = float(kw["read_weight"][r]) * _python_explicit(mp, base["pa_contig"][b:e], base["pa_mid1"][b:e], base["pa_mid2"][b:e])
+        assert np.array_equal(got["pa_ln_prob"][b:e], base["pa_ln_prob"][b:e] * w)
+        assert got["unmapped_prob"][r] == w * (2.0 * mp.unmapped_penalty + mp.insert_penalty)
+    assert np.array_equal(got["pa_off"], base["pa_off"]) and np.array_equal(got["pa_mid1"], base["pa_mid1"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,R,seed", [(5, 40, 11), (12, 25, 12), (60, 500, 13)])
+def test_device_single_end_and_explicit_weights_bit_exact(oracle, gpu_ctx, H, R, seed):
+    for m in (genotype.Mates(**_single_end(H, R, 4000, seed)),
+              genotype.Mates(**_single_end(H, R, 4000, seed), **_explicit_weights(H, 4000, seed)),
+              genotype.Mates(**synth.make_mates(H, R, 4000, seed, multi_frac=0.3), **_explicit_weights(H, 4000, seed + 1))):
+        _same(genotype.pair_alignments(gpu_ctx, m), oracle.pair_alignments(m))
+    bad = genotype.Mates(**{**synth.make_mates(H, R, 4000, seed), "single_end": True})      # second-end records
+    with pytest.raises(Exception):
+        genotype.pair_alignments(gpu_ctx, bad)
+
+
+@pytest.mark.gpu
+def test_device_resident_pairs_feed_the_locus_without_a_host_round_trip(oracle, gpu_ctx, small_locus):
+    """lctp_pair_alignments_dev -> lctp_locus_upload_pairs: the pa_* section never visits the host; matrix, prefilter
+    and a solver stage equal the host-array path and the oracle."""
+    import copy
+    loc = copy.copy(small_locus)
+    m = genotype.Mates(**synth.make_mates(loc.n_haps, loc.n_reads, 2500, 77, multi_frac=0.3))
+    dp = genotype.DevicePairs(gpu_ctx, m)
+    out = dp.fetch()
+    _same(out, oracle.pair_alignments(m))
+    loc.pa_off, loc.pa_contig, loc.pa_ln_prob = out["pa_off"], out["pa_contig"], out["pa_ln_prob"]
+    loc.pa_mid1, loc.pa_mid2, loc.unmapped_prob = out["pa_mid1"], out["pa_mid2"], out["unmapped_prob"]
+    ol = oracle.OracleLocus(loc)
+    blank = copy.copy(loc)                   # the same locus WITHOUT its pair-alignment section
+    blank.pa_off = blank.pa_contig = blank.pa_ln_prob = blank.pa_mid1 = blank.pa_mid2 = blank.unmapped_prob = None
+    dl = gpu_ctx.upload(blank, pairs=dp)
+    dp.free()                                # the locus owns its copy
+    assert np.array_equal(dl.best_aln_matrix(), oracle.best_aln_matrix(ol))
+    assert np.array_equal(dl.prefilter_scores(), oracle.prefilter_scores(ol))
+    scheme = genotype.Scheme.parse(["greedy:i=50,a=2"])
+    r1, r2 = genotype.init_rng(5), oracle.Rng.from_seed(5)
+    got = dl.solve(scheme, 8, r1)
+    ref = oracle.solve(ol, [oracle.Stage("greedy", attempts=2, in_size=50)], 8, r2, os_threads=2)
+    assert np.array_equal(got.gt_ix, ref["gt_ix"]) and np.array_equal(got.lik_mean, ref["lik_mean"])
+    assert got.unexpl_reads == ref["unexpl_reads"] and list(r1) == r2.state()
+    dl.free()
 
 
 def test_oracle_pairing_hand_checked_case(oracle):
