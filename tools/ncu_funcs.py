@@ -21,17 +21,11 @@ def fn_of(line):
         if s <= line: name = n
         else: break
     return name
-tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "locityper_b200/_lib/liblctp.so")], cwd=tmp, capture_output=True)
-sass = ""
-for f in os.listdir(tmp):
-    out = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
-    if kern in out and "solver" in f:
-        sass = out
+from ncu_common import sass_sections
+sass_lines = sass_sections(rep, kern, ("-gi", "-c"))
 chain, off2path, infunc, pending = [], {}, False, []
-for ln in sass.split("\n"):
-    if ".text." in ln:
-        infunc = kern in ln
+infunc = True
+for ln in sass_lines:
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
         pending.append(int(m.group(2)) if m.group(1).endswith("solver.cu") else -1)

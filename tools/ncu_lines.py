@@ -5,17 +5,11 @@ rep = sys.argv[1]
 kern = sys.argv[2] if len(sys.argv) > 2 else "k_solve_stage"
 iters = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "locityper_b200/_lib/liblctp.so")], cwd=tmp, capture_output=True)
-sass = ""
-for f in os.listdir(tmp):
-    out = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
-    if kern in out:
-        sass = out
+from ncu_common import sass_sections
+sass_lines = sass_sections(rep, kern, ("-g", "-c"))
 cur, off2line, infunc = None, {}, False
-for ln in sass.split("\n"):
-    if ".text." in ln and kern in ln:
-        infunc = True
+infunc = True
+for ln in sass_lines:
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
         cur = (os.path.basename(m.group(1)), int(m.group(2)))
