@@ -216,7 +216,7 @@ __device__ __noinline__ void fill_block(uint64_t *buf, uint64_t *blk, const ulon
         ulonglong2 v;
         v.x = gen_next(gen);
         v.y = gen_next(gen);
-        __stcg(o + q, v);
+        o[q] = v;      // plain store: the greedy pipeline reads the draws with L1-cached 4-byte cp.async
     }
     __syncwarp();
 }
@@ -1018,94 +1018,6 @@ __device__ __forceinline__ bool cand_better(const Cand<WIDE> &a, const Cand<WIDE
     return job_c(a.job) < job_c(b.job);
 }
 
-// Prefetch pipeline of the greedy loop.  The jobs of an iteration -- every (sampled read, alternative candidate)
-// pair, "flattened" best_read_improvement (src/model/assgn.rs:287-317) -- are dealt to the lanes by an exclusive
-// prefix sum over the sampled reads' alternative counts, so that (almost always) ONE evaluation pass covers the
-// whole sample whatever the candidate counts are.  A job's data is two dependent hops away (private candidate
-// records + the read's run offsets, then the shared ln-probabilities), so samples are drawn three iterations
-// ahead and move through four stages, one per loop round:
-//   S  sample drawn, the read ids of the sampled non-trivial reads in flight
-//   A  jobs dealt, first-hop loads in flight
-//   B  second-hop loads in flight
-//   C  evaluated: touches only registers and shared memory
-// The loop body has exactly one site for each group of loads (a stage that has nothing to do is skipped, an empty
-// pipeline refills through the same code), so that the hardware scoreboard slots of one group never alias
-// another's: with several code paths issuing the same loads the evaluation waited on loads issued a few
-// instructions earlier (ncu: 10 % of the kernel in one DADD).
-template <bool WIDE>
-struct SlotA {
-    uint32_t job;               // this lane's job (valid for lanes < min(total, 32))
-    typename RecWord<WIDE>::T ro, rn;   // records of the current / this lane's alternative candidate
-    uint32_t b0, b1;            // cm_off of the read on the genotype's first two haplotypes
-    uint32_t lead;              // lanes < amount: sampled non-trivial read index | first job position << 16
-    uint32_t total;             // jobs of the sample (warp-uniform)
-};
-template <bool WIDE>
-struct SlotB {
-    uint32_t job, lead, total;
-    typename RecWord<WIDE>::T ro, rn;
-    double lpo, lpn;
-};
-
-// Deal the jobs of the sample `myv` (lane k < amount holds the k-th sampled read) and issue the first-hop loads.
-template <bool WIDE>
-__device__ __forceinline__ void load_slot_a(const LocusDev &L, const Slab<WIDE> &S, const Instance &I,
-                                            const WarpShared &ws, uint32_t amount, uint32_t myv, uint2 linfo,
-                                            SlotA<WIDE> &x) {
-    const uint32_t lane = ws.lane;
-    const bool lead = lane < amount;
-    const uint32_t n_alt = lead ? (linfo.x >> 16) - 1u : 0u;
-    uint32_t incl = n_alt;
-#pragma unroll
-    for (int d = 1; d < 16; d <<= 1) {              // amount <= 11: four rounds
-        const uint32_t t = __shfl_up_sync(FULL, incl, d);
-        if (lane >= (uint32_t)d) incl += t;
-    }
-    x.total = wshfl(incl, (int)amount - 1);
-    const uint32_t first = incl - n_alt;
-    x.lead = myv | (first << 16);
-    const unsigned starts = __reduce_or_sync(FULL, (lead && first < 32u) ? (1u << first) : 0u);
-    const uint32_t slot = (uint32_t)__popc(starts & (0xFFFFFFFFu >> (31u - lane))) - 1u;   // starts has bit 0 set
-    const uint32_t r = wshfl(linfo.y, (int)slot);
-    const uint32_t on = wshfl(linfo.x, (int)slot);
-    const uint32_t alt = lane - wshfl(first, (int)slot);
-    const uint32_t o = on & 0xFFFFu, n = on >> 16;
-    const uint32_t a = ws.assgn[r];
-    const uint32_t c = min(alt_rank(alt, a), n - 1u);     // lanes >= total: clamped, loaded, never evaluated
-    x.job = r | (slot << 16) | (c << 24);
-    x.ro = S.rec[o + a];
-    x.rn = S.rec[o + c];
-    x.b0 = __ldg(L.cm_off + (size_t)I.h0 * L.R + r);
-    x.b1 = L.p > 1 ? __ldg(L.cm_off + (size_t)I.h1 * L.R + r) : 0u;
-}
-template <bool WIDE>
-__device__ __forceinline__ void load_slot_b(const LocusDev &L, const Instance &I, const WarpShared &ws,
-                                            const SlotA<WIDE> &x, SlotB<WIDE> &y) {
-    typedef RecWord<WIDE> RW;
-    y.job = x.job; y.ro = x.ro; y.rn = x.rn; y.lead = x.lead; y.total = x.total;
-    const uint32_t r = job_r(x.job);
-    uint32_t io, in;
-    if (L.p <= 2) { io = lp_index2(L, r, RW::src(x.ro), x.b0, x.b1); in = lp_index2(L, r, RW::src(x.rn), x.b0, x.b1); }
-    else { io = lp_index(L, I, ws, r, RW::src(x.ro)); in = lp_index(L, I, ws, r, RW::src(x.rn)); }
-    y.lpo = __ldg(L.cm_lnprob + io);
-    y.lpn = __ldg(L.cm_lnprob + in);
-}
-// A move of read w_r was applied: the in-flight jobs on that read saw its old assignment.
-template <bool WIDE>
-__device__ __forceinline__ void reload_slot_a(const Slab<WIDE> &S, const WarpShared &ws, uint32_t w_r, uint32_t old_a,
-                                              SlotA<WIDE> &x) {
-    if (job_r(x.job) == w_r) {
-        const uint32_t o = ws.off[w_r], n = (uint32_t)ws.off[w_r + 1] - o, a = ws.assgn[w_r];
-        // this lane's alternative number: invert alt_rank under the old assignment, redo it under the new one
-        const uint32_t c_old = job_c(x.job);
-        const uint32_t alt = c_old > old_a ? c_old - 1u : c_old;
-        const uint32_t c = min(alt_rank(alt, a), n - 1u);
-        x.job = (x.job & 0x00FFFFFFu) | (c << 24);
-        x.ro = S.rec[o + a];
-        x.rn = S.rec[o + c];
-    }
-}
-
 template <bool WIDE>
 __device__ __forceinline__ void eval_cand(const LocusDev &L, const WarpShared &ws, double lp_old, double lp,
                                           typename RecWord<WIDE>::T raw_old, typename RecWord<WIDE>::T raw_new,
@@ -1129,10 +1041,18 @@ __device__ __noinline__ uint32_t sample_resolve_seq(uint32_t n_nt, uint32_t amou
     return myv;
 }
 
+// The register part of a sample in flight: this lane's job, the sample's layout.
+struct JobRegs {
+    uint32_t job;               // read id | slot << 16 | candidate rank << 24 (valid for lanes < min(total, 32))
+    uint32_t lead;              // lanes < amount: sampled non-trivial read index | first job position << 16
+    uint32_t total;             // jobs of the sample (warp-uniform)
+};
+
 template <bool WIDE>
 __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab<WIDE> &S, const Instance &I,
                              const WarpShared &ws, Xo &rng) {
     typedef RecWord<WIDE> RW;
+    typedef typename RW::T Rec;
     const uint32_t lane = ws.lane;
     const uint32_t amount = min(P.sample_size, I.n_nt);
     init_assignment<WIDE>(L, S, I, ws, rng, P.best_start ? 0 : 1);
@@ -1149,13 +1069,17 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
     const uint32_t plato_size = (uint32_t)P.plato_size, max_iter = (uint32_t)P.max_iter;
     // The sample pipeline.  A sample takes `amount` consecutive draws of the worker's stream (Floyd: draw k is
     // random_range(..=n_nt - amount + k)); it moves through five stages, one per loop round:
-    //   S0  the raw draws are fetched straight from the worker's pre-generated buffer (one 32-bit load per lane)
-    //   S1  bounded values; MATCH.ANY looks for equal draws and the index entries of the sampled reads are fetched
-    //       -- both results are first looked at a round later, so their latency (~250 cycles each) is never waited for
-    //   A   duplicates resolved (5 % of the samples: sequential path + index entries fetched again), jobs dealt,
-    //       first-hop loads in flight
-    //   B   second-hop loads in flight
-    //   C   evaluated
+    //   S0  the raw draws are fetched from the worker's pre-generated buffer
+    //   S1  bounded values; MATCH.ANY looks for equal draws, the index entries of the sampled reads are fetched
+    //   A   duplicates resolved (5 % of the samples: sequential path, index entries fetched again), jobs dealt:
+    //       every (sampled read, alternative candidate) pair -- "flattened" best_read_improvement
+    //       (src/model/assgn.rs:287-317) -- gets a lane by an exclusive prefix sum over the reads' alternative
+    //       counts, so that (almost always) ONE evaluation pass covers the sample; first-hop loads (the private
+    //       candidate records, the read's run offsets)
+    //   B   second-hop loads (the shared ln-probabilities)
+    //   C   evaluated: touches only registers and shared memory
+    // A round is: C; wait for the copies issued in the previous round (a whole stage C ago); pick up their results
+    // and compute every address; issue the copies of all stages back to back.
     // dpos = stream position behind the last fetched sample.  A sample that would need a bias-correction draw, or
     // that does not fit in the current fill, is not fetched: the pipeline drains and the sample is drawn one draw
     // at a time (refill, bias correction) on the empty pipeline -- the samples in flight are given back to the
@@ -1164,20 +1088,27 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
     const uint32_t my_range = n_nt - amount + min(lane, amount - 1u) + 1u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t *draw_hi = (const uint32_t *)rng.buf + 1 + 2u * min(lane, amount - 1u);   // next_u32 = upper half
+    // What the loads of a round deliver; each is defined at exactly ONE place (the load) and first read a round later.
+    // A second definition on some rare path would make the compiler merge the two at a join with a register move,
+    // which waits for the load right behind its issue (ncu: 6 % of the kernel in one such move at the loop top).
+    uint32_t f_raw = 0;                 // S0: upper half of the raw draw
+    uint2 f_info = ws.ntinfo[0];        // S1: index entry of the sampled read (lanes < amount)
+    Rec f_ro = 0, f_rn = 0;             // A: records of the job's current candidate / of its alternative
+    uint32_t f_b0 = 0, f_b1 = 0;        //    cm_off of the job's read on the first two haplotypes
+    double f_lpo = 0.0, f_lpn = 0.0;    // B: their ln-probabilities
     uint32_t dpos = rng.pos;
-    bool blocked = false;
+    bool blocked = false, slow = false;
     bool v0 = false, v1 = false, vA = false, vB = false, vC = false;
-    uint32_t raw_hi = 0;                // S0
     uint32_t s_v = 0;                   // S1: sampled index (lanes < amount) ...
-    unsigned s_match = 0;               //     ... lanes holding the same value ...
-    uint2 s_info = nt_info(ws, 0);      //     ... and what the index says about that read
+    bool s_dup = false;                 //     ... two of its draws are equal (Floyd's replacement needed)
+    JobRegs ja, jb;                     // samples in stages A and B
+    ja.job = ja.lead = ja.total = 0; jb = ja;
+    Rec b_ro = 0, b_rn = 0;             // stage B: the records of its jobs
+    struct { uint32_t job, lead, total; Rec ro, rn; double lpo, lpn; } cur;   // stage C
+    cur.job = cur.lead = cur.total = 0; cur.ro = cur.rn = 0; cur.lpo = cur.lpn = 0.0;
     __syncwarp();
-    SlotA<WIDE> sa;
-    SlotB<WIDE> sb, cur;
-    sa.job = sa.b0 = sa.b1 = sa.lead = sa.total = 0; sa.ro = sa.rn = 0;
-    sb.job = sb.lead = sb.total = 0; sb.ro = sb.rn = 0; sb.lpo = sb.lpn = 0.0;
-    cur = sb;
     for (;;) {
+        uint32_t mv_r = 0xFFFFFFFFu, mv_old = 0;     // read moved by this round's stage C
         if (vC) {
             // ---- stage C: evaluate the sample of this iteration
             Cand<WIDE> best;
@@ -1199,7 +1130,7 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
                         const uint2 inf = nt_info(ws, idx);
                         const uint32_t r = inf.y, o = inf.x & 0xFFFFu, a = ws.assgn[r];
                         const uint32_t c = alt_rank(f0 + lane - sfirst, a);
-                        const typename RW::T ro = S.rec[o + a], rn = S.rec[o + c];
+                        const Rec ro = S.rec[o + a], rn = S.rec[o + c];
                         const double lpo = __ldg(L.cm_lnprob + lp_index(L, I, ws, r, RW::src(ro)));
                         const double lpn = __ldg(L.cm_lnprob + lp_index(L, I, ws, r, RW::src(rn)));
                         Cand<WIDE> cd;
@@ -1233,7 +1164,7 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
             }
             it++;
             // the winning lane decides and applies its own move (reassign, src/model/assgn.rs:331-343): nothing but
-            // the four windows and the job word has to reach the other lanes, and that goes through shared memory
+            // the four windows and the moved read has to reach the other lanes, and that goes through shared memory
             if (wany((int)lane == wl && best.s > *v_min_diff)) {
                 if ((int)lane == wl) {
                     const uint32_t w1 = RW::w1(best.raw_old), w2 = RW::w2(best.raw_old);
@@ -1251,75 +1182,128 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
                     ws.samp[4] = w_r; ws.samp[5] = old_a;
                 }
                 __syncwarp();
-                const uint32_t w_r = ws.samp[4], old_a = ws.samp[5];
+                mv_r = ws.samp[4]; mv_old = ws.samp[5];
                 // slide the product slices of the (up to four) windows whose depth changed
                 if (lane < 20u) win_refresh(ws, L.depth_table, ws.samp[lane / 5u], (int)(lane % 5u));
                 __syncwarp();
                 curr_plato = 0;
-                // samples in flight saw the old assignment of the moved read: redo their loads (rare)
-                if (__builtin_expect(vB && wany(lane < sb.total && job_r(sb.job) == w_r), 0)) {
-                    SlotA<WIDE> t;
-                    t.job = sb.job; t.lead = sb.lead; t.total = sb.total; t.ro = sb.ro; t.rn = sb.rn;
-                    t.b0 = __ldg(L.cm_off + (size_t)I.h0 * L.R + job_r(sb.job));
-                    t.b1 = L.p > 1 ? __ldg(L.cm_off + (size_t)I.h1 * L.R + job_r(sb.job)) : 0u;
-                    const bool mine = job_r(sb.job) == w_r;
-                    reload_slot_a<WIDE>(S, ws, w_r, old_a, t);
-                    SlotB<WIDE> nb;
-                    load_slot_b<WIDE>(L, I, ws, t, nb);
-                    if (mine) sb = nb;
-                }
-                if (__builtin_expect(vA && wany(lane < sa.total && job_r(sa.job) == w_r), 0)) reload_slot_a<WIDE>(S, ws, w_r, old_a, sa);
             } else {
                 curr_plato += 1;
                 if (curr_plato > plato_size) break;
             }
             if (it >= max_iter) break;
         }
-        // ---- advance the pipeline by one stage.  Unconditionally: a stage that holds nothing valid (start-up, the
-        // rounds after the fill ran out) moves harmless stale values.  With the loads under `if (valid)` the compiler
-        // cannot see that last round's loads were consumed on every path and guards each re-issued load with a wait
-        // on its scoreboard slot -- the slot the loads issued just before it share (ncu: 7 % of the kernel).
-        cur = sb; vC = vB;
-        load_slot_b<WIDE>(L, I, ws, sa, sb);
+        // ---- pick up what last round's loads delivered, oldest first.  B -> C
+        cur.job = jb.job; cur.lead = jb.lead; cur.total = jb.total; cur.ro = b_ro; cur.rn = b_rn;
+        cur.lpo = f_lpo; cur.lpn = f_lpn;
+        vC = vB;
+        // ---- A -> B
+        jb = ja;
+        b_ro = f_ro; b_rn = f_rn;
+        const uint32_t b0 = f_b0, b1 = f_b1;
         vB = vA;
-        // ---- stage A: Floyd's replacements if two draws of the sample were equal, then deal the jobs
-        if (__builtin_expect(wany(v1 && lane < amount && (s_match & lt_mask) != 0u), 0)) {
-            s_v = sample_resolve_seq(n_nt, amount, s_v);
-            s_info = nt_info(ws, lane < amount ? s_v : 0u);
+        // samples in flight saw the old assignment of the read that stage C moved: redo their jobs on it (rare)
+        if (__builtin_expect(mv_r != 0xFFFFFFFFu, 1)) {
+            const bool hitC = vC && lane < cur.total && job_r(cur.job) == mv_r;
+            const bool hitB = vB && lane < jb.total && job_r(jb.job) == mv_r;
+            if (__builtin_expect(wany(hitC || hitB), 0)) {
+                const uint32_t o = ws.off[mv_r], n = (uint32_t)ws.off[mv_r + 1] - o, a = ws.assgn[mv_r];
+                // a lane's alternative number: invert alt_rank under the old assignment, redo it under the new one
+                if (hitC) {
+                    const uint32_t c_old = job_c(cur.job), alt = c_old > mv_old ? c_old - 1u : c_old;
+                    const uint32_t c = min(alt_rank(alt, a), n - 1u);
+                    cur.job = (cur.job & 0x00FFFFFFu) | (c << 24);
+                    cur.ro = S.rec[o + a]; cur.rn = S.rec[o + c];
+                    cur.lpo = __ldg(L.cm_lnprob + lp_index(L, I, ws, mv_r, RW::src(cur.ro)));
+                    cur.lpn = __ldg(L.cm_lnprob + lp_index(L, I, ws, mv_r, RW::src(cur.rn)));
+                }
+                if (hitB) {
+                    const uint32_t c_old = job_c(jb.job), alt = c_old > mv_old ? c_old - 1u : c_old;
+                    const uint32_t c = min(alt_rank(alt, a), n - 1u);
+                    jb.job = (jb.job & 0x00FFFFFFu) | (c << 24);
+                    b_ro = S.rec[o + a]; b_rn = S.rec[o + c];
+                }
+            }
         }
-        load_slot_a<WIDE>(L, S, I, ws, amount, s_v, s_info, sa);
-        vA = v1;
-        // ---- stage S1: bounded values of the draws fetched last round (rand UniformInt::sample_single_inclusive)
+        // ---- stage B: where the ln-probabilities of its jobs are
+        uint32_t b_io, b_in;
         {
-            const uint64_t m = (uint64_t)raw_hi * (uint64_t)my_range;
+            const uint32_t r = job_r(jb.job);
+            if (L.p <= 2) { b_io = lp_index2(L, r, RW::src(b_ro), b0, b1); b_in = lp_index2(L, r, RW::src(b_rn), b0, b1); }
+            else { b_io = lp_index(L, I, ws, r, RW::src(b_ro)); b_in = lp_index(L, I, ws, r, RW::src(b_rn)); }
+        }
+        // ---- stage A: Floyd's replacements if two draws of the sample were equal, then deal the jobs
+        uint32_t a_v = s_v;
+        uint2 a_info = f_info;
+        const bool a_valid = v1;
+        // (stage S1 of the NEXT sample goes first: its MATCH.ANY is issued here and its result read at the end of
+        // the round, so that nothing variable-latency but the loads is in flight across the loop's back edge)
+        unsigned n_match;
+        {
+            const uint64_t m = (uint64_t)f_raw * (uint64_t)my_range;     // rand UniformInt::sample_single_inclusive
             v1 = v0;
             if (__builtin_expect(v0 && wany(lane < amount && (uint32_t)m > 0u - my_range), 0)) {
                 v1 = false; blocked = true; dpos -= amount;      // biased zone: this sample takes the sequential path
             }
             s_v = (uint32_t)(m >> 32);
-            s_match = __match_any_sync(FULL, lane < amount ? s_v : 0x80000000u | lane);
-            // The index entry is fetched through asm: whatever the compiler derives from its own load (a
-            // zero-extension, a field extraction) it schedules right behind the load and waits there.
-            const uint32_t q = lane < amount ? s_v : 0u;
-            if (ws.ntinfo) asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(s_info.x), "=r"(s_info.y) : "l"(ws.ntinfo + q));
-            else s_info = nt_info(ws, q);
+            n_match = __match_any_sync(FULL, lane < amount ? s_v : 0x80000000u | lane);
         }
-        // ---- stage S0: fetch the raw draws of the next sample (always the same load; past the fill it re-reads the
-        // last sample and the result is not used)
-        v0 = !blocked && dpos + amount <= RNG_FILL;
+        if (__builtin_expect(slow, 0)) {                    // the sample was drawn one draw at a time (see below)
+            a_v = ws.samp[lane & 15u];
+            a_info = nt_info(ws, lane < amount ? a_v : 0u);
+            slow = false;
+        } else if (__builtin_expect(s_dup, 0)) {
+            a_v = sample_resolve_seq(n_nt, amount, a_v);
+            a_info = nt_info(ws, lane < amount ? a_v : 0u);
+        }
+        uint32_t a_r, a_oa, a_oc;       // the job's read, positions of its current / alternative candidate
         {
-            const uint32_t at = min(dpos, RNG_FILL - amount);
-            asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(raw_hi) : "l"(draw_hi + 2u * at));
+            const bool lead = lane < amount;
+            const uint32_t n_alt = lead ? (a_info.x >> 16) - 1u : 0u;
+            uint32_t incl = n_alt;
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) {              // amount <= 11: four rounds
+                const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= (uint32_t)d) incl += t;
+            }
+            ja.total = wshfl(incl, (int)amount - 1);
+            const uint32_t first = incl - n_alt;
+            ja.lead = a_v | (first << 16);
+            const unsigned starts = __reduce_or_sync(FULL, (lead && first < 32u) ? (1u << first) : 0u);
+            const uint32_t slot = (uint32_t)__popc(starts & (0xFFFFFFFFu >> (31u - lane))) - 1u;   // starts has bit 0 set
+            a_r = wshfl(a_info.y, (int)slot);
+            const uint32_t on = wshfl(a_info.x, (int)slot);
+            const uint32_t alt = lane - wshfl(first, (int)slot);
+            const uint32_t o = on & 0xFFFFu, n = on >> 16;
+            const uint32_t a = ws.assgn[a_r];
+            const uint32_t c = min(alt_rank(alt, a), n - 1u);     // lanes >= total: clamped, loaded, never evaluated
+            ja.job = a_r | (slot << 16) | (c << 24);
+            a_oa = o + a; a_oc = o + c;
         }
+        vA = a_valid;
+        // ---- the loads of all stages, back to back, in the order in which the next round reads them
+        f_lpo = __ldg(L.cm_lnprob + b_io);
+        f_lpn = __ldg(L.cm_lnprob + b_in);
+        f_ro = S.rec[a_oa];
+        f_rn = S.rec[a_oc];
+        f_b0 = __ldg(L.cm_off + (size_t)I.h0 * L.R + a_r);
+        f_b1 = __ldg(L.cm_off + (size_t)I.h1 * L.R + a_r);     // (ploidy 1: h1 = 0, loaded and not used -- a conditional load is a second definition)
+        // through asm: whatever the compiler derives from its own load (a zero-extension, a field extraction) it
+        // schedules right behind the load and waits there
+        asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(f_info.x), "=r"(f_info.y) : "l"(ws.ntinfo + (lane < amount ? s_v : 0u)));
+        v0 = !blocked && dpos + amount <= RNG_FILL;
+        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(f_raw) : "l"(draw_hi + 2u * min(dpos, RNG_FILL - amount)));   // past the fill: re-read, not used
         dpos += v0 ? amount : 0u;
+        s_dup = wany(v1 && lane < amount && (n_match & lt_mask) != 0u);
         if (__builtin_expect(!v0 && !v1 && !vA && !vB && !vC, 0)) {
-            // empty pipeline: the next sample one draw at a time
+            // empty pipeline: the next sample one draw at a time; stage A of the next round picks it up
+            uint32_t v = 0;
             rng.pos = dpos;
-            sample_draw(rng, n_nt, amount, true, s_v);
-            sample_resolve(ws, n_nt, amount, s_v);
-            s_match = 0u;
-            s_info = nt_info(ws, lane < amount ? s_v : 0u);
-            v1 = true; blocked = false;
+            sample_draw(rng, n_nt, amount, true, v);
+            sample_resolve(ws, n_nt, amount, v);
+            if (lane < 16u) ws.samp[lane] = v;
+            __syncwarp();
+            slow = true; v1 = true; blocked = false; s_dup = false;
             dpos = rng.pos;
         }
     }
