@@ -156,6 +156,9 @@ def input_bytes(loc) -> int:
         "hap_reg_start", "hap_pos_off", "pos_weight", "pos_gc", "depth_table")))
 
 
+MAX_SM_MHZ = [1965.0]      # replaced by the sampled nvidia-smi max SM clock of the run
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -312,6 +315,8 @@ def run_ours(args):
         ev[k][1].record(stream)
     barrier()
     clocks = sampler.stop()
+    if clocks.get("sm_max_mhz"):
+        MAX_SM_MHZ[0] = float(clocks["sm_max_mhz"])
     launches = pool.launch_count() - launches0
     st = pool.stats(reset=True)
     ms_steps = [a.elapsed_time(b) for a, b in ev]
@@ -474,14 +479,17 @@ def shard_kir(args, ctx, genotype, rank, world, dev):
             "call": list(loc.genotype_tuple(int(res.gt_ix[0]))), "truth": list(loc.truth), "scaling": "strong"}
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r01_ncu_traffic.json), or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
-            e = json.load(f)[kernel]
-        return {"dram_bytes_per_launch": e["dram_bytes_per_launch"], "capture": e["capture"]}
-    except Exception:
-        return None
+def ncu_traffic(kernel, full=False):
+    """Per-launch numbers of `kernel` from the committed ncu captures (profiles/r02_ncu_traffic.json, written by
+    tools/ncu_summary.py; round-1 file as fallback), or None."""
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                e = json.load(f)[kernel]
+            return e if full else {"dram_bytes_per_launch": e["dram_bytes_per_launch"], "capture": e["capture"]}
+        except Exception:
+            continue
+    return None
 
 
 def rooflines(st, loci, args, peak, peak_src, fp64_rate=None):
@@ -489,20 +497,45 @@ def rooflines(st, loci, args, peak, peak_src, fp64_rate=None):
     loc = loci[0]
     R, p = loc.n_reads, loc.ploidy
     out = {}
-    # solver stage kernel: algorithmic bytes = build + tweak + iterations (DESIGN.md section "Kernels")
+    # solver stage kernel.  Algorithmic bytes = the COMPULSORY traffic of a launch: per genotype the
+    # shared arrays read once (CSR offsets of its p haplotypes 8 B per read and haplotype, ln-probability 8 B and
+    # pair-alignment middles 8 B per candidate), the worker's candidate records written and read once per attempt
+    # (4 B each way) and the pre-generated draws written and read once (16 B per draw; draws = one per candidate and
+    # attempt in the tweak + 10 per greedy iteration / ~2 per annealing step).  The kernel is a set of dependent
+    # chains, not a streaming kernel: the number that describes it is the issue-slot utilisation (`issue`).
     if st["stage_launches"]:
-        g, A, it = st["stage_genotypes"], st["stage_alns"], st["stage_iters"]
-        cbar = A / max(1, g * R)
-        bytes_alg = g * R * p * 24 + A * 17 + st["stage_attempts"] * (A / max(1, g)) * 16 + it * 10 * max(cbar - 1, 0.5) * 80
+        g, A, it, att = st["stage_genotypes"], st["stage_alns"], st["stage_iters"], st["stage_attempts"]
+        per_iter_draws = 10 if "greedy" in " ".join(args.scheme) else 2
+        apg = A / max(1, g)                                   # candidates per genotype
+        draws = att * apg + it * per_iter_draws
+        bytes_alg = g * R * p * 8 + A * 16 + att * apg * 8 + draws * 16
         sec = st["stage_ms"] / 1e3
         ach = bytes_alg / sec / 1e9
+        cap = ncu_traffic("k_solve_stage", full=True) if args.config == "C2" else None
         out["roofline"] = {"kernel": "k_solve_stage", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                           "frac": ach / peak, "traffic": ncu_traffic("k_solve_stage") if args.config == "C2" else None,
+                           "frac": ach / peak,
+                           "traffic": ({"dram_bytes_per_launch": cap["dram_bytes_per_launch"], "capture": cap["capture"]}
+                                       if cap else None),
                            "peak_source": peak_src,
                            "bytes_alg_per_launch": bytes_alg / st["stage_launches"],
+                           "bytes_alg_model": "compulsory: shared arrays once per genotype, candidate records and draws "
+                                              "written + read once (DESIGN.md 3.2)",
                            "avg_launch_ms": st["stage_ms"] / st["stage_launches"],
-                           "note": "latency/issue-bound dependent chains (SURVEY 8d): HBM fraction is not the limiter; "
-                                   "see iters_per_s", "iters_per_s": it / sec, "genotypes_per_s": g / sec}
+                           "note": "dependent chains (one warp per logical worker): neither HBM nor a math pipe binds; "
+                                   "see `issue` (issue-slot utilisation) and iters_per_s",
+                           "iters_per_s": it / sec, "genotypes_per_s": g / sec}
+        if cap and cap.get("warp_instructions_per_launch"):
+            # warp-instructions of a launch are a property of the workload (same seeds, same build as the capture);
+            # the duration is the one measured here with CUDA events
+            slots = 148 * 4 * MAX_SM_MHZ[0] * 1e6 if MAX_SM_MHZ[0] else None
+            ips = cap["warp_instructions_per_launch"] / (st["stage_ms"] / st["stage_launches"] / 1e3)
+            out["roofline"]["issue"] = {
+                "achieved": ips / 1e9, "peak": slots / 1e9 if slots else None, "unit": "G warp-instructions/s",
+                "frac": ips / slots if slots else None,
+                "warp_instructions_per_launch": cap["warp_instructions_per_launch"],
+                "ncu_issue_active_pct": cap.get("issue_active_pct"), "ncu_l2_hit_pct": cap.get("l2_hit_pct"),
+                "ncu_cycles_per_issue_per_warp": cap.get("cycles_per_issued_instruction_per_warp"),
+                "peak_source": "148 SMs x 4 schedulers x 1 instruction per cycle at the max SM clock"}
     if st["prefilter_launches"]:
         gp = st["prefilter_genotypes"]
         sec = st["prefilter_ms"] / 1e3
@@ -611,6 +644,8 @@ def run_shard(args, ctx, scheme, T, rank, world, dev):
     b.record(stream)
     barrier()
     clocks = sampler.stop()
+    if clocks.get("sm_max_mhz"):
+        MAX_SM_MHZ[0] = float(clocks["sm_max_mhz"])
     t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -57,6 +57,21 @@ __device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned 
 }
 
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+// acc += max(a, b).  LCTP_PRED_ADD=1 (experiment, measured and rejected): a compare and two complementary predicated
+// adds, DSETP + @p DADD + @!p DADD = three issue slots per element instead of DSETP + 2 FSEL + DADD = four (sm_100a has
+// no DMNMX).  Bit-identical, but the nullified DADD still occupies the FP64 pipe for its two cycles: KIR-scale prefilter
+// 1.89 ms against 1.02 ms (profiles/r02_summary.md).
+#ifndef LCTP_PRED_ADD
+#define LCTP_PRED_ADD 0
+#endif
+__device__ __forceinline__ void acc_max(double &acc, double a, double b) {
+#if LCTP_PRED_ADD
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\t@p add.rn.f64 %0, %0, %1;\n\t@!p add.rn.f64 %0, %0, %2;\n\t}"
+        : "+d"(acc) : "d"(a), "d"(b));
+#else
+    acc = __dadd_rn(acc, dmax(a, b));
+#endif
+}
 // max of two values that are both <= +0.0 (ln-probabilities): their order is the reverse order of their
 // bit patterns as unsigned integers, so the comparison runs on the integer pipe and leaves the FP64
 // pipe to the additions.  Only used when the upload verified that no matrix entry is positive or NaN.
@@ -469,12 +484,12 @@ __device__ __forceinline__ void bal_consume(const BalWarp &w, BalPipe &pipe, int
 #pragma unroll
             for (int x = 0; x < 4; x++)
 #pragma unroll
-                for (int y = 0; y < C; y++) acc[x][y] = __dadd_rn(acc[x][y], dmax(a[x], b[y]));
+                for (int y = 0; y < C; y++) acc_max(acc[x][y], a[x], b[y]);
 #else
 #pragma unroll
             for (int y = 0; y < C; y++)
 #pragma unroll
-                for (int x = 0; x < 4; x++) acc[x][y] = __dadd_rn(acc[x][y], dmax(a[x], b[y]));
+                for (int x = 0; x < 4; x++) acc_max(acc[x][y], a[x], b[y]);
 #endif
 #pragma unroll
             for (int x = 0; x < 4; x++) a[x] = an[x];

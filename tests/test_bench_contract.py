@@ -48,10 +48,12 @@ def test_rooflines_and_rates_are_pure_functions_of_the_stats():
               stage_genotypes=15000, stage_attempts=15000, stage_iters=22_000_000, stage_alns=160_000_000,
               pairing_ms=0.0, pairing_launches=0, pairing_mates=0, pairing_pairs=0)
     loc = types.SimpleNamespace(n_reads=2000, ploidy=2)
-    args = types.SimpleNamespace(config="C2")
+    args = types.SimpleNamespace(config="C2", scheme=["greedy:i=5k,a=1"])
     out = bench.rooflines(st, [loc], args, 6550.7, "measured", fp64_rate=18.3e12)
     assert set(out) >= {"roofline", "roofline_prefilter", "rates"}
     assert 0 < out["roofline"]["frac"] < 1 and out["roofline"]["unit"] == "GB/s"
+    iss = out["roofline"].get("issue")       # from the committed ncu capture: warp-instructions per launch / measured time
+    assert iss is None or (0 < iss["frac"] < 1 and iss["warp_instructions_per_launch"] > 1e9)
     r = out["rates"]
     assert abs(r["stage_genotypes_per_s"] - 15000 / 0.0304) < 1e-6 * r["stage_genotypes_per_s"]
     assert abs(r["prefilter_genotypes_per_s"] - 135450 / 0.00024) < 1e-6 * r["prefilter_genotypes_per_s"]
