@@ -284,6 +284,47 @@ int  lctp_solve_stage(lctp_locus_h *h, const lctp_stage *st,
                       uint64_t counts_cap,
                       uint64_t *n_alns_out /* nullable [n] */, uint64_t *iters_out /* nullable [n] */);
 
+/* ---- output side, SURVEY 8(f) rank 4: what `--debug` of the reference writes per locus ------------------------- */
+/* Per (genotype position j, attempt a) of a stage, index j * attempts + a: the fields of ReadAssignment::summarize
+ * (src/model/assgn.rs:413-425) and, when the win_* pointers are given, of ReadAssignment::write_depth (:356-372) for
+ * every window w of the genotype (index (j * attempts + a) * wmax + w; windows 0 / 1 are the "unmapped" / "out of
+ * bounds" windows, contig i owns windows [wshift_i, wshift_{i+1}) with wshift_0 = 2).  All pointers are
+ * caller-allocated host arrays; NULL = not wanted. */
+typedef struct lctp_stage_debug {
+    double   *aln_lik;       /* [n * attempts] ReadAssignment::aln_lik (ln) */
+    double   *depth_lik;     /* [n * attempts] ReadAssignment::depth_lik (ln) */
+    uint32_t *unmapped;      /* [n * attempts] depth[UNMAPPED_WINDOW] */
+    uint32_t *out_of_bounds; /* [n * attempts] depth[BOUNDARY_WINDOW] */
+    uint32_t  wmax;          /* stride of the win_* arrays: >= 2 + ploidy * max windows per contig (lctp_locus_wmax) */
+    uint32_t  _pad;
+    double   *win_weight;    /* WindowDistr::weight() */
+    uint32_t *win_depth;     /* ReadAssignment::depth[w] */
+    double   *win_lik;       /* WindowDistr::ln_prob(depth[w]) (ln) */
+} lctp_stage_debug;
+uint32_t lctp_locus_wmax(const lctp_locus_h *h);
+/* lctp_solve_stage + the debug fields above (dbg may be NULL). */
+int  lctp_solve_stage_dbg(lctp_locus_h *h, const lctp_stage *st,
+                          const uint64_t *worker_ixs, const uint64_t *worker_off, size_t n_workers,
+                          uint64_t *worker_rng, double *lik_mean, double *lik_var, double *liks,
+                          uint64_t *counts_off, uint16_t *counts, uint64_t counts_cap,
+                          uint64_t *n_alns_out, uint64_t *iters_out, const lctp_stage_debug *dbg);
+/* Debug sink of a context: while open, lctp_solve writes the reference's per-locus debug tables into `dir`
+ * (src/solvers/solve.rs:852-952): level >= 1 (DebugLvl::Some): sol.csv ("stage genotype score": stage 0 = prefilter
+ * score of every genotype :115-117, stages 1.. = lik_mean :1074-1075) and sol_ext.csv (summarize rows); level >= 2
+ * (DebugLvl::Full): depth.csv (write_depth rows).  Plain text, uncompressed: the reference wraps the same rows in a
+ * brotli writer (.csv.br), which stays on the Rust side.  Rows of a stage are written in dispatch order (the
+ * reference's order inside a stage depends on thread timing).  hap_names: n_haps NUL-terminated contig names
+ * (Genotype display = names joined by ','); they are copied. */
+int  lctp_debug_open(lctp_ctx *ctx, const char *dir, int level, const char *const *hap_names, size_t n_haps);
+void lctp_debug_close(lctp_ctx *ctx);
+/* lctp_solve that also returns the assignment counts (Prediction::assgn_counts, src/solvers/solve.rs:286-317, the
+ * input of write_bam, src/model/bam.rs:356-413) of the first `n_counts` genotypes of the result (the reference writes
+ * BAMs for `out_bams` of them): counts_off[k] .. counts_off[k+1] = the candidates of res->gt_ix[k] in
+ * GenotypeAlignments order, counts[c] = attempts in which candidate c was the read's location. */
+int  lctp_solve_counts(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_t threads,
+                       uint64_t rng[4], lctp_result *res, size_t n_counts,
+                       uint64_t *counts_off /* [n_counts + 1] */, uint16_t *counts, uint64_t counts_cap);
+
 /* ---- host-side mirror of the scheduler (a14-a16) ------------------------------------------- */
 void lctp_rng_seed_from_u64(uint64_t state[4], uint64_t seed);   /* src/ext/rand.rs:12 */
 void lctp_rng_jump(uint64_t state[4]);                            /* src/solvers/solve.rs:1017 */

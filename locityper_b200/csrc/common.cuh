@@ -115,6 +115,14 @@ struct lctp_ctx {
     lctp::DevBuf<uint16_t> d_counts;
     lctp::DevBuf<int> d_flags;
     lctp::PinBuf<unsigned char> pin;
+    // debug outputs of the next stage launch (lctp_solve_stage_dbg sets it around its launch) and the debug sink
+    const lctp_stage_debug *dbg_req = nullptr;
+    lctp::DevBuf<double> d_dbg_lik, d_dbg_ww, d_dbg_wl;
+    lctp::DevBuf<uint32_t> d_dbg_cnt, d_dbg_wd;
+    int dbg_level = 0;
+    std::string dbg_dir;
+    std::vector<std::string> dbg_names;
+    FILE *dbg_sol = nullptr, *dbg_sol_ext = nullptr, *dbg_depth = nullptr;
 };
 
 // Device-side view of one uploaded locus (all pointers are device pointers).

@@ -386,6 +386,7 @@ int lctp_init(const lctp_device_cfg *cfg, lctp_ctx **out) {
 }
 
 void lctp_destroy(lctp_ctx *ctx) {
+    lctp_debug_close(ctx);
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     set_alloc_stream(ctx->stream);
@@ -853,12 +854,87 @@ int lctp_produce_result(lctp_locus_h *h, uint64_t *ixs, size_t n, const double *
     return LCTP_OK;
 }
 
-int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_t threads, uint64_t rng[4],
-               lctp_result *res) {
+// ---- output side: the per-locus debug tables of the reference -------------------------------
+
+uint32_t lctp_locus_wmax(const lctp_locus_h *h) { return h ? 2 + h->dev.p * h->max_n_windows : 0; }
+
+int lctp_solve_stage_dbg(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_ixs, const uint64_t *worker_off,
+                         size_t n_workers, uint64_t *worker_rng, double *lik_mean, double *lik_var, double *liks,
+                         uint64_t *counts_off, uint16_t *counts, uint64_t counts_cap, uint64_t *n_alns_out,
+                         uint64_t *iters_out, const lctp_stage_debug *dbg) {
+    if (!h) { set_error("lctp_solve_stage: NULL handle"); return LCTP_E_INVALID; }
+    LCTP_CUDA_CHECK(cudaSetDevice(h->ctx->device));
+    set_alloc_stream(h->ctx->stream);
+    h->ctx->dbg_req = dbg;
+    const int rc = launch_stage(h, st, worker_ixs, worker_off, n_workers, worker_rng, lik_mean, lik_var, liks, counts_off,
+                                counts, counts_cap, n_alns_out, iters_out);
+    h->ctx->dbg_req = nullptr;
+    return rc;
+}
+
+void lctp_debug_close(lctp_ctx *ctx) {
+    if (!ctx) return;
+    for (FILE **f : {&ctx->dbg_sol, &ctx->dbg_sol_ext, &ctx->dbg_depth}) { if (*f) fclose(*f); *f = nullptr; }
+    ctx->dbg_names.clear();
+    ctx->dbg_level = 0;
+    ctx->dbg_dir.clear();
+}
+
+int lctp_debug_open(lctp_ctx *ctx, const char *dir, int level, const char *const *hap_names, size_t n_haps) {
+    if (!ctx || !dir || !hap_names || level < 0) { set_error("lctp_debug_open: invalid argument"); return LCTP_E_INVALID; }
+    lctp_debug_close(ctx);
+    ctx->dbg_dir = dir;
+    ctx->dbg_level = level;
+    ctx->dbg_names.assign(hap_names, hap_names + n_haps);
+    auto open = [&](const char *name) { return fopen((ctx->dbg_dir + "/" + name).c_str(), "w"); };
+    ctx->dbg_sol = open("sol.csv");                                                  // solve.rs:937-938
+    if (ctx->dbg_sol) fprintf(ctx->dbg_sol, "stage\tgenotype\tscore\n");
+    if (level >= 1) {                                                                // DebugFiles::new, solve.rs:890-897
+        ctx->dbg_sol_ext = open("sol_ext.csv");
+        if (ctx->dbg_sol_ext)
+            fprintf(ctx->dbg_sol_ext, "stage\tgenotype\tattempt\ttotal_reads\tunmapped\tout_of_bounds\taln_lik\tdepth_lik\tlik\n");
+    }
+    if (level >= 2) {                                                                // :882-888
+        ctx->dbg_depth = open("depth.csv");
+        if (ctx->dbg_depth) fprintf(ctx->dbg_depth, "stage\tgenotype\tattempt\tcontig\twindow\tweight\tdepth\tlik\n");
+    }
+    if (!ctx->dbg_sol || (level >= 1 && !ctx->dbg_sol_ext) || (level >= 2 && !ctx->dbg_depth)) {
+        lctp_debug_close(ctx);
+        set_error("lctp_debug_open: cannot create the debug tables in %s", dir);
+        return LCTP_E_INVALID;
+    }
+    return LCTP_OK;
+}
+
+static const double INV_LN10 = 0.4342944819032518277;      // Ln::INV_LN10, src/math/mod.rs:14
+
+// Rust's `{:.N}` of an f64: the correctly rounded decimal expansion, like printf("%.Nf"), but "NaN" for NaNs.
+static void print_fixed(FILE *f, double v, int prec) {
+    if (std::isnan(v)) fputs("NaN", f);
+    else fprintf(f, "%.*f", prec, v);
+}
+
+static void print_gt(FILE *f, const lctp_locus_h *h, uint64_t g) {    // Genotype::new name, src/seq/contigs.rs:412-424
+    uint32_t ids[LCTP_MAX_PLOIDY];
+    lctp::genotype_tuple(h->dev.H, h->dev.p, h->gt_tuples_host.empty() ? nullptr : h->gt_tuples_host.data(), g, ids);
+    for (uint32_t k = 0; k < h->dev.p; k++) {
+        if (k) fputc(',', f);
+        fputs(ids[k] < h->ctx->dbg_names.size() ? h->ctx->dbg_names[ids[k]].c_str() : "?", f);
+    }
+}
+
+static int solve_impl(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_t threads, uint64_t rng[4],
+                      lctp_result *res, size_t n_counts, uint64_t *counts_off_out, uint16_t *counts_out,
+                      uint64_t counts_cap) {
     if (!h || !stages || !rng || !res || n_stages == 0 || n_stages > LCTP_MAX_STAGES) {
         set_error("lctp_solve: invalid argument");
         return LCTP_E_INVALID;
     }
+    if (n_counts && (!counts_off_out || !counts_out || n_counts > LCTP_MAX_OUT)) {
+        set_error("lctp_solve_counts: invalid counts arguments");
+        return LCTP_E_INVALID;
+    }
+    lctp_ctx *ctx = h->ctx;
     const double t_in = now_s();
     const uint64_t G = h->dev.G;
     std::memset(res, 0, sizeof(*res));
@@ -872,8 +948,15 @@ int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_
 
     const double t0 = now_s();
     if (h->host.dont_skip || stages[0].in_size < G) {                // solve.rs:941-945
-        int rc = lctp_prefilter(h, ixs.data(), n, stages[0].in_size, threads, &n, nullptr);
+        const bool rows = ctx->dbg_sol && ctx->dbg_level >= 1;       // the writer is passed with debug != None only (:942)
+        std::vector<double> scores(rows ? G : 0);
+        int rc = lctp_prefilter(h, ixs.data(), n, stages[0].in_size, threads, &n, rows ? scores.data() : nullptr);
         if (rc) return rc;
+        if (rows)                                                    // run_filter, solve.rs:115-117
+            for (uint64_t g = 0; g < G; g++) {
+                fputs("0\t", ctx->dbg_sol); print_gt(ctx->dbg_sol, h, g); fputc('\t', ctx->dbg_sol);
+                print_fixed(ctx->dbg_sol, scores[g] * INV_LN10, 3); fputc('\n', ctx->dbg_sol);
+            }
     }
     res->n_filtered = n;
     const double t1 = now_s();
@@ -887,6 +970,10 @@ int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_
     const double t_jump = now_s();
     std::vector<uint64_t> off(threads + 1);
     std::vector<double> lm, lv;
+    std::vector<uint64_t> c_off;            // assignment counts of the last stage, by position
+    std::vector<uint16_t> c_val;
+    std::vector<uint64_t> last_ixs;         // its genotypes in dispatch order
+    const uint32_t wmax = lctp_locus_wmax(h);
     for (size_t s = 0; s < n_stages; s++) {
         const lctp_stage &st = stages[s];
         const bool has_next = s + 1 < n_stages;
@@ -894,22 +981,83 @@ int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_
         if (!(h->host.dont_skip || !has_next || out_size < n)) continue;   // solve.rs:1041-1045
         res->n_stage_in[s] = n;
         lm.resize(n); lv.resize(n);
-        int rc;
-        if (threads == 1) {                                          // solve_single_thread, solve.rs:814-843
-            off[0] = 0; off[1] = n;
-            rc = lctp_solve_stage(h, &st, ixs.data(), off.data(), 1, rng, lm.data(), lv.data(), nullptr, nullptr,
-                                  nullptr, 0, nullptr, nullptr);
-        } else {
-            const size_t nw = lctp_plan_stage(rng, ixs.data(), n, threads, off.data());
-            rc = lctp_solve_stage(h, &st, ixs.data(), off.data(), nw, wrng.data(), lm.data(), lv.data(), nullptr,
-                                  nullptr, nullptr, 0, nullptr, nullptr);
+        // debug tables of this stage (Worker::run, solve.rs:1128-1134; MainWorker::run :1064-1075)
+        const bool ext_rows = ctx->dbg_sol_ext != nullptr, depth_rows = ctx->dbg_depth != nullptr;
+        const bool sol_rows = ctx->dbg_sol && (ctx->dbg_level >= 1 || !has_next);
+        const size_t na = n * st.attempts;
+        std::vector<double> d_al, d_dl, d_ww, d_wl;
+        std::vector<uint32_t> d_un, d_ob, d_wd;
+        lctp_stage_debug dbg;
+        std::memset(&dbg, 0, sizeof dbg);
+        if (ext_rows || depth_rows) {
+            d_al.resize(na); d_dl.resize(na); d_un.resize(na); d_ob.resize(na);
+            dbg.aln_lik = d_al.data(); dbg.depth_lik = d_dl.data(); dbg.unmapped = d_un.data(); dbg.out_of_bounds = d_ob.data();
+            if (depth_rows) {
+                d_ww.resize(na * wmax); d_wl.resize(na * wmax); d_wd.resize(na * wmax);
+                dbg.wmax = wmax; dbg.win_weight = d_ww.data(); dbg.win_lik = d_wl.data(); dbg.win_depth = d_wd.data();
+            }
         }
+        const bool want_c = n_counts > 0 && !has_next;
+        std::vector<uint64_t> nal;
+        if (want_c) {
+            // candidate totals are not known before the stage ran: bound by n * (R + sum of the p largest haplotypes)
+            std::vector<uint32_t> ha(h->hap_alns);
+            std::sort(ha.begin(), ha.end(), std::greater<uint32_t>());
+            uint64_t per = h->dev.R;
+            for (uint32_t k = 0; k < h->dev.p && k < ha.size(); k++) per += ha[k < ha.size() ? k : 0];
+            per = std::min<uint64_t>(per, 65535);
+            c_off.assign(n + 1, 0);
+            c_val.assign((size_t)n * per, 0);
+        }
+        int rc;
+        size_t nw = 1;
+        uint64_t *wr = rng;
+        if (threads == 1) { off[0] = 0; off[1] = n; }                // solve_single_thread, solve.rs:814-843
+        else { nw = lctp_plan_stage(rng, ixs.data(), n, threads, off.data()); wr = wrng.data(); }
+        rc = lctp_solve_stage_dbg(h, &st, ixs.data(), off.data(), nw, wr, lm.data(), lv.data(), nullptr,
+                                  want_c ? c_off.data() : nullptr, want_c ? c_val.data() : nullptr, c_val.size(), nullptr,
+                                  nullptr, (ext_rows || depth_rows) ? &dbg : nullptr);
         if (rc) return rc;
+        if (want_c) last_ixs.assign(ixs.begin(), ixs.begin() + n);
         for (size_t q = 0; q < n; q++) { lik_mean[ixs[q]] = lm[q]; lik_var[ixs[q]] = lv[q]; attempts[ixs[q]] = (uint16_t)st.attempts; }
+        for (size_t q = 0; q < n && (ext_rows || depth_rows || sol_rows); q++) {
+            uint32_t ids[LCTP_MAX_PLOIDY];
+            lctp::genotype_tuple(h->dev.H, h->dev.p, h->gt_tuples_host.empty() ? nullptr : h->gt_tuples_host.data(), ixs[q], ids);
+            for (uint32_t a = 0; a < st.attempts; a++) {
+                const size_t ja = q * st.attempts + a;
+                if (depth_rows) {                                    // write_depth, assgn.rs:359-372
+                    uint32_t w = 2;
+                    for (uint32_t i = 0; i < h->dev.p; i++)
+                        for (uint32_t k = 0; k < h->hap_n_windows[ids[i]]; k++, w++) {
+                            FILE *f = ctx->dbg_depth;
+                            fprintf(f, "%zu\t", s + 1); print_gt(f, h, ixs[q]);
+                            fprintf(f, "\t%u\t%u\t%u\t", a + 1, i + 1, k + 1);
+                            print_fixed(f, d_ww[ja * wmax + w], 4);
+                            fprintf(f, "\t%u\t", d_wd[ja * wmax + w]);
+                            print_fixed(f, d_wl[ja * wmax + w] * INV_LN10, 3); fputc('\n', f);
+                        }
+                }
+                if (ext_rows) {                                      // summarize, assgn.rs:416-425
+                    FILE *f = ctx->dbg_sol_ext;
+                    const double lik = h->dev.depth_contrib * d_dl[ja] + h->dev.aln_contrib * d_al[ja];   // likelihood(), :235-237
+                    fprintf(f, "%zu\t", s + 1); print_gt(f, h, ixs[q]);
+                    fprintf(f, "\t%u\t%u\t%u\t%u\t", a + 1, h->dev.R, d_un[ja], d_ob[ja]);
+                    print_fixed(f, d_al[ja] * INV_LN10, 7); fputc('\t', f);
+                    print_fixed(f, d_dl[ja] * INV_LN10, 7); fputc('\t', f);
+                    print_fixed(f, lik * INV_LN10, 7); fputc('\n', f);
+                }
+            }
+            if (sol_rows) {                                          // MainWorker::run, solve.rs:1074-1075
+                FILE *f = ctx->dbg_sol;
+                fprintf(f, "%zu\t", s + 1); print_gt(f, h, ixs[q]); fputc('\t', f);
+                print_fixed(f, lm[q] * INV_LN10, 4); fputc('\n', f);
+            }
+        }
         if (has_next)
             n = lctp_discard_improbable(ixs.data(), n, lik_mean.data(), lik_var.data(), attempts.data(),
                                         h->host.prob_thresh, out_size, threads);
     }
+    for (FILE *f : {ctx->dbg_sol, ctx->dbg_sol_ext, ctx->dbg_depth}) if (f) fflush(f);
     res->t_stages_s = now_s() - t1;
     const double t_st = now_s();
     const uint64_t n_filtered = res->n_filtered;
@@ -921,10 +1069,35 @@ int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_
     res->n_filtered = n_filtered;
     std::memcpy(res->n_stage_in, n_stage_in, sizeof(n_stage_in));
     res->t_prefilter_s = tp; res->t_stages_s = ts;
+    if (n_counts) {                                                  // Prediction::assgn_counts of the reported genotypes
+        uint64_t o = 0;
+        counts_off_out[0] = 0;
+        for (size_t k = 0; k < n_counts; k++) {
+            if (k < res->n_out) {
+                const size_t q = std::find(last_ixs.begin(), last_ixs.end(), res->gt_ix[k]) - last_ixs.begin();
+                if (q == last_ixs.size()) { set_error("lctp_solve_counts: genotype missing from the last stage"); return LCTP_E_INVALID; }
+                const uint64_t len = c_off[q + 1] - c_off[q];
+                if (o + len > counts_cap) { set_error("lctp_solve_counts: counts buffer too small"); return LCTP_E_CAPACITY; }
+                std::copy(c_val.begin() + c_off[q], c_val.begin() + c_off[q + 1], counts_out + o);
+                o += len;
+            }
+            counts_off_out[k + 1] = o;
+        }
+    }
     if (getenv("LCTP_DEBUG_TIMES"))
         fprintf(stderr, "[lctp debug] ctx %p lctp_solve host: setup %.3f, prefilter %.3f, worker streams %.3f, stages %.3f, result %.3f ms\n",
                 (void *)h->ctx, (t0 - t_in) * 1e3, (t1 - t0) * 1e3, (t_jump - t1) * 1e3, (t_st - t_jump) * 1e3, (now_s() - t_st) * 1e3);
     return LCTP_OK;
+}
+
+int lctp_solve(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_t threads, uint64_t rng[4],
+               lctp_result *res) {
+    return solve_impl(h, stages, n_stages, threads, rng, res, 0, nullptr, nullptr, 0);
+}
+
+int lctp_solve_counts(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages, size_t threads, uint64_t rng[4],
+                      lctp_result *res, size_t n_counts, uint64_t *counts_off, uint16_t *counts, uint64_t counts_cap) {
+    return solve_impl(h, stages, n_stages, threads, rng, res, n_counts, counts_off, counts, counts_cap);
 }
 
 // ---- Genotyping::find_weighted_dist (src/solvers/solve.rs:616-632) ---------------------------------------

@@ -51,6 +51,15 @@ static constexpr size_t JUMP_TAB_WORDS = 32 * 256 * 4;  // u64 words per table: 
 static constexpr uint32_t SRC_UNMAPPED = 0xFFu;
 static constexpr uint32_t MAX_RUN = 15;                 // rank in a (read, contig) run must fit 4 bits (reference: <= 10)
 
+// Optional per-(genotype, attempt) debug outputs of a stage (lctp_stage_debug); all pointers device pointers or null.
+struct DbgOut {
+    double *lik;          // [n*attempts][2]: aln_lik, depth_lik
+    uint32_t *cnt;        // [n*attempts][2]: depth[UNMAPPED_WINDOW], depth[BOUNDARY_WINDOW]
+    double *ww, *wl;      // [n*attempts][wmax]: window weight, window ln-prob at its depth
+    uint32_t *wd;         // [n*attempts][wmax]: window depth
+    uint32_t wmax;
+};
+
 struct StageParams {
     uint32_t kind, attempts, best_start, sample_size;
     uint64_t plato_size, anneal_steps, max_iter;
@@ -1573,7 +1582,7 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
               double *__restrict__ liks, uint64_t *__restrict__ n_alns, uint64_t *__restrict__ iters,
               uint16_t *__restrict__ counts, unsigned char *__restrict__ scratch,
               unsigned int *__restrict__ work_counter, int *__restrict__ err,
-              const ulonglong2 *__restrict__ jump_tabs) {
+              const ulonglong2 *__restrict__ jump_tabs, DbgOut dbg) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t lane_reg;
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_reg));      // read once (see lane_id)
@@ -1660,6 +1669,19 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
                     const double prior = L.priors ? L.priors[worker_ixs[j]] : 0.0;
                     liks[j * P.attempts + a] = __dadd_rn(prior, __dadd_rn(__dmul_rn(L.depth_contrib, ws.lik[1]),
                                                                           __dmul_rn(L.aln_contrib, ws.lik[0])));
+                }
+                if (dbg.lik) {         // ReadAssignment::summarize / write_depth (assgn.rs:356-372,413-425)
+                    const size_t ja = (size_t)j * P.attempts + a;
+                    if (lane == 0) {
+                        dbg.lik[2 * ja] = ws.lik[0]; dbg.lik[2 * ja + 1] = ws.lik[1];
+                        dbg.cnt[2 * ja] = ws.win.depth(0); dbg.cnt[2 * ja + 1] = ws.win.depth(1);
+                    }
+                    if (dbg.ww)
+                        for (uint32_t w = lane; w < dbg.wmax; w += 32) {      // windows the genotype does not have: zeros
+                            dbg.ww[ja * dbg.wmax + w] = w < I.W ? ws.win.weight(w) : 0.0;
+                            dbg.wd[ja * dbg.wmax + w] = w < I.W ? ws.win.depth(w) : 0u;
+                            dbg.wl[ja * dbg.wmax + w] = w < I.W ? ws.win.p(w, 2) : 0.0;
+                        }
                 }
                 if (P.want_counts) {   // update_counts (assgn.rs:374-378)
                     uint16_t *cnt = counts + (size_t)j * P.cap;
@@ -1779,7 +1801,7 @@ static int env_int(const char *name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-static int launch_stage_kernel(lctp_locus_h *h, const StageParams &P, size_t n_workers, bool want_counts) {
+static int launch_stage_kernel(lctp_locus_h *h, const StageParams &P, size_t n_workers, size_t n_total, bool want_counts) {
     lctp_ctx *ctx = h->ctx;
     cudaStream_t s = ctx->stream;
     const LocusDev &L = h->dev;
@@ -1824,11 +1846,25 @@ static int launch_stage_kernel(lctp_locus_h *h, const StageParams &P, size_t n_w
 
     int rc;
     if ((rc = ctx->scratch.ensure((size_t)grid * P.slab_bytes))) return rc;
+    DbgOut dbg = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    if (ctx->dbg_req) {
+        const size_t na = n_total * P.attempts;
+        if ((rc = ctx->d_dbg_lik.ensure(2 * na))) return rc;
+        if ((rc = ctx->d_dbg_cnt.ensure(2 * na))) return rc;
+        dbg.lik = ctx->d_dbg_lik.p; dbg.cnt = ctx->d_dbg_cnt.p;
+        if (ctx->dbg_req->win_weight && ctx->dbg_req->win_depth && ctx->dbg_req->win_lik) {
+            dbg.wmax = ctx->dbg_req->wmax;
+            if ((rc = ctx->d_dbg_ww.ensure(na * dbg.wmax))) return rc;
+            if ((rc = ctx->d_dbg_wl.ensure(na * dbg.wmax))) return rc;
+            if ((rc = ctx->d_dbg_wd.ensure(na * dbg.wmax))) return rc;
+            dbg.ww = ctx->d_dbg_ww.p; dbg.wl = ctx->d_dbg_wl.p; dbg.wd = ctx->d_dbg_wd.p;
+        }
+    }
     LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[2], s));
     kern<<<grid, CTA_THREADS, smem, s>>>(
         L, P, ctx->d_worker_ixs.p, ctx->d_worker_off.p, ctx->d_tuples.p, ctx->d_rng.p, ctx->d_lik_mean.p,
         ctx->d_lik_var.p, ctx->d_liks.p, ctx->d_nalns.p, ctx->d_iters.p, want_counts ? ctx->d_counts.p : nullptr,
-        ctx->scratch.p, (unsigned int *)(ctx->d_flags.p + 1), ctx->d_flags.p, (const ulonglong2 *)ctx->d_rng_mats.p);
+        ctx->scratch.p, (unsigned int *)(ctx->d_flags.p + 1), ctx->d_flags.p, (const ulonglong2 *)ctx->d_rng_mats.p, dbg);
     ctx->launches++;
     LCTP_CUDA_CHECK(cudaGetLastError());
     LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[3], s));
@@ -1951,7 +1987,11 @@ int launch_stage_ex(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worke
     ctx->stats.h2d_bytes += n * 8 + (n_workers + 1) * 8 + n_workers * 32 + n * p * 4;
 
     const double t_launch = dbg_now();
-    rc = launch_stage_kernel(h, P, n_workers, want_counts);
+    if (ctx->dbg_req && ctx->dbg_req->win_weight && ctx->dbg_req->wmax < P.Wmax) {
+        set_error("lctp_solve_stage_dbg: wmax %u < %u windows of a genotype", ctx->dbg_req->wmax, P.Wmax);
+        return LCTP_E_INVALID;
+    }
+    rc = launch_stage_kernel(h, P, n_workers, n, want_counts);
     if (rc) return rc;
     if (device_only) {
         ctx->stats.stage_launches += 1;
@@ -1998,6 +2038,25 @@ int launch_stage_ex(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worke
         ctx->stats.stage_genotypes += n;
         ctx->stats.stage_attempts += n * st->attempts;
         for (size_t j = 0; j < n; j++) { ctx->stats.stage_iters += its[j]; ctx->stats.stage_alns += nal[j]; }
+    }
+    if (const lctp_stage_debug *d = ctx->dbg_req) {
+        const size_t na = n * st->attempts;
+        std::vector<double> lk(2 * na);
+        std::vector<uint32_t> ct(2 * na);
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(lk.data(), ctx->d_dbg_lik.p, 2 * na * 8, cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(ct.data(), ctx->d_dbg_cnt.p, 2 * na * 4, cudaMemcpyDeviceToHost, s));
+        if (d->win_weight && d->win_depth && d->win_lik) {
+            LCTP_CUDA_CHECK(cudaMemcpyAsync(d->win_weight, ctx->d_dbg_ww.p, na * d->wmax * 8, cudaMemcpyDeviceToHost, s));
+            LCTP_CUDA_CHECK(cudaMemcpyAsync(d->win_lik, ctx->d_dbg_wl.p, na * d->wmax * 8, cudaMemcpyDeviceToHost, s));
+            LCTP_CUDA_CHECK(cudaMemcpyAsync(d->win_depth, ctx->d_dbg_wd.p, na * d->wmax * 4, cudaMemcpyDeviceToHost, s));
+        }
+        LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
+        for (size_t q = 0; q < na; q++) {
+            if (d->aln_lik) d->aln_lik[q] = lk[2 * q];
+            if (d->depth_lik) d->depth_lik[q] = lk[2 * q + 1];
+            if (d->unmapped) d->unmapped[q] = ct[2 * q];
+            if (d->out_of_bounds) d->out_of_bounds[q] = ct[2 * q + 1];
+        }
     }
     if (n_alns_out) std::copy(nal.begin(), nal.end(), n_alns_out);
     if (iters_out) std::copy(its.begin(), its.end(), iters_out);

@@ -56,6 +56,12 @@ class StageC(C.Structure):
     ]
 
 
+class StageDebugC(C.Structure):
+    _fields_ = [("aln_lik", C.c_void_p), ("depth_lik", C.c_void_p), ("unmapped", C.c_void_p), ("out_of_bounds", C.c_void_p),
+                ("wmax", C.c_uint32), ("_pad", C.c_uint32), ("win_weight", C.c_void_p), ("win_depth", C.c_void_p),
+                ("win_lik", C.c_void_p)]
+
+
 class ResultC(C.Structure):
     _fields_ = [
         ("n_out", C.c_uint64), ("gt_ix", C.c_uint64 * MAX_OUT), ("lik_mean", C.c_double * MAX_OUT),
@@ -143,6 +149,11 @@ SYMBOLS = {
     "lctp_find_weighted_dist": (C.c_int, [_P, _P, _P, C.c_int]),
     "lctp_produce_result": (C.c_int, [_P, _P, C.c_size_t, _P, _P, _P, _P]),
     "lctp_solve": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, _P]),
+    "lctp_solve_counts": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, _P, C.c_size_t, _P, _P, C.c_uint64]),
+    "lctp_locus_wmax": (C.c_uint32, [_P]),
+    "lctp_solve_stage_dbg": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P, _P, _P, _P, _P, _P, C.c_uint64, _P, _P, _P]),
+    "lctp_debug_open": (C.c_int, [_P, C.c_char_p, C.c_int, _P, C.c_size_t]),
+    "lctp_debug_close": (None, [_P]),
     "lctp_result_json": (C.c_size_t, [_P, _P, _P, _P, C.c_size_t]),
     "lctp_dist_unique_id": (C.c_int, [_P]),
     "lctp_dist_init": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),

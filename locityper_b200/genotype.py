@@ -234,6 +234,15 @@ class Context:
         ignored and the device-resident pair alignments are used instead."""
         return DeviceLocus(self, loc, pairs)
 
+    def debug_open(self, directory: str, level: int, hap_names: Sequence[str]) -> None:
+        """lctp_debug_open: while open, solve() writes sol.csv / sol_ext.csv (level >= 1) / depth.csv (level >= 2) of the
+        reference's `--debug` into `directory` (src/solvers/solve.rs:852-952), uncompressed."""
+        cn = (C.c_char_p * len(hap_names))(*[s.encode() for s in hap_names])
+        ffi.check(self.lib.lctp_debug_open(self._h, directory.encode(), level, cn, len(hap_names)))
+
+    def debug_close(self) -> None:
+        self.lib.lctp_debug_close(self._h)
+
     def close(self) -> None:
         if self._h:
             self.lib.lctp_destroy(self._h)
@@ -600,6 +609,39 @@ class DeviceLocus:
             ffi.check(self.lib.lctp_find_weighted_dist(C.byref(res), C.byref(self.c), cd.ctypes.data,
                                                        int(true_edit_distances)))
         return self._genotyping(res, hap_names)
+
+    def solve_counts(self, scheme: Scheme, threads: int, rng: np.ndarray, n_counts: int):
+        """lctp_solve_counts: solve::solve + Prediction::assgn_counts of the first n_counts reported genotypes (the input
+        of write_bam, src/model/bam.rs:356-413).  Returns (Genotyping, [u16 counts array per genotype])."""
+        st = scheme.to_c()
+        res = ffi.ResultC()
+        cap = n_counts * 65535
+        off = np.zeros(n_counts + 1, dtype=np.uint64)
+        cnt = np.zeros(cap, dtype=np.uint16)
+        ffi.check(self.lib.lctp_solve_counts(self._h, st, len(scheme.stages), threads, rng.ctypes.data, C.byref(res),
+                                             n_counts, off.ctypes.data, cnt.ctypes.data, cap))
+        return self._genotyping(res), [cnt[int(off[k]):int(off[k + 1])].copy() for k in range(n_counts)]
+
+    def solve_stage_debug(self, stage: Stage, worker_ixs, worker_off, worker_rng: np.ndarray, windows: bool = True) -> dict:
+        """lctp_solve_stage_dbg: a stage + the fields of ReadAssignment::summarize / write_depth per (genotype, attempt)."""
+        worker_ixs = np.ascontiguousarray(worker_ixs, dtype=np.uint64)
+        worker_off = np.ascontiguousarray(worker_off, dtype=np.uint64)
+        n, na = int(worker_off[-1]), int(worker_off[-1]) * stage.attempts
+        wmax = int(self.lib.lctp_locus_wmax(self._h))
+        out = dict(lik_mean=np.empty(n), lik_var=np.empty(n), liks=np.empty((n, stage.attempts)), aln_lik=np.empty(na),
+                   depth_lik=np.empty(na), unmapped=np.zeros(na, dtype=np.uint32), out_of_bounds=np.zeros(na, dtype=np.uint32),
+                   wmax=wmax)
+        d = ffi.StageDebugC(out["aln_lik"].ctypes.data, out["depth_lik"].ctypes.data, out["unmapped"].ctypes.data,
+                            out["out_of_bounds"].ctypes.data, wmax, 0, None, None, None)
+        if windows:
+            out.update(win_weight=np.zeros((na, wmax)), win_depth=np.zeros((na, wmax), dtype=np.uint32), win_lik=np.zeros((na, wmax)))
+            d.win_weight, d.win_depth, d.win_lik = (out[k].ctypes.data for k in ("win_weight", "win_depth", "win_lik"))
+        stc = stage.to_c()
+        ffi.check(self.lib.lctp_solve_stage_dbg(self._h, C.byref(stc), worker_ixs.ctypes.data, worker_off.ctypes.data,
+                                                len(worker_off) - 1, worker_rng.ctypes.data, out["lik_mean"].ctypes.data,
+                                                out["lik_var"].ctypes.data, out["liks"].ctypes.data, None, None, 0, None,
+                                                None, C.byref(d)))
+        return out
 
     def _genotyping(self, res, hap_names=None) -> "Genotyping":
         n = int(res.n_out)

@@ -225,6 +225,7 @@ int lcto_solve(const lcto_locus *L, const lcto_stage *stages, size_t n_stages, s
  * lcto_solve / lcto_solve_stage between open and close.  hap_names[H] must outlive the sink.  Not thread-safe across
  * concurrent lcto_solve calls (oracle/rust_diff.sh runs one locus at a time). */
 int  lcto_debug_open(const char *sol_path, const char *sol_ext_path, const char *const *hap_names);
+int  lcto_debug_open_depth(const char *depth_path);
 void lcto_debug_close(void);
 
 const char *lcto_version(void);

@@ -107,7 +107,7 @@ size_t lcto_truncate_ixs(uint64_t *ixs, size_t n, const double *scores, double f
  * oracle/rust_diff.sh diffs against the files of a real `locityper genotype --debug 2` run.  Row order inside a stage
  * depends on thread timing in the reference, so the comparison sorts the rows. */
 #include <stdio.h>
-static FILE *g_sol = NULL, *g_sol_ext = NULL;
+static FILE *g_sol = NULL, *g_sol_ext = NULL, *g_depth = NULL;
 static const char *const *g_hap_names = NULL;
 static unsigned g_stage_no = 0;                      /* 1-based stage of the rows being written */
 static pthread_mutex_t g_dbg_mutex = PTHREAD_MUTEX_INITIALIZER;
@@ -128,9 +128,19 @@ int lcto_debug_open(const char *sol_path, const char *sol_ext_path, const char *
     return 0;
 }
 
+/* depth.csv of `--debug 3` (DebugLvl::Full): DebugFiles::new, src/solvers/solve.rs:882-888; call after lcto_debug_open */
+int lcto_debug_open_depth(const char *depth_path) {
+    g_depth = fopen(depth_path, "w");
+    if (!g_depth) return -1;
+    fprintf(g_depth, "stage\tgenotype\tattempt\tcontig\twindow\tweight\tdepth\tlik\n");
+    return 0;
+}
+
 void lcto_debug_close(void) {
     if (g_sol) fclose(g_sol);
     if (g_sol_ext) fclose(g_sol_ext);
+    if (g_depth) fclose(g_depth);
+    g_depth = NULL;
     g_sol = g_sol_ext = NULL;
     g_hap_names = NULL;
 }
@@ -186,6 +196,19 @@ static int run_worker(stage_ctx *C, size_t w) {
                 return -1;
             }
             liks[a] = prior + out.lik;                              /* solve.rs:1126 */
+            if (g_depth) {                                          /* ReadAssignment::write_depth, assgn.rs:359-372 */
+                pthread_mutex_lock(&g_dbg_mutex);
+                for (uint32_t i = 0; i < I->ploidy; i++)
+                    for (uint32_t w = I->wshift[i]; w < I->wshift[i + 1]; w++) {
+                        double lp = I->win_trivial[w] ? 0.0
+                                  : I->win_weight[w] * L->depth_table[(size_t)I->win_gc[w] * L->depth_k + depth[w]];
+                        fprintf(g_depth, "%u\t", g_stage_no);
+                        fprint_gt(g_depth, L, g);
+                        fprintf(g_depth, "\t%u\t%u\t%u\t%.4f\t%u\t%.3f\n", a + 1, i + 1, w - I->wshift[i] + 1,
+                                I->win_weight[w], depth[w], lp * LCTO_INV_LN10);
+                    }
+                pthread_mutex_unlock(&g_dbg_mutex);
+            }
             if (g_sol_ext) {                                        /* ReadAssignment::summarize, assgn.rs:416-425 */
                 pthread_mutex_lock(&g_dbg_mutex);
                 fprintf(g_sol_ext, "%u\t", g_stage_no);

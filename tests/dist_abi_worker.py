@@ -1,6 +1,7 @@
 """Worker of tests/test_gpu_dist_abi.py: one rank of a sharded solve through the C ABI (lctp_dist_*).
 Launched by `python -m torch.distributed.run --nproc-per-node N tests/dist_abi_worker.py OUT.json`; torch.distributed
 is only the out-of-band channel for the 128-byte NCCL id and for comparing the ranks' results."""
+import hashlib
 import json
 import os
 import sys
@@ -46,7 +47,8 @@ def main():
               and list(rng_d) == list(rng_s) and got.n_filtered == ref.n_filtered and got.n_stage_in == ref.n_stage_in
               and np.array_equal(surv_d, surv_s) and got.json_text == ref.json_text)
         # identical on every rank
-        h = torch.tensor([hash(got.json_text) & 0x7FFFFFFFFFFF], dtype=torch.int64, device="cuda")
+        # (not Python's hash(): it is salted per process)
+        h = torch.tensor([int.from_bytes(hashlib.sha256(got.json_text.encode()).digest()[:6], "little")], dtype=torch.int64, device="cuda")
         hs = [torch.zeros_like(h) for _ in range(world)]
         dist.all_gather(hs, h)
         same = all(int(x) == int(hs[0]) for x in hs)
