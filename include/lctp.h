@@ -259,6 +259,34 @@ int  lctp_locus_upload_pairs(lctp_ctx *ctx, const lctp_locus *in /* pa_*, unmapp
 int  lctp_rescore_alignments(lctp_ctx *ctx, const lctp_alns *in, double *ln_prob, uint32_t *edit,
                              uint32_t *read_len, uint8_t *save);
 size_t lctp_sizeof_alns(void);
+/* SURVEY 8(f) rank 2, second slice: the per read-end protocol of read_next_alns (src/model/locs.rs:502-567) around
+ * push, with the PosCollection de-duplication of alignment starts (:166-187, 315-343), for every (read, read end) of a
+ * locus at once.  Records are grouped by (read, read end), first record of a group = the primary alignment (unmapped
+ * read ends are simply absent); secondary records come after Cigar::hard_to_soft, empty CIGARs dropped (:548-554). */
+typedef struct lctp_read_ends {
+    lctp_alns alns;                    /* passable_dist is ignored (derived per group below) */
+    uint64_t n_groups;
+    const uint64_t *grp_off;           /* [n_groups+1] */
+    const uint32_t *rec_contig;        /* [n_alns] contig id of the record */
+    const uint8_t  *grp_read_end;      /* [n_groups] 0 / 1 */
+    const uint32_t *grp_read_len;      /* record.seq().len() of the primary record */
+    const uint32_t *grp_good_dist;     /* EditDistCache::get(read_len).0 */
+    const uint32_t *grp_passable_dist; /* EditDistCache::get(read_len).1 */
+    const double   *grp_neighb_complexity;   /* ContigInfos::neighb_complexity(&primary); 1.0 for long reads (:527) */
+    double poor_compl, poor_compl_edit;      /* Params::poor_compl / poor_compl_edit */
+    uint32_t strict_subset;                  /* Data::strict_subset */
+    uint32_t _pad;
+} lctp_read_ends;
+/* Outputs, caller-allocated.  Per record [n_alns]: ln_prob, edit, read_len as in lctp_rescore_alignments.  Per group
+ * [n_groups]: ok = read_next_alns returned true; best_edit = PrelimAlignments::best_edit of the read end; weight_factor =
+ * what read_data.weight is multiplied by (:564; 1.0 when !ok); thr_dist / pass_dist = the thresholds given to
+ * set_thresholds (:536); n_kept = alignments left in PrelimAlignments::alns for this read end, kept_rec[grp_off[g] + k]
+ * = record index of the k-th of them (the order of `alns`: a better alignment of an occupied 128-bp bin replaces the
+ * earlier one in place).  A group whose primary alignment is not good enough (:538-542) has ok = 0 and n_kept = 0. */
+int  lctp_collect_read_ends(lctp_ctx *ctx, const lctp_read_ends *in, double *ln_prob, uint32_t *edit,
+                            uint32_t *read_len, uint8_t *ok, uint32_t *best_edit, double *weight_factor,
+                            uint32_t *thr_dist, uint32_t *pass_dist, uint32_t *n_kept, uint32_t *kept_rec);
+size_t lctp_sizeof_read_ends(void);
 
 /* ---- prefilter (a2 + a3) ------------------------------------------------------------------ */
 /* Scores of genotypes [g_begin, g_end) (src/solvers/solve.rs:105-119) computed on the device into the

@@ -200,6 +200,9 @@ int pairs_fetch(lctp_pairs_h *p, uint64_t cap, uint64_t *pa_off, uint32_t *pa_co
 // rescore.cu
 int rescore_alignments(lctp_ctx *ctx, const lctp_alns *in, double *ln_prob, uint32_t *edit, uint32_t *read_len,
                        uint8_t *save);
+int collect_read_ends(lctp_ctx *ctx, const lctp_read_ends *in, double *ln_prob, uint32_t *edit, uint32_t *read_len,
+                      uint8_t *ok, uint32_t *best_edit, double *weight_factor, uint32_t *thr_dist, uint32_t *pass_dist,
+                      uint32_t *n_kept, uint32_t *kept_rec);
 // solver.cu
 int launch_stage(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worker_ixs,
                  const uint64_t *worker_off, size_t n_workers, uint64_t *worker_rng,

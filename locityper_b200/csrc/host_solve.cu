@@ -431,6 +431,26 @@ int lctp_rescore_alignments(lctp_ctx *ctx, const lctp_alns *in, double *ln_prob,
     return rescore_alignments(ctx, in, ln_prob, edit, read_len, save);
 }
 
+size_t lctp_sizeof_read_ends(void) { return sizeof(lctp_read_ends); }
+
+int lctp_collect_read_ends(lctp_ctx *ctx, const lctp_read_ends *in, double *ln_prob, uint32_t *edit, uint32_t *read_len,
+                           uint8_t *ok, uint32_t *best_edit, double *weight_factor, uint32_t *thr_dist,
+                           uint32_t *pass_dist, uint32_t *n_kept, uint32_t *kept_rec) {
+    if (!ctx || !in) { set_error("lctp_collect_read_ends: NULL argument"); return LCTP_E_INVALID; }
+    const lctp_alns &a = in->alns;
+    if (a.n_alns && (!a.cigar_off || !a.cigar_ops || !a.aln_start || !a.aln_end || !a.contig_len || !in->grp_off ||
+                     !in->rec_contig || !in->grp_read_end || !in->grp_read_len || !in->grp_good_dist ||
+                     !in->grp_passable_dist || !in->grp_neighb_complexity || !ln_prob || !edit || !read_len || !ok ||
+                     !best_edit || !weight_factor || !thr_dist || !pass_dist || !n_kept || !kept_rec)) {
+        set_error("lctp_collect_read_ends: NULL array");
+        return LCTP_E_INVALID;
+    }
+    LCTP_CUDA_CHECK(cudaSetDevice(ctx->device));
+    set_alloc_stream(ctx->stream);
+    return collect_read_ends(ctx, in, ln_prob, edit, read_len, ok, best_edit, weight_factor, thr_dist, pass_dist, n_kept,
+                             kept_rec);
+}
+
 int lctp_pair_alignments(lctp_ctx *ctx, const lctp_mates *in, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig,
                          double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob,
                          uint64_t *n_out) {

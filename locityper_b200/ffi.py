@@ -107,6 +107,13 @@ class AlnsC(C.Structure):
                 ("ln_deletion", C.c_double), ("ln_clipping", C.c_double)]
 
 
+class ReadEndsC(C.Structure):
+    _fields_ = [("alns", AlnsC), ("n_groups", C.c_uint64), ("grp_off", C.c_void_p), ("rec_contig", C.c_void_p),
+                ("grp_read_end", C.c_void_p), ("grp_read_len", C.c_void_p), ("grp_good_dist", C.c_void_p),
+                ("grp_passable_dist", C.c_void_p), ("grp_neighb_complexity", C.c_void_p), ("poor_compl", C.c_double),
+                ("poor_compl_edit", C.c_double), ("strict_subset", C.c_uint32), ("_pad", C.c_uint32)]
+
+
 # Every symbol include/lctp.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -131,6 +138,8 @@ SYMBOLS = {
     "lctp_locus_upload_pairs": (C.c_int, [_P, _P, _P, _P]),
     "lctp_rescore_alignments": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "lctp_sizeof_alns": (C.c_size_t, []),
+    "lctp_sizeof_read_ends": (C.c_size_t, []),
+    "lctp_collect_read_ends": (C.c_int, [_P] * 12),
     "lctp_locus_upload": (C.c_int, [_P, _P, _P]),
     "lctp_locus_free": (None, [_P]),
     "lctp_best_aln_matrix": (C.c_int, [_P, _P]),
@@ -196,6 +205,7 @@ def load():
         assert lib.lctp_sizeof_result() == C.sizeof(ResultC)
         assert lib.lctp_sizeof_mates() == C.sizeof(MatesC)
         assert lib.lctp_sizeof_alns() == C.sizeof(AlnsC)
+        assert lib.lctp_sizeof_read_ends() == C.sizeof(ReadEndsC)
         _lib = lib
     return _lib
 

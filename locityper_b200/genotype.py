@@ -396,6 +396,66 @@ class Alns:
         return c
 
 
+@dataclass
+class ReadEnds:
+    """Alignment records grouped by (read, read end) + the per-group inputs of read_next_alns (src/model/locs.rs:502-567)."""
+
+    alns: Alns                     # passable_dist ignored
+    grp_off: np.ndarray
+    rec_contig: np.ndarray
+    grp_read_end: np.ndarray
+    grp_read_len: np.ndarray
+    grp_good_dist: np.ndarray
+    grp_passable_dist: np.ndarray
+    grp_neighb_complexity: np.ndarray
+    poor_compl: float
+    poor_compl_edit: float
+    strict_subset: bool = False
+
+    @property
+    def n_groups(self) -> int:
+        return len(self.grp_off) - 1
+
+    def to_c(self, keep: list, struct=None, alns_struct=None):
+        def arr(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data
+        c = (struct or ffi.ReadEndsC)()
+        c.alns = self.alns.to_c(keep, struct=alns_struct)
+        c.n_groups = self.n_groups
+        c.grp_off = arr(self.grp_off, np.uint64)
+        c.rec_contig = arr(self.rec_contig, np.uint32)
+        c.grp_read_end = arr(self.grp_read_end, np.uint8)
+        c.grp_read_len = arr(self.grp_read_len, np.uint32)
+        c.grp_good_dist = arr(self.grp_good_dist, np.uint32)
+        c.grp_passable_dist = arr(self.grp_passable_dist, np.uint32)
+        c.grp_neighb_complexity = arr(self.grp_neighb_complexity, np.float64)
+        c.poor_compl, c.poor_compl_edit, c.strict_subset = float(self.poor_compl), float(self.poor_compl_edit), int(self.strict_subset)
+        return c
+
+
+def _read_ends_outputs(re_: ReadEnds) -> dict:
+    n, ng = re_.alns.n_alns, re_.n_groups
+    return dict(ln_prob=np.zeros(n), edit=np.zeros(n, dtype=np.uint32), read_len=np.zeros(n, dtype=np.uint32),
+                ok=np.zeros(ng, dtype=np.uint8), best_edit=np.zeros(ng, dtype=np.uint32), weight_factor=np.zeros(ng),
+                thr_dist=np.zeros(ng, dtype=np.uint32), pass_dist=np.zeros(ng, dtype=np.uint32),
+                n_kept=np.zeros(ng, dtype=np.uint32), kept_rec=np.full(n, 0xFFFFFFFF, dtype=np.uint32))
+
+
+READ_ENDS_OUT_ORDER = ("ln_prob", "edit", "read_len", "ok", "best_edit", "weight_factor", "thr_dist", "pass_dist", "n_kept",
+                       "kept_rec")
+
+
+def collect_read_ends(ctx: "Context", re_: ReadEnds) -> dict:
+    """lctp_collect_read_ends: the read_next_alns protocol + PosCollection de-duplication for every read end, on the device."""
+    keep: list = []
+    c = re_.to_c(keep)
+    out = _read_ends_outputs(re_)
+    ffi.check(ctx.lib.lctp_collect_read_ends(ctx._h, C.byref(c), *[out[k].ctypes.data for k in READ_ENDS_OUT_ORDER]))
+    return out
+
+
 def rescore_alignments(ctx: "Context", alns: Alns) -> dict:
     """lctp_rescore_alignments: ln_prob / EditDist / save of every alignment record, computed on the device."""
     keep: list = []

@@ -267,6 +267,25 @@ typedef struct lcto_alns {
 
 int lcto_rescore_alignments(const lcto_alns *in, double *ln_prob, uint32_t *edit, uint32_t *read_len, uint8_t *save);
 
+/* second slice: the per read-end protocol around push (read_next_alns, src/model/locs.rs:502-567) with the PosCollection
+ * de-duplication of alignment starts (:166-187, 315-343).  Records are grouped by (read, read end); the first record of a
+ * group is the primary alignment. */
+typedef struct lcto_read_ends {
+    lcto_alns alns;                    /* passable_dist is ignored (derived per group) */
+    uint64_t n_groups;
+    const uint64_t *grp_off;           /* [n_groups+1] */
+    const uint32_t *rec_contig;        /* [n_alns] */
+    const uint8_t  *grp_read_end;      /* [n_groups] 0 / 1 */
+    const uint32_t *grp_read_len;      /* record.seq().len() */
+    const uint32_t *grp_good_dist, *grp_passable_dist;    /* EditDistCache::get(read_len) */
+    const double   *grp_neighb_complexity;                /* 1.0 for long reads (locs.rs:527) */
+    double poor_compl, poor_compl_edit;                   /* Params */
+    uint32_t strict_subset;
+} lcto_read_ends;
+int lcto_collect_read_ends(const lcto_read_ends *in, double *ln_prob, uint32_t *edit, uint32_t *read_len,
+                           uint8_t *ok, uint32_t *best_edit, double *weight_factor, uint32_t *thr_dist,
+                           uint32_t *pass_dist, uint32_t *n_kept, uint32_t *kept_rec);
+
 #ifdef __cplusplus
 }
 #endif

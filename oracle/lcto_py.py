@@ -466,3 +466,27 @@ def rescore_alignments(alns) -> dict:
     if rc != 0:
         raise RuntimeError(f"lcto_rescore_alignments failed: {rc}")
     return dict(ln_prob=ln_prob, edit=edit, read_len=read_len, save=save)
+
+
+class ReadEndsC(C.Structure):
+    _fields_ = [("alns", AlnsC), ("n_groups", C.c_uint64), ("grp_off", C.c_void_p), ("rec_contig", C.c_void_p),
+                ("grp_read_end", C.c_void_p), ("grp_read_len", C.c_void_p), ("grp_good_dist", C.c_void_p),
+                ("grp_passable_dist", C.c_void_p), ("grp_neighb_complexity", C.c_void_p), ("poor_compl", C.c_double),
+                ("poor_compl_edit", C.c_double), ("strict_subset", C.c_uint32)]
+
+
+def collect_read_ends(re_) -> dict:
+    """lcto_collect_read_ends on a locityper_b200.genotype.ReadEnds-shaped object (plain data)."""
+    keep: list = []
+    c = re_.to_c(keep, struct=ReadEndsC, alns_struct=AlnsC)
+    n, ng = re_.alns.n_alns, re_.n_groups
+    out = dict(ln_prob=np.zeros(n), edit=np.zeros(n, dtype=np.uint32), read_len=np.zeros(n, dtype=np.uint32),
+               ok=np.zeros(ng, dtype=np.uint8), best_edit=np.zeros(ng, dtype=np.uint32), weight_factor=np.zeros(ng),
+               thr_dist=np.zeros(ng, dtype=np.uint32), pass_dist=np.zeros(ng, dtype=np.uint32),
+               n_kept=np.zeros(ng, dtype=np.uint32), kept_rec=np.full(n, 0xFFFFFFFF, dtype=np.uint32))
+    order = ("ln_prob", "edit", "read_len", "ok", "best_edit", "weight_factor", "thr_dist", "pass_dist", "n_kept", "kept_rec")
+    lib().lcto_collect_read_ends.argtypes = [C.c_void_p] * 11
+    rc = lib().lcto_collect_read_ends(C.byref(c), *[out[k].ctypes.data for k in order])
+    if rc != 0:
+        raise RuntimeError(f"lcto_collect_read_ends failed: {rc}")
+    return out

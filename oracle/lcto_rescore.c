@@ -48,3 +48,73 @@ int lcto_rescore_alignments(const lcto_alns *in, double *ln_prob, uint32_t *edit
     }
     return 0;
 }
+
+/* ---- second slice: read_next_alns (src/model/locs.rs:502-567) + PrelimAlignments::push with the PosCollection
+ * (:166-187, 297-343).  Plain restatement: the map is a linear list of (key, value) per group.  Pinned by a
+ * statement-by-statement Python transcription (dict) in tests/test_rescore.py. */
+#include <stdlib.h>
+#include <math.h>
+
+#define NOT_SAVED 0xFFFFFFFFu                                               /* locs.rs:209 */
+
+int lcto_collect_read_ends(const lcto_read_ends *in, double *ln_prob, uint32_t *edit, uint32_t *read_len,
+                           uint8_t *ok, uint32_t *best_edit, double *weight_factor, uint32_t *thr_dist,
+                           uint32_t *pass_dist, uint32_t *n_kept, uint32_t *kept_rec) {
+    const uint64_t n = in->alns.n_alns;
+    uint8_t *save = (uint8_t *)malloc(n ? n : 1);
+    lcto_alns a = in->alns;
+    uint32_t *inf = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
+    for (uint64_t i = 0; i < n; i++) inf[i] = 0xFFFFFFFFu;
+    a.passable_dist = inf;
+    int rc = lcto_rescore_alignments(&a, ln_prob, edit, read_len, save);   /* the per-alignment part of push, :304-307 */
+    free(save); free(inf);
+    if (rc) return rc;
+    uint64_t max_grp = 1;
+    for (uint64_t g = 0; g < in->n_groups; g++)
+        if (in->grp_off[g + 1] - in->grp_off[g] > max_grp) max_grp = in->grp_off[g + 1] - in->grp_off[g];
+    uint64_t *keys = (uint64_t *)malloc(sizeof(uint64_t) * max_grp);
+    uint32_t *vals = (uint32_t *)malloc(sizeof(uint32_t) * max_grp);
+    for (uint64_t g = 0; g < in->n_groups; g++) {
+        const uint64_t b = in->grp_off[g], e = in->grp_off[g + 1];
+        const uint32_t rl = in->grp_read_len[g], good = in->grp_good_dist[g];
+        uint32_t passable = in->grp_passable_dist[g], threshold = good;     /* locs.rs:529-530 */
+        if (in->grp_neighb_complexity[g] <= in->poor_compl) {               /* :531-534 */
+            double v = in->poor_compl_edit * (double)rl;
+            uint32_t t = v != v || v <= 0.0 ? 0u : (v >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)v);   /* `as u32` */
+            threshold = good > t ? good : t;
+            passable += threshold - good;
+        }
+        thr_dist[g] = threshold; pass_dist[g] = passable;
+        uint32_t be = 0xFFFFFFFFu, kept = 0;
+        uint64_t n_map = 0;
+        int failed = 0;
+        for (uint64_t i = b; i < e && !failed; i++) {                       /* push, :297-343 */
+            if (edit[i] < be) be = edit[i];                                 /* :308 */
+            const uint32_t new_ix = kept;
+            const int sv = edit[i] <= passable;                             /* :312 */
+            if (new_ix == 0 && !sv) { failed = 1; break; }                  /* :314-316 (only the primary can get here) */
+            const uint64_t key = ((uint64_t)in->grp_read_end[g] << 48) | ((uint64_t)in->rec_contig[i] << 32)
+                               | (uint64_t)(in->alns.aln_start[i] >> 7);     /* encode, :166-168 */
+            uint64_t q = 0;
+            while (q < n_map && keys[q] != key) q++;
+            if (q < n_map) {                                                /* Entry::Occupied */
+                if (sv) {
+                    if (vals[q] == NOT_SAVED) { vals[q] = new_ix; kept_rec[b + kept++] = (uint32_t)i; }       /* :322-325 */
+                    else if (ln_prob[i] > ln_prob[kept_rec[b + vals[q]]]) kept_rec[b + vals[q]] = (uint32_t)i; /* :326-329 */
+                }
+            } else {                                                        /* Entry::Vacant */
+                keys[n_map] = key;
+                if (sv) { vals[n_map] = new_ix; kept_rec[b + kept++] = (uint32_t)i; }                        /* :333-336 */
+                else vals[n_map] = NOT_SAVED;                                                                 /* :337-339 */
+                n_map++;
+            }
+        }
+        best_edit[g] = be;
+        n_kept[g] = failed ? 0 : kept;
+        const uint32_t req = in->strict_subset ? passable : threshold;      /* :560 */
+        ok[g] = (!failed && be <= req) ? 1 : 0;                             /* :538-542, 561-563 */
+        weight_factor[g] = (!ok[g] || be <= good) ? 1.0 : sqrt((double)good / (double)be);   /* :564 (only on success) */
+    }
+    free(keys); free(vals);
+    return 0;
+}

@@ -164,3 +164,152 @@ def test_device_reproduces_golden_rescoring(gpu_ctx):
     from conftest import load_golden_alns
     a, want = load_golden_alns()
     assert _same(genotype.rescore_alignments(gpu_ctx, a), want)
+
+
+# ---- second slice: read_next_alns (src/model/locs.rs:502-567) + push with the PosCollection (:166-187, 297-343) ----
+
+NOT_SAVED = 0xFFFFFFFF
+
+
+def _read_ends(n_groups, seed, *, contigs=6, per_group=(1, 40), poor_frac=0.5, strict=False, contig_len=3500):
+    """Groups of alignment records: the starts of a group cluster around a few positions per contig, so that 128-bp bins
+    are hit repeatedly (replacement, NOT_SAVED bins) and the order of the records matters."""
+    rng = np.random.default_rng(seed)
+    sizes = rng.integers(per_group[0], per_group[1] + 1, n_groups)
+    off = np.r_[0, np.cumsum(sizes)].astype(np.uint64)
+    n = int(off[-1])
+    kw = synth.make_alns(n, seed + 1, contig_len=contig_len)
+    rec_contig = np.zeros(n, dtype=np.uint32)
+    for g in range(n_groups):
+        b, e = int(off[g]), int(off[g + 1])
+        anchors = rng.integers(0, contig_len - 400, 3)
+        rec_contig[b:e] = rng.integers(0, contigs, e - b)
+        span = (kw["aln_end"][b:e] - kw["aln_start"][b:e]).astype(np.int64)
+        st = (anchors[rng.integers(0, 3, e - b)] + rng.integers(-90, 91, e - b)).clip(0, None)
+        st = np.minimum(st, contig_len - span).clip(0, None)
+        kw["aln_start"][b:e] = st
+        kw["aln_end"][b:e] = st + span
+    good = rng.integers(2, 14, n_groups).astype(np.uint32)
+    passable = (good + rng.integers(0, 12, n_groups)).astype(np.uint32)
+    compl = np.where(rng.random(n_groups) < poor_frac, rng.random(n_groups) * 0.5, 0.5 + rng.random(n_groups) * 0.5)
+    return genotype.ReadEnds(alns=genotype.Alns(**kw), grp_off=off, rec_contig=rec_contig,
+                             grp_read_end=rng.integers(0, 2, n_groups).astype(np.uint8),
+                             grp_read_len=rng.integers(100, 251, n_groups).astype(np.uint32), grp_good_dist=good,
+                             grp_passable_dist=passable, grp_neighb_complexity=compl, poor_compl=0.5,
+                             poor_compl_edit=0.15, strict_subset=strict)
+
+
+def _transcription_read_ends(re_: genotype.ReadEnds) -> dict:
+    """read_next_alns + PrelimAlignments::push, line by line; the PosCollection is a dict like the reference's IntMap."""
+    import math
+    a = re_.alns
+    per = _transcription(genotype.Alns(**{**a.__dict__, "passable_dist": np.full(a.n_alns, NOT_SAVED, dtype=np.uint32)}))
+    n, ng = a.n_alns, re_.n_groups
+    out = dict(ln_prob=per["ln_prob"], edit=per["edit"], read_len=per["read_len"], ok=np.zeros(ng, dtype=np.uint8),
+               best_edit=np.zeros(ng, dtype=np.uint32), weight_factor=np.ones(ng), thr_dist=np.zeros(ng, dtype=np.uint32),
+               pass_dist=np.zeros(ng, dtype=np.uint32), n_kept=np.zeros(ng, dtype=np.uint32),
+               kept_rec=np.full(n, NOT_SAVED, dtype=np.uint32))
+    for g in range(ng):
+        b, e = int(re_.grp_off[g]), int(re_.grp_off[g + 1])
+        read_len = int(re_.grp_read_len[g])
+        good_dist, passable_dist = int(re_.grp_good_dist[g]), int(re_.grp_passable_dist[g])     # locs.rs:529
+        threshold_dist = good_dist                                                              # :530
+        if re_.grp_neighb_complexity[g] <= re_.poor_compl:                                      # :531
+            threshold_dist = max(good_dist, int(re_.poor_compl_edit * float(read_len)))         # :532 (`as u32` truncates)
+            passable_dist += threshold_dist - good_dist                                         # :533
+        out["thr_dist"][g], out["pass_dist"][g] = threshold_dist, passable_dist                 # set_thresholds, :536
+        alns, pos_collection = [], {}                       # PrelimAlignments::alns (record indices), PosCollection::map
+        best_edit, primary_ok = NOT_SAVED, True
+        for i in range(b, e):                                                                   # push, :297-343
+            dist_edit, aln_prob = int(per["edit"][i]), float(per["ln_prob"][i])
+            best_edit = min(best_edit, dist_edit)                                               # :308
+            new_aln_ix = len(alns)                                                              # :311
+            save = dist_edit <= passable_dist                                                   # :312
+            if new_aln_ix == 0 and not save:                                                    # :314-316
+                assert i == b
+                primary_ok = False
+                break                                                                           # skip_until_primary, :539-541
+            key = (int(re_.grp_read_end[g]) << 48) | (int(re_.rec_contig[i]) << 32) | (int(a.aln_start[i]) >> 7)   # :166-168
+            if key in pos_collection and save:                                                  # (Occupied, true)
+                aln_ix = pos_collection[key]
+                if aln_ix == NOT_SAVED:
+                    pos_collection[key] = new_aln_ix
+                    alns.append(i)
+                elif aln_prob > float(per["ln_prob"][alns[aln_ix]]):
+                    alns[aln_ix] = i
+            elif key in pos_collection:                                                         # (Occupied, false)
+                pass
+            elif save:                                                                          # (Vacant, true)
+                pos_collection[key] = new_aln_ix
+                alns.append(i)
+            else:                                                                               # (Vacant, false)
+                pos_collection[key] = NOT_SAVED
+        out["best_edit"][g] = best_edit
+        if not primary_ok:
+            continue
+        out["n_kept"][g] = len(alns)
+        out["kept_rec"][b:b + len(alns)] = alns
+        req_edit = passable_dist if re_.strict_subset else threshold_dist                       # :560
+        if best_edit > req_edit:                                                                # :561-563
+            continue
+        out["ok"][g] = 1
+        out["weight_factor"][g] = 1.0 if best_edit <= good_dist else math.sqrt(float(good_dist) / float(best_edit))   # :564
+    return out
+
+
+def _same_ends(x, y):
+    for k in genotype.READ_ENDS_OUT_ORDER:
+        assert np.array_equal(x[k], y[k]), k
+
+
+@pytest.mark.parametrize("seed,strict", [(1, False), (2, True), (3, False)])
+def test_oracle_read_ends_equal_python_transcription(oracle, seed, strict):
+    re_ = _read_ends(300, seed, strict=strict)
+    got = oracle.collect_read_ends(re_)
+    ref = _transcription_read_ends(re_)
+    _same_ends(got, ref)
+    # the cases the protocol distinguishes all occur in the generated data
+    assert 0 < got["ok"].sum() < re_.n_groups
+    assert (got["n_kept"] == 0).any() and (got["n_kept"] > 1).any()
+    assert ((got["weight_factor"] < 1.0) & (got["ok"] == 1)).any()
+    sizes = np.diff(re_.grp_off.astype(np.int64))
+    assert (got["n_kept"] < sizes).any()                       # bins shared by several records
+
+
+def test_oracle_read_ends_hand_checked(oracle):
+    """One group, contig 0, passable 3: primary at 1000 (edit 0); 1010 same bin, worse -> dropped; 1020 same bin, better
+    -> replaces the primary in place; 1200 other bin with edit 5 -> NOT_SAVED bin; 1210 same bin, edit 1 -> saved as #2."""
+    recs = [("100=", 1000, 1100, 5000, 0), ("98=2X", 1010, 1110, 5000, 0), ("100=", 1020, 1120, 5000, 0),
+            ("95=5X", 1200, 1300, 5000, 0), ("99=1X", 1210, 1310, 5000, 0)]
+    a = _alns(recs, ln_oper=(-0.005, -5.8, -6.5, -6.9, -5.8))
+    re_ = genotype.ReadEnds(alns=a, grp_off=np.array([0, 5], dtype=np.uint64), rec_contig=np.zeros(5, dtype=np.uint32),
+                            grp_read_end=np.array([0], dtype=np.uint8), grp_read_len=np.array([100], dtype=np.uint32),
+                            grp_good_dist=np.array([2], dtype=np.uint32), grp_passable_dist=np.array([3], dtype=np.uint32),
+                            grp_neighb_complexity=np.array([1.0]), poor_compl=0.5, poor_compl_edit=0.07)
+    got = oracle.collect_read_ends(re_)
+    assert list(got["edit"]) == [0, 2, 0, 5, 1]
+    assert got["ok"][0] == 1 and got["n_kept"][0] == 2 and got["best_edit"][0] == 0 and got["weight_factor"][0] == 1.0
+    # equal ln-probabilities do not replace (strict '>'), so the primary keeps slot 0; slot 1 is the record at 1210
+    assert list(got["kept_rec"][:2]) == [0, 4]
+    _same_ends(got, _transcription_read_ends(re_))
+    # a primary above `passable` ends the read end at once
+    re_.alns = _alns([("90=10X", 1000, 1100, 5000, 0)] + recs[1:])
+    got = oracle.collect_read_ends(re_)
+    assert got["ok"][0] == 0 and got["n_kept"][0] == 0 and got["best_edit"][0] == 10
+    _same_ends(got, _transcription_read_ends(re_))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_groups,seed,strict,per_group", [(300, 1, False, (1, 40)), (300, 2, True, (1, 40)),
+                                                              (4000, 5, False, (1, 120)), (2, 7, False, (600, 900))])
+def test_device_read_ends_bit_exact(oracle, gpu_ctx, n_groups, seed, strict, per_group):
+    re_ = _read_ends(n_groups, seed, strict=strict, per_group=per_group)
+    _same_ends(genotype.collect_read_ends(gpu_ctx, re_), oracle.collect_read_ends(re_))
+
+
+@pytest.mark.gpu
+def test_device_read_ends_reject_malformed_input(gpu_ctx):
+    re_ = _read_ends(5, 9)
+    re_.grp_off = re_.grp_off.copy(); re_.grp_off[-1] -= 1
+    with pytest.raises(Exception):
+        genotype.collect_read_ends(gpu_ctx, re_)
