@@ -146,6 +146,10 @@ typedef struct lctp_stats {
     uint64_t rescore_launches;
     uint64_t rescore_alns;         /* alignment records rescored */
     uint64_t rescore_ops;          /* CIGAR operations read */
+    double   recruit_ms;           /* sum of the minimizer / recruitment kernel durations */
+    uint64_t recruit_launches;
+    uint64_t recruit_bases;        /* sequence bytes scanned */
+    uint64_t recruit_reads;        /* reads (pairs) recruited against the targets */
     uint64_t h2d_bytes;            /* bytes copied host -> device by the library's calls on this context */
     uint64_t d2h_bytes;            /* bytes copied device -> host */
 } lctp_stats;
@@ -287,6 +291,50 @@ int  lctp_collect_read_ends(lctp_ctx *ctx, const lctp_read_ends *in, double *ln_
                             uint32_t *read_len, uint8_t *ok, uint32_t *best_edit, double *weight_factor,
                             uint32_t *thr_dist, uint32_t *pass_dist, uint32_t *n_kept, uint32_t *kept_rec);
 size_t lctp_sizeof_read_ends(void);
+
+/* ---- SURVEY 8(f) rank 3, first slice: short-read recruitment ---------------------------------------------------------
+ * Canonical minimizers (kmers::minimizers::<u64, _, CANONICAL>, src/seq/kmers.rs:71-103, 256-340) of n sequences
+ * (ASCII A/C/G/T, anything else is an N) on the device.  Outputs of sequence s start at off[s] in hash / pos / fw (a
+ * sequence has fewer minimizers than bases) and count[s] says how many there are: hash = fast_hash of the canonical
+ * k-mer (what the reference stores as "the minimizer"), pos = start of the k-mer, fw = 1 if the forward k-mer was the
+ * canonical one. */
+int  lctp_minimizers(lctp_ctx *ctx, const uint8_t *seqs, const uint64_t *off, uint64_t n, uint32_t k, uint32_t w,
+                     uint32_t *count, uint64_t *hash, uint32_t *pos, uint8_t *fw);
+/* Fraction::<u16>::approximate (src/math/frac.rs:48-80): Params::match_frac_short */
+void lctp_fraction_approximate_u16(double x, uint16_t *num, uint16_t *den);
+/* Recruitment targets = TargetBuilder::add for every locus + finalize (src/seq/recruit.rs:680-760). */
+typedef struct lctp_target_seqs {
+    uint64_t n_seqs;
+    const uint64_t *seq_off;        /* [n_seqs+1] into seqs */
+    const uint8_t  *seqs;
+    const uint32_t *seq_locus;      /* [n_seqs] locus index of the sequence, ascending (add() is called locus by locus) */
+    const uint64_t *cnt_off;        /* [n_seqs+1] into kmer_counts */
+    const uint16_t *kmer_counts;    /* KmerCounts of the sequence: len + 1 - base_k entries (the reference asserts) */
+    uint32_t base_k;                /* KmerCounts::k() */
+    uint32_t minimizer_k, minimizer_w;   /* Params::minimizer_k / minimizer_w */
+    uint32_t thresh_kmer_count;     /* Params::thresh_kmer_count */
+    double match_frac;              /* Params::match_frac */
+} lctp_target_seqs;
+typedef struct lctp_targets_h lctp_targets_h;
+int  lctp_targets_build(lctp_ctx *ctx, const lctp_target_seqs *in, lctp_targets_h **out);
+void lctp_targets_free(lctp_targets_h *t);
+/* minim_to_loci flattened in insertion order: (minimizer, locus, info = direction | rare << 2); returns the entry count */
+uint64_t lctp_targets_entries(const lctp_targets_h *t, uint64_t *key, uint32_t *locus, uint8_t *info, uint64_t cap);
+void lctp_targets_match_frac(const lctp_targets_h *t, uint16_t *num, uint16_t *den);
+/* Reads: first mates (or single-end reads) and, when off2 / seq2 are given, the second mates of the same pairs. */
+typedef struct lctp_reads {
+    uint64_t n_reads;
+    const uint64_t *off1; const uint8_t *seq1;
+    const uint64_t *off2; const uint8_t *seq2;     /* NULL = single-end */
+} lctp_reads;
+/* recruit_short_read (src/seq/recruit.rs:852-881) / recruit_read_pair (:885-930) for every read (pair): ans_count[r] loci,
+ * ans_locus[r * cap ..] their indices in ascending order (the reference's answer is a set).  Reads longer than 500 bp
+ * (READ_LENGTH_THRESH) are refused: recruit_long_read is not covered.  LCTP_E_CAPACITY when a read matches more than 8
+ * loci; ans_count[r] > cap means the list of that read was cut at cap. */
+int  lctp_recruit_short(lctp_ctx *ctx, const lctp_targets_h *t, const lctp_reads *reads, uint32_t cap,
+                        uint32_t *ans_count, uint32_t *ans_locus);
+size_t lctp_sizeof_target_seqs(void);
+size_t lctp_sizeof_reads(void);
 
 /* ---- prefilter (a2 + a3) ------------------------------------------------------------------ */
 /* Scores of genotypes [g_begin, g_end) (src/solvers/solve.rs:105-119) computed on the device into the

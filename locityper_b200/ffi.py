@@ -82,7 +82,9 @@ class StatsC(C.Structure):
                 ("pairing_ms", C.c_double), ("pairing_launches", C.c_uint64), ("pairing_mates", C.c_uint64),
                 ("pairing_pairs", C.c_uint64),
                 ("rescore_ms", C.c_double), ("rescore_launches", C.c_uint64), ("rescore_alns", C.c_uint64),
-                ("rescore_ops", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("rescore_ops", C.c_uint64),
+                ("recruit_ms", C.c_double), ("recruit_launches", C.c_uint64), ("recruit_bases", C.c_uint64),
+                ("recruit_reads", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 class DistTimingC(C.Structure):
@@ -114,6 +116,17 @@ class ReadEndsC(C.Structure):
                 ("poor_compl_edit", C.c_double), ("strict_subset", C.c_uint32), ("_pad", C.c_uint32)]
 
 
+class TargetSeqsC(C.Structure):
+    _fields_ = [("n_seqs", C.c_uint64), ("seq_off", C.c_void_p), ("seqs", C.c_void_p), ("seq_locus", C.c_void_p),
+                ("cnt_off", C.c_void_p), ("kmer_counts", C.c_void_p), ("base_k", C.c_uint32), ("minimizer_k", C.c_uint32),
+                ("minimizer_w", C.c_uint32), ("thresh_kmer_count", C.c_uint32), ("match_frac", C.c_double)]
+
+
+class ReadsC(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("off1", C.c_void_p), ("seq1", C.c_void_p), ("off2", C.c_void_p),
+                ("seq2", C.c_void_p)]
+
+
 # Every symbol include/lctp.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -138,6 +151,15 @@ SYMBOLS = {
     "lctp_locus_upload_pairs": (C.c_int, [_P, _P, _P, _P]),
     "lctp_rescore_alignments": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "lctp_sizeof_alns": (C.c_size_t, []),
+    "lctp_minimizers": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
+    "lctp_fraction_approximate_u16": (None, [C.c_double, _P, _P]),
+    "lctp_targets_build": (C.c_int, [_P, _P, _P]),
+    "lctp_targets_free": (None, [_P]),
+    "lctp_targets_entries": (C.c_uint64, [_P, _P, _P, _P, C.c_uint64]),
+    "lctp_targets_match_frac": (None, [_P, _P, _P]),
+    "lctp_recruit_short": (C.c_int, [_P, _P, _P, C.c_uint32, _P, _P]),
+    "lctp_sizeof_target_seqs": (C.c_size_t, []),
+    "lctp_sizeof_reads": (C.c_size_t, []),
     "lctp_sizeof_read_ends": (C.c_size_t, []),
     "lctp_collect_read_ends": (C.c_int, [_P] * 12),
     "lctp_locus_upload": (C.c_int, [_P, _P, _P]),
@@ -206,6 +228,7 @@ def load():
         assert lib.lctp_sizeof_mates() == C.sizeof(MatesC)
         assert lib.lctp_sizeof_alns() == C.sizeof(AlnsC)
         assert lib.lctp_sizeof_read_ends() == C.sizeof(ReadEndsC)
+        assert lib.lctp_sizeof_target_seqs() == C.sizeof(TargetSeqsC) and lib.lctp_sizeof_reads() == C.sizeof(ReadsC)
         _lib = lib
     return _lib
 

@@ -396,6 +396,120 @@ class Alns:
         return c
 
 
+def _concat(seqs: Sequence[bytes]):
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(s) for s in seqs])
+    return off, np.frombuffer(b"".join(seqs) or b"\0", dtype=np.uint8).copy()
+
+
+def minimizers(ctx: "Context", seqs: Sequence[bytes], k: int, w: int):
+    """lctp_minimizers: canonical minimizers (kmers::minimizers::<u64,_,CANONICAL>) of every sequence, on the device.
+    Returns a list of (hash u64[], pos u32[], forward u8[]) per sequence."""
+    off, buf = _concat(seqs)
+    n, total = len(seqs), max(1, int(off[-1]))
+    cnt = np.zeros(n, dtype=np.uint32)
+    h, p, f = np.zeros(total, dtype=np.uint64), np.zeros(total, dtype=np.uint32), np.zeros(total, dtype=np.uint8)
+    ffi.check(ctx.lib.lctp_minimizers(ctx._h, buf.ctypes.data, off.ctypes.data, n, k, w, cnt.ctypes.data, h.ctypes.data,
+                                      p.ctypes.data, f.ctypes.data))
+    return [(h[int(off[s]):int(off[s]) + int(cnt[s])].copy(), p[int(off[s]):int(off[s]) + int(cnt[s])].copy(),
+             f[int(off[s]):int(off[s]) + int(cnt[s])].copy()) for s in range(n)]
+
+
+@dataclass
+class TargetSeqs:
+    """Input of TargetBuilder::add for every locus (src/seq/recruit.rs:680-735): the allele sequences of each locus, their
+    k-mer counts (KmerCounts: one u16 per base_k-mer of the sequence) and the recruitment Params."""
+
+    seqs: Sequence[bytes]
+    seq_locus: np.ndarray
+    kmer_counts: Sequence[np.ndarray]
+    base_k: int
+    minimizer_k: int
+    minimizer_w: int
+    thresh_kmer_count: int
+    match_frac: float
+
+    def to_c(self, keep: list, struct=None):
+        def arr(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data
+        off, buf = _concat(self.seqs)
+        coff = np.zeros(len(self.seqs) + 1, dtype=np.uint64)
+        coff[1:] = np.cumsum([len(c) for c in self.kmer_counts])
+        c = (struct or ffi.TargetSeqsC)()
+        c.n_seqs = len(self.seqs)
+        c.seq_off, c.seqs, c.seq_locus = arr(off, np.uint64), arr(buf, np.uint8), arr(self.seq_locus, np.uint32)
+        c.cnt_off = arr(coff, np.uint64)
+        c.kmer_counts = arr(np.concatenate(self.kmer_counts) if len(self.kmer_counts) else np.zeros(1), np.uint16)
+        c.base_k, c.minimizer_k, c.minimizer_w = int(self.base_k), int(self.minimizer_k), int(self.minimizer_w)
+        c.thresh_kmer_count, c.match_frac = int(self.thresh_kmer_count), float(self.match_frac)
+        return c
+
+
+@dataclass
+class Reads:
+    """Short reads: first mates (or single-end reads) and optionally the second mates of the same pairs."""
+
+    seq1: Sequence[bytes]
+    seq2: Optional[Sequence[bytes]] = None
+
+    def to_c(self, keep: list, struct=None):
+        c = (struct or ffi.ReadsC)()
+        c.n_reads = len(self.seq1)
+        for name, seqs in (("1", self.seq1), ("2", self.seq2)):
+            if seqs is None:
+                continue
+            off, buf = _concat(seqs)
+            keep += [off, buf]
+            setattr(c, "off" + name, off.ctypes.data)
+            setattr(c, "seq" + name, buf.ctypes.data)
+        return c
+
+
+class Targets:
+    """lctp_targets_h: the recruitment targets (minimizer -> loci table) resident on the device."""
+
+    def __init__(self, ctx: "Context", ts: TargetSeqs):
+        self.ctx, self.lib = ctx, ctx.lib
+        keep: list = []
+        c = ts.to_c(keep)
+        self._h = C.c_void_p()
+        ffi.check(self.lib.lctp_targets_build(ctx._h, C.byref(c), C.byref(self._h)))
+
+    def entries(self):
+        n = int(self.lib.lctp_targets_entries(self._h, None, None, None, 0))
+        k, l, i = np.zeros(max(1, n), dtype=np.uint64), np.zeros(max(1, n), dtype=np.uint32), np.zeros(max(1, n), dtype=np.uint8)
+        self.lib.lctp_targets_entries(self._h, k.ctypes.data, l.ctypes.data, i.ctypes.data, n)
+        return k[:n], l[:n], i[:n]
+
+    def match_frac(self):
+        a, b = C.c_uint16(), C.c_uint16()
+        self.lib.lctp_targets_match_frac(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def recruit(self, reads: Reads, cap: int = 8):
+        """lctp_recruit_short: per read (pair) the sorted list of loci it is recruited to."""
+        keep: list = []
+        c = reads.to_c(keep)
+        n = len(reads.seq1)
+        cnt = np.zeros(max(1, n), dtype=np.uint32)
+        ans = np.zeros(max(1, n) * cap, dtype=np.uint32)
+        ffi.check(self.lib.lctp_recruit_short(self.ctx._h, self._h, C.byref(c), cap, cnt.ctypes.data, ans.ctypes.data))
+        return [list(ans[r * cap:r * cap + min(int(cnt[r]), cap)]) for r in range(n)]
+
+    def free(self) -> None:
+        if self._h:
+            self.lib.lctp_targets_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 @dataclass
 class ReadEnds:
     """Alignment records grouped by (read, read end) + the per-group inputs of read_next_alns (src/model/locs.rs:502-567)."""

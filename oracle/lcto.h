@@ -286,6 +286,31 @@ int lcto_collect_read_ends(const lcto_read_ends *in, double *ln_prob, uint32_t *
                            uint8_t *ok, uint32_t *best_edit, double *weight_factor, uint32_t *thr_dist,
                            uint32_t *pass_dist, uint32_t *n_kept, uint32_t *kept_rec);
 
+/* ------------------------------------------------ short-read recruitment (lcto_recruit.c) */
+
+typedef struct lcto_target_seqs {
+    uint64_t n_seqs;
+    const uint64_t *seq_off;        /* [n_seqs+1] into seqs */
+    const uint8_t  *seqs;           /* ASCII, A/C/G/T; anything else is an N */
+    const uint32_t *seq_locus;      /* [n_seqs] locus index, ascending (TargetBuilder::add is called locus by locus) */
+    const uint64_t *cnt_off;        /* [n_seqs+1] into kmer_counts */
+    const uint16_t *kmer_counts;    /* KmerCounts of the sequence: len + 1 - base_k entries */
+    uint32_t base_k, minimizer_k, minimizer_w, thresh_kmer_count;
+    double match_frac;
+} lcto_target_seqs;
+typedef struct lcto_reads {
+    uint64_t n_reads;
+    const uint64_t *off1; const uint8_t *seq1;      /* first mates / single-end reads */
+    const uint64_t *off2; const uint8_t *seq2;      /* second mates; NULL = single-end */
+} lcto_reads;
+typedef struct lcto_targets lcto_targets;
+size_t lcto_minimizers(const uint8_t *seq, size_t len, uint32_t k, uint32_t w, uint64_t *hash, uint32_t *pos, uint8_t *fw, size_t cap);
+void lcto_fraction_approximate_u16(double x, uint16_t *num, uint16_t *den);
+lcto_targets *lcto_targets_build(const lcto_target_seqs *in);
+void lcto_targets_free(lcto_targets *T);
+size_t lcto_targets_entries(const lcto_targets *T, uint64_t *key, uint32_t *locus, uint8_t *info, size_t cap);
+int lcto_recruit_short(const lcto_targets *T, const lcto_reads *R, uint32_t cap, uint32_t *ans_count, uint32_t *ans_locus);
+
 #ifdef __cplusplus
 }
 #endif

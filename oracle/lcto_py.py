@@ -490,3 +490,74 @@ def collect_read_ends(re_) -> dict:
     if rc != 0:
         raise RuntimeError(f"lcto_collect_read_ends failed: {rc}")
     return out
+
+
+# ---- short-read recruitment (lcto_recruit.c) ----
+
+class TargetSeqsC(C.Structure):
+    _fields_ = [("n_seqs", C.c_uint64), ("seq_off", C.c_void_p), ("seqs", C.c_void_p), ("seq_locus", C.c_void_p),
+                ("cnt_off", C.c_void_p), ("kmer_counts", C.c_void_p), ("base_k", C.c_uint32), ("minimizer_k", C.c_uint32),
+                ("minimizer_w", C.c_uint32), ("thresh_kmer_count", C.c_uint32), ("match_frac", C.c_double)]
+
+
+class ReadsC(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("off1", C.c_void_p), ("seq1", C.c_void_p), ("off2", C.c_void_p),
+                ("seq2", C.c_void_p)]
+
+
+def minimizers(seq: bytes, k: int, w: int):
+    n = max(1, len(seq))
+    h, p, f = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint8)
+    buf = np.frombuffer(seq or b"\0", dtype=np.uint8).copy()
+    L = lib()
+    L.lcto_minimizers.restype = C.c_size_t
+    L.lcto_minimizers.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    c = L.lcto_minimizers(buf.ctypes.data, len(seq), k, w, h.ctypes.data, p.ctypes.data, f.ctypes.data, n)
+    return h[:c].copy(), p[:c].copy(), f[:c].copy()
+
+
+def fraction_approximate_u16(x: float):
+    a, b = C.c_uint16(), C.c_uint16()
+    L = lib()
+    L.lcto_fraction_approximate_u16.argtypes = [C.c_double, C.c_void_p, C.c_void_p]
+    L.lcto_fraction_approximate_u16(x, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+class Targets:
+    def __init__(self, ts):
+        keep: list = []
+        c = ts.to_c(keep, struct=TargetSeqsC)
+        L = lib()
+        L.lcto_targets_build.restype = C.c_void_p
+        L.lcto_targets_build.argtypes = [C.c_void_p]
+        self._h = C.c_void_p(L.lcto_targets_build(C.byref(c)))
+
+    def entries(self):
+        L = lib()
+        L.lcto_targets_entries.restype = C.c_size_t
+        L.lcto_targets_entries.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        n = L.lcto_targets_entries(self._h, None, None, None, 0)
+        k, l, i = np.zeros(max(1, n), dtype=np.uint64), np.zeros(max(1, n), dtype=np.uint32), np.zeros(max(1, n), dtype=np.uint8)
+        L.lcto_targets_entries(self._h, k.ctypes.data, l.ctypes.data, i.ctypes.data, n)
+        return k[:n], l[:n], i[:n]
+
+    def recruit(self, reads, cap: int = 8):
+        keep: list = []
+        c = reads.to_c(keep, struct=ReadsC)
+        n = len(reads.seq1)
+        cnt = np.zeros(max(1, n), dtype=np.uint32)
+        ans = np.zeros(max(1, n) * cap, dtype=np.uint32)
+        L = lib()
+        L.lcto_recruit_short.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        rc = L.lcto_recruit_short(self._h, C.byref(c), cap, cnt.ctypes.data, ans.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"lcto_recruit_short failed: {rc}")
+        return [list(ans[r * cap:r * cap + min(int(cnt[r]), cap)]) for r in range(n)]
+
+    def __del__(self):
+        try:
+            lib().lcto_targets_free.argtypes = [C.c_void_p]
+            lib().lcto_targets_free(self._h)
+        except Exception:
+            pass
