@@ -1040,6 +1040,9 @@ __device__ __forceinline__ void eval_cand(const LocusDev &L, const WarpShared &w
 
 // Greedy::solve_nontrivial (src/solvers/stoch.rs:81-120).  The winner of an iteration is found with REDUX
 // reductions in the reference's tie order.
+__device__ __forceinline__ uint32_t ld_rec(const uint32_t *p) { uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint64_t ld_rec(const uint64_t *p) { uint64_t v; asm volatile("ld.global.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
+
 // Sequential part of Floyd's duplicate handling: draw k equal to an earlier entry replaces that entry by j_k.
 __device__ __noinline__ uint32_t sample_resolve_seq(uint32_t n_nt, uint32_t amount, uint32_t myv) {
     const uint32_t lane = lane_id();
@@ -1097,14 +1100,15 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
     const uint32_t my_range = n_nt - amount + min(lane, amount - 1u) + 1u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t *draw_hi = (const uint32_t *)rng.buf + 1 + 2u * min(lane, amount - 1u);   // next_u32 = upper half
-    // What the loads of a round deliver; each is defined at exactly ONE place (the load) and first read a round later.
-    // A second definition on some rare path would make the compiler merge the two at a join with a register move,
-    // which waits for the load right behind its issue (ncu: 6 % of the kernel in one such move at the loop top).
-    uint32_t f_raw = 0;                 // S0: upper half of the raw draw
-    uint2 f_info = ws.ntinfo[0];        // S1: index entry of the sampled read (lanes < amount)
-    Rec f_ro = 0, f_rn = 0;             // A: records of the job's current candidate / of its alternative
-    uint32_t f_b0 = 0, f_b1 = 0;        //    cm_off of the job's read on the first two haplotypes
-    double f_lpo = 0.0, f_lpn = 0.0;    // B: their ln-probabilities
+    // Loop-carried state of the loads is their ADDRESSES (ALU values), never a loaded value: the loads of all stages are
+    // issued at the top of a round, stage C runs while they are in flight, and their results are read at the bottom of
+    // the same round.  (With the loads issued at the bottom and read a round later the compiler moved every freshly
+    // loaded value into its loop-carried register right behind the load -- a full L2 latency per round, ncu: 15 % of the
+    // kernel in one register move.)
+    uint32_t q_io = 0, q_in = 0;        // B: indices of the two ln-probabilities in cm_lnprob
+    uint32_t q_oa = 0, q_oc = 0, q_r = 0;   // A: positions of the job's two candidate records, the job's read
+    uint32_t q_nt = 0;                  // S1: index entry to fetch
+    uint32_t q_at = min(rng.pos, RNG_FILL - amount);   // S0: stream position to fetch
     uint32_t dpos = rng.pos;
     bool blocked = false, slow = false;
     bool v0 = false, v1 = false, vA = false, vB = false, vC = false;
@@ -1117,6 +1121,20 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
     cur.job = cur.lead = cur.total = 0; cur.ro = cur.rn = 0; cur.lpo = cur.lpn = 0.0;
     __syncwarp();
     for (;;) {
+        // ---- the loads of all stages, back to back (through asm volatile: they stay here, in this order)
+        double f_lpo, f_lpn;                // B: ln-probabilities of the job's current candidate / of its alternative
+        Rec f_ro, f_rn;                     // A: their records ...
+        uint32_t f_b0, f_b1;                //    ... and cm_off of the job's read on the first two haplotypes
+        uint2 f_info;                       // S1: index entry of the sampled read (lanes < amount)
+        uint32_t f_raw;                     // S0: upper half of the raw draw
+        asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(f_lpo) : "l"(L.cm_lnprob + q_io));
+        asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(f_lpn) : "l"(L.cm_lnprob + q_in));
+        f_ro = ld_rec(S.rec + q_oa);
+        f_rn = ld_rec(S.rec + q_oc);
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(f_b0) : "l"(L.cm_off + (size_t)I.h0 * L.R + q_r));
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(f_b1) : "l"(L.cm_off + (size_t)I.h1 * L.R + q_r));   // (ploidy 1: h1 = 0, loaded, not used)
+        asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(f_info.x), "=r"(f_info.y) : "l"(ws.ntinfo + q_nt));
+        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(f_raw) : "l"(draw_hi + 2u * q_at));
         uint32_t mv_r = 0xFFFFFFFFu, mv_old = 0;     // read moved by this round's stage C
         if (vC) {
             // ---- stage C: evaluate the sample of this iteration
@@ -1202,7 +1220,7 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
             }
             if (it >= max_iter) break;
         }
-        // ---- pick up what last round's loads delivered, oldest first.  B -> C
+        // ---- pick up what the loads issued at the top of the round delivered, oldest first.  B -> C
         cur.job = jb.job; cur.lead = jb.lead; cur.total = jb.total; cur.ro = b_ro; cur.rn = b_rn;
         cur.lpo = f_lpo; cur.lpn = f_lpn;
         vC = vB;
@@ -1290,18 +1308,12 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
             a_oa = o + a; a_oc = o + c;
         }
         vA = a_valid;
-        // ---- the loads of all stages, back to back, in the order in which the next round reads them
-        f_lpo = __ldg(L.cm_lnprob + b_io);
-        f_lpn = __ldg(L.cm_lnprob + b_in);
-        f_ro = S.rec[a_oa];
-        f_rn = S.rec[a_oc];
-        f_b0 = __ldg(L.cm_off + (size_t)I.h0 * L.R + a_r);
-        f_b1 = __ldg(L.cm_off + (size_t)I.h1 * L.R + a_r);     // (ploidy 1: h1 = 0, loaded and not used -- a conditional load is a second definition)
-        // through asm: whatever the compiler derives from its own load (a zero-extension, a field extraction) it
-        // schedules right behind the load and waits there
-        asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(f_info.x), "=r"(f_info.y) : "l"(ws.ntinfo + (lane < amount ? s_v : 0u)));
+        // ---- what the next round fetches
+        q_io = b_io; q_in = b_in;
+        q_oa = a_oa; q_oc = a_oc; q_r = a_r;
+        q_nt = lane < amount ? s_v : 0u;
         v0 = !blocked && dpos + amount <= RNG_FILL;
-        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(f_raw) : "l"(draw_hi + 2u * min(dpos, RNG_FILL - amount)));   // past the fill: re-read, not used
+        q_at = min(dpos, RNG_FILL - amount);        // past the fill: re-read, not used
         dpos += v0 ? amount : 0u;
         s_dup = wany(v1 && lane < amount && (n_match & lt_mask) != 0u);
         if (__builtin_expect(!v0 && !v1 && !vA && !vB && !vC, 0)) {
