@@ -1220,6 +1220,20 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
             }
             if (it >= max_iter) break;
         }
+        // ---- stage S1 of the newest sample first: its MATCH.ANY is issued here and its result read at the end of the
+        // round (~150 instructions later), so that its ~250 cycles are not waited for
+        const uint32_t a_v0 = s_v;           // (stage A's sample, before S1 overwrites it)
+        const bool a_valid = v1;
+        unsigned n_match;
+        {
+            const uint64_t m = (uint64_t)f_raw * (uint64_t)my_range;     // rand UniformInt::sample_single_inclusive
+            v1 = v0;
+            if (__builtin_expect(v0 && wany(lane < amount && (uint32_t)m > 0u - my_range), 0)) {
+                v1 = false; blocked = true; dpos -= amount;      // biased zone: this sample takes the sequential path
+            }
+            s_v = (uint32_t)(m >> 32);
+            n_match = __match_any_sync(FULL, lane < amount ? s_v : 0x80000000u | lane);
+        }
         // ---- pick up what the loads issued at the top of the round delivered, oldest first.  B -> C
         cur.job = jb.job; cur.lead = jb.lead; cur.total = jb.total; cur.ro = b_ro; cur.rn = b_rn;
         cur.lpo = f_lpo; cur.lpn = f_lpn;
@@ -1260,21 +1274,8 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
             else { b_io = lp_index(L, I, ws, r, RW::src(b_ro)); b_in = lp_index(L, I, ws, r, RW::src(b_rn)); }
         }
         // ---- stage A: Floyd's replacements if two draws of the sample were equal, then deal the jobs
-        uint32_t a_v = s_v;
+        uint32_t a_v = a_v0;
         uint2 a_info = f_info;
-        const bool a_valid = v1;
-        // (stage S1 of the NEXT sample goes first: its MATCH.ANY is issued here and its result read at the end of
-        // the round, so that nothing variable-latency but the loads is in flight across the loop's back edge)
-        unsigned n_match;
-        {
-            const uint64_t m = (uint64_t)f_raw * (uint64_t)my_range;     // rand UniformInt::sample_single_inclusive
-            v1 = v0;
-            if (__builtin_expect(v0 && wany(lane < amount && (uint32_t)m > 0u - my_range), 0)) {
-                v1 = false; blocked = true; dpos -= amount;      // biased zone: this sample takes the sequential path
-            }
-            s_v = (uint32_t)(m >> 32);
-            n_match = __match_any_sync(FULL, lane < amount ? s_v : 0x80000000u | lane);
-        }
         if (__builtin_expect(slow, 0)) {                    // the sample was drawn one draw at a time (see below)
             a_v = ws.samp[lane & 15u];
             a_info = nt_info(ws, lane < amount ? a_v : 0u);
