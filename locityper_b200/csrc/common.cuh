@@ -131,6 +131,7 @@ struct LocusDev {
     uint64_t G;
     uint32_t window, left_padding, tweak, depth_k;
     double prob_diff, depth_contrib, aln_contrib, rel_contrib, min_weight;
+    uint64_t c_window, c_span;   // ceil(2^64 / window), ceil(2^64 / (2 tweak + 1)): division / remainder by multiplication
     const double *Mt;            // [R][Hpad] best-alignment matrix, read-major (a1)
     const double *unmapped;      // [R]
     const uint32_t *cm_off;      // [H*R+1] contig-major CSR of pair alignments

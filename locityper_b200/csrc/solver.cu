@@ -46,7 +46,7 @@ static constexpr int MAX_SAMPLE = 11;          // Floyd branch of rand::seq::ind
 #endif
 static constexpr int RNG_C = LCTP_RNG_C;                // stream outputs generated per lane per fill
 static constexpr uint32_t RNG_FILL = 32u * RNG_C;       // draws per fill (per-worker buffer: 8 KB at C = 32)
-static constexpr int N_JUMP_TABS = 6;                   // T^(C*2^k), k = 0..4 (stream start), T^FILL (refill)
+static constexpr int N_JUMP_TABS = 33;                  // T^(C*l), l = 0..31 (stream start of lane l; l = 0 unused), T^FILL (refill)
 static constexpr size_t JUMP_TAB_WORDS = 32 * 256 * 4;  // u64 words per table: [32 state bytes][256 values][4]
 static constexpr uint32_t SRC_UNMAPPED = 0xFFu;
 static constexpr uint32_t MAX_RUN = 15;                 // rank in a (read, contig) run must fit 4 bits (reference: <= 10)
@@ -231,7 +231,7 @@ __device__ __noinline__ void fill_block(uint64_t *buf, uint64_t *blk, const ulon
 }
 __device__ __forceinline__ void stream_refill(Xo &x) {
     if (x.pend) ring_wait();
-    fill_block(x.buf, x.blk, x.tabs + (size_t)5 * (JUMP_TAB_WORDS / 2));
+    fill_block(x.buf, x.blk, x.tabs + (size_t)32 * (JUMP_TAB_WORDS / 2));
     x.pos = 0;
     stream_resync(x);
 }
@@ -241,8 +241,9 @@ __device__ __noinline__ void stream_begin_blocks(const uint64_t *__restrict__ st
                                                  const ulonglong2 *tabs) {
     Gen g; g.s0 = st[0]; g.s1 = st[1]; g.s2 = st[2]; g.s3 = st[3];
     const int lane = lane_id();
-    for (int k = 0; k < 5; k++)
-        if ((lane >> k) & 1) g = gen_tab_apply(g, tabs + (size_t)k * (JUMP_TAB_WORDS / 2));
+    // one table per lane (T^(C * lane), 8 MB in all, L2-resident): a single application instead of up to five
+    // dependent ones by the binary decomposition of the lane id (ncu: 3 % of the C2 stage kernel, one worker per genotype)
+    if (lane) g = gen_tab_apply(g, tabs + (size_t)lane * (JUMP_TAB_WORDS / 2));
     __syncwarp();
     uint64_t *b = blk + lane * 4;
     b[0] = g.s0; b[1] = g.s1; b[2] = g.s2; b[3] = g.s3;
@@ -599,7 +600,7 @@ __device__ bool build_instance(const LocusDev &L, const Slab<WIDE> &S, const War
 // ContigInfo::get_shifted_window_ix (src/model/windows.rs:62-68,465-470)
 __device__ __forceinline__ uint32_t shifted_window(const LocusDev &L, uint32_t reg_start, uint32_t reg_end, uint32_t shift,
                                                    uint32_t middle) {
-    if (reg_start <= middle && middle < reg_end) return (middle - reg_start) / L.window + shift;
+    if (reg_start <= middle && middle < reg_end) return (L.window == 1u ? middle - reg_start : (uint32_t)__umul64hi(middle - reg_start, L.c_window)) + shift;   // (middle - reg_start) / L.window
     return 1;   // BOUNDARY_WINDOW
 }
 
@@ -673,8 +674,9 @@ __device__ void apply_tweak(const LocusDev &L, const Slab<WIDE> &S, const Instan
                         const uint32_t shift = inst_wshift(ws, sb >> 4);
                         const uint32_t reg_start = L.hap_reg_start[hap[t]];
                         const uint32_t reg_end = reg_start + L.hap_n_windows[hap[t]] * L.window;
-                        const uint32_t t1 = tweak ? (uint32_t)(draw[t] >> 32) % span : 0u;
-                        const uint32_t t2 = tweak ? (uint32_t)draw[t] % span : 0u;
+                        // x % span = hi64((c * x mod 2^64) * span), c = ceil(2^64 / span) (exact for 32-bit x and span)
+                        const uint32_t t1 = tweak ? (uint32_t)__umul64hi(L.c_span * (uint64_t)(uint32_t)(draw[t] >> 32), span) : 0u;
+                        const uint32_t t2 = tweak ? (uint32_t)__umul64hi(L.c_span * (uint64_t)(uint32_t)draw[t], span) : 0u;
                         const uint32_t w1 = mid[t].x == LCTP_NONE_U32 ? 0u : shifted_window(L, reg_start, reg_end, shift, mid[t].x + t1);
                         const uint32_t w2 = mid[t].y == LCTP_NONE_U32 ? 0u : shifted_window(L, reg_start, reg_end, shift, mid[t].y + t2);
                         S.rec[o + j0 + t] = RW::make(sb, w1, w2);
@@ -1783,12 +1785,15 @@ static const std::vector<uint64_t> &jump_tables() {
         static BitMat T, M;
         bm_step(T);
         tabs.resize((size_t)N_JUMP_TABS * JUMP_TAB_WORDS);
-        for (int k = 0; k < 5; k++) {
-            bm_pow(T, (unsigned)RNG_C << k, M);
-            bm_to_table(M, &tabs[(size_t)k * JUMP_TAB_WORDS]);
+        static BitMat S, P, Q;
+        bm_pow(T, (unsigned)RNG_C, S);                     // S = T^C; table l = S^l
+        P = S;
+        for (int l = 1; l < 32; l++) {
+            bm_to_table(P, &tabs[(size_t)l * JUMP_TAB_WORDS]);
+            bm_mul(S, P, Q); P = Q;
         }
-        bm_pow(T, RNG_FILL, M);
-        bm_to_table(M, &tabs[(size_t)5 * JUMP_TAB_WORDS]);
+        bm_to_table(P, &tabs[(size_t)32 * JUMP_TAB_WORDS]);   // S^32 = T^FILL
+        (void)M;
     });
     return tabs;
 }

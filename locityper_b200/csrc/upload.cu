@@ -262,6 +262,10 @@ int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h, const lct
     d.depth_contrib = 1.0 + in->lik_skew;
     d.rel_contrib = d.depth_contrib / d.aln_contrib;    // src/model/assgn.rs:299
     d.min_weight = in->min_weight;
+    // exact for every 32-bit dividend (Lemire et al., "Faster remainder by direct computation"); a divisor of 1 wraps c to 0,
+    // handled where it is used (window >= 2 is validated above; span = 1 means tweak = 0, where the remainder is not taken)
+    d.c_window = ~0ull / (in->window ? in->window : 1u) + 1ull;
+    d.c_span = ~0ull / (2ull * in->tweak + 1ull) + 1ull;
     d.Mt = h->Mt.p; d.unmapped = h->unmapped.p; d.cm_off = h->cm_off.p; d.cm_lnprob = h->cm_lnprob.p;
     d.cm_mid = h->cm_mid.p; d.hap_len = h->hap_len.p; d.hap_n_windows = h->hap_nw.p;
     d.hap_reg_start = h->hap_rs.p; d.hap_pos_off = h->hap_pos_off.p; d.pos_weight = h->pos_weight.p;
