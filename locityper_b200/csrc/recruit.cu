@@ -35,16 +35,19 @@ __host__ __device__ __forceinline__ uint64_t fast_hash64(uint64_t x) {      // M
 }
 
 // kmers::minimizers::<u64, _, CANONICAL> (kmers.rs:256-331), statement for statement; `emit(pos, hash, forward)`.
-template <typename Emit>
-__device__ __forceinline__ void dev_minimizers(const uint8_t *__restrict__ seq, uint32_t len, uint32_t k, uint32_t w, Emit emit) {
+// `hashes`: the 64-entry hash ring of this thread, element q at hashes[q * stride] (shared memory, one column per thread:
+// as a per-thread local array it went through local memory -- 390 MB of DRAM writes per 200k read pairs, ncu).
+// RING: entries of the ring, a power of two >= w (the reference's CircArray has 64; only the last w entries are ever read).
+template <uint32_t RING, typename Emit>
+__device__ __forceinline__ void dev_minimizers(const uint8_t *__restrict__ seq, uint32_t len, uint32_t k, uint32_t w,
+                                               uint64_t *hashes, uint32_t stride, Emit emit) {
     const uint64_t mask = (1ull << (2 * k)) - 1ull;
     const uint32_t rv_shift = 2 * k - 2;
     uint64_t fw_kmer = 0, rv_kmer = 0;
     const uint32_t k_1 = k - 1, w_1 = w - 1;
-    uint64_t hashes[MAXW];
     uint64_t forward = ~0ull;                      // CircArray<bool> as a 64-bit mask
 #pragma unroll 1
-    for (uint32_t q = 0; q < MAXW; q++) hashes[q] = KM_UNDEF;
+    for (uint32_t q = 0; q < RING; q++) hashes[q * stride] = KM_UNDEF;
     long long last_pos = -1;
     uint32_t best_pos = 0;
     uint64_t best_hash = KM_UNDEF;
@@ -64,16 +67,16 @@ __device__ __forceinline__ void dev_minimizers(const uint8_t *__restrict__ seq, 
         const bool f = !(rv_kmer < fw_kmer);
         const uint64_t kmer = f ? fw_kmer : rv_kmer;
         const uint64_t h = i < first_kmer ? KM_UNDEF : fast_hash64(kmer);
-        hashes[i & (MAXW - 1)] = h;
+        hashes[(i & (RING - 1)) * stride] = h;
         forward = (forward & ~(1ull << (i & (MAXW - 1)))) | ((uint64_t)f << (i & (MAXW - 1)));
         if (h < best_hash) { best_hash = h; best_pos = i; }
         if (i < first_window) continue;
         const uint32_t start = i - w_1;
         if (best_pos < start) {
             uint32_t p = start;                    // find_min, kmers.rs:237-252
-            uint64_t m = hashes[start & (MAXW - 1)];
+            uint64_t m = hashes[(start & (RING - 1)) * stride];
             for (uint32_t j = start + 1; j < i + 1; j++) {
-                const uint64_t v = hashes[j & (MAXW - 1)];
+                const uint64_t v = hashes[(j & (RING - 1)) * stride];
                 if (v < m) { p = j; m = v; }
             }
             best_pos = p; best_hash = m;
@@ -86,14 +89,20 @@ __device__ __forceinline__ void dev_minimizers(const uint8_t *__restrict__ seq, 
     }
 }
 
-__global__ void __launch_bounds__(128)
+// threads per CTA for a ring of RING entries: 16 or 32 KB of hash rings per CTA
+template <uint32_t RING> struct RecruitCfg { static constexpr int THREADS = RING <= 32 ? 128 : 64; };
+
+template <uint32_t RING>
+__global__ void __launch_bounds__(RecruitCfg<RING>::THREADS)
 k_minimizers(const uint8_t *__restrict__ seqs, const uint64_t *__restrict__ off, uint64_t n, uint32_t k, uint32_t w,
              uint32_t *__restrict__ count, uint64_t *__restrict__ hash, uint32_t *__restrict__ pos, uint8_t *__restrict__ fw) {
+    constexpr int NT = RecruitCfg<RING>::THREADS;
+    __shared__ uint64_t ring[RING * NT];
     const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const uint64_t b = off[s];
     uint32_t c = 0;
-    dev_minimizers(seqs + b, (uint32_t)(off[s + 1] - b), k, w, [&](uint32_t p, uint64_t h, uint32_t f) {
+    dev_minimizers<RING>(seqs + b, (uint32_t)(off[s + 1] - b), k, w, ring + threadIdx.x, NT, [&](uint32_t p, uint64_t h, uint32_t f) {
         hash[b + c] = h; pos[b + c] = p; fw[b + c] = (uint8_t)f; c++;
     });
     count[s] = c;
@@ -132,9 +141,12 @@ struct ReadsDev {
     const uint8_t *seq1, *seq2;
 };
 
-__global__ void __launch_bounds__(128)
+template <uint32_t RING>
+__global__ void __launch_bounds__(RecruitCfg<RING>::THREADS)
 k_recruit_short(ReadsDev R, TableDev T, uint32_t k, uint32_t w, uint32_t fnum, uint32_t fden, uint32_t cap,
                 uint32_t *__restrict__ ans_count, uint32_t *__restrict__ ans_locus, int *__restrict__ err) {
+    constexpr int NT = RecruitCfg<RING>::THREADS;
+    __shared__ uint64_t ring[RING * NT];
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R.n) return;
     uint32_t loci[LOCI_PER_READ];
@@ -168,7 +180,7 @@ k_recruit_short(ReadsDev R, TableDev T, uint32_t k, uint32_t w, uint32_t fnum, u
     };
     {
         const uint64_t b = R.off1[r];
-        dev_minimizers(R.seq1 + b, (uint32_t)(R.off1[r + 1] - b), k, w, [&](uint32_t, uint64_t h, uint32_t f) { total1++; lookup(h, f, false); });
+        dev_minimizers<RING>(R.seq1 + b, (uint32_t)(R.off1[r + 1] - b), k, w, ring + threadIdx.x, NT, [&](uint32_t, uint64_t h, uint32_t f) { total1++; lookup(h, f, false); });
     }
     uint32_t n_ans = 0;
     uint32_t *ans = ans_locus + r * cap;
@@ -184,7 +196,7 @@ k_recruit_short(ReadsDev R, TableDev T, uint32_t k, uint32_t w, uint32_t fnum, u
     if (R.off2) {
         if (nm != 0) {                                            // :906
             const uint64_t b = R.off2[r];
-            dev_minimizers(R.seq2 + b, (uint32_t)(R.off2[r + 1] - b), k, w, [&](uint32_t, uint64_t h, uint32_t f) { total2++; lookup(h, f, true); });
+            dev_minimizers<RING>(R.seq2 + b, (uint32_t)(R.off2[r + 1] - b), k, w, ring + threadIdx.x, NT, [&](uint32_t, uint64_t h, uint32_t f) { total2++; lookup(h, f, true); });
             if (total2 > 65535u) atomicOr(err, 2);
             for (int z = 0; z < nm; z++) {
                 const Bmc a = first[z], b2 = second[z];
@@ -232,7 +244,9 @@ int minimizers(lctp_ctx *ctx, const uint8_t *seqs, const uint64_t *off, uint64_t
     if ((rc = put(d_seq, seqs, (size_t)total, s)) || (rc = put(d_off, off, (size_t)n + 1, s))) return rc;
     if ((rc = d_cnt.alloc(n)) || (rc = d_hash.alloc(total ? total : 1)) || (rc = d_pos.alloc(total ? total : 1)) || (rc = d_fw.alloc(total ? total : 1))) return rc;
     LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[0], s));
-    k_minimizers<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_seq.p, d_off.p, n, k, w, d_cnt.p, d_hash.p, d_pos.p, d_fw.p);
+    if (w <= 16) k_minimizers<16><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_seq.p, d_off.p, n, k, w, d_cnt.p, d_hash.p, d_pos.p, d_fw.p);
+    else if (w <= 32) k_minimizers<32><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_seq.p, d_off.p, n, k, w, d_cnt.p, d_hash.p, d_pos.p, d_fw.p);
+    else k_minimizers<64><<<(unsigned)((n + 63) / 64), 64, 0, s>>>(d_seq.p, d_off.p, n, k, w, d_cnt.p, d_hash.p, d_pos.p, d_fw.p);
     ctx->launches++;
     LCTP_CUDA_CHECK(cudaGetLastError());
     LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[1], s));
@@ -446,7 +460,9 @@ int lctp_recruit_short(lctp_ctx *ctx, const lctp_targets_h *t, const lctp_reads 
     TableDev T;
     T.key = t->key.p; T.span = t->span.p; T.e_locus = t->e_locus.p; T.e_info = t->e_info.p; T.mask = t->cap - 1;
     LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[0], s));
-    k_recruit_short<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(R, T, t->k, t->w, t->fnum, t->fden, cap, d_cnt.p, d_ans.p, d_err.p);
+    if (t->w <= 16) k_recruit_short<16><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(R, T, t->k, t->w, t->fnum, t->fden, cap, d_cnt.p, d_ans.p, d_err.p);
+    else if (t->w <= 32) k_recruit_short<32><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(R, T, t->k, t->w, t->fnum, t->fden, cap, d_cnt.p, d_ans.p, d_err.p);
+    else k_recruit_short<64><<<(unsigned)((n + 63) / 64), 64, 0, s>>>(R, T, t->k, t->w, t->fnum, t->fden, cap, d_cnt.p, d_ans.p, d_err.p);
     ctx->launches++;
     LCTP_CUDA_CHECK(cudaGetLastError());
     LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[1], s));
