@@ -314,6 +314,8 @@ typedef struct lctp_target_seqs {
     uint32_t minimizer_k, minimizer_w;   /* Params::minimizer_k / minimizer_w */
     uint32_t thresh_kmer_count;     /* Params::thresh_kmer_count */
     double match_frac;              /* Params::match_frac */
+    uint32_t match_length;          /* Params::match_length (long reads: stretch_minims / stretch_score, recruit.rs:95-98) */
+    uint32_t _pad;
 } lctp_target_seqs;
 typedef struct lctp_targets_h lctp_targets_h;
 int  lctp_targets_build(lctp_ctx *ctx, const lctp_target_seqs *in, lctp_targets_h **out);
@@ -327,10 +329,11 @@ typedef struct lctp_reads {
     const uint64_t *off1; const uint8_t *seq1;
     const uint64_t *off2; const uint8_t *seq2;     /* NULL = single-end */
 } lctp_reads;
-/* recruit_short_read (src/seq/recruit.rs:852-881) / recruit_read_pair (:885-930) for every read (pair): ans_count[r] loci,
- * ans_locus[r * cap ..] their indices in ascending order (the reference's answer is a set).  Reads longer than 500 bp
- * (READ_LENGTH_THRESH) are refused: recruit_long_read is not covered.  LCTP_E_CAPACITY when a read matches more than 8
- * loci; ans_count[r] > cap means the list of that read was cut at cap. */
+/* RecruitableRecord::recruit (src/seq/recruit.rs:582-611) for every read (pair): single-end reads of at most 500 bp
+ * (READ_LENGTH_THRESH) -> recruit_short_read (:852-881), longer ones -> recruit_long_read with has_matching_stretch
+ * (:932-998), pairs -> recruit_read_pair (:885-930).  ans_count[r] loci, ans_locus[r * cap ..] their indices in ascending
+ * order (the reference's answer is a set).  LCTP_E_CAPACITY when a read matches more than 8 loci; ans_count[r] > cap
+ * means the list of that read was cut at cap. */
 int  lctp_recruit_short(lctp_ctx *ctx, const lctp_targets_h *t, const lctp_reads *reads, uint32_t cap,
                         uint32_t *ans_count, uint32_t *ans_locus);
 size_t lctp_sizeof_target_seqs(void);

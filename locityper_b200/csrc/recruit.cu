@@ -6,7 +6,7 @@
 //   per read (pair): match counters           BaseMatchCount<u16>::inc / has_rare / better_fraction /
 //                                             better_pair_fraction (:234-366), Fraction<u16> comparison (frac.rs:92-98)
 //   decision                                  recruit_short_read (:852-881), recruit_read_pair (:885-930)
-// Long reads (recruit_long_read / has_matching_stretch, :932-998) are not covered.
+//   long single-end reads                    recruit_long_read + has_matching_stretch (:932-998)
 //
 // One thread per read (pair): the minimizer scan is a sequential sliding-window minimum (the emitted set depends on the
 // scan order through `last_pos` and the window restarts after an N), 150-250 steps for a short read; a read touches its
@@ -141,14 +141,102 @@ struct ReadsDev {
     const uint8_t *seq1, *seq2;
 };
 
+struct LongParams { double match_frac; uint32_t stretch_minims, stretch_score; };
+
+// recruit_long_read (recruit.rs:967-998) + has_matching_stretch (:932-964) for one single-end read longer than
+// READ_LENGTH_THRESH.  Two scans of the read: the first counts matches per locus (BaseMatchCount<u32>), the second -- only
+// for loci that pass the count threshold and have at least `stretch_minims` usable minimizers -- runs the Kadane-style
+// stretch test; the minimizers are recomputed instead of buffered (a 15-kb read has ~3,000 of them).
+template <uint32_t RING>
+__device__ void recruit_long(const uint8_t *__restrict__ seq, uint32_t len, const TableDev &T, uint32_t k, uint32_t w,
+                             const LongParams &P, uint64_t *ring, uint32_t stride, uint32_t cap, uint32_t *ans,
+                             uint32_t &n_ans, bool &overflow) {
+    uint32_t loci[LOCI_PER_READ];
+    uint32_t cnt[LOCI_PER_READ][4];
+    int nm = 0;
+    uint32_t total = 0;
+    auto find = [&](uint64_t h, uint2 &sp) -> bool {
+        if (h == KM_UNDEF) return false;
+        uint64_t s = table_slot(h, T.mask);
+        while (true) {
+            const uint64_t kk = T.key[s];
+            if (kk == h) break;
+            if (kk == KM_UNDEF) return false;
+            s = (s + 1) & T.mask;
+        }
+        sp = T.span[s];
+        return true;
+    };
+    dev_minimizers<RING>(seq, len, k, w, ring, stride, [&](uint32_t, uint64_t h, uint32_t f) {
+        total++;
+        uint2 sp;
+        if (!find(h, sp)) return;
+        for (uint32_t e = sp.x; e < sp.x + sp.y; e++) {
+            const uint32_t locus = T.e_locus[e], info = T.e_info[e];
+            int z = 0;
+            while (z < nm && loci[z] != locus) z++;
+            if (z == nm) {
+                if (nm == LOCI_PER_READ) { overflow = true; continue; }
+                loci[nm] = locus; cnt[nm][0] = cnt[nm][1] = cnt[nm][2] = cnt[nm][3] = 0;
+                nm++;
+            }
+            const int i = ((info >> 2) & 1) << 1;                                          // BaseMatchCount<u32>::inc, :246-252
+            cnt[z][i] += directed_to(info, f == 0) ? 1u : 0u;
+            cnt[z][i | 1] += directed_to(info, f != 0) ? 1u : 0u;
+        }
+    });
+    for (int z = 0; z < nm; z++) {
+        const uint32_t bw_c = cnt[z][0], fw_c = cnt[z][1], bw_r = cnt[z][2], fw_r = cnt[z][3];
+        const uint32_t num = fw_r >= bw_r ? fw_r : bw_r, den = fw_r >= bw_r ? total - fw_c : total - bw_c;   // rare_fraction, :266-274
+        const uint32_t thr = max(1u, __double2uint_rz(ceil(__dmul_rn((double)min(P.stretch_minims, den), P.match_frac))));   // long_read_threshold
+        if (num < thr) continue;
+        bool okay = den < P.stretch_minims;
+        if (!okay) {                                                                        // has_matching_stretch, :944-963
+            uint32_t s_fw = 0, s_bw = 0;
+            const uint32_t want = loci[z];
+            dev_minimizers<RING>(seq, len, k, w, ring, stride, [&](uint32_t, uint64_t h, uint32_t f) {
+                if (okay) return;
+                uint2 sp;
+                if (find(h, sp))
+                    for (uint32_t e = sp.x; e < sp.x + sp.y; e++)
+                        if (T.e_locus[e] == want) {
+                            const uint32_t info = T.e_info[e], x = 1u + ((info >> 2) & 1u) * 3u;   // SUBSUM_PENALTY + rare * SUBSUM_BONUS
+                            s_fw += directed_to(info, f != 0) ? x : 0u;
+                            s_bw += directed_to(info, f == 0) ? x : 0u;
+                        }
+                s_fw = s_fw >= 1u ? s_fw - 1u : 0u;                                         // saturating_sub(SUBSUM_PENALTY)
+                s_bw = s_bw >= 1u ? s_bw - 1u : 0u;
+                if (s_fw >= P.stretch_score || s_bw >= P.stretch_score) okay = true;
+            });
+        }
+        if (okay) {
+            if (n_ans < cap) {
+                uint32_t y = n_ans;
+                while (y > 0 && ans[y - 1] > loci[z]) { ans[y] = ans[y - 1]; y--; }
+                ans[y] = loci[z];
+            }
+            n_ans++;
+        }
+    }
+}
+
 template <uint32_t RING>
 __global__ void __launch_bounds__(RecruitCfg<RING>::THREADS)
-k_recruit_short(ReadsDev R, TableDev T, uint32_t k, uint32_t w, uint32_t fnum, uint32_t fden, uint32_t cap,
+k_recruit_short(ReadsDev R, TableDev T, uint32_t k, uint32_t w, uint32_t fnum, uint32_t fden, LongParams LP, uint32_t cap,
                 uint32_t *__restrict__ ans_count, uint32_t *__restrict__ ans_locus, int *__restrict__ err) {
     constexpr int NT = RecruitCfg<RING>::THREADS;
     __shared__ uint64_t ring[RING * NT];
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R.n) return;
+    if (!R.off2 && R.off1[r + 1] - R.off1[r] > 500) {         // RecruitableRecord::recruit, recruit.rs:589 (READ_LENGTH_THRESH)
+        uint32_t n_long = 0;
+        bool ovf = false;
+        const uint64_t b = R.off1[r];
+        recruit_long<RING>(R.seq1 + b, (uint32_t)(R.off1[r + 1] - b), T, k, w, LP, ring + threadIdx.x, NT, cap, ans_locus + r * cap, n_long, ovf);
+        ans_count[r] = n_long;
+        if (ovf) atomicOr(err, 1);
+        return;
+    }
     uint32_t loci[LOCI_PER_READ];
     Bmc first[LOCI_PER_READ], second[LOCI_PER_READ];
     int nm = 0;
@@ -295,6 +383,7 @@ struct lctp_targets_h {
     lctp_ctx *ctx = nullptr;
     uint32_t k = 0, w = 0, n_loci = 0;
     uint16_t fnum = 0, fden = 1;
+    LongParams lp = {0.0, 0, 0};
     uint64_t n_keys = 0, n_entries = 0, cap = 0;
     DevBuf<uint64_t> key;
     DevBuf<uint2> span;
@@ -326,8 +415,9 @@ int lctp_targets_build(lctp_ctx *ctx, const lctp_target_seqs *in, lctp_targets_h
         return LCTP_E_INVALID;
     }
     const double min_frac = 1.0 / 4.0;                               // SUBSUM_PENALTY / (SUBSUM_BONUS + 1), recruit.rs:82-84
-    if (!(in->match_frac >= min_frac && in->match_frac <= 1.0) || in->thresh_kmer_count == 0 || in->thresh_kmer_count > 65535) {
-        set_error("lctp_targets_build: match fraction must be in [0.25, 1], the k-mer threshold positive");
+    if (!(in->match_frac >= min_frac && in->match_frac <= 1.0) || in->thresh_kmer_count == 0 || in->thresh_kmer_count > 65535 ||
+        in->match_length < 200 || in->match_length > 100000) {           // Params::new, recruit.rs:82-91
+        set_error("lctp_targets_build: match fraction must be in [0.25, 1], the k-mer threshold positive, the match length in [200, 100000]");
         return LCTP_E_INVALID;
     }
     const uint64_t n = in->n_seqs, total = in->seq_off[n];
@@ -342,6 +432,9 @@ int lctp_targets_build(lctp_ctx *ctx, const lctp_target_seqs *in, lctp_targets_h
     auto h = new lctp_targets_h;
     h->ctx = ctx; h->k = mk; h->w = in->minimizer_w;
     lctp_fraction_approximate_u16(in->match_frac, &h->fnum, &h->fden);              // Params::new, recruit.rs:101
+    h->lp.match_frac = in->match_frac;
+    h->lp.stretch_minims = (2 * in->match_length + (in->minimizer_w + 1) - 1) / (in->minimizer_w + 1);     // fast_ceil_div, :95
+    h->lp.stretch_score = (uint32_t)std::ceil(std::max((double)h->lp.stretch_minims * (4.0 * in->match_frac - 1.0), 3.0));   // :96-98
     std::unordered_map<uint64_t, uint32_t> last;
     uint32_t prev_locus = 0;
     for (uint64_t s = 0; s < n; s++) {
@@ -440,8 +533,8 @@ int lctp_recruit_short(lctp_ctx *ctx, const lctp_targets_h *t, const lctp_reads 
     cudaStream_t s = ctx->stream;
     for (uint64_t r = 0; r < n; r++) {
         const uint64_t l1 = reads->off1[r + 1] - reads->off1[r], l2 = reads->off2 ? reads->off2[r + 1] - reads->off2[r] : 0;
-        if (reads->off1[r + 1] < reads->off1[r] || l1 > 500 || l2 > 500) {       // READ_LENGTH_THRESH, recruit.rs:35,589
-            set_error("lctp_recruit_short: read %llu is longer than 500 bp (long reads are not recruited by this entry point)", (unsigned long long)r);
+        if (reads->off1[r + 1] < reads->off1[r] || l1 > 0xFFFFFFF0ull || l2 > 0xFFFFFFF0ull) {
+            set_error("lctp_recruit_short: bad offsets of read %llu", (unsigned long long)r);
             return LCTP_E_INVALID;
         }
     }
@@ -460,9 +553,9 @@ int lctp_recruit_short(lctp_ctx *ctx, const lctp_targets_h *t, const lctp_reads 
     TableDev T;
     T.key = t->key.p; T.span = t->span.p; T.e_locus = t->e_locus.p; T.e_info = t->e_info.p; T.mask = t->cap - 1;
     LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[0], s));
-    if (t->w <= 16) k_recruit_short<16><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(R, T, t->k, t->w, t->fnum, t->fden, cap, d_cnt.p, d_ans.p, d_err.p);
-    else if (t->w <= 32) k_recruit_short<32><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(R, T, t->k, t->w, t->fnum, t->fden, cap, d_cnt.p, d_ans.p, d_err.p);
-    else k_recruit_short<64><<<(unsigned)((n + 63) / 64), 64, 0, s>>>(R, T, t->k, t->w, t->fnum, t->fden, cap, d_cnt.p, d_ans.p, d_err.p);
+    if (t->w <= 16) k_recruit_short<16><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(R, T, t->k, t->w, t->fnum, t->fden, t->lp, cap, d_cnt.p, d_ans.p, d_err.p);
+    else if (t->w <= 32) k_recruit_short<32><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(R, T, t->k, t->w, t->fnum, t->fden, t->lp, cap, d_cnt.p, d_ans.p, d_err.p);
+    else k_recruit_short<64><<<(unsigned)((n + 63) / 64), 64, 0, s>>>(R, T, t->k, t->w, t->fnum, t->fden, t->lp, cap, d_cnt.p, d_ans.p, d_err.p);
     ctx->launches++;
     LCTP_CUDA_CHECK(cudaGetLastError());
     LCTP_CUDA_CHECK(cudaEventRecord(ctx->ev[1], s));

@@ -428,6 +428,7 @@ class TargetSeqs:
     minimizer_w: int
     thresh_kmer_count: int
     match_frac: float
+    match_length: int = 2000
 
     def to_c(self, keep: list, struct=None):
         def arr(a, dt):
@@ -444,6 +445,7 @@ class TargetSeqs:
         c.kmer_counts = arr(np.concatenate(self.kmer_counts) if len(self.kmer_counts) else np.zeros(1), np.uint16)
         c.base_k, c.minimizer_k, c.minimizer_w = int(self.base_k), int(self.minimizer_k), int(self.minimizer_w)
         c.thresh_kmer_count, c.match_frac = int(self.thresh_kmer_count), float(self.match_frac)
+        c.match_length = int(self.match_length)
         return c
 
 

@@ -297,6 +297,7 @@ typedef struct lcto_target_seqs {
     const uint16_t *kmer_counts;    /* KmerCounts of the sequence: len + 1 - base_k entries */
     uint32_t base_k, minimizer_k, minimizer_w, thresh_kmer_count;
     double match_frac;
+    uint32_t match_length, _pad;
 } lcto_target_seqs;
 typedef struct lcto_reads {
     uint64_t n_reads;

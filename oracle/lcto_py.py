@@ -497,7 +497,8 @@ def collect_read_ends(re_) -> dict:
 class TargetSeqsC(C.Structure):
     _fields_ = [("n_seqs", C.c_uint64), ("seq_off", C.c_void_p), ("seqs", C.c_void_p), ("seq_locus", C.c_void_p),
                 ("cnt_off", C.c_void_p), ("kmer_counts", C.c_void_p), ("base_k", C.c_uint32), ("minimizer_k", C.c_uint32),
-                ("minimizer_w", C.c_uint32), ("thresh_kmer_count", C.c_uint32), ("match_frac", C.c_double)]
+                ("minimizer_w", C.c_uint32), ("thresh_kmer_count", C.c_uint32), ("match_frac", C.c_double),
+                ("match_length", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class ReadsC(C.Structure):

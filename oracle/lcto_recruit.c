@@ -100,6 +100,7 @@ typedef struct { uint64_t key; uint32_t locus; uint8_t dir, rare; } tentry;
 struct lcto_targets {
     tentry *e; size_t n, cap;      /* in insertion order: per minimizer the loci are appended in locus order */
     uint32_t k, w; uint16_t fnum, fden;
+    double match_frac; uint32_t stretch_minims, stretch_score;     /* Params, recruit.rs:95-103 */
 };
 
 static tentry *find_last(lcto_targets *T, uint64_t key) {         /* v.last_mut() of minim_to_loci[key] */
@@ -111,6 +112,13 @@ lcto_targets *lcto_targets_build(const lcto_target_seqs *in) {
     lcto_targets *T = (lcto_targets *)calloc(1, sizeof *T);
     T->k = in->minimizer_k; T->w = in->minimizer_w;
     lcto_fraction_approximate_u16(in->match_frac, &T->fnum, &T->fden);   /* Params::new, recruit.rs:101 */
+    T->match_frac = in->match_frac;
+    T->stretch_minims = (2 * in->match_length + (in->minimizer_w + 1) - 1) / (in->minimizer_w + 1);   /* fast_ceil_div, :95 */
+    {
+        double sc = (double)T->stretch_minims * ((double)(3 + 1) * in->match_frac - (double)1);        /* :96-97 */
+        if (!(sc > 3.0)) sc = 3.0;                                                                      /* .max(SUBSUM_BONUS) */
+        T->stretch_score = (uint32_t)ceil(sc);                                                          /* :98 */
+    }
     const uint32_t base_k = in->base_k, mk = in->minimizer_k;
     const size_t shift = mk <= base_k ? (base_k - mk) / 2 : mk - base_k;  /* :688-692 */
     for (uint64_t s = 0; s < in->n_seqs; s++) {
@@ -217,11 +225,63 @@ done:
     return n_ans;
 }
 
+/* recruit_long_read (recruit.rs:967-998) with has_matching_stretch (:932-964); single-end reads longer than
+ * READ_LENGTH_THRESH.  The per-locus MinimInfo of locus_minimizers equals the (minimizer, locus) entry of minim_to_loci:
+ * both merge every occurrence of the minimizer in the locus' sequences (:721-725). */
+typedef struct { uint32_t locus; uint32_t arr[4]; } lmatch32;
+static int recruit_one_long(const lcto_targets *T, const uint8_t *s1, size_t l1, uint32_t *ans, uint32_t cap) {
+    const size_t mcap = l1 + 1;
+    uint64_t *h = (uint64_t *)malloc(8 * mcap); uint32_t *p = (uint32_t *)malloc(4 * mcap); uint8_t *f = (uint8_t *)malloc(mcap);
+    lmatch32 *m = NULL; size_t nm = 0, mc = 0;
+    int n_ans = 0;
+    const size_t total = lcto_minimizers(s1, l1, T->k, T->w, h, p, f, mcap);
+    for (size_t q = 0; q < total; q++)
+        for (size_t e = 0; e < T->n; e++) {
+            if (T->e[e].key != h[q]) continue;
+            size_t z = 0;
+            while (z < nm && m[z].locus != T->e[e].locus) z++;
+            if (z == nm) { if (nm == mc) { mc = mc ? 2 * mc : 8; m = (lmatch32 *)realloc(m, mc * sizeof(lmatch32)); } memset(&m[nm], 0, sizeof(lmatch32)); m[nm].locus = T->e[e].locus; nm++; }
+            const int i = T->e[e].rare << 1;                          /* BaseMatchCount<u32>::inc, :246-252 */
+            m[z].arr[i] += (uint32_t)directed_to(T->e[e].dir, !f[q]);
+            m[z].arr[i | 1] += (uint32_t)directed_to(T->e[e].dir, f[q]);
+        }
+    for (size_t z = 0; z < nm; z++) {
+        const uint32_t bw_c = m[z].arr[0], fw_c = m[z].arr[1], bw_r = m[z].arr[2], fw_r = m[z].arr[3];
+        uint32_t num, den;                                             /* rare_fraction, :266-274 */
+        if (fw_r >= bw_r) { num = fw_r; den = (uint32_t)total - fw_c; } else { num = bw_r; den = (uint32_t)total - bw_c; }
+        const uint32_t nmin = T->stretch_minims < den ? T->stretch_minims : den;
+        uint32_t thr = (uint32_t)ceil((double)nmin * T->match_frac);   /* long_read_threshold, :107-109 */
+        if (thr < 1) thr = 1;
+        if (num < thr) continue;
+        int okay = den < T->stretch_minims;
+        if (!okay) {                                                   /* has_matching_stretch, :944-963 */
+            uint32_t s_fw = 0, s_bw = 0;
+            for (size_t q = 0; q < total && !okay; q++) {
+                for (size_t e = 0; e < T->n; e++)
+                    if (T->e[e].key == h[q] && T->e[e].locus == m[z].locus) {
+                        const uint32_t x = 1 + (uint32_t)T->e[e].rare * 3;
+                        s_fw += (uint32_t)directed_to(T->e[e].dir, f[q]) * x;
+                        s_bw += (uint32_t)directed_to(T->e[e].dir, !f[q]) * x;
+                    }
+                s_fw = s_fw >= 1 ? s_fw - 1 : 0;                        /* saturating_sub(SUBSUM_PENALTY) */
+                s_bw = s_bw >= 1 ? s_bw - 1 : 0;
+                if (s_fw >= T->stretch_score || s_bw >= T->stretch_score) okay = 1;
+            }
+        }
+        if (okay) { if ((uint32_t)n_ans < cap) ans[n_ans] = m[z].locus; n_ans++; }
+    }
+    for (int x = 1; x < n_ans && x < (int)cap; x++) { uint32_t v = ans[x]; int y = x; while (y > 0 && ans[y - 1] > v) { ans[y] = ans[y - 1]; y--; } ans[y] = v; }
+    free(h); free(p); free(f); free(m);
+    return n_ans;
+}
+
 int lcto_recruit_short(const lcto_targets *T, const lcto_reads *R, uint32_t cap, uint32_t *ans_count, uint32_t *ans_locus) {
     for (uint64_t r = 0; r < R->n_reads; r++) {
         const uint8_t *s1 = R->seq1 + R->off1[r]; const size_t l1 = R->off1[r + 1] - R->off1[r];
         const uint8_t *s2 = R->seq2 ? R->seq2 + R->off2[r] : NULL; const size_t l2 = R->seq2 ? R->off2[r + 1] - R->off2[r] : 0;
-        const int n = recruit_one(T, s1, l1, s2, l2, ans_locus + r * cap, cap);
+        /* RecruitableRecord::recruit, recruit.rs:582-611: single records by length, pairs always as short pairs */
+        const int n = (!s2 && l1 > 500) ? recruit_one_long(T, s1, l1, ans_locus + r * cap, cap)
+                                        : recruit_one(T, s1, l1, s2, l2, ans_locus + r * cap, cap);
         if (n < 0) return -1;
         ans_count[r] = (uint32_t)n;
     }

@@ -3,7 +3,8 @@
 CPU: the oracle (oracle/lcto_recruit.c) against a statement-by-statement Python transcription of the cited Rust --
 canonical minimizers (src/seq/kmers.rs:71-103, 256-340), TargetBuilder::add (src/seq/recruit.rs:680-735), the match
 counters (:234-385), Fraction (src/math/frac.rs:48-98), recruit_short_read / recruit_read_pair (recruit.rs:852-930) -- and
-hand-checkable properties.  GPU: lctp_minimizers / lctp_targets_build / lctp_recruit_short against the oracle, exactly."""
+recruit_long_read / has_matching_stretch (:932-998) -- and hand-checkable properties.  GPU: lctp_minimizers /
+lctp_targets_build / lctp_recruit_short against the oracle, exactly."""
 import math
 
 import numpy as np
@@ -178,6 +179,65 @@ def _recruit(minim_to_loci, mf, ts, seq1, seq2):
     return sorted(answer)
 
 
+def _recruit_long(minim_to_loci, ts, seq):
+    """recruit_long_read (recruit.rs:967-998) + has_matching_stretch (:932-964) + Params (:95-109); sorted answer."""
+    stretch_minims = (2 * ts.match_length + (ts.minimizer_w + 1) - 1) // (ts.minimizer_w + 1)       # fast_ceil_div
+    stretch_score = int(math.ceil(max(float(stretch_minims) * (float(3 + 1) * ts.match_frac - float(1)), float(3))))
+    buf = _minimizers(seq, ts.minimizer_k, ts.minimizer_w)
+    total = len(buf)
+    matches = {}
+    for _, minimizer, forward in buf:
+        for locus_ix, info in minim_to_loci.get(minimizer, ()):
+            _inc(matches.setdefault(locus_ix, [0, 0, 0, 0]), forward, info)
+    answer = []
+    for locus_ix, (bw_c, fw_c, bw_r, fw_r) in matches.items():
+        num, den = (fw_r, total - fw_c) if fw_r >= bw_r else (bw_r, total - bw_c)                   # rare_fraction
+        if num < max(1, int(math.ceil(float(min(stretch_minims, den)) * ts.match_frac))):           # long_read_threshold
+            continue
+        ok = den < stretch_minims
+        if not ok:
+            locus_minimizers = {m: i for m, v in minim_to_loci.items() for l, i in v if l == locus_ix}
+            s_fw = s_bw = 0
+            for _, minimizer, forward in buf:
+                info = locus_minimizers.get(minimizer)
+                if info is not None:
+                    x = 1 + int(info.rare) * 3
+                    s_fw += int(info.is_directed_to(forward)) * x
+                    s_bw += int(info.is_directed_to(not forward)) * x
+                s_fw, s_bw = max(s_fw - 1, 0), max(s_bw - 1, 0)
+                if s_fw >= stretch_score or s_bw >= stretch_score:
+                    ok = True
+                    break
+        if ok:
+            answer.append(locus_ix)
+    return sorted(answer)
+
+
+def _long_world(seed, n_reads=30):
+    """Targets of 12-kb alleles and HiFi-like single-end reads of 3-9 kb: on target (low error), on target but diverged,
+    chimeric (a short on-target stretch inside random sequence: passes the count test on few minimizers only) and random."""
+    rng = np.random.default_rng(seed)
+    ts, _ = _world(seed, n_loci=3, alleles=2, length=12000, n_reads=1, paired=False)
+    ts.match_length = 2000
+    ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+    reads = []
+    for _ in range(n_reads):
+        kind = rng.random()
+        n = int(rng.integers(3000, 9000))
+        if kind < 0.2:
+            r = bytes(rng.choice(ACGT, n))
+        else:
+            s = ts.seqs[int(rng.integers(0, len(ts.seqs)))]
+            st = int(rng.integers(0, len(s) - n))
+            r = _mutate(rng, s[st:st + n], 0.3 if kind < 0.35 else 0.005, 0.0005)
+            if kind > 0.8:                                                       # chimera: 600 on-target bases in the middle
+                r = bytes(rng.choice(ACGT, n // 2)) + r[:600] + bytes(rng.choice(ACGT, n // 2))
+            if rng.random() < 0.5:
+                r = _revcomp(r.replace(b"N", b"A"))
+        reads.append(r)
+    return ts, genotype.Reads(seq1=reads)
+
+
 # ------------------------------------------------------------------ synthetic targets and reads
 
 _COMP = bytes.maketrans(b"ACGT", b"TGCA")
@@ -294,6 +354,17 @@ def test_oracle_targets_and_recruitment_equal_python_transcription(oracle, seed,
         assert any(len(a) > 1 for a in got) or True               # (reads in the shared repeat may hit several loci)
 
 
+@pytest.mark.parametrize("seed", [11, 12])
+def test_oracle_long_read_recruitment_equals_python_transcription(oracle, seed):
+    ts, reads = _long_world(seed)
+    t = oracle.Targets(ts)
+    ref = _build_targets(ts)
+    got = t.recruit(reads)
+    want = [_recruit_long(ref, ts, r) for r in reads.seq1]
+    assert got == want
+    assert 0 < sum(1 for a in got if a) < len(got)
+
+
 # ------------------------------------------------------------------ GPU: the product against the oracle
 
 @pytest.mark.gpu
@@ -330,12 +401,27 @@ def test_device_recruitment_equals_the_oracle(oracle, gpu_ctx, seed, paired, mk,
 
 
 @pytest.mark.gpu
-def test_device_recruitment_rejects_long_reads_and_bad_targets(gpu_ctx):
-    ts, reads = _world(9, n_reads=5)
+@pytest.mark.parametrize("seed,n_reads", [(11, 30), (13, 400)])
+def test_device_long_read_recruitment_equals_the_oracle(oracle, gpu_ctx, seed, n_reads):
+    ts, reads = _long_world(seed, n_reads=n_reads)
     t = genotype.Targets(gpu_ctx, ts)
-    with pytest.raises(Exception):
-        t.recruit(genotype.Reads(seq1=[b"A" * 501]))
+    o = oracle.Targets(ts)
+    got = t.recruit(reads)
+    assert got == o.recruit(reads)
+    assert 0 < sum(1 for a in got if a) < len(got)
+    # a mix of short and long single-end reads in one call: each goes down its own path (recruit.rs:589)
+    ts2, short = _world(seed, n_loci=3, alleles=2, length=12000, n_reads=50, paired=False)
+    mixed = genotype.Reads(seq1=list(reads.seq1[:10]) + list(short.seq1[:40]))
+    assert t.recruit(mixed) == o.recruit(mixed)
     t.free()
+
+
+@pytest.mark.gpu
+def test_device_recruitment_rejects_bad_targets(gpu_ctx):
+    ts, reads = _world(9, n_reads=5)
     ts.match_frac = 0.1
+    with pytest.raises(Exception):
+        genotype.Targets(gpu_ctx, ts)
+    ts.match_frac, ts.match_length = 0.5, 100
     with pytest.raises(Exception):
         genotype.Targets(gpu_ctx, ts)
