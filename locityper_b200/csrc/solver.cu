@@ -612,82 +612,66 @@ __device__ void apply_tweak(const LocusDev &L, const Slab<WIDE> &S, const Instan
     const uint32_t tweak = L.tweak, R = L.R, p = L.p;
     const uint32_t span = 2 * tweak + 1;
     // (i) read middles: one next_u64 per candidate that has a parent, in candidate order (read-major).
-    // Lanes over reads; a read's candidates take consecutive draws starting at the exclusive prefix sum of the
-    // parented-candidate counts, fetched from the draw buffer by index.  A batch that straddles the end of the
-    // fill is processed in two epochs with the refill in between.  Candidates are handled four at a time so that
-    // the dependent gathers (record -> pair-alignment middles, draw) of different candidates overlap.
-    for (uint32_t r0 = 0; r0 < R; r0 += 32) {
-        const uint32_t r = r0 + lane;
-        const bool valid = r < R;
-        uint32_t o = 0, n = 0, b0 = 0, b1 = 0;
-        if (valid) {
-            o = ws.off[r];
-            n = (uint32_t)ws.off[r + 1] - o;
-            b0 = L.cm_off[(size_t)I.h0 * R + r];
-            if (p > 1) b1 = L.cm_off[(size_t)I.h1 * R + r];
-        }
-        const uint32_t has_unm = (ws.unm_bits[r0 >> 5] >> lane) & 1u;
-        const uint32_t npar = (tweak != 0 && valid) ? n - has_unm : 0u;
-        uint32_t incl = npar;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(FULL, incl, d);
-            if (lane >= d) incl += t;
-        }
-        const uint32_t total = wshfl(incl, 31);
-        const uint32_t q0 = incl - npar;
-        uint32_t done = 0;
-        for (;;) {
-            if (rng.pos == RNG_FILL && total > done) stream_refill(rng);
-            const uint32_t take = min(total - done, RNG_FILL - rng.pos);
-            uint32_t q = q0;
-            for (uint32_t j0 = 0; j0 < n; j0 += 4) {
-                Rec rc[4];
-                uint2 mid[4];
-                uint64_t draw[4];
-                uint32_t hap[4];
-                bool mine[4];
-#pragma unroll
-                for (int t = 0; t < 4; t++) rc[t] = j0 + t < n ? S.rec[o + j0 + t] : RW::make(SRC_UNMAPPED, 0u, 0u);
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const uint32_t sb = RW::src(rc[t]);
-                    const bool par = j0 + t < n && sb != SRC_UNMAPPED;
-                    mine[t] = par && (tweak == 0 ? done == 0 : (q >= done && q < done + take));
-                    mid[t] = make_uint2(0u, 0u); draw[t] = 0; hap[t] = 0;
-                    if (mine[t]) {
-                        const uint32_t k = sb >> 4;
-                        hap[t] = inst_hap(I, ws, k);
-                        const uint32_t cb = k == 0 ? b0 : k == 1 ? b1 : L.cm_off[(size_t)hap[t] * R + r];
-                        mid[t] = L.cm_mid[cb + (sb & 15u)];
-                        if (tweak != 0) draw[t] = __ldcg(rng.buf + rng.pos + (q - done));
-                    }
-                    q += par ? 1u : 0u;
-                }
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    if (j0 + t >= n) continue;
-                    const uint32_t sb = RW::src(rc[t]);
-                    if (sb == SRC_UNMAPPED) {
-                        if (done == 0) S.rec[o + j0 + t] = RW::make(SRC_UNMAPPED, 0u, 0u);   // [UNMAPPED_WINDOW; 2] (windows.rs:99-105)
-                    } else if (mine[t]) {
-                        const uint32_t shift = inst_wshift(ws, sb >> 4);
-                        const uint32_t reg_start = L.hap_reg_start[hap[t]];
-                        const uint32_t reg_end = reg_start + L.hap_n_windows[hap[t]] * L.window;
-                        // x % span = hi64((c * x mod 2^64) * span), c = ceil(2^64 / span) (exact for 32-bit x and span)
-                        const uint32_t t1 = tweak ? (uint32_t)__umul64hi(L.c_span * (uint64_t)(uint32_t)(draw[t] >> 32), span) : 0u;
-                        const uint32_t t2 = tweak ? (uint32_t)__umul64hi(L.c_span * (uint64_t)(uint32_t)draw[t], span) : 0u;
-                        const uint32_t w1 = mid[t].x == LCTP_NONE_U32 ? 0u : shifted_window(L, reg_start, reg_end, shift, mid[t].x + t1);
-                        const uint32_t w2 = mid[t].y == LCTP_NONE_U32 ? 0u : shifted_window(L, reg_start, reg_end, shift, mid[t].y + t2);
-                        S.rec[o + j0 + t] = RW::make(sb, w1, w2);
-                    }
-                }
+    // Lanes over CANDIDATES (the records of a genotype are contiguous in read order): candidate i takes draw number
+    // i - #(unmapped options before i), its read is found from the offsets of the <= 32 reads that a round of 32
+    // candidates touches (one coalesced load + one REDUX), records are read and written coalesced.  A round that
+    // straddles the end of the draw buffer is processed in two parts with the refill in between.  (Lanes over reads,
+    // four candidates at a time, cost 8x the instructions: 11 % of the C2 stage kernel, profiles/r02_summary.md.)
+    {
+        const uint32_t A = I.A;
+        uint32_t r_lo = 0;                       // read of candidate i0
+        uint32_t cum_unm = 0;                    // unmapped options among the candidates before i0
+        int fill_q0 = -(int)rng.pos;             // draw number that sits at position 0 of the current fill
+        for (uint32_t i0 = 0; i0 < A; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const bool valid = i < A;
+            // ends of the reads r_lo, r_lo + 1, ...: a read that ends inside (i0, i0 + 32) starts the next one there
+            const uint32_t er = r_lo + 1u + lane;
+            const uint32_t e = er <= R ? (uint32_t)ws.off[er] : 0xFFFFFFFFu;
+            const unsigned starts = __reduce_or_sync(FULL, (e > i0 && e < i0 + 32u) ? (1u << (e - i0)) : 0u);
+            const uint32_t r = r_lo + (uint32_t)__popc(starts & (0xFFFFFFFFu >> (31u - lane)));
+            r_lo += (uint32_t)__popc(starts) + (wany(e == i0 + 32u) ? 1u : 0u);
+            const Rec rc = valid ? S.rec[i] : RW::make(SRC_UNMAPPED, 0u, 0u);
+            const uint32_t sb = RW::src(rc);
+            const bool par = valid && sb != SRC_UNMAPPED;
+            const unsigned unm = wballot(valid && sb == SRC_UNMAPPED);
+            const int q = (int)(i - cum_unm - (uint32_t)__popc(unm & ((1u << lane) - 1u)));     // draw number of this candidate
+            cum_unm += (uint32_t)__popc(unm);
+            uint2 mid = make_uint2(0u, 0u);
+            uint32_t hap = 0;
+            if (par) {
+                const uint32_t k = sb >> 4;
+                hap = inst_hap(I, ws, k);
+                mid = L.cm_mid[L.cm_off[(size_t)hap * R + r] + (sb & 15u)];
             }
-            __syncwarp();            // every lane has read its draws of this epoch before the buffer is refilled
-            rng.pos += take;
-            done += take;
-            if (done >= total) break;
+            if (valid && !par) S.rec[i] = RW::make(SRC_UNMAPPED, 0u, 0u);       // [UNMAPPED_WINDOW; 2] (windows.rs:99-105)
+            bool todo = par;
+            for (;;) {
+                const int rel = q - fill_q0;                                    // position of the draw in the current fill
+                const bool now = todo && (tweak == 0 || rel < (int)RNG_FILL);
+                if (now) {
+                    uint32_t t1 = 0, t2 = 0;
+                    if (tweak) {
+                        // x % span = hi64((c * x mod 2^64) * span), c = ceil(2^64 / span) (exact for 32-bit x and span)
+                        const uint64_t draw = __ldcg(rng.buf + rel);
+                        t1 = (uint32_t)__umul64hi(L.c_span * (uint64_t)(uint32_t)(draw >> 32), span);
+                        t2 = (uint32_t)__umul64hi(L.c_span * (uint64_t)(uint32_t)draw, span);
+                    }
+                    const uint32_t shift = inst_wshift(ws, sb >> 4);
+                    const uint32_t reg_start = L.hap_reg_start[hap];
+                    const uint32_t reg_end = reg_start + L.hap_n_windows[hap] * L.window;
+                    const uint32_t w1 = mid.x == LCTP_NONE_U32 ? 0u : shifted_window(L, reg_start, reg_end, shift, mid.x + t1);
+                    const uint32_t w2 = mid.y == LCTP_NONE_U32 ? 0u : shifted_window(L, reg_start, reg_end, shift, mid.y + t2);
+                    S.rec[i] = RW::make(sb, w1, w2);
+                    todo = false;
+                }
+                if (!wany(todo)) break;
+                __syncwarp();                    // every lane has read its draws of this fill before it is replaced
+                stream_refill(rng);
+                fill_q0 += (int)RNG_FILL;
+            }
         }
+        if (tweak) rng.pos = (uint32_t)((int)(A - cum_unm) - fill_q0);
     }
     // (ii) window distributions: one bounded i32 draw per window, contigs in genotype order
     if (lane < 2) { ws.win.weight(lane) = 0.0; ws.win.row(lane) = ws.zero_row; ws.win.depth(lane) = 0; }
