@@ -1122,6 +1122,9 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
         asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(f_info.x), "=r"(f_info.y) : "l"(ws.ntinfo + q_nt));
         asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(f_raw) : "l"(draw_hi + 2u * q_at));
         uint32_t mv_r = 0xFFFFFFFFu, mv_old = 0;     // read moved by this round's stage C
+        bool refresh = false;                        // ... and the deferred refresh of its windows' products
+        uint32_t rf_w = 0;
+        double rf_t = 0.0;
         if (vC) {
             // ---- stage C: evaluate the sample of this iteration
             Cand<WIDE> best;
@@ -1196,15 +1199,27 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
                 }
                 __syncwarp();
                 mv_r = ws.samp[4]; mv_old = ws.samp[5];
-                // slide the product slices of the (up to four) windows whose depth changed
-                if (lane < 20u) win_refresh(ws, L.depth_table, ws.samp[lane / 5u], (int)(lane % 5u));
-                __syncwarp();
+                // slide the product slices of the (up to four) windows whose depth changed.  Only the next stage C reads
+                // them: the depth-table entries are fetched here and the products are stored at the end of the round, so
+                // that the L2 latency of the fetch (ncu: 3.7 % of the kernel in the dependent DMUL) is not waited for.
+                if (lane < 20u) {
+                    rf_w = ws.samp[lane / 5u];
+                    const int d = min(max((int)ws.win.depth(rf_w) + (int)(lane % 5u) - 2, 0), (int)ws.depth_k - 1);
+                    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(rf_t) : "l"(L.depth_table + ws.win.row(rf_w) + d));
+                }
+                refresh = true;
                 curr_plato = 0;
             } else {
                 curr_plato += 1;
                 if (curr_plato > plato_size) break;
             }
-            if (it >= max_iter) break;
+            if (it >= max_iter) {
+                if (refresh) {                       // leave the window state complete (the debug outputs read it)
+                    if (lane < 20u) ws.win.p(rf_w, (int)(lane % 5u)) = __dmul_rn(ws.win.weight(rf_w), rf_t);
+                    __syncwarp();
+                }
+                break;
+            }
         }
         // ---- stage S1 of the newest sample first: its MATCH.ANY is issued here and its result read at the end of the
         // round (~150 instructions later), so that its ~250 cycles are not waited for
@@ -1303,6 +1318,10 @@ __device__ void greedy_solve(const LocusDev &L, const StageParams &P, const Slab
         q_at = min(dpos, RNG_FILL - amount);        // past the fill: re-read, not used
         dpos += v0 ? amount : 0u;
         s_dup = wany(v1 && lane < amount && (n_match & lt_mask) != 0u);
+        if (refresh) {                               // second half of win_refresh (see stage C)
+            if (lane < 20u) ws.win.p(rf_w, (int)(lane % 5u)) = __dmul_rn(ws.win.weight(rf_w), rf_t);
+            __syncwarp();
+        }
         if (__builtin_expect(!v0 && !v1 && !vA && !vB && !vC, 0)) {
             // empty pipeline: the next sample one draw at a time; stage A of the next round picks it up
             uint32_t v = 0;
