@@ -114,3 +114,43 @@ def test_stage_debug_fields_and_counts(oracle, gpu_ctx, small_locus):
         assert np.array_equal(counts[k], want)
         assert counts[k].sum() == 4 * loc.n_reads            # every read is somewhere in each of the 4 attempts
     dl.free()
+
+
+def test_edge_cases_of_the_widened_entry_points(gpu_ctx, tmp_path):
+    """Empty and degenerate inputs of the section-8(f) entry points: nothing to do is not an error, malformed input is."""
+    import ctypes as C
+    from locityper_b200 import ffi
+    lib = gpu_ctx.lib
+    # no reads: nothing is launched
+    ts = genotype.TargetSeqs(seqs=[b"ACGT" * 100], seq_locus=np.zeros(1, dtype=np.uint32),
+                             kmer_counts=[np.zeros(400 + 1 - 25, dtype=np.uint16)], base_k=25, minimizer_k=15, minimizer_w=10,
+                             thresh_kmer_count=10, match_frac=0.5)
+    t = genotype.Targets(gpu_ctx, ts)
+    assert t.recruit(genotype.Reads(seq1=[])) == []
+    # reads shorter than k have no minimizers and are not recruited; an all-N read neither
+    assert t.recruit(genotype.Reads(seq1=[b"ACG", b"", b"N" * 150], seq2=[b"ACG", b"ACGT", b"N" * 150])) == [[], [], []]
+    t.free()
+    assert genotype.minimizers(gpu_ctx, [], 15, 10) == []
+    # a k-mer count array of the wrong length is refused (the reference asserts, recruit.rs:698-699)
+    ts.kmer_counts = [np.zeros(10, dtype=np.uint16)]
+    with pytest.raises(Exception):
+        genotype.Targets(gpu_ctx, ts)
+    # the debug sink needs an existing directory
+    with pytest.raises(Exception):
+        gpu_ctx.debug_open(str(tmp_path / "does" / "not" / "exist"), 2, ["a", "b"])
+    gpu_ctx.debug_close()                      # closing a closed sink is a no-op
+    # read ends: zero groups
+    empty = genotype.ReadEnds(alns=genotype.Alns(cigar_off=np.zeros(1, dtype=np.uint64), cigar_ops=np.zeros(0, dtype=np.uint32),
+                                                 aln_start=np.zeros(0, dtype=np.uint32), aln_end=np.zeros(0, dtype=np.uint32),
+                                                 contig_len=np.zeros(0, dtype=np.uint32), passable_dist=np.zeros(0, dtype=np.uint32),
+                                                 ln_oper=(-0.005, -5.8, -6.5, -6.9, -5.8)),
+                              grp_off=np.zeros(1, dtype=np.uint64), rec_contig=np.zeros(0, dtype=np.uint32),
+                              grp_read_end=np.zeros(0, dtype=np.uint8), grp_read_len=np.zeros(0, dtype=np.uint32),
+                              grp_good_dist=np.zeros(0, dtype=np.uint32), grp_passable_dist=np.zeros(0, dtype=np.uint32),
+                              grp_neighb_complexity=np.zeros(0), poor_compl=0.5, poor_compl_edit=0.07)
+    out = genotype.collect_read_ends(gpu_ctx, empty)
+    assert len(out["ok"]) == 0 and len(out["kept_rec"]) == 0
+    # NULL handles return error codes, never crash
+    assert lib.lctp_recruit_short(gpu_ctx._h, None, None, 8, None, None) == -1
+    assert lib.lctp_debug_open(None, b"/tmp", 1, None, 0) == -1
+    assert lib.lctp_solve_counts(None, None, 0, 1, None, None, 0, None, None, 0) == -1
