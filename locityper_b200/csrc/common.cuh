@@ -96,6 +96,7 @@ struct BalPlan {
 
 }  // namespace lctp
 
+struct lctp_dist;
 struct lctp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -123,6 +124,7 @@ struct lctp_ctx {
     std::string dbg_dir;
     std::vector<std::string> dbg_names;
     FILE *dbg_sol = nullptr, *dbg_sol_ext = nullptr, *dbg_depth = nullptr;
+    lctp_dist *local_sel = nullptr;      // one-rank candidate selector of the single-GPU prefilter (dist.cu)
 };
 
 // Device-side view of one uploaded locus (all pointers are device pointers).
@@ -213,6 +215,9 @@ int launch_stage_ex(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worke
                     const uint64_t *worker_off, size_t n_workers, uint64_t *worker_rng,
                     double *lik_mean, double *lik_var, double *liks, uint64_t *counts_off,
                     uint16_t *counts, uint64_t counts_cap, uint64_t *n_alns_out, uint64_t *iters_out, bool device_only);
+// dist.cu
+lctp_dist *local_selector(lctp_ctx *ctx);
+void free_local_selector(lctp_ctx *ctx);
 // host_solve.cpp
 void genotype_tuple(uint32_t H, uint32_t p, const uint32_t *gt_tuples, uint64_t g, uint32_t *out);
 }  // namespace lctp

@@ -168,6 +168,12 @@ static int gather_to_host(lctp_dist *d, size_t bytes) {
     int rc;
     if ((rc = d->recv.ensure(bytes * d->world))) return rc;
     if ((rc = d->host_recv.ensure(bytes * d->world))) return rc;
+    if (!d->comm) {        // the context's own one-rank selector (lctp::local_selector): no communicator, nothing to gather
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(d->host_recv.p, d->send.p, bytes, cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
+        ctx->stats.d2h_bytes += bytes;
+        return LCTP_OK;
+    }
     LCTP_CUDA_CHECK(cudaEventRecord(d->ev[0], s));
     LCTP_NCCL_CHECK(nccl_api()->AllGather(d->send.p, d->recv.p, bytes, ncclChar, d->comm, s));
     LCTP_CUDA_CHECK(cudaEventRecord(d->ev[1], s));
@@ -249,6 +255,29 @@ int lctp_dist_init(lctp_ctx *ctx, const uint8_t id[LCTP_DIST_ID_BYTES], int rank
     *out = d;
     return LCTP_OK;
 }
+
+}  // extern "C"
+
+// The single-GPU prefilter uses the same device-side candidate selection (sort of the scores on the device, the candidate set
+// is a prefix, a few thousand (score, id) pairs cross to the host instead of all G scores): a one-rank selector without a
+// communicator, owned by the context.
+namespace lctp {
+lctp_dist *local_selector(lctp_ctx *ctx) {
+    if (!ctx->local_sel) {
+        lctp_dist *d = new lctp_dist();
+        d->ctx = ctx; d->rank = 0; d->world = 1; d->comm = nullptr;
+        cudaEventCreate(&d->ev[0]);
+        cudaEventCreate(&d->ev[1]);
+        ctx->local_sel = d;
+    }
+    return ctx->local_sel;
+}
+void free_local_selector(lctp_ctx *ctx) {
+    if (ctx->local_sel) { lctp_dist_destroy(ctx->local_sel); ctx->local_sel = nullptr; }
+}
+}  // namespace lctp
+
+extern "C" {
 
 void lctp_dist_destroy(lctp_dist *d) {
     if (!d) return;

@@ -388,6 +388,7 @@ int lctp_init(const lctp_device_cfg *cfg, lctp_ctx **out) {
 void lctp_destroy(lctp_ctx *ctx) {
     lctp_debug_close(ctx);
     if (!ctx) return;
+    lctp::free_local_selector(ctx);
     cudaSetDevice(ctx->device);
     set_alloc_stream(ctx->stream);
     cudaStreamSynchronize(ctx->stream);
@@ -699,9 +700,15 @@ int lctp_prefilter(lctp_locus_h *h, uint64_t *ixs, size_t n, size_t min_size, si
                    double *scores_out) {
     if (!h || !ixs || !out_n || n == 0) { set_error("lctp_prefilter: NULL/empty argument"); return LCTP_E_INVALID; }
     const uint64_t G = h->dev.G;
+    // The usual call (solve.rs:939-944: the complete list 0..G, scores not wanted on the host): candidates are selected on
+    // the device, only they cross to the host (csrc/dist.cu; the same code path as one rank of the multi-GPU split).
+    if (!scores_out && n == G && n >= 4096 && !getenv("LCTP_HOST_PREFILTER")) {
+        bool full = true;
+        for (size_t q = 0; q < n && full; q++) full = ixs[q] == q;
+        if (full) return lctp_dist_prefilter(lctp::local_selector(h->ctx), h, min_size, threads, ixs, n, out_n);
+    }
     std::vector<double> scores(G, -std::numeric_limits<double>::infinity());
-    // The reference always filters the complete list (predictions.ixs = 0..G, solve.rs:939-944); an
-    // arbitrary subset is scored over its covering range.
+    // an arbitrary subset is scored over its covering range.
     uint64_t lo = G, hi = 0;
     for (size_t q = 0; q < n; q++) {
         if (ixs[q] >= G) { set_error("lctp_prefilter: genotype id out of range"); return LCTP_E_INVALID; }
