@@ -58,6 +58,9 @@ def parse_args():
                     help="skip the extra prefilter-only measurement at the KIR-scale shape (configs[3])")
     ap.add_argument("--cpu-loci", type=int, default=0, help="loci in the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-shard-kir", action="store_true", help="skip the sharded KIR-scale solve (configs[3])")
+    ap.add_argument("--kir-threads", type=int, default=5000,
+                    help="-@ of the sharded KIR-scale solve: one logical worker per surviving genotype of its greedy:i=5k stage, so\n"
+                         "that the longest chain of a rank is one genotype (0 = same as --threads)")
     ap.add_argument("--no-t-sweep", action="store_true", help="skip the T = 8 / 64 / bench-T rows")
     return ap.parse_args()
 
@@ -437,7 +440,7 @@ def shard_kir(args, ctx, genotype, rank, world, dev):
     import torch
     import torch.distributed as dist
     from locityper_b200 import synth
-    T = auto_threads(args)
+    T = args.kir_threads if args.kir_threads > 0 else auto_threads(args)
     loc = synth.make_locus(**synth.config_shape("C4"), seed=4001, table_builder=genotype.build_depth_table)
     dl = ctx.upload(loc)
     idt = torch.zeros(128, dtype=torch.uint8, device=dev)
