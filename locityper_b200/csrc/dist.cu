@@ -457,16 +457,18 @@ int lctp_dist_solve(lctp_dist *d, lctp_locus_h *h, const lctp_stage *stages, siz
     const uint64_t G = h->dev.G;
     std::memset(res, 0, sizeof(*res));
     threads = std::max<size_t>(1, std::min<size_t>(threads, G));     // genotype.rs:1247
-    std::vector<uint64_t> ixs(G);
     size_t n = G;
-    const double nan = std::numeric_limits<double>::quiet_NaN();
-    // per-genotype results by id, only for ids that were ever solved (sparse: G can be 500,500)
-    std::vector<double> lik_mean(G, nan), lik_var(G, nan);
-    std::vector<uint16_t> attempts(G, 0);
+    // per-genotype results by id: the context's reusable arrays (clean between solves), see common.cuh
+    lctp::per_id_reserve(d->ctx, G);
+    std::vector<uint64_t> &ixs = d->ctx->id_list;
+    std::vector<double> &lik_mean = d->ctx->id_mean, &lik_var = d->ctx->id_var;
+    std::vector<uint16_t> &attempts = d->ctx->id_attempts;
+    std::vector<uint64_t> touched;
+    struct Cleaner { lctp_ctx *c; std::vector<uint64_t> &t; ~Cleaner() { lctp::per_id_clean(c, t); } } cleaner{d->ctx, touched};
     int rc;
     if (h->host.dont_skip || stages[0].in_size < G) {                // solve.rs:941-945
-        if ((rc = lctp_dist_prefilter(d, h, stages[0].in_size, threads, ixs.data(), ixs.size(), &n))) return rc;
-    } else std::iota(ixs.begin(), ixs.end(), 0);
+        if ((rc = lctp_dist_prefilter(d, h, stages[0].in_size, threads, ixs.data(), G, &n))) return rc;
+    } else std::iota(ixs.begin(), ixs.begin() + G, 0);
     res->n_filtered = n;
     std::vector<uint64_t> wrng;
     if (threads > 1) {                                               // MainWorker::new, solve.rs:1007-1018
@@ -482,6 +484,7 @@ int lctp_dist_solve(lctp_dist *d, lctp_locus_h *h, const lctp_stage *stages, siz
         if (!(h->host.dont_skip || !has_next || out_size < n)) continue;   // solve.rs:1041-1045
         res->n_stage_in[s] = n;
         lm.resize(n); lv.resize(n);
+        if (touched.empty()) touched.assign(ixs.begin(), ixs.begin() + n);     // later stages solve subsets of these
         if (threads == 1) {                                          // solve_single_thread: one stream, no shuffle
             off[0] = 0; off[1] = n;
             rc = lctp_dist_solve_stage(d, h, &st, ixs.data(), off.data(), 1, rng, lm.data(), lv.data());

@@ -966,12 +966,15 @@ static int solve_impl(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages
     const uint64_t G = h->dev.G;
     std::memset(res, 0, sizeof(*res));
     threads = std::max<size_t>(1, std::min<size_t>(threads, G));     // genotype.rs:1247
-    std::vector<uint64_t> ixs(G);
-    std::iota(ixs.begin(), ixs.end(), 0);
+    // per-genotype results by id: the context's reusable arrays (clean between solves), see common.cuh
+    lctp::per_id_reserve(ctx, G);
+    std::vector<uint64_t> &ixs = ctx->id_list;
+    std::iota(ixs.begin(), ixs.begin() + G, 0);
     size_t n = G;
-    const double nan = std::numeric_limits<double>::quiet_NaN();
-    std::vector<double> lik_mean(G, nan), lik_var(G, nan);
-    std::vector<uint16_t> attempts(G, 0);
+    std::vector<double> &lik_mean = ctx->id_mean, &lik_var = ctx->id_var;
+    std::vector<uint16_t> &attempts = ctx->id_attempts;
+    std::vector<uint64_t> touched;
+    struct Cleaner { lctp_ctx *c; std::vector<uint64_t> &t; ~Cleaner() { lctp::per_id_clean(c, t); } } cleaner{ctx, touched};
 
     const double t0 = now_s();
     if (h->host.dont_skip || stages[0].in_size < G) {                // solve.rs:941-945
@@ -1008,6 +1011,7 @@ static int solve_impl(lctp_locus_h *h, const lctp_stage *stages, size_t n_stages
         if (!(h->host.dont_skip || !has_next || out_size < n)) continue;   // solve.rs:1041-1045
         res->n_stage_in[s] = n;
         lm.resize(n); lv.resize(n);
+        if (touched.empty()) touched.assign(ixs.begin(), ixs.begin() + n);     // later stages solve subsets of these
         // debug tables of this stage (Worker::run, solve.rs:1128-1134; MainWorker::run :1064-1075)
         const bool ext_rows = ctx->dbg_sol_ext != nullptr, depth_rows = ctx->dbg_depth != nullptr;
         const bool sol_rows = ctx->dbg_sol && (ctx->dbg_level >= 1 || !has_next);
