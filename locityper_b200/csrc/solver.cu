@@ -1460,10 +1460,171 @@ __device__ bool greedy_solve_big(const LocusDev &L, const StageParams &P, const 
 
 // ------------------------------------------------------------------ a11: SimAnneal --------------
 
-// SimAnneal::solve_nontrivial (src/solvers/stoch.rs:197-242).  One candidate per step in the reference; here
-// whole chains of steps are evaluated speculatively against the current state (spec_targets) and committed up
-// to the first accepted step, which reproduces the sequential result exactly: a rejected step changes nothing
-// but the plateau counter.
+// Look-ahead over the next 32 stream positions.  A step's draws fix its read and (given the read's current
+// assignment) its new location, and everything calculate_improvement loads from global memory for it -- the two
+// candidate records and their ln-probabilities -- depends on nothing else.  So lane l prepares the step that WOULD
+// start at stream position pos + l: all the dependent loads of ~12 future steps are in flight together, once per
+// round, instead of once per step.  The walk then follows the actual chain of steps (2 or 3 draws each) one after
+// the other on warp-uniform values: broadcast the prepared step of the lane at the current position, take the
+// depth-likelihood difference from the shared-memory window state, decide, apply.  A prepared step whose read was
+// reassigned earlier in the same walk is stale (its new location was derived from the old assignment): the walk
+// stops there and the next round looks again.  Exact by construction: every step is evaluated against the state
+// the sequential solver would see, with the same draws.
+struct Look {
+    bool ok;                     // the step at this lane's position needs no bias-correction draw and fits the fill
+    uint32_t r, o, a, new_a;     // its target
+    uint32_t nd;                 // draws of the target (1 or 2)
+    uint64_t udraw;              // the draw after them
+};
+template <bool WITH_U>
+__device__ __forceinline__ void look_targets(const WarpShared &ws, const Instance &I, Xo &rng, Look &lk) {
+    const uint32_t lane = ws.lane;
+    lk.ok = false; lk.r = lk.o = lk.a = lk.new_a = 0; lk.nd = 1; lk.udraw = 0;
+    if (rng.pos >= RNG_FILL) return;
+    stream_cover(rng, 1);
+    const uint32_t avail = min(32u, RNG_FILL - rng.pos);
+    const uint64_t d = stream_peek64(rng, lane);
+    const uint64_t d1 = __shfl_down_sync(FULL, d, 1), d2 = __shfl_down_sync(FULL, d, 2);
+    const uint64_t m = (d >> 32) * (uint64_t)I.n_nt;
+    const bool bias1 = (uint32_t)m > 0u - I.n_nt;
+    const uint2 inf = nt_info(ws, (uint32_t)(m >> 32));
+    lk.r = inf.y;
+    lk.o = inf.x & 0xFFFFu;
+    const uint32_t n = inf.x >> 16;
+    lk.a = ws.assgn[lk.r];
+    const bool two = n > 2;
+    const uint64_t m2 = (d1 >> 32) * (uint64_t)(n - 1u);
+    const bool bias2 = two && (uint32_t)m2 > 0u - (n - 1u);
+    const uint32_t i2 = 1u + (uint32_t)(m2 >> 32);
+    lk.new_a = two ? (i2 <= lk.a ? i2 - 1u : i2) : 1u - lk.a;
+    lk.nd = two ? 2u : 1u;
+    lk.udraw = two ? d2 : d1;
+    lk.ok = lane + lk.nd + (WITH_U ? 1u : 0u) <= avail && !bias1 && !bias2;
+}
+
+// The state-independent part of calculate_improvement: candidate records and aln-likelihood difference.
+template <bool WIDE>
+__device__ __forceinline__ void calc_static(const LocusDev &L, const Slab<WIDE> &S, const Instance &I,
+                                            const WarpShared &ws, uint32_t r, uint32_t o, uint32_t a, uint32_t new_a,
+                                            Move<WIDE> &mv) {
+    typedef RecWord<WIDE> RW;
+    mv.raw_old = S.rec[o + a];
+    mv.raw_new = S.rec[o + new_a];
+    const uint32_t so = RW::src(mv.raw_old), sn = RW::src(mv.raw_new);
+    uint32_t io, in;
+    if (L.p <= 2) {
+        const uint32_t b0 = __ldg(L.cm_off + (size_t)I.h0 * L.R + r);
+        const uint32_t b1 = L.p > 1 ? __ldg(L.cm_off + (size_t)I.h1 * L.R + r) : 0u;
+        io = lp_index2(L, r, so, b0, b1);
+        in = lp_index2(L, r, sn, b0, b1);
+    } else {
+        io = lp_index(L, I, ws, r, so);
+        in = lp_index(L, I, ws, r, sn);
+    }
+    mv.dlp = __dsub_rn(__ldg(L.cm_lnprob + in), __ldg(L.cm_lnprob + io));
+    mv.dld = 0.0;
+}
+
+// reassign for the walk: the window slices are SHIFTED instead of recomputed.  A depth change of +-1 moves the five
+// products weight * table[row][d-2 .. d+2] by one place inside shared memory; only the entry that enters at the edge
+// (k = 4 or 0) comes from the depth table in global memory.  That load is issued here and its product is stored by
+// pend_flush -- before the next reassign, before a step that reads an edge entry (a depth change of +-2: both windows
+// of a location equal), and at the end of the walk -- so the steps in between run while it is in flight.  The shifted
+// values are the very products a recomputation would store (same weight, same table entry), so this is exact.
+struct Pend { uint32_t idx; double tv; };      // idx = window | slice entry << 24 (0xFFFFFFFF = nothing pending)
+static constexpr uint32_t PEND_NONE = 0xFFFFFFFFu;
+__device__ __forceinline__ void pend_flush(const WarpShared &ws, Pend &pd) {
+    if (pd.idx != PEND_NONE) {
+        const uint32_t w = pd.idx & 0xFFFFFFu;
+        ws.win.p(w, (int)(pd.idx >> 24)) = __dmul_rn(ws.win.weight(w), pd.tv);
+        pd.idx = PEND_NONE;
+    }
+    __syncwarp();
+}
+template <bool WIDE>
+__device__ __forceinline__ void apply_move_shift(const WarpShared &ws, const double *__restrict__ table, uint32_t r,
+                                                 uint32_t new_a, const Move<WIDE> &mv, Pend &pd) {
+    typedef RecWord<WIDE> RW;
+    const uint32_t w1 = RW::w1(mv.raw_old), w2 = RW::w2(mv.raw_old), w3 = RW::w1(mv.raw_new), w4 = RW::w2(mv.raw_new);
+    pend_flush(ws, pd);
+    // net depth change of every distinct window, carried by its first occurrence (depth_lik_diff's c1..c4)
+    const int e21 = w2 == w1, e31 = w3 == w1, e32 = (w3 == w2) & !e31;
+    const int e41 = w4 == w1, e42 = (w4 == w2) & !e41, e43 = (w4 == w3) & !e41 & !e42;
+    const int c1 = -1 - e21 + e31 + e41;
+    const int c2 = e21 ? 0 : -1 + e32 + e42;
+    const int c3 = (e31 | e32) ? 0 : 1 + e43;
+    const int c4 = (e41 | e42 | e43) ? 0 : 1;
+    const int j = (int)ws.lane / 5, k = (int)ws.lane % 5;
+    const uint32_t w = j == 0 ? w1 : j == 1 ? w2 : j == 2 ? w3 : w4;
+    const int c = ws.lane >= 20u ? 0 : j == 0 ? c1 : j == 1 ? c2 : j == 2 ? c3 : c4;
+    const int src = k + c;
+    const bool inside = src >= 0 && src <= 4;
+    double v = 0.0;
+    if (c != 0) {
+        if (inside) v = ws.win.p(w, src);
+        else {
+            const int d = min(max((int)ws.win.depth(w) + c + k - 2, 0), (int)ws.depth_k - 1);
+            pd.tv = __ldg(table + ws.win.row(w) + d);
+            pd.idx = w | ((uint32_t)k << 24);
+        }
+    }
+    __syncwarp();                                      // every old slice entry has been read
+    if (ws.lane == 0) {
+        ws.win.depth(w3) += 1;
+        ws.win.depth(w4) += 1;
+        ws.win.depth(w1) -= 1;
+        ws.win.depth(w2) -= 1;
+        ws.assgn[r] = (uint8_t)new_a;
+        ws.lik[1] = __dadd_rn(ws.lik[1], mv.dld);       // depth_lik += ..., aln_lik += ... (assgn.rs:336-337)
+        ws.lik[0] = __dadd_rn(ws.lik[0], mv.dlp);
+    }
+    if (c != 0 && inside) ws.win.p(w, k) = v;
+    // a change of +-2 leaves an entry next to the centre pending, and those are read by ordinary steps
+    if ((c1 == -2) | (c3 == 2)) pend_flush(ws, pd);    // (c2 and c4 stay within -1..1)
+    else __syncwarp();
+}
+
+// One prepared step at walk position q (warp-uniform): target and move broadcast from lane q; false = stale.
+template <bool WIDE>
+__device__ __forceinline__ bool walk_fetch(const WarpShared &ws, const Look &lk, const Move<WIDE> &mv, uint32_t q,
+                                           uint32_t &r, uint32_t &new_a, Move<WIDE> &w, Pend &pd) {
+    typedef RecWord<WIDE> RW;
+    const uint32_t packed = wshfl(lk.r | (lk.a << 16) | (lk.new_a << 24), (int)q);
+    r = packed & 0xFFFFu;
+    new_a = packed >> 24;
+    if (ws.assgn[r] != ((packed >> 16) & 0xFFu)) return false;
+    w.raw_old = wshfl(mv.raw_old, (int)q); w.raw_new = wshfl(mv.raw_new, (int)q);
+    w.dlp = wshfl(mv.dlp, (int)q);
+    // a location with both windows equal changes a depth by two: that reads an edge entry (see apply_move_shift)
+    if ((RW::w1(w.raw_old) == RW::w2(w.raw_old)) | (RW::w1(w.raw_new) == RW::w2(w.raw_new))) pend_flush(ws, pd);
+    w.dld = depth_lik_diff_raw<WIDE>(ws, w.raw_old, w.raw_new);
+    return true;
+}
+
+// The acceptance test of a step with a negative diff, `rng.random::<f64>() <= (diff / temp).exp()` (stoch.rs:216), v = the
+// raw draw.  An f64 division and exponential are ~80 FP64-pipe instructions, and 70 % of the annealing steps need
+// them; the FP64 pipe (16 lanes per clock per sub-partition) is shared by the four resident workers.  The test is
+// therefore decided in single precision whenever the two sides are further apart than that evaluation can be wrong:
+// x32 = diff / temp within 4e-7 relative (two conversions, __fdividef), __expf within 2 + 1.16 |x| ulp, and u is taken
+// from the top 24 bits of the draw, u in [ulo, ulo + 2^-24).  The margin (1 + |x|) * 4e-6 is more than four times the
+// sum of these.  Only the remaining cases (about one in 1e5) evaluate the f64 expression, so the decision is always the
+// one the f64 expression gives.
+__device__ __forceinline__ bool anneal_accept(uint64_t v, double diff, double temp) {
+    const float df = (float)diff, tf = (float)temp;
+    const bool sane = tf >= 1e-30f && tf <= 1e30f && df <= -1e-30f && df >= -1e30f;
+    if (sane) {
+        const float x = __fdividef(df, tf);                   // x <= 0; -inf when the quotient overflows
+        if (x <= -80.f) return (v >> 11) == 0;                // exp(...) < 2^-53: only u = 0 passes
+        const float e = __expf(x);
+        const float m = (1.f + fabsf(x)) * 4e-6f;
+        const float ulo = (float)(uint32_t)(v >> 40) * (1.f / 16777216.f);
+        if (ulo + (1.f / 16777216.f) <= e * (1.f - m)) return true;
+        if (ulo > e * (1.f + m)) return false;
+    }
+    return u64_to_unit_f64(v) <= exp(__ddiv_rn(diff, temp));
+}
+
+// SimAnneal::solve_nontrivial (src/solvers/stoch.rs:197-242).
 template <bool WIDE>
 __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab<WIDE> &S, const Instance &I,
                              const WarpShared &ws, Xo &rng) {
@@ -1475,65 +1636,53 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
     uint64_t curr_plato = 0, steps = 0;
     // phase 1: annealing, i = anneal_steps .. 1
     uint64_t i = P.anneal_steps;
-    while (i >= 1) {
-        Spec sp;
-        spec_targets<true>(ws, I, rng, sp);
-        if (sp.count == 0) {               // sequential step (refill / biased draw / end of the register window)
+    bool plateau = false;
+    Pend pd;
+    pd.idx = PEND_NONE; pd.tv = 0.0;
+    while (i >= 1 && !plateau) {
+        Look lk;
+        look_targets<true>(ws, I, rng, lk);
+        const unsigned okmask = wballot(lk.ok);
+        if (!(okmask & 1u)) {              // sequential step (refill / biased draw / end of the fill)
             const Target t = random_target(ws, I, rng);
             Move<WIDE> mv;
             const double diff = __dsub_rn(calc_improvement<WIDE>(L, S, I, ws, t.r, t.o, t.a, t.new_a, mv), min_diff);
             steps++;
             bool accept = diff >= 0.0;
-            if (!accept) {
-                const double u = xo_f64(rng);
-                accept = u <= exp(__ddiv_rn(diff, __dmul_rn(temp_step, (double)i)));
-            }
+            if (!accept) accept = anneal_accept(xo_next(rng), diff, __dmul_rn(temp_step, (double)i));
             i--;
             if (accept) { apply_move<WIDE>(ws, L.depth_table, t.r, t.new_a, mv); curr_plato = 0; }
             else { curr_plato += 1; if (curr_plato >= P.plato_size) break; }
             continue;
         }
-        const uint32_t limit = (uint32_t)min((uint64_t)sp.count, i);
         Move<WIDE> mv;
         mv.dld = mv.dlp = 0.0; mv.raw_old = mv.raw_new = 0;
-        bool acc = false, neg = false;
-        if (sp.usable && sp.rank < limit) {
-            const double diff = __dsub_rn(calc_improvement<WIDE>(L, S, I, ws, sp.r, sp.o, sp.a, sp.new_a, mv), min_diff);
-            neg = !(diff >= 0.0);
-            acc = !neg;
-            if (neg) {
-                const double u = u64_to_unit_f64(sp.udraw);
-                acc = u <= exp(__ddiv_rn(diff, __dmul_rn(temp_step, (double)(i - sp.rank))));
-            }
-        }
-        const unsigned accmask = wballot(acc);
-        const uint32_t first_acc = accmask ? (uint32_t)__popc(sp.umask & ((1u << (__ffs(accmask) - 1)) - 1u)) : 0xFFFFFFFFu;
-        const uint32_t n_rej = min(first_acc, limit);              // leading rejected steps available
-        // the plato_left-th reject from here breaks the loop (the check follows the increment, stoch.rs:219-222)
-        const uint64_t plato_left = P.plato_size > curr_plato ? P.plato_size - curr_plato : 1;
-        if ((uint64_t)n_rej >= plato_left) {
-            const uint32_t e = (uint32_t)plato_left;
-            rng.pos += spec_offset_after(sp, ws.lane, e, sp.nd + 1u);
-            steps += e; i -= e; curr_plato += e;
-            break;
-        }
-        steps += n_rej; i -= n_rej; curr_plato += n_rej;
-        if (first_acc < limit) {
-            const int src = __ffs(accmask) - 1;
-            // the accepted step consumed its U(0,1) only if its diff was negative (short-circuit, stoch.rs:216)
-            const uint32_t off_acc = wshfl(ws.lane + sp.nd + (neg ? 1u : 0u), src);
+        if (lk.ok) calc_static<WIDE>(L, S, I, ws, lk.r, lk.o, lk.a, lk.new_a, mv);
+        const unsigned twomask = wballot(lk.nd == 2u);
+        uint32_t q = 0;
+        while (q < 32u && ((okmask >> q) & 1u) && i >= 1) {
+            uint32_t r, new_a;
             Move<WIDE> w;
-            w.dld = wshfl(mv.dld, src); w.dlp = wshfl(mv.dlp, src);
-            w.raw_old = wshfl(mv.raw_old, src); w.raw_new = wshfl(mv.raw_new, src);
-            const uint32_t w_r = wshfl(sp.r, src), w_new = wshfl(sp.new_a, src);
-            rng.pos += off_acc;
-            apply_move<WIDE>(ws, L.depth_table, w_r, w_new, w);
-            steps++; i--; curr_plato = 0;
-        } else {
-            rng.pos += spec_offset_after(sp, ws.lane, n_rej, sp.nd + 1u);
+            if (!walk_fetch<WIDE>(ws, lk, mv, q, r, new_a, w, pd)) break;
+            const double diff = __dsub_rn(__dadd_rn(__dmul_rn(L.depth_contrib, w.dld), __dmul_rn(L.aln_contrib, w.dlp)), min_diff);
+            uint32_t len = 1u + ((twomask >> q) & 1u);
+            steps++;
+            bool accept = diff >= 0.0;
+            if (!accept) {                 // the U(0,1) is drawn only for a negative diff (short-circuit, stoch.rs:216)
+                len++;
+                accept = anneal_accept(wshfl(lk.udraw, (int)q), diff, __dmul_rn(temp_step, (double)i));
+            }
+            i--;
+            q += len;
+            if (accept) { apply_move_shift<WIDE>(ws, L.depth_table, r, new_a, w, pd); curr_plato = 0; }
+            else { curr_plato += 1; if (curr_plato >= P.plato_size) { plateau = true; break; } }
         }
+        pend_flush(ws, pd);
+        rng.pos += q;
     }
-    // phase 2: hill climbing until the plateau
+    // phase 2: hill climbing until the plateau.  Nearly every step is rejected here (a rejected step changes nothing but
+    // the plateau counter), so whole chains of steps are evaluated in parallel against the current state (spec_targets)
+    // and committed up to the first accepted one.
     uint64_t k = 0;
     while (k < P.max_iter && curr_plato < P.plato_size) {
         Spec sp;
