@@ -403,12 +403,15 @@ struct WarpShared {
     uint32_t *samp;        // [12] scratch of sample_resolve; [12..16) spare
     double *lik;           // [0] aln_lik, [1] depth_lik of the assignment being solved (lane 0 updates them: two fewer
                            //     64-bit values live in the solver loops), [2] = iterations of the genotype as u64
+    uint32_t steps_sa;     // annealing: shared-memory address of the 32 prepared step records (48 bytes each)
+    uint32_t p2_sa;        // shared-memory address of win.p(0, 2)
     uint32_t zero_row;     // offset of the all-zero row
     uint32_t depth_k;
     uint32_t lane;
 };
-__host__ __device__ inline size_t group_smem_bytes(uint32_t Wmax, uint32_t R, bool nt_global) {
-    return align_up((size_t)win_stride(Wmax) * 56, 16) +
+static constexpr size_t STEP_REC_BYTES = 48;
+__host__ __device__ inline size_t group_smem_bytes(uint32_t Wmax, uint32_t R, bool nt_global, bool anneal) {
+    return (anneal ? 32 * STEP_REC_BYTES : 0) + align_up((size_t)win_stride(Wmax) * 56, 16) +
            (nt_global ? 0 : align_up(((size_t)R + 1) * 2, 16) + align_up((size_t)R * 2, 16)) +
            align_up((size_t)R, 16) + align_up((size_t)((R + 31) / 32) * 4, 16) +
            align_up((size_t)(2 * LCTP_MAX_PLOIDY + 1) * 4, 16) + 64 /* samp */ + 32 /* lik */ + 1024 /* draw ring */;
@@ -876,8 +879,8 @@ __device__ __forceinline__ void spec_targets(const WarpShared &ws, const Instanc
     sp.usable = false; sp.rank = 0; sp.count = 0; sp.umask = 0u;
     sp.r = sp.o = sp.a = sp.new_a = 0; sp.nd = 1; sp.udraw = 0;
     if (rng.pos >= RNG_FILL) return;
-    stream_cover(rng, 1);
     const uint32_t avail = min(32u, RNG_FILL - rng.pos);
+    stream_cover(rng, avail);              // every position a lane peeks at is in the ring
     const uint64_t d = stream_peek64(rng, lane);
     const uint64_t d1 = __shfl_down_sync(FULL, d, 1), d2 = __shfl_down_sync(FULL, d, 2);
     const uint64_t m = (d >> 32) * (uint64_t)I.n_nt;
@@ -1473,18 +1476,17 @@ __device__ bool greedy_solve_big(const LocusDev &L, const StageParams &P, const 
 struct Look {
     bool ok;                     // the step at this lane's position needs no bias-correction draw and fits the fill
     uint32_t r, o, a, new_a;     // its target
-    uint32_t nd;                 // draws of the target (1 or 2)
-    uint64_t udraw;              // the draw after them
+    uint32_t nd;                 // draws of the target (1 or 2); the walk takes the U(0,1) after them from the ring
 };
 template <bool WITH_U>
 __device__ __forceinline__ void look_targets(const WarpShared &ws, const Instance &I, Xo &rng, Look &lk) {
     const uint32_t lane = ws.lane;
-    lk.ok = false; lk.r = lk.o = lk.a = lk.new_a = 0; lk.nd = 1; lk.udraw = 0;
+    lk.ok = false; lk.r = lk.o = lk.a = lk.new_a = 0; lk.nd = 1;
     if (rng.pos >= RNG_FILL) return;
-    stream_cover(rng, 1);
     const uint32_t avail = min(32u, RNG_FILL - rng.pos);
+    stream_cover(rng, avail);              // every position a lane (or the walk) peeks at is in the ring
     const uint64_t d = stream_peek64(rng, lane);
-    const uint64_t d1 = __shfl_down_sync(FULL, d, 1), d2 = __shfl_down_sync(FULL, d, 2);
+    const uint64_t d1 = __shfl_down_sync(FULL, d, 1);
     const uint64_t m = (d >> 32) * (uint64_t)I.n_nt;
     const bool bias1 = (uint32_t)m > 0u - I.n_nt;
     const uint2 inf = nt_info(ws, (uint32_t)(m >> 32));
@@ -1498,7 +1500,6 @@ __device__ __forceinline__ void look_targets(const WarpShared &ws, const Instanc
     const uint32_t i2 = 1u + (uint32_t)(m2 >> 32);
     lk.new_a = two ? (i2 <= lk.a ? i2 - 1u : i2) : 1u - lk.a;
     lk.nd = two ? 2u : 1u;
-    lk.udraw = two ? d2 : d1;
     lk.ok = lane + lk.nd + (WITH_U ? 1u : 0u) <= avail && !bias1 && !bias2;
 }
 
@@ -1541,28 +1542,85 @@ __device__ __forceinline__ void pend_flush(const WarpShared &ws, Pend &pd) {
     }
     __syncwarp();
 }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
+// Prepared step record (48 bytes in shared memory, one per look-ahead position, written by the lane of that position):
+//   addr[8]  shared-memory addresses of the eight slice entries of depth_lik_diff (assgn.rs:259-284), in the order
+//            p(w1, 2 + c1), p(w1, 2), p(w2, 2 + c2), p(w2, 2), ... -- the window merging (which of w1..w4 are equal, the
+//            net depth change c_j carried by the first occurrence) is static, so it is done once per record by the
+//            preparing lane instead of once per step by the whole warp; a merged-away window has c = 0: p - p = +0.0;
+//   dlp      aln-likelihood difference;   packed = read | old rank << 16 | new rank << 24;
+//   cpack    (c_j + 2) << 3 (j - 1), bit 12 = some |c_j| is 2.
 template <bool WIDE>
-__device__ __forceinline__ void apply_move_shift(const WarpShared &ws, const double *__restrict__ table, uint32_t r,
-                                                 uint32_t new_a, const Move<WIDE> &mv, Pend &pd) {
+__device__ __forceinline__ void step_record_store(const WarpShared &ws, const Look &lk, const Move<WIDE> &mv) {
     typedef RecWord<WIDE> RW;
     const uint32_t w1 = RW::w1(mv.raw_old), w2 = RW::w2(mv.raw_old), w3 = RW::w1(mv.raw_new), w4 = RW::w2(mv.raw_new);
-    pend_flush(ws, pd);
-    // net depth change of every distinct window, carried by its first occurrence (depth_lik_diff's c1..c4)
     const int e21 = w2 == w1, e31 = w3 == w1, e32 = (w3 == w2) & !e31;
     const int e41 = w4 == w1, e42 = (w4 == w2) & !e41, e43 = (w4 == w3) & !e41 & !e42;
     const int c1 = -1 - e21 + e31 + e41;
     const int c2 = e21 ? 0 : -1 + e32 + e42;
     const int c3 = (e31 | e32) ? 0 : 1 + e43;
     const int c4 = (e41 | e42 | e43) ? 0 : 1;
-    const int j = (int)ws.lane / 5, k = (int)ws.lane % 5;
-    const uint32_t w = j == 0 ? w1 : j == 1 ? w2 : j == 2 ? w3 : w4;
-    const int c = ws.lane >= 20u ? 0 : j == 0 ? c1 : j == 1 ? c2 : j == 2 ? c3 : c4;
+    const int stride = (int)(ws.win.wp * 8u);
+    const uint32_t b1 = ws.p2_sa + w1 * 8u, b2 = ws.p2_sa + w2 * 8u, b3 = ws.p2_sa + w3 * 8u, b4 = ws.p2_sa + w4 * 8u;
+    const uint32_t ra = ws.steps_sa + ws.lane * (uint32_t)STEP_REC_BYTES;
+    sts_v4(ra, make_uint4(b1 + (uint32_t)(c1 * stride), b1, b2 + (uint32_t)(c2 * stride), b2));
+    sts_v4(ra + 16u, make_uint4(b3 + (uint32_t)(c3 * stride), b3, b4 + (uint32_t)(c4 * stride), b4));
+    const uint32_t cpack = (uint32_t)(c1 + 2) | ((uint32_t)(c2 + 2) << 3) | ((uint32_t)(c3 + 2) << 6) |
+                           ((uint32_t)(c4 + 2) << 9) | (((c1 == -2) | (c3 == 2)) ? 1u << 12 : 0u);
+    const unsigned long long dl = (unsigned long long)__double_as_longlong(mv.dlp);
+    sts_v4(ra + 32u, make_uint4((uint32_t)dl, (uint32_t)(dl >> 32), lk.r | (lk.a << 16) | (lk.new_a << 24), cpack));
+}
+
+// The prepared step at walk position q, read by the whole warp (broadcast loads).
+struct Step { uint4 a0, a1; double dlp, dld; uint32_t r, new_a, cpack; };
+__device__ __forceinline__ bool walk_fetch(const WarpShared &ws, uint32_t q, Step &st, Pend &pd) {
+    const uint32_t ra = ws.steps_sa + q * (uint32_t)STEP_REC_BYTES;
+    const uint4 m = lds_v4(ra + 32u);
+    st.r = m.z & 0xFFFFu;
+    st.new_a = m.z >> 24;
+    if (ws.assgn[st.r] != ((m.z >> 16) & 0xFFu)) return false;        // reassigned since the look-ahead: stale
+    st.a0 = lds_v4(ra); st.a1 = lds_v4(ra + 16u);
+    st.cpack = m.w;
+    st.dlp = __longlong_as_double((long long)(((unsigned long long)m.y << 32) | m.x));
+    // a depth change of two reads an edge entry of the slices (see apply_step)
+    if (m.w & (1u << 12)) pend_flush(ws, pd);
+    double s = __dadd_rn(__dsub_rn(lds_f64(st.a0.x), lds_f64(st.a0.y)), __dsub_rn(lds_f64(st.a0.z), lds_f64(st.a0.w)));
+    s = __dadd_rn(s, __dsub_rn(lds_f64(st.a1.x), lds_f64(st.a1.y)));
+    st.dld = __dadd_rn(s, __dsub_rn(lds_f64(st.a1.z), lds_f64(st.a1.w)));
+    return true;
+}
+
+// reassign (src/model/assgn.rs:331-343) for a prepared step: slices shifted, edge entries deferred (see Pend).
+__device__ __forceinline__ void apply_step(const WarpShared &ws, const double *__restrict__ table, const Step &st, Pend &pd) {
+    pend_flush(ws, pd);
+    const uint32_t j = ws.lane / 5u;
+    const int k = (int)(ws.lane - 5u * j);
+    const uint32_t bj = j == 0 ? st.a0.y : j == 1 ? st.a0.w : j == 2 ? st.a1.y : st.a1.w;     // address of p(w_j, 2)
+    const int c = ws.lane >= 20u ? 0 : (int)((st.cpack >> (3u * j)) & 7u) - 2;
+    const int stride = (int)(ws.win.wp * 8u);
     const int src = k + c;
     const bool inside = src >= 0 && src <= 4;
     double v = 0.0;
     if (c != 0) {
-        if (inside) v = ws.win.p(w, src);
+        if (inside) v = lds_f64(bj + (uint32_t)((src - 2) * stride));
         else {
+            const uint32_t w = (bj - ws.p2_sa) >> 3;
             const int d = min(max((int)ws.win.depth(w) + c + k - 2, 0), (int)ws.depth_k - 1);
             pd.tv = __ldg(table + ws.win.row(w) + d);
             pd.idx = w | ((uint32_t)k << 24);
@@ -1570,35 +1628,20 @@ __device__ __forceinline__ void apply_move_shift(const WarpShared &ws, const dou
     }
     __syncwarp();                                      // every old slice entry has been read
     if (ws.lane == 0) {
+        const uint32_t w1 = (st.a0.y - ws.p2_sa) >> 3, w2 = (st.a0.w - ws.p2_sa) >> 3;
+        const uint32_t w3 = (st.a1.y - ws.p2_sa) >> 3, w4 = (st.a1.w - ws.p2_sa) >> 3;
         ws.win.depth(w3) += 1;
         ws.win.depth(w4) += 1;
         ws.win.depth(w1) -= 1;
         ws.win.depth(w2) -= 1;
-        ws.assgn[r] = (uint8_t)new_a;
-        ws.lik[1] = __dadd_rn(ws.lik[1], mv.dld);       // depth_lik += ..., aln_lik += ... (assgn.rs:336-337)
-        ws.lik[0] = __dadd_rn(ws.lik[0], mv.dlp);
+        ws.assgn[st.r] = (uint8_t)st.new_a;
+        ws.lik[1] = __dadd_rn(ws.lik[1], st.dld);       // depth_lik += ..., aln_lik += ... (assgn.rs:336-337)
+        ws.lik[0] = __dadd_rn(ws.lik[0], st.dlp);
     }
-    if (c != 0 && inside) ws.win.p(w, k) = v;
+    if (c != 0 && inside) sts_f64(bj + (uint32_t)((k - 2) * stride), v);
     // a change of +-2 leaves an entry next to the centre pending, and those are read by ordinary steps
-    if ((c1 == -2) | (c3 == 2)) pend_flush(ws, pd);    // (c2 and c4 stay within -1..1)
+    if (st.cpack & (1u << 12)) pend_flush(ws, pd);
     else __syncwarp();
-}
-
-// One prepared step at walk position q (warp-uniform): target and move broadcast from lane q; false = stale.
-template <bool WIDE>
-__device__ __forceinline__ bool walk_fetch(const WarpShared &ws, const Look &lk, const Move<WIDE> &mv, uint32_t q,
-                                           uint32_t &r, uint32_t &new_a, Move<WIDE> &w, Pend &pd) {
-    typedef RecWord<WIDE> RW;
-    const uint32_t packed = wshfl(lk.r | (lk.a << 16) | (lk.new_a << 24), (int)q);
-    r = packed & 0xFFFFu;
-    new_a = packed >> 24;
-    if (ws.assgn[r] != ((packed >> 16) & 0xFFu)) return false;
-    w.raw_old = wshfl(mv.raw_old, (int)q); w.raw_new = wshfl(mv.raw_new, (int)q);
-    w.dlp = wshfl(mv.dlp, (int)q);
-    // a location with both windows equal changes a depth by two: that reads an edge entry (see apply_move_shift)
-    if ((RW::w1(w.raw_old) == RW::w2(w.raw_old)) | (RW::w1(w.raw_new) == RW::w2(w.raw_new))) pend_flush(ws, pd);
-    w.dld = depth_lik_diff_raw<WIDE>(ws, w.raw_old, w.raw_new);
-    return true;
 }
 
 // The acceptance test of a step with a negative diff, `rng.random::<f64>() <= (diff / temp).exp()` (stoch.rs:216), v = the
@@ -1655,26 +1698,28 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
             else { curr_plato += 1; if (curr_plato >= P.plato_size) break; }
             continue;
         }
-        Move<WIDE> mv;
-        mv.dld = mv.dlp = 0.0; mv.raw_old = mv.raw_new = 0;
-        if (lk.ok) calc_static<WIDE>(L, S, I, ws, lk.r, lk.o, lk.a, lk.new_a, mv);
+        if (lk.ok) {
+            Move<WIDE> mv;
+            calc_static<WIDE>(L, S, I, ws, lk.r, lk.o, lk.a, lk.new_a, mv);
+            step_record_store<WIDE>(ws, lk, mv);
+        }
         const unsigned twomask = wballot(lk.nd == 2u);
+        __syncwarp();
         uint32_t q = 0;
         while (q < 32u && ((okmask >> q) & 1u) && i >= 1) {
-            uint32_t r, new_a;
-            Move<WIDE> w;
-            if (!walk_fetch<WIDE>(ws, lk, mv, q, r, new_a, w, pd)) break;
-            const double diff = __dsub_rn(__dadd_rn(__dmul_rn(L.depth_contrib, w.dld), __dmul_rn(L.aln_contrib, w.dlp)), min_diff);
+            Step st;
+            if (!walk_fetch(ws, q, st, pd)) break;
+            const double diff = __dsub_rn(__dadd_rn(__dmul_rn(L.depth_contrib, st.dld), __dmul_rn(L.aln_contrib, st.dlp)), min_diff);
             uint32_t len = 1u + ((twomask >> q) & 1u);
             steps++;
             bool accept = diff >= 0.0;
             if (!accept) {                 // the U(0,1) is drawn only for a negative diff (short-circuit, stoch.rs:216)
+                accept = anneal_accept(stream_peek64(rng, q + len), diff, __dmul_rn(temp_step, (double)i));
                 len++;
-                accept = anneal_accept(wshfl(lk.udraw, (int)q), diff, __dmul_rn(temp_step, (double)i));
             }
             i--;
             q += len;
-            if (accept) { apply_move_shift<WIDE>(ws, L.depth_table, r, new_a, w, pd); curr_plato = 0; }
+            if (accept) { apply_step(ws, L.depth_table, st, pd); curr_plato = 0; }
             else { curr_plato += 1; if (curr_plato >= P.plato_size) { plateau = true; break; } }
         }
         pend_flush(ws, pd);
@@ -1763,7 +1808,10 @@ k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs
         rng.ring = (uint64_t *)base;           base += 1024;
         ws.samp = (uint32_t *)base;            base += 64;
         ws.lik = (double *)base;               base += 32;
+        ws.steps_sa = (uint32_t)__cvta_generic_to_shared(base);
+        if (MODE == 2) base += 32 * STEP_REC_BYTES;
         ws.win.base = (double *)base;          ws.win.wp = win_stride(P.Wmax);
+        ws.p2_sa = (uint32_t)__cvta_generic_to_shared(ws.win.base + 2u * ws.win.wp);
         base += align_up((size_t)ws.win.wp * 56, 16);
         if (P.nt_global) {
             ws.off = S.off;
@@ -1975,7 +2023,7 @@ static int launch_stage_kernel(lctp_locus_h *h, const StageParams &P, size_t n_w
     lctp_ctx *ctx = h->ctx;
     cudaStream_t s = ctx->stream;
     const LocusDev &L = h->dev;
-    const size_t smem = group_smem_bytes(P.Wmax, L.R, P.nt_global != 0);
+    const size_t smem = group_smem_bytes(P.Wmax, L.R, P.nt_global != 0, P.kind == 1);
     if (smem > ctx->smem_optin) {
         set_error("lctp_solve_stage: %zu bytes of shared memory per worker needed (R=%u reads, %u windows); "
                   "loci this large are not supported by the shared-memory resident solver", smem, L.R, P.Wmax);
@@ -2124,7 +2172,7 @@ int launch_stage_ex(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worke
     // at the KIR-scale shape 8 workers per SM instead of 4.  The greedy loop fetches its entries a round ahead.
     {
         const size_t per_sm = ctx->smem_optin + 1024;            // opt-in limit per CTA = SM capacity - 1 KB
-        const size_t with_nt = group_smem_bytes(P.Wmax, L.R, false) + 1024;
+        const size_t with_nt = group_smem_bytes(P.Wmax, L.R, false, st->kind == 1) + 1024;
         (void)per_sm; (void)with_nt;
         P.nt_global = 1;   // measured at the C2 shape too: 16 workers per SM instead of 14, stage kernel 10.8 -> 10.1 ms
         if (const char *e = getenv("LCTP_NT_GLOBAL")) P.nt_global = atoi(e) ? 1 : 0;      // test / tuning knob
