@@ -201,6 +201,9 @@ typedef struct lctp_mates {
      * value once more); NULL = no explicit weights (weight 1) */
     const uint64_t *exp_off;       /* [H+1] */
     const double   *exp_weight;
+    /* per-read limit instead of max_alns: MAX_USED_ALNS (10) for reads with weight >= Params::min_weight, MAX_UNUSED_ALNS
+     * (2) for the others (recover_and_group_alignments, src/model/locs.rs:739-742, 1263); NULL = max_alns for every read */
+    const uint8_t  *read_max_alns; /* [R], each 1..=16 */
 } lctp_mates;
 
 /* ---- library / context -------------------------------------------------------------------- */
@@ -291,6 +294,52 @@ int  lctp_collect_read_ends(lctp_ctx *ctx, const lctp_read_ends *in, double *ln_
                             uint32_t *read_len, uint8_t *ok, uint32_t *best_edit, double *weight_factor,
                             uint32_t *thr_dist, uint32_t *pass_dist, uint32_t *n_kept, uint32_t *kept_rec);
 size_t lctp_sizeof_read_ends(void);
+
+/* SURVEY 8(f) rank 1, remainder: from the per read-end results to the pairing input, for every read of a locus at once.
+ * AllAlignments::load after read_next_alns (src/model/locs.rs:1117-1137): a read is well mapped when read_next_alns
+ * returned true for its read ends (the second end is only read when the first was fine), and in bounds when some
+ * alignment of PrelimAlignments::alns has its middle outside the boundary regions (in_bounds, :1008-1014).  Then
+ * recover_and_group_alignments (:1237-1288) WITHOUT the alignment transfer (opt_hap_alns = None; the transfer needs
+ * WFA2, an un-vendored submodule): best_edit_is_good (:293-295), normalize_probs (:358-360: ln_prob -= the best
+ * ln_prob over every pushed alignment of the read end), max_alns = 10 / 2 by the read weight (:1263), and the order in
+ * which identify_paired_end_alignments / identify_single_end_alignments consume the alignments after their sorts
+ * (:819-820, 883): contig ascending, first read end before second, ln_prob descending.  The reference's sorts are
+ * unstable; equal keys keep the order of PrelimAlignments::alns here. */
+typedef struct lctp_prelim {
+    uint64_t n_reads, n_groups;
+    const int64_t  *read_group;        /* [n_reads][2] group (of the lctp_collect_read_ends call) of the first / second
+                                          read end, -1 = none (unmapped / not read; single-end: second always -1) */
+    const uint64_t *grp_off;           /* [n_groups+1] records of a group, as in lctp_read_ends */
+    const uint32_t *rec_contig;        /* [n_alns] */
+    const uint32_t *rec_start;         /* [n_alns] Interval::start */
+    const uint32_t *rec_end;           /* [n_alns] Interval::end (exclusive) */
+    const uint8_t  *rec_strand;        /* [n_alns] 1 = reverse */
+    const double   *rec_ln_prob;       /* [n_alns] ln_prob output of lctp_collect_read_ends */
+    const uint8_t  *grp_ok;            /* [n_groups] outputs of lctp_collect_read_ends: ok, */
+    const uint32_t *grp_best_edit;     /*   best_edit, */
+    const uint32_t *grp_thr_dist;      /*   thr_dist (= PrelimAlignments::good_dist after set_thresholds), */
+    const uint32_t *grp_n_kept;        /*   n_kept, */
+    const uint32_t *kept_rec;          /*   kept_rec [n_alns] */
+    const uint32_t *contig_len;        /* [n_haps] */
+    const double   *read_weight;       /* [n_reads] ReadData::weight after calculate_read_weight (:1144-1148) */
+    double min_weight;                 /* Params::min_weight */
+    uint32_t n_haps;
+    uint32_t boundary;                 /* params.boundary_size - params.tweak (:1099) */
+    uint32_t single_end;
+    uint32_t _pad;
+} lctp_prelim;
+/* Outputs, caller-allocated.  status[n_reads]: 0 = goes on to the pairing, 1 = not well mapped (ReadCounts::
+ * poorly_mapped of load), 2 = out of bounds, 3 = best edit distance not good (poorly_mapped of
+ * recover_and_group_alignments).  The reads with status 0 are numbered 0 .. *n_reads_out in read order: out_read[k] =
+ * the read, out_max_alns[k] = its max_alns (lctp_mates::read_max_alns), ma_off[k] .. ma_off[k+1] = its entries of
+ * ma_contig / ma_flags / ma_start / ma_end / ma_ln_prob (the lctp_mates arrays of the same names; `cap` entries each)
+ * and ma_rec (the record each entry came from).  counts[3] = poorly mapped (status 1 and 3), out of bounds, passed.
+ * LCTP_E_CAPACITY when cap is too small (the number of kept records always suffices). */
+int  lctp_group_reads(lctp_ctx *ctx, const lctp_prelim *in, uint64_t cap, uint8_t *status, uint64_t *n_reads_out,
+                      uint32_t *out_read, uint8_t *out_max_alns, uint64_t *ma_off, uint32_t *ma_contig,
+                      uint8_t *ma_flags, uint32_t *ma_start, uint32_t *ma_end, double *ma_ln_prob, uint32_t *ma_rec,
+                      uint64_t *counts);
+size_t lctp_sizeof_prelim(void);
 
 /* ---- SURVEY 8(f) rank 3, first slice: short-read recruitment ---------------------------------------------------------
  * Canonical minimizers (kmers::minimizers::<u64, _, CANONICAL>, src/seq/kmers.rs:71-103, 256-340) of n sequences

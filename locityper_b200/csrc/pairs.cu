@@ -31,6 +31,7 @@ struct MatesDev {
     const uint32_t *ma_contig, *ma_start, *ma_end;
     const uint8_t *ma_flags;
     const double *ma_ln_prob, *read_weight, *ins_ln_pmf;
+    const uint8_t *read_max;         // [R] per-read max_alns, or nullptr
     const uint64_t *exp_off;         // [H+1] explicit region weights per contig position, or nullptr
     const double *exp_weight;
     double unmapped_penalty, insert_penalty, prob_diff;
@@ -104,7 +105,7 @@ k_pair_groups(MatesDev D, const uint32_t *__restrict__ group_start, const uint32
     uint64_t f = i;
     while (f < e && (D.ma_flags[f] & 1u) == 0) f++;
     for (uint64_t q = f; q < e; q++) if ((D.ma_flags[q] & 1u) == 0) atomicOr(err, 2);   // first end before second
-    const uint32_t M = D.max_alns;
+    const uint32_t M = D.read_max ? D.read_max[r] : D.max_alns;
     if (D.single_end) {
         // identify_single_end_alignments (locs.rs:870-911): the records of the contig in descending ln_prob; the best
         // one sets the threshold, at most max_alns within prob_diff of it are kept as "first mate only" pairs.
@@ -274,6 +275,12 @@ int pair_alignments_dev(lctp_ctx *ctx, const lctp_mates *in, lctp_pairs_h *P) {
     cudaStream_t s = ctx->stream;
     const uint32_t R = in->n_reads;
     if (R == 0 || !in->ma_off) { set_error("lctp_pair_alignments: no reads"); return LCTP_E_INVALID; }
+    if (in->read_max_alns)
+        for (uint32_t r = 0; r < in->n_reads; r++)
+            if (in->read_max_alns[r] == 0 || in->read_max_alns[r] > PAIR_MAX_ALNS) {
+                set_error("lctp_pair_alignments: read_max_alns[%u] = %u unsupported (1..=%d)", r, in->read_max_alns[r], PAIR_MAX_ALNS);
+                return LCTP_E_INVALID;
+            }
     if (in->max_alns == 0 || in->max_alns > (uint32_t)PAIR_MAX_ALNS) {
         set_error("lctp_pair_alignments: max_alns %u unsupported (1..=%d)", in->max_alns, PAIR_MAX_ALNS);
         return LCTP_E_CAPACITY;
@@ -286,7 +293,7 @@ int pair_alignments_dev(lctp_ctx *ctx, const lctp_mates *in, lctp_pairs_h *P) {
     const uint64_t N = in->ma_off[R];
     DevBuf<uint64_t> d_off, d_offs, d_exp_off;
     DevBuf<uint32_t> d_contig, d_start, d_end, d_counts, d_head, d_gidx, d_gstart;
-    DevBuf<uint8_t> d_flags;
+    DevBuf<uint8_t> d_flags, d_rmax;
     DevBuf<double> d_lp, d_w, d_ins, d_exp;
     DevBuf<int> d_err;
     DevBuf<unsigned char> d_tmp;
@@ -301,6 +308,7 @@ int pair_alignments_dev(lctp_ctx *ctx, const lctp_mates *in, lctp_pairs_h *P) {
     if ((rc = to_dev(d_lp, in->ma_ln_prob, N, s))) return rc;
     h2d += ((size_t)R + 1) * 8 + N * (4 + 4 + 4 + 1 + 8);
     if (in->read_weight) { if ((rc = to_dev(d_w, in->read_weight, R, s))) return rc; h2d += (uint64_t)R * 8; }
+    if (in->read_max_alns) { if ((rc = to_dev(d_rmax, in->read_max_alns, R, s))) return rc; h2d += (uint64_t)R; }
     if (!in->single_end) { if ((rc = to_dev(d_ins, in->ins_ln_pmf, in->ins_len, s))) return rc; h2d += (uint64_t)in->ins_len * 8; }
     if (in->exp_weight) {
         const uint64_t tot = in->exp_off[in->n_haps];
@@ -326,6 +334,7 @@ int pair_alignments_dev(lctp_ctx *ctx, const lctp_mates *in, lctp_pairs_h *P) {
     D.ma_off = d_off.p; D.ma_contig = d_contig.p; D.ma_start = d_start.p; D.ma_end = d_end.p;
     D.ma_flags = d_flags.p; D.ma_ln_prob = d_lp.p; D.read_weight = in->read_weight ? d_w.p : nullptr;
     D.ins_ln_pmf = d_ins.p;
+    D.read_max = in->read_max_alns ? d_rmax.p : nullptr;
     D.exp_off = in->exp_weight ? d_exp_off.p : nullptr; D.exp_weight = in->exp_weight ? d_exp.p : nullptr;
     D.unmapped_penalty = in->unmapped_penalty; D.insert_penalty = in->insert_penalty; D.prob_diff = in->prob_diff;
 

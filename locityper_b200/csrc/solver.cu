@@ -1592,17 +1592,21 @@ struct Step { uint4 a0, a1; double dlp, dld; uint32_t r, new_a, cpack; };
 __device__ __forceinline__ bool walk_fetch(const WarpShared &ws, uint32_t q, Step &st, Pend &pd) {
     const uint32_t ra = ws.steps_sa + q * (uint32_t)STEP_REC_BYTES;
     const uint4 m = lds_v4(ra + 32u);
+    st.a0 = lds_v4(ra); st.a1 = lds_v4(ra + 16u);      // the three loads of the record are in flight together
     st.r = m.z & 0xFFFFu;
     st.new_a = m.z >> 24;
-    if (ws.assgn[st.r] != ((m.z >> 16) & 0xFFu)) return false;        // reassigned since the look-ahead: stale
-    st.a0 = lds_v4(ra); st.a1 = lds_v4(ra + 16u);
     st.cpack = m.w;
     st.dlp = __longlong_as_double((long long)(((unsigned long long)m.y << 32) | m.x));
+    const uint32_t cur = ws.assgn[st.r];
     // a depth change of two reads an edge entry of the slices (see apply_step)
     if (m.w & (1u << 12)) pend_flush(ws, pd);
-    double s = __dadd_rn(__dsub_rn(lds_f64(st.a0.x), lds_f64(st.a0.y)), __dsub_rn(lds_f64(st.a0.z), lds_f64(st.a0.w)));
-    s = __dadd_rn(s, __dsub_rn(lds_f64(st.a1.x), lds_f64(st.a1.y)));
-    st.dld = __dadd_rn(s, __dsub_rn(lds_f64(st.a1.z), lds_f64(st.a1.w)));
+    // the eight slice entries are read next to the assignment check, not behind it (a stale step wastes them)
+    const double p1 = lds_f64(st.a0.x), q1 = lds_f64(st.a0.y), p2 = lds_f64(st.a0.z), q2 = lds_f64(st.a0.w);
+    const double p3 = lds_f64(st.a1.x), q3 = lds_f64(st.a1.y), p4 = lds_f64(st.a1.z), q4 = lds_f64(st.a1.w);
+    if (cur != ((m.z >> 16) & 0xFFu)) return false;        // reassigned since the look-ahead: stale
+    double s = __dadd_rn(__dsub_rn(p1, q1), __dsub_rn(p2, q2));
+    s = __dadd_rn(s, __dsub_rn(p3, q3));
+    st.dld = __dadd_rn(s, __dsub_rn(p4, q4));
     return true;
 }
 
@@ -1626,18 +1630,16 @@ __device__ __forceinline__ void apply_step(const WarpShared &ws, const double *_
             pd.idx = w | ((uint32_t)k << 24);
         }
     }
-    __syncwarp();                                      // every old slice entry has been read
-    if (ws.lane == 0) {
-        const uint32_t w1 = (st.a0.y - ws.p2_sa) >> 3, w2 = (st.a0.w - ws.p2_sa) >> 3;
-        const uint32_t w3 = (st.a1.y - ws.p2_sa) >> 3, w4 = (st.a1.w - ws.p2_sa) >> 3;
-        ws.win.depth(w3) += 1;
-        ws.win.depth(w4) += 1;
-        ws.win.depth(w1) -= 1;
-        ws.win.depth(w2) -= 1;
-        ws.assgn[st.r] = (uint8_t)st.new_a;
-        ws.lik[1] = __dadd_rn(ws.lik[1], st.dld);       // depth_lik += ..., aln_lik += ... (assgn.rs:336-337)
-        ws.lik[0] = __dadd_rn(ws.lik[0], st.dlp);
+    __syncwarp();                                      // every old slice entry and depth has been read
+    // depth[w] += c for the first occurrence of every distinct window (the lane with k = 0 of its group of five; the
+    // net changes of merged windows are what the four +-1 updates of reassign add up to); lanes 20 / 21 add the two
+    // likelihood differences, lane 22 stores the assignment
+    if (c != 0 && k == 0) ws.win.depth((bj - ws.p2_sa) >> 3) += c;
+    if (ws.lane == 20u || ws.lane == 21u) {            // depth_lik += ..., aln_lik += ... (assgn.rs:336-337)
+        const uint32_t which = 21u - ws.lane;          // lik[1] = depth_lik (lane 20), lik[0] = aln_lik (lane 21)
+        ws.lik[which] = __dadd_rn(ws.lik[which], which ? st.dld : st.dlp);
     }
+    if (ws.lane == 22u) ws.assgn[st.r] = (uint8_t)st.new_a;
     if (c != 0 && inside) sts_f64(bj + (uint32_t)((k - 2) * stride), v);
     // a change of +-2 leaves an entry next to the centre pending, and those are read by ordinary steps
     if (st.cpack & (1u << 12)) pend_flush(ws, pd);
@@ -1783,11 +1785,16 @@ __device__ void anneal_solve(const LocusDev &L, const StageParams &P, const Slab
 #ifndef LCTP_MIN_CTAS
 #define LCTP_MIN_CTAS 16
 #endif
+#ifndef LCTP_ANNEAL_CTAS_DEFAULT
+#define LCTP_ANNEAL_CTAS_DEFAULT 24
+#endif
 // MODE: 0 = greedy (samples of <= 11 reads), 1 = greedy with larger samples, 2 = simulated annealing.  One kernel per
 // solver: the code of the others is not in the instruction stream (the single kernel was 364 KB of SASS and lost
 // 10 % of its cycles to instruction-cache misses with 16 workers per SM in different phases).
-template <bool WIDE, int MODE>
-__global__ void __launch_bounds__(CTA_THREADS, LCTP_MIN_CTAS)
+// NCTA: resident workers per SM the registers are capped for (annealing is instantiated for more than one value: its
+// walk needs fewer registers than the greedy pipeline, and more resident chains hide more of its latency).
+template <bool WIDE, int MODE, int NCTA = LCTP_MIN_CTAS>
+__global__ void __launch_bounds__(CTA_THREADS, NCTA)
 k_solve_stage(LocusDev L, StageParams P, const uint64_t *__restrict__ worker_ixs,
               const uint64_t *__restrict__ worker_off, const uint32_t *__restrict__ tuples,
               uint64_t *__restrict__ rng_states, double *__restrict__ lik_mean, double *__restrict__ lik_var,
@@ -2031,15 +2038,24 @@ static int launch_stage_kernel(lctp_locus_h *h, const StageParams &P, size_t n_w
     }
     const bool bigs = P.kind == 0 && P.sample_size > (uint32_t)MAX_SAMPLE;
     const int mode = P.kind == 1 ? 2 : bigs ? 1 : 0;
-    auto kern = P.narrow_w ? (mode == 2 ? k_solve_stage<false, 2> : mode == 1 ? k_solve_stage<false, 1> : k_solve_stage<false, 0>)
-                           : (mode == 2 ? k_solve_stage<true, 2> : mode == 1 ? k_solve_stage<true, 1> : k_solve_stage<true, 0>);
+    // annealing: register cap for 16 / 20 / 24 / 28 / 32 resident workers per SM (LCTP_ANNEAL_CTAS, tuning knob; C3 stage
+    // launch 915 / 755 / 733 ms at 16 / 20 / 24: the walk is a dependent chain, resident chains are what hides it)
+    const int acta = env_int("LCTP_ANNEAL_CTAS", LCTP_ANNEAL_CTAS_DEFAULT);
+    const int variant = mode != 2 ? 0 : acta >= 32 ? 4 : acta >= 28 ? 3 : acta >= 24 ? 2 : acta >= 20 ? 1 : 0;
+    typedef decltype(&k_solve_stage<false, 0>) KernT;
+    static const KernT anneal_kerns[2][5] = {
+        {k_solve_stage<false, 2, 16>, k_solve_stage<false, 2, 20>, k_solve_stage<false, 2, 24>, k_solve_stage<false, 2, 28>, k_solve_stage<false, 2, 32>},
+        {k_solve_stage<true, 2, 16>, k_solve_stage<true, 2, 20>, k_solve_stage<true, 2, 24>, k_solve_stage<true, 2, 28>, k_solve_stage<true, 2, 32>}};
+    KernT kern = mode == 2 ? anneal_kerns[P.narrow_w ? 0 : 1][variant]
+                           : P.narrow_w ? (mode == 1 ? k_solve_stage<false, 1> : k_solve_stage<false, 0>)
+                                        : (mode == 1 ? k_solve_stage<true, 1> : k_solve_stage<true, 0>);
     // function attributes are per-device state shared by every context: configure + launch under one lock
     static std::mutex launch_mutex;
     std::lock_guard<std::mutex> lock(launch_mutex);
     // Only raise the limit when needed: re-setting a function attribute makes the next launch of the function wait
     // for its running instances, which serialised the stage kernels of loci in flight on different contexts.
     static std::unordered_map<int, size_t> smem_limit;     // by device ordinal and kernel instantiation
-    size_t &lim = smem_limit[ctx->device * 8 + (P.narrow_w ? 1 : 0) + mode * 2];
+    size_t &lim = smem_limit[ctx->device * 32 + (P.narrow_w ? 1 : 0) + mode * 2 + variant * 6];
     if (smem > 48 * 1024 && smem > lim) {
         LCTP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lim = smem;

@@ -99,7 +99,17 @@ class MatesC(C.Structure):
                 ("ma_end", C.c_void_p), ("ma_ln_prob", C.c_void_p), ("read_weight", C.c_void_p),
                 ("ins_ln_pmf", C.c_void_p),
                 ("unmapped_penalty", C.c_double), ("insert_penalty", C.c_double), ("prob_diff", C.c_double),
-                ("single_end", C.c_uint32), ("window", C.c_uint32), ("exp_off", C.c_void_p), ("exp_weight", C.c_void_p)]
+                ("single_end", C.c_uint32), ("window", C.c_uint32), ("exp_off", C.c_void_p), ("exp_weight", C.c_void_p),
+                ("read_max_alns", C.c_void_p)]
+
+
+class PrelimC(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_groups", C.c_uint64), ("read_group", C.c_void_p), ("grp_off", C.c_void_p),
+                ("rec_contig", C.c_void_p), ("rec_start", C.c_void_p), ("rec_end", C.c_void_p), ("rec_strand", C.c_void_p),
+                ("rec_ln_prob", C.c_void_p), ("grp_ok", C.c_void_p), ("grp_best_edit", C.c_void_p),
+                ("grp_thr_dist", C.c_void_p), ("grp_n_kept", C.c_void_p), ("kept_rec", C.c_void_p),
+                ("contig_len", C.c_void_p), ("read_weight", C.c_void_p), ("min_weight", C.c_double),
+                ("n_haps", C.c_uint32), ("boundary", C.c_uint32), ("single_end", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class AlnsC(C.Structure):
@@ -163,6 +173,8 @@ SYMBOLS = {
     "lctp_sizeof_reads": (C.c_size_t, []),
     "lctp_sizeof_read_ends": (C.c_size_t, []),
     "lctp_collect_read_ends": (C.c_int, [_P] * 12),
+    "lctp_sizeof_prelim": (C.c_size_t, []),
+    "lctp_group_reads": (C.c_int, [_P, _P, C.c_uint64] + [_P] * 12),
     "lctp_locus_upload": (C.c_int, [_P, _P, _P]),
     "lctp_locus_free": (None, [_P]),
     "lctp_best_aln_matrix": (C.c_int, [_P, _P]),
@@ -229,6 +241,7 @@ def load():
         assert lib.lctp_sizeof_mates() == C.sizeof(MatesC)
         assert lib.lctp_sizeof_alns() == C.sizeof(AlnsC)
         assert lib.lctp_sizeof_read_ends() == C.sizeof(ReadEndsC)
+        assert lib.lctp_sizeof_prelim() == C.sizeof(PrelimC)
         assert lib.lctp_sizeof_target_seqs() == C.sizeof(TargetSeqsC) and lib.lctp_sizeof_reads() == C.sizeof(ReadsC)
         _lib = lib
     return _lib

@@ -278,6 +278,7 @@ class Mates:
     window: int = 0                               # window size, with explicit weights
     exp_off: Optional[np.ndarray] = None          # u64[H+1]: explicit region weights per contig position
     exp_weight: Optional[np.ndarray] = None       # f64 (contig_len + 1 entries per contig)
+    read_max_alns: Optional[np.ndarray] = None    # u8[R]: per-read max_alns (10 / 2 by read weight, locs.rs:1263)
 
     def to_c(self, keep: list, struct=None):
         def arr(a, dt):
@@ -300,6 +301,7 @@ class Mates:
         m.single_end, m.window = int(self.single_end), int(self.window)
         m.exp_off = arr(self.exp_off, np.uint64)
         m.exp_weight = arr(self.exp_weight, np.float64)
+        m.read_max_alns = arr(self.read_max_alns, np.uint8)
         return m
 
 
@@ -570,6 +572,84 @@ def collect_read_ends(ctx: "Context", re_: ReadEnds) -> dict:
     out = _read_ends_outputs(re_)
     ffi.check(ctx.lib.lctp_collect_read_ends(ctx._h, C.byref(c), *[out[k].ctypes.data for k in READ_ENDS_OUT_ORDER]))
     return out
+
+
+@dataclass
+class Prelim:
+    """Input of lctp_group_reads: the records and outputs of lctp_collect_read_ends plus, per read, its two groups
+    (AllAlignments::load after read_next_alns + recover_and_group_alignments without the transfer,
+    src/model/locs.rs:1117-1137, 1237-1288)."""
+
+    read_group: np.ndarray          # i64[n_reads, 2], -1 = none
+    grp_off: np.ndarray             # u64[n_groups + 1]
+    rec_contig: np.ndarray
+    rec_start: np.ndarray
+    rec_end: np.ndarray
+    rec_strand: np.ndarray          # u8, 1 = reverse
+    rec_ln_prob: np.ndarray
+    grp_ok: np.ndarray
+    grp_best_edit: np.ndarray
+    grp_thr_dist: np.ndarray
+    grp_n_kept: np.ndarray
+    kept_rec: np.ndarray
+    contig_len: np.ndarray
+    read_weight: np.ndarray
+    min_weight: float
+    boundary: int
+    single_end: bool = False
+
+    @property
+    def n_reads(self) -> int:
+        return len(self.read_group)
+
+    def to_c(self, keep: list, struct=None):
+        def arr(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data
+        c = (struct or ffi.PrelimC)()
+        c.n_reads, c.n_groups = self.n_reads, len(self.grp_off) - 1
+        c.read_group = arr(self.read_group, np.int64)
+        c.grp_off = arr(self.grp_off, np.uint64)
+        c.rec_contig, c.rec_start, c.rec_end = (arr(a, np.uint32) for a in (self.rec_contig, self.rec_start, self.rec_end))
+        c.rec_strand = arr(self.rec_strand, np.uint8)
+        c.rec_ln_prob = arr(self.rec_ln_prob, np.float64)
+        c.grp_ok = arr(self.grp_ok, np.uint8)
+        c.grp_best_edit, c.grp_thr_dist, c.grp_n_kept, c.kept_rec, c.contig_len = (
+            arr(a, np.uint32) for a in (self.grp_best_edit, self.grp_thr_dist, self.grp_n_kept, self.kept_rec, self.contig_len))
+        c.read_weight = arr(self.read_weight, np.float64)
+        c.min_weight, c.n_haps, c.boundary, c.single_end = self.min_weight, len(self.contig_len), self.boundary, int(self.single_end)
+        return c
+
+    def alloc_outputs(self) -> dict:
+        R, n = self.n_reads, max(1, len(self.rec_contig))
+        return dict(status=np.zeros(max(1, R), dtype=np.uint8), out_read=np.zeros(max(1, R), dtype=np.uint32),
+                    out_max_alns=np.zeros(max(1, R), dtype=np.uint8), ma_off=np.zeros(R + 1, dtype=np.uint64),
+                    ma_contig=np.zeros(n, dtype=np.uint32), ma_flags=np.zeros(n, dtype=np.uint8),
+                    ma_start=np.zeros(n, dtype=np.uint32), ma_end=np.zeros(n, dtype=np.uint32),
+                    ma_ln_prob=np.zeros(n), ma_rec=np.zeros(n, dtype=np.uint32), counts=np.zeros(3, dtype=np.uint64))
+
+    def trim_outputs(self, out: dict, n_out: int) -> dict:
+        n = int(out["ma_off"][n_out]) if n_out else 0
+        res = dict(status=out["status"][:self.n_reads].copy(), n_reads_out=n_out, counts=out["counts"].copy(),
+                   out_read=out["out_read"][:n_out].copy(), out_max_alns=out["out_max_alns"][:n_out].copy(),
+                   ma_off=out["ma_off"][:n_out + 1].copy())
+        for k in ("ma_contig", "ma_flags", "ma_start", "ma_end", "ma_ln_prob", "ma_rec"):
+            res[k] = out[k][:n].copy()
+        return res
+
+
+def group_reads(ctx: "Context", pre: Prelim) -> dict:
+    """lctp_group_reads: read status, normalised ln-probabilities and the pairing input in consumption order."""
+    keep: list = []
+    c = pre.to_c(keep)
+    out = pre.alloc_outputs()
+    n_out = C.c_uint64(0)
+    ffi.check(ctx.lib.lctp_group_reads(ctx._h, C.byref(c), max(1, len(pre.rec_contig)), out["status"].ctypes.data,
+                                       C.byref(n_out), *[out[k].ctypes.data for k in (
+                                           "out_read", "out_max_alns", "ma_off", "ma_contig", "ma_flags", "ma_start",
+                                           "ma_end", "ma_ln_prob", "ma_rec", "counts")]))
+    return pre.trim_outputs(out, int(n_out.value))
 
 
 def rescore_alignments(ctx: "Context", alns: Alns) -> dict:

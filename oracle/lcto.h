@@ -248,6 +248,7 @@ typedef struct lcto_mates {
     uint32_t window;             /* ContigInfo::window_size (explicit weights) */
     const uint64_t *exp_off;     /* [H+1] explicit weights per contig position (ExplicitWeights::at), or NULL */
     const double   *exp_weight;
+    const uint8_t  *read_max_alns;   /* [R] per-read max_alns (locs.rs:1263), or NULL (= max_alns) */
 } lcto_mates;
 
 /* identify_paired_end_alignments for every read (src/model/locs.rs:805-868). Outputs are the `pa_*` /
@@ -285,6 +286,27 @@ typedef struct lcto_read_ends {
 int lcto_collect_read_ends(const lcto_read_ends *in, double *ln_prob, uint32_t *edit, uint32_t *read_len,
                            uint8_t *ok, uint32_t *best_edit, double *weight_factor, uint32_t *thr_dist,
                            uint32_t *pass_dist, uint32_t *n_kept, uint32_t *kept_rec);
+
+/* from the per read-end results to the pairing input (lcto_group.c): AllAlignments::load after read_next_alns
+ * (src/model/locs.rs:1117-1137) + recover_and_group_alignments without the transfer (:1237-1288). */
+typedef struct lcto_prelim {
+    uint64_t n_reads, n_groups;
+    const int64_t  *read_group;        /* [n_reads][2] group of the first / second read end, -1 = none */
+    const uint64_t *grp_off;           /* [n_groups+1] */
+    const uint32_t *rec_contig, *rec_start, *rec_end;   /* [n_alns] */
+    const uint8_t  *rec_strand;        /* [n_alns] 1 = reverse */
+    const double   *rec_ln_prob;       /* [n_alns] */
+    const uint8_t  *grp_ok;            /* [n_groups] */
+    const uint32_t *grp_best_edit, *grp_thr_dist, *grp_n_kept;
+    const uint32_t *kept_rec;          /* [n_alns] */
+    const uint32_t *contig_len;        /* [n_haps] */
+    const double   *read_weight;       /* [n_reads] */
+    double min_weight;
+    uint32_t n_haps, boundary, single_end, _pad;
+} lcto_prelim;
+int lcto_group_reads(const lcto_prelim *in, uint64_t cap, uint8_t *status, uint64_t *n_reads_out, uint32_t *out_read,
+                     uint8_t *out_max_alns, uint64_t *ma_off, uint32_t *ma_contig, uint8_t *ma_flags,
+                     uint32_t *ma_start, uint32_t *ma_end, double *ma_ln_prob, uint32_t *ma_rec, uint64_t *counts);
 
 /* ------------------------------------------------ short-read recruitment (lcto_recruit.c) */
 

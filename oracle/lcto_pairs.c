@@ -129,7 +129,7 @@ static int single_end_alignments(const lcto_mates *in, uint64_t cap, uint64_t *p
                 thresh = in->ma_ln_prob[a] - in->prob_diff;
                 curr_saved = 0;
             }
-            if (in->ma_ln_prob[a] >= thresh && curr_saved < in->max_alns) {
+            if (in->ma_ln_prob[a] >= thresh && curr_saved < (in->read_max_alns ? in->read_max_alns[r] : in->max_alns)) {
                 if (n_out >= cap) return -3;
                 pa_contig[n_out] = curr_contig; pa_ln_prob[n_out] = in->ma_ln_prob[a];
                 pa_mid1[n_out] = (in->ma_start[a] + in->ma_end[a]) / 2; pa_mid2[n_out] = LCTO_NONE_U32;
@@ -145,17 +145,19 @@ static int single_end_alignments(const lcto_mates *in, uint64_t cap, uint64_t *p
 int lcto_pair_alignments(const lcto_mates *in, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig,
                          double *pa_ln_prob, uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob) {
     if (in->single_end) return single_end_alignments(in, cap, pa_off, pa_contig, pa_ln_prob, pa_mid1, pa_mid2, unmapped_prob);
-    const uint32_t M = in->max_alns;
-    pair_cand *cands = (pair_cand *)malloc(sizeof(pair_cand) * ((size_t)M * M + 2 * M));
-    pair_cand *kept = (pair_cand *)malloc(sizeof(pair_cand) * M);
-    double *buffer = (double *)malloc(sizeof(double) * M);
-    uint64_t *sel = (uint64_t *)malloc(sizeof(uint64_t) * 2 * M);
+    uint32_t Mmax = in->max_alns;                 /* per-read limits (recover_and_group_alignments, locs.rs:1263) */
+    if (in->read_max_alns) for (uint32_t r = 0; r < in->n_reads; r++) Mmax = in->read_max_alns[r] > Mmax ? in->read_max_alns[r] : Mmax;
+    pair_cand *cands = (pair_cand *)malloc(sizeof(pair_cand) * ((size_t)Mmax * Mmax + 2 * Mmax));
+    pair_cand *kept = (pair_cand *)malloc(sizeof(pair_cand) * Mmax);
+    double *buffer = (double *)malloc(sizeof(double) * Mmax);
+    uint64_t *sel = (uint64_t *)malloc(sizeof(uint64_t) * 2 * Mmax);
     const double insert_penalty = in->insert_penalty;
     const double unm_ins_penalty = in->unmapped_penalty + insert_penalty;          /* locs.rs:815-816 */
     uint64_t n_out = 0;
     int rc = 0;
     for (uint32_t r = 0; r < in->n_reads && rc == 0; r++) {
         pa_off[r] = n_out;
+        const uint32_t M = in->read_max_alns ? in->read_max_alns[r] : in->max_alns;
         uint64_t a = in->ma_off[r];
         const uint64_t end = in->ma_off[r + 1];
         while (a < end) {
@@ -171,6 +173,7 @@ int lcto_pair_alignments(const lcto_mates *in, uint64_t cap, uint64_t *pa_off, u
             for (uint64_t q = 0; q < n2; q++) sel[n1 + q] = f + q;
             /* contig_pairs works on index ranges; build a compact view */
             lcto_mates v = *in;
+            v.max_alns = M;
             uint32_t st[2 * 64], en[2 * 64];
             uint8_t fl[2 * 64];
             double lp[2 * 64];

@@ -18,7 +18,8 @@ _SO = os.path.join(_HERE, "_build", "liblcto.so")
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("lcto_rng.c", "lcto_specfun.c", "lcto_model.c", "lcto_solve.c", "lcto.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("lcto_rng.c", "lcto_specfun.c", "lcto_model.c", "lcto_solve.c", "lcto_pairs.c", "lcto_rescore.c",
+                                             "lcto_recruit.c", "lcto_group.c", "lcto.h")]
     stale = force or not os.path.exists(_SO) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if stale:
@@ -420,7 +421,8 @@ class MatesC(C.Structure):
                 ("ma_end", C.c_void_p), ("ma_ln_prob", C.c_void_p), ("read_weight", C.c_void_p),
                 ("ins_ln_pmf", C.c_void_p),
                 ("unmapped_penalty", C.c_double), ("insert_penalty", C.c_double), ("prob_diff", C.c_double),
-                ("single_end", C.c_uint32), ("window", C.c_uint32), ("exp_off", C.c_void_p), ("exp_weight", C.c_void_p)]
+                ("single_end", C.c_uint32), ("window", C.c_uint32), ("exp_off", C.c_void_p), ("exp_weight", C.c_void_p),
+                ("read_max_alns", C.c_void_p)]
 
 
 def pair_alignments(mates) -> dict:
@@ -490,6 +492,33 @@ def collect_read_ends(re_) -> dict:
     if rc != 0:
         raise RuntimeError(f"lcto_collect_read_ends failed: {rc}")
     return out
+
+
+# ---- per read-end results -> pairing input (lcto_group.c) ----
+
+class PrelimC(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_groups", C.c_uint64), ("read_group", C.c_void_p), ("grp_off", C.c_void_p),
+                ("rec_contig", C.c_void_p), ("rec_start", C.c_void_p), ("rec_end", C.c_void_p), ("rec_strand", C.c_void_p),
+                ("rec_ln_prob", C.c_void_p), ("grp_ok", C.c_void_p), ("grp_best_edit", C.c_void_p),
+                ("grp_thr_dist", C.c_void_p), ("grp_n_kept", C.c_void_p), ("kept_rec", C.c_void_p),
+                ("contig_len", C.c_void_p), ("read_weight", C.c_void_p), ("min_weight", C.c_double),
+                ("n_haps", C.c_uint32), ("boundary", C.c_uint32), ("single_end", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+def group_reads(pre) -> dict:
+    """lcto_group_reads on a locityper_b200.genotype.Prelim-shaped object (plain data)."""
+    keep: list = []
+    c = pre.to_c(keep, struct=PrelimC)
+    R, n = pre.n_reads, len(pre.rec_contig)
+    out = pre.alloc_outputs()
+    n_out = C.c_uint64(0)
+    lib().lcto_group_reads.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 12
+    rc = lib().lcto_group_reads(C.byref(c), max(1, n), out["status"].ctypes.data, C.byref(n_out),
+                                *[out[k].ctypes.data for k in ("out_read", "out_max_alns", "ma_off", "ma_contig", "ma_flags",
+                                                               "ma_start", "ma_end", "ma_ln_prob", "ma_rec", "counts")])
+    if rc != 0:
+        raise RuntimeError(f"lcto_group_reads failed: {rc}")
+    return pre.trim_outputs(out, int(n_out.value))
 
 
 # ---- short-read recruitment (lcto_recruit.c) ----
