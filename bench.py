@@ -514,7 +514,11 @@ def rooflines(st, loci, args, peak, peak_src, fp64_rate=None):
         bytes_alg = g * R * p * 8 + A * 16 + att * apg * 8 + draws * 16
         sec = st["stage_ms"] / 1e3
         ach = bytes_alg / sec / 1e9
-        cap = ncu_traffic("k_solve_stage", full=True) if args.config == "C2" else None
+        # committed capture of the same launch: C2 greedy (the default line) or C3 annealing (`--config C3 --scheme
+        # anneal:i=5k,a=20`, tools/final_run.sh)
+        is_anneal = "anneal" in " ".join(args.scheme)
+        cap = (ncu_traffic("k_solve_stage", full=True) if args.config == "C2" and not is_anneal else
+               ncu_traffic("k_solve_stage_anneal_c3", full=True) if args.config == "C3" and is_anneal else None)
         out["roofline"] = {"kernel": "k_solve_stage", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                            "frac": ach / peak,
                            "traffic": ({"dram_bytes_per_launch": cap["dram_bytes_per_launch"], "capture": cap["capture"]}

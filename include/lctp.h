@@ -453,6 +453,12 @@ int  lctp_solve_counts(lctp_locus_h *h, const lctp_stage *stages, size_t n_stage
                        uint64_t rng[4], lctp_result *res, size_t n_counts,
                        uint64_t *counts_off /* [n_counts + 1] */, uint16_t *counts, uint64_t counts_cap);
 
+/* count_to_prob (src/model/bam.rs:54-66): what write_bam turns an assignment count into, for n counts at once (host):
+ * prob (f32, the `pr` tag) and mapq.  count 0 -> (0, 0), count == attempts -> (1, 60), otherwise prob = count / attempts
+ * in f32 and mapq = round(-10 log10(1 - prob)) capped at 60.  LCTP_E_INVALID when a count exceeds `attempts` (the
+ * reference asserts). */
+int  lctp_counts_to_prob(const uint16_t *counts, uint64_t n, uint16_t attempts, float *prob, uint8_t *mapq);
+
 /* ---- host-side mirror of the scheduler (a14-a16) ------------------------------------------- */
 void lctp_rng_seed_from_u64(uint64_t state[4], uint64_t seed);   /* src/ext/rand.rs:12 */
 void lctp_rng_jump(uint64_t state[4]);                            /* src/solvers/solve.rs:1017 */

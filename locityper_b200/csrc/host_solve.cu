@@ -434,6 +434,24 @@ int lctp_rescore_alignments(lctp_ctx *ctx, const lctp_alns *in, double *ln_prob,
 
 size_t lctp_sizeof_read_ends(void) { return sizeof(lctp_read_ends); }
 
+// count_to_prob, src/model/bam.rs:54-66 (f32 arithmetic throughout, f32::log10 / round / min as the reference)
+int lctp_counts_to_prob(const uint16_t *counts, uint64_t n, uint16_t attempts, float *prob, uint8_t *mapq) {
+    if (n && (!counts || !prob || !mapq)) { set_error("lctp_counts_to_prob: NULL array"); return LCTP_E_INVALID; }
+    for (uint64_t i = 0; i < n; i++) {
+        const uint16_t c = counts[i];
+        if (c == 0) { prob[i] = 0.0f; mapq[i] = 0; }
+        else if (c == attempts) { prob[i] = 1.0f; mapq[i] = 60; }
+        else if (c > attempts) { set_error("lctp_counts_to_prob: count %u of %u attempts", c, attempts); return LCTP_E_INVALID; }
+        else {
+            const float p = (float)c / (float)attempts;
+            const float q = std::fmin(std::round(-10.0f * std::log10(1.0f - p)), 60.0f);
+            prob[i] = p;
+            mapq[i] = (uint8_t)q;
+        }
+    }
+    return LCTP_OK;
+}
+
 int lctp_collect_read_ends(lctp_ctx *ctx, const lctp_read_ends *in, double *ln_prob, uint32_t *edit, uint32_t *read_len,
                            uint8_t *ok, uint32_t *best_edit, double *weight_factor, uint32_t *thr_dist,
                            uint32_t *pass_dist, uint32_t *n_kept, uint32_t *kept_rec) {

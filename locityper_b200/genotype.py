@@ -652,6 +652,14 @@ def group_reads(ctx: "Context", pre: Prelim) -> dict:
     return pre.trim_outputs(out, int(n_out.value))
 
 
+def counts_to_prob(counts: np.ndarray, attempts: int):
+    """lctp_counts_to_prob: (prob f32, mapq u8) of assignment counts, count_to_prob of src/model/bam.rs:54-66 (host)."""
+    counts = np.ascontiguousarray(counts, dtype=np.uint16)
+    prob, mapq = np.zeros(len(counts), dtype=np.float32), np.zeros(len(counts), dtype=np.uint8)
+    ffi.check(ffi.load().lctp_counts_to_prob(counts.ctypes.data, len(counts), attempts, prob.ctypes.data, mapq.ctypes.data))
+    return prob, mapq
+
+
 def rescore_alignments(ctx: "Context", alns: Alns) -> dict:
     """lctp_rescore_alignments: ln_prob / EditDist / save of every alignment record, computed on the device."""
     keep: list = []

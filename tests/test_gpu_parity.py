@@ -126,6 +126,18 @@ def test_anneal_stage_parity(oracle, gpu_ctx, small_locus):
                   2, gts)
 
 
+@pytest.mark.parametrize("env", [{"LCTP_WIDE_WINDOWS": "1"}, {"LCTP_ANNEAL_CTAS": "16"}, {"LCTP_ANNEAL_CTAS": "32"},
+                                 {"LCTP_WIDE_WINDOWS": "1", "LCTP_ANNEAL_CTAS": "20"}, {"LCTP_NT_GLOBAL": "0"}])
+def test_stage_parity_kernel_variants(oracle, gpu_ctx, small_locus, env, monkeypatch):
+    """The other instantiations of the stage kernel (64-bit candidate records, the register caps of the annealing
+    kernel, the per-read index in shared memory) must give the same iterations, RNG streams, counts and likelihoods."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)                       # read by the library at every launch
+    gts = list(range(2, small_locus.n_genotypes, 53))
+    _stage_parity(oracle, gpu_ctx, small_locus, dict(kind="anneal", attempts=2, anneal_steps=2500, plato_size=1200), 3, gts)
+    _stage_parity(oracle, gpu_ctx, small_locus, dict(kind="greedy", attempts=2), 3, gts)
+
+
 def test_stage_parity_ploidy3_and_hifi(oracle, gpu_ctx):
     loc3 = _mk(oracle, 8, 150, 2500, 21, ploidy=3)
     _stage_parity(oracle, gpu_ctx, loc3, dict(kind="greedy", attempts=2), 4, list(range(0, loc3.n_genotypes, 5)))

@@ -177,3 +177,26 @@ def test_worker_streams_equal_clone_and_jump():
         assert np.array_equal(ws[w], b)
         genotype.rng_jump(b)
     assert np.array_equal(a, b)
+
+
+def test_counts_to_prob_matches_transcription():
+    """count_to_prob (src/model/bam.rs:54-66), statement by statement in numpy float32; every count of several attempt
+    numbers.  A mapq whose unrounded value sits within 1e-4 of a half-integer is not compared (numpy's f32 log10 and
+    the C library's may differ in the last bit there)."""
+    import math
+    for attempts in (1, 2, 5, 20, 100, 1000, 65535):
+        counts = np.arange(0, attempts + 1, max(1, attempts // 997), dtype=np.uint16)
+        prob, mapq = genotype.counts_to_prob(counts, attempts)
+        for c, p, q in zip(counts.tolist(), prob.tolist(), mapq.tolist()):
+            if c == 0:
+                assert (p, q) == (0.0, 0)
+            elif c == attempts:
+                assert (p, q) == (1.0, 60)
+            else:
+                pr = np.float32(c) / np.float32(attempts)
+                assert np.float32(p) == pr
+                x = float(np.float32(-10.0) * np.log10(np.float32(1.0) - pr, dtype=np.float32))
+                if abs(x - math.floor(x) - 0.5) > 1e-4:
+                    assert q == int(min(math.floor(x + 0.5), 60.0)), (c, attempts, x, q)
+    with pytest.raises(RuntimeError):
+        genotype.counts_to_prob(np.array([3], dtype=np.uint16), 2)
