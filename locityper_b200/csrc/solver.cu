@@ -2191,7 +2191,8 @@ int launch_stage_ex(lctp_locus_h *h, const lctp_stage *st, const uint64_t *worke
         const size_t with_nt = group_smem_bytes(P.Wmax, L.R, false, st->kind == 1) + 1024;
         (void)per_sm; (void)with_nt;
         P.nt_global = 1;   // measured at the C2 shape too: 16 workers per SM instead of 14, stage kernel 10.8 -> 10.1 ms
-        if (const char *e = getenv("LCTP_NT_GLOBAL")) P.nt_global = atoi(e) ? 1 : 0;      // test / tuning knob
+        // test / tuning knob, annealing only: the greedy pipeline fetches its index entries from the slab a round ahead
+        if (const char *e = getenv("LCTP_NT_GLOBAL")) { if (st->kind == 1) P.nt_global = atoi(e) ? 1 : 0; }
     }
     P.slab_bytes = slab_bytes_for(cap, P.narrow_w == 0, P.nt_global ? L.R : 0);
     // samples of more than 11 reads (greedy_solve_big): sample + swap partners + index vector behind the slab

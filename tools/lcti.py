@@ -1,6 +1,6 @@
 """`.lcti` dumps: the flat per-locus input as a directory of raw little-endian arrays plus
 `meta.json` -- the format `FlatLocus::dump` (rust/gpu.rs) writes from inside the reference and this module reads and
-writes from Python.  Used by tools/rust_diff.sh to run the oracle / the CUDA path on exactly the
+writes from Python.  Used by oracle/rust_diff.sh (entry point: tools/rust_diff.sh) to run the oracle / the CUDA path on exactly the
 `solve::Data` a real `locityper genotype` run saw.
 
     python tools/lcti.py write DIR --config C1 --seed 1001     # synthetic locus -> dump (round-trip / demo)
