@@ -58,3 +58,17 @@ def load_golden_alns():
     a = genotype.Alns(cigar_off=z["cigar_off"], cigar_ops=z["cigar_ops"], aln_start=z["aln_start"], aln_end=z["aln_end"],
                       contig_len=z["contig_len"], passable_dist=z["passable_dist"], ln_oper=tuple(z["ln_oper"]))
     return a, {k[4:]: z[k] for k in z.files if k.startswith("out_")}
+
+
+def load_golden_prelim(tag):
+    """(genotype.Prelim, expected outputs) of tests/golden/group_{pe,se}_small.npz."""
+    import numpy as np
+    from locityper_b200 import genotype
+    z = np.load(os.path.join(GOLDEN_DIR, f"group_{tag}_small.npz"))
+    sc = z["_scalars"]
+    fields = ("read_group", "grp_off", "rec_contig", "rec_start", "rec_end", "rec_strand", "rec_ln_prob", "grp_ok",
+              "grp_best_edit", "grp_thr_dist", "grp_n_kept", "kept_rec", "contig_len", "read_weight")
+    p = genotype.Prelim(**{k: z[k] for k in fields}, min_weight=float(sc[0]), boundary=int(sc[1]), single_end=bool(sc[2]))
+    out = {k[4:]: z[k] for k in z.files if k.startswith("out_")}
+    out["n_reads_out"] = int(out["n_reads_out"])
+    return p, out

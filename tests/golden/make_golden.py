@@ -135,8 +135,33 @@ def make_upstream():
     return len(m.ma_contig), a.n_alns
 
 
+PRELIM_FIELDS = ("read_group", "grp_off", "rec_contig", "rec_start", "rec_end", "rec_strand", "rec_ln_prob", "grp_ok",
+                 "grp_best_edit", "grp_thr_dist", "grp_n_kept", "kept_rec", "contig_len", "read_weight")
+
+
+def make_group():
+    """Fixture of the step in front of the pairing (lctp_group_reads, SURVEY 8(f) rank 1 remainder): a paired-end and a
+    single-end input (the generator of tests/test_group.py) with the oracle's outputs."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_group import _random_prelim
+    n = 0
+    for tag, single in (("pe", False), ("se", True)):
+        p = _random_prelim(515151 + int(single), n_reads=120, single_end=single)
+        out = O.group_reads(p)
+        scal = np.array([p.min_weight, p.boundary, int(p.single_end)], dtype=np.float64)
+        np.savez_compressed(os.path.join(HERE, f"group_{tag}_small.npz"), _scalars=scal,
+                            **{k: np.asarray(getattr(p, k)) for k in PRELIM_FIELDS},
+                            **{"out_" + k: np.asarray(v) for k, v in out.items()})
+        n += len(p.rec_contig)
+    return n
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["group"]:
+        print("group fixtures: %d alignment records" % make_group())
+        sys.exit(0)
     for name, spec in CASES.items():
         o = make_case(name, spec)
         print(name, "G =", o["n_genotypes"], "call =", o["solve"][-1]["gt_ix"][:1], "truth =", o["truth"])
     print("upstream fixtures: %d mate records, %d alignment records" % make_upstream())
+    print("group fixtures: %d alignment records" % make_group())

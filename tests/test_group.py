@@ -178,6 +178,22 @@ def test_gpu_group_reads_equals_oracle(gpu_ctx, oracle, seed, single_end, n_read
     assert _same(got, oracle.group_reads(p))
 
 
+@pytest.mark.parametrize("tag", ["pe", "se"])
+def test_oracle_equals_golden(oracle, tag):
+    from conftest import load_golden_prelim
+    p, want = load_golden_prelim(tag)
+    assert _same(oracle.group_reads(p), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["pe", "se"])
+def test_gpu_group_reads_equals_golden(gpu_ctx, tag):
+    """No oracle at run time: the committed fixtures (tests/golden/group_*_small.npz) are the reference."""
+    from conftest import load_golden_prelim
+    p, want = load_golden_prelim(tag)
+    assert _same(genotype.group_reads(gpu_ctx, p), want)
+
+
 @pytest.mark.gpu
 def test_gpu_group_reads_edge_cases(gpu_ctx, oracle):
     assert _same(genotype.group_reads(gpu_ctx, _hand_case()), oracle.group_reads(_hand_case()))
