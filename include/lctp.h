@@ -341,6 +341,25 @@ int  lctp_group_reads(lctp_ctx *ctx, const lctp_prelim *in, uint64_t cap, uint8_
                       uint64_t *counts);
 size_t lctp_sizeof_prelim(void);
 
+/* Read weights from the k-mers unique to the locus: UniqueKmers (src/model/locs.rs:915-1003), the step of
+ * AllAlignments::load between read_next_alns and recover_and_group_alignments (:1144-1148).
+ * lctp_unique_kmers_build = UniqueKmers::new (:930-963): the canonical k-mers (kmers::kmers::<u128, _, CANONICAL>,
+ * src/seq/kmers.rs:163-202; k = KmerCounts::k(), 2..=63) of the n_seqs contig sequences (ASCII, anything but A/C/G/T is
+ * an N) whose off-target count (kmer_counts, len + 1 - k entries per sequence at cnt_off) is 0; host pass + upload of an
+ * open-addressing table.  hard / soft threshold = Params::kmer_hard_thresh / kmer_soft_thresh.
+ * lctp_read_weights = calculate_read_weight (:968-1002) for n_reads reads of `ends` (1 or 2) read ends each on the
+ * device: sequence e of read r = seqs[seq_off[r * ends + e] .. seq_off[r * ends + e + 1]), empty = no mate;
+ * unique[r * ends + e] = MateData::unique_kmers (non-overlapping unique k-mers of the read end), weight[r] = the factor
+ * read_data.weight is multiplied by, clamp(intercept + count * slope, 0, 1). */
+typedef struct lctp_unique_kmers_h lctp_unique_kmers_h;
+int  lctp_unique_kmers_build(lctp_ctx *ctx, const uint8_t *seqs, const uint64_t *seq_off, uint64_t n_seqs,
+                             const uint16_t *kmer_counts, const uint64_t *cnt_off, uint32_t k, uint16_t hard_threshold,
+                             uint16_t soft_threshold, lctp_unique_kmers_h **out, uint64_t *n_unique);
+uint64_t lctp_unique_kmers_count(const lctp_unique_kmers_h *u);
+void lctp_unique_kmers_free(lctp_unique_kmers_h *u);
+int  lctp_read_weights(lctp_ctx *ctx, const lctp_unique_kmers_h *u, const uint8_t *seqs, const uint64_t *seq_off,
+                       uint64_t n_reads, uint32_t ends, uint16_t *unique, double *weight);
+
 /* ---- SURVEY 8(f) rank 3, first slice: short-read recruitment ---------------------------------------------------------
  * Canonical minimizers (kmers::minimizers::<u64, _, CANONICAL>, src/seq/kmers.rs:71-103, 256-340) of n sequences
  * (ASCII A/C/G/T, anything else is an N) on the device.  Outputs of sequence s start at off[s] in hash / pos / fw (a

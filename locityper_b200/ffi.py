@@ -174,6 +174,10 @@ SYMBOLS = {
     "lctp_sizeof_read_ends": (C.c_size_t, []),
     "lctp_collect_read_ends": (C.c_int, [_P] * 12),
     "lctp_sizeof_prelim": (C.c_size_t, []),
+    "lctp_unique_kmers_build": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P, C.c_uint32, C.c_uint16, C.c_uint16, _P, _P]),
+    "lctp_unique_kmers_count": (C.c_uint64, [_P]),
+    "lctp_unique_kmers_free": (None, [_P]),
+    "lctp_read_weights": (C.c_int, [_P, _P, _P, _P, C.c_uint64, C.c_uint32, _P, _P]),
     "lctp_counts_to_prob": (C.c_int, [_P, C.c_uint64, C.c_uint16, _P, _P]),
     "lctp_group_reads": (C.c_int, [_P, _P, C.c_uint64] + [_P] * 12),
     "lctp_locus_upload": (C.c_int, [_P, _P, _P]),

@@ -652,6 +652,53 @@ def group_reads(ctx: "Context", pre: Prelim) -> dict:
     return pre.trim_outputs(out, int(n_out.value))
 
 
+def _seq_arrays(seqs):
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(s) for s in seqs])
+    cat = np.frombuffer(b"".join(seqs), dtype=np.uint8) if int(off[-1]) else np.zeros(1, dtype=np.uint8)
+    return np.ascontiguousarray(cat), off
+
+
+class UniqueKmers:
+    """lctp_unique_kmers_h: the k-mers unique to a locus (UniqueKmers::new, src/model/locs.rs:930-963) as a device table;
+    `read_weights` = calculate_read_weight (:968-1002) for all reads in one launch."""
+
+    def __init__(self, ctx: "Context", contig_seqs, kmer_counts, k: int, hard_threshold: int, soft_threshold: int):
+        self.ctx, self.lib = ctx, ctx.lib
+        cat, off = _seq_arrays(contig_seqs)
+        cnt_off = np.zeros(len(kmer_counts) + 1, dtype=np.uint64)
+        cnt_off[1:] = np.cumsum([len(c) for c in kmer_counts])
+        cnt = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.uint16) for c in kmer_counts] or [np.zeros(0, np.uint16)]))
+        if len(cnt) == 0:
+            cnt = np.zeros(1, dtype=np.uint16)
+        self._h = C.c_void_p()
+        n = C.c_uint64(0)
+        ffi.check(self.lib.lctp_unique_kmers_build(ctx._h, cat.ctypes.data, off.ctypes.data, len(contig_seqs), cnt.ctypes.data,
+                                                   cnt_off.ctypes.data, k, hard_threshold, soft_threshold,
+                                                   C.byref(self._h), C.byref(n)))
+        self.n_unique = int(n.value)
+
+    def read_weights(self, read_seqs, ends: int):
+        """read_seqs: list of bytes, `ends` per read (b"" = no mate) -> (unique u16[n * ends], weight f64[n])."""
+        n = len(read_seqs) // ends
+        cat, off = _seq_arrays(read_seqs)
+        unique, weight = np.zeros(max(1, n * ends), dtype=np.uint16), np.zeros(max(1, n))
+        ffi.check(self.lib.lctp_read_weights(self.ctx._h, self._h, cat.ctypes.data, off.ctypes.data, n, ends,
+                                             unique.ctypes.data, weight.ctypes.data))
+        return unique[:n * ends], weight[:n]
+
+    def free(self):
+        if self._h:
+            self.lib.lctp_unique_kmers_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def counts_to_prob(counts: np.ndarray, attempts: int):
     """lctp_counts_to_prob: (prob f32, mapq u8) of assignment counts, count_to_prob of src/model/bam.rs:54-66 (host)."""
     counts = np.ascontiguousarray(counts, dtype=np.uint16)

@@ -308,6 +308,16 @@ int lcto_group_reads(const lcto_prelim *in, uint64_t cap, uint8_t *status, uint6
                      uint8_t *out_max_alns, uint64_t *ma_off, uint32_t *ma_contig, uint8_t *ma_flags,
                      uint32_t *ma_start, uint32_t *ma_end, double *ma_ln_prob, uint32_t *ma_rec, uint64_t *counts);
 
+/* read weights from the k-mers unique to the locus (lcto_weights.c): UniqueKmers, src/model/locs.rs:915-1003 */
+typedef struct lcto_unique_kmers lcto_unique_kmers;
+lcto_unique_kmers *lcto_unique_kmers_build(const uint8_t *seqs, const uint64_t *seq_off, uint64_t n_seqs,
+                                           const uint16_t *kmer_counts, const uint64_t *cnt_off, uint32_t k,
+                                           uint16_t hard_threshold, uint16_t soft_threshold);
+uint64_t lcto_unique_kmers_count(const lcto_unique_kmers *u);
+void lcto_unique_kmers_free(lcto_unique_kmers *u);
+int lcto_read_weights(const lcto_unique_kmers *u, const uint8_t *seqs, const uint64_t *seq_off, uint64_t n_reads,
+                      uint32_t ends, uint16_t *unique, double *weight);
+
 /* ------------------------------------------------ short-read recruitment (lcto_recruit.c) */
 
 typedef struct lcto_target_seqs {

@@ -19,7 +19,7 @@ _SO = os.path.join(_HERE, "_build", "liblcto.so")
 
 def build(force: bool = False) -> str:
     srcs = [os.path.join(_HERE, f) for f in ("lcto_rng.c", "lcto_specfun.c", "lcto_model.c", "lcto_solve.c", "lcto_pairs.c", "lcto_rescore.c",
-                                             "lcto_recruit.c", "lcto_group.c", "lcto.h")]
+                                             "lcto_recruit.c", "lcto_group.c", "lcto_weights.c", "lcto.h")]
     stale = force or not os.path.exists(_SO) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if stale:
@@ -519,6 +519,55 @@ def group_reads(pre) -> dict:
     if rc != 0:
         raise RuntimeError(f"lcto_group_reads failed: {rc}")
     return pre.trim_outputs(out, int(n_out.value))
+
+
+# ---- read weights from unique k-mers (lcto_weights.c) ----
+
+def _seq_arrays(seqs):
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(s) for s in seqs])
+    cat = np.frombuffer(b"".join(seqs), dtype=np.uint8) if int(off[-1]) else np.zeros(1, dtype=np.uint8)
+    return np.ascontiguousarray(cat), off
+
+
+class UniqueKmers:
+    """lcto_unique_kmers_build: UniqueKmers::new.  contig_seqs: list of bytes; kmer_counts: list of u16 arrays."""
+
+    def __init__(self, contig_seqs, kmer_counts, k, hard_threshold, soft_threshold):
+        L = lib()
+        L.lcto_unique_kmers_build.restype = C.c_void_p
+        L.lcto_unique_kmers_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
+                                              C.c_uint16, C.c_uint16]
+        L.lcto_unique_kmers_count.restype = C.c_uint64
+        L.lcto_unique_kmers_count.argtypes = [C.c_void_p]
+        L.lcto_unique_kmers_free.argtypes = [C.c_void_p]
+        L.lcto_read_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
+        cat, off = _seq_arrays(contig_seqs)
+        cnt_off = np.zeros(len(kmer_counts) + 1, dtype=np.uint64)
+        cnt_off[1:] = np.cumsum([len(c) for c in kmer_counts])
+        cnt = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.uint16) for c in kmer_counts] or [np.zeros(0, np.uint16)]))
+        if len(cnt) == 0:
+            cnt = np.zeros(1, dtype=np.uint16)
+        self._h = L.lcto_unique_kmers_build(cat.ctypes.data, off.ctypes.data, len(contig_seqs), cnt.ctypes.data,
+                                            cnt_off.ctypes.data, k, hard_threshold, soft_threshold)
+        if not self._h:
+            raise RuntimeError("lcto_unique_kmers_build failed")
+        self.n_unique = int(L.lcto_unique_kmers_count(self._h))
+
+    def read_weights(self, read_seqs, ends):
+        """read_seqs: list of bytes, `ends` per read (b"" = no mate) -> (unique u16[n * ends], weight f64[n])."""
+        n = len(read_seqs) // ends
+        cat, off = _seq_arrays(read_seqs)
+        unique, weight = np.zeros(max(1, n * ends), dtype=np.uint16), np.zeros(max(1, n))
+        rc = lib().lcto_read_weights(self._h, cat.ctypes.data, off.ctypes.data, n, ends, unique.ctypes.data, weight.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"lcto_read_weights failed: {rc}")
+        return unique[:n * ends], weight[:n]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().lcto_unique_kmers_free(self._h)
+            self._h = None
 
 
 # ---- short-read recruitment (lcto_recruit.c) ----
