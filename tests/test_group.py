@@ -226,3 +226,42 @@ def test_gpu_group_then_pair_with_per_read_max_alns(gpu_ctx, oracle):
         assert np.array_equal(got[k], want[k]), k
     capped = genotype.Mates(**{**mates.__dict__, "read_max_alns": None, "max_alns": 10})
     assert len(oracle.pair_alignments(capped)["pa_contig"]) > len(want["pa_contig"])      # the limit of 2 binds somewhere
+
+
+def _chain(collect, group, pair, seed=77, n_reads=600):
+    """records -> read ends (read_next_alns protocol) -> status / order (load + recover_and_group_alignments) -> pair
+    alignments, every stage fed with the arrays of the previous one as they are."""
+    from test_rescore import _read_ends
+    re_ = _read_ends(2 * n_reads, seed, contigs=5, per_group=(1, 12), contig_len=3500, strict=True)
+    re_.grp_read_end = (np.arange(2 * n_reads) % 2).astype(np.uint8)        # group 2r = first end, 2r + 1 = second end of read r
+    c = collect(re_)
+    rng = np.random.default_rng(seed + 5)
+    wf = c["weight_factor"].reshape(n_reads, 2)
+    pre = genotype.Prelim(read_group=np.arange(2 * n_reads, dtype=np.int64).reshape(n_reads, 2), grp_off=re_.grp_off,
+                          rec_contig=re_.rec_contig, rec_start=re_.alns.aln_start, rec_end=re_.alns.aln_end,
+                          rec_strand=rng.integers(0, 2, re_.alns.n_alns).astype(np.uint8), rec_ln_prob=c["ln_prob"],
+                          grp_ok=c["ok"], grp_best_edit=c["best_edit"], grp_thr_dist=c["thr_dist"], grp_n_kept=c["n_kept"],
+                          kept_rec=c["kept_rec"], contig_len=np.full(5, 3500, dtype=np.uint32),
+                          read_weight=wf[:, 0] * wf[:, 1] * rng.uniform(0.2, 1.0, n_reads), min_weight=0.5, boundary=1400)
+    g = group(pre)
+    R = g["n_reads_out"]
+    ins = -np.abs(np.arange(8192) - 400.0) / 50.0
+    mates = genotype.Mates(n_reads=R, n_haps=5, ma_off=g["ma_off"], ma_contig=g["ma_contig"], ma_flags=g["ma_flags"],
+                           ma_start=g["ma_start"], ma_end=g["ma_end"], ma_ln_prob=g["ma_ln_prob"], ins_ln_pmf=ins,
+                           unmapped_penalty=-20.0, insert_penalty=-12.0, prob_diff=8.0,
+                           read_weight=pre.read_weight[g["out_read"]], read_max_alns=g["out_max_alns"])
+    return c, g, pair(mates)
+
+
+@pytest.mark.gpu
+def test_gpu_chain_records_to_pairs(gpu_ctx, oracle):
+    """The three upstream calls chained on the device path against the same chain on the oracle."""
+    import functools
+    got = _chain(functools.partial(genotype.collect_read_ends, gpu_ctx), functools.partial(genotype.group_reads, gpu_ctx),
+                 functools.partial(genotype.pair_alignments, gpu_ctx))
+    want = _chain(oracle.collect_read_ends, oracle.group_reads, oracle.pair_alignments)
+    assert _same(got[1], want[1])
+    assert want[1]["n_reads_out"] > 50 and set(int(v) for v in want[1]["status"]) == {0, 1, 2, 3}
+    for k in want[2]:
+        assert np.array_equal(got[2][k], want[2][k]), k
+    assert len(want[2]["pa_contig"]) > 100
