@@ -819,6 +819,7 @@ __device__ __forceinline__ void apply_move(const WarpShared &ws, const double *_
                                            uint32_t new_a, const Move<WIDE> &mv) {
     typedef RecWord<WIDE> RW;
     const uint32_t w1 = RW::w1(mv.raw_old), w2 = RW::w2(mv.raw_old), w3 = RW::w1(mv.raw_new), w4 = RW::w2(mv.raw_new);
+    __syncwarp();          // every lane is done reading the assignments / window state this move overwrites
     if (ws.lane == 0) {
         ws.win.depth(w3) += 1;
         ws.win.depth(w4) += 1;
