@@ -340,6 +340,19 @@ int  lctp_group_reads(lctp_ctx *ctx, const lctp_prelim *in, uint64_t cap, uint8_
                       uint8_t *ma_flags, uint32_t *ma_start, uint32_t *ma_end, double *ma_ln_prob, uint32_t *ma_rec,
                       uint64_t *counts);
 size_t lctp_sizeof_prelim(void);
+/* Same, leaving the pairing input on the device: the handle replaces the ma_* / read_max_alns fields of lctp_mates in
+ * lctp_pair_alignments_from, so that the (largest) arrays of the upstream chain cross PCIe once, as records, and never
+ * again (group -> pair -> locus upload all read device memory).  Only status, out_read (may be NULL), the counts and the
+ * number of passing reads come back.  `params` of lctp_pair_alignments_from = an lctp_mates whose ma_* / read_max_alns /
+ * n_reads are ignored: n_haps, max_alns, the insert-size table, penalties, prob_diff, single_end, window, explicit
+ * weights, and read_weight = the weights of the PASSING reads in out_read order (or NULL = 1.0). */
+typedef struct lctp_mates_h lctp_mates_h;
+int  lctp_group_reads_dev(lctp_ctx *ctx, const lctp_prelim *in, uint8_t *status, uint64_t *n_reads_out,
+                          uint32_t *out_read, uint64_t *counts, lctp_mates_h **out);
+uint64_t lctp_mates_count(const lctp_mates_h *m);
+void lctp_mates_free(lctp_mates_h *m);
+int  lctp_pair_alignments_from(lctp_ctx *ctx, const lctp_mates_h *mates, const lctp_mates *params, lctp_pairs_h **out,
+                               uint64_t *n_out);
 
 /* Read weights from the k-mers unique to the locus: UniqueKmers (src/model/locs.rs:915-1003), the step of
  * AllAlignments::load between read_next_alns and recover_and_group_alignments (:1144-1148).

@@ -43,6 +43,11 @@ struct DevBuf {
         return LCTP_OK;
     }
     int ensure(size_t count) { return count <= n ? LCTP_OK : alloc(count); }
+    void take(DevBuf &o) {              // move: this buffer becomes o's allocation, o becomes empty
+        release();
+        p = o.p; n = o.n; s = o.s;
+        o.p = nullptr; o.n = 0;
+    }
     void release() {
         if (p) cudaFreeAsync(p, s);
         p = nullptr;
@@ -209,6 +214,18 @@ struct lctp_pairs_h {
     lctp::DevBuf<double> lnprob, unmapped;
 };
 
+// Device-resident input of the pairing (lctp_group_reads_dev -> lctp_pair_alignments_from): the lctp_mates arrays of the
+// reads that passed, in consumption order, plus the per-read max_alns.
+struct lctp_mates_h {
+    lctp_ctx *ctx = nullptr;
+    uint32_t n_reads = 0;
+    uint64_t n = 0;
+    lctp::DevBuf<uint64_t> ma_off;
+    lctp::DevBuf<uint32_t> contig, start, end, rec;
+    lctp::DevBuf<uint8_t> flags, max_alns;
+    lctp::DevBuf<double> lnprob;
+};
+
 namespace lctp {
 // upload.cu
 int upload_locus(lctp_ctx *ctx, const lctp_locus *in, lctp_locus_h *h, const lctp_pairs_h *pairs);
@@ -218,7 +235,7 @@ int measure_fp64_rate(lctp_ctx *ctx, double *lane_inst_per_s);
 int prefilter_plan_check(uint32_t H, uint32_t n_sm, const uint32_t *pattern, uint32_t n_pattern, uint64_t g_begin,
                          uint64_t g_end, uint32_t *n_regions, uint32_t *load, uint32_t *pattern_out);
 // pairs.cu
-int pair_alignments_dev(lctp_ctx *ctx, const lctp_mates *in, lctp_pairs_h *out);
+int pair_alignments_dev(lctp_ctx *ctx, const lctp_mates *in, lctp_pairs_h *out, const lctp_mates_h *src = nullptr);
 int pairs_fetch(lctp_pairs_h *p, uint64_t cap, uint64_t *pa_off, uint32_t *pa_contig, double *pa_ln_prob,
                 uint32_t *pa_mid1, uint32_t *pa_mid2, double *unmapped_prob);
 // rescore.cu

@@ -119,28 +119,27 @@ static int up(DevBuf<T> &dst, const T *src, size_t n, cudaStream_t s) {
     return LCTP_OK;
 }
 
-int group_reads(lctp_ctx *ctx, const lctp_prelim *in, uint64_t cap, uint8_t *status, uint64_t *n_reads_out,
-                uint32_t *out_read, uint8_t *out_max_alns, uint64_t *ma_off, uint32_t *ma_contig, uint8_t *ma_flags,
-                uint32_t *ma_start, uint32_t *ma_end, double *ma_ln_prob, uint32_t *ma_rec, uint64_t *counts) {
+// Device-side results of one run: everything lctp_group_reads returns, still in device memory.
+struct GroupDev {
+    DevBuf<uint8_t> status, omax, mfl;
+    DevBuf<uint32_t> oread, mcon, mst, men, mrec;
+    DevBuf<uint64_t> maoff;
+    DevBuf<double> mlp;
+    uint32_t n_pass = 0;
+    uint64_t n_ma = 0;
+};
+
+static int group_reads_run(lctp_ctx *ctx, const lctp_prelim *in, uint8_t *status, GroupDev &g) {
     cudaStream_t s = ctx->stream;
     const uint64_t R = in->n_reads, G = in->n_groups;
-    *n_reads_out = 0;
-    counts[0] = counts[1] = counts[2] = 0;
-    ma_off[0] = 0;
-    if (R == 0) return LCTP_OK;
-    if (G == 0 || !in->grp_off || !in->read_group) {
-        for (uint64_t r = 0; r < R; r++) status[r] = 1;
-        counts[0] = R;
-        return LCTP_OK;
-    }
     const uint64_t N = in->grp_off[G];
     for (uint64_t r = 0; r < 2 * R; r++)
         if (in->read_group[r] >= (int64_t)G) { set_error("lctp_group_reads: read_group entry %llu out of range", (unsigned long long)r); return LCTP_E_INVALID; }
     DevBuf<int64_t> d_rg;
-    DevBuf<uint64_t> d_goff, d_nent, d_first, d_maoff;
-    DevBuf<uint32_t> d_con, d_st, d_en, d_be, d_thr, d_nk, d_kept, d_clen, d_pass, d_place, d_oread, d_mcon, d_mst, d_men, d_mrec;
-    DevBuf<uint8_t> d_str, d_ok, d_status, d_omax, d_mfl;
-    DevBuf<double> d_lp, d_w, d_mlp;
+    DevBuf<uint64_t> d_goff, d_nent, d_first;
+    DevBuf<uint32_t> d_con, d_st, d_en, d_be, d_thr, d_nk, d_kept, d_clen, d_pass, d_place;
+    DevBuf<uint8_t> d_str, d_ok;
+    DevBuf<double> d_lp, d_w;
     DevBuf<unsigned char> d_tmp;
     int rc;
     if ((rc = up(d_rg, in->read_group, 2 * R, s)) || (rc = up(d_goff, in->grp_off, G + 1, s)) ||
@@ -149,17 +148,18 @@ int group_reads(lctp_ctx *ctx, const lctp_prelim *in, uint64_t cap, uint8_t *sta
         (rc = up(d_be, in->grp_best_edit, G, s)) || (rc = up(d_thr, in->grp_thr_dist, G, s)) ||
         (rc = up(d_nk, in->grp_n_kept, G, s)) || (rc = up(d_kept, in->kept_rec, N, s)) ||
         (rc = up(d_clen, in->contig_len, in->n_haps, s)) || (rc = up(d_w, in->read_weight, R, s))) return rc;
+    ctx->stats.h2d_bytes += 2 * R * 8 + (G + 1) * 8 + N * (4 + 4 + 4 + 1 + 8 + 4) + G * (1 + 4 + 4 + 4) + in->n_haps * 4 + R * 8;
     if ((rc = d_nent.alloc(R + 1)) || (rc = d_first.alloc(R + 1)) || (rc = d_pass.alloc(R + 1)) || (rc = d_place.alloc(R + 1)) ||
-        (rc = d_status.alloc(R)) || (rc = d_oread.alloc(R)) || (rc = d_omax.alloc(R)) || (rc = d_maoff.alloc(R + 1))) return rc;
+        (rc = g.status.alloc(R)) || (rc = g.oread.alloc(R)) || (rc = g.omax.alloc(R)) || (rc = g.maoff.alloc(R + 1))) return rc;
     const size_t M = (size_t)std::max<uint64_t>(1, N);
-    if ((rc = d_mcon.alloc(M)) || (rc = d_mfl.alloc(M)) || (rc = d_mst.alloc(M)) || (rc = d_men.alloc(M)) ||
-        (rc = d_mlp.alloc(M)) || (rc = d_mrec.alloc(M))) return rc;
+    if ((rc = g.mcon.alloc(M)) || (rc = g.mfl.alloc(M)) || (rc = g.mst.alloc(M)) || (rc = g.men.alloc(M)) ||
+        (rc = g.mlp.alloc(M)) || (rc = g.mrec.alloc(M))) return rc;
     PrelimDev D;
     D.n_reads = R; D.read_group = d_rg.p; D.grp_off = d_goff.p; D.rec_contig = d_con.p; D.rec_start = d_st.p;
     D.rec_end = d_en.p; D.rec_strand = d_str.p; D.rec_ln_prob = d_lp.p; D.grp_ok = d_ok.p; D.best_edit = d_be.p;
     D.thr_dist = d_thr.p; D.n_kept = d_nk.p; D.kept_rec = d_kept.p; D.contig_len = d_clen.p; D.read_weight = d_w.p;
     D.min_weight = in->min_weight; D.boundary = in->boundary; D.single_end = in->single_end;
-    k_group_status<<<(unsigned)((R + 1 + 255) / 256), 256, 0, s>>>(D, d_status.p, d_pass.p, d_nent.p);
+    k_group_status<<<(unsigned)((R + 1 + 255) / 256), 256, 0, s>>>(D, g.status.p, d_pass.p, d_nent.p);
     ctx->launches++;
     LCTP_CUDA_CHECK(cudaGetLastError());
     size_t t32 = 0, t64 = 0;
@@ -169,41 +169,96 @@ int group_reads(lctp_ctx *ctx, const lctp_prelim *in, uint64_t cap, uint8_t *sta
     LCTP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(d_tmp.p, t32, d_pass.p, d_place.p, (int)(R + 1), s));
     LCTP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(d_tmp.p, t64, d_nent.p, d_first.p, (int)(R + 1), s));
     ctx->launches += 2;
-    k_group_write<<<(unsigned)((R + 1 + 127) / 128), 128, 0, s>>>(D, d_status.p, d_place.p, d_first.p, d_oread.p, d_omax.p,
-                                                                  d_maoff.p, d_mcon.p, d_mfl.p, d_mst.p, d_men.p, d_mlp.p,
-                                                                  d_mrec.p);
+    k_group_write<<<(unsigned)((R + 1 + 127) / 128), 128, 0, s>>>(D, g.status.p, d_place.p, d_first.p, g.oread.p, g.omax.p,
+                                                                  g.maoff.p, g.mcon.p, g.mfl.p, g.mst.p, g.men.p, g.mlp.p,
+                                                                  g.mrec.p);
     ctx->launches++;
     LCTP_CUDA_CHECK(cudaGetLastError());
-    uint32_t n_pass = 0;
-    uint64_t n_ma = 0;
-    LCTP_CUDA_CHECK(cudaMemcpyAsync(&n_pass, d_place.p + R, 4, cudaMemcpyDeviceToHost, s));
-    LCTP_CUDA_CHECK(cudaMemcpyAsync(&n_ma, d_first.p + R, 8, cudaMemcpyDeviceToHost, s));
-    LCTP_CUDA_CHECK(cudaMemcpyAsync(status, d_status.p, R, cudaMemcpyDeviceToHost, s));
-    LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
-    if (n_ma > cap) {
-        set_error("lctp_group_reads: %llu entries, capacity %llu", (unsigned long long)n_ma, (unsigned long long)cap);
-        return LCTP_E_CAPACITY;
-    }
-    if (n_pass) {
-        LCTP_CUDA_CHECK(cudaMemcpyAsync(out_read, d_oread.p, (size_t)n_pass * 4, cudaMemcpyDeviceToHost, s));
-        LCTP_CUDA_CHECK(cudaMemcpyAsync(out_max_alns, d_omax.p, n_pass, cudaMemcpyDeviceToHost, s));
-    }
-    LCTP_CUDA_CHECK(cudaMemcpyAsync(ma_off, d_maoff.p, ((size_t)n_pass + 1) * 8, cudaMemcpyDeviceToHost, s));
-    if (n_ma) {
-        LCTP_CUDA_CHECK(cudaMemcpyAsync(ma_contig, d_mcon.p, n_ma * 4, cudaMemcpyDeviceToHost, s));
-        LCTP_CUDA_CHECK(cudaMemcpyAsync(ma_flags, d_mfl.p, n_ma, cudaMemcpyDeviceToHost, s));
-        LCTP_CUDA_CHECK(cudaMemcpyAsync(ma_start, d_mst.p, n_ma * 4, cudaMemcpyDeviceToHost, s));
-        LCTP_CUDA_CHECK(cudaMemcpyAsync(ma_end, d_men.p, n_ma * 4, cudaMemcpyDeviceToHost, s));
-        LCTP_CUDA_CHECK(cudaMemcpyAsync(ma_ln_prob, d_mlp.p, n_ma * 8, cudaMemcpyDeviceToHost, s));
-        LCTP_CUDA_CHECK(cudaMemcpyAsync(ma_rec, d_mrec.p, n_ma * 4, cudaMemcpyDeviceToHost, s));
-    }
-    LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(&g.n_pass, d_place.p + R, 4, cudaMemcpyDeviceToHost, s));
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(&g.n_ma, d_first.p + R, 8, cudaMemcpyDeviceToHost, s));
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(status, g.status.p, R, cudaMemcpyDeviceToHost, s));
+    LCTP_CUDA_CHECK(cudaStreamSynchronize(s));       // the inputs (local buffers) are released after this point
+    ctx->stats.d2h_bytes += R + 12;
+    return LCTP_OK;
+}
+
+static void count_status(const uint8_t *status, uint64_t R, uint32_t n_pass, uint64_t *counts) {
+    counts[0] = counts[1] = 0;
     for (uint64_t r = 0; r < R; r++) {
         if (status[r] == 2) counts[1]++;
         else if (status[r] != 0) counts[0]++;
     }
     counts[2] = n_pass;
+}
+
+// false = nothing to run (no reads / no groups); the outputs are then complete
+static bool group_trivial(const lctp_prelim *in, uint8_t *status, uint64_t *n_reads_out, uint64_t *counts) {
+    *n_reads_out = 0;
+    counts[0] = counts[1] = counts[2] = 0;
+    if (in->n_reads == 0) return true;
+    if (in->n_groups == 0 || !in->grp_off || !in->read_group) {
+        for (uint64_t r = 0; r < in->n_reads; r++) status[r] = 1;
+        counts[0] = in->n_reads;
+        return true;
+    }
+    return false;
+}
+
+int group_reads(lctp_ctx *ctx, const lctp_prelim *in, uint64_t cap, uint8_t *status, uint64_t *n_reads_out,
+                uint32_t *out_read, uint8_t *out_max_alns, uint64_t *ma_off, uint32_t *ma_contig, uint8_t *ma_flags,
+                uint32_t *ma_start, uint32_t *ma_end, double *ma_ln_prob, uint32_t *ma_rec, uint64_t *counts) {
+    cudaStream_t s = ctx->stream;
+    ma_off[0] = 0;
+    if (group_trivial(in, status, n_reads_out, counts)) return LCTP_OK;
+    GroupDev g;
+    int rc = group_reads_run(ctx, in, status, g);
+    if (rc) return rc;
+    const uint32_t n_pass = g.n_pass;
+    const uint64_t n_ma = g.n_ma;
+    if (n_ma > cap) {
+        set_error("lctp_group_reads: %llu entries, capacity %llu", (unsigned long long)n_ma, (unsigned long long)cap);
+        return LCTP_E_CAPACITY;
+    }
+    if (n_pass) {
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(out_read, g.oread.p, (size_t)n_pass * 4, cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(out_max_alns, g.omax.p, n_pass, cudaMemcpyDeviceToHost, s));
+    }
+    LCTP_CUDA_CHECK(cudaMemcpyAsync(ma_off, g.maoff.p, ((size_t)n_pass + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (n_ma) {
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(ma_contig, g.mcon.p, n_ma * 4, cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(ma_flags, g.mfl.p, n_ma, cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(ma_start, g.mst.p, n_ma * 4, cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(ma_end, g.men.p, n_ma * 4, cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(ma_ln_prob, g.mlp.p, n_ma * 8, cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(ma_rec, g.mrec.p, n_ma * 4, cudaMemcpyDeviceToHost, s));
+    }
+    LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
+    ctx->stats.d2h_bytes += (uint64_t)n_pass * 5 + ((uint64_t)n_pass + 1) * 8 + n_ma * 25;
+    count_status(status, in->n_reads, n_pass, counts);
     *n_reads_out = n_pass;
+    return LCTP_OK;
+}
+
+// Same, leaving the pairing input on the device (lctp_mates_h); only the status, the read numbers and the counts
+// cross to the host.
+int group_reads_dev(lctp_ctx *ctx, const lctp_prelim *in, uint8_t *status, uint64_t *n_reads_out, uint32_t *out_read,
+                    uint64_t *counts, lctp_mates_h *out) {
+    cudaStream_t s = ctx->stream;
+    out->ctx = ctx; out->n_reads = 0; out->n = 0;
+    if (group_trivial(in, status, n_reads_out, counts)) return LCTP_OK;
+    GroupDev g;
+    int rc = group_reads_run(ctx, in, status, g);
+    if (rc) return rc;
+    if (g.n_pass && out_read) {
+        LCTP_CUDA_CHECK(cudaMemcpyAsync(out_read, g.oread.p, (size_t)g.n_pass * 4, cudaMemcpyDeviceToHost, s));
+        LCTP_CUDA_CHECK(cudaStreamSynchronize(s));
+        ctx->stats.d2h_bytes += (uint64_t)g.n_pass * 4;
+    }
+    out->n_reads = g.n_pass; out->n = g.n_ma;
+    out->ma_off.take(g.maoff); out->contig.take(g.mcon); out->start.take(g.mst); out->end.take(g.men);
+    out->rec.take(g.mrec); out->flags.take(g.mfl); out->max_alns.take(g.omax); out->lnprob.take(g.mlp);
+    count_status(status, in->n_reads, g.n_pass, counts);
+    *n_reads_out = g.n_pass;
     return LCTP_OK;
 }
 
@@ -220,3 +275,40 @@ extern "C" int lctp_group_reads(lctp_ctx *ctx, const lctp_prelim *in, uint64_t c
                              ma_end, ma_ln_prob, ma_rec, counts);
 }
 extern "C" size_t lctp_sizeof_prelim(void) { return sizeof(lctp_prelim); }
+
+extern "C" int lctp_group_reads_dev(lctp_ctx *ctx, const lctp_prelim *in, uint8_t *status, uint64_t *n_reads_out,
+                                    uint32_t *out_read, uint64_t *counts, lctp_mates_h **out) {
+    if (!ctx || !in || !status || !n_reads_out || !counts || !out) { lctp::set_error("lctp_group_reads_dev: NULL argument"); return LCTP_E_INVALID; }
+    *out = nullptr;
+    LCTP_CUDA_CHECK(cudaSetDevice(ctx->device));
+    lctp::set_alloc_stream(ctx->stream);
+    lctp_mates_h *m = new lctp_mates_h();
+    const int rc = lctp::group_reads_dev(ctx, in, status, n_reads_out, out_read, counts, m);
+    if (rc) { delete m; return rc; }
+    *out = m;
+    return LCTP_OK;
+}
+extern "C" uint64_t lctp_mates_count(const lctp_mates_h *m) { return m ? m->n : 0; }
+extern "C" void lctp_mates_free(lctp_mates_h *m) {
+    if (!m) return;
+    if (m->ctx) cudaSetDevice(m->ctx->device);
+    delete m;
+}
+extern "C" int lctp_pair_alignments_from(lctp_ctx *ctx, const lctp_mates_h *mates, const lctp_mates *params,
+                                         lctp_pairs_h **out, uint64_t *n_out) {
+    if (!ctx || !mates || !params || !out) { lctp::set_error("lctp_pair_alignments_from: NULL argument"); return LCTP_E_INVALID; }
+    *out = nullptr;
+    if (mates->ctx != ctx) { lctp::set_error("lctp_pair_alignments_from: the mates belong to another context"); return LCTP_E_INVALID; }
+    if (!params->single_end && (!params->ins_ln_pmf || params->ins_len == 0)) {
+        lctp::set_error("lctp_pair_alignments_from: NULL insert-size table");
+        return LCTP_E_INVALID;
+    }
+    LCTP_CUDA_CHECK(cudaSetDevice(ctx->device));
+    lctp::set_alloc_stream(ctx->stream);
+    lctp_pairs_h *p = new lctp_pairs_h();
+    const int rc = lctp::pair_alignments_dev(ctx, params, p, mates);
+    if (rc) { delete p; return rc; }
+    if (n_out) *n_out = p->n_pairs;
+    *out = p;
+    return LCTP_OK;
+}

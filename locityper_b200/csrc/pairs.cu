@@ -271,11 +271,13 @@ static int to_dev(DevBuf<T> &dst, const T *src, size_t n, cudaStream_t s) {
     return LCTP_OK;
 }
 
-int pair_alignments_dev(lctp_ctx *ctx, const lctp_mates *in, lctp_pairs_h *P) {
+// src != nullptr: the mate arrays are already on the device (lctp_group_reads_dev); `in` then only carries the
+// parameters, the insert-size table, the explicit weights and the weights of the src->n_reads reads.
+int pair_alignments_dev(lctp_ctx *ctx, const lctp_mates *in, lctp_pairs_h *P, const lctp_mates_h *src) {
     cudaStream_t s = ctx->stream;
-    const uint32_t R = in->n_reads;
-    if (R == 0 || !in->ma_off) { set_error("lctp_pair_alignments: no reads"); return LCTP_E_INVALID; }
-    if (in->read_max_alns)
+    const uint32_t R = src ? src->n_reads : in->n_reads;
+    if (R == 0 || (!src && !in->ma_off)) { set_error("lctp_pair_alignments: no reads"); return LCTP_E_INVALID; }
+    if (!src && in->read_max_alns)
         for (uint32_t r = 0; r < in->n_reads; r++)
             if (in->read_max_alns[r] == 0 || in->read_max_alns[r] > PAIR_MAX_ALNS) {
                 set_error("lctp_pair_alignments: read_max_alns[%u] = %u unsupported (1..=%d)", r, in->read_max_alns[r], PAIR_MAX_ALNS);
@@ -290,7 +292,7 @@ int pair_alignments_dev(lctp_ctx *ctx, const lctp_mates *in, lctp_pairs_h *P) {
         return LCTP_E_INVALID;
     }
     if (!in->single_end && !in->ins_ln_pmf) { set_error("lctp_pair_alignments: NULL insert-size table"); return LCTP_E_INVALID; }
-    const uint64_t N = in->ma_off[R];
+    const uint64_t N = src ? src->n : in->ma_off[R];
     DevBuf<uint64_t> d_off, d_offs, d_exp_off;
     DevBuf<uint32_t> d_contig, d_start, d_end, d_counts, d_head, d_gidx, d_gstart;
     DevBuf<uint8_t> d_flags, d_rmax;
@@ -300,15 +302,17 @@ int pair_alignments_dev(lctp_ctx *ctx, const lctp_mates *in, lctp_pairs_h *P) {
     int rc;
     if (N >= 0xFFFFFFFFull) { set_error("lctp_pair_alignments: %llu mate records (limit 2^32 - 2)", (unsigned long long)N); return LCTP_E_CAPACITY; }
     uint64_t h2d = 0;
-    if ((rc = to_dev(d_off, in->ma_off, (size_t)R + 1, s))) return rc;
-    if ((rc = to_dev(d_contig, in->ma_contig, N, s))) return rc;
-    if ((rc = to_dev(d_start, in->ma_start, N, s))) return rc;
-    if ((rc = to_dev(d_end, in->ma_end, N, s))) return rc;
-    if ((rc = to_dev(d_flags, in->ma_flags, N, s))) return rc;
-    if ((rc = to_dev(d_lp, in->ma_ln_prob, N, s))) return rc;
-    h2d += ((size_t)R + 1) * 8 + N * (4 + 4 + 4 + 1 + 8);
+    if (!src) {
+        if ((rc = to_dev(d_off, in->ma_off, (size_t)R + 1, s))) return rc;
+        if ((rc = to_dev(d_contig, in->ma_contig, N, s))) return rc;
+        if ((rc = to_dev(d_start, in->ma_start, N, s))) return rc;
+        if ((rc = to_dev(d_end, in->ma_end, N, s))) return rc;
+        if ((rc = to_dev(d_flags, in->ma_flags, N, s))) return rc;
+        if ((rc = to_dev(d_lp, in->ma_ln_prob, N, s))) return rc;
+        h2d += ((size_t)R + 1) * 8 + N * (4 + 4 + 4 + 1 + 8);
+        if (in->read_max_alns) { if ((rc = to_dev(d_rmax, in->read_max_alns, R, s))) return rc; h2d += (uint64_t)R; }
+    }
     if (in->read_weight) { if ((rc = to_dev(d_w, in->read_weight, R, s))) return rc; h2d += (uint64_t)R * 8; }
-    if (in->read_max_alns) { if ((rc = to_dev(d_rmax, in->read_max_alns, R, s))) return rc; h2d += (uint64_t)R; }
     if (!in->single_end) { if ((rc = to_dev(d_ins, in->ins_ln_pmf, in->ins_len, s))) return rc; h2d += (uint64_t)in->ins_len * 8; }
     if (in->exp_weight) {
         const uint64_t tot = in->exp_off[in->n_haps];
@@ -335,6 +339,10 @@ int pair_alignments_dev(lctp_ctx *ctx, const lctp_mates *in, lctp_pairs_h *P) {
     D.ma_flags = d_flags.p; D.ma_ln_prob = d_lp.p; D.read_weight = in->read_weight ? d_w.p : nullptr;
     D.ins_ln_pmf = d_ins.p;
     D.read_max = in->read_max_alns ? d_rmax.p : nullptr;
+    if (src) {
+        D.ma_off = src->ma_off.p; D.ma_contig = src->contig.p; D.ma_start = src->start.p; D.ma_end = src->end.p;
+        D.ma_flags = src->flags.p; D.ma_ln_prob = src->lnprob.p; D.read_max = src->max_alns.p;
+    }
     D.exp_off = in->exp_weight ? d_exp_off.p : nullptr; D.exp_weight = in->exp_weight ? d_exp.p : nullptr;
     D.unmapped_penalty = in->unmapped_penalty; D.insert_penalty = in->insert_penalty; D.prob_diff = in->prob_diff;
 

@@ -174,6 +174,10 @@ SYMBOLS = {
     "lctp_sizeof_read_ends": (C.c_size_t, []),
     "lctp_collect_read_ends": (C.c_int, [_P] * 12),
     "lctp_sizeof_prelim": (C.c_size_t, []),
+    "lctp_group_reads_dev": (C.c_int, [_P] * 7),
+    "lctp_mates_count": (C.c_uint64, [_P]),
+    "lctp_mates_free": (None, [_P]),
+    "lctp_pair_alignments_from": (C.c_int, [_P] * 5),
     "lctp_unique_kmers_build": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P, C.c_uint32, C.c_uint16, C.c_uint16, _P, _P]),
     "lctp_unique_kmers_count": (C.c_uint64, [_P]),
     "lctp_unique_kmers_free": (None, [_P]),

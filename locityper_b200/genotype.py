@@ -652,6 +652,43 @@ def group_reads(ctx: "Context", pre: Prelim) -> dict:
     return pre.trim_outputs(out, int(n_out.value))
 
 
+class DeviceMates:
+    """lctp_mates_h: the pairing input of a locus, resident on the device (lctp_group_reads_dev).  `pair(params)` runs the
+    pairing on it (lctp_pair_alignments_from) and returns DevicePairs-like access to the result."""
+
+    def __init__(self, ctx: "Context", pre: Prelim):
+        self.ctx, self.lib = ctx, ctx.lib
+        keep: list = []
+        c = pre.to_c(keep)
+        R = pre.n_reads
+        self.status = np.zeros(max(1, R), dtype=np.uint8)
+        out_read = np.zeros(max(1, R), dtype=np.uint32)
+        self.counts = np.zeros(3, dtype=np.uint64)
+        n_out = C.c_uint64(0)
+        self._h = C.c_void_p()
+        ffi.check(self.lib.lctp_group_reads_dev(ctx._h, C.byref(c), self.status.ctypes.data, C.byref(n_out),
+                                                out_read.ctypes.data, self.counts.ctypes.data, C.byref(self._h)))
+        self.n_reads_out = int(n_out.value)
+        self.status, self.out_read = self.status[:R], out_read[:self.n_reads_out].copy()
+        self.n_entries = int(self.lib.lctp_mates_count(self._h))
+
+    def pair(self, params: Mates) -> "DevicePairs":
+        keep: list = []
+        m = params.to_c(keep)
+        dp = DevicePairs.__new__(DevicePairs)
+        dp.ctx, dp.lib, dp.n_reads = self.ctx, self.lib, self.n_reads_out
+        dp._h = C.c_void_p()
+        n = C.c_uint64(0)
+        ffi.check(self.lib.lctp_pair_alignments_from(self.ctx._h, self._h, C.byref(m), C.byref(dp._h), C.byref(n)))
+        dp.n_pairs = int(n.value)
+        return dp
+
+    def free(self):
+        if self._h:
+            self.lib.lctp_mates_free(self._h)
+            self._h = C.c_void_p()
+
+
 def _seq_arrays(seqs):
     off = np.zeros(len(seqs) + 1, dtype=np.uint64)
     off[1:] = np.cumsum([len(s) for s in seqs])

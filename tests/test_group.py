@@ -265,3 +265,39 @@ def test_gpu_chain_records_to_pairs(gpu_ctx, oracle):
     for k in want[2]:
         assert np.array_equal(got[2][k], want[2][k]), k
     assert len(want[2]["pa_contig"]) > 100
+
+
+@pytest.mark.gpu
+def test_gpu_chain_device_resident(gpu_ctx, oracle):
+    """Same chain with the pairing input left on the device (lctp_group_reads_dev -> lctp_pair_alignments_from): the
+    pair alignments equal the oracle chain's, and only status / read numbers / counts came back from the grouping."""
+    import functools
+    captured = {}
+
+    def group_dev(pre):
+        dm = genotype.DeviceMates(gpu_ctx, pre)
+        captured["dm"], captured["pre"] = dm, pre
+        # the host-array variant gives the arrays the rest of _chain wants to look at (weights of the passing reads)
+        return genotype.group_reads(gpu_ctx, pre)
+
+    def pair_dev(mates):
+        dm = captured["dm"]
+        params = genotype.Mates(**{**mates.__dict__, "n_reads": 0, "ma_off": np.zeros(1, dtype=np.uint64),
+                                   "ma_contig": np.zeros(0, dtype=np.uint32), "ma_flags": np.zeros(0, dtype=np.uint8),
+                                   "ma_start": np.zeros(0, dtype=np.uint32), "ma_end": np.zeros(0, dtype=np.uint32),
+                                   "ma_ln_prob": np.zeros(0), "read_max_alns": None,
+                                   "read_weight": captured["pre"].read_weight[dm.out_read]})
+        dp = dm.pair(params)
+        out = dp.fetch()
+        dp.free()
+        return out
+
+    got = _chain(functools.partial(genotype.collect_read_ends, gpu_ctx), group_dev, pair_dev)
+    want = _chain(oracle.collect_read_ends, oracle.group_reads, oracle.pair_alignments)
+    dm = captured["dm"]
+    assert dm.n_reads_out == want[1]["n_reads_out"] and dm.n_entries == len(want[1]["ma_contig"])
+    assert np.array_equal(dm.status, want[1]["status"]) and np.array_equal(dm.out_read, want[1]["out_read"])
+    assert np.array_equal(dm.counts, want[1]["counts"])
+    for k in want[2]:
+        assert np.array_equal(got[2][k], want[2][k]), k
+    dm.free()
