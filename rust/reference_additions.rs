@@ -56,3 +56,33 @@ if let Ok(dir) = std::env::var("LCTP_DUMP_LCTI") {
     let bytes: Vec<u8> = state.iter().flat_map(|w| w.to_le_bytes()).collect();
     std::fs::write(std::path::Path::new(&dir).join(locus.set.tag()).join("rng_state.u64"), bytes).unwrap();
 }
+
+// (7) src/model/locs.rs, `AllAlignments::load` (:1085-1186) with the upstream chain of liblctp.  The BAM
+// reader, the name hash and the debug writers stay as they are; the loop body only COLLECTS what it used to compute:
+//
+//   while reader.has_more() {                                   // :1115
+//       // per read end: push the raw records (cigar as the BAM u32 operations, tid -> contig id, interval, strand) and
+//       // the per-group inputs of read_next_alns (:502-567): record.seq().len(), edit_dist_cache.get(len),
+//       // contig_infos.neighb_complexity(&primary); remember group indices of the read: read_group[r] = [g1, g2] (-1 = none)
+//       // and MateData (sequence, name) for both mates
+//   }
+//   let ends  = lctp_collect_read_ends(ctx, &read_ends)?;        // ok / best_edit / thr_dist / weight_factor / kept_rec / ln_prob
+//   let uk    = lctp_unique_kmers_build(ctx, contig_set.seqs(), kmer_counts, k, hard, soft)?;   // UniqueKmers::new, :930-963
+//   let wts   = lctp_read_weights(ctx, uk, mate_sequences, 2)?;  // calculate_read_weight, :968-1002 (+ the read_kmers debug rows)
+//   // read_data.weight = product of the weight factors of its ends (:564) * wts.weight[r]
+//   let (mates, status, out_read, counts) = lctp_group_reads_dev(ctx, &prelim)?;   // :1119-1137 + :1237-1288 without the transfer
+//   counts.poorly_mapped / out_of_bounds / good_reads + few_kmers come from `counts` and `weight >= min_weight`
+//   let pairs = lctp_pair_alignments_from(ctx, mates, &pairing_params)?;            // identify_*_alignments, :805-911
+//   let locus = lctp_locus_upload_pairs(ctx, &flat_locus_without_pairs, pairs)?;    // solve::Data for the solvers, no host copy
+//   // only when BAM output or debug tables are requested: lctp_pairs_fetch(pairs) -> GrouppedAlignments::aln_pairs
+//
+// Accessors this needs, none of which changes behaviour:
+//   src/model/locs.rs  : `pub(crate)` on PrelimAlignments::{alns, best_edit, good_dist} (:266-274) is not needed any more --
+//                        the protocol runs in the library; ReadData / MateData stay host structs (:569-598);
+//   src/seq/counts.rs  : KmerCounts::k() and iter() are already public (:used by UniqueKmers::new);
+//   src/bg/err_prof.rs : ErrorProfile::{match_prob, mismatch_prob, insert_prob, deletion_prob, clipping_prob} are public (:282-304)
+//                        = lctp_alns::ln_* ; EditDistCache::get is public (:436-450);
+//   src/bg/insertsz.rs : InsertDistr::ln_prob(size) for 0..=max contig length -> lctp_mates::ins_ln_pmf, insert_penalty() (:153-173).
+// With `opt_hap_alns = Some(..)` (pairwise haplotype alignments in the database) the reference additionally transfers
+// alignments between haplotypes (HapAlns::transfer_alignments, src/seq/transfer.rs:70-141, WFA2): that step is not in the
+// library; a host that wants it runs it between lctp_collect_read_ends and lctp_group_reads on the fetched arrays.
