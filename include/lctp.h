@@ -334,7 +334,10 @@ typedef struct lctp_prelim {
  * the read, out_max_alns[k] = its max_alns (lctp_mates::read_max_alns), ma_off[k] .. ma_off[k+1] = its entries of
  * ma_contig / ma_flags / ma_start / ma_end / ma_ln_prob (the lctp_mates arrays of the same names; `cap` entries each)
  * and ma_rec (the record each entry came from).  counts[3] = poorly mapped (status 1 and 3), out of bounds, passed.
- * LCTP_E_CAPACITY when cap is too small (the number of kept records always suffices). */
+ * LCTP_E_CAPACITY when cap is too small (the number of kept records always suffices).  Preconditions (the outputs of
+ * lctp_collect_read_ends satisfy them): grp_n_kept[g] <= grp_off[g+1] - grp_off[g], the first grp_n_kept[g] entries of
+ * kept_rec at grp_off[g] are record indices < n_alns, rec_contig < n_haps; read_group entries are -1 or < n_groups
+ * (checked: LCTP_E_INVALID). */
 int  lctp_group_reads(lctp_ctx *ctx, const lctp_prelim *in, uint64_t cap, uint8_t *status, uint64_t *n_reads_out,
                       uint32_t *out_read, uint8_t *out_max_alns, uint64_t *ma_off, uint32_t *ma_contig,
                       uint8_t *ma_flags, uint32_t *ma_start, uint32_t *ma_end, double *ma_ln_prob, uint32_t *ma_rec,
