@@ -301,3 +301,37 @@ def test_gpu_chain_device_resident(gpu_ctx, oracle):
     for k in want[2]:
         assert np.array_equal(got[2][k], want[2][k]), k
     dm.free()
+
+
+def _check_properties(p: genotype.Prelim, g: dict):
+    """Size-independent properties of the grouping output: every kept record of a passing read appears exactly once, the
+    entries of a read are in consumption order, normalised ln-probabilities are <= 0, max_alns follows the weight."""
+    assert int(g["counts"].sum()) == p.n_reads and int(g["counts"][2]) == g["n_reads_out"]
+    assert np.all(g["ma_ln_prob"] <= 0.0)
+    assert np.array_equal(g["out_max_alns"], np.where(p.read_weight[g["out_read"]] >= p.min_weight, 10, 2))
+    assert np.array_equal(np.nonzero(g["status"] == 0)[0], g["out_read"])
+    for k, r in enumerate(g["out_read"]):
+        b, e = int(g["ma_off"][k]), int(g["ma_off"][k + 1])
+        want = []
+        for end in range(1 if p.single_end else 2):
+            gi = int(p.read_group[r, end])
+            o = int(p.grp_off[gi])
+            want += [int(x) for x in p.kept_rec[o:o + int(p.grp_n_kept[gi])]]
+        assert sorted(int(x) for x in g["ma_rec"][b:e]) == sorted(want)
+        key = [(int(g["ma_contig"][q]), int(g["ma_flags"][q]) & 1, -float(g["ma_ln_prob"][q])) for q in range(b, e)]
+        assert key == sorted(key)
+        assert np.array_equal(g["ma_contig"][b:e], p.rec_contig[g["ma_rec"][b:e]])
+        assert np.array_equal(g["ma_start"][b:e], p.rec_start[g["ma_rec"][b:e]])
+
+
+@pytest.mark.parametrize("seed,single_end", [(41, False), (42, True)])
+def test_oracle_output_properties(oracle, seed, single_end):
+    p = _random_prelim(seed, n_reads=400, single_end=single_end)
+    _check_properties(p, oracle.group_reads(p))
+
+
+@pytest.mark.gpu
+def test_gpu_output_properties_large(gpu_ctx):
+    """No oracle: 20,000 reads (~170,000 records), properties only."""
+    p = _random_prelim(43, n_reads=20000)
+    _check_properties(p, genotype.group_reads(gpu_ctx, p))
